@@ -1,0 +1,185 @@
+/*
+ * kb_b200.h -- C ABI of libkbb200.so: the B200-native MVCC range-scan / compaction-sweep /
+ * watch fan-out engine that drops in behind KubeBrain's Go plugin surfaces.
+ *
+ * The reference (kubewharf/kubebrain) is 100 % Go and has NO native boundary today; the entry points
+ * below are what a cgo shim for this path binds (INTEGRATION.md shows the binding).  Each symbol cites
+ * the reference interface (file:line in the reference tree) whose hot loop it replaces.
+ *
+ * Conventions: every function returns 0 (KB_OK) or a negative kb_status; no exception crosses the
+ * boundary; all pointers are plain host pointers unless a field says "device"; inputs are caller-owned
+ * and may be released when the call returns; results are library-owned handles (kb_result) that stay
+ * valid until kb_result_free (this is what lets the Go side keep slices alive after Iter.Close, as
+ * worker.run requires -- pkg/backend/scanner/scanner.go:493-495).  A kb_ctx serialises its own calls
+ * (one CUDA stream); use one ctx per goroutine-pool shard or guard it with a mutex.
+ * There is NO CPU fallback: without a CUDA device kb_open fails with KB_ECUDA.
+ */
+#ifndef KB_B200_H
+#define KB_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KB_ABI_VERSION 1
+
+typedef enum kb_status {
+    KB_OK = 0,
+    KB_EINVAL = -1,      /* bad argument                                                         */
+    KB_ECUDA = -2,       /* CUDA runtime / driver failure (kb_last_error has the text)            */
+    KB_ENOMEM = -3,
+    KB_EUNSORTED = -4,   /* kb_load_sorted: keys not strictly ascending (storage.Iter contract)   */
+    KB_ECOMPACTED = -5,  /* range revision below the compact revision (scanner.go:618-624)        */
+    KB_ESTATE = -6,      /* call out of order (no store loaded, NCCL not initialised, ...)         */
+    KB_ENCCL = -7,
+    KB_ELIMIT = -8       /* input exceeds a documented format limit (key > 65535 B, n >= 2^32-1)   */
+} kb_status;
+
+typedef struct kb_ctx kb_ctx;
+typedef struct kb_result kb_result;
+typedef struct kb_events_dev kb_events_dev;
+
+typedef struct kb_config {
+    uint32_t struct_size;   /* sizeof(kb_config), for forward compatibility */
+    uint32_t flags;         /* reserved, 0 */
+} kb_config;
+
+/* ---- lifecycle ------------------------------------------------------------------------------ */
+int kb_abi_version(void);
+int kb_open(int device_ordinal, const kb_config *cfg, kb_ctx **out);
+void kb_close(kb_ctx *ctx);
+const char *kb_last_error(kb_ctx *ctx);
+/* the cudaStream_t every kernel of this ctx is launched on (so callers can record events on it) */
+void *kb_stream(kb_ctx *ctx);
+int kb_sync(kb_ctx *ctx);
+
+/* ---- store: replaces storage.Iter over badger (pkg/storage/badger/iter.go:27-98) --------------
+ * Bulk-loads a snapshot of the engine: n unique internal keys in ascending bytes.Compare order with
+ * their values, packed back to back (record i = keys[key_off[i]..key_off[i+1])).  The snapshot becomes
+ * an HBM-resident slab (16-byte aligned records) that every scan below reads.  */
+int kb_load_sorted(kb_ctx *ctx, const uint8_t *keys, const uint64_t *key_off, const uint8_t *vals,
+                   const uint64_t *val_off, uint64_t n);
+int kb_store_info(kb_ctx *ctx, uint64_t *n_records, uint64_t *key_bytes, uint64_t *val_bytes);
+/* compact_key record used by checkCompactRace (scanner.go:594-626); present=0 clears it */
+int kb_set_compact_revision(kb_ctx *ctx, int present, uint64_t rev);
+
+/* ---- range scan: replaces scanner.Range / Count / RangeStream -> worker.run -------------------
+ * (pkg/backend/scanner/scanner.go:83-145, 389-516; receivers scanner/receiver.go:62-103) */
+enum {
+    KB_OUT_HOST = 0,    /* results copied to pinned host memory inside the call                    */
+    KB_OUT_DEVICE = 1,  /* results stay in HBM; the view holds device pointers                      */
+    KB_OUT_COUNT = 2    /* emptyResultReceiver: counts only (scanner.Count)                         */
+};
+
+typedef struct kb_range_req {
+    const uint8_t *start;  uint64_t start_len;   /* internal keys: coder.EncodeObjectKey(key, 0)  */
+    const uint8_t *end;    uint64_t end_len;     /* half-open [start, end)                        */
+    uint64_t read_rev;                            /* workerConfig.revision                         */
+    int64_t  limit;                               /* scanner.Range limit; <= 0 means unlimited     */
+} kb_range_req;
+
+typedef struct kb_range_view {
+    uint64_t n_req;
+    const uint64_t *req_first;  /* n_req+1: kvs of request q are [req_first[q], req_first[q+1])   */
+    const uint64_t *req_count;  /* n_req: worker.run's object count (for scanner.Count)            */
+    const uint64_t *req_examined; /* n_req: records pulled from the iterator                      */
+    uint64_t n_kvs;
+    /* per emitted kv, in the reference's emission order */
+    const uint32_t *rec_idx;    /* index of the store record that supplied key/value/revision     */
+    const uint64_t *rev;        /* KeyValue.Revision                                              */
+    const uint64_t *key_off;    /* offset of the USER key inside bytes                            */
+    const uint32_t *key_len;
+    const uint64_t *val_off;
+    const uint32_t *val_len;
+    const uint8_t  *bytes;      /* arena (host pinned for KB_OUT_HOST, device for KB_OUT_DEVICE)   */
+    uint64_t n_bytes;
+    int on_device;              /* 1: bytes is a device pointer (metadata arrays are always host)  */
+} kb_range_view;
+
+/* One call = one batch of independent scanner.Range requests answered on one snapshot. */
+int kb_range_batch(kb_ctx *ctx, const kb_range_req *reqs, uint64_t n_req, int out_mode, kb_result **out);
+int kb_range_view_get(const kb_result *res, kb_range_view *view);
+
+/* ---- compaction sweep: replaces scanner.Compact -> worker.run(compact=true) --------------------
+ * (scanner.go:195-199, 457-491, 538-591; driver pkg/backend/compact.go:31-127).
+ * Classifies every record of [start,end) visible at `rev`; the deletes themselves are applied by the
+ * caller in bulk (the reference issues one storage transaction per victim, scanner.go:538-564). */
+enum {
+    KB_V_SUPERSEDED = 1,  /* scanner.go:465-469 store.Del of an older version                     */
+    KB_V_TOMBSTONE  = 2,  /* scanner.go:472-475 store.Del of a tombstone-valued version            */
+    KB_V_REVRECORD  = 3,  /* scanner.go:477-491 store.DelCurrent of a deleted-flag revision record */
+    KB_V_TTL_REVREC = 4,  /* scanner.go:576-581 (only when !SupportTTL and timeout_rev != 0)       */
+    KB_V_TTL_OBJECT = 5   /* scanner.go:582-585                                                    */
+};
+
+typedef struct kb_compact_view {
+    uint64_t n_victims;
+    const uint32_t *victim_idx;    /* store record index of every delete call, in the reference's order */
+    const uint8_t  *victim_class;
+    uint64_t count;                /* worker.run's count (includes the Q5 double count)            */
+    uint64_t examined;
+    int on_device;                 /* 1: victim_idx / victim_class are device pointers              */
+} kb_compact_view;
+
+int kb_compact_sweep(kb_ctx *ctx, const uint8_t *start, uint64_t start_len, const uint8_t *end, uint64_t end_len,
+                     uint64_t rev, uint64_t timeout_rev, int support_ttl, int out_mode, kb_result **out);
+int kb_compact_view_get(const kb_result *res, kb_compact_view *view);
+
+/* ---- watch fan-out: replaces WatcherHub.Stream + processEvents/filterByRevision/filterByPrefix --
+ * (pkg/backend/watcherhub.go:78-92, pkg/backend/watch.go:119-159) */
+int kb_watch_add(kb_ctx *ctx, const uint8_t *prefix, uint64_t prefix_len, uint64_t min_rev, uint32_t *id);
+int kb_watch_del(kb_ctx *ctx, uint32_t id);
+int kb_watch_count(kb_ctx *ctx, uint64_t *n);
+
+typedef struct kb_events {
+    const uint8_t  *keys;  const uint64_t *key_off;   /* Event.Kv.Key (user keys), n+1 offsets     */
+    const uint64_t *rev;                               /* Event.Revision                            */
+    uint64_t n;
+    const uint64_t *batch_off; uint64_t n_batches;    /* collector batches (<=300, backend.go:41);
+                                                          NULL/0 = one batch                        */
+} kb_events;
+
+typedef struct kb_match_view {
+    uint64_t n_watchers;         /* number of registered watcher ids covered (max id + 1)          */
+    const uint64_t *start;       /* n_watchers+1: deliveries of watcher id w = [start[w],start[w+1]) */
+    const uint32_t *event_idx;   /* event indices, ascending per watcher (stream order)             */
+    uint64_t n_deliveries;
+    int on_device;
+} kb_match_view;
+
+int kb_watch_match(kb_ctx *ctx, const kb_events *ev, int out_mode, kb_result **out);
+/* device-resident event slabs (benchmarks / GPU-side producers) */
+int kb_events_upload(kb_ctx *ctx, const kb_events *ev, kb_events_dev **out);
+void kb_events_free(kb_ctx *ctx, kb_events_dev *ev);
+int kb_watch_match_dev(kb_ctx *ctx, const kb_events_dev *ev, int out_mode, kb_result **out);
+int kb_match_view_get(const kb_result *res, kb_match_view *view);
+
+void kb_result_free(kb_ctx *ctx, kb_result *res);
+
+/* ---- multi-GPU: the committed-revision cursor (tso.GetRevision, pkg/backend/tso/tso.go:47-49;
+ * follower /status poll pkg/server/service/revision/revision.go:219-259) as ONE ncclAllGather of one
+ * uint64 per rank; min over ranks = the globally readable revision. */
+#define KB_NCCL_ID_BYTES 128
+int kb_nccl_unique_id(uint8_t id[KB_NCCL_ID_BYTES]);
+int kb_nccl_init(kb_ctx *ctx, const uint8_t id[KB_NCCL_ID_BYTES], int rank, int nranks);
+int kb_cursor_allgather(kb_ctx *ctx, uint64_t local_rev, uint64_t *all_revs /* nranks */, uint64_t *min_rev);
+
+/* ---- measurement hooks (bench.py): per-kernel CUDA-event timing on the ctx stream -------------- */
+typedef struct kb_prof_entry {
+    char     name[32];
+    uint64_t launches;
+    double   total_ms;
+    uint64_t alg_bytes;   /* algorithmic bytes the launches were asked to move */
+} kb_prof_entry;
+int kb_prof_enable(kb_ctx *ctx, int on);
+int kb_prof_reset(kb_ctx *ctx);
+int kb_prof_read(kb_ctx *ctx, kb_prof_entry *entries, int cap, int *n);
+uint64_t kb_launch_count(kb_ctx *ctx); /* kernels launched by this ctx since open */
+
+#ifdef __cplusplus
+}
+#endif
+#endif

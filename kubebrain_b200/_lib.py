@@ -1,0 +1,417 @@
+"""ctypes binding of the C ABI in include/kb_b200.h (libkbb200.so).
+
+There is no CPU fallback anywhere in this package: if the shared library is missing, or no CUDA device
+is present, every entry point raises.  The library is built in-tree by ``__graft_entry__.build()`` /
+``make -C kubebrain_b200/csrc``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from .packed import PackedEvents, PackedStore, PackedWatchers, Slab
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libkbb200.so")
+
+KB_OUT_HOST, KB_OUT_DEVICE, KB_OUT_COUNT = 0, 1, 2
+KB_OK, KB_EINVAL, KB_ECUDA, KB_ENOMEM, KB_EUNSORTED, KB_ECOMPACTED, KB_ESTATE, KB_ENCCL, KB_ELIMIT = (
+    0, -1, -2, -3, -4, -5, -6, -7, -8)
+NCCL_ID_BYTES = 128
+
+u8p = C.POINTER(C.c_uint8)
+u32p = C.POINTER(C.c_uint32)
+u64p = C.POINTER(C.c_uint64)
+
+# every symbol include/kb_b200.h declares (tests/test_abi.py checks the .so exports all of them)
+ABI_SYMBOLS = [
+    "kb_abi_version", "kb_open", "kb_close", "kb_last_error", "kb_stream", "kb_sync",
+    "kb_load_sorted", "kb_store_info", "kb_set_compact_revision",
+    "kb_range_batch", "kb_range_view_get",
+    "kb_compact_sweep", "kb_compact_view_get",
+    "kb_watch_add", "kb_watch_del", "kb_watch_count", "kb_watch_match", "kb_events_upload", "kb_events_free",
+    "kb_watch_match_dev", "kb_match_view_get", "kb_result_free",
+    "kb_nccl_unique_id", "kb_nccl_init", "kb_cursor_allgather",
+    "kb_prof_enable", "kb_prof_reset", "kb_prof_read", "kb_launch_count",
+]
+
+
+class KbError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"kb_b200 error {code}: {msg}")
+        self.code = code
+
+
+class KbRangeReq(C.Structure):
+    _fields_ = [("start", C.c_char_p), ("start_len", C.c_uint64), ("end", C.c_char_p), ("end_len", C.c_uint64),
+                ("read_rev", C.c_uint64), ("limit", C.c_int64)]
+
+
+class KbRangeView(C.Structure):
+    _fields_ = [("n_req", C.c_uint64), ("req_first", u64p), ("req_count", u64p), ("req_examined", u64p),
+                ("n_kvs", C.c_uint64), ("rec_idx", u32p), ("rev", u64p), ("key_off", u64p), ("key_len", u32p),
+                ("val_off", u64p), ("val_len", u32p), ("bytes", C.c_void_p), ("n_bytes", C.c_uint64),
+                ("on_device", C.c_int)]
+
+
+class KbCompactView(C.Structure):
+    _fields_ = [("n_victims", C.c_uint64), ("victim_idx", C.c_void_p), ("victim_class", C.c_void_p),
+                ("count", C.c_uint64), ("examined", C.c_uint64), ("on_device", C.c_int)]
+
+
+class KbEvents(C.Structure):
+    _fields_ = [("keys", u8p), ("key_off", u64p), ("rev", u64p), ("n", C.c_uint64),
+                ("batch_off", u64p), ("n_batches", C.c_uint64)]
+
+
+class KbMatchView(C.Structure):
+    _fields_ = [("n_watchers", C.c_uint64), ("start", u64p), ("event_idx", C.c_void_p),
+                ("n_deliveries", C.c_uint64), ("on_device", C.c_int)]
+
+
+class KbProfEntry(C.Structure):
+    _fields_ = [("name", C.c_char * 32), ("launches", C.c_uint64), ("total_ms", C.c_double),
+                ("alg_bytes", C.c_uint64)]
+
+
+_lib = None
+
+
+def lib():
+    """Load libkbb200.so; fail loudly when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: the CUDA extension has not been built (run __graft_entry__.build() or "
+            "`make -C kubebrain_b200/csrc`). kubebrain_b200 has no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    vp = C.c_void_p
+    L.kb_abi_version.restype = C.c_int
+    L.kb_open.restype = C.c_int
+    L.kb_open.argtypes = [C.c_int, vp, C.POINTER(vp)]
+    L.kb_close.argtypes = [vp]
+    L.kb_close.restype = None
+    L.kb_last_error.restype = C.c_char_p
+    L.kb_last_error.argtypes = [vp]
+    L.kb_stream.restype = vp
+    L.kb_stream.argtypes = [vp]
+    L.kb_sync.restype = C.c_int
+    L.kb_sync.argtypes = [vp]
+    L.kb_load_sorted.restype = C.c_int
+    L.kb_load_sorted.argtypes = [vp, u8p, u64p, u8p, u64p, C.c_uint64]
+    L.kb_store_info.restype = C.c_int
+    L.kb_store_info.argtypes = [vp, u64p, u64p, u64p]
+    L.kb_set_compact_revision.restype = C.c_int
+    L.kb_set_compact_revision.argtypes = [vp, C.c_int, C.c_uint64]
+    L.kb_range_batch.restype = C.c_int
+    L.kb_range_batch.argtypes = [vp, C.POINTER(KbRangeReq), C.c_uint64, C.c_int, C.POINTER(vp)]
+    L.kb_range_view_get.restype = C.c_int
+    L.kb_range_view_get.argtypes = [vp, C.POINTER(KbRangeView)]
+    L.kb_compact_sweep.restype = C.c_int
+    L.kb_compact_sweep.argtypes = [vp, C.c_char_p, C.c_uint64, C.c_char_p, C.c_uint64, C.c_uint64, C.c_uint64,
+                                   C.c_int, C.c_int, C.POINTER(vp)]
+    L.kb_compact_view_get.restype = C.c_int
+    L.kb_compact_view_get.argtypes = [vp, C.POINTER(KbCompactView)]
+    L.kb_watch_add.restype = C.c_int
+    L.kb_watch_add.argtypes = [vp, C.c_char_p, C.c_uint64, C.c_uint64, u32p]
+    L.kb_watch_del.restype = C.c_int
+    L.kb_watch_del.argtypes = [vp, C.c_uint32]
+    L.kb_watch_count.restype = C.c_int
+    L.kb_watch_count.argtypes = [vp, u64p]
+    L.kb_watch_match.restype = C.c_int
+    L.kb_watch_match.argtypes = [vp, C.POINTER(KbEvents), C.c_int, C.POINTER(vp)]
+    L.kb_events_upload.restype = C.c_int
+    L.kb_events_upload.argtypes = [vp, C.POINTER(KbEvents), C.POINTER(vp)]
+    L.kb_events_free.restype = None
+    L.kb_events_free.argtypes = [vp, vp]
+    L.kb_watch_match_dev.restype = C.c_int
+    L.kb_watch_match_dev.argtypes = [vp, vp, C.c_int, C.POINTER(vp)]
+    L.kb_match_view_get.restype = C.c_int
+    L.kb_match_view_get.argtypes = [vp, C.POINTER(KbMatchView)]
+    L.kb_result_free.restype = None
+    L.kb_result_free.argtypes = [vp, vp]
+    L.kb_nccl_unique_id.restype = C.c_int
+    L.kb_nccl_unique_id.argtypes = [u8p]
+    L.kb_nccl_init.restype = C.c_int
+    L.kb_nccl_init.argtypes = [vp, u8p, C.c_int, C.c_int]
+    L.kb_cursor_allgather.restype = C.c_int
+    L.kb_cursor_allgather.argtypes = [vp, C.c_uint64, u64p, u64p]
+    L.kb_prof_enable.restype = C.c_int
+    L.kb_prof_enable.argtypes = [vp, C.c_int]
+    L.kb_prof_reset.restype = C.c_int
+    L.kb_prof_reset.argtypes = [vp]
+    L.kb_prof_read.restype = C.c_int
+    L.kb_prof_read.argtypes = [vp, C.POINTER(KbProfEntry), C.c_int, C.POINTER(C.c_int)]
+    L.kb_launch_count.restype = C.c_uint64
+    L.kb_launch_count.argtypes = [vp]
+    _lib = L
+    return L
+
+
+def _np(ptr, n: int, dtype) -> np.ndarray:
+    if n == 0 or not ptr:
+        return np.zeros(0, dtype=dtype)
+    addr = ptr if isinstance(ptr, int) else C.cast(ptr, C.c_void_p).value
+    buf = (C.c_uint8 * (n * np.dtype(dtype).itemsize)).from_address(addr)
+    return np.frombuffer(buf, dtype=dtype, count=n)
+
+
+def _slab_ptrs(s: Slab):
+    data = s.data if s.data.size else np.zeros(1, np.uint8)
+    data = np.ascontiguousarray(data)
+    off = np.ascontiguousarray(s.off, dtype=np.uint64)
+    return data, off, data.ctypes.data_as(u8p), off.ctypes.data_as(u64p)
+
+
+class RangeResult:
+    """One batch of scanner.Range answers (copies taken out of the library-owned arena on demand)."""
+
+    def __init__(self, eng: "Engine", handle):
+        self._eng, self._h = eng, handle
+        v = KbRangeView()
+        eng._check(lib().kb_range_view_get(handle, C.byref(v)))
+        self.n_req = int(v.n_req)
+        self.req_first = _np(v.req_first, self.n_req + 1, np.uint64).copy()
+        self.req_count = _np(v.req_count, self.n_req, np.uint64).copy()
+        self.req_examined = _np(v.req_examined, self.n_req, np.uint64).copy()
+        self.n_kvs = int(v.n_kvs)
+        self.n_bytes = int(v.n_bytes)
+        self.on_device = bool(v.on_device)
+        self.bytes_ptr = v.bytes
+        n = self.n_kvs
+        self.rec_idx = _np(v.rec_idx, n, np.uint32)
+        self.rev = _np(v.rev, n, np.uint64)
+        self.key_off = _np(v.key_off, n, np.uint64)
+        self.key_len = _np(v.key_len, n, np.uint32)
+        self.val_off = _np(v.val_off, n, np.uint64)
+        self.val_len = _np(v.val_len, n, np.uint32)
+        self.arena = _np(v.bytes, self.n_bytes, np.uint8) if (not self.on_device and v.bytes) else None
+
+    def kvs(self, q: int = 0) -> List[Tuple[bytes, bytes, int]]:
+        assert self.arena is not None, "results were left on the device"
+        a, b = int(self.req_first[q]), int(self.req_first[q + 1])
+        out = []
+        for k in range(a, b):
+            ko, kl, vo, vl = int(self.key_off[k]), int(self.key_len[k]), int(self.val_off[k]), int(self.val_len[k])
+            out.append((self.arena[ko : ko + kl].tobytes(), self.arena[vo : vo + vl].tobytes(), int(self.rev[k])))
+        return out
+
+    def rec_indices(self, q: int = 0) -> np.ndarray:
+        return self.rec_idx[int(self.req_first[q]) : int(self.req_first[q + 1])].copy()
+
+    def close(self):
+        if self._h:
+            lib().kb_result_free(self._eng._ctx, self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class CompactResult:
+    def __init__(self, eng: "Engine", handle):
+        self._eng, self._h = eng, handle
+        v = KbCompactView()
+        eng._check(lib().kb_compact_view_get(handle, C.byref(v)))
+        self.n_victims = int(v.n_victims)
+        self.count = int(v.count)
+        self.examined = int(v.examined)
+        self.on_device = bool(v.on_device)
+        if not self.on_device and v.victim_idx:
+            self.victim_idx = _np(v.victim_idx, self.n_victims, np.uint32).copy()
+            self.victim_class = _np(v.victim_class, self.n_victims, np.uint8).copy()
+        else:
+            self.victim_idx = np.zeros(0, np.uint32)
+            self.victim_class = np.zeros(0, np.uint8)
+
+    def close(self):
+        if self._h:
+            lib().kb_result_free(self._eng._ctx, self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class MatchResult:
+    def __init__(self, eng: "Engine", handle):
+        self._eng, self._h = eng, handle
+        v = KbMatchView()
+        eng._check(lib().kb_match_view_get(handle, C.byref(v)))
+        self.n_watchers = int(v.n_watchers)
+        self.n_deliveries = int(v.n_deliveries)
+        self.on_device = bool(v.on_device)
+        self.start = _np(v.start, self.n_watchers + 1, np.uint64).copy()
+        self.event_idx = (_np(v.event_idx, self.n_deliveries, np.uint32).copy()
+                          if not self.on_device else np.zeros(0, np.uint32))
+
+    def deliveries(self, watcher_id: int) -> np.ndarray:
+        return self.event_idx[int(self.start[watcher_id]) : int(self.start[watcher_id + 1])]
+
+    def close(self):
+        if self._h:
+            lib().kb_result_free(self._eng._ctx, self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Engine:
+    """A kb_ctx: one HBM-resident snapshot + watcher table on one GPU."""
+
+    def __init__(self, device: int = 0):
+        self._ctx = C.c_void_p()
+        rc = lib().kb_open(device, None, C.byref(self._ctx))
+        if rc != 0:
+            raise KbError(rc, "kb_open failed: no usable CUDA device (kubebrain_b200 has no CPU fallback)")
+        self.device = device
+        self._keep = []
+
+    def _check(self, rc: int):
+        if rc != 0:
+            raise KbError(rc, (lib().kb_last_error(self._ctx) or b"").decode("utf-8", "replace"))
+
+    def close(self):
+        if self._ctx:
+            lib().kb_close(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- store ----
+    def load_sorted(self, store: PackedStore):
+        kd, ko, kp, kop = _slab_ptrs(store.keys)
+        vd, vo, vp, vop = _slab_ptrs(store.vals)
+        self._check(lib().kb_load_sorted(self._ctx, kp, kop, vp, vop, store.n))
+
+    def store_info(self) -> Tuple[int, int, int]:
+        a, b, c = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        self._check(lib().kb_store_info(self._ctx, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
+
+    def set_compact_revision(self, rev: Optional[int]):
+        self._check(lib().kb_set_compact_revision(self._ctx, int(rev is not None), rev or 0))
+
+    # ---- scans ----
+    def range_batch(self, reqs: Sequence[Tuple[bytes, bytes, int, int]], out_mode: int = KB_OUT_HOST) -> RangeResult:
+        """reqs: (start_internal_key, end_internal_key, read_rev, limit)"""
+        arr = (KbRangeReq * max(len(reqs), 1))()
+        for i, (s, e, rev, lim) in enumerate(reqs):
+            arr[i] = KbRangeReq(s, len(s), e, len(e), rev, lim)
+        h = C.c_void_p()
+        self._check(lib().kb_range_batch(self._ctx, arr, len(reqs), out_mode, C.byref(h)))
+        return RangeResult(self, h)
+
+    def compact_sweep(self, start: bytes, end: bytes, rev: int, timeout_rev: int = 0, support_ttl: bool = True,
+                      out_mode: int = KB_OUT_HOST) -> CompactResult:
+        h = C.c_void_p()
+        self._check(lib().kb_compact_sweep(self._ctx, start, len(start), end, len(end), rev, timeout_rev,
+                                           int(support_ttl), out_mode, C.byref(h)))
+        return CompactResult(self, h)
+
+    # ---- watch ----
+    def watch_add(self, prefix: bytes, min_rev: int) -> int:
+        wid = C.c_uint32()
+        self._check(lib().kb_watch_add(self._ctx, prefix, len(prefix), min_rev, C.byref(wid)))
+        return wid.value
+
+    def watch_add_many(self, w: PackedWatchers) -> List[int]:
+        return [self.watch_add(w.prefixes[i], int(w.min_rev[i])) for i in range(w.n)]
+
+    def watch_del(self, wid: int):
+        self._check(lib().kb_watch_del(self._ctx, wid))
+
+    def watch_count(self) -> int:
+        n = C.c_uint64()
+        self._check(lib().kb_watch_count(self._ctx, C.byref(n)))
+        return n.value
+
+    @staticmethod
+    def _events_c(ev: PackedEvents):
+        kd, ko, kp, kop = _slab_ptrs(ev.keys)
+        rev = np.ascontiguousarray(ev.rev, dtype=np.uint64)
+        bo = np.ascontiguousarray(ev.batch_off, dtype=np.uint64)
+        c = KbEvents(kp, kop, rev.ctypes.data_as(u64p), ev.n, bo.ctypes.data_as(u64p), len(bo) - 1)
+        return c, (kd, ko, rev, bo)
+
+    def watch_match(self, ev: PackedEvents, out_mode: int = KB_OUT_HOST) -> MatchResult:
+        c, keep = self._events_c(ev)
+        h = C.c_void_p()
+        self._check(lib().kb_watch_match(self._ctx, C.byref(c), out_mode, C.byref(h)))
+        return MatchResult(self, h)
+
+    def events_upload(self, ev: PackedEvents):
+        c, keep = self._events_c(ev)
+        h = C.c_void_p()
+        self._check(lib().kb_events_upload(self._ctx, C.byref(c), C.byref(h)))
+        return h
+
+    def events_free(self, h):
+        lib().kb_events_free(self._ctx, h)
+
+    def watch_match_dev(self, ev_handle, out_mode: int = KB_OUT_DEVICE) -> MatchResult:
+        h = C.c_void_p()
+        self._check(lib().kb_watch_match_dev(self._ctx, ev_handle, out_mode, C.byref(h)))
+        return MatchResult(self, h)
+
+    # ---- multi-GPU cursor ----
+    @staticmethod
+    def nccl_unique_id() -> bytes:
+        buf = (C.c_uint8 * NCCL_ID_BYTES)()
+        rc = lib().kb_nccl_unique_id(buf)
+        if rc != 0:
+            raise KbError(rc, "ncclGetUniqueId failed (libnccl.so.2 not loadable?)")
+        return bytes(buf)
+
+    def nccl_init(self, uid: bytes, rank: int, nranks: int):
+        buf = (C.c_uint8 * NCCL_ID_BYTES).from_buffer_copy(uid)
+        self._check(lib().kb_nccl_init(self._ctx, buf, rank, nranks))
+        self._nranks = nranks
+
+    def cursor_allgather(self, local_rev: int) -> Tuple[np.ndarray, int]:
+        out = np.zeros(self._nranks, np.uint64)
+        mn = C.c_uint64()
+        self._check(lib().kb_cursor_allgather(self._ctx, local_rev, out.ctypes.data_as(u64p), C.byref(mn)))
+        return out, mn.value
+
+    # ---- measurement ----
+    def stream(self) -> int:
+        return lib().kb_stream(self._ctx) or 0
+
+    def sync(self):
+        self._check(lib().kb_sync(self._ctx))
+
+    def prof_enable(self, on: bool):
+        self._check(lib().kb_prof_enable(self._ctx, int(on)))
+
+    def prof_reset(self):
+        self._check(lib().kb_prof_reset(self._ctx))
+
+    def prof_read(self):
+        arr = (KbProfEntry * 64)()
+        n = C.c_int()
+        self._check(lib().kb_prof_read(self._ctx, arr, 64, C.byref(n)))
+        return [dict(name=arr[i].name.decode(), launches=int(arr[i].launches), total_ms=float(arr[i].total_ms),
+                     alg_bytes=int(arr[i].alg_bytes)) for i in range(min(n.value, 64))]
+
+    def launch_count(self) -> int:
+        return int(lib().kb_launch_count(self._ctx))

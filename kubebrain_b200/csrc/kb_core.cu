@@ -1,0 +1,555 @@
+// kb_core.cu -- context lifecycle, buffer pools, profiling hooks, store ingest (kb_load_sorted) and the
+// NCCL revision-cursor exchange of libkbb200.so.
+#include <dlfcn.h>
+#include <stdarg.h>
+
+#include <algorithm>
+
+#include "kb_internal.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// errors / buffers
+// ------------------------------------------------------------------------------------------------
+int kb_fail(kb_ctx *ctx, int code, const char *fmt, ...)
+{
+    if (ctx) {
+        char buf[512];
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(buf, sizeof(buf), fmt, ap);
+        va_end(ap);
+        ctx->err = buf;
+    }
+    return code;
+}
+
+int kb_cuda_fail(kb_ctx *ctx, cudaError_t e, const char *what)
+{
+    return kb_fail(ctx, e == cudaErrorMemoryAllocation ? KB_ENOMEM : KB_ECUDA, "CUDA error %d (%s) at %s", (int)e,
+                   cudaGetErrorString(e), what);
+}
+
+int dbuf_ensure(kb_ctx *ctx, DBuf &b, size_t bytes)
+{
+    if (bytes <= b.cap && b.p) return KB_OK;
+    size_t want = std::max(bytes + bytes / 4, (size_t)4096);
+    want = (want + 255) & ~(size_t)255;
+    if (b.p) {
+        KB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        cudaFree(b.p);
+        b.p = nullptr;
+        b.cap = 0;
+    }
+    KB_CUDA(ctx, cudaMalloc(&b.p, want));
+    b.cap = want;
+    return KB_OK;
+}
+
+int hbuf_ensure(kb_ctx *ctx, HBuf &b, size_t bytes)
+{
+    if (bytes <= b.cap && b.p) return KB_OK;
+    size_t want = std::max(bytes + bytes / 4, (size_t)4096);
+    if (b.p) {
+        KB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        cudaFreeHost(b.p);
+        b.p = nullptr;
+        b.cap = 0;
+    }
+    KB_CUDA(ctx, cudaHostAlloc(&b.p, want, cudaHostAllocDefault));
+    b.cap = want;
+    return KB_OK;
+}
+
+template <typename B>
+static bool pool_take(std::vector<B> &pool, size_t bytes, B *out)
+{
+    int best = -1;
+    for (int i = 0; i < (int)pool.size(); i++)
+        if (pool[i].cap >= bytes && (best < 0 || pool[i].cap < pool[best].cap)) best = i;
+    if (best < 0) return false;
+    *out = pool[best];
+    pool.erase(pool.begin() + best);
+    return true;
+}
+
+int pool_get_dev(kb_ctx *ctx, size_t bytes, DBuf *out)
+{
+    if (bytes == 0) bytes = 16;
+    if (pool_take(ctx->free_dev, bytes, out)) return KB_OK;
+    DBuf b;
+    KB_TRY(dbuf_ensure(ctx, b, bytes));
+    *out = b;
+    return KB_OK;
+}
+
+int pool_get_host(kb_ctx *ctx, size_t bytes, HBuf *out)
+{
+    if (bytes == 0) bytes = 16;
+    if (pool_take(ctx->free_host, bytes, out)) return KB_OK;
+    HBuf b;
+    KB_TRY(hbuf_ensure(ctx, b, bytes));
+    *out = b;
+    return KB_OK;
+}
+
+void pool_put_dev(kb_ctx *ctx, DBuf b)
+{
+    if (!b.p) return;
+    if (ctx->free_dev.size() >= 16) {
+        cudaFree(b.p);
+        return;
+    }
+    ctx->free_dev.push_back(b);
+}
+
+void pool_put_host(kb_ctx *ctx, HBuf b)
+{
+    if (!b.p) return;
+    if (ctx->free_host.size() >= 16) {
+        cudaFreeHost(b.p);
+        return;
+    }
+    ctx->free_host.push_back(b);
+}
+
+// ------------------------------------------------------------------------------------------------
+// profiling
+// ------------------------------------------------------------------------------------------------
+int prof_index(kb_ctx *ctx, const char *name)
+{
+    for (int i = 0; i < (int)ctx->prof.size(); i++)
+        if (ctx->prof[i].name == name) return i;
+    ProfEntry e;
+    e.name = name;
+    ctx->prof.push_back(e);
+    return (int)ctx->prof.size() - 1;
+}
+
+static cudaEvent_t ev_get(kb_ctx *ctx)
+{
+    if (!ctx->ev_pool.empty()) {
+        cudaEvent_t e = ctx->ev_pool.back();
+        ctx->ev_pool.pop_back();
+        return e;
+    }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+}
+
+void prof_begin(kb_ctx *ctx, int idx, uint64_t alg_bytes)
+{
+    ProfPending p;
+    p.idx = idx;
+    p.a = ev_get(ctx);
+    p.b = ev_get(ctx);
+    cudaEventRecord(p.a, ctx->stream);
+    ctx->prof_pending.push_back(p);
+    ctx->prof[idx].launches++;
+    ctx->prof[idx].bytes += alg_bytes;
+}
+
+void prof_end(kb_ctx *ctx) { cudaEventRecord(ctx->prof_pending.back().b, ctx->stream); }
+
+static void prof_resolve(kb_ctx *ctx)
+{
+    if (ctx->prof_pending.empty()) return;
+    cudaStreamSynchronize(ctx->stream);
+    for (auto &p : ctx->prof_pending) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) ctx->prof[p.idx].ms += ms;
+        ctx->ev_pool.push_back(p.a);
+        ctx->ev_pool.push_back(p.b);
+    }
+    ctx->prof_pending.clear();
+}
+
+extern "C" int kb_prof_enable(kb_ctx *ctx, int on)
+{
+    if (!ctx) return KB_EINVAL;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    if (!on) prof_resolve(ctx);
+    ctx->prof_on = on != 0;
+    return KB_OK;
+}
+
+extern "C" int kb_prof_reset(kb_ctx *ctx)
+{
+    if (!ctx) return KB_EINVAL;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    prof_resolve(ctx);
+    ctx->prof.clear();
+    return KB_OK;
+}
+
+extern "C" int kb_prof_read(kb_ctx *ctx, kb_prof_entry *entries, int cap, int *n)
+{
+    if (!ctx || !n) return KB_EINVAL;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    prof_resolve(ctx);
+    int k = 0;
+    for (auto &e : ctx->prof) {
+        if (k < cap && entries) {
+            memset(&entries[k], 0, sizeof(kb_prof_entry));
+            strncpy(entries[k].name, e.name.c_str(), sizeof(entries[k].name) - 1);
+            entries[k].launches = e.launches;
+            entries[k].total_ms = e.ms;
+            entries[k].alg_bytes = e.bytes;
+        }
+        k++;
+    }
+    *n = k;
+    return KB_OK;
+}
+
+extern "C" uint64_t kb_launch_count(kb_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+// ------------------------------------------------------------------------------------------------
+// lifecycle
+// ------------------------------------------------------------------------------------------------
+extern "C" int kb_abi_version(void) { return KB_ABI_VERSION; }
+
+extern "C" int kb_open(int device_ordinal, const kb_config *cfg, kb_ctx **out)
+{
+    (void)cfg;
+    if (!out) return KB_EINVAL;
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev <= 0 || device_ordinal < 0 || device_ordinal >= ndev) {
+        // no CPU fallback: the product path refuses to run without a CUDA device
+        return KB_ECUDA;
+    }
+    kb_ctx *ctx = new kb_ctx();
+    ctx->device = device_ordinal;
+    if (cudaSetDevice(device_ordinal) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete ctx;
+        return KB_ECUDA;
+    }
+    *out = ctx;
+    return KB_OK;
+}
+
+static void dfree(DBuf &b)
+{
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr;
+    b.cap = 0;
+}
+
+extern "C" void kb_close(kb_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    watch_tables_free(ctx);
+    DBuf *all[] = {&ctx->d_kslab, &ctx->d_koff16, &ctx->d_klen, &ctx->d_vslab, &ctx->d_voff16, &ctx->d_vlen,
+                   &ctx->d_bounds, &ctx->d_boff, &ctx->d_blen, &ctx->d_bres, &ctx->d_reqs, &ctx->d_tiles,
+                   &ctx->d_meta, &ctx->d_tgt, &ctx->d_agg, &ctx->d_tcnt, &ctx->d_tscan, &ctx->d_reqout,
+                   &ctx->d_sel, &ctx->d_slot, &ctx->d_jobs, &ctx->d_scan_tmp, &ctx->d_flags, &ctx->d_cursor};
+    for (DBuf *b : all) dfree(*b);
+    for (auto &b : ctx->free_dev) cudaFree(b.p);
+    for (auto &b : ctx->free_host) cudaFreeHost(b.p);
+    if (ctx->h_stage.p) cudaFreeHost(ctx->h_stage.p);
+    if (ctx->h_stage2.p) cudaFreeHost(ctx->h_stage2.p);
+    for (auto &p : ctx->prof_pending) {
+        cudaEventDestroy(p.a);
+        cudaEventDestroy(p.b);
+    }
+    for (auto e : ctx->ev_pool) cudaEventDestroy(e);
+    if (ctx->nccl_comm) {
+        void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+        if (h) {
+            typedef int (*destroy_t)(void *);
+            destroy_t f = (destroy_t)dlsym(h, "ncclCommDestroy");
+            if (f) f(ctx->nccl_comm);
+        }
+    }
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+extern "C" const char *kb_last_error(kb_ctx *ctx) { return ctx ? ctx->err.c_str() : "no context"; }
+extern "C" void *kb_stream(kb_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+
+extern "C" int kb_sync(kb_ctx *ctx)
+{
+    if (!ctx) return KB_EINVAL;
+    KB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return KB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// store ingest
+// ------------------------------------------------------------------------------------------------
+// one warp per record: copy the packed bytes into the 16-byte aligned slab (destination is pre-zeroed)
+__global__ void k_repack(const uint8_t *__restrict__ src, const uint64_t *__restrict__ soff, uint8_t *__restrict__ dst,
+                         const uint32_t *__restrict__ doff16_32, const uint64_t *__restrict__ doff16_64, uint32_t n)
+{
+    uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    uint32_t nw = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t i = w; i < n; i += nw) {
+        uint64_t s = soff[i], e = soff[i + 1];
+        uint64_t d = (doff16_32 ? (uint64_t)doff16_32[i] : doff16_64[i]) * 16ull;
+        for (uint64_t b = lane; b < e - s; b += 32) dst[d + b] = src[s + b];
+    }
+}
+
+// strict ascending order of adjacent keys (storage.Iter contract); thread per record
+__global__ void k_check_sorted(StoreDev st, uint32_t *bad)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0 || i >= st.n) return;
+    const uint4 *a = st.kslab + st.koff16[i - 1];
+    const uint4 *b = st.kslab + st.koff16[i];
+    uint32_t la = st.klen[i - 1], lb = st.klen[i];
+    uint32_t m = la < lb ? la : lb;
+    bool less = la < lb;  // all common bytes equal -> shorter first; equal length -> duplicate -> not less
+    for (uint32_t c = 0; c * 16 < m; c++) {
+        uint4 x = a[c], y = b[c];
+        int p = first_diff16(x, y);
+        if (p < 16 && c * 16 + p < m) {
+            less = byte_of(x, p) < byte_of(y, p);
+            break;
+        }
+    }
+    if (!less) atomicMin(bad, i);
+}
+
+extern "C" int kb_load_sorted(kb_ctx *ctx, const uint8_t *keys, const uint64_t *key_off, const uint8_t *vals,
+                              const uint64_t *val_off, uint64_t n)
+{
+    if (!ctx || (n && (!keys || !key_off || !vals || !val_off))) return KB_EINVAL;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    cudaSetDevice(ctx->device);
+    if (n >= 0xFFFFFFFEull) return kb_fail(ctx, KB_ELIMIT, "too many records (%llu)", (unsigned long long)n);
+    ctx->loaded = false;
+
+    // destination offsets (host): every record padded to a 16-byte multiple
+    std::vector<uint32_t> koff16(n + 1);
+    std::vector<uint16_t> klen(n ? n : 1);
+    std::vector<uint64_t> voff16(n + 1);
+    std::vector<uint32_t> vlen(n ? n : 1);
+    uint64_t kacc = 0, vacc = 0;
+    for (uint64_t i = 0; i < n; i++) {
+        uint64_t kl = key_off[i + 1] - key_off[i], vl = val_off[i + 1] - val_off[i];
+        if (kl > 65535) return kb_fail(ctx, KB_ELIMIT, "key %llu longer than 65535 bytes", (unsigned long long)i);
+        if (vl > 0xFFFFFFFFull) return kb_fail(ctx, KB_ELIMIT, "value %llu too long", (unsigned long long)i);
+        koff16[i] = (uint32_t)kacc;
+        voff16[i] = vacc;
+        klen[i] = (uint16_t)kl;
+        vlen[i] = (uint32_t)vl;
+        kacc += (kl + 15) / 16;
+        vacc += (vl + 15) / 16;
+        if (kacc > 0xFFFFFFF0ull) return kb_fail(ctx, KB_ELIMIT, "key slab exceeds 64 GiB");
+    }
+    koff16[n] = (uint32_t)kacc;
+    voff16[n] = vacc;
+    ctx->key_bytes = kacc * 16;
+    ctx->val_bytes = vacc * 16;
+
+    KB_TRY(dbuf_ensure(ctx, ctx->d_kslab, kacc * 16 + 16));
+    KB_TRY(dbuf_ensure(ctx, ctx->d_vslab, vacc * 16 + 16));
+    KB_TRY(dbuf_ensure(ctx, ctx->d_koff16, (n + 1) * 4));
+    KB_TRY(dbuf_ensure(ctx, ctx->d_klen, (n + 1) * 2));
+    KB_TRY(dbuf_ensure(ctx, ctx->d_voff16, (n + 1) * 8));
+    KB_TRY(dbuf_ensure(ctx, ctx->d_vlen, (n + 1) * 4));
+    KB_CUDA(ctx, cudaMemsetAsync(ctx->d_kslab.p, 0, kacc * 16 + 16, ctx->stream));
+    KB_CUDA(ctx, cudaMemsetAsync(ctx->d_vslab.p, 0, vacc * 16 + 16, ctx->stream));
+    KB_CUDA(ctx, cudaMemcpyAsync(ctx->d_koff16.p, koff16.data(), (n + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
+    KB_CUDA(ctx, cudaMemcpyAsync(ctx->d_klen.p, klen.data(), n * 2, cudaMemcpyHostToDevice, ctx->stream));
+    KB_CUDA(ctx, cudaMemcpyAsync(ctx->d_voff16.p, voff16.data(), (n + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    KB_CUDA(ctx, cudaMemcpyAsync(ctx->d_vlen.p, vlen.data(), n * 4, cudaMemcpyHostToDevice, ctx->stream));
+
+    // packed source bytes -> device (temporary), then repack on the device
+    uint64_t ksrc = n ? key_off[n] - key_off[0] : 0, vsrc = n ? val_off[n] - val_off[0] : 0;
+    DBuf tmp_b, tmp_o;
+    uint64_t maxsrc = std::max(ksrc, vsrc);
+    KB_TRY(dbuf_ensure(ctx, tmp_b, maxsrc + 16));
+    KB_TRY(dbuf_ensure(ctx, tmp_o, (n + 1) * 8));
+    const int TB = 256;
+    int rg = (int)std::min<uint64_t>((n * 32 + TB - 1) / TB + 1, 148 * 16);
+    int rc = KB_OK;
+    do {
+        if (n == 0) break;
+        // keys (offsets rebased to 0 if the caller's first offset is not 0)
+        std::vector<uint64_t> rebased;
+        const uint64_t *ko = key_off, *vo = val_off;
+        if (key_off[0] != 0) {
+            rebased.resize(n + 1);
+            for (uint64_t i = 0; i <= n; i++) rebased[i] = key_off[i] - key_off[0];
+            ko = rebased.data();
+        }
+        if (cudaMemcpyAsync(tmp_b.p, keys + key_off[0], ksrc, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess ||
+            cudaMemcpyAsync(tmp_o.p, ko, (n + 1) * 8, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) {
+            rc = kb_fail(ctx, KB_ECUDA, "H2D of keys failed");
+            break;
+        }
+        k_repack<<<rg, TB, 0, ctx->stream>>>((const uint8_t *)tmp_b.p, (const uint64_t *)tmp_o.p,
+                                             (uint8_t *)ctx->d_kslab.p, (const uint32_t *)ctx->d_koff16.p, nullptr,
+                                             (uint32_t)n);
+        if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+            rc = kb_fail(ctx, KB_ECUDA, "key repack failed: %s", cudaGetErrorString(cudaGetLastError()));
+            break;
+        }
+        std::vector<uint64_t> rebased_v;
+        if (val_off[0] != 0) {
+            rebased_v.resize(n + 1);
+            for (uint64_t i = 0; i <= n; i++) rebased_v[i] = val_off[i] - val_off[0];
+            vo = rebased_v.data();
+        }
+        if (cudaMemcpyAsync(tmp_b.p, vals + val_off[0], vsrc, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess ||
+            cudaMemcpyAsync(tmp_o.p, vo, (n + 1) * 8, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) {
+            rc = kb_fail(ctx, KB_ECUDA, "H2D of values failed");
+            break;
+        }
+        k_repack<<<rg, TB, 0, ctx->stream>>>((const uint8_t *)tmp_b.p, (const uint64_t *)tmp_o.p,
+                                             (uint8_t *)ctx->d_vslab.p, nullptr, (const uint64_t *)ctx->d_voff16.p,
+                                             (uint32_t)n);
+        if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+            rc = kb_fail(ctx, KB_ECUDA, "value repack failed: %s", cudaGetErrorString(cudaGetLastError()));
+            break;
+        }
+    } while (0);
+    cudaFree(tmp_b.p);
+    cudaFree(tmp_o.p);
+    if (rc != KB_OK) return rc;
+
+    ctx->st.kslab = (const uint4 *)ctx->d_kslab.p;
+    ctx->st.koff16 = (const uint32_t *)ctx->d_koff16.p;
+    ctx->st.klen = (const uint16_t *)ctx->d_klen.p;
+    ctx->st.vslab = (const uint4 *)ctx->d_vslab.p;
+    ctx->st.voff16 = (const uint64_t *)ctx->d_voff16.p;
+    ctx->st.vlen = (const uint32_t *)ctx->d_vlen.p;
+    ctx->st.n = (uint32_t)n;
+    ctx->h_koff16 = koff16;
+
+    // the iterator contract: strictly ascending unique keys
+    if (n > 1) {
+        KB_TRY(dbuf_ensure(ctx, ctx->d_flags, 64));
+        uint32_t init = 0xFFFFFFFFu, bad = 0;
+        KB_CUDA(ctx, cudaMemcpyAsync(ctx->d_flags.p, &init, 4, cudaMemcpyHostToDevice, ctx->stream));
+        k_check_sorted<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->st, (uint32_t *)ctx->d_flags.p);
+        KB_CUDA(ctx, cudaMemcpyAsync(&bad, ctx->d_flags.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        KB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (bad != 0xFFFFFFFFu)
+            return kb_fail(ctx, KB_EUNSORTED, "record %u is not greater than its predecessor", bad);
+    }
+    ctx->loaded = true;
+    return KB_OK;
+}
+
+extern "C" int kb_store_info(kb_ctx *ctx, uint64_t *n_records, uint64_t *key_bytes, uint64_t *val_bytes)
+{
+    if (!ctx) return KB_EINVAL;
+    if (!ctx->loaded) return kb_fail(ctx, KB_ESTATE, "no store loaded");
+    if (n_records) *n_records = ctx->st.n;
+    if (key_bytes) *key_bytes = ctx->key_bytes;
+    if (val_bytes) *val_bytes = ctx->val_bytes;
+    return KB_OK;
+}
+
+extern "C" int kb_set_compact_revision(kb_ctx *ctx, int present, uint64_t rev)
+{
+    if (!ctx) return KB_EINVAL;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    ctx->compact_present = present != 0;
+    ctx->compact_rev = rev;
+    return KB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// NCCL revision cursor (one ncclAllGather of one uint64 per rank; min over ranks on the device)
+// ------------------------------------------------------------------------------------------------
+struct IdBlob {
+    char internal[KB_NCCL_ID_BYTES];
+};
+
+namespace {
+struct NcclApi {
+    void *h = nullptr;
+    int (*GetUniqueId)(void *) = nullptr;
+    int (*CommInitRank)(void **, int, /* ncclUniqueId by value */ IdBlob, int) = nullptr;
+    int (*AllGather)(const void *, void *, size_t, int, void *, cudaStream_t) = nullptr;
+    int (*CommDestroy)(void *) = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+};
+}  // namespace
+
+static NcclApi *nccl_api()
+{
+    static NcclApi api;
+    static bool tried = false;
+    if (tried) return api.h ? &api : nullptr;
+    tried = true;
+    // reuse the copy already mapped into the process (torch bundles one) before falling back to the system lib
+    void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) return nullptr;
+    api.GetUniqueId = (int (*)(void *))dlsym(h, "ncclGetUniqueId");
+    api.CommInitRank = (int (*)(void **, int, IdBlob, int))dlsym(h, "ncclCommInitRank");
+    api.AllGather = (int (*)(const void *, void *, size_t, int, void *, cudaStream_t))dlsym(h, "ncclAllGather");
+    api.CommDestroy = (int (*)(void *))dlsym(h, "ncclCommDestroy");
+    api.GetErrorString = (const char *(*)(int))dlsym(h, "ncclGetErrorString");
+    if (!api.GetUniqueId || !api.CommInitRank || !api.AllGather) return nullptr;
+    api.h = h;
+    return &api;
+}
+
+extern "C" int kb_nccl_unique_id(uint8_t id[KB_NCCL_ID_BYTES])
+{
+    NcclApi *a = nccl_api();
+    if (!a) return KB_ENCCL;
+    IdBlob b;
+    memset(&b, 0, sizeof(b));
+    if (a->GetUniqueId(&b) != 0) return KB_ENCCL;
+    memcpy(id, &b, KB_NCCL_ID_BYTES);
+    return KB_OK;
+}
+
+extern "C" int kb_nccl_init(kb_ctx *ctx, const uint8_t id[KB_NCCL_ID_BYTES], int rank, int nranks)
+{
+    if (!ctx || !id || rank < 0 || rank >= nranks) return KB_EINVAL;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    NcclApi *a = nccl_api();
+    if (!a) return kb_fail(ctx, KB_ENCCL, "libnccl.so.2 not loadable");
+    cudaSetDevice(ctx->device);
+    IdBlob b;
+    memcpy(&b, id, KB_NCCL_ID_BYTES);
+    int rc = a->CommInitRank(&ctx->nccl_comm, nranks, b, rank);
+    if (rc != 0) return kb_fail(ctx, KB_ENCCL, "ncclCommInitRank: %s", a->GetErrorString ? a->GetErrorString(rc) : "?");
+    ctx->nccl_rank = rank;
+    ctx->nccl_nranks = nranks;
+    return KB_OK;
+}
+
+__global__ void k_cursor_min(const uint64_t *all, int n, uint64_t *out)
+{
+    uint64_t m = ~0ull;
+    for (int i = 0; i < n; i++) m = all[i] < m ? all[i] : m;
+    *out = m;
+}
+
+extern "C" int kb_cursor_allgather(kb_ctx *ctx, uint64_t local_rev, uint64_t *all_revs, uint64_t *min_rev)
+{
+    if (!ctx) return KB_EINVAL;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    if (!ctx->nccl_comm) return kb_fail(ctx, KB_ESTATE, "kb_nccl_init has not been called");
+    NcclApi *a = nccl_api();
+    cudaSetDevice(ctx->device);
+    int n = ctx->nccl_nranks;
+    KB_TRY(dbuf_ensure(ctx, ctx->d_cursor, (size_t)(n + 2) * 8));
+    uint64_t *d = (uint64_t *)ctx->d_cursor.p;  // [0]=local, [1..n]=gathered, [n+1]=min
+    KB_CUDA(ctx, cudaMemcpyAsync(d, &local_rev, 8, cudaMemcpyHostToDevice, ctx->stream));
+    int rc = a->AllGather(d, d + 1, 1, /*ncclUint64*/ 5, ctx->nccl_comm, ctx->stream);
+    if (rc != 0) return kb_fail(ctx, KB_ENCCL, "ncclAllGather: %s", a->GetErrorString ? a->GetErrorString(rc) : "?");
+    KB_LAUNCH(ctx, "cursor_min", (uint64_t)n * 8, (k_cursor_min<<<1, 1, 0, ctx->stream>>>(d + 1, n, d + 1 + n)));
+    std::vector<uint64_t> host(n + 1);
+    KB_CUDA(ctx, cudaMemcpyAsync(host.data(), d + 1, (size_t)(n + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    KB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (all_revs) memcpy(all_revs, host.data(), (size_t)n * 8);
+    if (min_rev) *min_rev = host[n];
+    return KB_OK;
+}

@@ -1,0 +1,258 @@
+// kb_internal.cuh -- shared host/device plumbing of libkbb200.so (sm_100a only, no CPU fallback).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/kb_b200.h"
+
+// ------------------------------------------------------------------------------------------------
+// HBM layouts
+// ------------------------------------------------------------------------------------------------
+struct StoreDev {
+    const uint4    *kslab;   // internal keys, every record starts on a 16-byte boundary, zero padded
+    const uint32_t *koff16;  // n+1 offsets in 16-byte units
+    const uint16_t *klen;    // n exact key lengths
+    const uint4    *vslab;   // values, 16-byte aligned, zero padded
+    const uint64_t *voff16;  // n+1 offsets in 16-byte units
+    const uint32_t *vlen;    // n exact value lengths
+    uint32_t        n;
+};
+
+// one scanner.Range / Count / Compact request, resolved to record indices
+struct ReqDev {
+    uint32_t lo, hi;       // record interval [lo, hi)
+    uint32_t flat0;        // first slot of this request in the flat per-record scratch (multiple of TILE)
+    uint32_t tile0;        // first tile of this request
+    uint32_t ntiles;
+    uint32_t sel_base;     // first slot of this request in the selection arrays
+    uint64_t read_rev;
+    int64_t  limit;
+};
+
+struct TileDev {
+    uint32_t req;
+    uint32_t rec0;   // first store record of the tile
+    uint32_t n;      // records in the tile (<= TILE)
+    uint32_t flat0;  // flat slot of rec0
+};
+
+struct ScanMode {
+    int      compact;      // workerConfig.compact
+    int      ttl_scan;     // !SupportTTL() && timeoutRevision != 0
+    uint64_t timeout_rev;
+    int      want_sel;     // 0: count only
+};
+
+// per-record meta word produced by the decode pass
+#define KB_M_LCP_MASK 0x0000FFFFu
+#define KB_M_DEC_OK   (1u << 16)
+#define KB_M_REV0     (1u << 17)   // revision == 0 (revision record)
+#define KB_M_TRIG     (1u << 18)   // takes part as "cur": decodable, not TTL-expired, rev <= read_rev
+#define KB_M_TOMB     (1u << 19)   // value == "tombstone"
+#define KB_M_PREVOK   (1u << 20)   // becomes "prev" (TRIG and not the Q5 skip)
+#define KB_M_REVDEL   (1u << 21)   // class 3 victim
+#define KB_M_TTLREV   (1u << 22)   // class 4 victim
+#define KB_M_TTLOBJ   (1u << 23)   // class 5 victim
+#define KB_LCP_INF    0xFFFFu
+#define KB_NONE       0xFFFFFFFFu
+
+#define KB_TILE       1024          // records per tile (256 threads x 4)
+#define KB_WARP_STAGE_CHUNKS 640    // 16-byte chunks of shared memory staged per warp (10 KiB)
+
+// ------------------------------------------------------------------------------------------------
+// device helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 ldg_stream(const uint4 *p)
+{
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+
+__device__ __forceinline__ void stg_stream(uint4 *p, const uint4 &v)
+{
+    asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z),
+                 "r"(v.w)
+                 : "memory");
+}
+
+// first differing byte (memory order) of two 16-byte chunks, 16 when equal
+__device__ __forceinline__ int first_diff16(const uint4 &a, const uint4 &b)
+{
+    uint32_t x;
+    x = a.x ^ b.x; if (x) return (__ffs(x) - 1) >> 3;
+    x = a.y ^ b.y; if (x) return 4 + ((__ffs(x) - 1) >> 3);
+    x = a.z ^ b.z; if (x) return 8 + ((__ffs(x) - 1) >> 3);
+    x = a.w ^ b.w; if (x) return 12 + ((__ffs(x) - 1) >> 3);
+    return 16;
+}
+
+__device__ __forceinline__ uint32_t byte_of(const uint4 &a, int i)
+{
+    uint32_t w = (i < 4) ? a.x : (i < 8) ? a.y : (i < 12) ? a.z : a.w;
+    return (w >> ((i & 3) * 8)) & 0xffu;
+}
+
+__device__ __forceinline__ uint64_t be64_bytes(const uint8_t *p)
+{
+    uint64_t v = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) v = (v << 8) | (uint64_t)p[i];
+    return v;
+}
+
+__device__ __forceinline__ uint32_t pad16(uint32_t x) { return (x + 15u) & ~15u; }
+
+// ------------------------------------------------------------------------------------------------
+// host plumbing
+// ------------------------------------------------------------------------------------------------
+struct DBuf {
+    void  *p = nullptr;
+    size_t cap = 0;
+};
+
+struct HBuf {  // pinned host
+    void  *p = nullptr;
+    size_t cap = 0;
+};
+
+struct ProfEntry {
+    std::string name;
+    uint64_t launches = 0;
+    double   ms = 0;
+    uint64_t bytes = 0;
+};
+
+struct ProfPending {
+    int idx;
+    cudaEvent_t a, b;
+};
+
+struct Watcher {
+    std::string prefix;
+    uint64_t min_rev;
+    bool live;
+};
+
+struct WatchTablesDev;  // kb_watch.cu
+
+struct kb_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    std::mutex mu;
+
+    // store
+    bool loaded = false;
+    StoreDev st{};
+    DBuf d_kslab, d_koff16, d_klen, d_vslab, d_voff16, d_vlen;
+    uint64_t key_bytes = 0, val_bytes = 0;
+    std::vector<uint32_t> h_koff16;  // host copy, algorithmic-byte accounting only
+    bool compact_present = false;
+    uint64_t compact_rev = 0;
+
+    // scratch (grow only)
+    DBuf d_bounds, d_boff, d_blen, d_bres, d_reqs, d_tiles, d_meta, d_tgt, d_agg, d_tcnt, d_tscan, d_reqout, d_sel,
+        d_slot, d_jobs, d_scan_tmp, d_flags;
+    HBuf h_stage, h_stage2;
+
+    // buffer pools for results
+    std::vector<DBuf> free_dev;
+    std::vector<HBuf> free_host;
+
+    // watchers
+    std::vector<Watcher> watchers;
+    bool watch_dirty = true;
+    WatchTablesDev *wt = nullptr;
+    struct kb_events_dev *ev_scratch = nullptr;  // grow-only upload slab of kb_watch_match
+
+    // NCCL (dlopen'ed)
+    void *nccl_comm = nullptr;
+    int nccl_rank = -1, nccl_nranks = 0;
+    DBuf d_cursor;
+
+    // profiling
+    bool prof_on = false;
+    std::vector<ProfEntry> prof;
+    std::vector<ProfPending> prof_pending;
+    std::vector<cudaEvent_t> ev_pool;
+    uint64_t launches = 0;
+};
+
+struct kb_result {
+    int type = 0;  // 1 range, 2 compact, 3 match
+    int out_mode = 0;
+    // range
+    std::vector<uint64_t> req_first, req_count, req_examined;
+    uint64_t n_kvs = 0, n_bytes = 0;
+    HBuf h_meta, h_bytes;
+    DBuf d_bytes;
+    const uint32_t *rec_idx = nullptr;
+    const uint64_t *rev = nullptr, *key_off = nullptr, *val_off = nullptr;
+    const uint32_t *key_len = nullptr, *val_len = nullptr;
+    // compact
+    uint64_t n_victims = 0, count = 0, examined = 0;
+    HBuf h_vic;
+    DBuf d_vic;
+    // match
+    uint64_t n_watchers = 0, n_deliveries = 0;
+    HBuf h_match;
+    DBuf d_match;
+};
+
+kb_result *kb_result_new(int type, int out_mode);
+
+int kb_fail(kb_ctx *ctx, int code, const char *fmt, ...);
+int kb_cuda_fail(kb_ctx *ctx, cudaError_t e, const char *what);
+
+#define KB_CUDA(ctx, call)                                               \
+    do {                                                                 \
+        cudaError_t _e = (call);                                         \
+        if (_e != cudaSuccess) return kb_cuda_fail((ctx), _e, #call);    \
+    } while (0)
+
+#define KB_TRY(expr)              \
+    do {                          \
+        int _rc = (expr);         \
+        if (_rc != KB_OK) return _rc; \
+    } while (0)
+
+int dbuf_ensure(kb_ctx *ctx, DBuf &b, size_t bytes);
+int hbuf_ensure(kb_ctx *ctx, HBuf &b, size_t bytes);
+int pool_get_dev(kb_ctx *ctx, size_t bytes, DBuf *out);
+int pool_get_host(kb_ctx *ctx, size_t bytes, HBuf *out);
+void pool_put_dev(kb_ctx *ctx, DBuf b);
+void pool_put_host(kb_ctx *ctx, HBuf b);
+
+// profiling: bracket a kernel launch with events when enabled
+int prof_index(kb_ctx *ctx, const char *name);
+void prof_begin(kb_ctx *ctx, int idx, uint64_t alg_bytes);
+void prof_end(kb_ctx *ctx);
+
+#define KB_LAUNCH(ctx, name, bytes, ...)                      \
+    do {                                                      \
+        static thread_local int _pi = -1;                     \
+        if ((ctx)->prof_on) {                                 \
+            _pi = prof_index((ctx), (name));                  \
+            prof_begin((ctx), _pi, (bytes));                  \
+        }                                                     \
+        __VA_ARGS__;                                          \
+        (ctx)->launches++;                                    \
+        if ((ctx)->prof_on) prof_end((ctx));                  \
+    } while (0)
+
+// generic exclusive scans on the ctx stream (kb_scan_util.cu)
+int scan_exclusive_u32(kb_ctx *ctx, const uint32_t *in, uint32_t *out, uint32_t n, uint32_t *total_dev);
+int scan_exclusive_u64(kb_ctx *ctx, const uint64_t *in, uint64_t *out, uint32_t n, uint64_t *total_dev);
+
+// kb_watch.cu
+void watch_tables_free(kb_ctx *ctx);

@@ -1,0 +1,1109 @@
+// kb_scan.cu -- the MVCC range-scan and compaction-sweep path.
+//
+// Replaces (reference file:line):
+//   storage.Iter over badger            pkg/storage/badger/iter.go:27-98        -> HBM slab + k_search
+//   coder.Decode                        pkg/backend/coder/normal.go:58-70       -> k_decode_lcp
+//   worker.run (range + compact)        pkg/backend/scanner/scanner.go:389-516  -> k_decode_lcp, k_emit, k_place
+//   commonResultReceiver (limit)        pkg/backend/scanner/receiver.go:62-103  -> k_tile_scan, k_place, k_gather
+//
+// Kernel pipeline for one batch of requests (all on ctx->stream):
+//   k_search      lower_bound of every [start,end) bound in the sorted slab (warp per bound, 32-ary)
+//   k_decode_lcp  HBM-bound pass: stream the raw internal keys (16-byte loads, per-warp shared-memory
+//                 staging), decode magic/split/revision, visibility, tombstone probe, and the common-prefix
+//                 length with the preceding key -> one 32-bit meta word per record + per-tile aggregates
+//   k_emit        per tile: segmented "last visible version" scan over the meta words (prev pointer +
+//                 running min-LCP), decides which record every key change emits / supersedes
+//   k_tile_scan   prefix sums of per-tile counts/bytes, per-request totals
+//   k_place       ordered placement of the selection (limit applied) / ordered victim list
+//   k_gather      copy the winners' key+value into the response arena (16-byte vector copies)
+#include <algorithm>
+
+#include "kb_internal.cuh"
+
+namespace {
+
+constexpr uint32_t MAGIC_LE = 0x8b80fb57u;  // bytes 57 fb 80 8b (coder/normal.go:26)
+constexpr unsigned FULL = 0xffffffffu;
+
+// ------------------------------------------------------------------------------------------------
+// k_search
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool key_less(const StoreDev &st, uint32_t rec, const uint4 *b, uint32_t blen)
+{
+    const uint4 *a = st.kslab + st.koff16[rec];
+    uint32_t la = st.klen[rec];
+    uint32_t m = la < blen ? la : blen;
+    for (uint32_t c = 0; c * 16 < m; c++) {
+        uint4 x = a[c], y = b[c];
+        int p = first_diff16(x, y);
+        if (p < 16 && c * 16 + p < m) return byte_of(x, p) < byte_of(y, p);
+    }
+    return la < blen;
+}
+
+// out[w] = index of the first record whose key >= bound w (bytes.Compare order)
+__global__ void __launch_bounds__(128) k_search(StoreDev st, const uint4 *__restrict__ bounds,
+                                                const uint32_t *__restrict__ boff16,
+                                                const uint32_t *__restrict__ blen, uint32_t nb,
+                                                uint32_t *__restrict__ out)
+{
+    uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    uint32_t lane = threadIdx.x & 31;
+    if (w >= nb) return;
+    const uint4 *b = bounds + boff16[w];
+    uint32_t bl = blen[w];
+    uint32_t lo = 0, hi = st.n;
+    for (;;) {
+        uint32_t span = hi - lo;
+        if (span == 0) break;
+        if (span <= 32) {
+            bool less = lane < span ? key_less(st, lo + lane, b, bl) : false;
+            lo += __popc(__ballot_sync(FULL, less));
+            break;
+        }
+        uint32_t piv = lo + (uint32_t)(((uint64_t)span * (lane + 1)) / 33);
+        bool less = key_less(st, piv, b, bl);
+        int k = __popc(__ballot_sync(FULL, less));  // sorted slab: `less` holds for a prefix of the pivots
+        uint32_t nlo = lo, nhi = hi;
+        if (k > 0) nlo = __shfl_sync(FULL, piv, k - 1) + 1;
+        if (k < 32) nhi = __shfl_sync(FULL, piv, k);
+        lo = nlo;
+        hi = nhi;
+    }
+    if (lane == 0) out[w] = lo;
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_decode_lcp
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t bswap32(uint32_t x) { return __byte_perm(x, 0, 0x0123); }
+
+__device__ __forceinline__ bool contains_events(const uint8_t *uk, uint32_t n)  // bytes.Contains(rawKey, "/events/")
+{
+    uint64_t w = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        w = (w << 8) | uk[i];
+        if (i >= 7 && w == 0x2f6576656e74732full) return true;
+    }
+    return false;
+}
+
+__global__ void __launch_bounds__(256, 2)
+k_decode_lcp(StoreDev st, const ReqDev *__restrict__ reqs, const TileDev *__restrict__ tiles, ScanMode mode,
+             uint32_t *__restrict__ meta, uint2 *__restrict__ tile_agg)
+{
+    extern __shared__ uint4 stage[];  // 8 warps x KB_WARP_STAGE_CHUNKS
+    __shared__ uint2 sub_agg[32];
+    const TileDev tile = tiles[blockIdx.x];
+    const ReqDev req = reqs[tile.req];
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint4 *ws = stage + warp * KB_WARP_STAGE_CHUNKS;
+    const uint32_t nsub = (tile.n + 31) >> 5;
+
+    for (uint32_t sub = warp; sub < nsub; sub += 8) {
+        const uint32_t r0 = tile.rec0 + sub * 32;
+        const uint32_t nrec = min(32u, tile.n - sub * 32);
+        const bool valid = lane < nrec;
+        const uint32_t r = r0 + (valid ? lane : 0);
+        const bool halo = r0 > req.lo;  // the record before the sub-tile is needed for the first LCP
+        const uint32_t base16 = st.koff16[halo ? r0 - 1 : r0];
+        const uint32_t span = st.koff16[r0 + nrec] - base16;
+        const bool staged = span <= KB_WARP_STAGE_CHUNKS;
+        if (staged) {
+            const uint4 *src = st.kslab + base16;
+            for (uint32_t c = lane; c < span; c += 32) ws[c] = ldg_stream(src + c);
+        }
+        __syncwarp();
+
+        uint32_t word = KB_LCP_INF;
+        if (valid) {
+            const uint32_t o16 = st.koff16[r];
+            const uint32_t len = st.klen[r];
+            const uint4 *kp = staged ? (const uint4 *)(ws + (o16 - base16)) : st.kslab + o16;
+            const uint8_t *kb = (const uint8_t *)kp;
+            uint32_t lcp = KB_LCP_INF;
+            if (r > req.lo) {
+                const uint32_t po16 = st.koff16[r - 1];
+                const uint32_t plen = st.klen[r - 1];
+                const uint4 *pp = staged ? (const uint4 *)(ws + (po16 - base16)) : st.kslab + po16;
+                const uint32_t m = min(len, plen);
+                lcp = m;
+                for (uint32_t c = 0; c * 16 < m; c++) {
+                    uint4 x = kp[c], y = pp[c];
+                    int p = first_diff16(x, y);
+                    if (p < 16) {
+                        lcp = min(m, c * 16 + (uint32_t)p);
+                        break;
+                    }
+                }
+            }
+            uint32_t flags = 0;
+            // coder.Decode (normal.go:58-70); keys shorter than 13 bytes are undecodable (Go would panic)
+            bool dec_ok = len >= 13;
+            if (dec_ok) dec_ok = (((const uint32_t *)kp)[0] == MAGIC_LE) && (kb[len - 9] == 0x24);
+            if (dec_ok) {
+                const uint64_t rev = be64_bytes(kb + len - 8);
+                flags |= KB_M_DEC_OK;
+                if (rev == 0) flags |= KB_M_REV0;
+                const uint32_t vl = st.vlen[r];
+                uint4 v0 = make_uint4(0, 0, 0, 0);
+                if (vl >= 8 && (vl == 9 || (mode.ttl_scan && rev == 0))) v0 = st.vslab[st.voff16[r]];
+                const uint64_t vrev = ((uint64_t)bswap32(v0.x) << 32) | bswap32(v0.y);
+                bool expired = false;
+                if (mode.ttl_scan && contains_events(kb + 4, len - 13)) {  // compactIfExpired scanner.go:566-591
+                    if (rev == 0) {
+                        if (vl >= 8 && vrev <= mode.timeout_rev) {
+                            expired = true;
+                            flags |= KB_M_TTLREV;
+                        }
+                    } else if (rev <= mode.timeout_rev) {
+                        expired = true;
+                        flags |= KB_M_TTLOBJ;
+                    }
+                }
+                if (!expired && rev <= req.read_rev) {  // scanner.go:451-453
+                    flags |= KB_M_TRIG;
+                    if (vl == 9 && v0.x == 0x626d6f74u && v0.y == 0x6e6f7473u && (v0.z & 0xffu) == 0x65u)
+                        flags |= KB_M_TOMB;  // "tombstone" util.go:28
+                    bool prevok = true;
+                    if (mode.compact && rev == 0 && vl == 9) {  // scanner.go:476-491
+                        if (vrev > req.read_rev)
+                            prevok = false;  // `continue` without updating prev (Q5)
+                        else
+                            flags |= KB_M_REVDEL;
+                    }
+                    if (prevok) flags |= KB_M_PREVOK;
+                }
+            }
+            word = lcp | flags;
+            meta[tile.flat0 + sub * 32 + lane] = word;
+        }
+        // sub-tile aggregate: (last PREVOK slot, min LCP of the records after it)
+        const unsigned pm = __ballot_sync(FULL, valid && (word & KB_M_PREVOK));
+        uint32_t mval = valid ? (word & KB_M_LCP_MASK) : KB_LCP_INF;
+        uint32_t L = KB_NONE;
+        if (pm) {
+            const uint32_t top = 31 - __clz(pm);
+            if (lane <= top) mval = KB_LCP_INF;
+            L = tile.flat0 + sub * 32 + top;
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) mval = min(mval, __shfl_xor_sync(FULL, mval, d));
+        if (lane == 0) sub_agg[sub] = make_uint2(L, mval);
+        __syncwarp();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t L = KB_NONE, m = KB_LCP_INF;
+        for (uint32_t s = 0; s < nsub; s++) {
+            uint2 a = sub_agg[s];
+            if (a.x != KB_NONE) {
+                L = a.x;
+                m = a.y;
+            } else {
+                m = min(m, a.y);
+            }
+        }
+        tile_agg[blockIdx.x] = make_uint2(L, m);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// block-wide exclusive scan of the (last-prev slot, min-LCP-since) state
+//   combine(A, B) = B.L != NONE ? B : (A.L, min(A.m, B.m))
+// ------------------------------------------------------------------------------------------------
+struct LM {
+    uint32_t L, m;
+};
+
+__device__ __forceinline__ LM lm_combine(LM a, LM b)
+{
+    if (b.L != KB_NONE) return b;
+    LM r;
+    r.L = a.L;
+    r.m = min(a.m, b.m);
+    return r;
+}
+
+__device__ __forceinline__ LM block_excl_scan_lm(LM v, LM *warp_tot /* 8 */)
+{
+    const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    LM inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        LM o;
+        o.L = __shfl_up_sync(FULL, inc.L, d);
+        o.m = __shfl_up_sync(FULL, inc.m, d);
+        if (lane >= (unsigned)d) inc = lm_combine(o, inc);
+    }
+    if (lane == 31) warp_tot[w] = inc;
+    __syncthreads();
+    LM ex;  // exclusive within the warp
+    ex.L = __shfl_up_sync(FULL, inc.L, 1);
+    ex.m = __shfl_up_sync(FULL, inc.m, 1);
+    if (lane == 0) {
+        ex.L = KB_NONE;
+        ex.m = KB_LCP_INF;
+    }
+    LM pre;
+    pre.L = KB_NONE;
+    pre.m = KB_LCP_INF;
+    for (unsigned k = 0; k < w; k++) pre = lm_combine(pre, warp_tot[k]);
+    __syncthreads();
+    return lm_combine(pre, ex);
+}
+
+__device__ __forceinline__ uint64_t warp_incl_scan_u64(uint64_t v)
+{
+    const unsigned lane = threadIdx.x & 31;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint64_t o = __shfl_up_sync(FULL, v, d);
+        if (lane >= (unsigned)d) v += o;
+    }
+    return v;
+}
+
+// exclusive scan of two u64 values per thread over 256 threads
+__device__ __forceinline__ void block_excl_scan2(uint64_t a, uint64_t b, uint64_t &ea, uint64_t &eb, uint64_t &ta,
+                                                 uint64_t &tb, uint64_t *ws /* 2*9 */)
+{
+    const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    uint64_t ia = warp_incl_scan_u64(a), ib = warp_incl_scan_u64(b);
+    if (lane == 31) {
+        ws[w] = ia;
+        ws[9 + w] = ib;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint64_t ra = 0, rb = 0;
+        for (int k = 0; k < 8; k++) {
+            uint64_t x = ws[k], y = ws[9 + k];
+            ws[k] = ra;
+            ws[9 + k] = rb;
+            ra += x;
+            rb += y;
+        }
+        ws[8] = ra;
+        ws[17] = rb;
+    }
+    __syncthreads();
+    ea = ia - a + ws[w];
+    eb = ib - b + ws[9 + w];
+    ta = ws[8];
+    tb = ws[17];
+    __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_emit: the worker.run state machine, data-parallel.
+// For every TRIG record i with prev p = last PREVOK record before it (inside the request):
+//   same key  <=> klen[i] == klen[p] && min LCP over (p, i] >= klen[i] - 9
+//   range  : key change && rev[p] > 0 && value[p] != tombstone  -> emit p         (scanner.go:457-462)
+//   compact: same key && rev[p] > 0                             -> p superseded   (scanner.go:463-469)
+// After the last record of a request the trailing prev is emitted (scanner.go:503-507).
+// tgt[i] = flat slot of the emitted (range) / superseded (compact) record, or NONE.
+// tcnt[2t] = emissions (range) or delete calls (compact) of tile t; tcnt[2t+1] = response bytes (range) or
+// object count (compact).
+// ------------------------------------------------------------------------------------------------
+template <bool COMPACT>
+__global__ void __launch_bounds__(256)
+k_emit(StoreDev st, const ReqDev *__restrict__ reqs, const TileDev *__restrict__ tiles,
+       const uint2 *__restrict__ tile_agg, const uint32_t *__restrict__ meta, uint32_t *__restrict__ tgt,
+       uint32_t *__restrict__ tail_tgt, uint64_t *__restrict__ tcnt)
+{
+    __shared__ LM warp_tot[8];
+    __shared__ LM carry_s;
+    __shared__ uint64_t ws2[18];
+    const TileDev tile = tiles[blockIdx.x];
+    const ReqDev req = reqs[tile.req];
+    if (threadIdx.x == 0) {
+        LM c;
+        c.L = KB_NONE;
+        c.m = KB_LCP_INF;
+        for (uint32_t t = blockIdx.x; t-- > req.tile0;) {
+            uint2 a = tile_agg[t];
+            c.m = min(c.m, a.y);
+            if (a.x != KB_NONE) {
+                c.L = a.x;
+                break;
+            }
+        }
+        carry_s = c;
+    }
+    const uint32_t base = threadIdx.x * 4;
+    const uint32_t flat = tile.flat0 + base;
+    uint32_t w[4];
+    {
+        uint4 mw = make_uint4(KB_LCP_INF, KB_LCP_INF, KB_LCP_INF, KB_LCP_INF);
+        if (base < tile.n) mw = *(const uint4 *)(meta + flat);
+        w[0] = base + 0 < tile.n ? mw.x : KB_LCP_INF;
+        w[1] = base + 1 < tile.n ? mw.y : KB_LCP_INF;
+        w[2] = base + 2 < tile.n ? mw.z : KB_LCP_INF;
+        w[3] = base + 3 < tile.n ? mw.w : KB_LCP_INF;
+    }
+    LM mine;
+    mine.L = KB_NONE;
+    mine.m = KB_LCP_INF;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        if (w[k] & KB_M_PREVOK) {
+            mine.L = flat + k;
+            mine.m = KB_LCP_INF;
+        } else {
+            mine.m = min(mine.m, w[k] & KB_M_LCP_MASK);
+        }
+    }
+    LM ex = block_excl_scan_lm(mine, warp_tot);  // contains a __syncthreads: carry_s is visible after it
+    LM x = lm_combine(carry_s, ex);
+
+    uint64_t cnt = 0, aux = 0;
+    const bool last_tile = (blockIdx.x == req.tile0 + req.ntiles - 1);
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        if (base + k >= tile.n) break;
+        const uint32_t i = flat + k;
+        const uint32_t word = w[k];
+        uint32_t t = KB_NONE;
+        if (word & KB_M_TRIG) {
+            if (x.L != KB_NONE) {
+                const uint32_t mm = min(x.m, word & KB_M_LCP_MASK);
+                const uint32_t irec = req.lo + (i - req.flat0), prec = req.lo + (x.L - req.flat0);
+                const uint32_t pw = meta[x.L];
+                const uint32_t kl = st.klen[irec], pkl = st.klen[prec];
+                const bool same = (kl == pkl) && (mm >= kl - 9);
+                if (!same) {
+                    if (!(pw & KB_M_REV0) && !(pw & KB_M_TOMB)) {
+                        if (COMPACT) {
+                            aux++;  // count++ only
+                        } else {
+                            t = x.L;
+                            cnt++;
+                            aux += pad16(pkl) + pad16(st.vlen[prec]);
+                        }
+                    }
+                } else if (COMPACT && !(pw & KB_M_REV0)) {
+                    t = x.L;  // superseded version
+                    cnt++;
+                }
+            }
+            if (COMPACT) {
+                if (word & KB_M_TOMB) cnt++;
+                if (word & KB_M_REVDEL) cnt++;
+            }
+        }
+        if (COMPACT && (word & (KB_M_TTLREV | KB_M_TTLOBJ))) cnt++;
+        if (word & KB_M_PREVOK) {
+            x.L = i;
+            x.m = KB_LCP_INF;
+        } else {
+            x.m = min(x.m, word & KB_M_LCP_MASK);
+        }
+        tgt[i] = t;
+        if (last_tile && base + k == tile.n - 1) {
+            // end of the request's iterator: the trailing prev (scanner.go:503-507)
+            uint32_t tt = KB_NONE;
+            if (x.L != KB_NONE) {
+                const uint32_t pw = meta[x.L];
+                if (!(pw & KB_M_REV0) && !(pw & KB_M_TOMB)) {
+                    if (COMPACT) {
+                        aux++;
+                    } else {
+                        const uint32_t prec = req.lo + (x.L - req.flat0);
+                        tt = x.L;
+                        cnt++;
+                        aux += pad16(st.klen[prec]) + pad16(st.vlen[prec]);
+                    }
+                }
+            }
+            tail_tgt[tile.req] = tt;
+        }
+    }
+    uint64_t ea, eb, ta, tb;
+    block_excl_scan2(cnt, aux, ea, eb, ta, tb, ws2);
+    if (threadIdx.x == 0) {
+        tcnt[2 * blockIdx.x] = ta;
+        tcnt[2 * blockIdx.x + 1] = tb;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_tile_scan: one CTA; exclusive prefix of the per-tile pairs + per-request totals
+// ------------------------------------------------------------------------------------------------
+struct ReqOut {
+    uint64_t total;        // emissions (range) / delete calls (compact)
+    uint64_t total_aux;    // response bytes (range) / object count (compact)
+    uint64_t capped_aux;   // response bytes of the first `limit` emissions
+    uint32_t examined;
+    uint32_t limit_stop;
+};
+
+__global__ void __launch_bounds__(256)
+k_tile_scan(const ReqDev *__restrict__ reqs, uint32_t nreq, const uint64_t *__restrict__ tcnt,
+            uint64_t *__restrict__ tscan /* 2*(T+1) */, uint32_t ntiles, ReqOut *__restrict__ rout)
+{
+    __shared__ uint64_t ws2[18];
+    __shared__ uint64_t carry[2];
+    if (threadIdx.x == 0) carry[0] = carry[1] = 0;
+    __syncthreads();
+    for (uint32_t c0 = 0; c0 < ntiles; c0 += 256) {
+        uint32_t t = c0 + threadIdx.x;
+        uint64_t a = t < ntiles ? tcnt[2 * t] : 0, b = t < ntiles ? tcnt[2 * t + 1] : 0;
+        uint64_t ea, eb, ta, tb;
+        block_excl_scan2(a, b, ea, eb, ta, tb, ws2);
+        uint64_t ca = carry[0], cb = carry[1];
+        if (t < ntiles) {
+            tscan[2 * t] = ca + ea;
+            tscan[2 * t + 1] = cb + eb;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            carry[0] = ca + ta;
+            carry[1] = cb + tb;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        tscan[2 * ntiles] = carry[0];
+        tscan[2 * ntiles + 1] = carry[1];
+    }
+    __syncthreads();
+    for (uint32_t q = threadIdx.x; q < nreq; q += 256) {
+        ReqDev r = reqs[q];
+        ReqOut o;
+        o.total = o.total_aux = 0;
+        if (r.ntiles) {
+            o.total = tscan[2 * (r.tile0 + r.ntiles)] - tscan[2 * r.tile0];
+            o.total_aux = tscan[2 * (r.tile0 + r.ntiles) + 1] - tscan[2 * r.tile0 + 1];
+        }
+        o.capped_aux = o.total_aux;
+        o.examined = r.hi - r.lo;
+        o.limit_stop = 0;
+        rout[q] = o;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_place: ordered selection (range) -- position = emissions before it in the request; the first `limit`
+// positions are kept (commonResultReceiver.needMore, receiver.go:82-87).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_place(StoreDev st, const ReqDev *__restrict__ reqs, const TileDev *__restrict__ tiles,
+        const uint32_t *__restrict__ tgt, const uint32_t *__restrict__ tail_tgt,
+        const uint64_t *__restrict__ tscan, uint32_t *__restrict__ sel, uint64_t *__restrict__ slot,
+        ReqOut *__restrict__ rout)
+{
+    __shared__ uint64_t ws2[18];
+    const TileDev tile = tiles[blockIdx.x];
+    const ReqDev req = reqs[tile.req];
+    const uint32_t base = threadIdx.x * 4;
+    const uint32_t flat = tile.flat0 + base;
+    const bool last_tile = (blockIdx.x == req.tile0 + req.ntiles - 1);
+    uint32_t t[5];
+    uint32_t sz[5];
+    uint64_t cnt = 0, bytes = 0;
+#pragma unroll
+    for (int k = 0; k < 5; k++) {
+        t[k] = KB_NONE;
+        sz[k] = 0;
+    }
+    if (base < tile.n) {
+        uint4 tw = *(const uint4 *)(tgt + flat);
+        t[0] = tw.x;
+        t[1] = base + 1 < tile.n ? tw.y : KB_NONE;
+        t[2] = base + 2 < tile.n ? tw.z : KB_NONE;
+        t[3] = base + 3 < tile.n ? tw.w : KB_NONE;
+        if (last_tile && tile.n - 1 >= base && tile.n - 1 < base + 4) t[4] = tail_tgt[tile.req];
+    }
+#pragma unroll
+    for (int k = 0; k < 5; k++) {
+        if (t[k] != KB_NONE) {
+            const uint32_t prec = req.lo + (t[k] - req.flat0);
+            sz[k] = pad16(st.klen[prec]) + pad16(st.vlen[prec]);
+            cnt++;
+            bytes += sz[k];
+        }
+    }
+    uint64_t ea, eb, ta, tb;
+    block_excl_scan2(cnt, bytes, ea, eb, ta, tb, ws2);
+    uint64_t pos = tscan[2 * blockIdx.x] - tscan[2 * req.tile0] + ea;
+    uint64_t off = tscan[2 * blockIdx.x + 1] - tscan[2 * req.tile0 + 1] + eb;
+    const bool limited = req.limit > 0;
+#pragma unroll
+    for (int k = 0; k < 5; k++) {
+        if (t[k] == KB_NONE) continue;
+        if (!limited || pos < (uint64_t)req.limit) {
+            sel[req.sel_base + pos] = req.lo + (t[k] - req.flat0);
+            slot[req.sel_base + pos] = off;
+            if (limited && pos == (uint64_t)req.limit - 1) {
+                rout[tile.req].capped_aux = off + sz[k];
+                if (k < 4) {
+                    // the limit-th append happened inside the loop: the iterator stops here (Q4)
+                    rout[tile.req].examined = (flat + k) - req.flat0 + 1;
+                    rout[tile.req].limit_stop = 1;
+                }
+            }
+        }
+        pos++;
+        off += sz[k];
+    }
+}
+
+// ordered delete calls (compact): per record [superseded prev] [tombstone] [revision record] | [ttl]
+__global__ void __launch_bounds__(256)
+k_place_victims(const ReqDev *__restrict__ reqs, const TileDev *__restrict__ tiles,
+                const uint32_t *__restrict__ meta, const uint32_t *__restrict__ tgt,
+                const uint64_t *__restrict__ tscan, uint32_t *__restrict__ vidx, uint8_t *__restrict__ vcls)
+{
+    __shared__ uint64_t ws2[18];
+    const TileDev tile = tiles[blockIdx.x];
+    const ReqDev req = reqs[tile.req];
+    const uint32_t base = threadIdx.x * 4;
+    const uint32_t flat = tile.flat0 + base;
+    uint32_t t[4], w[4];
+    uint64_t cnt = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        t[k] = KB_NONE;
+        w[k] = 0;
+        if (base + k < tile.n) {
+            t[k] = tgt[flat + k];
+            w[k] = meta[flat + k];
+            if (t[k] != KB_NONE) cnt++;
+            if ((w[k] & KB_M_TRIG) && (w[k] & KB_M_TOMB)) cnt++;
+            if (w[k] & KB_M_REVDEL) cnt++;
+            if (w[k] & (KB_M_TTLREV | KB_M_TTLOBJ)) cnt++;
+        }
+    }
+    uint64_t ea, eb, ta, tb;
+    block_excl_scan2(cnt, 0, ea, eb, ta, tb, ws2);
+    uint64_t pos = req.sel_base + tscan[2 * blockIdx.x] - tscan[2 * req.tile0] + ea;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        if (base + k >= tile.n) break;
+        const uint32_t irec = req.lo + (flat + k - req.flat0);
+        if (t[k] != KB_NONE) {
+            vidx[pos] = req.lo + (t[k] - req.flat0);
+            vcls[pos++] = KB_V_SUPERSEDED;
+        }
+        if ((w[k] & KB_M_TRIG) && (w[k] & KB_M_TOMB)) {
+            vidx[pos] = irec;
+            vcls[pos++] = KB_V_TOMBSTONE;
+        }
+        if (w[k] & KB_M_REVDEL) {
+            vidx[pos] = irec;
+            vcls[pos++] = KB_V_REVRECORD;
+        }
+        if (w[k] & KB_M_TTLREV) {
+            vidx[pos] = irec;
+            vcls[pos++] = KB_V_TTL_REVREC;
+        }
+        if (w[k] & KB_M_TTLOBJ) {
+            vidx[pos] = irec;
+            vcls[pos++] = KB_V_TTL_OBJECT;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_gather: one warp per emitted kv; key (internal key, padded) then value (padded), 16-byte vector copies
+// ------------------------------------------------------------------------------------------------
+struct GatherOut {
+    uint32_t *rec_idx;
+    uint64_t *rev;
+    uint64_t *key_off;
+    uint32_t *key_len;
+    uint64_t *val_off;
+    uint32_t *val_len;
+};
+
+__global__ void __launch_bounds__(256)
+k_gather(StoreDev st, const ReqDev *__restrict__ reqs, uint32_t nreq, const uint64_t *__restrict__ job_first,
+         const uint64_t *__restrict__ arena_base, uint64_t n_kvs, const uint32_t *__restrict__ sel,
+         const uint64_t *__restrict__ slot, uint4 *__restrict__ arena, GatherOut out)
+{
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t k = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; k < n_kvs; k += nwarps) {
+        // request of kv k: last q with job_first[q] <= k
+        uint32_t lo = 0, hi = nreq;
+        while (hi - lo > 1) {
+            uint32_t mid = (lo + hi) >> 1;
+            if (job_first[mid] <= k) lo = mid; else hi = mid;
+        }
+        const uint32_t q = lo;
+        const uint64_t s = reqs[q].sel_base + (k - job_first[q]);
+        const uint32_t rec = sel[s];
+        const uint64_t dst_byte = arena_base[q] + slot[s];
+        const uint32_t kl = st.klen[rec], vl = st.vlen[rec];
+        const uint32_t nk = (kl + 15) >> 4, nv = (vl + 15) >> 4;
+        const uint4 *ks = st.kslab + st.koff16[rec];
+        const uint4 *vs = st.vslab + st.voff16[rec];
+        uint4 *dk = arena + (dst_byte >> 4);
+        uint4 *dv = dk + nk;
+        for (uint32_t c = lane; c < nk; c += 32) stg_stream(dk + c, ldg_stream(ks + c));
+        uint32_t c = lane;
+        for (; c + 96 < nv; c += 128) {
+            uint4 a0 = ldg_stream(vs + c), a1 = ldg_stream(vs + c + 32), a2 = ldg_stream(vs + c + 64),
+                  a3 = ldg_stream(vs + c + 96);
+            stg_stream(dv + c, a0);
+            stg_stream(dv + c + 32, a1);
+            stg_stream(dv + c + 64, a2);
+            stg_stream(dv + c + 96, a3);
+        }
+        for (; c < nv; c += 32) stg_stream(dv + c, ldg_stream(vs + c));
+        if (lane == 0) {
+            out.rec_idx[k] = rec;
+            out.rev[k] = be64_bytes((const uint8_t *)ks + kl - 8);
+            out.key_off[k] = dst_byte + 4;
+            out.key_len[k] = kl - 13;
+            out.val_off[k] = dst_byte + (uint64_t)nk * 16;
+            out.val_len[k] = vl;
+        }
+    }
+}
+
+}  // namespace
+
+// ================================================================================================
+// host orchestration
+// ================================================================================================
+kb_result *kb_result_new(int type, int out_mode)
+{
+    kb_result *r = new kb_result();
+    r->type = type;
+    r->out_mode = out_mode;
+    return r;
+}
+
+extern "C" void kb_result_free(kb_ctx *ctx, kb_result *res)
+{
+    if (!res) return;
+    if (ctx) {
+        std::lock_guard<std::mutex> g(ctx->mu);
+        pool_put_host(ctx, res->h_meta);
+        pool_put_host(ctx, res->h_bytes);
+        pool_put_dev(ctx, res->d_bytes);
+        pool_put_host(ctx, res->h_vic);
+        pool_put_dev(ctx, res->d_vic);
+        pool_put_host(ctx, res->h_match);
+        pool_put_dev(ctx, res->d_match);
+    }
+    delete res;
+}
+
+namespace {
+
+struct Resolved {
+    std::vector<ReqDev> reqs;
+    std::vector<TileDev> tiles;
+    uint64_t total_flat = 0, total_sel = 0, key_bytes = 0, n_records = 0;
+};
+
+// upload the bound keys, run k_search, and lay the requests out as tiles
+int resolve_requests(kb_ctx *ctx, const kb_range_req *reqs, uint64_t nreq, bool cap_by_limit, Resolved &R)
+{
+    // bound slab: 2 keys per request, each padded to 16 bytes
+    uint64_t chunks = 0;
+    for (uint64_t q = 0; q < nreq; q++) {
+        if ((!reqs[q].start && reqs[q].start_len) || (!reqs[q].end && reqs[q].end_len)) return KB_EINVAL;
+        if (reqs[q].start_len > 65535 || reqs[q].end_len > 65535) return kb_fail(ctx, KB_ELIMIT, "bound key too long");
+        chunks += (reqs[q].start_len + 15) / 16 + (reqs[q].end_len + 15) / 16 + 2;
+    }
+    const uint64_t nb = 2 * nreq;
+    size_t stage_bytes = chunks * 16 + nb * 8 + 64;
+    KB_TRY(hbuf_ensure(ctx, ctx->h_stage, stage_bytes + nb * 4));
+    uint8_t *hs = (uint8_t *)ctx->h_stage.p;
+    memset(hs, 0, chunks * 16);
+    uint32_t *hboff = (uint32_t *)(hs + chunks * 16);
+    uint32_t *hblen = hboff + nb;
+    uint32_t *hres = hblen + nb;  // D2H target
+    uint64_t c = 0;
+    for (uint64_t q = 0; q < nreq; q++) {
+        const uint8_t *keys[2] = {reqs[q].start, reqs[q].end};
+        const uint64_t lens[2] = {reqs[q].start_len, reqs[q].end_len};
+        for (int j = 0; j < 2; j++) {
+            hboff[2 * q + j] = (uint32_t)c;
+            hblen[2 * q + j] = (uint32_t)lens[j];
+            if (lens[j]) memcpy(hs + c * 16, keys[j], lens[j]);
+            c += (lens[j] + 15) / 16 + 1;
+        }
+    }
+    KB_TRY(dbuf_ensure(ctx, ctx->d_bounds, chunks * 16 + 16));
+    KB_TRY(dbuf_ensure(ctx, ctx->d_boff, nb * 4));
+    KB_TRY(dbuf_ensure(ctx, ctx->d_blen, nb * 4));
+    KB_TRY(dbuf_ensure(ctx, ctx->d_bres, nb * 4));
+    KB_CUDA(ctx, cudaMemcpyAsync(ctx->d_bounds.p, hs, chunks * 16, cudaMemcpyHostToDevice, ctx->stream));
+    KB_CUDA(ctx, cudaMemcpyAsync(ctx->d_boff.p, hboff, nb * 4, cudaMemcpyHostToDevice, ctx->stream));
+    KB_CUDA(ctx, cudaMemcpyAsync(ctx->d_blen.p, hblen, nb * 4, cudaMemcpyHostToDevice, ctx->stream));
+    const unsigned sgrid = (unsigned)((nb * 32 + 127) / 128);
+    KB_LAUNCH(ctx, "k_search", nb * 64,
+              (k_search<<<sgrid, 128, 0, ctx->stream>>>(ctx->st, (const uint4 *)ctx->d_bounds.p,
+                                                        (const uint32_t *)ctx->d_boff.p,
+                                                        (const uint32_t *)ctx->d_blen.p, (uint32_t)nb,
+                                                        (uint32_t *)ctx->d_bres.p)));
+    KB_CUDA(ctx, cudaMemcpyAsync(hres, ctx->d_bres.p, nb * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    KB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+
+    R.reqs.resize(nreq);
+    R.tiles.clear();
+    uint64_t flat = 0, selb = 0;
+    for (uint64_t q = 0; q < nreq; q++) {
+        ReqDev &r = R.reqs[q];
+        r.lo = hres[2 * q];
+        r.hi = std::max(hres[2 * q + 1], r.lo);
+        r.flat0 = (uint32_t)flat;
+        r.tile0 = (uint32_t)R.tiles.size();
+        uint32_t n = r.hi - r.lo;
+        r.ntiles = (n + KB_TILE - 1) / KB_TILE;
+        r.sel_base = (uint32_t)selb;
+        r.read_rev = reqs[q].read_rev;
+        r.limit = reqs[q].limit;
+        for (uint32_t t = 0; t < r.ntiles; t++) {
+            TileDev td;
+            td.req = (uint32_t)q;
+            td.rec0 = r.lo + t * KB_TILE;
+            td.n = std::min<uint32_t>(KB_TILE, n - t * KB_TILE);
+            td.flat0 = r.flat0 + t * KB_TILE;
+            R.tiles.push_back(td);
+        }
+        flat += (uint64_t)r.ntiles * KB_TILE;
+        uint64_t cap = n;
+        if (cap_by_limit && r.limit > 0) cap = std::min<uint64_t>(cap, (uint64_t)r.limit);
+        selb += cap;
+        R.n_records += n;
+        if (flat >= 0xFFFFF000ull || selb >= 0xFFFFF000ull)
+            return kb_fail(ctx, KB_ELIMIT, "batch examines more than 2^32 records; split it");
+    }
+    R.total_flat = flat;
+    R.total_sel = selb;
+    return KB_OK;
+}
+
+int upload_layout(kb_ctx *ctx, const Resolved &R)
+{
+    const size_t nreq = R.reqs.size(), nt = R.tiles.size();
+    KB_TRY(dbuf_ensure(ctx, ctx->d_reqs, std::max<size_t>(nreq, 1) * sizeof(ReqDev)));
+    KB_TRY(dbuf_ensure(ctx, ctx->d_tiles, std::max<size_t>(nt, 1) * sizeof(TileDev)));
+    KB_TRY(dbuf_ensure(ctx, ctx->d_meta, std::max<uint64_t>(R.total_flat, 4) * 4));
+    KB_TRY(dbuf_ensure(ctx, ctx->d_tgt, std::max<uint64_t>(R.total_flat, 4) * 4 + nreq * 4 + 16));
+    KB_TRY(dbuf_ensure(ctx, ctx->d_agg, std::max<size_t>(nt, 1) * 8));
+    KB_TRY(dbuf_ensure(ctx, ctx->d_tcnt, std::max<size_t>(nt, 1) * 16));
+    KB_TRY(dbuf_ensure(ctx, ctx->d_tscan, (nt + 1) * 16));
+    KB_TRY(dbuf_ensure(ctx, ctx->d_reqout, std::max<size_t>(nreq, 1) * sizeof(ReqOut)));
+    // pinned staging so the async copies really are asynchronous
+    size_t bytes = nreq * sizeof(ReqDev) + nt * sizeof(TileDev);
+    KB_TRY(hbuf_ensure(ctx, ctx->h_stage2, bytes + 64));
+    uint8_t *h = (uint8_t *)ctx->h_stage2.p;
+    memcpy(h, R.reqs.data(), nreq * sizeof(ReqDev));
+    memcpy(h + nreq * sizeof(ReqDev), R.tiles.data(), nt * sizeof(TileDev));
+    KB_CUDA(ctx, cudaMemcpyAsync(ctx->d_reqs.p, h, nreq * sizeof(ReqDev), cudaMemcpyHostToDevice, ctx->stream));
+    if (nt)
+        KB_CUDA(ctx, cudaMemcpyAsync(ctx->d_tiles.p, h + nreq * sizeof(ReqDev), nt * sizeof(TileDev),
+                                     cudaMemcpyHostToDevice, ctx->stream));
+    return KB_OK;
+}
+
+}  // namespace
+
+// host copy of the slab offsets, kept for algorithmic-byte accounting only
+static inline std::vector<uint32_t> &host_koff16(kb_ctx *ctx) { return ctx->h_koff16; }
+
+extern "C" int kb_range_batch(kb_ctx *ctx, const kb_range_req *reqs, uint64_t nreq, int out_mode, kb_result **out)
+{
+    if (!ctx || !out || (nreq && !reqs)) return KB_EINVAL;
+    if (out_mode != KB_OUT_HOST && out_mode != KB_OUT_DEVICE && out_mode != KB_OUT_COUNT) return KB_EINVAL;
+    *out = nullptr;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    if (!ctx->loaded) return kb_fail(ctx, KB_ESTATE, "no store loaded");
+    cudaSetDevice(ctx->device);
+    for (uint64_t q = 0; q < nreq; q++) {
+        // checkCompactRace (scanner.go:594-626)
+        if (ctx->compact_present && ctx->compact_rev > reqs[q].read_rev)
+            return kb_fail(ctx, KB_ECOMPACTED, "range stream revision %llu less than compact revision %llu",
+                           (unsigned long long)reqs[q].read_rev, (unsigned long long)ctx->compact_rev);
+    }
+    Resolved R;
+    KB_TRY(resolve_requests(ctx, reqs, nreq, true, R));
+    KB_TRY(upload_layout(ctx, R));
+    const uint32_t nt = (uint32_t)R.tiles.size();
+    KB_TRY(dbuf_ensure(ctx, ctx->d_sel, std::max<uint64_t>(R.total_sel, 1) * 4));
+    KB_TRY(dbuf_ensure(ctx, ctx->d_slot, std::max<uint64_t>(R.total_sel, 1) * 8));
+
+    const ReqDev *d_reqs = (const ReqDev *)ctx->d_reqs.p;
+    const TileDev *d_tiles = (const TileDev *)ctx->d_tiles.p;
+    uint32_t *d_meta = (uint32_t *)ctx->d_meta.p;
+    uint32_t *d_tgt = (uint32_t *)ctx->d_tgt.p;
+    uint32_t *d_tail = d_tgt + std::max<uint64_t>(R.total_flat, 4);
+    uint2 *d_agg = (uint2 *)ctx->d_agg.p;
+    uint64_t *d_tcnt = (uint64_t *)ctx->d_tcnt.p;
+    uint64_t *d_tscan = (uint64_t *)ctx->d_tscan.p;
+    ReqOut *d_rout = (ReqOut *)ctx->d_reqout.p;
+
+    ScanMode mode;
+    mode.compact = 0;
+    mode.ttl_scan = 0;
+    mode.timeout_rev = 0;
+    mode.want_sel = out_mode != KB_OUT_COUNT;
+    const size_t smem = 8 * KB_WARP_STAGE_CHUNKS * 16;
+    static bool attr_set = false;
+    if (!attr_set) {
+        KB_CUDA(ctx, cudaFuncSetAttribute(k_decode_lcp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    // algorithmic bytes of the decode pass: key bytes of the examined records + 10 B of offsets/lengths each
+    uint64_t kbytes = 0;
+    {
+        std::vector<uint32_t> &ko = host_koff16(ctx);
+        for (auto &r : R.reqs) kbytes += (uint64_t)(ko[r.hi] - ko[r.lo]) * 16 + (uint64_t)(r.hi - r.lo) * 10;
+    }
+    if (nt) {
+        KB_LAUNCH(ctx, "k_decode_lcp", kbytes,
+                  (k_decode_lcp<<<nt, 256, smem, ctx->stream>>>(ctx->st, d_reqs, d_tiles, mode, d_meta, d_agg)));
+        KB_LAUNCH(ctx, "k_emit", R.n_records * 8,
+                  (k_emit<false><<<nt, 256, 0, ctx->stream>>>(ctx->st, d_reqs, d_tiles, d_agg, d_meta, d_tgt, d_tail,
+                                                             d_tcnt)));
+    }
+    KB_LAUNCH(ctx, "k_tile_scan", (uint64_t)nt * 32,
+              (k_tile_scan<<<1, 256, 0, ctx->stream>>>(d_reqs, (uint32_t)nreq, d_tcnt, d_tscan, nt, d_rout)));
+    if (nt && out_mode != KB_OUT_COUNT) {
+        KB_LAUNCH(ctx, "k_place", R.n_records * 4,
+                  (k_place<<<nt, 256, 0, ctx->stream>>>(ctx->st, d_reqs, d_tiles, d_tgt, d_tail, d_tscan,
+                                                        (uint32_t *)ctx->d_sel.p, (uint64_t *)ctx->d_slot.p, d_rout)));
+    }
+    KB_CUDA(ctx, cudaGetLastError());
+    std::vector<ReqOut> rout(std::max<uint64_t>(nreq, 1));
+    if (nreq) {
+        KB_TRY(hbuf_ensure(ctx, ctx->h_stage, nreq * sizeof(ReqOut) + 64));
+        KB_CUDA(ctx, cudaMemcpyAsync(ctx->h_stage.p, d_rout, nreq * sizeof(ReqOut), cudaMemcpyDeviceToHost,
+                                     ctx->stream));
+    }
+    KB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (nreq) memcpy(rout.data(), ctx->h_stage.p, nreq * sizeof(ReqOut));
+
+    kb_result *res = kb_result_new(1, out_mode);
+    res->req_first.resize(nreq + 1);
+    res->req_count.resize(nreq);
+    res->req_examined.resize(nreq);
+    std::vector<uint64_t> arena_base(nreq + 1), job_first(nreq + 1);
+    uint64_t nk = 0, nbytes = 0;
+    for (uint64_t q = 0; q < nreq; q++) {
+        uint64_t ne = rout[q].total;
+        bool capped = R.reqs[q].limit > 0 && ne > (uint64_t)R.reqs[q].limit;
+        if (capped) ne = (uint64_t)R.reqs[q].limit;
+        res->req_first[q] = nk;
+        job_first[q] = nk;
+        arena_base[q] = nbytes;
+        if (out_mode == KB_OUT_COUNT) {
+            res->req_count[q] = rout[q].total;  // emptyResultReceiver never stops the loop
+            res->req_examined[q] = R.reqs[q].hi - R.reqs[q].lo;
+        } else {
+            res->req_count[q] = rout[q].limit_stop ? 0 : ne;  // (0, nil) when the limit stopped the loop (Q4)
+            res->req_examined[q] = rout[q].examined;
+            nk += ne;
+            nbytes += capped || R.reqs[q].limit > 0 ? rout[q].capped_aux : rout[q].total_aux;
+        }
+    }
+    res->req_first[nreq] = nk;
+    job_first[nreq] = nk;
+    arena_base[nreq] = nbytes;
+    res->n_kvs = nk;
+    res->n_bytes = nbytes;
+
+    if (out_mode != KB_OUT_COUNT && nk > 0) {
+        // metadata SoA on the device: rec_idx u32 | key_len u32 | val_len u32 | rev u64 | key_off u64 | val_off u64
+        const size_t meta_bytes = nk * (4 + 4 + 4 + 8 + 8 + 8) + 64;
+        DBuf d_om;
+        int rc = pool_get_dev(ctx, meta_bytes, &d_om);
+        if (rc == KB_OK) rc = pool_get_dev(ctx, nbytes + 16, &res->d_bytes);
+        if (rc == KB_OK) rc = dbuf_ensure(ctx, ctx->d_jobs, (nreq + 1) * 16);
+        if (rc == KB_OK) rc = hbuf_ensure(ctx, ctx->h_stage2, (nreq + 1) * 16 + 64);
+        if (rc != KB_OK) {
+            pool_put_dev(ctx, d_om);
+            kb_result_free(nullptr, res);
+            return rc;
+        }
+        uint64_t *hj = (uint64_t *)ctx->h_stage2.p;
+        memcpy(hj, job_first.data(), (nreq + 1) * 8);
+        memcpy(hj + nreq + 1, arena_base.data(), (nreq + 1) * 8);
+        cudaMemcpyAsync(ctx->d_jobs.p, hj, (nreq + 1) * 16, cudaMemcpyHostToDevice, ctx->stream);
+        uint8_t *om = (uint8_t *)d_om.p;
+        GatherOut go;
+        go.rev = (uint64_t *)om;
+        go.key_off = go.rev + nk;
+        go.val_off = go.key_off + nk;
+        go.rec_idx = (uint32_t *)(go.val_off + nk);
+        go.key_len = go.rec_idx + nk;
+        go.val_len = go.key_len + nk;
+        const unsigned ggrid = (unsigned)std::min<uint64_t>((nk + 7) / 8, 148 * 8);
+        KB_LAUNCH(ctx, "k_gather", 2 * nbytes + nk * 48,
+                  (k_gather<<<ggrid, 256, 0, ctx->stream>>>(
+                      ctx->st, d_reqs, (uint32_t)nreq, (const uint64_t *)ctx->d_jobs.p,
+                      (const uint64_t *)ctx->d_jobs.p + nreq + 1, nk, (const uint32_t *)ctx->d_sel.p,
+                      (const uint64_t *)ctx->d_slot.p, (uint4 *)res->d_bytes.p, go)));
+        rc = pool_get_host(ctx, meta_bytes, &res->h_meta);
+        if (rc == KB_OK && out_mode == KB_OUT_HOST) rc = pool_get_host(ctx, nbytes + 16, &res->h_bytes);
+        if (rc == KB_OK) {
+            cudaMemcpyAsync(res->h_meta.p, d_om.p, nk * 36, cudaMemcpyDeviceToHost, ctx->stream);
+            if (out_mode == KB_OUT_HOST)
+                cudaMemcpyAsync(res->h_bytes.p, res->d_bytes.p, nbytes, cudaMemcpyDeviceToHost, ctx->stream);
+        }
+        cudaError_t e = cudaStreamSynchronize(ctx->stream);
+        pool_put_dev(ctx, d_om);
+        if (rc == KB_OK && e != cudaSuccess) rc = kb_cuda_fail(ctx, e, "gather");
+        if (rc != KB_OK) {
+            kb_result_free(nullptr, res);
+            return rc;
+        }
+        uint8_t *hm = (uint8_t *)res->h_meta.p;
+        res->rev = (const uint64_t *)hm;
+        res->key_off = res->rev + nk;
+        res->val_off = res->key_off + nk;
+        res->rec_idx = (const uint32_t *)(res->val_off + nk);
+        res->key_len = res->rec_idx + nk;
+        res->val_len = res->key_len + nk;
+        if (out_mode == KB_OUT_HOST) {
+            pool_put_dev(ctx, res->d_bytes);
+            res->d_bytes = DBuf();
+        }
+    }
+    *out = res;
+    return KB_OK;
+}
+
+extern "C" int kb_range_view_get(const kb_result *res, kb_range_view *v)
+{
+    if (!res || !v || res->type != 1) return KB_EINVAL;
+    memset(v, 0, sizeof(*v));
+    v->n_req = res->req_count.size();
+    v->req_first = res->req_first.data();
+    v->req_count = res->req_count.data();
+    v->req_examined = res->req_examined.data();
+    v->n_kvs = res->n_kvs;
+    v->rec_idx = res->rec_idx;
+    v->rev = res->rev;
+    v->key_off = res->key_off;
+    v->key_len = res->key_len;
+    v->val_off = res->val_off;
+    v->val_len = res->val_len;
+    v->n_bytes = res->n_bytes;
+    v->on_device = res->out_mode == KB_OUT_DEVICE;
+    v->bytes = res->out_mode == KB_OUT_DEVICE ? (const uint8_t *)res->d_bytes.p : (const uint8_t *)res->h_bytes.p;
+    return KB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// compaction sweep
+// ------------------------------------------------------------------------------------------------
+extern "C" int kb_compact_sweep(kb_ctx *ctx, const uint8_t *start, uint64_t start_len, const uint8_t *end,
+                                uint64_t end_len, uint64_t rev, uint64_t timeout_rev, int support_ttl, int out_mode,
+                                kb_result **out)
+{
+    if (!ctx || !out) return KB_EINVAL;
+    if (out_mode != KB_OUT_HOST && out_mode != KB_OUT_DEVICE && out_mode != KB_OUT_COUNT) return KB_EINVAL;
+    *out = nullptr;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    if (!ctx->loaded) return kb_fail(ctx, KB_ESTATE, "no store loaded");
+    cudaSetDevice(ctx->device);
+    kb_range_req rq;
+    rq.start = start;
+    rq.start_len = start_len;
+    rq.end = end;
+    rq.end_len = end_len;
+    rq.read_rev = rev;
+    rq.limit = 0;
+    Resolved R;
+    KB_TRY(resolve_requests(ctx, &rq, 1, false, R));
+    KB_TRY(upload_layout(ctx, R));
+    const uint32_t nt = (uint32_t)R.tiles.size();
+    const ReqDev *d_reqs = (const ReqDev *)ctx->d_reqs.p;
+    const TileDev *d_tiles = (const TileDev *)ctx->d_tiles.p;
+    uint32_t *d_meta = (uint32_t *)ctx->d_meta.p;
+    uint32_t *d_tgt = (uint32_t *)ctx->d_tgt.p;
+    uint32_t *d_tail = d_tgt + std::max<uint64_t>(R.total_flat, 4);
+    uint2 *d_agg = (uint2 *)ctx->d_agg.p;
+    uint64_t *d_tcnt = (uint64_t *)ctx->d_tcnt.p;
+    uint64_t *d_tscan = (uint64_t *)ctx->d_tscan.p;
+    ReqOut *d_rout = (ReqOut *)ctx->d_reqout.p;
+    ScanMode mode;
+    mode.compact = 1;
+    mode.ttl_scan = (!support_ttl && timeout_rev != 0) ? 1 : 0;
+    mode.timeout_rev = timeout_rev;
+    mode.want_sel = out_mode != KB_OUT_COUNT;
+    const size_t smem = 8 * KB_WARP_STAGE_CHUNKS * 16;
+    KB_CUDA(ctx, cudaFuncSetAttribute(k_decode_lcp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    uint64_t kbytes = 0;
+    {
+        std::vector<uint32_t> &ko = host_koff16(ctx);
+        for (auto &r : R.reqs) kbytes += (uint64_t)(ko[r.hi] - ko[r.lo]) * 16 + (uint64_t)(r.hi - r.lo) * 10;
+    }
+    if (nt) {
+        KB_LAUNCH(ctx, "k_decode_lcp", kbytes,
+                  (k_decode_lcp<<<nt, 256, smem, ctx->stream>>>(ctx->st, d_reqs, d_tiles, mode, d_meta, d_agg)));
+        KB_LAUNCH(ctx, "k_emit_compact", R.n_records * 8,
+                  (k_emit<true><<<nt, 256, 0, ctx->stream>>>(ctx->st, d_reqs, d_tiles, d_agg, d_meta, d_tgt, d_tail,
+                                                            d_tcnt)));
+    }
+    KB_LAUNCH(ctx, "k_tile_scan", (uint64_t)nt * 32,
+              (k_tile_scan<<<1, 256, 0, ctx->stream>>>(d_reqs, 1u, d_tcnt, d_tscan, nt, d_rout)));
+    KB_TRY(hbuf_ensure(ctx, ctx->h_stage, sizeof(ReqOut) + 64));
+    KB_CUDA(ctx, cudaMemcpyAsync(ctx->h_stage.p, d_rout, sizeof(ReqOut), cudaMemcpyDeviceToHost, ctx->stream));
+    KB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ReqOut ro;
+    memcpy(&ro, ctx->h_stage.p, sizeof(ro));
+
+    // scan(compact=true) blindly stores the compact revision (checkCompactRace, scanner.go:596-604)
+    ctx->compact_present = true;
+    ctx->compact_rev = rev;
+
+    kb_result *res = kb_result_new(2, out_mode);
+    res->n_victims = ro.total;
+    res->count = ro.total_aux;
+    res->examined = R.reqs[0].hi - R.reqs[0].lo;
+    if (out_mode != KB_OUT_COUNT && ro.total > 0) {
+        const uint64_t nv = ro.total;
+        int rc = pool_get_dev(ctx, nv * 5 + 64, &res->d_vic);
+        if (rc != KB_OK) {
+            kb_result_free(nullptr, res);
+            return rc;
+        }
+        uint32_t *vidx = (uint32_t *)res->d_vic.p;
+        uint8_t *vcls = (uint8_t *)(vidx + nv);
+        // sel_base of the single request is 0
+        KB_LAUNCH(ctx, "k_place_victims", R.n_records * 8 + nv * 5,
+                  (k_place_victims<<<nt, 256, 0, ctx->stream>>>(d_reqs, d_tiles, d_meta, d_tgt, d_tscan, vidx, vcls)));
+        if (out_mode == KB_OUT_HOST) {
+            rc = pool_get_host(ctx, nv * 5 + 64, &res->h_vic);
+            if (rc == KB_OK) cudaMemcpyAsync(res->h_vic.p, res->d_vic.p, nv * 5, cudaMemcpyDeviceToHost, ctx->stream);
+        }
+        cudaError_t e = cudaStreamSynchronize(ctx->stream);
+        if (rc == KB_OK && e != cudaSuccess) rc = kb_cuda_fail(ctx, e, "compact sweep");
+        if (rc != KB_OK) {
+            kb_result_free(nullptr, res);
+            return rc;
+        }
+        if (out_mode == KB_OUT_HOST) {
+            pool_put_dev(ctx, res->d_vic);
+            res->d_vic = DBuf();
+        }
+    }
+    *out = res;
+    return KB_OK;
+}
+
+extern "C" int kb_compact_view_get(const kb_result *res, kb_compact_view *v)
+{
+    if (!res || !v || res->type != 2) return KB_EINVAL;
+    memset(v, 0, sizeof(*v));
+    v->n_victims = res->n_victims;
+    v->count = res->count;
+    v->examined = res->examined;
+    v->on_device = res->out_mode == KB_OUT_DEVICE;
+    const uint8_t *base = v->on_device ? (const uint8_t *)res->d_vic.p : (const uint8_t *)res->h_vic.p;
+    if (base && res->out_mode != KB_OUT_COUNT) {
+        v->victim_idx = (const uint32_t *)base;
+        v->victim_class = base + res->n_victims * 4;
+    }
+    return KB_OK;
+}
+

@@ -1,0 +1,695 @@
+// kb_watch.cu -- watch fan-out: one revision-ordered event slab x every registered watcher's
+// (key-prefix, min-revision) predicate -> per-watcher ordered delivery lists.
+//
+// Replaces (reference file:line):
+//   WatcherHub.Stream broadcast           pkg/backend/watcherhub.go:78-92   (every batch handed to every watcher)
+//   processEvents / filterByRevision /    pkg/backend/watch.go:119-159      (per watcher: strip leading events below
+//   filterByPrefix                                                           min_rev, keep bytes.HasPrefix matches)
+//
+// Brute force is W x E prefix tests (1e9 for 10k watchers x 100k events).  Here watchers are grouped by
+// distinct prefix; an event probes a device hash table once per DISTINCT PREFIX LENGTH with the FNV-1a
+// hash of its own leading bytes (verified byte-exactly), so the work is O(E * #lengths + deliveries):
+//   k_batch_pm       per collector batch: running max of Event.Revision (the "leading strip" predicate becomes
+//                    pm[i] >= min_rev) + a flag "revisions globally non-decreasing"
+//   k_match<COUNT>   per event: matched groups -> per-group counts
+//   (scan)           group segment offsets
+//   k_match<SCATTER> per event: event index appended to each matched group's segment (unordered)
+//   k_sort_small / k_sort_big  every segment sorted ascending (warp rank-sort / shared-memory bitmap)
+//   k_expand<COUNT>  per watcher: deliveries = its group's segment filtered by min_rev
+//   (scan)           per-watcher output offsets
+//   k_expand<WRITE>  per watcher: ordered event indices
+#include <algorithm>
+#include <map>
+#include <unordered_map>
+
+#include "kb_internal.cuh"
+
+struct kb_events_dev {
+    DBuf keys;       // n x stride bytes: the first `stride` bytes of every event key (zero padded)
+    DBuf klen;       // n x u32 true key lengths
+    DBuf rev;        // n x u64
+    DBuf batch_off;  // (nb+1) x u64
+    uint32_t n = 0, nb = 0, stride = 0;
+};
+
+struct WatchTablesDev {
+    uint32_t n_ids = 0, n_groups = 0, n_lens = 0, table_size = 0, max_len = 0;
+    DBuf gprefix, goff16, glen, ghash, gstart, gmember, wgroup, wminrev, lens, table;
+    // per-call scratch
+    DBuf gcnt, gbase, gfill, seg, seg_sorted, big, pm, flag, wcnt, wstart, total;
+};
+
+namespace {
+
+constexpr unsigned FULL = 0xffffffffu;
+constexpr uint64_t FNV_OFFSET = 14695981039346656037ull;
+constexpr uint64_t FNV_PRIME = 1099511628211ull;
+
+__host__ __device__ __forceinline__ uint32_t slot_of(uint64_t h, uint32_t len, uint32_t mask)
+{
+    uint64_t m = h ^ ((uint64_t)len * 0x9E3779B97F4A7C15ull);
+    m ^= m >> 29;
+    return (uint32_t)(m ^ (m >> 32)) & mask;
+}
+
+struct EvDev {
+    const uint4 *keys;
+    const uint32_t *klen;
+    const uint64_t *rev;
+    const uint64_t *batch_off;
+    uint32_t n, nb, stride16;
+};
+
+struct TabDev {
+    const uint4 *gprefix;
+    const uint32_t *goff16, *glen;
+    const uint64_t *ghash;
+    const uint32_t *gstart, *gmember, *wgroup;
+    const uint64_t *wminrev;
+    const uint32_t *lens;
+    const uint32_t *table;
+    uint32_t n_ids, n_groups, n_lens, mask, max_len;
+};
+
+// ---- running max of the revisions inside each collector batch (filterByRevision strips only the LEADING
+//      events below min_rev, watch.go:153-159, so event i survives iff max(rev[batch start..i]) >= min_rev)
+__global__ void __launch_bounds__(128) k_batch_pm(EvDev ev, uint64_t *__restrict__ pm, uint32_t *__restrict__ nonmono)
+{
+    const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (w >= ev.nb) return;
+    const uint64_t lo = ev.batch_off[w], hi = ev.batch_off[w + 1];
+    uint64_t carry = 0;
+    bool bad = false;
+    for (uint64_t c = lo; c < hi; c += 32) {
+        const uint64_t i = c + lane;
+        uint64_t v = i < hi ? ev.rev[i] : 0;
+        if (i < hi && i > 0 && ev.rev[i - 1] > v) bad = true;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint64_t o = __shfl_up_sync(FULL, v, d);
+            if (lane >= (unsigned)d) v = max(v, o);
+        }
+        v = max(v, carry);
+        if (i < hi) pm[i] = v;
+        carry = __shfl_sync(FULL, v, 31);
+    }
+    if (__any_sync(FULL, bad) && lane == 0) atomicOr(nonmono, 1u);
+}
+
+// ---- per event: which prefix groups does its key start with?
+template <bool SCATTER>
+__global__ void __launch_bounds__(256)
+k_match(EvDev ev, TabDev tb, uint32_t *__restrict__ gcnt, const uint32_t *__restrict__ gbase,
+        uint32_t *__restrict__ gfill, uint32_t *__restrict__ seg)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ev.n) return;
+    const uint32_t klen = ev.klen[i];
+    const uint4 *kp = ev.keys + (uint64_t)i * ev.stride16;
+    uint64_t h = FNV_OFFSET;
+    uint32_t li = 0;
+    uint32_t pos = 0;  // bytes hashed so far
+    uint4 chunk = make_uint4(0, 0, 0, 0);
+    while (li < tb.n_lens) {
+        const uint32_t L = tb.lens[li];
+        if (L > klen) break;  // longer prefixes cannot match a shorter key
+        while (pos < L) {
+            if ((pos & 15) == 0) chunk = kp[pos >> 4];
+            h = (h ^ (uint64_t)byte_of(chunk, pos & 15)) * FNV_PRIME;
+            pos++;
+        }
+        // probe (hash, length); verify the bytes so the result is exact
+        uint32_t s = slot_of(h, L, tb.mask);
+        for (;;) {
+            const uint32_t g = tb.table[s];
+            if (g == KB_NONE) break;
+            if (tb.ghash[g] == h && tb.glen[g] == L) {
+                const uint4 *gp = tb.gprefix + tb.goff16[g];
+                bool eq = true;
+                for (uint32_t c = 0; c * 16 < L && eq; c++) {
+                    uint4 a = kp[c], b = gp[c];
+                    int p = first_diff16(a, b);
+                    if (p < 16 && c * 16 + p < L) eq = false;
+                }
+                if (eq) {
+                    if (SCATTER) {
+                        const uint32_t at = gbase[g] + atomicAdd(&gfill[g], 1u);
+                        seg[at] = i;
+                    } else {
+                        atomicAdd(&gcnt[g], 1u);
+                    }
+                    break;  // prefixes are unique per group
+                }
+            }
+            s = (s + 1) & tb.mask;
+        }
+        li++;
+    }
+}
+
+// ---- segment sort: ascending event index per group
+__global__ void __launch_bounds__(256)
+k_sort_small(uint32_t n_groups, const uint32_t *__restrict__ gcnt, const uint32_t *__restrict__ gbase,
+             const uint32_t *__restrict__ seg, uint32_t *__restrict__ sorted, uint32_t *__restrict__ big /* [0]=count */)
+{
+    const uint32_t g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (g >= n_groups) return;
+    const uint32_t n = gcnt[g];
+    if (n == 0) return;
+    if (n > 32) {
+        if (lane == 0) big[1 + atomicAdd(&big[0], 1u)] = g;
+        return;
+    }
+    const uint32_t base = gbase[g];
+    const uint32_t v = lane < n ? seg[base + lane] : 0xFFFFFFFFu;
+    uint32_t rank = 0;
+#pragma unroll
+    for (int j = 0; j < 32; j++) {
+        const uint32_t o = __shfl_sync(FULL, v, j);
+        rank += (o < v) ? 1u : 0u;  // event indices inside one group are distinct
+    }
+    if (lane < n) sorted[base + rank] = v;
+}
+
+constexpr uint32_t BM_WORDS = 8192;  // 262144 event indices per window (32 KiB of shared memory)
+
+__global__ void __launch_bounds__(256)
+k_sort_big(const uint32_t *__restrict__ big, const uint32_t *__restrict__ gcnt, const uint32_t *__restrict__ gbase,
+           const uint32_t *__restrict__ seg, uint32_t *__restrict__ sorted)
+{
+    __shared__ uint32_t bm[BM_WORDS];
+    __shared__ uint32_t wsum[9];
+    __shared__ uint32_t red[2];
+    __shared__ uint32_t outpos_s;
+    const uint32_t nbig = big[0];
+    for (uint32_t bi = blockIdx.x; bi < nbig; bi += gridDim.x) {
+        const uint32_t g = big[1 + bi];
+        const uint32_t n = gcnt[g], base = gbase[g];
+        // min / max of the segment
+        if (threadIdx.x == 0) {
+            red[0] = 0xFFFFFFFFu;
+            red[1] = 0;
+            outpos_s = 0;
+        }
+        __syncthreads();
+        uint32_t mn = 0xFFFFFFFFu, mx = 0;
+        for (uint32_t j = threadIdx.x; j < n; j += blockDim.x) {
+            const uint32_t v = seg[base + j];
+            mn = min(mn, v);
+            mx = max(mx, v);
+        }
+        atomicMin(&red[0], mn);
+        atomicMax(&red[1], mx);
+        __syncthreads();
+        mn = red[0];
+        mx = red[1];
+        for (uint64_t w0 = mn & ~31u; w0 <= mx; w0 += (uint64_t)BM_WORDS * 32) {
+            const uint64_t need_words = ((uint64_t)mx - w0) / 32 + 1;
+            const uint32_t nwords = need_words < BM_WORDS ? (uint32_t)need_words : BM_WORDS;
+            for (uint32_t j = threadIdx.x; j < nwords; j += blockDim.x) bm[j] = 0;
+            __syncthreads();
+            for (uint32_t j = threadIdx.x; j < n; j += blockDim.x) {
+                const uint64_t v = seg[base + j];
+                if (v >= w0 && v < w0 + (uint64_t)nwords * 32) {
+                    const uint32_t d = (uint32_t)(v - w0);
+                    atomicOr(&bm[d >> 5], 1u << (d & 31));
+                }
+            }
+            __syncthreads();
+            // ordered expansion of the bitmap: each thread owns a contiguous run of words
+            const uint32_t per = (nwords + blockDim.x - 1) / blockDim.x;
+            const uint32_t wlo = min(nwords, threadIdx.x * per), whi = min(nwords, wlo + per);
+            uint32_t cnt = 0;
+            for (uint32_t j = wlo; j < whi; j++) cnt += __popc(bm[j]);
+            // block exclusive scan of cnt
+            const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+            uint32_t inc = cnt;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                uint32_t o = __shfl_up_sync(FULL, inc, d);
+                if (lane >= (unsigned)d) inc += o;
+            }
+            if (lane == 31) wsum[wid] = inc;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                uint32_t run = 0;
+                for (int k = 0; k < 8; k++) {
+                    uint32_t x = wsum[k];
+                    wsum[k] = run;
+                    run += x;
+                }
+                wsum[8] = run;
+            }
+            __syncthreads();
+            uint32_t at = outpos_s + wsum[wid] + inc - cnt;
+            for (uint32_t j = wlo; j < whi; j++) {
+                uint32_t bits = bm[j];
+                while (bits) {
+                    const uint32_t b = __ffs(bits) - 1;
+                    bits &= bits - 1;
+                    sorted[base + at++] = (uint32_t)(w0 + (uint64_t)j * 32 + b);
+                }
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) outpos_s += wsum[8];
+            __syncthreads();
+        }
+    }
+}
+
+// ---- per watcher: its group's sorted segment filtered by pm[e] >= min_rev
+template <bool WRITE>
+__global__ void __launch_bounds__(256)
+k_expand(TabDev tb, const uint32_t *__restrict__ gcnt, const uint32_t *__restrict__ gbase,
+         const uint32_t *__restrict__ sorted, const uint64_t *__restrict__ pm, const uint32_t *__restrict__ nonmono,
+         uint64_t *__restrict__ wcnt, const uint64_t *__restrict__ wstart, uint32_t *__restrict__ out)
+{
+    const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (w >= tb.n_ids) return;
+    const uint32_t g = tb.wgroup[w];
+    if (g == KB_NONE) {
+        if (!WRITE && lane == 0) wcnt[w] = 0;
+        return;
+    }
+    const uint32_t n = gcnt[g];
+    const uint32_t *M = sorted + gbase[g];
+    const uint64_t mr = tb.wminrev[w];
+    if (*nonmono == 0) {
+        // revisions non-decreasing over the whole slab: the survivors are a suffix of the segment
+        uint32_t lo = 0, hi = n;
+        while (lo < hi) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (pm[M[mid]] >= mr) hi = mid; else lo = mid + 1;
+        }
+        if (!WRITE) {
+            if (lane == 0) wcnt[w] = n - lo;
+        } else {
+            const uint64_t o = wstart[w];
+            for (uint32_t j = lo + lane; j < n; j += 32) out[o + (j - lo)] = M[j];
+        }
+        return;
+    }
+    uint64_t total = 0;
+    const uint64_t o = WRITE ? wstart[w] : 0;
+    for (uint32_t c = 0; c < n; c += 32) {
+        const uint32_t j = c + lane;
+        const uint32_t e = j < n ? M[j] : 0;
+        const bool keep = j < n && pm[e] >= mr;
+        const unsigned m = __ballot_sync(FULL, keep);
+        if (WRITE && keep) out[o + total + __popc(m & ((1u << lane) - 1))] = e;
+        total += __popc(m);
+    }
+    if (!WRITE && lane == 0) wcnt[w] = total;
+}
+
+uint64_t fnv1a(const std::string &s)
+{
+    uint64_t h = FNV_OFFSET;
+    for (unsigned char c : s) h = (h ^ c) * FNV_PRIME;
+    return h;
+}
+
+int upload(kb_ctx *ctx, DBuf &b, const void *src, size_t bytes)
+{
+    KB_TRY(dbuf_ensure(ctx, b, std::max<size_t>(bytes, 16)));
+    if (bytes) KB_CUDA(ctx, cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return KB_OK;
+}
+
+// rebuild the device tables after kb_watch_add / kb_watch_del
+int rebuild_tables(kb_ctx *ctx)
+{
+    if (!ctx->wt) ctx->wt = new WatchTablesDev();
+    WatchTablesDev &T = *ctx->wt;
+    const uint32_t n_ids = (uint32_t)ctx->watchers.size();
+    std::map<std::string, std::vector<uint32_t>> groups;  // ordered: deterministic group ids
+    for (uint32_t w = 0; w < n_ids; w++)
+        if (ctx->watchers[w].live) groups[ctx->watchers[w].prefix].push_back(w);
+    const uint32_t G = (uint32_t)groups.size();
+    std::vector<uint8_t> gprefix;
+    std::vector<uint32_t> goff16(G + 1), glen(G), gstart(G + 1), gmember, wgroup(std::max(n_ids, 1u), KB_NONE), lens;
+    std::vector<uint64_t> ghash(std::max(G, 1u)), wminrev(std::max(n_ids, 1u), 0);
+    uint32_t gi = 0, max_len = 0;
+    for (auto &kv : groups) {
+        const std::string &p = kv.first;
+        goff16[gi] = (uint32_t)(gprefix.size() / 16);
+        glen[gi] = (uint32_t)p.size();
+        ghash[gi] = fnv1a(p);
+        gprefix.insert(gprefix.end(), p.begin(), p.end());
+        gprefix.resize((gprefix.size() + 15) / 16 * 16 + 16, 0);
+        gstart[gi] = (uint32_t)gmember.size();
+        for (uint32_t w : kv.second) {
+            gmember.push_back(w);
+            wgroup[w] = gi;
+        }
+        lens.push_back((uint32_t)p.size());
+        max_len = std::max<uint32_t>(max_len, (uint32_t)p.size());
+        gi++;
+    }
+    goff16[G] = (uint32_t)(gprefix.size() / 16);
+    gstart[G] = (uint32_t)gmember.size();
+    for (uint32_t w = 0; w < n_ids; w++) wminrev[w] = ctx->watchers[w].min_rev;
+    std::sort(lens.begin(), lens.end());
+    lens.erase(std::unique(lens.begin(), lens.end()), lens.end());
+    uint32_t tsize = 16;
+    while (tsize < 2 * G + 2) tsize <<= 1;
+    std::vector<uint32_t> table(tsize, KB_NONE);
+    for (uint32_t g = 0; g < G; g++) {
+        uint32_t s = slot_of(ghash[g], glen[g], tsize - 1);
+        while (table[s] != KB_NONE) s = (s + 1) & (tsize - 1);
+        table[s] = g;
+    }
+    if (gprefix.empty()) gprefix.resize(16, 0);
+    KB_TRY(upload(ctx, T.gprefix, gprefix.data(), gprefix.size()));
+    KB_TRY(upload(ctx, T.goff16, goff16.data(), goff16.size() * 4));
+    KB_TRY(upload(ctx, T.glen, glen.data(), glen.size() * 4));
+    KB_TRY(upload(ctx, T.ghash, ghash.data(), ghash.size() * 8));
+    KB_TRY(upload(ctx, T.gstart, gstart.data(), gstart.size() * 4));
+    KB_TRY(upload(ctx, T.gmember, gmember.data(), gmember.size() * 4));
+    KB_TRY(upload(ctx, T.wgroup, wgroup.data(), wgroup.size() * 4));
+    KB_TRY(upload(ctx, T.wminrev, wminrev.data(), wminrev.size() * 8));
+    KB_TRY(upload(ctx, T.lens, lens.data(), lens.size() * 4));
+    KB_TRY(upload(ctx, T.table, table.data(), table.size() * 4));
+    KB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // the host vectors die here
+    T.n_ids = n_ids;
+    T.n_groups = G;
+    T.n_lens = (uint32_t)lens.size();
+    T.table_size = tsize;
+    T.max_len = max_len;
+    ctx->watch_dirty = false;
+    return KB_OK;
+}
+
+uint32_t needed_stride(kb_ctx *ctx)
+{
+    uint32_t max_len = 0;
+    for (auto &w : ctx->watchers)
+        if (w.live) max_len = std::max<uint32_t>(max_len, (uint32_t)w.prefix.size());
+    return std::max<uint32_t>(16, (max_len + 15) / 16 * 16);
+}
+
+int events_upload_locked(kb_ctx *ctx, const kb_events *ev, kb_events_dev *d)
+{
+    if (ev->n >= 0xFFFFFFF0ull) return kb_fail(ctx, KB_ELIMIT, "too many events");
+    const uint32_t n = (uint32_t)ev->n;
+    const uint32_t stride = needed_stride(ctx);
+    const uint32_t nb = ev->batch_off && ev->n_batches ? (uint32_t)ev->n_batches : 1;
+    // pinned staging: [keys n*stride][klen n*4][rev n*8][batch_off (nb+1)*8]
+    const size_t kbytes = (size_t)n * stride, total = kbytes + (size_t)n * 12 + (size_t)(nb + 1) * 8 + 64;
+    KB_TRY(hbuf_ensure(ctx, ctx->h_stage, total));
+    uint8_t *h = (uint8_t *)ctx->h_stage.p;
+    uint32_t *hl = (uint32_t *)(h + kbytes);
+    uint64_t *hr = (uint64_t *)(h + kbytes + (size_t)n * 4);
+    // keep 8-byte alignment for the u64 arrays
+    size_t rev_off = (kbytes + (size_t)n * 4 + 7) & ~(size_t)7;
+    hr = (uint64_t *)(h + rev_off);
+    uint64_t *hb = hr + n;
+    for (uint32_t i = 0; i < n; i++) {
+        const uint64_t o = ev->key_off[i], l = ev->key_off[i + 1] - o;
+        const uint32_t c = (uint32_t)std::min<uint64_t>(l, stride);
+        uint8_t *dst = h + (size_t)i * stride;
+        memcpy(dst, ev->keys + o, c);
+        if (c < stride) memset(dst + c, 0, stride - c);
+        hl[i] = (uint32_t)std::min<uint64_t>(l, 0xFFFFFFFFull);
+    }
+    if (n) memcpy(hr, ev->rev, (size_t)n * 8);
+    if (ev->batch_off && ev->n_batches) {
+        memcpy(hb, ev->batch_off, (size_t)(nb + 1) * 8);
+    } else {
+        hb[0] = 0;
+        hb[1] = n;
+    }
+    KB_TRY(dbuf_ensure(ctx, d->keys, std::max<size_t>(kbytes, 16)));
+    KB_TRY(dbuf_ensure(ctx, d->klen, std::max<size_t>((size_t)n * 4, 16)));
+    KB_TRY(dbuf_ensure(ctx, d->rev, std::max<size_t>((size_t)n * 8, 16)));
+    KB_TRY(dbuf_ensure(ctx, d->batch_off, (size_t)(nb + 1) * 8));
+    if (n) {
+        KB_CUDA(ctx, cudaMemcpyAsync(d->keys.p, h, kbytes, cudaMemcpyHostToDevice, ctx->stream));
+        KB_CUDA(ctx, cudaMemcpyAsync(d->klen.p, hl, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+        KB_CUDA(ctx, cudaMemcpyAsync(d->rev.p, hr, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    KB_CUDA(ctx, cudaMemcpyAsync(d->batch_off.p, hb, (size_t)(nb + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    d->n = n;
+    d->nb = nb;
+    d->stride = stride;
+    return KB_OK;
+}
+
+void events_release(kb_events_dev *d)
+{
+    if (d->keys.p) cudaFree(d->keys.p);
+    if (d->klen.p) cudaFree(d->klen.p);
+    if (d->rev.p) cudaFree(d->rev.p);
+    if (d->batch_off.p) cudaFree(d->batch_off.p);
+    d->keys = d->klen = d->rev = d->batch_off = DBuf();
+}
+
+}  // namespace
+
+void watch_tables_free(kb_ctx *ctx)
+{
+    if (!ctx->wt) return;
+    WatchTablesDev &T = *ctx->wt;
+    DBuf *all[] = {&T.gprefix, &T.goff16, &T.glen, &T.ghash, &T.gstart, &T.gmember, &T.wgroup, &T.wminrev,
+                   &T.lens, &T.table, &T.gcnt, &T.gbase, &T.gfill, &T.seg, &T.seg_sorted, &T.big, &T.pm,
+                   &T.flag, &T.wcnt, &T.wstart, &T.total};
+    for (DBuf *b : all)
+        if (b->p) cudaFree(b->p);
+    delete ctx->wt;
+    ctx->wt = nullptr;
+    if (ctx->ev_scratch) {
+        events_release(ctx->ev_scratch);
+        delete ctx->ev_scratch;
+        ctx->ev_scratch = nullptr;
+    }
+}
+
+extern "C" int kb_watch_add(kb_ctx *ctx, const uint8_t *prefix, uint64_t prefix_len, uint64_t min_rev, uint32_t *id)
+{
+    if (!ctx || !id || (prefix_len && !prefix)) return KB_EINVAL;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    if (prefix_len > 65535) return kb_fail(ctx, KB_ELIMIT, "watch prefix longer than 65535 bytes");
+    Watcher w;
+    w.prefix.assign((const char *)prefix, (size_t)prefix_len);
+    w.min_rev = min_rev;
+    w.live = true;
+    ctx->watchers.push_back(w);
+    *id = (uint32_t)ctx->watchers.size() - 1;
+    ctx->watch_dirty = true;
+    return KB_OK;
+}
+
+extern "C" int kb_watch_del(kb_ctx *ctx, uint32_t id)
+{
+    if (!ctx) return KB_EINVAL;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    if (id >= ctx->watchers.size() || !ctx->watchers[id].live) return kb_fail(ctx, KB_EINVAL, "unknown watcher %u", id);
+    ctx->watchers[id].live = false;
+    ctx->watch_dirty = true;
+    return KB_OK;
+}
+
+extern "C" int kb_watch_count(kb_ctx *ctx, uint64_t *n)
+{
+    if (!ctx || !n) return KB_EINVAL;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    uint64_t c = 0;
+    for (auto &w : ctx->watchers) c += w.live ? 1 : 0;
+    *n = c;
+    return KB_OK;
+}
+
+extern "C" int kb_events_upload(kb_ctx *ctx, const kb_events *ev, kb_events_dev **out)
+{
+    if (!ctx || !ev || !out || (ev->n && (!ev->keys || !ev->key_off || !ev->rev))) return KB_EINVAL;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    cudaSetDevice(ctx->device);
+    kb_events_dev *d = new kb_events_dev();
+    int rc = events_upload_locked(ctx, ev, d);
+    if (rc == KB_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = kb_fail(ctx, KB_ECUDA, "event upload");
+    if (rc != KB_OK) {
+        events_release(d);
+        delete d;
+        return rc;
+    }
+    *out = d;
+    return KB_OK;
+}
+
+extern "C" void kb_events_free(kb_ctx *ctx, kb_events_dev *ev)
+{
+    if (!ev) return;
+    if (ctx) {
+        std::lock_guard<std::mutex> g(ctx->mu);
+        cudaSetDevice(ctx->device);
+        cudaStreamSynchronize(ctx->stream);
+        events_release(ev);
+    }
+    delete ev;
+}
+
+static int match_locked(kb_ctx *ctx, const kb_events_dev *d, int out_mode, kb_result **out)
+{
+    if (ctx->watch_dirty || !ctx->wt) KB_TRY(rebuild_tables(ctx));
+    WatchTablesDev &T = *ctx->wt;
+    if (d->stride < needed_stride(ctx))
+        return kb_fail(ctx, KB_ESTATE, "event slab was uploaded for shorter watcher prefixes (stride %u < %u); upload again",
+                       d->stride, needed_stride(ctx));
+    const uint32_t E = d->n, G = T.n_groups, W = T.n_ids;
+    const uint64_t seg_cap = std::max<uint64_t>((uint64_t)E * std::max(T.n_lens, 1u), 1);
+    if (seg_cap >= 0xFFFFFFF0ull) return kb_fail(ctx, KB_ELIMIT, "events x distinct prefix lengths exceeds 2^32");
+    KB_TRY(dbuf_ensure(ctx, T.gcnt, (size_t)(G + 1) * 4));
+    KB_TRY(dbuf_ensure(ctx, T.gbase, (size_t)(G + 1) * 4));
+    KB_TRY(dbuf_ensure(ctx, T.gfill, (size_t)(G + 1) * 4));
+    KB_TRY(dbuf_ensure(ctx, T.seg, seg_cap * 4));
+    KB_TRY(dbuf_ensure(ctx, T.seg_sorted, seg_cap * 4));
+    KB_TRY(dbuf_ensure(ctx, T.big, (size_t)(G + 2) * 4));
+    KB_TRY(dbuf_ensure(ctx, T.pm, std::max<size_t>((size_t)E * 8, 16)));
+    KB_TRY(dbuf_ensure(ctx, T.flag, 16));
+    KB_TRY(dbuf_ensure(ctx, T.wcnt, (size_t)(W + 1) * 8));
+    KB_TRY(dbuf_ensure(ctx, T.wstart, (size_t)(W + 2) * 8));
+    KB_TRY(dbuf_ensure(ctx, T.total, 16));
+
+    EvDev ev;
+    ev.keys = (const uint4 *)d->keys.p;
+    ev.klen = (const uint32_t *)d->klen.p;
+    ev.rev = (const uint64_t *)d->rev.p;
+    ev.batch_off = (const uint64_t *)d->batch_off.p;
+    ev.n = E;
+    ev.nb = d->nb;
+    ev.stride16 = d->stride / 16;
+    TabDev tb;
+    tb.gprefix = (const uint4 *)T.gprefix.p;
+    tb.goff16 = (const uint32_t *)T.goff16.p;
+    tb.glen = (const uint32_t *)T.glen.p;
+    tb.ghash = (const uint64_t *)T.ghash.p;
+    tb.gstart = (const uint32_t *)T.gstart.p;
+    tb.gmember = (const uint32_t *)T.gmember.p;
+    tb.wgroup = (const uint32_t *)T.wgroup.p;
+    tb.wminrev = (const uint64_t *)T.wminrev.p;
+    tb.lens = (const uint32_t *)T.lens.p;
+    tb.table = (const uint32_t *)T.table.p;
+    tb.n_ids = W;
+    tb.n_groups = G;
+    tb.n_lens = T.n_lens;
+    tb.mask = T.table_size - 1;
+    tb.max_len = T.max_len;
+
+    uint32_t *gcnt = (uint32_t *)T.gcnt.p, *gbase = (uint32_t *)T.gbase.p, *gfill = (uint32_t *)T.gfill.p;
+    uint32_t *seg = (uint32_t *)T.seg.p, *sorted = (uint32_t *)T.seg_sorted.p, *big = (uint32_t *)T.big.p;
+    uint64_t *pm = (uint64_t *)T.pm.p;
+    uint32_t *flag = (uint32_t *)T.flag.p;
+    uint64_t *wcnt = (uint64_t *)T.wcnt.p, *wstart = (uint64_t *)T.wstart.p, *total = (uint64_t *)T.total.p;
+
+    KB_CUDA(ctx, cudaMemsetAsync(gcnt, 0, (size_t)(G + 1) * 4, ctx->stream));
+    KB_CUDA(ctx, cudaMemsetAsync(gfill, 0, (size_t)(G + 1) * 4, ctx->stream));
+    KB_CUDA(ctx, cudaMemsetAsync(big, 0, 4, ctx->stream));
+    KB_CUDA(ctx, cudaMemsetAsync(flag, 0, 4, ctx->stream));
+    const uint64_t ev_bytes = (uint64_t)E * (d->stride + 4);
+    if (E && W) {
+        KB_LAUNCH(ctx, "k_batch_pm", (uint64_t)E * 16,
+                  (k_batch_pm<<<(d->nb * 32 + 127) / 128, 128, 0, ctx->stream>>>(ev, pm, flag)));
+        if (G) {
+            KB_LAUNCH(ctx, "k_match_count", ev_bytes,
+                      (k_match<false><<<(E + 255) / 256, 256, 0, ctx->stream>>>(ev, tb, gcnt, gbase, gfill, seg)));
+        }
+    }
+    KB_TRY(scan_exclusive_u32(ctx, gcnt, gbase, G, nullptr));
+    if (E && W && G) {
+        KB_LAUNCH(ctx, "k_match_scatter", ev_bytes,
+                  (k_match<true><<<(E + 255) / 256, 256, 0, ctx->stream>>>(ev, tb, gcnt, gbase, gfill, seg)));
+        KB_LAUNCH(ctx, "k_sort_small", (uint64_t)G * 8,
+                  (k_sort_small<<<(G * 32 + 255) / 256, 256, 0, ctx->stream>>>(G, gcnt, gbase, seg, sorted, big)));
+        KB_LAUNCH(ctx, "k_sort_big", 0, (k_sort_big<<<148 * 2, 256, 0, ctx->stream>>>(big, gcnt, gbase, seg, sorted)));
+    }
+    if (W) {
+        KB_LAUNCH(ctx, "k_expand_count", (uint64_t)W * 24,
+                  (k_expand<false><<<(W * 32 + 255) / 256, 256, 0, ctx->stream>>>(tb, gcnt, gbase, sorted, pm, flag,
+                                                                               wcnt, wstart, nullptr)));
+    }
+    KB_TRY(scan_exclusive_u64(ctx, wcnt, wstart, W, total));
+    uint64_t D = 0;
+    KB_TRY(hbuf_ensure(ctx, ctx->h_stage2, 64));
+    KB_CUDA(ctx, cudaMemcpyAsync(ctx->h_stage2.p, total, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    KB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    D = *(uint64_t *)ctx->h_stage2.p;
+
+    // output: [start (W+1) x u64][event_idx D x u32]
+    const size_t out_bytes = (size_t)(W + 1) * 8 + D * 4 + 16;
+    DBuf d_out;
+    KB_TRY(pool_get_dev(ctx, out_bytes, &d_out));
+    uint64_t *o_start = (uint64_t *)d_out.p;
+    uint32_t *o_idx = (uint32_t *)(o_start + W + 1);
+    cudaMemcpyAsync(o_start, wstart, (size_t)W * 8, cudaMemcpyDeviceToDevice, ctx->stream);
+    cudaMemcpyAsync(o_start + W, total, 8, cudaMemcpyDeviceToDevice, ctx->stream);
+    if (W && D) {
+        KB_LAUNCH(ctx, "k_expand_write", D * 8,
+                  (k_expand<true><<<(W * 32 + 255) / 256, 256, 0, ctx->stream>>>(tb, gcnt, gbase, sorted, pm, flag, wcnt,
+                                                                              wstart, o_idx)));
+    }
+    HBuf h_out;
+    int rc = KB_OK;
+    if (out_mode == KB_OUT_HOST) {
+        rc = pool_get_host(ctx, out_bytes, &h_out);
+        if (rc == KB_OK)
+            cudaMemcpyAsync(h_out.p, d_out.p, (size_t)(W + 1) * 8 + D * 4, cudaMemcpyDeviceToHost, ctx->stream);
+    } else {
+        // the offsets are always readable on the host
+        rc = pool_get_host(ctx, (size_t)(W + 1) * 8 + 16, &h_out);
+        if (rc == KB_OK) cudaMemcpyAsync(h_out.p, d_out.p, (size_t)(W + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream);
+    }
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (rc == KB_OK && e != cudaSuccess) rc = kb_cuda_fail(ctx, e, "watch match");
+    if (rc != KB_OK) {
+        pool_put_dev(ctx, d_out);
+        pool_put_host(ctx, h_out);
+        return rc;
+    }
+    kb_result *res = kb_result_new(3, out_mode);
+    if (out_mode == KB_OUT_HOST) {
+        pool_put_dev(ctx, d_out);
+        d_out = DBuf();
+    }
+    res->n_watchers = W;
+    res->n_deliveries = D;
+    res->h_match = h_out;
+    res->d_match = d_out;
+    *out = res;
+    return KB_OK;
+}
+
+extern "C" int kb_watch_match_dev(kb_ctx *ctx, const kb_events_dev *ev, int out_mode, kb_result **out)
+{
+    if (!ctx || !ev || !out || (out_mode != KB_OUT_HOST && out_mode != KB_OUT_DEVICE)) return KB_EINVAL;
+    *out = nullptr;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    cudaSetDevice(ctx->device);
+    return match_locked(ctx, ev, out_mode, out);
+}
+
+extern "C" int kb_watch_match(kb_ctx *ctx, const kb_events *ev, int out_mode, kb_result **out)
+{
+    if (!ctx || !ev || !out || (out_mode != KB_OUT_HOST && out_mode != KB_OUT_DEVICE)) return KB_EINVAL;
+    if (ev->n && (!ev->keys || !ev->key_off || !ev->rev)) return KB_EINVAL;
+    *out = nullptr;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    cudaSetDevice(ctx->device);
+    if (!ctx->ev_scratch) ctx->ev_scratch = new kb_events_dev();
+    KB_TRY(events_upload_locked(ctx, ev, ctx->ev_scratch));
+    return match_locked(ctx, ctx->ev_scratch, out_mode, out);
+}
+
+extern "C" int kb_match_view_get(const kb_result *res, kb_match_view *v)
+{
+    if (!res || !v || res->type != 3) return KB_EINVAL;
+    memset(v, 0, sizeof(*v));
+    v->n_watchers = res->n_watchers;
+    v->n_deliveries = res->n_deliveries;
+    v->on_device = res->out_mode == KB_OUT_DEVICE;
+    v->start = (const uint64_t *)res->h_match.p;  // offsets are always host readable
+    if (v->on_device)
+        v->event_idx = (const uint32_t *)((const uint64_t *)res->d_match.p + res->n_watchers + 1);
+    else
+        v->event_idx = (const uint32_t *)((const uint64_t *)res->h_match.p + res->n_watchers + 1);
+    return KB_OK;
+}
