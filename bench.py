@@ -1,0 +1,416 @@
+#!/usr/bin/env python
+"""bench.py -- range-scan + watch-fanout throughput of the B200 path (and of the reference CPU path).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+One STEP = one pass of the hot path over one batch of synthetic input (BASELINE.json configs[1]+[2]):
+  * scan   : one full-range unlimited Range (RangeStream shape) + Q=256 namespace List requests (limit 10 001) on
+             a 1M-record snapshot (200k objects x [1 revision record + 4 versions], 256 B keys, 2 KB values,
+             5 % tombstoned, read revision = 90th percentile);
+  * fan-out: a 100k-event burst (334 collector batches of <= 300) against 10k watchers
+             (9 984 namespace prefixes + 16 cluster-wide);
+  * at N > 1 every rank owns the namespaces that fnv1a64(prefix) maps to it (weak scaling: ~1M records, ~10k
+    watchers, ~100k events per GPU) and the step starts with ONE ncclAllGather of the per-shard revision cursor.
+Unit of work ("event") = one stored MVCC record examined by a scan, or one watch event matched against the whole
+watcher set.  `value` = events/s with inputs resident in HBM; `e2e` = the same through the C-ABI with HOST buffers
+(host->device and device->host copies inside the timed region).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from kubebrain_b200 import synth  # noqa: E402
+from kubebrain_b200.coder import NormalCoder, prefix_end  # noqa: E402
+from kubebrain_b200.packed import PackedEvents, PackedWatchers, Slab  # noqa: E402
+
+CODER = NormalCoder()
+METRIC = "range-scan + watch-fanout events/sec"
+FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
+
+N_OBJECTS, VERSIONS, LU, LV = 200_000, 4, 256, 2048
+NS_STORE, NS_EVENTS, N_NS_WATCH, N_CLUSTER_WATCH, N_EVENTS, Q_LISTS = 1000, 11_000, 9984, 16, 100_000, 256
+BURST_START = 2_000_000
+
+
+ns_shard = synth.ns_shard
+
+
+def build_workload(rank: int, world: int):
+    """per-rank shard of the synthetic: store, list requests, watchers, event burst"""
+    t0 = time.time()
+    store, meta = synth.gen_store(N_OBJECTS * world, VERSIONS, LU, LV, NS_STORE * world, config_id=2,
+                                  shard=(rank, world) if world > 1 else None)
+    lo, hi = CODER.encode_object_key(b"/registry/", 0), CODER.encode_object_key(b"/registry0", 0)
+    reqs = [(lo, hi, meta.read_rev, 0)]
+    owned = np.nonzero(ns_shard(np.arange(NS_STORE * world), world) == rank)[0]
+    resn = [b"pods", b"configmaps", b"secrets", b"services", b"deployments", b"events"]
+    for i in range(Q_LISTS):
+        p = b"/registry/" + resn[i % 6] + b"/ns-%05d/" % int(owned[(i * 7) % len(owned)])
+        reqs.append((CODER.encode_object_key(p, 0), CODER.encode_object_key(prefix_end(p), 0), meta.read_rev, 10001))
+    # watchers: namespace watchers of the namespaces this rank owns + the cluster-wide ones (replicated)
+    w_all = synth.gen_watchers(N_NS_WATCH * world, N_CLUSTER_WATCH, BURST_START, BURST_START + N_EVENTS // 2)
+    ns_ids = np.arange(N_NS_WATCH * world)
+    keep = np.concatenate([ns_shard(ns_ids, world) == rank, np.ones(N_CLUSTER_WATCH, dtype=bool)])
+    idx = np.nonzero(keep)[0]
+    watchers = PackedWatchers(w_all.prefixes.take(idx), w_all.min_rev[idx])
+    # events: the burst routed by the same hash
+    ev_all = synth.gen_events(N_EVENTS * world, LU, NS_EVENTS * world, BURST_START)
+    if world > 1:
+        ev_ns = np.array([int(ev_all.keys.data[int(o) + 18 : int(o) + 23].tobytes()) for o in ev_all.keys.off[:-1]])
+        sel = np.nonzero(ns_shard(ev_ns, world) == rank)[0]
+        mat = ev_all.keys.data.reshape(-1, LU)[sel]
+        n = len(sel)
+        ev = PackedEvents(Slab.from_fixed(mat), ev_all.rev[sel],
+                          np.array(list(range(0, n, 300)) + [n], dtype=np.uint64))
+    else:
+        ev = ev_all
+    return dict(store=store, meta=meta, reqs=reqs, watchers=watchers, events=ev, gen_s=time.time() - t0)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)"""
+
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.p = None
+        self.path = f"/tmp/kb_clocks_{os.getpid()}.csv"
+
+    def start(self):
+        try:
+            self.f = open(self.path, "w")
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.FIELDS}",
+                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        if not self.p:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.close()
+        sm, mx, reasons = [], [], set()
+        for line in open(self.path):
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1]))
+                mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        try:
+            os.unlink(self.path)
+        except OSError:
+            pass
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            for k in ("hbm_gbs", "hbm_gb_s", "hbm_copy_gbs"):
+                if k in d:
+                    return float(d[k]), "measured"
+        except Exception:
+            pass
+    return FALLBACK_HBM_GBS, "fallback"
+
+
+def ncu_traffic(kernel: str):
+    """dram bytes per launch of the dominant kernel from the committed ncu --set full capture, if any"""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get(kernel)
+        except Exception:
+            return None
+    return None
+
+
+# ---------------------------------------------------------------------------------------------------------
+# reference arm: the reference's own CPU implementation of the path (C restatement, all host threads)
+# ---------------------------------------------------------------------------------------------------------
+def cpu_step(ost, wl, threads: int, faithful: bool = True):
+    from oracle import binding as ko
+
+    examined = 0
+    s, e, rev, lim = wl["reqs"][0]
+    n, ex, _ = ko.bench_scan(ost, s, e, rev, 0, faithful, threads)
+    examined += ex
+    emitted = n
+    for s, e, rev, lim in wl["reqs"][1:]:
+        n, ex, _ = ko.bench_scan(ost, s, e, rev, lim, faithful, 1)
+        examined += ex
+        emitted += n
+    start, idx, msgs = ko.fanout(wl["events"], wl["watchers"], threads=threads, alloc_per_batch=True)
+    return examined, emitted, len(idx)
+
+
+def run_reference(args, rank: int, world: int):
+    if rank != 0:
+        return
+    from oracle import binding as ko
+
+    wl = build_workload(0, 1)
+    ost = ko.OracleStore(wl["store"])
+    threads = os.cpu_count() or 1
+    for _ in range(max(args.warmup, 1)):
+        cpu_step(ost, wl, threads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        examined, emitted, deliveries = cpu_step(ost, wl, threads)
+    dt = (time.perf_counter() - t0) / args.steps
+    events = examined + wl["events"].n
+    # context: the badger shape (single partition => the full scan is one goroutine) and the zero-copy variant
+    t1 = time.perf_counter()
+    s, e, rev, _ = wl["reqs"][0]
+    ko.bench_scan(ost, s, e, rev, 0, True, 1)
+    badger_scan_s = time.perf_counter() - t1
+    t1 = time.perf_counter()
+    ko.bench_scan(ost, s, e, rev, 0, False, threads)
+    zero_copy_s = time.perf_counter() - t1
+    value = events / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "events/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": workload_config(1, wl),
+        "cpu_baseline": {
+            "value": value, "unit": "events/s", "cores": threads, "kind": "port",
+            "sample": "full step: 1 unlimited Range over 1M records partition-parallel on all cores WITH the badger "
+                      "iterator's per-record copies (KeyCopy + 2x ValueCopy) + 256 List(limit 10001) + 100k-event "
+                      "burst x 10k watchers (watchers sharded over all cores, per-batch allocation)",
+            "badger_single_partition_scan_s": badger_scan_s, "zero_copy_all_cores_scan_s": zero_copy_s,
+        },
+        "e2e": {"value": value, "unit": "events/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(world: int, wl):
+    return {
+        "workload": "configs[1]+[2]: 1M MVCC records/GPU (256B key, 2KB val), 1 full Range + 256 List(limit 10001), "
+                    "100k-event burst x 10k watchers/GPU",
+        "records_per_gpu": int(wl["store"].n), "list_requests": Q_LISTS, "watchers_per_gpu": int(wl["watchers"].n),
+        "events_per_gpu": int(wl["events"].n), "read_rev": int(wl["meta"].read_rev),
+        "parallelism": f"hash-shard x{world}" if world > 1 else "single GPU",
+        "l2": "inputs larger than L2 (>= 0.7 GB streamed from HBM per step)",
+        "unit_of_work": "records examined + events matched",
+    }
+
+
+# ---------------------------------------------------------------------------------------------------------
+# B200 arm
+# ---------------------------------------------------------------------------------------------------------
+def run_b200(args, rank: int, local_rank: int, world: int):
+    import torch
+
+    from kubebrain_b200._lib import KB_OUT_DEVICE, KB_OUT_HOST, Engine
+
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    wl = build_workload(rank, world)
+    eng = Engine(local_rank)
+    eng.load_sorted(wl["store"])
+    eng.watch_add_many(wl["watchers"])
+    # the revision-cursor communicator (one uint64 per rank)
+    uid = Engine.nccl_unique_id() if rank == 0 else bytes(128)
+    if world > 1:
+        t = torch.tensor(list(uid), dtype=torch.uint8, device="cuda")
+        dist.broadcast(t, 0)
+        uid = bytes(t.cpu().tolist())
+    eng.nccl_init(uid, rank, world)
+    evh = eng.events_upload(wl["events"])
+    stream = torch.cuda.ExternalStream(eng.stream())
+    reqs = wl["reqs"]
+    local_rev = int(wl["meta"].last_rev)
+
+    def step_device():
+        _, readable = eng.cursor_allgather(local_rev)
+        r = eng.range_batch(reqs, KB_OUT_DEVICE)
+        ex = int(r.req_examined.sum())
+        nk = r.n_kvs
+        r.close()
+        m = eng.watch_match_dev(evh, KB_OUT_DEVICE)
+        d = m.n_deliveries
+        m.close()
+        return ex, nk, d
+
+    def step_e2e():
+        _, readable = eng.cursor_allgather(local_rev)
+        r = eng.range_batch(reqs, KB_OUT_HOST)
+        ex = int(r.req_examined.sum())
+        nbytes = r.n_bytes + r.n_kvs * 36
+        checksum = int(r.arena[:: max(1, r.n_bytes // 4096)].sum()) if r.n_bytes else 0  # the host reads the result
+        r.close()
+        m = eng.watch_match(wl["events"], KB_OUT_HOST)
+        d = m.n_deliveries
+        dbytes = d * 4 + (m.n_watchers + 1) * 8
+        m.close()
+        return ex, nbytes + dbytes, checksum
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        t0 = time.perf_counter()
+        out = None
+        for _ in range(steps):
+            out = fn()
+        b.record(stream)
+        barrier()
+        wall = time.perf_counter() - t0
+        dev_ms = a.elapsed_time(b)
+        if dist is not None:
+            t = torch.tensor([dev_ms, wall * 1e3], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dev_ms, wall = float(t[0]), float(t[1]) / 1e3
+        return dev_ms, wall, out
+
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+        step_e2e()
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    eng.prof_reset()
+    eng.prof_enable(True)
+    l0 = eng.launch_count()
+    dev_ms, wall_s, (examined, n_kvs, deliveries) = timed(step_device, args.steps)
+    launches = eng.launch_count() - l0
+    eng.prof_enable(False)
+    prof = eng.prof_read()
+    e2e_ms, e2e_wall, (examined2, d2h_bytes, _) = timed(step_e2e, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+
+    events_local = examined + wl["events"].n
+    if dist is not None:
+        t = torch.tensor([events_local, launches], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        events_total, launches_total = float(t[0]), int(t[1])
+    else:
+        events_total, launches_total = float(events_local), int(launches)
+    ms_per_step = dev_ms / args.steps
+    value = events_total / (ms_per_step / 1e3)
+    e2e_value = events_total / (e2e_ms / args.steps / 1e3)
+    h2d_bytes = wl["events"].n * (32 + 12) + len(reqs) * 2 * 300
+
+    if rank == 0:
+        peak, peak_src = measured_hbm_peak()
+        kern = []
+        for p in prof:
+            if p["launches"] == 0:
+                continue
+            ms = p["total_ms"] / p["launches"]
+            per_launch = p["alg_bytes"] / p["launches"]
+            kern.append({"name": p["name"], "launches_per_step": p["launches"] / args.steps, "avg_us": ms * 1e3,
+                         "alg_bytes_per_launch": per_launch,
+                         "achieved_gbs": (per_launch / 1e9) / (ms / 1e3) if ms > 0 else None,
+                         "share": p["total_ms"] / max(dev_ms, 1e-9)})
+        kern.sort(key=lambda k: -k["share"])
+        dom = kern[0] if kern else None
+        roof = None
+        if dom:
+            roof = {"kernel": dom["name"], "bound": "hbm", "achieved": dom["achieved_gbs"], "peak": peak,
+                    "peak_source": peak_src, "unit": "GB/s", "frac": dom["achieved_gbs"] / peak,
+                    "traffic": ncu_traffic(dom["name"]), "share_of_step": dom["share"]}
+        line = {
+            "metric": METRIC, "value": value, "unit": "events/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": workload_config(world, wl),
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "events/s", "h2d_bytes_per_step": int(h2d_bytes),
+                    "d2h_bytes_per_step": int(d2h_bytes), "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": launches_total,
+            "roofline": roof,
+            "kernels": kern,
+            "scan_records_per_step": int(examined), "emitted_kvs_per_step": int(n_kvs),
+            "fanout_events_per_step": int(wl["events"].n), "deliveries_per_step": int(deliveries),
+            "wall_ms_per_step": wall_s * 1e3 / args.steps, "gen_s": wl["gen_s"],
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(wl)
+        print(json.dumps(line), flush=True)
+    eng.events_free(evh)
+    eng.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def cpu_baseline(wl):
+    """the oracle port timed on this box's host cores on the same workload (bounded: 2 full steps)"""
+    from oracle import binding as ko
+
+    ost = ko.OracleStore(wl["store"])
+    threads = os.cpu_count() or 1
+    cpu_step(ost, wl, threads)
+    t0 = time.perf_counter()
+    reps = 2
+    for _ in range(reps):
+        examined, emitted, deliveries = cpu_step(ost, wl, threads)
+    dt = (time.perf_counter() - t0) / reps
+    return {"value": (examined + wl["events"].n) / dt, "unit": "events/s", "cores": threads, "kind": "port",
+            "sample": f"{reps} full steps (1M-record Range with badger-style per-record copies partition-parallel on "
+                      f"{threads} threads + 256 Lists + 100k events x 10k watchers on {threads} threads)",
+            "s_per_step": dt}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    run_b200(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -190,7 +190,10 @@ class RangeResult:
         self.key_len = _np(v.key_len, n, np.uint32)
         self.val_off = _np(v.val_off, n, np.uint64)
         self.val_len = _np(v.val_len, n, np.uint32)
-        self.arena = _np(v.bytes, self.n_bytes, np.uint8) if (not self.on_device and v.bytes) else None
+        if self.on_device:
+            self.arena = None
+        else:
+            self.arena = _np(v.bytes, self.n_bytes, np.uint8) if v.bytes else np.zeros(0, np.uint8)
 
     def kvs(self, q: int = 0) -> List[Tuple[bytes, bytes, int]]:
         assert self.arena is not None, "results were left on the device"

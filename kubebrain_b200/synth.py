@@ -101,20 +101,44 @@ class StoreMeta:
     n_tombstoned: int
 
 
+def fnv1a64_rows(mat: np.ndarray) -> np.ndarray:
+    """FNV-1a 64 of every row of a uint8 matrix"""
+    h = np.full(mat.shape[0], 14695981039346656037, dtype=np.uint64)
+    with np.errstate(over="ignore"):
+        for j in range(mat.shape[1]):
+            h = (h ^ mat[:, j].astype(np.uint64)) * np.uint64(1099511628211)
+    return h
+
+
+def ns_shard(ns: np.ndarray, world: int) -> np.ndarray:
+    """shard of a namespace = fnv1a64("ns-%05d") mod G (hash of the object-key prefix)"""
+    if world <= 1:
+        return np.zeros(ns.shape[0], dtype=np.int64)
+    return (fnv1a64_rows(_ns_digits(ns)) % np.uint64(world)).astype(np.int64)
+
+
 def gen_store(n_objects: int, versions: int, lu: int, lv: int, n_namespaces: int, config_id: int = 2,
               tomb_frac: float = 0.05, only_resource: Optional[bytes] = None,
-              first_rev: int = 1000) -> Tuple[PackedStore, StoreMeta]:
-    """n_objects * (1 + versions) records sorted by internal key."""
+              first_rev: int = 1000, shard: Optional[Tuple[int, int]] = None) -> Tuple[PackedStore, StoreMeta]:
+    """n_objects * (1 + versions) records sorted by internal key.  shard=(rank, world) keeps only the objects
+    whose namespace hashes to `rank` (revisions stay those of the global data set)."""
     seed = SEED ^ config_id
     res_idx = _pick_resources(seed, n_objects, 1, only_resource)
     ns = (_stream(seed, n_objects, 2) % np.uint64(n_namespaces)).astype(np.int64)
     uk = _user_keys(seed, n_objects, lu, n_namespaces, res_idx, ns, 3)
+    n_global = n_objects
+    global_idx = np.arange(n_objects, dtype=np.uint64)
+    tomb_all = (_stream(seed, n_objects, 4) % np.uint64(10000)) < np.uint64(int(tomb_frac * 10000))
+    if shard is not None and shard[1] > 1:
+        mine = np.nonzero(ns_shard(ns, shard[1]) == shard[0])[0]
+        uk, global_idx, tomb_all = uk[mine], global_idx[mine], tomb_all[mine]
+        n_objects = int(mine.shape[0])
     # unique + sorted user keys (fixed length, so user-key order == internal-key order)
     order = np.argsort(uk.view(f"S{lu}").reshape(-1), kind="stable")
     uk = uk[order]
     dup = np.nonzero((uk[1:] == uk[:-1]).all(axis=1))[0]
     assert dup.size == 0, "synthetic user keys collided; change the seed"
-    creation = order.astype(np.uint64)  # creation index of the object now at sorted position i
+    creation = global_idx[order]  # creation index (in the global data set) of the object now at sorted position i
 
     per = versions + 1
     n = n_objects * per
@@ -125,14 +149,13 @@ def gen_store(n_objects: int, versions: int, lu: int, lv: int, n_namespaces: int
     keys[:, :, 4 + lu] = 0x24
     # revisions: version v of the object created c-th gets first_rev + v*n_objects + c + 1
     vidx = np.arange(versions, dtype=np.uint64)
-    revs = np.uint64(first_rev) + vidx[None, :] * np.uint64(n_objects) + creation[:, None] + np.uint64(1)
+    revs = np.uint64(first_rev) + vidx[None, :] * np.uint64(n_global) + creation[:, None] + np.uint64(1)
     rev_all = np.zeros((n_objects, per), dtype=np.uint64)
     rev_all[:, 1:] = revs
     keys[:, :, 5 + lu :] = rev_all.astype(">u8").view(np.uint8).reshape(n_objects, per, 8)
     key_slab = Slab.from_fixed(keys.reshape(n, lk))
 
-    tomb = (_stream(seed, n_objects, 4) % np.uint64(10000)) < np.uint64(int(tomb_frac * 10000))
-    tomb = tomb[order]
+    tomb = tomb_all[order]
     # Values.  Per object: [revision record: BE64(latest) (+0x00 when deleted)] [v1] ... [v_last or "tombstone"].
     # Payload bytes come from a PCG64 raw stream seeded by splitmix64 (bit-stable across numpy versions).
     # Every object is first generated as a live row of A = 8 + versions*lv bytes; runs of consecutive live
@@ -167,8 +190,8 @@ def gen_store(n_objects: int, versions: int, lu: int, lv: int, n_namespaces: int
     del M2
     val_slab = Slab(vals, voff)
 
-    last_rev = first_rev + versions * n_objects
-    read_rev = first_rev + int(0.9 * versions * n_objects)
+    last_rev = first_rev + versions * n_global
+    read_rev = first_rev + int(0.9 * versions * n_global)
     meta = StoreMeta(n_objects, versions, lu, lv, first_rev, last_rev, read_rev, int(tomb.sum()))
     return PackedStore(key_slab, val_slab), meta
 
