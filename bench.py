@@ -312,13 +312,23 @@ def run_b200(args, rank: int, local_rank: int, world: int):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    # timed region: CUDA events bracket only the two HBM-bound kernels (level 2) so the event records do not
+    # perturb the step; a second, untimed pass with every kernel bracketed fills the per-kernel table
     eng.prof_reset()
-    eng.prof_enable(True)
+    eng.prof_enable(2)
     l0 = eng.launch_count()
     dev_ms, wall_s, (examined, n_kvs, deliveries) = timed(step_device, args.steps)
     launches = eng.launch_count() - l0
-    eng.prof_enable(False)
+    eng.prof_enable(0)
+    prof_major = {p["name"]: p for p in eng.prof_read()}
+    eng.prof_reset()
+    eng.prof_enable(1)
+    prof_ms, _, _ = timed(step_device, args.steps)
+    eng.prof_enable(0)
     prof = eng.prof_read()
+    for p in prof:  # the timed-region measurement wins for the kernels it covers
+        if p["name"] in prof_major:
+            p.update(prof_major[p["name"]])
     e2e_ms, e2e_wall, (examined2, d2h_bytes, _) = timed(step_e2e, args.steps)
     clocks = sampler.stop() if rank == 0 else None
 
@@ -345,7 +355,8 @@ def run_b200(args, rank: int, local_rank: int, world: int):
             kern.append({"name": p["name"], "launches_per_step": p["launches"] / args.steps, "avg_us": ms * 1e3,
                          "alg_bytes_per_launch": per_launch,
                          "achieved_gbs": (per_launch / 1e9) / (ms / 1e3) if ms > 0 else None,
-                         "share": p["total_ms"] / max(dev_ms, 1e-9)})
+                         "share": p["total_ms"] / max(dev_ms if p["name"] in prof_major else prof_ms, 1e-9),
+                         "timed_region": p["name"] in prof_major})
         kern.sort(key=lambda k: -k["share"])
         dom = kern[0] if kern else None
         roof = None

@@ -96,7 +96,7 @@ typedef struct kb_range_view {
     const uint32_t *val_len;
     const uint8_t  *bytes;      /* arena (host pinned for KB_OUT_HOST, device for KB_OUT_DEVICE)   */
     uint64_t n_bytes;
-    int on_device;              /* 1: bytes is a device pointer (metadata arrays are always host)  */
+    int on_device;              /* 1: bytes AND the per-kv arrays are device pointers (req_* stay host) */
 } kb_range_view;
 
 /* One call = one batch of independent scanner.Range requests answered on one snapshot. */
@@ -174,7 +174,7 @@ typedef struct kb_prof_entry {
     double   total_ms;
     uint64_t alg_bytes;   /* algorithmic bytes the launches were asked to move */
 } kb_prof_entry;
-int kb_prof_enable(kb_ctx *ctx, int on);
+int kb_prof_enable(kb_ctx *ctx, int on); /* 0 off, 1 every kernel, 2 only k_decode_lcp and k_gather */
 int kb_prof_reset(kb_ctx *ctx);
 int kb_prof_read(kb_ctx *ctx, kb_prof_entry *entries, int cap, int *n);
 uint64_t kb_launch_count(kb_ctx *ctx); /* kernels launched by this ctx since open */

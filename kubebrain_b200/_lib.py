@@ -184,15 +184,17 @@ class RangeResult:
         self.on_device = bool(v.on_device)
         self.bytes_ptr = v.bytes
         n = self.n_kvs
-        self.rec_idx = _np(v.rec_idx, n, np.uint32)
-        self.rev = _np(v.rev, n, np.uint64)
-        self.key_off = _np(v.key_off, n, np.uint64)
-        self.key_len = _np(v.key_len, n, np.uint32)
-        self.val_off = _np(v.val_off, n, np.uint64)
-        self.val_len = _np(v.val_len, n, np.uint32)
         if self.on_device:
+            # KB_OUT_DEVICE: the arena and the per-kv arrays stay in HBM (device pointers)
             self.arena = None
+            self.rec_idx = self.rev = self.key_off = self.key_len = self.val_off = self.val_len = None
         else:
+            self.rec_idx = _np(v.rec_idx, n, np.uint32)
+            self.rev = _np(v.rev, n, np.uint64)
+            self.key_off = _np(v.key_off, n, np.uint64)
+            self.key_len = _np(v.key_len, n, np.uint32)
+            self.val_off = _np(v.val_off, n, np.uint64)
+            self.val_len = _np(v.val_len, n, np.uint32)
             self.arena = _np(v.bytes, self.n_bytes, np.uint8) if v.bytes else np.zeros(0, np.uint8)
 
     def kvs(self, q: int = 0) -> List[Tuple[bytes, bytes, int]]:
@@ -403,8 +405,9 @@ class Engine:
     def sync(self):
         self._check(lib().kb_sync(self._ctx))
 
-    def prof_enable(self, on: bool):
-        self._check(lib().kb_prof_enable(self._ctx, int(on)))
+    def prof_enable(self, level: int):
+        """0 off, 1 every kernel, 2 only the two HBM-bound kernels"""
+        self._check(lib().kb_prof_enable(self._ctx, int(level)))
 
     def prof_reset(self):
         self._check(lib().kb_prof_reset(self._ctx))

@@ -169,7 +169,7 @@ extern "C" int kb_prof_enable(kb_ctx *ctx, int on)
     if (!ctx) return KB_EINVAL;
     std::lock_guard<std::mutex> g(ctx->mu);
     if (!on) prof_resolve(ctx);
-    ctx->prof_on = on != 0;
+    ctx->prof_on = on;
     return KB_OK;
 }
 
@@ -247,7 +247,7 @@ extern "C" void kb_close(kb_ctx *ctx)
     DBuf *all[] = {&ctx->d_kslab, &ctx->d_koff16, &ctx->d_klen, &ctx->d_vslab, &ctx->d_voff16, &ctx->d_vlen,
                    &ctx->d_bounds, &ctx->d_boff, &ctx->d_blen, &ctx->d_bres, &ctx->d_reqs, &ctx->d_tiles,
                    &ctx->d_meta, &ctx->d_tgt, &ctx->d_agg, &ctx->d_tcnt, &ctx->d_tscan, &ctx->d_reqout,
-                   &ctx->d_sel, &ctx->d_slot, &ctx->d_jobs, &ctx->d_scan_tmp, &ctx->d_flags, &ctx->d_cursor};
+                   &ctx->d_sel, &ctx->d_slot, &ctx->d_jobs, &ctx->d_gjobs, &ctx->d_scan_tmp, &ctx->d_flags, &ctx->d_cursor};
     for (DBuf *b : all) dfree(*b);
     for (auto &b : ctx->free_dev) cudaFree(b.p);
     for (auto &b : ctx->free_host) cudaFreeHost(b.p);
@@ -349,7 +349,7 @@ extern "C" int kb_load_sorted(kb_ctx *ctx, const uint8_t *keys, const uint64_t *
     ctx->key_bytes = kacc * 16;
     ctx->val_bytes = vacc * 16;
 
-    KB_TRY(dbuf_ensure(ctx, ctx->d_kslab, kacc * 16 + 16));
+    KB_TRY(dbuf_ensure(ctx, ctx->d_kslab, kacc * 16 + 64));
     KB_TRY(dbuf_ensure(ctx, ctx->d_vslab, vacc * 16 + 16));
     KB_TRY(dbuf_ensure(ctx, ctx->d_koff16, (n + 1) * 4));
     KB_TRY(dbuf_ensure(ctx, ctx->d_klen, (n + 1) * 2));

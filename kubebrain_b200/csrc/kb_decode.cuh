@@ -1,0 +1,272 @@
+// kb_decode.cuh -- k_decode_lcp: the HBM-bound pass of the scan (included by kb_scan.cu).
+//
+// Streams the raw internal keys of every examined record once (coalesced 16-byte transfers into a per-warp
+// shared-memory ring with cp.async, two stages deep so the next sub-tile is in flight while the current one is
+// decoded), and reduces each record to one 32-bit meta word:
+//   bits 0..15  LCP with the preceding key (common-prefix length, the input of the "same user key" test)
+//   bits 16..23 decode / visibility / tombstone / compaction-class flags (KB_M_*)
+// plus one (last PREVOK slot, min LCP after it) aggregate per 32-record sub-tile for the cross-tile carry.
+//
+// Replaces coder.Decode (pkg/backend/coder/normal.go:58-70) and the per-record front half of worker.run
+// (pkg/backend/scanner/scanner.go:430-453, 471-491, 566-591): decode, TTL expiry, revision visibility,
+// tombstone test, deleted-flag revision-record test.  Warps are persistent and fully independent (no CTA barrier).
+#pragma once
+
+#include "kb_internal.cuh"
+
+namespace {
+
+constexpr uint32_t MAGIC_LE = 0x8b80fb57u;  // bytes 57 fb 80 8b (coder/normal.go:26)
+constexpr int DECODE_WARPS = 12;
+constexpr int DECODE_STAGES = 2;
+
+__device__ __forceinline__ uint32_t bswap32(uint32_t x) { return __byte_perm(x, 0, 0x0123); }
+
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src)
+{
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait()
+{
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+__device__ __forceinline__ bool contains_events(const uint8_t *uk, uint32_t n)  // bytes.Contains(rawKey, "/events/")
+{
+    uint64_t w = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        w = (w << 8) | uk[i];
+        if (i >= 7 && w == 0x2f6576656e74732full) return true;
+    }
+    return false;
+}
+
+// everything a warp needs to know about one 32-record sub-tile; the global loads that fill it are issued two
+// iterations before it is processed
+struct SubDesc {
+    uint32_t valid;     // sub-tile exists
+    uint32_t sid;       // flat sub-tile id (= flat slot / 32)
+    uint32_t r0, nrec;  // first record, records in the sub-tile (0 for padding sub-tiles)
+    uint32_t lo;        // first record of the request (the LCP of that record is never used)
+    uint64_t read_rev;
+    // per lane
+    uint32_t ko, kl, vl;  // koff16[r], klen[r], vlen[r]
+    uint32_t pko, pkl;    // lane 0 only: koff16[r0-1], klen[r0-1] when r0 > lo
+};
+
+__device__ __forceinline__ SubDesc load_desc(const StoreDev &st, const ReqDev *__restrict__ reqs,
+                                             const TileDev *__restrict__ tiles, uint32_t sid, uint32_t n_sub,
+                                             uint32_t lane)
+{
+    SubDesc d;
+    d.valid = sid < n_sub;
+    d.sid = sid;
+    d.r0 = d.nrec = d.lo = 0;
+    d.read_rev = 0;
+    d.ko = d.kl = d.vl = d.pko = d.pkl = 0;
+    if (!d.valid) return d;
+    const TileDev tile = tiles[sid >> 5];
+    const uint32_t sub = sid & 31;
+    if (sub * 32 >= tile.n) return d;  // padding sub-tile of the request's last tile
+    d.r0 = tile.rec0 + sub * 32;
+    d.nrec = min(32u, tile.n - sub * 32);
+    d.lo = tile.lo;
+    d.read_rev = tile.read_rev;
+    if (lane < d.nrec) {
+        const uint32_t r = d.r0 + lane;
+        d.ko = st.koff16[r];
+        d.kl = st.klen[r];
+        d.vl = st.vlen[r];
+    }
+    if (lane == 0 && d.r0 > d.lo) {
+        d.pko = st.koff16[d.r0 - 1];
+        d.pkl = st.klen[d.r0 - 1];
+    }
+    return d;
+}
+
+// start the asynchronous copy of the sub-tile's key bytes (plus the record before it) into `buf`
+__device__ __forceinline__ void issue_stage(const StoreDev &st, const SubDesc &d, uint4 *buf, uint32_t lane)
+{
+    if (!d.valid || d.nrec == 0) return;
+    const bool halo = d.r0 > d.lo;
+    const uint32_t base16 = __shfl_sync(0xffffffffu, halo ? d.pko : d.ko, 0);
+    const uint32_t end16 = __shfl_sync(0xffffffffu, d.ko + ((d.kl + 15) >> 4), d.nrec - 1);
+    const uint32_t span = end16 - base16;
+    if (span <= KB_WARP_STAGE_CHUNKS) {
+        const uint4 *src = st.kslab + base16;
+        for (uint32_t c = lane; c < span; c += 32) cp_async16(buf + c, src + c);
+    }
+}
+
+template <bool STAGED>
+__device__ __forceinline__ uint32_t decode_record(const StoreDev &st, const ScanMode &mode, const SubDesc &d,
+                                                  const uint4 *kp, const uint4 *pp, uint32_t len, uint32_t plen,
+                                                  bool has_prev, uint32_t r)
+{
+    const uint8_t *kb = (const uint8_t *)kp;
+    uint32_t lcp = KB_LCP_INF;
+    if (has_prev) {
+        const uint32_t m = min(len, plen);
+        const uint32_t nch = (m + 15) >> 4;
+        lcp = m;
+        // four chunks per step; one OR-reduced difference word per chunk, one branch per step.  In the staged
+        // path the loads may run up to three chunks past the shorter key: shared memory is always readable and a
+        // difference found at or beyond m is clamped to m below.
+        for (uint32_t c0 = 0; c0 < nch; c0 += 4) {
+            uint4 x[4], y[4];
+            uint32_t dw[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const uint32_t c = STAGED ? c0 + j : min(c0 + j, nch - 1);
+                x[j] = kp[c];
+                y[j] = pp[c];
+            }
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                dw[j] = (x[j].x ^ y[j].x) | (x[j].y ^ y[j].y) | (x[j].z ^ y[j].z) | (x[j].w ^ y[j].w);
+            if (dw[0] | dw[1] | dw[2] | dw[3]) {
+                const int j = dw[0] ? 0 : dw[1] ? 1 : dw[2] ? 2 : 3;
+                const uint4 xa = j == 0 ? x[0] : j == 1 ? x[1] : j == 2 ? x[2] : x[3];
+                const uint4 ya = j == 0 ? y[0] : j == 1 ? y[1] : j == 2 ? y[2] : y[3];
+                lcp = min(m, (c0 + j) * 16 + (uint32_t)first_diff16(xa, ya));
+                break;
+            }
+        }
+    }
+    uint32_t flags = 0;
+    // coder.Decode (normal.go:58-70); keys shorter than 13 bytes are undecodable (Go would panic)
+    bool dec_ok = len >= 13;
+    if (dec_ok) dec_ok = (((const uint32_t *)kp)[0] == MAGIC_LE) && (kb[len - 9] == 0x24);
+    if (dec_ok) {
+        uint64_t rev;
+        if (STAGED) {
+            // the 8 revision bytes sit at an arbitrary offset: two aligned 64-bit loads + funnel shift + byte swap
+            const uint32_t off = len - 8, sh = (off & 7) * 8;
+            const uint64_t *w = (const uint64_t *)(kb + (off & ~7u));
+            const uint64_t lo = w[0], hi = w[1];
+            const uint64_t le = sh ? (lo >> sh) | (hi << (64 - sh)) : lo;
+            rev = ((uint64_t)bswap32((uint32_t)le) << 32) | bswap32((uint32_t)(le >> 32));
+        } else {
+            rev = be64_bytes(kb + len - 8);
+        }
+        flags |= KB_M_DEC_OK;
+        if (rev == 0) flags |= KB_M_REV0;
+        const uint32_t vl = d.vl;
+        uint4 v0 = make_uint4(0, 0, 0, 0);
+        if (vl >= 8 && (vl == 9 || (mode.ttl_scan && rev == 0))) v0 = st.vslab[st.voff16[r]];
+        const uint64_t vrev = ((uint64_t)bswap32(v0.x) << 32) | bswap32(v0.y);
+        bool expired = false;
+        if (mode.ttl_scan && contains_events(kb + 4, len - 13)) {  // compactIfExpired scanner.go:566-591
+            if (rev == 0) {
+                if (vl >= 8 && vrev <= mode.timeout_rev) {
+                    expired = true;
+                    flags |= KB_M_TTLREV;
+                }
+            } else if (rev <= mode.timeout_rev) {
+                expired = true;
+                flags |= KB_M_TTLOBJ;
+            }
+        }
+        if (!expired && rev <= d.read_rev) {  // scanner.go:451-453
+            flags |= KB_M_TRIG;
+            if (vl == 9 && v0.x == 0x626d6f74u && v0.y == 0x6e6f7473u && (v0.z & 0xffu) == 0x65u)
+                flags |= KB_M_TOMB;  // "tombstone" util.go:28
+            bool prevok = true;
+            if (mode.compact && rev == 0 && vl == 9) {  // scanner.go:476-491
+                if (vrev > d.read_rev)
+                    prevok = false;  // `continue` without updating prev (Q5)
+                else
+                    flags |= KB_M_REVDEL;
+            }
+            if (prevok) flags |= KB_M_PREVOK;
+        }
+    }
+    return lcp | flags;
+}
+
+__device__ __forceinline__ void process_sub(const StoreDev &st, const ScanMode &mode, const SubDesc &d,
+                                            const uint4 *buf, uint32_t lane, uint32_t *__restrict__ meta,
+                                            uint2 *__restrict__ sub_agg)
+{
+    const unsigned FULLM = 0xffffffffu;
+    if (d.nrec == 0) {
+        if (lane == 0) sub_agg[d.sid] = make_uint2(KB_NONE, KB_LCP_INF);
+        return;
+    }
+    const bool valid = lane < d.nrec;
+    const bool halo = d.r0 > d.lo;
+    const uint32_t base16 = __shfl_sync(FULLM, halo ? d.pko : d.ko, 0);
+    const uint32_t end16 = __shfl_sync(FULLM, d.ko + ((d.kl + 15) >> 4), d.nrec - 1);
+    const bool staged = (end16 - base16) <= KB_WARP_STAGE_CHUNKS;
+    // previous record's offset / length: lane-1, or the halo record for lane 0
+    uint32_t pko = __shfl_up_sync(FULLM, d.ko, 1), pkl = __shfl_up_sync(FULLM, d.kl, 1);
+    if (lane == 0) {
+        pko = d.pko;
+        pkl = d.pkl;
+    }
+    uint32_t word = KB_LCP_INF;
+    if (valid) {
+        const uint32_t r = d.r0 + lane;
+        const bool has_prev = r > d.lo;
+        if (staged) {
+            word = decode_record<true>(st, mode, d, buf + (d.ko - base16), buf + (has_prev ? pko - base16 : 0), d.kl, pkl,
+                                       has_prev, r);
+        } else {
+            word = decode_record<false>(st, mode, d, st.kslab + d.ko, st.kslab + (has_prev ? pko : d.ko), d.kl, pkl,
+                                        has_prev, r);
+        }
+        meta[d.sid * 32 + lane] = word;
+    }
+    // sub-tile aggregate: (last PREVOK slot, min LCP of the records after it)
+    const unsigned pm = __ballot_sync(FULLM, valid && (word & KB_M_PREVOK));
+    uint32_t mval = valid ? (word & KB_M_LCP_MASK) : KB_LCP_INF;
+    uint32_t L = KB_NONE;
+    if (pm) {
+        const uint32_t top = 31 - __clz(pm);
+        if (lane <= top) mval = KB_LCP_INF;
+        L = d.sid * 32 + top;
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) mval = min(mval, __shfl_xor_sync(FULLM, mval, s));
+    if (lane == 0) sub_agg[d.sid] = make_uint2(L, mval);
+}
+
+__global__ void __launch_bounds__(DECODE_WARPS * 32, 1)
+k_decode_lcp(StoreDev st, const ReqDev *__restrict__ reqs, const TileDev *__restrict__ tiles, uint32_t n_sub,
+             ScanMode mode, uint32_t *__restrict__ meta, uint2 *__restrict__ sub_agg)
+{
+    extern __shared__ uint4 stage[];  // DECODE_WARPS x DECODE_STAGES x KB_WARP_STAGE_CHUNKS (+ 4 chunks of slack)
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint4 *buf0 = stage + (size_t)warp * DECODE_STAGES * KB_WARP_STAGE_CHUNKS;
+    const uint32_t stride = gridDim.x * DECODE_WARPS;
+    uint32_t sid = blockIdx.x * DECODE_WARPS + warp;
+
+    // software pipeline: descriptor loads run two sub-tiles ahead, the key bytes one sub-tile ahead
+    SubDesc dB = load_desc(st, reqs, tiles, sid, n_sub, lane);
+    sid += stride;
+    SubDesc dA = load_desc(st, reqs, tiles, sid, n_sub, lane);
+    sid += stride;
+    issue_stage(st, dB, buf0, lane);
+    cp_async_commit();
+    uint32_t it = 0;
+    while (dB.valid) {
+        const SubDesc dC = dB;
+        dB = dA;
+        dA = load_desc(st, reqs, tiles, sid, n_sub, lane);
+        sid += stride;
+        issue_stage(st, dB, buf0 + ((it + 1) & 1) * KB_WARP_STAGE_CHUNKS, lane);
+        cp_async_commit();
+        cp_async_wait<1>();  // everything but the newest group has landed: dC's bytes are in shared memory
+        __syncwarp();
+        process_sub(st, mode, dC, buf0 + (it & 1) * KB_WARP_STAGE_CHUNKS, lane, meta, sub_agg);
+        __syncwarp();
+        it++;
+    }
+    cp_async_wait<0>();
+}
+
+}  // namespace

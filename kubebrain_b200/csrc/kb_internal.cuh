@@ -41,6 +41,9 @@ struct TileDev {
     uint32_t rec0;   // first store record of the tile
     uint32_t n;      // records in the tile (<= TILE)
     uint32_t flat0;  // flat slot of rec0
+    uint32_t lo;     // first record of the request (copy of ReqDev.lo: one load instead of two in the decode pass)
+    uint32_t pad;
+    uint64_t read_rev;
 };
 
 struct ScanMode {
@@ -64,7 +67,7 @@ struct ScanMode {
 #define KB_NONE       0xFFFFFFFFu
 
 #define KB_TILE       1024          // records per tile (256 threads x 4)
-#define KB_WARP_STAGE_CHUNKS 640    // 16-byte chunks of shared memory staged per warp (10 KiB)
+#define KB_WARP_STAGE_CHUNKS 576    // 16-byte chunks of shared memory per warp and stage (9 KiB: 33 keys of 272 B)
 
 // ------------------------------------------------------------------------------------------------
 // device helpers
@@ -162,7 +165,7 @@ struct kb_ctx {
 
     // scratch (grow only)
     DBuf d_bounds, d_boff, d_blen, d_bres, d_reqs, d_tiles, d_meta, d_tgt, d_agg, d_tcnt, d_tscan, d_reqout, d_sel,
-        d_slot, d_jobs, d_scan_tmp, d_flags;
+        d_slot, d_jobs, d_gjobs, d_scan_tmp, d_flags;
     HBuf h_stage, h_stage2;
 
     // buffer pools for results
@@ -181,7 +184,7 @@ struct kb_ctx {
     DBuf d_cursor;
 
     // profiling
-    bool prof_on = false;
+    int prof_on = 0;  // 0 off, 1 every kernel, 2 only the two HBM-bound kernels (k_decode_lcp, k_gather)
     std::vector<ProfEntry> prof;
     std::vector<ProfPending> prof_pending;
     std::vector<cudaEvent_t> ev_pool;
@@ -235,19 +238,21 @@ void pool_put_host(kb_ctx *ctx, HBuf b);
 
 // profiling: bracket a kernel launch with events when enabled
 int prof_index(kb_ctx *ctx, const char *name);
+static inline bool prof_major(const char *n) { return n[0] == 'k' && n[1] == '_' && ((n[2] == 'd' && n[3] == 'e') || (n[2] == 'g' && n[3] == 'a' && n[8] == 0)); }
 void prof_begin(kb_ctx *ctx, int idx, uint64_t alg_bytes);
 void prof_end(kb_ctx *ctx);
 
 #define KB_LAUNCH(ctx, name, bytes, ...)                      \
     do {                                                      \
         static thread_local int _pi = -1;                     \
-        if ((ctx)->prof_on) {                                 \
+        const bool _p = (ctx)->prof_on == 1 || ((ctx)->prof_on == 2 && prof_major(name)); \
+        if (_p) {                                             \
             _pi = prof_index((ctx), (name));                  \
             prof_begin((ctx), _pi, (bytes));                  \
         }                                                     \
         __VA_ARGS__;                                          \
         (ctx)->launches++;                                    \
-        if ((ctx)->prof_on) prof_end((ctx));                  \
+        if (_p) prof_end((ctx));                              \
     } while (0)
 
 // generic exclusive scans on the ctx stream (kb_scan_util.cu)

@@ -19,10 +19,11 @@
 #include <algorithm>
 
 #include "kb_internal.cuh"
+#include "kb_decode.cuh"
 
 namespace {
 
-constexpr uint32_t MAGIC_LE = 0x8b80fb57u;  // bytes 57 fb 80 8b (coder/normal.go:26)
+
 constexpr unsigned FULL = 0xffffffffu;
 
 // ------------------------------------------------------------------------------------------------
@@ -73,140 +74,6 @@ __global__ void __launch_bounds__(128) k_search(StoreDev st, const uint4 *__rest
     if (lane == 0) out[w] = lo;
 }
 
-// ------------------------------------------------------------------------------------------------
-// k_decode_lcp
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t bswap32(uint32_t x) { return __byte_perm(x, 0, 0x0123); }
-
-__device__ __forceinline__ bool contains_events(const uint8_t *uk, uint32_t n)  // bytes.Contains(rawKey, "/events/")
-{
-    uint64_t w = 0;
-    for (uint32_t i = 0; i < n; i++) {
-        w = (w << 8) | uk[i];
-        if (i >= 7 && w == 0x2f6576656e74732full) return true;
-    }
-    return false;
-}
-
-__global__ void __launch_bounds__(256, 2)
-k_decode_lcp(StoreDev st, const ReqDev *__restrict__ reqs, const TileDev *__restrict__ tiles, ScanMode mode,
-             uint32_t *__restrict__ meta, uint2 *__restrict__ tile_agg)
-{
-    extern __shared__ uint4 stage[];  // 8 warps x KB_WARP_STAGE_CHUNKS
-    __shared__ uint2 sub_agg[32];
-    const TileDev tile = tiles[blockIdx.x];
-    const ReqDev req = reqs[tile.req];
-    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint4 *ws = stage + warp * KB_WARP_STAGE_CHUNKS;
-    const uint32_t nsub = (tile.n + 31) >> 5;
-
-    for (uint32_t sub = warp; sub < nsub; sub += 8) {
-        const uint32_t r0 = tile.rec0 + sub * 32;
-        const uint32_t nrec = min(32u, tile.n - sub * 32);
-        const bool valid = lane < nrec;
-        const uint32_t r = r0 + (valid ? lane : 0);
-        const bool halo = r0 > req.lo;  // the record before the sub-tile is needed for the first LCP
-        const uint32_t base16 = st.koff16[halo ? r0 - 1 : r0];
-        const uint32_t span = st.koff16[r0 + nrec] - base16;
-        const bool staged = span <= KB_WARP_STAGE_CHUNKS;
-        if (staged) {
-            const uint4 *src = st.kslab + base16;
-            for (uint32_t c = lane; c < span; c += 32) ws[c] = ldg_stream(src + c);
-        }
-        __syncwarp();
-
-        uint32_t word = KB_LCP_INF;
-        if (valid) {
-            const uint32_t o16 = st.koff16[r];
-            const uint32_t len = st.klen[r];
-            const uint4 *kp = staged ? (const uint4 *)(ws + (o16 - base16)) : st.kslab + o16;
-            const uint8_t *kb = (const uint8_t *)kp;
-            uint32_t lcp = KB_LCP_INF;
-            if (r > req.lo) {
-                const uint32_t po16 = st.koff16[r - 1];
-                const uint32_t plen = st.klen[r - 1];
-                const uint4 *pp = staged ? (const uint4 *)(ws + (po16 - base16)) : st.kslab + po16;
-                const uint32_t m = min(len, plen);
-                lcp = m;
-                for (uint32_t c = 0; c * 16 < m; c++) {
-                    uint4 x = kp[c], y = pp[c];
-                    int p = first_diff16(x, y);
-                    if (p < 16) {
-                        lcp = min(m, c * 16 + (uint32_t)p);
-                        break;
-                    }
-                }
-            }
-            uint32_t flags = 0;
-            // coder.Decode (normal.go:58-70); keys shorter than 13 bytes are undecodable (Go would panic)
-            bool dec_ok = len >= 13;
-            if (dec_ok) dec_ok = (((const uint32_t *)kp)[0] == MAGIC_LE) && (kb[len - 9] == 0x24);
-            if (dec_ok) {
-                const uint64_t rev = be64_bytes(kb + len - 8);
-                flags |= KB_M_DEC_OK;
-                if (rev == 0) flags |= KB_M_REV0;
-                const uint32_t vl = st.vlen[r];
-                uint4 v0 = make_uint4(0, 0, 0, 0);
-                if (vl >= 8 && (vl == 9 || (mode.ttl_scan && rev == 0))) v0 = st.vslab[st.voff16[r]];
-                const uint64_t vrev = ((uint64_t)bswap32(v0.x) << 32) | bswap32(v0.y);
-                bool expired = false;
-                if (mode.ttl_scan && contains_events(kb + 4, len - 13)) {  // compactIfExpired scanner.go:566-591
-                    if (rev == 0) {
-                        if (vl >= 8 && vrev <= mode.timeout_rev) {
-                            expired = true;
-                            flags |= KB_M_TTLREV;
-                        }
-                    } else if (rev <= mode.timeout_rev) {
-                        expired = true;
-                        flags |= KB_M_TTLOBJ;
-                    }
-                }
-                if (!expired && rev <= req.read_rev) {  // scanner.go:451-453
-                    flags |= KB_M_TRIG;
-                    if (vl == 9 && v0.x == 0x626d6f74u && v0.y == 0x6e6f7473u && (v0.z & 0xffu) == 0x65u)
-                        flags |= KB_M_TOMB;  // "tombstone" util.go:28
-                    bool prevok = true;
-                    if (mode.compact && rev == 0 && vl == 9) {  // scanner.go:476-491
-                        if (vrev > req.read_rev)
-                            prevok = false;  // `continue` without updating prev (Q5)
-                        else
-                            flags |= KB_M_REVDEL;
-                    }
-                    if (prevok) flags |= KB_M_PREVOK;
-                }
-            }
-            word = lcp | flags;
-            meta[tile.flat0 + sub * 32 + lane] = word;
-        }
-        // sub-tile aggregate: (last PREVOK slot, min LCP of the records after it)
-        const unsigned pm = __ballot_sync(FULL, valid && (word & KB_M_PREVOK));
-        uint32_t mval = valid ? (word & KB_M_LCP_MASK) : KB_LCP_INF;
-        uint32_t L = KB_NONE;
-        if (pm) {
-            const uint32_t top = 31 - __clz(pm);
-            if (lane <= top) mval = KB_LCP_INF;
-            L = tile.flat0 + sub * 32 + top;
-        }
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) mval = min(mval, __shfl_xor_sync(FULL, mval, d));
-        if (lane == 0) sub_agg[sub] = make_uint2(L, mval);
-        __syncwarp();
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        uint32_t L = KB_NONE, m = KB_LCP_INF;
-        for (uint32_t s = 0; s < nsub; s++) {
-            uint2 a = sub_agg[s];
-            if (a.x != KB_NONE) {
-                L = a.x;
-                m = a.y;
-            } else {
-                m = min(m, a.y);
-            }
-        }
-        tile_agg[blockIdx.x] = make_uint2(L, m);
-    }
-}
 
 // ------------------------------------------------------------------------------------------------
 // block-wide exclusive scan of the (last-prev slot, min-LCP-since) state
@@ -309,7 +176,7 @@ __device__ __forceinline__ void block_excl_scan2(uint64_t a, uint64_t b, uint64_
 template <bool COMPACT>
 __global__ void __launch_bounds__(256)
 k_emit(StoreDev st, const ReqDev *__restrict__ reqs, const TileDev *__restrict__ tiles,
-       const uint2 *__restrict__ tile_agg, const uint32_t *__restrict__ meta, uint32_t *__restrict__ tgt,
+       const uint2 *__restrict__ sub_agg, const uint32_t *__restrict__ meta, uint32_t *__restrict__ tgt,
        uint32_t *__restrict__ tail_tgt, uint64_t *__restrict__ tcnt)
 {
     __shared__ LM warp_tot[8];
@@ -321,8 +188,9 @@ k_emit(StoreDev st, const ReqDev *__restrict__ reqs, const TileDev *__restrict__
         LM c;
         c.L = KB_NONE;
         c.m = KB_LCP_INF;
-        for (uint32_t t = blockIdx.x; t-- > req.tile0;) {
-            uint2 a = tile_agg[t];
+        // carry-in: walk the 32-record sub-tile aggregates of this request backwards until one holds a PREVOK
+        for (uint32_t t = tile.flat0 >> 5; t-- > (req.flat0 >> 5);) {
+            uint2 a = sub_agg[t];
             c.m = min(c.m, a.y);
             if (a.x != KB_NONE) {
                 c.L = a.x;
@@ -617,50 +485,79 @@ struct GatherOut {
     uint32_t *val_len;
 };
 
+// one copy job per emitted kv (32 bytes): built thread-parallel so the per-kv lookups (request search, selection,
+// offsets, lengths) do not sit in front of the streaming copy
+struct GatherJob {
+    uint64_t dst16;   // arena chunk index
+    uint64_t vsrc16;  // value slab chunk index
+    uint32_t ksrc16;  // key slab chunk index
+    uint32_t nk, nv;  // 16-byte chunks of key / value
+    uint32_t kl;      // exact key length
+};
+
 __global__ void __launch_bounds__(256)
-k_gather(StoreDev st, const ReqDev *__restrict__ reqs, uint32_t nreq, const uint64_t *__restrict__ job_first,
-         const uint64_t *__restrict__ arena_base, uint64_t n_kvs, const uint32_t *__restrict__ sel,
-         const uint64_t *__restrict__ slot, uint4 *__restrict__ arena, GatherOut out)
+k_gather_jobs(StoreDev st, const ReqDev *__restrict__ reqs, uint32_t nreq, const uint64_t *__restrict__ job_first,
+              const uint64_t *__restrict__ arena_base, uint64_t n_kvs, const uint32_t *__restrict__ sel,
+              const uint64_t *__restrict__ slot, GatherJob *__restrict__ jobs, GatherOut out)
+{
+    const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_kvs) return;
+    uint32_t lo = 0, hi = nreq;  // request of kv k: last q with job_first[q] <= k
+    while (hi - lo > 1) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (job_first[mid] <= k) lo = mid; else hi = mid;
+    }
+    const uint32_t q = lo;
+    const uint64_t s = reqs[q].sel_base + (k - job_first[q]);
+    const uint32_t rec = sel[s];
+    const uint64_t dst_byte = arena_base[q] + slot[s];
+    const uint32_t kl = st.klen[rec], vl = st.vlen[rec];
+    GatherJob j;
+    j.dst16 = dst_byte >> 4;
+    j.vsrc16 = st.voff16[rec];
+    j.ksrc16 = st.koff16[rec];
+    j.nk = (kl + 15) >> 4;
+    j.nv = (vl + 15) >> 4;
+    j.kl = kl;
+    jobs[k] = j;
+    out.rec_idx[k] = rec;
+    out.key_off[k] = dst_byte + 4;
+    out.key_len[k] = kl - 13;
+    out.val_off[k] = dst_byte + (uint64_t)j.nk * 16;
+    out.val_len[k] = vl;
+}
+
+// one warp per emitted kv: [internal key, padded][value, padded] as one stream of 16-byte chunks,
+// 8 independent loads in flight per lane
+__global__ void __launch_bounds__(256)
+k_gather(StoreDev st, const GatherJob *__restrict__ jobs, uint64_t n_kvs, uint4 *__restrict__ arena,
+         uint64_t *__restrict__ out_rev)
 {
     const uint32_t lane = threadIdx.x & 31;
-    const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
-    for (uint64_t k = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; k < n_kvs; k += nwarps) {
-        // request of kv k: last q with job_first[q] <= k
-        uint32_t lo = 0, hi = nreq;
-        while (hi - lo > 1) {
-            uint32_t mid = (lo + hi) >> 1;
-            if (job_first[mid] <= k) lo = mid; else hi = mid;
+    const uint64_t k = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (k >= n_kvs) return;
+    const uint4 *jp = (const uint4 *)(jobs + k);
+    const uint4 j0 = __ldg(jp), j1 = __ldg(jp + 1);
+    const uint64_t dst16 = ((uint64_t)j0.y << 32) | j0.x, vsrc16 = ((uint64_t)j0.w << 32) | j0.z;
+    const uint32_t ksrc16 = j1.x, nk = j1.y, nv = j1.z, kl = j1.w;
+    const uint4 *ks = st.kslab + ksrc16;
+    const uint4 *vs = st.vslab + vsrc16;
+    uint4 *dst = arena + dst16;
+    const uint32_t n = nk + nv;
+    for (uint32_t c0 = lane; c0 < n; c0 += 32 * 8) {
+        uint4 v[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const uint32_t c = c0 + j * 32;
+            if (c < n) v[j] = ldg_stream(c < nk ? ks + c : vs + (c - nk));
         }
-        const uint32_t q = lo;
-        const uint64_t s = reqs[q].sel_base + (k - job_first[q]);
-        const uint32_t rec = sel[s];
-        const uint64_t dst_byte = arena_base[q] + slot[s];
-        const uint32_t kl = st.klen[rec], vl = st.vlen[rec];
-        const uint32_t nk = (kl + 15) >> 4, nv = (vl + 15) >> 4;
-        const uint4 *ks = st.kslab + st.koff16[rec];
-        const uint4 *vs = st.vslab + st.voff16[rec];
-        uint4 *dk = arena + (dst_byte >> 4);
-        uint4 *dv = dk + nk;
-        for (uint32_t c = lane; c < nk; c += 32) stg_stream(dk + c, ldg_stream(ks + c));
-        uint32_t c = lane;
-        for (; c + 96 < nv; c += 128) {
-            uint4 a0 = ldg_stream(vs + c), a1 = ldg_stream(vs + c + 32), a2 = ldg_stream(vs + c + 64),
-                  a3 = ldg_stream(vs + c + 96);
-            stg_stream(dv + c, a0);
-            stg_stream(dv + c + 32, a1);
-            stg_stream(dv + c + 64, a2);
-            stg_stream(dv + c + 96, a3);
-        }
-        for (; c < nv; c += 32) stg_stream(dv + c, ldg_stream(vs + c));
-        if (lane == 0) {
-            out.rec_idx[k] = rec;
-            out.rev[k] = be64_bytes((const uint8_t *)ks + kl - 8);
-            out.key_off[k] = dst_byte + 4;
-            out.key_len[k] = kl - 13;
-            out.val_off[k] = dst_byte + (uint64_t)nk * 16;
-            out.val_len[k] = vl;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const uint32_t c = c0 + j * 32;
+            if (c < n) stg_stream(dst + c, v[j]);
         }
     }
+    if (lane == 0) out_rev[k] = be64_bytes((const uint8_t *)ks + kl - 8);
 }
 
 }  // namespace
@@ -765,6 +662,9 @@ int resolve_requests(kb_ctx *ctx, const kb_range_req *reqs, uint64_t nreq, bool 
             td.rec0 = r.lo + t * KB_TILE;
             td.n = std::min<uint32_t>(KB_TILE, n - t * KB_TILE);
             td.flat0 = r.flat0 + t * KB_TILE;
+            td.lo = r.lo;
+            td.pad = 0;
+            td.read_rev = r.read_rev;
             R.tiles.push_back(td);
         }
         flat += (uint64_t)r.ntiles * KB_TILE;
@@ -787,7 +687,7 @@ int upload_layout(kb_ctx *ctx, const Resolved &R)
     KB_TRY(dbuf_ensure(ctx, ctx->d_tiles, std::max<size_t>(nt, 1) * sizeof(TileDev)));
     KB_TRY(dbuf_ensure(ctx, ctx->d_meta, std::max<uint64_t>(R.total_flat, 4) * 4));
     KB_TRY(dbuf_ensure(ctx, ctx->d_tgt, std::max<uint64_t>(R.total_flat, 4) * 4 + nreq * 4 + 16));
-    KB_TRY(dbuf_ensure(ctx, ctx->d_agg, std::max<size_t>(nt, 1) * 8));
+    KB_TRY(dbuf_ensure(ctx, ctx->d_agg, std::max<size_t>(nt, 1) * 32 * 8));  // one aggregate per 32-record sub-tile
     KB_TRY(dbuf_ensure(ctx, ctx->d_tcnt, std::max<size_t>(nt, 1) * 16));
     KB_TRY(dbuf_ensure(ctx, ctx->d_tscan, (nt + 1) * 16));
     KB_TRY(dbuf_ensure(ctx, ctx->d_reqout, std::max<size_t>(nreq, 1) * sizeof(ReqOut)));
@@ -808,6 +708,24 @@ int upload_layout(kb_ctx *ctx, const Resolved &R)
 
 // host copy of the slab offsets, kept for algorithmic-byte accounting only
 static inline std::vector<uint32_t> &host_koff16(kb_ctx *ctx) { return ctx->h_koff16; }
+
+// persistent decode pass: one CTA per SM, 8 independent warps each
+static int launch_decode(kb_ctx *ctx, uint32_t ntiles, uint64_t alg_bytes, const ScanMode &mode, const ReqDev *d_reqs,
+                         const TileDev *d_tiles, uint32_t *d_meta, uint2 *d_agg)
+{
+    const size_t smem = ((size_t)DECODE_WARPS * DECODE_STAGES * KB_WARP_STAGE_CHUNKS + 4) * 16;
+    static bool attr_set = false;
+    if (!attr_set) {
+        KB_CUDA(ctx, cudaFuncSetAttribute(k_decode_lcp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    const uint32_t n_sub = ntiles * 32;
+    const uint32_t grid = std::min<uint32_t>((n_sub + DECODE_WARPS - 1) / DECODE_WARPS, 148);
+    KB_LAUNCH(ctx, "k_decode_lcp", alg_bytes,
+              (k_decode_lcp<<<grid, DECODE_WARPS * 32, smem, ctx->stream>>>(ctx->st, d_reqs, d_tiles, n_sub, mode, d_meta,
+                                                                          d_agg)));
+    return KB_OK;
+}
 
 extern "C" int kb_range_batch(kb_ctx *ctx, const kb_range_req *reqs, uint64_t nreq, int out_mode, kb_result **out)
 {
@@ -845,12 +763,6 @@ extern "C" int kb_range_batch(kb_ctx *ctx, const kb_range_req *reqs, uint64_t nr
     mode.ttl_scan = 0;
     mode.timeout_rev = 0;
     mode.want_sel = out_mode != KB_OUT_COUNT;
-    const size_t smem = 8 * KB_WARP_STAGE_CHUNKS * 16;
-    static bool attr_set = false;
-    if (!attr_set) {
-        KB_CUDA(ctx, cudaFuncSetAttribute(k_decode_lcp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
-    }
     // algorithmic bytes of the decode pass: key bytes of the examined records + 10 B of offsets/lengths each
     uint64_t kbytes = 0;
     {
@@ -858,8 +770,7 @@ extern "C" int kb_range_batch(kb_ctx *ctx, const kb_range_req *reqs, uint64_t nr
         for (auto &r : R.reqs) kbytes += (uint64_t)(ko[r.hi] - ko[r.lo]) * 16 + (uint64_t)(r.hi - r.lo) * 10;
     }
     if (nt) {
-        KB_LAUNCH(ctx, "k_decode_lcp", kbytes,
-                  (k_decode_lcp<<<nt, 256, smem, ctx->stream>>>(ctx->st, d_reqs, d_tiles, mode, d_meta, d_agg)));
+        KB_TRY(launch_decode(ctx, nt, kbytes, mode, d_reqs, d_tiles, d_meta, d_agg));
         KB_LAUNCH(ctx, "k_emit", R.n_records * 8,
                   (k_emit<false><<<nt, 256, 0, ctx->stream>>>(ctx->st, d_reqs, d_tiles, d_agg, d_meta, d_tgt, d_tail,
                                                              d_tcnt)));
@@ -935,27 +846,38 @@ extern "C" int kb_range_batch(kb_ctx *ctx, const kb_range_req *reqs, uint64_t nr
         go.rec_idx = (uint32_t *)(go.val_off + nk);
         go.key_len = go.rec_idx + nk;
         go.val_len = go.key_len + nk;
-        const unsigned ggrid = (unsigned)std::min<uint64_t>((nk + 7) / 8, 148 * 8);
-        KB_LAUNCH(ctx, "k_gather", 2 * nbytes + nk * 48,
-                  (k_gather<<<ggrid, 256, 0, ctx->stream>>>(
-                      ctx->st, d_reqs, (uint32_t)nreq, (const uint64_t *)ctx->d_jobs.p,
-                      (const uint64_t *)ctx->d_jobs.p + nreq + 1, nk, (const uint32_t *)ctx->d_sel.p,
-                      (const uint64_t *)ctx->d_slot.p, (uint4 *)res->d_bytes.p, go)));
-        rc = pool_get_host(ctx, meta_bytes, &res->h_meta);
-        if (rc == KB_OK && out_mode == KB_OUT_HOST) rc = pool_get_host(ctx, nbytes + 16, &res->h_bytes);
-        if (rc == KB_OK) {
-            cudaMemcpyAsync(res->h_meta.p, d_om.p, nk * 36, cudaMemcpyDeviceToHost, ctx->stream);
-            if (out_mode == KB_OUT_HOST)
-                cudaMemcpyAsync(res->h_bytes.p, res->d_bytes.p, nbytes, cudaMemcpyDeviceToHost, ctx->stream);
-        }
-        cudaError_t e = cudaStreamSynchronize(ctx->stream);
-        pool_put_dev(ctx, d_om);
-        if (rc == KB_OK && e != cudaSuccess) rc = kb_cuda_fail(ctx, e, "gather");
+        rc = dbuf_ensure(ctx, ctx->d_gjobs, nk * sizeof(GatherJob));
         if (rc != KB_OK) {
+            pool_put_dev(ctx, d_om);
             kb_result_free(nullptr, res);
             return rc;
         }
-        uint8_t *hm = (uint8_t *)res->h_meta.p;
+        GatherJob *d_jobs = (GatherJob *)ctx->d_gjobs.p;
+        KB_LAUNCH(ctx, "k_gather_jobs", nk * 80,
+                  (k_gather_jobs<<<(unsigned)((nk + 255) / 256), 256, 0, ctx->stream>>>(
+                      ctx->st, d_reqs, (uint32_t)nreq, (const uint64_t *)ctx->d_jobs.p,
+                      (const uint64_t *)ctx->d_jobs.p + nreq + 1, nk, (const uint32_t *)ctx->d_sel.p,
+                      (const uint64_t *)ctx->d_slot.p, d_jobs, go)));
+        KB_LAUNCH(ctx, "k_gather", 2 * nbytes + nk * 40,
+                  (k_gather<<<(unsigned)((nk + 7) / 8), 256, 0, ctx->stream>>>(ctx->st, d_jobs, nk,
+                                                                              (uint4 *)res->d_bytes.p, go.rev)));
+        if (out_mode == KB_OUT_HOST) {
+            rc = pool_get_host(ctx, meta_bytes, &res->h_meta);
+            if (rc == KB_OK) rc = pool_get_host(ctx, nbytes + 16, &res->h_bytes);
+            if (rc == KB_OK) {
+                cudaMemcpyAsync(res->h_meta.p, d_om.p, nk * 36, cudaMemcpyDeviceToHost, ctx->stream);
+                cudaMemcpyAsync(res->h_bytes.p, res->d_bytes.p, nbytes, cudaMemcpyDeviceToHost, ctx->stream);
+            }
+        }
+        cudaError_t e = cudaStreamSynchronize(ctx->stream);
+        if (rc == KB_OK && e != cudaSuccess) rc = kb_cuda_fail(ctx, e, "gather");
+        if (rc != KB_OK) {
+            pool_put_dev(ctx, d_om);
+            kb_result_free(nullptr, res);
+            return rc;
+        }
+        // per-kv arrays: host copies for KB_OUT_HOST, the device arrays themselves for KB_OUT_DEVICE
+        uint8_t *hm = out_mode == KB_OUT_HOST ? (uint8_t *)res->h_meta.p : (uint8_t *)d_om.p;
         res->rev = (const uint64_t *)hm;
         res->key_off = res->rev + nk;
         res->val_off = res->key_off + nk;
@@ -963,8 +885,11 @@ extern "C" int kb_range_batch(kb_ctx *ctx, const kb_range_req *reqs, uint64_t nr
         res->key_len = res->rec_idx + nk;
         res->val_len = res->key_len + nk;
         if (out_mode == KB_OUT_HOST) {
+            pool_put_dev(ctx, d_om);
             pool_put_dev(ctx, res->d_bytes);
             res->d_bytes = DBuf();
+        } else {
+            res->d_vic = d_om;  // owned by the result (returned to the pool by kb_result_free)
         }
     }
     *out = res;
@@ -1030,16 +955,13 @@ extern "C" int kb_compact_sweep(kb_ctx *ctx, const uint8_t *start, uint64_t star
     mode.ttl_scan = (!support_ttl && timeout_rev != 0) ? 1 : 0;
     mode.timeout_rev = timeout_rev;
     mode.want_sel = out_mode != KB_OUT_COUNT;
-    const size_t smem = 8 * KB_WARP_STAGE_CHUNKS * 16;
-    KB_CUDA(ctx, cudaFuncSetAttribute(k_decode_lcp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     uint64_t kbytes = 0;
     {
         std::vector<uint32_t> &ko = host_koff16(ctx);
         for (auto &r : R.reqs) kbytes += (uint64_t)(ko[r.hi] - ko[r.lo]) * 16 + (uint64_t)(r.hi - r.lo) * 10;
     }
     if (nt) {
-        KB_LAUNCH(ctx, "k_decode_lcp", kbytes,
-                  (k_decode_lcp<<<nt, 256, smem, ctx->stream>>>(ctx->st, d_reqs, d_tiles, mode, d_meta, d_agg)));
+        KB_TRY(launch_decode(ctx, nt, kbytes, mode, d_reqs, d_tiles, d_meta, d_agg));
         KB_LAUNCH(ctx, "k_emit_compact", R.n_records * 8,
                   (k_emit<true><<<nt, 256, 0, ctx->stream>>>(ctx->st, d_reqs, d_tiles, d_agg, d_meta, d_tgt, d_tail,
                                                             d_tcnt)));

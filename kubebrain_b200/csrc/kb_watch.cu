@@ -11,13 +11,16 @@
 // hash of its own leading bytes (verified byte-exactly), so the work is O(E * #lengths + deliveries):
 //   k_batch_pm       per collector batch: running max of Event.Revision (the "leading strip" predicate becomes
 //                    pm[i] >= min_rev) + a flag "revisions globally non-decreasing"
-//   k_match<COUNT>   per event: matched groups -> per-group counts
+//   k_match_count    per event and prefix length: matched group (kept in ematch) + warp-aggregated group counts
 //   (scan)           group segment offsets
-//   k_match<SCATTER> per event: event index appended to each matched group's segment (unordered)
-//   k_sort_small / k_sort_big  every segment sorted ascending (warp rank-sort / shared-memory bitmap)
-//   k_expand<COUNT>  per watcher: deliveries = its group's segment filtered by min_rev
+//   k_classify       groups by match count: small (<=32), medium (<= BIG_T), large (global bitmap)
+//   k_scatter        small/medium: warp-aggregated slot claim into the group's segment (unordered across warps);
+//                    large: the warp's ballot IS the 32-event bitmap word of the group (plain store, no atomics)
+//   k_sort_small / k_sort_medium / k_expand_large   every segment ascending (warp rank-sort / shared-memory bitmap /
+//                    ordered expansion of the global bitmap)
+//   k_expand_count   per watcher: deliveries = its group's segment filtered by min_rev
 //   (scan)           per-watcher output offsets
-//   k_expand<WRITE>  per watcher: ordered event indices
+//   k_expand_write   ordered event indices, one thread per delivery (suffix copy when revisions are monotone)
 #include <algorithm>
 #include <map>
 #include <unordered_map>
@@ -36,7 +39,7 @@ struct WatchTablesDev {
     uint32_t n_ids = 0, n_groups = 0, n_lens = 0, table_size = 0, max_len = 0;
     DBuf gprefix, goff16, glen, ghash, gstart, gmember, wgroup, wminrev, lens, table;
     // per-call scratch
-    DBuf gcnt, gbase, gfill, seg, seg_sorted, big, pm, flag, wcnt, wstart, total;
+    DBuf gcnt, gbase, gfill, gclass, ematch, seg, seg_sorted, lists, bitmaps, pm, flag, wcnt, wlo, wstart, total;
 };
 
 namespace {
@@ -96,70 +99,111 @@ __global__ void __launch_bounds__(128) k_batch_pm(EvDev ev, uint64_t *__restrict
     if (__any_sync(FULL, bad) && lane == 0) atomicOr(nonmono, 1u);
 }
 
-// ---- per event: which prefix groups does its key start with?
-template <bool SCATTER>
+// ---- per event and distinct prefix length: the group whose prefix the key starts with (or NONE).
+//      ematch[li * E + i]; group counts are aggregated inside the warp before touching memory.
 __global__ void __launch_bounds__(256)
-k_match(EvDev ev, TabDev tb, uint32_t *__restrict__ gcnt, const uint32_t *__restrict__ gbase,
-        uint32_t *__restrict__ gfill, uint32_t *__restrict__ seg)
+k_match_count(EvDev ev, TabDev tb, uint32_t *__restrict__ ematch, uint32_t *__restrict__ gcnt)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= ev.n) return;
-    const uint32_t klen = ev.klen[i];
-    const uint4 *kp = ev.keys + (uint64_t)i * ev.stride16;
+    const uint32_t lane = threadIdx.x & 31;
+    const bool valid = i < ev.n;
+    const uint32_t klen = valid ? ev.klen[i] : 0;
+    const uint4 *kp = ev.keys + (uint64_t)(valid ? i : 0) * ev.stride16;
     uint64_t h = FNV_OFFSET;
-    uint32_t li = 0;
     uint32_t pos = 0;  // bytes hashed so far
     uint4 chunk = make_uint4(0, 0, 0, 0);
-    while (li < tb.n_lens) {
+    for (uint32_t li = 0; li < tb.n_lens; li++) {  // uniform trip count: the warp collectives below need all lanes
         const uint32_t L = tb.lens[li];
-        if (L > klen) break;  // longer prefixes cannot match a shorter key
-        while (pos < L) {
-            if ((pos & 15) == 0) chunk = kp[pos >> 4];
-            h = (h ^ (uint64_t)byte_of(chunk, pos & 15)) * FNV_PRIME;
-            pos++;
-        }
-        // probe (hash, length); verify the bytes so the result is exact
-        uint32_t s = slot_of(h, L, tb.mask);
-        for (;;) {
-            const uint32_t g = tb.table[s];
-            if (g == KB_NONE) break;
-            if (tb.ghash[g] == h && tb.glen[g] == L) {
-                const uint4 *gp = tb.gprefix + tb.goff16[g];
-                bool eq = true;
-                for (uint32_t c = 0; c * 16 < L && eq; c++) {
-                    uint4 a = kp[c], b = gp[c];
-                    int p = first_diff16(a, b);
-                    if (p < 16 && c * 16 + p < L) eq = false;
-                }
-                if (eq) {
-                    if (SCATTER) {
-                        const uint32_t at = gbase[g] + atomicAdd(&gfill[g], 1u);
-                        seg[at] = i;
-                    } else {
-                        atomicAdd(&gcnt[g], 1u);
-                    }
-                    break;  // prefixes are unique per group
-                }
+        uint32_t g = KB_NONE;
+        if (valid && L <= klen) {
+            while (pos < L) {
+                if ((pos & 15) == 0) chunk = kp[pos >> 4];
+                h = (h ^ (uint64_t)byte_of(chunk, pos & 15)) * FNV_PRIME;
+                pos++;
             }
-            s = (s + 1) & tb.mask;
+            // probe (hash, length); verify the bytes so the result is exact
+            uint32_t s = slot_of(h, L, tb.mask);
+            for (;;) {
+                const uint32_t c = tb.table[s];
+                if (c == KB_NONE) break;
+                if (tb.ghash[c] == h && tb.glen[c] == L) {
+                    const uint4 *gp = tb.gprefix + tb.goff16[c];
+                    bool eq = true;
+                    for (uint32_t k = 0; k * 16 < L && eq; k++) {
+                        uint4 a = kp[k], b = gp[k];
+                        int p = first_diff16(a, b);
+                        if (p < 16 && k * 16 + p < L) eq = false;
+                    }
+                    if (eq) {
+                        g = c;
+                        break;  // prefixes are unique per group
+                    }
+                }
+                s = (s + 1) & tb.mask;
+            }
         }
-        li++;
+        if (valid) ematch[(uint64_t)li * ev.n + i] = g;
+        const unsigned peers = __match_any_sync(FULL, g);
+        if (g != KB_NONE && lane == (unsigned)(__ffs(peers) - 1)) atomicAdd(&gcnt[g], (uint32_t)__popc(peers));
+    }
+}
+
+// lists layout: [0]=n_medium [1]=n_large [2..2+G) medium groups [2+G..2+2G) large groups
+__global__ void __launch_bounds__(256)
+k_classify(uint32_t n_groups, const uint32_t *__restrict__ gcnt, uint32_t big_t, uint32_t max_large,
+           uint32_t *__restrict__ gclass, uint32_t *__restrict__ lists)
+{
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_groups) return;
+    const uint32_t n = gcnt[g];
+    uint32_t cls = KB_NONE;  // NONE: small or medium (segment scatter); otherwise the bitmap slot
+    if (n > big_t) {
+        const uint32_t slot = atomicAdd(&lists[1], 1u);
+        if (slot < max_large) {  // cannot overflow: sum(gcnt) <= E * n_lens
+            cls = slot;
+            lists[2 + n_groups + slot] = g;
+        }
+    } else if (n > 32) {
+        lists[2 + atomicAdd(&lists[0], 1u)] = g;
+    }
+    gclass[g] = cls;
+}
+
+__global__ void __launch_bounds__(256)
+k_scatter(uint32_t n_events, uint32_t n_lens, const uint32_t *__restrict__ ematch,
+          const uint32_t *__restrict__ gclass, const uint32_t *__restrict__ gbase, uint32_t *__restrict__ gfill,
+          uint32_t *__restrict__ seg, uint32_t *__restrict__ bitmaps, uint32_t bm_words)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t lane = threadIdx.x & 31;
+    const bool valid = i < n_events;
+    for (uint32_t li = 0; li < n_lens; li++) {
+        const uint32_t g = valid ? ematch[(uint64_t)li * n_events + i] : KB_NONE;
+        const unsigned peers = __match_any_sync(FULL, g);
+        if (g == KB_NONE) continue;
+        const uint32_t leader = __ffs(peers) - 1;
+        const uint32_t cls = gclass[g];
+        if (cls != KB_NONE) {
+            // the 32 events of this warp are exactly one bitmap word of the group
+            if (lane == leader) bitmaps[(uint64_t)cls * bm_words + (i >> 5)] = peers;
+        } else {
+            uint32_t base = 0;
+            if (lane == leader) base = atomicAdd(&gfill[g], (uint32_t)__popc(peers));
+            base = __shfl_sync(peers, base, leader);
+            seg[gbase[g] + base + __popc(peers & ((1u << lane) - 1))] = i;
+        }
     }
 }
 
 // ---- segment sort: ascending event index per group
 __global__ void __launch_bounds__(256)
 k_sort_small(uint32_t n_groups, const uint32_t *__restrict__ gcnt, const uint32_t *__restrict__ gbase,
-             const uint32_t *__restrict__ seg, uint32_t *__restrict__ sorted, uint32_t *__restrict__ big /* [0]=count */)
+             const uint32_t *__restrict__ seg, uint32_t *__restrict__ sorted)
 {
     const uint32_t g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (g >= n_groups) return;
     const uint32_t n = gcnt[g];
-    if (n == 0) return;
-    if (n > 32) {
-        if (lane == 0) big[1 + atomicAdd(&big[0], 1u)] = g;
-        return;
-    }
+    if (n == 0 || n > 32) return;
     const uint32_t base = gbase[g];
     const uint32_t v = lane < n ? seg[base + lane] : 0xFFFFFFFFu;
     uint32_t rank = 0;
@@ -173,23 +217,48 @@ k_sort_small(uint32_t n_groups, const uint32_t *__restrict__ gcnt, const uint32_
 
 constexpr uint32_t BM_WORDS = 8192;  // 262144 event indices per window (32 KiB of shared memory)
 
+__device__ __forceinline__ uint32_t block_excl_scan_u32(uint32_t v, uint32_t *wsum /* 9 */, uint32_t &total)
+{
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t o = __shfl_up_sync(FULL, inc, d);
+        if (lane >= (unsigned)d) inc += o;
+    }
+    if (lane == 31) wsum[wid] = inc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t run = 0;
+        for (int k = 0; k < 8; k++) {
+            uint32_t x = wsum[k];
+            wsum[k] = run;
+            run += x;
+        }
+        wsum[8] = run;
+    }
+    __syncthreads();
+    const uint32_t ex = wsum[wid] + inc - v;
+    total = wsum[8];
+    __syncthreads();
+    return ex;
+}
+
+// one CTA per medium group (33..big_t entries): shared-memory bitmap over [min, max] of the segment
 __global__ void __launch_bounds__(256)
-k_sort_big(const uint32_t *__restrict__ big, const uint32_t *__restrict__ gcnt, const uint32_t *__restrict__ gbase,
-           const uint32_t *__restrict__ seg, uint32_t *__restrict__ sorted)
+k_sort_medium(const uint32_t *__restrict__ lists, const uint32_t *__restrict__ gcnt,
+              const uint32_t *__restrict__ gbase, const uint32_t *__restrict__ seg, uint32_t *__restrict__ sorted)
 {
     __shared__ uint32_t bm[BM_WORDS];
     __shared__ uint32_t wsum[9];
     __shared__ uint32_t red[2];
-    __shared__ uint32_t outpos_s;
-    const uint32_t nbig = big[0];
-    for (uint32_t bi = blockIdx.x; bi < nbig; bi += gridDim.x) {
-        const uint32_t g = big[1 + bi];
+    const uint32_t nmed = lists[0];
+    for (uint32_t bi = blockIdx.x; bi < nmed; bi += gridDim.x) {
+        const uint32_t g = lists[2 + bi];
         const uint32_t n = gcnt[g], base = gbase[g];
-        // min / max of the segment
         if (threadIdx.x == 0) {
             red[0] = 0xFFFFFFFFu;
             red[1] = 0;
-            outpos_s = 0;
         }
         __syncthreads();
         uint32_t mn = 0xFFFFFFFFu, mx = 0;
@@ -203,6 +272,7 @@ k_sort_big(const uint32_t *__restrict__ big, const uint32_t *__restrict__ gcnt, 
         __syncthreads();
         mn = red[0];
         mx = red[1];
+        uint32_t outpos = 0;
         for (uint64_t w0 = mn & ~31u; w0 <= mx; w0 += (uint64_t)BM_WORDS * 32) {
             const uint64_t need_words = ((uint64_t)mx - w0) / 32 + 1;
             const uint32_t nwords = need_words < BM_WORDS ? (uint32_t)need_words : BM_WORDS;
@@ -216,32 +286,13 @@ k_sort_big(const uint32_t *__restrict__ big, const uint32_t *__restrict__ gcnt, 
                 }
             }
             __syncthreads();
-            // ordered expansion of the bitmap: each thread owns a contiguous run of words
+            // ordered expansion: each thread owns a contiguous run of words
             const uint32_t per = (nwords + blockDim.x - 1) / blockDim.x;
             const uint32_t wlo = min(nwords, threadIdx.x * per), whi = min(nwords, wlo + per);
             uint32_t cnt = 0;
             for (uint32_t j = wlo; j < whi; j++) cnt += __popc(bm[j]);
-            // block exclusive scan of cnt
-            const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-            uint32_t inc = cnt;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                uint32_t o = __shfl_up_sync(FULL, inc, d);
-                if (lane >= (unsigned)d) inc += o;
-            }
-            if (lane == 31) wsum[wid] = inc;
-            __syncthreads();
-            if (threadIdx.x == 0) {
-                uint32_t run = 0;
-                for (int k = 0; k < 8; k++) {
-                    uint32_t x = wsum[k];
-                    wsum[k] = run;
-                    run += x;
-                }
-                wsum[8] = run;
-            }
-            __syncthreads();
-            uint32_t at = outpos_s + wsum[wid] + inc - cnt;
+            uint32_t total;
+            uint32_t at = outpos + block_excl_scan_u32(cnt, wsum, total);
             for (uint32_t j = wlo; j < whi; j++) {
                 uint32_t bits = bm[j];
                 while (bits) {
@@ -250,25 +301,60 @@ k_sort_big(const uint32_t *__restrict__ big, const uint32_t *__restrict__ gcnt, 
                     sorted[base + at++] = (uint32_t)(w0 + (uint64_t)j * 32 + b);
                 }
             }
-            __syncthreads();
-            if (threadIdx.x == 0) outpos_s += wsum[8];
+            outpos += total;
             __syncthreads();
         }
+        __syncthreads();
     }
 }
 
-// ---- per watcher: its group's sorted segment filtered by pm[e] >= min_rev
-template <bool WRITE>
+// large groups: ordered expansion of the global bitmap; CTA = (large group, chunk of 256 words)
 __global__ void __launch_bounds__(256)
-k_expand(TabDev tb, const uint32_t *__restrict__ gcnt, const uint32_t *__restrict__ gbase,
-         const uint32_t *__restrict__ sorted, const uint64_t *__restrict__ pm, const uint32_t *__restrict__ nonmono,
-         uint64_t *__restrict__ wcnt, const uint64_t *__restrict__ wstart, uint32_t *__restrict__ out)
+k_expand_large(const uint32_t *__restrict__ lists, uint32_t n_groups, const uint32_t *__restrict__ gbase,
+               const uint32_t *__restrict__ bitmaps, uint32_t bm_words, uint32_t chunks_per_group,
+               uint32_t *__restrict__ sorted)
+{
+    __shared__ uint32_t wsum[9];
+    __shared__ uint32_t pre_s;
+    const uint32_t nlarge = lists[1];
+    for (uint32_t job = blockIdx.x; job < nlarge * chunks_per_group; job += gridDim.x) {
+        const uint32_t slot = job / chunks_per_group, chunk = job % chunks_per_group;
+        const uint32_t g = lists[2 + n_groups + slot];
+        const uint32_t *bm = bitmaps + (uint64_t)slot * bm_words;
+        // matches in the words before this chunk
+        uint32_t part = 0;
+        for (uint32_t j = threadIdx.x; j < chunk * 256; j += blockDim.x) part += __popc(bm[j]);
+        uint32_t tot;
+        block_excl_scan_u32(part, wsum, tot);
+        if (threadIdx.x == 0) pre_s = tot;
+        __syncthreads();
+        const uint32_t wi = chunk * 256 + threadIdx.x;
+        uint32_t bits = wi < bm_words ? bm[wi] : 0;
+        uint32_t total;
+        uint32_t at = gbase[g] + pre_s + block_excl_scan_u32(__popc(bits), wsum, total);
+        while (bits) {
+            const uint32_t b = __ffs(bits) - 1;
+            bits &= bits - 1;
+            sorted[at++] = wi * 32 + b;
+        }
+        __syncthreads();
+    }
+}
+
+// ---- per watcher: deliveries = its group's sorted segment filtered by pm[e] >= min_rev
+__global__ void __launch_bounds__(256)
+k_expand_count(TabDev tb, const uint32_t *__restrict__ gcnt, const uint32_t *__restrict__ gbase,
+               const uint32_t *__restrict__ sorted, const uint64_t *__restrict__ pm,
+               const uint32_t *__restrict__ nonmono, uint64_t *__restrict__ wcnt, uint32_t *__restrict__ wlo)
 {
     const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (w >= tb.n_ids) return;
     const uint32_t g = tb.wgroup[w];
     if (g == KB_NONE) {
-        if (!WRITE && lane == 0) wcnt[w] = 0;
+        if (lane == 0) {
+            wcnt[w] = 0;
+            wlo[w] = 0;
+        }
         return;
     }
     const uint32_t n = gcnt[g];
@@ -281,25 +367,68 @@ k_expand(TabDev tb, const uint32_t *__restrict__ gcnt, const uint32_t *__restric
             const uint32_t mid = (lo + hi) >> 1;
             if (pm[M[mid]] >= mr) hi = mid; else lo = mid + 1;
         }
-        if (!WRITE) {
-            if (lane == 0) wcnt[w] = n - lo;
-        } else {
-            const uint64_t o = wstart[w];
-            for (uint32_t j = lo + lane; j < n; j += 32) out[o + (j - lo)] = M[j];
+        if (lane == 0) {
+            wcnt[w] = n - lo;
+            wlo[w] = lo;
         }
         return;
     }
     uint64_t total = 0;
-    const uint64_t o = WRITE ? wstart[w] : 0;
+    for (uint32_t c = 0; c < n; c += 32) {
+        const uint32_t j = c + lane;
+        const bool keep = j < n && pm[M[j]] >= mr;
+        total += __popc(__ballot_sync(FULL, keep));
+    }
+    if (lane == 0) {
+        wcnt[w] = total;
+        wlo[w] = 0;
+    }
+}
+
+// monotone revisions: one thread per delivery (suffix copy)
+__global__ void __launch_bounds__(256)
+k_expand_write(TabDev tb, const uint32_t *__restrict__ gbase, const uint32_t *__restrict__ sorted,
+               const uint32_t *__restrict__ nonmono, const uint64_t *__restrict__ wstart,
+               const uint32_t *__restrict__ wlo, uint64_t n_deliveries, uint32_t *__restrict__ out)
+{
+    if (*nonmono != 0) return;
+    const uint64_t d = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= n_deliveries) return;
+    uint32_t lo = 0, hi = tb.n_ids;  // last watcher with wstart[w] <= d
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (wstart[mid] <= d) lo = mid; else hi = mid;
+    }
+    const uint32_t w = lo;
+    const uint32_t g = tb.wgroup[w];
+    out[d] = sorted[gbase[g] + wlo[w] + (uint32_t)(d - wstart[w])];
+}
+
+// non-monotone revisions (general case): warp per watcher, ordered filtered copy
+__global__ void __launch_bounds__(256)
+k_expand_write_general(TabDev tb, const uint32_t *__restrict__ gcnt, const uint32_t *__restrict__ gbase,
+                       const uint32_t *__restrict__ sorted, const uint64_t *__restrict__ pm,
+                       const uint32_t *__restrict__ nonmono, const uint64_t *__restrict__ wstart,
+                       uint32_t *__restrict__ out)
+{
+    if (*nonmono == 0) return;
+    const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (w >= tb.n_ids) return;
+    const uint32_t g = tb.wgroup[w];
+    if (g == KB_NONE) return;
+    const uint32_t n = gcnt[g];
+    const uint32_t *M = sorted + gbase[g];
+    const uint64_t mr = tb.wminrev[w];
+    const uint64_t o = wstart[w];
+    uint64_t total = 0;
     for (uint32_t c = 0; c < n; c += 32) {
         const uint32_t j = c + lane;
         const uint32_t e = j < n ? M[j] : 0;
         const bool keep = j < n && pm[e] >= mr;
         const unsigned m = __ballot_sync(FULL, keep);
-        if (WRITE && keep) out[o + total + __popc(m & ((1u << lane) - 1))] = e;
+        if (keep) out[o + total + __popc(m & ((1u << lane) - 1))] = e;
         total += __popc(m);
     }
-    if (!WRITE && lane == 0) wcnt[w] = total;
 }
 
 uint64_t fnv1a(const std::string &s)
@@ -451,7 +580,7 @@ void watch_tables_free(kb_ctx *ctx)
     if (!ctx->wt) return;
     WatchTablesDev &T = *ctx->wt;
     DBuf *all[] = {&T.gprefix, &T.goff16, &T.glen, &T.ghash, &T.gstart, &T.gmember, &T.wgroup, &T.wminrev,
-                   &T.lens, &T.table, &T.gcnt, &T.gbase, &T.gfill, &T.seg, &T.seg_sorted, &T.big, &T.pm,
+                   &T.lens, &T.table, &T.gcnt, &T.gbase, &T.gfill, &T.gclass, &T.ematch, &T.seg, &T.seg_sorted, &T.lists, &T.bitmaps, &T.wlo, &T.pm,
                    &T.flag, &T.wcnt, &T.wstart, &T.total};
     for (DBuf *b : all)
         if (b->p) cudaFree(b->p);
@@ -535,18 +664,27 @@ static int match_locked(kb_ctx *ctx, const kb_events_dev *d, int out_mode, kb_re
     if (d->stride < needed_stride(ctx))
         return kb_fail(ctx, KB_ESTATE, "event slab was uploaded for shorter watcher prefixes (stride %u < %u); upload again",
                        d->stride, needed_stride(ctx));
-    const uint32_t E = d->n, G = T.n_groups, W = T.n_ids;
-    const uint64_t seg_cap = std::max<uint64_t>((uint64_t)E * std::max(T.n_lens, 1u), 1);
+    const uint32_t E = d->n, G = T.n_groups, W = T.n_ids, NL = std::max(T.n_lens, 1u);
+    const uint64_t seg_cap = std::max<uint64_t>((uint64_t)E * NL, 1);
     if (seg_cap >= 0xFFFFFFF0ull) return kb_fail(ctx, KB_ELIMIT, "events x distinct prefix lengths exceeds 2^32");
+    // groups matching more than big_t events get a global bitmap; at most E*NL/big_t of them can exist
+    const uint32_t big_t = std::max<uint32_t>(1024, E / 64);
+    const uint32_t max_large = (uint32_t)(seg_cap / big_t) + 1;
+    const uint32_t bm_words = (E + 31) / 32;
+    const uint32_t chunks_per_group = (bm_words + 255) / 256;
     KB_TRY(dbuf_ensure(ctx, T.gcnt, (size_t)(G + 1) * 4));
     KB_TRY(dbuf_ensure(ctx, T.gbase, (size_t)(G + 1) * 4));
     KB_TRY(dbuf_ensure(ctx, T.gfill, (size_t)(G + 1) * 4));
+    KB_TRY(dbuf_ensure(ctx, T.gclass, (size_t)(G + 1) * 4));
+    KB_TRY(dbuf_ensure(ctx, T.ematch, seg_cap * 4));
     KB_TRY(dbuf_ensure(ctx, T.seg, seg_cap * 4));
     KB_TRY(dbuf_ensure(ctx, T.seg_sorted, seg_cap * 4));
-    KB_TRY(dbuf_ensure(ctx, T.big, (size_t)(G + 2) * 4));
+    KB_TRY(dbuf_ensure(ctx, T.lists, (size_t)(2 * G + 4) * 4));
+    KB_TRY(dbuf_ensure(ctx, T.bitmaps, std::max<size_t>((size_t)max_large * bm_words * 4, 16)));
     KB_TRY(dbuf_ensure(ctx, T.pm, std::max<size_t>((size_t)E * 8, 16)));
     KB_TRY(dbuf_ensure(ctx, T.flag, 16));
     KB_TRY(dbuf_ensure(ctx, T.wcnt, (size_t)(W + 1) * 8));
+    KB_TRY(dbuf_ensure(ctx, T.wlo, (size_t)(W + 1) * 4));
     KB_TRY(dbuf_ensure(ctx, T.wstart, (size_t)(W + 2) * 8));
     KB_TRY(dbuf_ensure(ctx, T.total, 16));
 
@@ -576,36 +714,46 @@ static int match_locked(kb_ctx *ctx, const kb_events_dev *d, int out_mode, kb_re
     tb.max_len = T.max_len;
 
     uint32_t *gcnt = (uint32_t *)T.gcnt.p, *gbase = (uint32_t *)T.gbase.p, *gfill = (uint32_t *)T.gfill.p;
-    uint32_t *seg = (uint32_t *)T.seg.p, *sorted = (uint32_t *)T.seg_sorted.p, *big = (uint32_t *)T.big.p;
+    uint32_t *gclass = (uint32_t *)T.gclass.p, *ematch = (uint32_t *)T.ematch.p, *lists = (uint32_t *)T.lists.p;
+    uint32_t *seg = (uint32_t *)T.seg.p, *sorted = (uint32_t *)T.seg_sorted.p, *bitmaps = (uint32_t *)T.bitmaps.p;
     uint64_t *pm = (uint64_t *)T.pm.p;
-    uint32_t *flag = (uint32_t *)T.flag.p;
+    uint32_t *flag = (uint32_t *)T.flag.p, *wlo = (uint32_t *)T.wlo.p;
     uint64_t *wcnt = (uint64_t *)T.wcnt.p, *wstart = (uint64_t *)T.wstart.p, *total = (uint64_t *)T.total.p;
 
     KB_CUDA(ctx, cudaMemsetAsync(gcnt, 0, (size_t)(G + 1) * 4, ctx->stream));
     KB_CUDA(ctx, cudaMemsetAsync(gfill, 0, (size_t)(G + 1) * 4, ctx->stream));
-    KB_CUDA(ctx, cudaMemsetAsync(big, 0, 4, ctx->stream));
+    KB_CUDA(ctx, cudaMemsetAsync(lists, 0, 8, ctx->stream));
     KB_CUDA(ctx, cudaMemsetAsync(flag, 0, 4, ctx->stream));
     const uint64_t ev_bytes = (uint64_t)E * (d->stride + 4);
+    const bool work = E && W && G;
     if (E && W) {
         KB_LAUNCH(ctx, "k_batch_pm", (uint64_t)E * 16,
                   (k_batch_pm<<<(d->nb * 32 + 127) / 128, 128, 0, ctx->stream>>>(ev, pm, flag)));
-        if (G) {
-            KB_LAUNCH(ctx, "k_match_count", ev_bytes,
-                      (k_match<false><<<(E + 255) / 256, 256, 0, ctx->stream>>>(ev, tb, gcnt, gbase, gfill, seg)));
-        }
+    }
+    if (work) {
+        KB_LAUNCH(ctx, "k_match_count", ev_bytes + (uint64_t)E * NL * 4,
+                  (k_match_count<<<(E + 255) / 256, 256, 0, ctx->stream>>>(ev, tb, ematch, gcnt)));
     }
     KB_TRY(scan_exclusive_u32(ctx, gcnt, gbase, G, nullptr));
-    if (E && W && G) {
-        KB_LAUNCH(ctx, "k_match_scatter", ev_bytes,
-                  (k_match<true><<<(E + 255) / 256, 256, 0, ctx->stream>>>(ev, tb, gcnt, gbase, gfill, seg)));
+    if (work) {
+        KB_CUDA(ctx, cudaMemsetAsync(bitmaps, 0, (size_t)max_large * bm_words * 4, ctx->stream));
+        KB_LAUNCH(ctx, "k_classify", (uint64_t)G * 8,
+                  (k_classify<<<(G + 255) / 256, 256, 0, ctx->stream>>>(G, gcnt, big_t, max_large, gclass, lists)));
+        KB_LAUNCH(ctx, "k_scatter", (uint64_t)E * NL * 8,
+                  (k_scatter<<<(E + 255) / 256, 256, 0, ctx->stream>>>(E, T.n_lens, ematch, gclass, gbase, gfill, seg,
+                                                                     bitmaps, bm_words)));
         KB_LAUNCH(ctx, "k_sort_small", (uint64_t)G * 8,
-                  (k_sort_small<<<(G * 32 + 255) / 256, 256, 0, ctx->stream>>>(G, gcnt, gbase, seg, sorted, big)));
-        KB_LAUNCH(ctx, "k_sort_big", 0, (k_sort_big<<<148 * 2, 256, 0, ctx->stream>>>(big, gcnt, gbase, seg, sorted)));
+                  (k_sort_small<<<(G * 32 + 255) / 256, 256, 0, ctx->stream>>>(G, gcnt, gbase, seg, sorted)));
+        KB_LAUNCH(ctx, "k_sort_medium", 0,
+                  (k_sort_medium<<<148 * 4, 256, 0, ctx->stream>>>(lists, gcnt, gbase, seg, sorted)));
+        KB_LAUNCH(ctx, "k_expand_large", (uint64_t)max_large * bm_words * 4,
+                  (k_expand_large<<<std::min<uint32_t>(148 * 8, max_large * chunks_per_group), 256, 0, ctx->stream>>>(
+                      lists, G, gbase, bitmaps, bm_words, chunks_per_group, sorted)));
     }
     if (W) {
         KB_LAUNCH(ctx, "k_expand_count", (uint64_t)W * 24,
-                  (k_expand<false><<<(W * 32 + 255) / 256, 256, 0, ctx->stream>>>(tb, gcnt, gbase, sorted, pm, flag,
-                                                                               wcnt, wstart, nullptr)));
+                  (k_expand_count<<<(W * 32 + 255) / 256, 256, 0, ctx->stream>>>(tb, gcnt, gbase, sorted, pm, flag, wcnt,
+                                                                              wlo)));
     }
     KB_TRY(scan_exclusive_u64(ctx, wcnt, wstart, W, total));
     uint64_t D = 0;
@@ -624,8 +772,11 @@ static int match_locked(kb_ctx *ctx, const kb_events_dev *d, int out_mode, kb_re
     cudaMemcpyAsync(o_start + W, total, 8, cudaMemcpyDeviceToDevice, ctx->stream);
     if (W && D) {
         KB_LAUNCH(ctx, "k_expand_write", D * 8,
-                  (k_expand<true><<<(W * 32 + 255) / 256, 256, 0, ctx->stream>>>(tb, gcnt, gbase, sorted, pm, flag, wcnt,
-                                                                              wstart, o_idx)));
+                  (k_expand_write<<<(unsigned)((D + 255) / 256), 256, 0, ctx->stream>>>(tb, gbase, sorted, flag, o_start,
+                                                                                     wlo, D, o_idx)));
+        KB_LAUNCH(ctx, "k_expand_write_general", 0,
+                  (k_expand_write_general<<<(W * 32 + 255) / 256, 256, 0, ctx->stream>>>(tb, gcnt, gbase, sorted, pm,
+                                                                                      flag, o_start, o_idx)));
     }
     HBuf h_out;
     int rc = KB_OK;

