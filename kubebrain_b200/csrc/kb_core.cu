@@ -424,6 +424,7 @@ extern "C" int kb_load_sorted(kb_ctx *ctx, const uint8_t *keys, const uint64_t *
     ctx->st.vlen = (const uint32_t *)ctx->d_vlen.p;
     ctx->st.n = (uint32_t)n;
     ctx->h_koff16 = koff16;
+    ctx->h_voff16 = voff16;
 
     // the iterator contract: strictly ascending unique keys
     if (n > 1) {
@@ -540,9 +541,17 @@ extern "C" int kb_cursor_allgather(kb_ctx *ctx, uint64_t local_rev, uint64_t *al
     NcclApi *a = nccl_api();
     cudaSetDevice(ctx->device);
     int n = ctx->nccl_nranks;
+    if (n == 1) {
+        // a single shard has nobody to exchange with: the readable revision is its own cursor
+        if (all_revs) all_revs[0] = local_rev;
+        if (min_rev) *min_rev = local_rev;
+        return KB_OK;
+    }
     KB_TRY(dbuf_ensure(ctx, ctx->d_cursor, (size_t)(n + 2) * 8));
     uint64_t *d = (uint64_t *)ctx->d_cursor.p;  // [0]=local, [1..n]=gathered, [n+1]=min
-    KB_CUDA(ctx, cudaMemcpyAsync(d, &local_rev, 8, cudaMemcpyHostToDevice, ctx->stream));
+    KB_TRY(hbuf_ensure(ctx, ctx->h_stage2, 64));
+    *(uint64_t *)ctx->h_stage2.p = local_rev;
+    KB_CUDA(ctx, cudaMemcpyAsync(d, ctx->h_stage2.p, 8, cudaMemcpyHostToDevice, ctx->stream));
     int rc = a->AllGather(d, d + 1, 1, /*ncclUint64*/ 5, ctx->nccl_comm, ctx->stream);
     if (rc != 0) return kb_fail(ctx, KB_ENCCL, "ncclAllGather: %s", a->GetErrorString ? a->GetErrorString(rc) : "?");
     KB_LAUNCH(ctx, "cursor_min", (uint64_t)n * 8, (k_cursor_min<<<1, 1, 0, ctx->stream>>>(d + 1, n, d + 1 + n)));

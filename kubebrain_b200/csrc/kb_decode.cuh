@@ -10,6 +10,10 @@
 // Replaces coder.Decode (pkg/backend/coder/normal.go:58-70) and the per-record front half of worker.run
 // (pkg/backend/scanner/scanner.go:430-453, 471-491, 566-591): decode, TTL expiry, revision visibility,
 // tombstone test, deleted-flag revision-record test.  Warps are persistent and fully independent (no CTA barrier).
+//
+// Per-warp software pipeline (every stage one iteration apart, so no load is waited for in the iteration that
+// issues it):   tile descriptor -> record directory (koff16/klen/vlen/voff16) -> key bytes (cp.async) + 16-byte
+// value probe of 9-byte values -> decode.
 #pragma once
 
 #include "kb_internal.cuh"
@@ -44,42 +48,75 @@ __device__ __forceinline__ bool contains_events(const uint8_t *uk, uint32_t n)  
     return false;
 }
 
-// everything a warp needs to know about one 32-record sub-tile; the global loads that fill it are issued two
-// iterations before it is processed
+// pipeline stage 0: the tile a sub-tile belongs to
+struct TileRef {
+    uint32_t valid, sid;
+    TileDev t;
+};
+
+__device__ __forceinline__ TileRef fetch_tile(const TileDev *__restrict__ tiles, uint32_t sid, uint32_t n_sub)
+{
+    TileRef r;
+    r.valid = sid < n_sub;
+    r.sid = sid;
+    if (r.valid) {
+        const uint4 *p = (const uint4 *)(tiles + (sid >> 5));
+        const uint4 a = __ldg(p), b = __ldg(p + 1);
+        r.t.req = a.x;
+        r.t.rec0 = a.y;
+        r.t.n = a.z;
+        r.t.flat0 = a.w;
+        r.t.lo = b.x;
+        r.t.pad = b.y;
+        r.t.read_rev = ((uint64_t)b.w << 32) | b.z;
+    } else {
+        r.t.req = r.t.rec0 = r.t.n = r.t.flat0 = r.t.lo = r.t.pad = 0;
+        r.t.read_rev = 0;
+    }
+    return r;
+}
+
+// everything a warp needs to know about one 32-record sub-tile
 struct SubDesc {
     uint32_t valid;     // sub-tile exists
     uint32_t sid;       // flat sub-tile id (= flat slot / 32)
     uint32_t r0, nrec;  // first record, records in the sub-tile (0 for padding sub-tiles)
     uint32_t lo;        // first record of the request (the LCP of that record is never used)
     uint64_t read_rev;
-    // per lane
+    // per lane (stage 1)
     uint32_t ko, kl, vl;  // koff16[r], klen[r], vlen[r]
+    uint64_t vo;          // voff16[r]
     uint32_t pko, pkl;    // lane 0 only: koff16[r0-1], klen[r0-1] when r0 > lo
+    // stage 2
+    uint32_t base16, span;  // staged chunk interval [base16, base16+span)
+    uint4 v0;               // first 16 bytes of the value when it has to be inspected
 };
 
-__device__ __forceinline__ SubDesc load_desc(const StoreDev &st, const ReqDev *__restrict__ reqs,
-                                             const TileDev *__restrict__ tiles, uint32_t sid, uint32_t n_sub,
-                                             uint32_t lane)
+// pipeline stage 1: the record directory of the sub-tile (all loads independent of each other)
+__device__ __forceinline__ SubDesc load_desc(const StoreDev &st, const TileRef &tr, uint32_t lane)
 {
     SubDesc d;
-    d.valid = sid < n_sub;
-    d.sid = sid;
+    d.valid = tr.valid;
+    d.sid = tr.sid;
     d.r0 = d.nrec = d.lo = 0;
     d.read_rev = 0;
     d.ko = d.kl = d.vl = d.pko = d.pkl = 0;
+    d.vo = 0;
+    d.base16 = d.span = 0;
+    d.v0 = make_uint4(0, 0, 0, 0);
     if (!d.valid) return d;
-    const TileDev tile = tiles[sid >> 5];
-    const uint32_t sub = sid & 31;
-    if (sub * 32 >= tile.n) return d;  // padding sub-tile of the request's last tile
-    d.r0 = tile.rec0 + sub * 32;
-    d.nrec = min(32u, tile.n - sub * 32);
-    d.lo = tile.lo;
-    d.read_rev = tile.read_rev;
+    const uint32_t sub = tr.sid & 31;
+    if (sub * 32 >= tr.t.n) return d;  // padding sub-tile of the request's last tile
+    d.r0 = tr.t.rec0 + sub * 32;
+    d.nrec = min(32u, tr.t.n - sub * 32);
+    d.lo = tr.t.lo;
+    d.read_rev = tr.t.read_rev;
     if (lane < d.nrec) {
         const uint32_t r = d.r0 + lane;
         d.ko = st.koff16[r];
         d.kl = st.klen[r];
         d.vl = st.vlen[r];
+        d.vo = st.voff16[r];
     }
     if (lane == 0 && d.r0 > d.lo) {
         d.pko = st.koff16[d.r0 - 1];
@@ -88,24 +125,27 @@ __device__ __forceinline__ SubDesc load_desc(const StoreDev &st, const ReqDev *_
     return d;
 }
 
-// start the asynchronous copy of the sub-tile's key bytes (plus the record before it) into `buf`
-__device__ __forceinline__ void issue_stage(const StoreDev &st, const SubDesc &d, uint4 *buf, uint32_t lane)
+// pipeline stage 2: start the asynchronous copy of the sub-tile's key bytes (plus the record before it) into `buf`
+// and the value probe of the 9-byte values (tombstone literal / deleted-flag revision record)
+__device__ __forceinline__ void issue_stage(const StoreDev &st, const ScanMode &mode, SubDesc &d, uint4 *buf,
+                                            uint32_t lane)
 {
     if (!d.valid || d.nrec == 0) return;
     const bool halo = d.r0 > d.lo;
-    const uint32_t base16 = __shfl_sync(0xffffffffu, halo ? d.pko : d.ko, 0);
+    d.base16 = __shfl_sync(0xffffffffu, halo ? d.pko : d.ko, 0);
     const uint32_t end16 = __shfl_sync(0xffffffffu, d.ko + ((d.kl + 15) >> 4), d.nrec - 1);
-    const uint32_t span = end16 - base16;
-    if (span <= KB_WARP_STAGE_CHUNKS) {
-        const uint4 *src = st.kslab + base16;
-        for (uint32_t c = lane; c < span; c += 32) cp_async16(buf + c, src + c);
+    d.span = end16 - d.base16;
+    if (d.span <= KB_WARP_STAGE_CHUNKS) {
+        const uint4 *src = st.kslab + d.base16;
+        for (uint32_t c = lane; c < d.span; c += 32) cp_async16(buf + c, src + c);
     }
+    // only 9-byte values are ever inspected by the range path; the TTL sweep also reads revision-record values
+    if (lane < d.nrec && d.vl >= 8 && (d.vl == 9 || mode.ttl_scan)) d.v0 = st.vslab[d.vo];
 }
 
 template <bool STAGED>
-__device__ __forceinline__ uint32_t decode_record(const StoreDev &st, const ScanMode &mode, const SubDesc &d,
-                                                  const uint4 *kp, const uint4 *pp, uint32_t len, uint32_t plen,
-                                                  bool has_prev, uint32_t r)
+__device__ __forceinline__ uint32_t decode_record(const ScanMode &mode, const SubDesc &d, const uint4 *kp,
+                                                  const uint4 *pp, uint32_t len, uint32_t plen, bool has_prev)
 {
     const uint8_t *kb = (const uint8_t *)kp;
     uint32_t lcp = KB_LCP_INF;
@@ -156,8 +196,7 @@ __device__ __forceinline__ uint32_t decode_record(const StoreDev &st, const Scan
         flags |= KB_M_DEC_OK;
         if (rev == 0) flags |= KB_M_REV0;
         const uint32_t vl = d.vl;
-        uint4 v0 = make_uint4(0, 0, 0, 0);
-        if (vl >= 8 && (vl == 9 || (mode.ttl_scan && rev == 0))) v0 = st.vslab[st.voff16[r]];
+        const uint4 v0 = d.v0;
         const uint64_t vrev = ((uint64_t)bswap32(v0.x) << 32) | bswap32(v0.y);
         bool expired = false;
         if (mode.ttl_scan && contains_events(kb + 4, len - 13)) {  // compactIfExpired scanner.go:566-591
@@ -188,6 +227,7 @@ __device__ __forceinline__ uint32_t decode_record(const StoreDev &st, const Scan
     return lcp | flags;
 }
 
+// pipeline stage 3
 __device__ __forceinline__ void process_sub(const StoreDev &st, const ScanMode &mode, const SubDesc &d,
                                             const uint4 *buf, uint32_t lane, uint32_t *__restrict__ meta,
                                             uint2 *__restrict__ sub_agg)
@@ -198,10 +238,7 @@ __device__ __forceinline__ void process_sub(const StoreDev &st, const ScanMode &
         return;
     }
     const bool valid = lane < d.nrec;
-    const bool halo = d.r0 > d.lo;
-    const uint32_t base16 = __shfl_sync(FULLM, halo ? d.pko : d.ko, 0);
-    const uint32_t end16 = __shfl_sync(FULLM, d.ko + ((d.kl + 15) >> 4), d.nrec - 1);
-    const bool staged = (end16 - base16) <= KB_WARP_STAGE_CHUNKS;
+    const bool staged = d.span <= KB_WARP_STAGE_CHUNKS;
     // previous record's offset / length: lane-1, or the halo record for lane 0
     uint32_t pko = __shfl_up_sync(FULLM, d.ko, 1), pkl = __shfl_up_sync(FULLM, d.kl, 1);
     if (lane == 0) {
@@ -213,11 +250,11 @@ __device__ __forceinline__ void process_sub(const StoreDev &st, const ScanMode &
         const uint32_t r = d.r0 + lane;
         const bool has_prev = r > d.lo;
         if (staged) {
-            word = decode_record<true>(st, mode, d, buf + (d.ko - base16), buf + (has_prev ? pko - base16 : 0), d.kl, pkl,
-                                       has_prev, r);
+            word = decode_record<true>(mode, d, buf + (d.ko - d.base16), buf + (has_prev ? pko - d.base16 : 0), d.kl, pkl,
+                                       has_prev);
         } else {
-            word = decode_record<false>(st, mode, d, st.kslab + d.ko, st.kslab + (has_prev ? pko : d.ko), d.kl, pkl,
-                                        has_prev, r);
+            word = decode_record<false>(mode, d, st.kslab + d.ko, st.kslab + (has_prev ? pko : d.ko), d.kl, pkl,
+                                        has_prev);
         }
         meta[d.sid * 32 + lane] = word;
     }
@@ -230,8 +267,7 @@ __device__ __forceinline__ void process_sub(const StoreDev &st, const ScanMode &
         if (lane <= top) mval = KB_LCP_INF;
         L = d.sid * 32 + top;
     }
-#pragma unroll
-    for (int s = 16; s > 0; s >>= 1) mval = min(mval, __shfl_xor_sync(FULLM, mval, s));
+    mval = __reduce_min_sync(FULLM, mval);
     if (lane == 0) sub_agg[d.sid] = make_uint2(L, mval);
 }
 
@@ -245,20 +281,25 @@ k_decode_lcp(StoreDev st, const ReqDev *__restrict__ reqs, const TileDev *__rest
     const uint32_t stride = gridDim.x * DECODE_WARPS;
     uint32_t sid = blockIdx.x * DECODE_WARPS + warp;
 
-    // software pipeline: descriptor loads run two sub-tiles ahead, the key bytes one sub-tile ahead
-    SubDesc dB = load_desc(st, reqs, tiles, sid, n_sub, lane);
+    // prologue: fill the pipeline
+    TileRef tA = fetch_tile(tiles, sid, n_sub);
     sid += stride;
-    SubDesc dA = load_desc(st, reqs, tiles, sid, n_sub, lane);
+    SubDesc dB = load_desc(st, tA, lane);
+    tA = fetch_tile(tiles, sid, n_sub);
     sid += stride;
-    issue_stage(st, dB, buf0, lane);
+    SubDesc dA = load_desc(st, tA, lane);
+    tA = fetch_tile(tiles, sid, n_sub);
+    sid += stride;
+    issue_stage(st, mode, dB, buf0, lane);
     cp_async_commit();
     uint32_t it = 0;
     while (dB.valid) {
-        const SubDesc dC = dB;
-        dB = dA;
-        dA = load_desc(st, reqs, tiles, sid, n_sub, lane);
+        const SubDesc dC = dB;  // key bytes + value probe in flight since the previous iteration
+        dB = dA;                // directory loaded one iteration ago
+        dA = load_desc(st, tA, lane);
+        tA = fetch_tile(tiles, sid, n_sub);
         sid += stride;
-        issue_stage(st, dB, buf0 + ((it + 1) & 1) * KB_WARP_STAGE_CHUNKS, lane);
+        issue_stage(st, mode, dB, buf0 + ((it + 1) & 1) * KB_WARP_STAGE_CHUNKS, lane);
         cp_async_commit();
         cp_async_wait<1>();  // everything but the newest group has landed: dC's bytes are in shared memory
         __syncwarp();

@@ -6,6 +6,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <chrono>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -159,7 +160,8 @@ struct kb_ctx {
     StoreDev st{};
     DBuf d_kslab, d_koff16, d_klen, d_vslab, d_voff16, d_vlen;
     uint64_t key_bytes = 0, val_bytes = 0;
-    std::vector<uint32_t> h_koff16;  // host copy, algorithmic-byte accounting only
+    std::vector<uint32_t> h_koff16;  // host copies of the slab offsets: byte accounting and response-arena bounds
+    std::vector<uint64_t> h_voff16;
     bool compact_present = false;
     uint64_t compact_rev = 0;
 
@@ -254,6 +256,19 @@ void prof_end(kb_ctx *ctx);
         (ctx)->launches++;                                    \
         if (_p) prof_end((ctx));                              \
     } while (0)
+
+// host wall-clock segments (only with kb_prof_enable(ctx, 1)): where the non-kernel time of a call goes
+typedef std::chrono::steady_clock::time_point kb_tp;
+static inline kb_tp kb_now() { return std::chrono::steady_clock::now(); }
+static inline void kb_seg(kb_ctx *ctx, const char *name, kb_tp &t)
+{
+    if (ctx->prof_on != 1) return;
+    kb_tp n = kb_now();
+    int i = prof_index(ctx, name);
+    ctx->prof[i].launches++;
+    ctx->prof[i].ms += std::chrono::duration<double, std::milli>(n - t).count();
+    t = n;
+}
 
 // generic exclusive scans on the ctx stream (kb_scan_util.cu)
 int scan_exclusive_u32(kb_ctx *ctx, const uint32_t *in, uint32_t *out, uint32_t n, uint32_t *total_dev);

@@ -497,11 +497,11 @@ struct GatherJob {
 
 __global__ void __launch_bounds__(256)
 k_gather_jobs(StoreDev st, const ReqDev *__restrict__ reqs, uint32_t nreq, const uint64_t *__restrict__ job_first,
-              const uint64_t *__restrict__ arena_base, uint64_t n_kvs, const uint32_t *__restrict__ sel,
+              const uint64_t *__restrict__ arena_base, const uint32_t *__restrict__ sel,
               const uint64_t *__restrict__ slot, GatherJob *__restrict__ jobs, GatherOut out)
 {
-    const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n_kvs) return;
+    const uint64_t n_kvs = job_first[nreq];  // written by k_req_finalize
+    for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n_kvs; k += (uint64_t)gridDim.x * blockDim.x) {
     uint32_t lo = 0, hi = nreq;  // request of kv k: last q with job_first[q] <= k
     while (hi - lo > 1) {
         uint32_t mid = (lo + hi) >> 1;
@@ -525,39 +525,147 @@ k_gather_jobs(StoreDev st, const ReqDev *__restrict__ reqs, uint32_t nreq, const
     out.key_len[k] = kl - 13;
     out.val_off[k] = dst_byte + (uint64_t)j.nk * 16;
     out.val_len[k] = vl;
+    out.rev[k] = be64_bytes((const uint8_t *)(st.kslab + j.ksrc16) + kl - 8);
+    }
 }
 
-// one warp per emitted kv: [internal key, padded][value, padded] as one stream of 16-byte chunks,
-// 8 independent loads in flight per lane
-__global__ void __launch_bounds__(256)
-k_gather(StoreDev st, const GatherJob *__restrict__ jobs, uint64_t n_kvs, uint4 *__restrict__ arena,
-         uint64_t *__restrict__ out_rev)
+// ---- k_gather: bulk-TMA copy of every winner's [internal key, padded][value, padded] into the response arena.
+// One elected lane per warp drives a ring of GATHER_STAGES shared-memory buffers: cp.async.bulk global->shared
+// (completion on an mbarrier), then cp.async.bulk shared->global into the arena.  A kv larger than one buffer is
+// moved in pieces.  The copy engine generates full-line requests; the SM only issues two or three instructions per
+// 2.5 KB piece.
+constexpr int GATHER_WARPS = 8;
+constexpr int GATHER_STAGES = 6;
+constexpr int GATHER_DIST = GATHER_STAGES - 2;   // pieces in flight per warp
+constexpr uint32_t GATHER_PIECE = 160;           // 16-byte chunks per buffer (2560 B)
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_wait_parity(uint64_t *bar, uint32_t parity)
 {
-    const uint32_t lane = threadIdx.x & 31;
-    const uint64_t k = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (k >= n_kvs) return;
-    const uint4 *jp = (const uint4 *)(jobs + k);
-    const uint4 j0 = __ldg(jp), j1 = __ldg(jp + 1);
-    const uint64_t dst16 = ((uint64_t)j0.y << 32) | j0.x, vsrc16 = ((uint64_t)j0.w << 32) | j0.z;
-    const uint32_t ksrc16 = j1.x, nk = j1.y, nv = j1.z, kl = j1.w;
-    const uint4 *ks = st.kslab + ksrc16;
-    const uint4 *vs = st.vslab + vsrc16;
-    uint4 *dst = arena + dst16;
-    const uint32_t n = nk + nv;
-    for (uint32_t c0 = lane; c0 < n; c0 += 32 * 8) {
-        uint4 v[8];
-#pragma unroll
-        for (int j = 0; j < 8; j++) {
-            const uint32_t c = c0 + j * 32;
-            if (c < n) v[j] = ldg_stream(c < nk ? ks + c : vs + (c - nk));
-        }
-#pragma unroll
-        for (int j = 0; j < 8; j++) {
-            const uint32_t c = c0 + j * 32;
-            if (c < n) stg_stream(dst + c, v[j]);
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "KB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra KB_DONE;\n"
+        "bra KB_WAIT;\n"
+        "KB_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+__global__ void __launch_bounds__(GATHER_WARPS * 32, 1)
+k_gather(StoreDev st, const GatherJob *__restrict__ jobs, const uint64_t *__restrict__ n_kvs_dev,
+         uint4 *__restrict__ arena)
+{
+    extern __shared__ __align__(128) uint4 gbuf[];  // GATHER_WARPS x GATHER_STAGES x GATHER_PIECE
+    __shared__ uint64_t bars[GATHER_WARPS * GATHER_STAGES];
+    __shared__ uint64_t ring_dst[GATHER_WARPS * GATHER_STAGES];
+    __shared__ uint32_t ring_len[GATHER_WARPS * GATHER_STAGES];
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane != 0) return;  // one driver lane per warp; the data never passes through registers
+    uint4 *buf = gbuf + (size_t)warp * GATHER_STAGES * GATHER_PIECE;
+    uint64_t *bar = bars + warp * GATHER_STAGES;
+    uint64_t *rdst = ring_dst + warp * GATHER_STAGES;
+    uint32_t *rlen = ring_len + warp * GATHER_STAGES;
+    for (int s = 0; s < GATHER_STAGES; s++)
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar + s)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+
+    const uint64_t n_kvs = *n_kvs_dev;
+    const uint64_t nwarps = (uint64_t)gridDim.x * GATHER_WARPS;
+    uint32_t t_issue = 0, t_store = 0;  // pieces issued / stored by this warp
+
+    // wait for the oldest in-flight piece and send it to the arena
+    auto retire = [&]() {
+        const uint32_t st_i = t_store % GATHER_STAGES;
+        mbar_wait_parity(bar + st_i, (t_store / GATHER_STAGES) & 1);
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(arena + rdst[st_i]),
+                     "r"(smem_u32(buf + st_i * GATHER_PIECE)), "r"(rlen[st_i] * 16)
+                     : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        t_store++;
+    };
+
+    for (uint64_t k = (uint64_t)blockIdx.x * GATHER_WARPS + warp; k < n_kvs; k += nwarps) {
+        const uint4 *jp = (const uint4 *)(jobs + k);
+        const uint4 j0 = __ldg(jp), j1 = __ldg(jp + 1);
+        const uint64_t dst16 = ((uint64_t)j0.y << 32) | j0.x, vsrc16 = ((uint64_t)j0.w << 32) | j0.z;
+        const uint32_t ksrc16 = j1.x, nk = j1.y, nv = j1.z;
+        const uint32_t n = nk + nv;
+        for (uint32_t c0 = 0; c0 < n; c0 += GATHER_PIECE) {
+            const uint32_t len = min(GATHER_PIECE, n - c0);
+            if (t_issue - t_store >= (uint32_t)GATHER_DIST) retire();
+            const uint32_t st_i = t_issue % GATHER_STAGES;
+            // the buffer was last read by the bulk store of piece t_issue - STAGES; at most two younger store groups
+            // can still be pending when it has finished reading shared memory
+            asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar + st_i)),
+                         "r"(len * 16)
+                         : "memory");
+            uint4 *dstbuf = buf + st_i * GATHER_PIECE;
+            const uint32_t kpart = c0 < nk ? min(nk - c0, len) : 0;  // chunks of this piece that come from the key
+            if (kpart)
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                 smem_u32(dstbuf)),
+                             "l"(st.kslab + ksrc16 + c0), "r"(kpart * 16), "r"(smem_u32(bar + st_i))
+                             : "memory");
+            if (len > kpart) {
+                const uint32_t v0c = (c0 + kpart) - nk;  // first value chunk of this piece
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                 smem_u32(dstbuf + kpart)),
+                             "l"(st.vslab + vsrc16 + v0c), "r"((len - kpart) * 16), "r"(smem_u32(bar + st_i))
+                             : "memory");
+            }
+            rdst[st_i] = dst16 + c0;
+            rlen[st_i] = len;
+            t_issue++;
         }
     }
-    if (lane == 0) out_rev[k] = be64_bytes((const uint8_t *)ks + kl - 8);
+    while (t_store < t_issue) retire();
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+// single CTA: per-request emitted count / response bytes (limit applied) and their exclusive prefixes over the
+// requests: job_first[q] = first kv of request q, arena_base[q] = first arena byte of request q; [nreq] = totals
+__global__ void __launch_bounds__(256)
+k_req_finalize(const ReqDev *__restrict__ reqs, uint32_t nreq, const ReqOut *__restrict__ rout,
+               uint64_t *__restrict__ job_first, uint64_t *__restrict__ arena_base)
+{
+    __shared__ uint64_t ws2[18];
+    __shared__ uint64_t carry[2];
+    if (threadIdx.x == 0) carry[0] = carry[1] = 0;
+    __syncthreads();
+    for (uint32_t c0 = 0; c0 < nreq; c0 += 256) {
+        const uint32_t q = c0 + threadIdx.x;
+        uint64_t ne = 0, nb = 0;
+        if (q < nreq) {
+            const ReqOut o = rout[q];
+            const int64_t lim = reqs[q].limit;
+            ne = (lim > 0 && o.total > (uint64_t)lim) ? (uint64_t)lim : o.total;
+            nb = lim > 0 ? o.capped_aux : o.total_aux;
+        }
+        uint64_t ea, eb, ta, tb;
+        block_excl_scan2(ne, nb, ea, eb, ta, tb, ws2);
+        const uint64_t ca = carry[0], cb = carry[1];
+        if (q < nreq) {
+            job_first[q] = ca + ea;
+            arena_base[q] = cb + eb;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            carry[0] = ca + ta;
+            carry[1] = cb + tb;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        job_first[nreq] = carry[0];
+        arena_base[nreq] = carry[1];
+    }
 }
 
 }  // namespace
@@ -741,8 +849,10 @@ extern "C" int kb_range_batch(kb_ctx *ctx, const kb_range_req *reqs, uint64_t nr
             return kb_fail(ctx, KB_ECOMPACTED, "range stream revision %llu less than compact revision %llu",
                            (unsigned long long)reqs[q].read_rev, (unsigned long long)ctx->compact_rev);
     }
+    kb_tp tseg = kb_now();
     Resolved R;
     KB_TRY(resolve_requests(ctx, reqs, nreq, true, R));
+    kb_seg(ctx, "host:range_resolve+sync", tseg);
     KB_TRY(upload_layout(ctx, R));
     const uint32_t nt = (uint32_t)R.tiles.size();
     KB_TRY(dbuf_ensure(ctx, ctx->d_sel, std::max<uint64_t>(R.total_sel, 1) * 4));
@@ -783,28 +893,83 @@ extern "C" int kb_range_batch(kb_ctx *ctx, const kb_range_req *reqs, uint64_t nr
                                                         (uint32_t *)ctx->d_sel.p, (uint64_t *)ctx->d_slot.p, d_rout)));
     }
     KB_CUDA(ctx, cudaGetLastError());
+
+    // Response arena: sized by an upper bound the host knows without a round trip (all key+value bytes of the examined
+    // record intervals), so the gather is enqueued right behind the placement and the only synchronisation left is
+    // the final one (the arena is pooled, so steady-state calls reuse it).
+    const bool want_kvs = out_mode != KB_OUT_COUNT && R.total_sel > 0;
+    uint64_t ub_bytes = 0;
+    for (auto &r : R.reqs)
+        ub_bytes += ((uint64_t)(ctx->h_koff16[r.hi] - ctx->h_koff16[r.lo]) + (ctx->h_voff16[r.hi] - ctx->h_voff16[r.lo])) * 16;
+    kb_result *res = kb_result_new(1, out_mode);
+    DBuf d_om;
+    GatherOut go;
+    memset(&go, 0, sizeof(go));
+    const uint64_t cap_kvs = R.total_sel;
+    const size_t meta_cap = cap_kvs * 36 + 64;
+    int rc = KB_OK;
+    if (want_kvs) {
+        rc = pool_get_dev(ctx, meta_cap, &d_om);
+        if (rc == KB_OK) rc = pool_get_dev(ctx, ub_bytes + 64, &res->d_bytes);
+        if (rc == KB_OK) rc = dbuf_ensure(ctx, ctx->d_jobs, (nreq + 1) * 16);
+        if (rc == KB_OK) rc = dbuf_ensure(ctx, ctx->d_gjobs, std::max<uint64_t>(cap_kvs, 1) * sizeof(GatherJob));
+        if (rc != KB_OK) {
+            pool_put_dev(ctx, d_om);
+            kb_result_free(nullptr, res);
+            return rc;
+        }
+        uint8_t *om = (uint8_t *)d_om.p;
+        go.rev = (uint64_t *)om;
+        go.key_off = go.rev + cap_kvs;
+        go.val_off = go.key_off + cap_kvs;
+        go.rec_idx = (uint32_t *)(go.val_off + cap_kvs);
+        go.key_len = go.rec_idx + cap_kvs;
+        go.val_len = go.key_len + cap_kvs;
+        uint64_t *d_jobfirst = (uint64_t *)ctx->d_jobs.p, *d_arenabase = d_jobfirst + nreq + 1;
+        GatherJob *d_gj = (GatherJob *)ctx->d_gjobs.p;
+        KB_LAUNCH(ctx, "k_req_finalize", nreq * 64,
+                  (k_req_finalize<<<1, 256, 0, ctx->stream>>>(d_reqs, (uint32_t)nreq, d_rout, d_jobfirst, d_arenabase)));
+        const unsigned jgrid = (unsigned)std::min<uint64_t>((cap_kvs + 255) / 256, 148 * 8);
+        KB_LAUNCH(ctx, "k_gather_jobs", cap_kvs * 20,
+                  (k_gather_jobs<<<jgrid, 256, 0, ctx->stream>>>(ctx->st, d_reqs, (uint32_t)nreq, d_jobfirst, d_arenabase,
+                                                                (const uint32_t *)ctx->d_sel.p,
+                                                                (const uint64_t *)ctx->d_slot.p, d_gj, go)));
+        const size_t gsmem = (size_t)GATHER_WARPS * GATHER_STAGES * GATHER_PIECE * 16;
+        static bool gattr = false;
+        if (!gattr) {
+            cudaFuncSetAttribute(k_gather, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem);
+            gattr = true;
+        }
+        const unsigned ggrid = (unsigned)std::min<uint64_t>((cap_kvs + GATHER_WARPS - 1) / GATHER_WARPS, 148);
+        KB_LAUNCH(ctx, "k_gather", 0,
+                  (k_gather<<<ggrid, GATHER_WARPS * 32, gsmem, ctx->stream>>>(ctx->st, d_gj, d_jobfirst + nreq,
+                                                                              (uint4 *)res->d_bytes.p)));
+    }
     std::vector<ReqOut> rout(std::max<uint64_t>(nreq, 1));
     if (nreq) {
         KB_TRY(hbuf_ensure(ctx, ctx->h_stage, nreq * sizeof(ReqOut) + 64));
         KB_CUDA(ctx, cudaMemcpyAsync(ctx->h_stage.p, d_rout, nreq * sizeof(ReqOut), cudaMemcpyDeviceToHost,
                                      ctx->stream));
     }
-    KB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    kb_seg(ctx, "host:range_launch", tseg);
+    cudaError_t e1 = cudaStreamSynchronize(ctx->stream);
+    kb_seg(ctx, "host:range_sync", tseg);
+    if (e1 != cudaSuccess) {
+        pool_put_dev(ctx, d_om);
+        kb_result_free(nullptr, res);
+        return kb_cuda_fail(ctx, e1, "range scan");
+    }
     if (nreq) memcpy(rout.data(), ctx->h_stage.p, nreq * sizeof(ReqOut));
 
-    kb_result *res = kb_result_new(1, out_mode);
     res->req_first.resize(nreq + 1);
     res->req_count.resize(nreq);
     res->req_examined.resize(nreq);
-    std::vector<uint64_t> arena_base(nreq + 1), job_first(nreq + 1);
     uint64_t nk = 0, nbytes = 0;
     for (uint64_t q = 0; q < nreq; q++) {
         uint64_t ne = rout[q].total;
         bool capped = R.reqs[q].limit > 0 && ne > (uint64_t)R.reqs[q].limit;
         if (capped) ne = (uint64_t)R.reqs[q].limit;
         res->req_first[q] = nk;
-        job_first[q] = nk;
-        arena_base[q] = nbytes;
         if (out_mode == KB_OUT_COUNT) {
             res->req_count[q] = rout[q].total;  // emptyResultReceiver never stops the loop
             res->req_examined[q] = R.reqs[q].hi - R.reqs[q].lo;
@@ -812,84 +977,65 @@ extern "C" int kb_range_batch(kb_ctx *ctx, const kb_range_req *reqs, uint64_t nr
             res->req_count[q] = rout[q].limit_stop ? 0 : ne;  // (0, nil) when the limit stopped the loop (Q4)
             res->req_examined[q] = rout[q].examined;
             nk += ne;
-            nbytes += capped || R.reqs[q].limit > 0 ? rout[q].capped_aux : rout[q].total_aux;
+            nbytes += R.reqs[q].limit > 0 ? rout[q].capped_aux : rout[q].total_aux;
         }
     }
     res->req_first[nreq] = nk;
-    job_first[nreq] = nk;
-    arena_base[nreq] = nbytes;
     res->n_kvs = nk;
     res->n_bytes = nbytes;
+    if (ctx->prof_on) {  // the gather's algorithmic bytes are only known now
+        int gi = prof_index(ctx, "k_gather");
+        ctx->prof[gi].bytes += 2 * nbytes + nk * 40;
+    }
 
-    if (out_mode != KB_OUT_COUNT && nk > 0) {
-        // metadata SoA on the device: rec_idx u32 | key_len u32 | val_len u32 | rev u64 | key_off u64 | val_off u64
-        const size_t meta_bytes = nk * (4 + 4 + 4 + 8 + 8 + 8) + 64;
-        DBuf d_om;
-        int rc = pool_get_dev(ctx, meta_bytes, &d_om);
-        if (rc == KB_OK) rc = pool_get_dev(ctx, nbytes + 16, &res->d_bytes);
-        if (rc == KB_OK) rc = dbuf_ensure(ctx, ctx->d_jobs, (nreq + 1) * 16);
-        if (rc == KB_OK) rc = hbuf_ensure(ctx, ctx->h_stage2, (nreq + 1) * 16 + 64);
-        if (rc != KB_OK) {
-            pool_put_dev(ctx, d_om);
-            kb_result_free(nullptr, res);
-            return rc;
-        }
-        uint64_t *hj = (uint64_t *)ctx->h_stage2.p;
-        memcpy(hj, job_first.data(), (nreq + 1) * 8);
-        memcpy(hj + nreq + 1, arena_base.data(), (nreq + 1) * 8);
-        cudaMemcpyAsync(ctx->d_jobs.p, hj, (nreq + 1) * 16, cudaMemcpyHostToDevice, ctx->stream);
-        uint8_t *om = (uint8_t *)d_om.p;
-        GatherOut go;
-        go.rev = (uint64_t *)om;
-        go.key_off = go.rev + nk;
-        go.val_off = go.key_off + nk;
-        go.rec_idx = (uint32_t *)(go.val_off + nk);
-        go.key_len = go.rec_idx + nk;
-        go.val_len = go.key_len + nk;
-        rc = dbuf_ensure(ctx, ctx->d_gjobs, nk * sizeof(GatherJob));
-        if (rc != KB_OK) {
-            pool_put_dev(ctx, d_om);
-            kb_result_free(nullptr, res);
-            return rc;
-        }
-        GatherJob *d_jobs = (GatherJob *)ctx->d_gjobs.p;
-        KB_LAUNCH(ctx, "k_gather_jobs", nk * 80,
-                  (k_gather_jobs<<<(unsigned)((nk + 255) / 256), 256, 0, ctx->stream>>>(
-                      ctx->st, d_reqs, (uint32_t)nreq, (const uint64_t *)ctx->d_jobs.p,
-                      (const uint64_t *)ctx->d_jobs.p + nreq + 1, nk, (const uint32_t *)ctx->d_sel.p,
-                      (const uint64_t *)ctx->d_slot.p, d_jobs, go)));
-        KB_LAUNCH(ctx, "k_gather", 2 * nbytes + nk * 40,
-                  (k_gather<<<(unsigned)((nk + 7) / 8), 256, 0, ctx->stream>>>(ctx->st, d_jobs, nk,
-                                                                              (uint4 *)res->d_bytes.p, go.rev)));
+    if (want_kvs && nk > 0) {
         if (out_mode == KB_OUT_HOST) {
-            rc = pool_get_host(ctx, meta_bytes, &res->h_meta);
+            // per-kv arrays: six strided pieces of the capacity-sized device layout -> one compact host layout
+            rc = pool_get_host(ctx, nk * 36 + 64, &res->h_meta);
             if (rc == KB_OK) rc = pool_get_host(ctx, nbytes + 16, &res->h_bytes);
             if (rc == KB_OK) {
-                cudaMemcpyAsync(res->h_meta.p, d_om.p, nk * 36, cudaMemcpyDeviceToHost, ctx->stream);
+                uint8_t *hm = (uint8_t *)res->h_meta.p;
+                const void *srcs[6] = {go.rev, go.key_off, go.val_off, go.rec_idx, go.key_len, go.val_len};
+                const size_t esz[6] = {8, 8, 8, 4, 4, 4};
+                size_t off = 0;
+                for (int i = 0; i < 6; i++) {
+                    cudaMemcpyAsync(hm + off, srcs[i], nk * esz[i], cudaMemcpyDeviceToHost, ctx->stream);
+                    off += nk * esz[i];
+                }
                 cudaMemcpyAsync(res->h_bytes.p, res->d_bytes.p, nbytes, cudaMemcpyDeviceToHost, ctx->stream);
             }
-        }
-        cudaError_t e = cudaStreamSynchronize(ctx->stream);
-        if (rc == KB_OK && e != cudaSuccess) rc = kb_cuda_fail(ctx, e, "gather");
-        if (rc != KB_OK) {
-            pool_put_dev(ctx, d_om);
-            kb_result_free(nullptr, res);
-            return rc;
-        }
-        // per-kv arrays: host copies for KB_OUT_HOST, the device arrays themselves for KB_OUT_DEVICE
-        uint8_t *hm = out_mode == KB_OUT_HOST ? (uint8_t *)res->h_meta.p : (uint8_t *)d_om.p;
-        res->rev = (const uint64_t *)hm;
-        res->key_off = res->rev + nk;
-        res->val_off = res->key_off + nk;
-        res->rec_idx = (const uint32_t *)(res->val_off + nk);
-        res->key_len = res->rec_idx + nk;
-        res->val_len = res->key_len + nk;
-        if (out_mode == KB_OUT_HOST) {
+            cudaError_t e = cudaStreamSynchronize(ctx->stream);
+            kb_seg(ctx, "host:range_d2h", tseg);
+            if (rc == KB_OK && e != cudaSuccess) rc = kb_cuda_fail(ctx, e, "range D2H");
+            if (rc != KB_OK) {
+                pool_put_dev(ctx, d_om);
+                kb_result_free(nullptr, res);
+                return rc;
+            }
+            uint8_t *hm = (uint8_t *)res->h_meta.p;
+            res->rev = (const uint64_t *)hm;
+            res->key_off = res->rev + nk;
+            res->val_off = res->key_off + nk;
+            res->rec_idx = (const uint32_t *)(res->val_off + nk);
+            res->key_len = res->rec_idx + nk;
+            res->val_len = res->key_len + nk;
             pool_put_dev(ctx, d_om);
             pool_put_dev(ctx, res->d_bytes);
             res->d_bytes = DBuf();
         } else {
+            res->rev = go.rev;
+            res->key_off = go.key_off;
+            res->val_off = go.val_off;
+            res->rec_idx = go.rec_idx;
+            res->key_len = go.key_len;
+            res->val_len = go.val_len;
             res->d_vic = d_om;  // owned by the result (returned to the pool by kb_result_free)
+        }
+    } else {
+        pool_put_dev(ctx, d_om);
+        if (res->d_bytes.p) {
+            pool_put_dev(ctx, res->d_bytes);
+            res->d_bytes = DBuf();
         }
     }
     *out = res;

@@ -39,7 +39,7 @@ struct WatchTablesDev {
     uint32_t n_ids = 0, n_groups = 0, n_lens = 0, table_size = 0, max_len = 0;
     DBuf gprefix, goff16, glen, ghash, gstart, gmember, wgroup, wminrev, lens, table;
     // per-call scratch
-    DBuf gcnt, gbase, gfill, gclass, ematch, seg, seg_sorted, lists, bitmaps, pm, flag, wcnt, wlo, wstart, total;
+    DBuf zeros, gbase, gclass, ematch, seg, seg_sorted, bitmaps, pm, wcnt, wlo, wstart, total;
 };
 
 namespace {
@@ -76,9 +76,10 @@ struct TabDev {
 
 // ---- running max of the revisions inside each collector batch (filterByRevision strips only the LEADING
 //      events below min_rev, watch.go:153-159, so event i survives iff max(rev[batch start..i]) >= min_rev)
-__global__ void __launch_bounds__(128) k_batch_pm(EvDev ev, uint64_t *__restrict__ pm, uint32_t *__restrict__ nonmono)
+__device__ __forceinline__ void d_batch_pm(const EvDev &ev, uint64_t *__restrict__ pm, uint32_t *__restrict__ nonmono,
+                                           uint32_t vblock)
 {
-    const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const uint32_t w = (vblock * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (w >= ev.nb) return;
     const uint64_t lo = ev.batch_off[w], hi = ev.batch_off[w + 1];
     uint64_t carry = 0;
@@ -101,10 +102,10 @@ __global__ void __launch_bounds__(128) k_batch_pm(EvDev ev, uint64_t *__restrict
 
 // ---- per event and distinct prefix length: the group whose prefix the key starts with (or NONE).
 //      ematch[li * E + i]; group counts are aggregated inside the warp before touching memory.
-__global__ void __launch_bounds__(256)
-k_match_count(EvDev ev, TabDev tb, uint32_t *__restrict__ ematch, uint32_t *__restrict__ gcnt)
+__device__ __forceinline__ void d_match_count(const EvDev &ev, const TabDev &tb, uint32_t *__restrict__ ematch,
+                                              uint32_t *__restrict__ gcnt, uint32_t vblock)
 {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t i = vblock * blockDim.x + threadIdx.x;
     const uint32_t lane = threadIdx.x & 31;
     const bool valid = i < ev.n;
     const uint32_t klen = valid ? ev.klen[i] : 0;
@@ -145,6 +146,114 @@ k_match_count(EvDev ev, TabDev tb, uint32_t *__restrict__ ematch, uint32_t *__re
         if (valid) ematch[(uint64_t)li * ev.n + i] = g;
         const unsigned peers = __match_any_sync(FULL, g);
         if (g != KB_NONE && lane == (unsigned)(__ffs(peers) - 1)) atomicAdd(&gcnt[g], (uint32_t)__popc(peers));
+    }
+}
+
+// one launch: blocks [0, pm_blocks) compute the per-batch running max, the rest match events against the groups
+__global__ void __launch_bounds__(256)
+k_match_count(EvDev ev, TabDev tb, uint32_t pm_blocks, uint64_t *__restrict__ pm, uint32_t *__restrict__ nonmono,
+              uint32_t *__restrict__ ematch, uint32_t *__restrict__ gcnt)
+{
+    if (blockIdx.x < pm_blocks)
+        d_batch_pm(ev, pm, nonmono, blockIdx.x);
+    else if (tb.n_groups)
+        d_match_count(ev, tb, ematch, gcnt, blockIdx.x - pm_blocks);
+}
+
+// single CTA: exclusive scan of the group counts (segment offsets) + classification by count.
+// lists layout: [0]=n_medium [1]=n_large [2..2+G) medium groups [2+G..2+2G) large groups
+__global__ void __launch_bounds__(1024)
+k_group_scan_classify(uint32_t n_groups, const uint32_t *__restrict__ gcnt, uint32_t big_t, uint32_t max_large,
+                      uint32_t *__restrict__ gbase, uint32_t *__restrict__ gclass, uint32_t *__restrict__ lists)
+{
+    __shared__ uint32_t wsum[33];
+    __shared__ uint32_t carry_s;
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (uint32_t c0 = 0; c0 < n_groups; c0 += 1024) {
+        const uint32_t g = c0 + threadIdx.x;
+        const uint32_t n = g < n_groups ? gcnt[g] : 0;
+        uint32_t inc = n;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t o = __shfl_up_sync(FULL, inc, d);
+            if (lane >= (unsigned)d) inc += o;
+        }
+        if (lane == 31) wsum[wid] = inc;
+        __syncthreads();
+        if (wid == 0) {
+            uint32_t v = wsum[lane], iv = v;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                uint32_t o = __shfl_up_sync(FULL, iv, d);
+                if (lane >= (unsigned)d) iv += o;
+            }
+            wsum[lane] = iv - v;
+            if (lane == 31) wsum[32] = iv;
+        }
+        __syncthreads();
+        const uint32_t carry = carry_s;
+        if (g < n_groups) {
+            gbase[g] = carry + wsum[wid] + inc - n;
+            uint32_t cls = KB_NONE;  // NONE: small or medium (segment scatter); otherwise the bitmap slot
+            if (n > big_t) {
+                const uint32_t slot = atomicAdd(&lists[1], 1u);
+                if (slot < max_large) {  // cannot overflow: sum(gcnt) <= E * n_lens
+                    cls = slot;
+                    lists[2 + n_groups + slot] = g;
+                }
+            } else if (n > 32) {
+                lists[2 + atomicAdd(&lists[0], 1u)] = g;
+            }
+            gclass[g] = cls;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) carry_s = carry + wsum[32];
+        __syncthreads();
+    }
+}
+
+// single CTA: exclusive scan of the per-watcher delivery counts; wstart[W] = total
+__global__ void __launch_bounds__(1024)
+k_watcher_scan(uint32_t n, const uint64_t *__restrict__ wcnt, uint64_t *__restrict__ wstart, uint64_t *__restrict__ total)
+{
+    __shared__ uint64_t wsum[33];
+    __shared__ uint64_t carry_s;
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (uint32_t c0 = 0; c0 < n; c0 += 1024) {
+        const uint32_t w = c0 + threadIdx.x;
+        const uint64_t v0 = w < n ? wcnt[w] : 0;
+        uint64_t inc = v0;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint64_t o = __shfl_up_sync(FULL, inc, d);
+            if (lane >= (unsigned)d) inc += o;
+        }
+        if (lane == 31) wsum[wid] = inc;
+        __syncthreads();
+        if (wid == 0) {
+            uint64_t v = wsum[lane], iv = v;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                uint64_t o = __shfl_up_sync(FULL, iv, d);
+                if (lane >= (unsigned)d) iv += o;
+            }
+            wsum[lane] = iv - v;
+            if (lane == 31) wsum[32] = iv;
+        }
+        __syncthreads();
+        const uint64_t carry = carry_s;
+        if (w < n) wstart[w] = carry + wsum[wid] + inc - v0;
+        __syncthreads();
+        if (threadIdx.x == 0) carry_s = carry + wsum[32];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        wstart[n] = carry_s;
+        *total = carry_s;
     }
 }
 
@@ -196,11 +305,11 @@ k_scatter(uint32_t n_events, uint32_t n_lens, const uint32_t *__restrict__ ematc
 }
 
 // ---- segment sort: ascending event index per group
-__global__ void __launch_bounds__(256)
-k_sort_small(uint32_t n_groups, const uint32_t *__restrict__ gcnt, const uint32_t *__restrict__ gbase,
-             const uint32_t *__restrict__ seg, uint32_t *__restrict__ sorted)
+__device__ __forceinline__ void d_sort_small(uint32_t n_groups, const uint32_t *__restrict__ gcnt,
+                                             const uint32_t *__restrict__ gbase, const uint32_t *__restrict__ seg,
+                                             uint32_t *__restrict__ sorted, uint32_t vblock)
 {
-    const uint32_t g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const uint32_t g = (vblock * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (g >= n_groups) return;
     const uint32_t n = gcnt[g];
     if (n == 0 || n > 32) return;
@@ -245,15 +354,13 @@ __device__ __forceinline__ uint32_t block_excl_scan_u32(uint32_t v, uint32_t *ws
 }
 
 // one CTA per medium group (33..big_t entries): shared-memory bitmap over [min, max] of the segment
-__global__ void __launch_bounds__(256)
-k_sort_medium(const uint32_t *__restrict__ lists, const uint32_t *__restrict__ gcnt,
-              const uint32_t *__restrict__ gbase, const uint32_t *__restrict__ seg, uint32_t *__restrict__ sorted)
+__device__ __forceinline__ void d_sort_medium(const uint32_t *__restrict__ lists, const uint32_t *__restrict__ gcnt,
+                                              const uint32_t *__restrict__ gbase, const uint32_t *__restrict__ seg,
+                                              uint32_t *__restrict__ sorted, uint32_t *bm, uint32_t *wsum, uint32_t *red,
+                                              uint32_t vblock, uint32_t vgrid)
 {
-    __shared__ uint32_t bm[BM_WORDS];
-    __shared__ uint32_t wsum[9];
-    __shared__ uint32_t red[2];
     const uint32_t nmed = lists[0];
-    for (uint32_t bi = blockIdx.x; bi < nmed; bi += gridDim.x) {
+    for (uint32_t bi = vblock; bi < nmed; bi += vgrid) {
         const uint32_t g = lists[2 + bi];
         const uint32_t n = gcnt[g], base = gbase[g];
         if (threadIdx.x == 0) {
@@ -309,15 +416,15 @@ k_sort_medium(const uint32_t *__restrict__ lists, const uint32_t *__restrict__ g
 }
 
 // large groups: ordered expansion of the global bitmap; CTA = (large group, chunk of 256 words)
-__global__ void __launch_bounds__(256)
-k_expand_large(const uint32_t *__restrict__ lists, uint32_t n_groups, const uint32_t *__restrict__ gbase,
-               const uint32_t *__restrict__ bitmaps, uint32_t bm_words, uint32_t chunks_per_group,
-               uint32_t *__restrict__ sorted)
+__device__ __forceinline__ void d_expand_large(const uint32_t *__restrict__ lists, uint32_t n_groups,
+                                               const uint32_t *__restrict__ gbase, const uint32_t *__restrict__ bitmaps,
+                                               uint32_t bm_words, uint32_t chunks_per_group,
+                                               uint32_t *__restrict__ sorted, uint32_t *wsum, uint32_t *pre_sp,
+                                               uint32_t vblock, uint32_t vgrid)
 {
-    __shared__ uint32_t wsum[9];
-    __shared__ uint32_t pre_s;
+    uint32_t &pre_s = *pre_sp;
     const uint32_t nlarge = lists[1];
-    for (uint32_t job = blockIdx.x; job < nlarge * chunks_per_group; job += gridDim.x) {
+    for (uint32_t job = vblock; job < nlarge * chunks_per_group; job += vgrid) {
         const uint32_t slot = job / chunks_per_group, chunk = job % chunks_per_group;
         const uint32_t g = lists[2 + n_groups + slot];
         const uint32_t *bm = bitmaps + (uint64_t)slot * bm_words;
@@ -339,6 +446,26 @@ k_expand_large(const uint32_t *__restrict__ lists, uint32_t n_groups, const uint
         }
         __syncthreads();
     }
+}
+
+// one launch for the three segment-ordering paths: blocks [0,nb_small) warp rank-sort, [nb_small, nb_small+nb_med)
+// shared-memory bitmap sort of medium groups, the rest expand the large groups' global bitmaps
+__global__ void __launch_bounds__(256)
+k_sort(uint32_t n_groups, const uint32_t *__restrict__ gcnt, const uint32_t *__restrict__ gbase,
+       const uint32_t *__restrict__ seg, uint32_t *__restrict__ sorted, const uint32_t *__restrict__ lists,
+       const uint32_t *__restrict__ bitmaps, uint32_t bm_words, uint32_t chunks_per_group, uint32_t nb_small,
+       uint32_t nb_med)
+{
+    __shared__ uint32_t bm[BM_WORDS];
+    __shared__ uint32_t wsum[9];
+    __shared__ uint32_t red[2];
+    if (blockIdx.x < nb_small)
+        d_sort_small(n_groups, gcnt, gbase, seg, sorted, blockIdx.x);
+    else if (blockIdx.x < nb_small + nb_med)
+        d_sort_medium(lists, gcnt, gbase, seg, sorted, bm, wsum, red, blockIdx.x - nb_small, nb_med);
+    else
+        d_expand_large(lists, n_groups, gbase, bitmaps, bm_words, chunks_per_group, sorted, wsum, red,
+                       blockIdx.x - nb_small - nb_med, gridDim.x - nb_small - nb_med);
 }
 
 // ---- per watcher: deliveries = its group's sorted segment filtered by pm[e] >= min_rev
@@ -386,12 +513,11 @@ k_expand_count(TabDev tb, const uint32_t *__restrict__ gcnt, const uint32_t *__r
 }
 
 // monotone revisions: one thread per delivery (suffix copy)
-__global__ void __launch_bounds__(256)
-k_expand_write(TabDev tb, const uint32_t *__restrict__ gbase, const uint32_t *__restrict__ sorted,
-               const uint32_t *__restrict__ nonmono, const uint64_t *__restrict__ wstart,
-               const uint32_t *__restrict__ wlo, uint64_t n_deliveries, uint32_t *__restrict__ out)
+__device__ __forceinline__ void d_expand_write(const TabDev &tb, const uint32_t *__restrict__ gbase,
+                                               const uint32_t *__restrict__ sorted, const uint64_t *__restrict__ wstart,
+                                               const uint32_t *__restrict__ wlo, uint64_t n_deliveries,
+                                               uint32_t *__restrict__ out)
 {
-    if (*nonmono != 0) return;
     const uint64_t d = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (d >= n_deliveries) return;
     uint32_t lo = 0, hi = tb.n_ids;  // last watcher with wstart[w] <= d
@@ -405,13 +531,12 @@ k_expand_write(TabDev tb, const uint32_t *__restrict__ gbase, const uint32_t *__
 }
 
 // non-monotone revisions (general case): warp per watcher, ordered filtered copy
-__global__ void __launch_bounds__(256)
-k_expand_write_general(TabDev tb, const uint32_t *__restrict__ gcnt, const uint32_t *__restrict__ gbase,
-                       const uint32_t *__restrict__ sorted, const uint64_t *__restrict__ pm,
-                       const uint32_t *__restrict__ nonmono, const uint64_t *__restrict__ wstart,
-                       uint32_t *__restrict__ out)
+__device__ __forceinline__ void d_expand_write_general(const TabDev &tb, const uint32_t *__restrict__ gcnt,
+                                                       const uint32_t *__restrict__ gbase,
+                                                       const uint32_t *__restrict__ sorted,
+                                                       const uint64_t *__restrict__ pm,
+                                                       const uint64_t *__restrict__ wstart, uint32_t *__restrict__ out)
 {
-    if (*nonmono == 0) return;
     const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (w >= tb.n_ids) return;
     const uint32_t g = tb.wgroup[w];
@@ -429,6 +554,19 @@ k_expand_write_general(TabDev tb, const uint32_t *__restrict__ gcnt, const uint3
         if (keep) out[o + total + __popc(m & ((1u << lane) - 1))] = e;
         total += __popc(m);
     }
+}
+
+// one launch for both output paths: revisions monotone -> one thread per delivery; otherwise warp per watcher
+__global__ void __launch_bounds__(256)
+k_expand_write(TabDev tb, const uint32_t *__restrict__ gcnt, const uint32_t *__restrict__ gbase,
+               const uint32_t *__restrict__ sorted, const uint64_t *__restrict__ pm,
+               const uint32_t *__restrict__ nonmono, const uint64_t *__restrict__ wstart,
+               const uint32_t *__restrict__ wlo, uint64_t n_deliveries, uint32_t *__restrict__ out)
+{
+    if (*nonmono == 0)
+        d_expand_write(tb, gbase, sorted, wstart, wlo, n_deliveries, out);
+    else
+        d_expand_write_general(tb, gcnt, gbase, sorted, pm, wstart, out);
 }
 
 uint64_t fnv1a(const std::string &s)
@@ -580,8 +718,8 @@ void watch_tables_free(kb_ctx *ctx)
     if (!ctx->wt) return;
     WatchTablesDev &T = *ctx->wt;
     DBuf *all[] = {&T.gprefix, &T.goff16, &T.glen, &T.ghash, &T.gstart, &T.gmember, &T.wgroup, &T.wminrev,
-                   &T.lens, &T.table, &T.gcnt, &T.gbase, &T.gfill, &T.gclass, &T.ematch, &T.seg, &T.seg_sorted, &T.lists, &T.bitmaps, &T.wlo, &T.pm,
-                   &T.flag, &T.wcnt, &T.wstart, &T.total};
+                   &T.lens, &T.table, &T.zeros, &T.gbase, &T.gclass, &T.ematch, &T.seg, &T.seg_sorted, &T.bitmaps, &T.wlo, &T.pm,
+                   &T.wcnt, &T.wstart, &T.total};
     for (DBuf *b : all)
         if (b->p) cudaFree(b->p);
     delete ctx->wt;
@@ -659,6 +797,7 @@ extern "C" void kb_events_free(kb_ctx *ctx, kb_events_dev *ev)
 
 static int match_locked(kb_ctx *ctx, const kb_events_dev *d, int out_mode, kb_result **out)
 {
+    kb_tp tseg = kb_now();
     if (ctx->watch_dirty || !ctx->wt) KB_TRY(rebuild_tables(ctx));
     WatchTablesDev &T = *ctx->wt;
     if (d->stride < needed_stride(ctx))
@@ -672,17 +811,14 @@ static int match_locked(kb_ctx *ctx, const kb_events_dev *d, int out_mode, kb_re
     const uint32_t max_large = (uint32_t)(seg_cap / big_t) + 1;
     const uint32_t bm_words = (E + 31) / 32;
     const uint32_t chunks_per_group = (bm_words + 255) / 256;
-    KB_TRY(dbuf_ensure(ctx, T.gcnt, (size_t)(G + 1) * 4));
+    KB_TRY(dbuf_ensure(ctx, T.zeros, (size_t)(4 + 2 * (G + 1) + 2 * G + 8) * 4));
     KB_TRY(dbuf_ensure(ctx, T.gbase, (size_t)(G + 1) * 4));
-    KB_TRY(dbuf_ensure(ctx, T.gfill, (size_t)(G + 1) * 4));
     KB_TRY(dbuf_ensure(ctx, T.gclass, (size_t)(G + 1) * 4));
     KB_TRY(dbuf_ensure(ctx, T.ematch, seg_cap * 4));
     KB_TRY(dbuf_ensure(ctx, T.seg, seg_cap * 4));
     KB_TRY(dbuf_ensure(ctx, T.seg_sorted, seg_cap * 4));
-    KB_TRY(dbuf_ensure(ctx, T.lists, (size_t)(2 * G + 4) * 4));
     KB_TRY(dbuf_ensure(ctx, T.bitmaps, std::max<size_t>((size_t)max_large * bm_words * 4, 16)));
     KB_TRY(dbuf_ensure(ctx, T.pm, std::max<size_t>((size_t)E * 8, 16)));
-    KB_TRY(dbuf_ensure(ctx, T.flag, 16));
     KB_TRY(dbuf_ensure(ctx, T.wcnt, (size_t)(W + 1) * 8));
     KB_TRY(dbuf_ensure(ctx, T.wlo, (size_t)(W + 1) * 4));
     KB_TRY(dbuf_ensure(ctx, T.wstart, (size_t)(W + 2) * 8));
@@ -713,53 +849,54 @@ static int match_locked(kb_ctx *ctx, const kb_events_dev *d, int out_mode, kb_re
     tb.mask = T.table_size - 1;
     tb.max_len = T.max_len;
 
-    uint32_t *gcnt = (uint32_t *)T.gcnt.p, *gbase = (uint32_t *)T.gbase.p, *gfill = (uint32_t *)T.gfill.p;
-    uint32_t *gclass = (uint32_t *)T.gclass.p, *ematch = (uint32_t *)T.ematch.p, *lists = (uint32_t *)T.lists.p;
+    // zeroed region: [flag x4][gcnt G+1][gfill G+1][lists 2G+4]
+    const size_t zero_bytes = (size_t)(4 + 2 * (G + 1) + 2) * 4;
+    uint32_t *zr = (uint32_t *)T.zeros.p;
+    uint32_t *gcnt = zr + 4, *gfill = zr + 4 + (G + 1), *lists = zr + 4 + 2 * (G + 1);
+    uint32_t *gbase = (uint32_t *)T.gbase.p;
+    uint32_t *gclass = (uint32_t *)T.gclass.p, *ematch = (uint32_t *)T.ematch.p;
     uint32_t *seg = (uint32_t *)T.seg.p, *sorted = (uint32_t *)T.seg_sorted.p, *bitmaps = (uint32_t *)T.bitmaps.p;
     uint64_t *pm = (uint64_t *)T.pm.p;
-    uint32_t *flag = (uint32_t *)T.flag.p, *wlo = (uint32_t *)T.wlo.p;
+    uint32_t *flag = zr, *wlo = (uint32_t *)T.wlo.p;
     uint64_t *wcnt = (uint64_t *)T.wcnt.p, *wstart = (uint64_t *)T.wstart.p, *total = (uint64_t *)T.total.p;
 
-    KB_CUDA(ctx, cudaMemsetAsync(gcnt, 0, (size_t)(G + 1) * 4, ctx->stream));
-    KB_CUDA(ctx, cudaMemsetAsync(gfill, 0, (size_t)(G + 1) * 4, ctx->stream));
-    KB_CUDA(ctx, cudaMemsetAsync(lists, 0, 8, ctx->stream));
-    KB_CUDA(ctx, cudaMemsetAsync(flag, 0, 4, ctx->stream));
+    // gcnt | gfill | lists header | flag live in one zeroed region (one memset per call)
+    KB_CUDA(ctx, cudaMemsetAsync(T.zeros.p, 0, zero_bytes, ctx->stream));
     const uint64_t ev_bytes = (uint64_t)E * (d->stride + 4);
     const bool work = E && W && G;
     if (E && W) {
-        KB_LAUNCH(ctx, "k_batch_pm", (uint64_t)E * 16,
-                  (k_batch_pm<<<(d->nb * 32 + 127) / 128, 128, 0, ctx->stream>>>(ev, pm, flag)));
+        const uint32_t pm_blocks = (d->nb * 32 + 255) / 256;
+        KB_LAUNCH(ctx, "k_match_count", ev_bytes + (uint64_t)E * NL * 4 + (uint64_t)E * 16,
+                  (k_match_count<<<pm_blocks + (G ? (E + 255) / 256 : 0), 256, 0, ctx->stream>>>(ev, tb, pm_blocks, pm,
+                                                                                            flag, ematch, gcnt)));
     }
-    if (work) {
-        KB_LAUNCH(ctx, "k_match_count", ev_bytes + (uint64_t)E * NL * 4,
-                  (k_match_count<<<(E + 255) / 256, 256, 0, ctx->stream>>>(ev, tb, ematch, gcnt)));
-    }
-    KB_TRY(scan_exclusive_u32(ctx, gcnt, gbase, G, nullptr));
     if (work) {
         KB_CUDA(ctx, cudaMemsetAsync(bitmaps, 0, (size_t)max_large * bm_words * 4, ctx->stream));
-        KB_LAUNCH(ctx, "k_classify", (uint64_t)G * 8,
-                  (k_classify<<<(G + 255) / 256, 256, 0, ctx->stream>>>(G, gcnt, big_t, max_large, gclass, lists)));
+        KB_LAUNCH(ctx, "k_group_scan_classify", (uint64_t)G * 12,
+                  (k_group_scan_classify<<<1, 1024, 0, ctx->stream>>>(G, gcnt, big_t, max_large, gbase, gclass, lists)));
         KB_LAUNCH(ctx, "k_scatter", (uint64_t)E * NL * 8,
                   (k_scatter<<<(E + 255) / 256, 256, 0, ctx->stream>>>(E, T.n_lens, ematch, gclass, gbase, gfill, seg,
                                                                      bitmaps, bm_words)));
-        KB_LAUNCH(ctx, "k_sort_small", (uint64_t)G * 8,
-                  (k_sort_small<<<(G * 32 + 255) / 256, 256, 0, ctx->stream>>>(G, gcnt, gbase, seg, sorted)));
-        KB_LAUNCH(ctx, "k_sort_medium", 0,
-                  (k_sort_medium<<<148 * 4, 256, 0, ctx->stream>>>(lists, gcnt, gbase, seg, sorted)));
-        KB_LAUNCH(ctx, "k_expand_large", (uint64_t)max_large * bm_words * 4,
-                  (k_expand_large<<<std::min<uint32_t>(148 * 8, max_large * chunks_per_group), 256, 0, ctx->stream>>>(
-                      lists, G, gbase, bitmaps, bm_words, chunks_per_group, sorted)));
+        const uint32_t nb_small = (G * 32 + 255) / 256, nb_med = 148 * 2;
+        const uint32_t nb_large = std::min<uint32_t>(148 * 4, max_large * chunks_per_group);
+        KB_LAUNCH(ctx, "k_sort", (uint64_t)E * NL * 8,
+                  (k_sort<<<nb_small + nb_med + nb_large, 256, 0, ctx->stream>>>(G, gcnt, gbase, seg, sorted, lists, bitmaps,
+                                                                               bm_words, chunks_per_group, nb_small,
+                                                                               nb_med)));
     }
     if (W) {
         KB_LAUNCH(ctx, "k_expand_count", (uint64_t)W * 24,
                   (k_expand_count<<<(W * 32 + 255) / 256, 256, 0, ctx->stream>>>(tb, gcnt, gbase, sorted, pm, flag, wcnt,
                                                                               wlo)));
     }
-    KB_TRY(scan_exclusive_u64(ctx, wcnt, wstart, W, total));
+    KB_LAUNCH(ctx, "k_watcher_scan", (uint64_t)W * 16,
+              (k_watcher_scan<<<1, 1024, 0, ctx->stream>>>(W, wcnt, wstart, total)));
     uint64_t D = 0;
     KB_TRY(hbuf_ensure(ctx, ctx->h_stage2, 64));
     KB_CUDA(ctx, cudaMemcpyAsync(ctx->h_stage2.p, total, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    kb_seg(ctx, "host:match_launch", tseg);
     KB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    kb_seg(ctx, "host:match_sync_count", tseg);
     D = *(uint64_t *)ctx->h_stage2.p;
 
     // output: [start (W+1) x u64][event_idx D x u32]
@@ -768,15 +905,12 @@ static int match_locked(kb_ctx *ctx, const kb_events_dev *d, int out_mode, kb_re
     KB_TRY(pool_get_dev(ctx, out_bytes, &d_out));
     uint64_t *o_start = (uint64_t *)d_out.p;
     uint32_t *o_idx = (uint32_t *)(o_start + W + 1);
-    cudaMemcpyAsync(o_start, wstart, (size_t)W * 8, cudaMemcpyDeviceToDevice, ctx->stream);
-    cudaMemcpyAsync(o_start + W, total, 8, cudaMemcpyDeviceToDevice, ctx->stream);
+    cudaMemcpyAsync(o_start, wstart, (size_t)(W + 1) * 8, cudaMemcpyDeviceToDevice, ctx->stream);
     if (W && D) {
+        const unsigned wgrid = (unsigned)std::max<uint64_t>((D + 255) / 256, ((uint64_t)W * 32 + 255) / 256);
         KB_LAUNCH(ctx, "k_expand_write", D * 8,
-                  (k_expand_write<<<(unsigned)((D + 255) / 256), 256, 0, ctx->stream>>>(tb, gbase, sorted, flag, o_start,
-                                                                                     wlo, D, o_idx)));
-        KB_LAUNCH(ctx, "k_expand_write_general", 0,
-                  (k_expand_write_general<<<(W * 32 + 255) / 256, 256, 0, ctx->stream>>>(tb, gcnt, gbase, sorted, pm,
-                                                                                      flag, o_start, o_idx)));
+                  (k_expand_write<<<wgrid, 256, 0, ctx->stream>>>(tb, gcnt, gbase, sorted, pm, flag, o_start, wlo, D,
+                                                                 o_idx)));
     }
     HBuf h_out;
     int rc = KB_OK;
@@ -789,7 +923,9 @@ static int match_locked(kb_ctx *ctx, const kb_events_dev *d, int out_mode, kb_re
         rc = pool_get_host(ctx, (size_t)(W + 1) * 8 + 16, &h_out);
         if (rc == KB_OK) cudaMemcpyAsync(h_out.p, d_out.p, (size_t)(W + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream);
     }
+    kb_seg(ctx, "host:match_write_launch", tseg);
     cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    kb_seg(ctx, "host:match_sync_final", tseg);
     if (rc == KB_OK && e != cudaSuccess) rc = kb_cuda_fail(ctx, e, "watch match");
     if (rc != KB_OK) {
         pool_put_dev(ctx, d_out);
