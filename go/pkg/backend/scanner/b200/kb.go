@@ -1,0 +1,251 @@
+//go:build b200
+
+// Package b200 binds libkbb200.so (include/kb_b200.h) under the reference's scanner.Scanner seam
+// (pkg/backend/scanner/interface.go:24-37) and exposes the watch matcher used by the backend's hub.
+//
+// NOTE: written without a Go toolchain (none exists in the build image); it is the binding a maintainer
+// adds to the kubebrain tree next to pkg/backend/scanner.  Every behaviour it relies on is exercised
+// through the same C ABI by tests/test_gpu_parity.py.
+package b200
+
+/*
+#cgo CFLAGS: -I${SRCDIR}/../../../../../include
+#cgo LDFLAGS: -L${SRCDIR}/../../../../../kubebrain_b200 -lkbb200 -Wl,-rpath,${SRCDIR}/../../../../../kubebrain_b200
+#include <stdlib.h>
+#include "kb_b200.h"
+*/
+import "C"
+
+import (
+	"context"
+	"errors"
+	"fmt"
+	"runtime"
+	"sync"
+	"unsafe"
+
+	proto "github.com/kubewharf/kubebrain-client/api/v2rpc"
+
+	"github.com/kubewharf/kubebrain/pkg/backend/scanner"
+)
+
+const rangeStreamBatch = 300 // pkg/backend/scanner/scanner.go:43
+
+// Engine owns one kb_ctx (one GPU, one HBM-resident snapshot).
+type Engine struct {
+	mu  sync.Mutex
+	ctx *C.kb_ctx
+}
+
+func Open(device int) (*Engine, error) {
+	e := &Engine{}
+	if rc := C.kb_open(C.int(device), nil, &e.ctx); rc != 0 {
+		return nil, fmt.Errorf("kb_open: %d (no CUDA device; there is no CPU fallback)", int(rc))
+	}
+	runtime.SetFinalizer(e, func(e *Engine) { C.kb_close(e.ctx) })
+	return e, nil
+}
+
+func (e *Engine) err(rc C.int) error {
+	if rc == 0 {
+		return nil
+	}
+	return fmt.Errorf("kb_b200 %d: %s", int(rc), C.GoString(C.kb_last_error(e.ctx)))
+}
+
+// LoadSorted ingests a snapshot pulled from storage.Iter (ascending unique internal keys).
+func (e *Engine) LoadSorted(keys []byte, keyOff []uint64, vals []byte, valOff []uint64) error {
+	n := len(keyOff) - 1
+	return e.err(C.kb_load_sorted(e.ctx, (*C.uint8_t)(unsafe.Pointer(&keys[0])), (*C.uint64_t)(unsafe.Pointer(&keyOff[0])),
+		(*C.uint8_t)(unsafe.Pointer(&vals[0])), (*C.uint64_t)(unsafe.Pointer(&valOff[0])), C.uint64_t(n)))
+}
+
+type b200Scanner struct {
+	e *Engine
+}
+
+// NewScanner replaces scanner.NewScanner at pkg/backend/backend.go:155.
+func NewScanner(e *Engine) scanner.Scanner { return &b200Scanner{e: e} }
+
+func (s *b200Scanner) rangeOnce(start, end []byte, revision uint64, limit int64, mode C.int) (*C.kb_result, C.kb_range_view, error) {
+	var req C.kb_range_req
+	pin := runtime.Pinner{}
+	defer pin.Unpin()
+	if len(start) > 0 {
+		pin.Pin(&start[0])
+		req.start = (*C.uint8_t)(unsafe.Pointer(&start[0]))
+	}
+	if len(end) > 0 {
+		pin.Pin(&end[0])
+		req.end = (*C.uint8_t)(unsafe.Pointer(&end[0]))
+	}
+	req.start_len, req.end_len = C.uint64_t(len(start)), C.uint64_t(len(end))
+	req.read_rev, req.limit = C.uint64_t(revision), C.int64_t(limit)
+	var res *C.kb_result
+	var view C.kb_range_view
+	s.e.mu.Lock()
+	defer s.e.mu.Unlock()
+	if rc := C.kb_range_batch(s.e.ctx, &req, 1, mode, &res); rc != 0 {
+		return nil, view, s.e.err(rc) // KB_ECOMPACTED carries the reference's message (scanner.go:620-623)
+	}
+	C.kb_range_view_get(res, &view)
+	return res, view, nil
+}
+
+// copyKvs moves the pinned result arena into Go-owned memory: the reference keeps Key/Val slices alive after
+// Iter.Close (scanner.go:493-495), so the arena cannot be handed out directly unless it is ref-counted.
+func copyKvs(view C.kb_range_view) []*proto.KeyValue {
+	n := int(view.n_kvs)
+	if n == 0 {
+		return nil
+	}
+	arena := C.GoBytes(unsafe.Pointer(view.bytes), C.int(view.n_bytes)) // one copy for the whole answer
+	keyOff := unsafe.Slice((*uint64)(unsafe.Pointer(view.key_off)), n)
+	keyLen := unsafe.Slice((*uint32)(unsafe.Pointer(view.key_len)), n)
+	valOff := unsafe.Slice((*uint64)(unsafe.Pointer(view.val_off)), n)
+	valLen := unsafe.Slice((*uint32)(unsafe.Pointer(view.val_len)), n)
+	rev := unsafe.Slice((*uint64)(unsafe.Pointer(view.rev)), n)
+	kvs := make([]*proto.KeyValue, n)
+	backing := make([]proto.KeyValue, n)
+	for i := 0; i < n; i++ {
+		backing[i] = proto.KeyValue{
+			Key:      arena[keyOff[i] : keyOff[i]+uint64(keyLen[i])],
+			Value:    arena[valOff[i] : valOff[i]+uint64(valLen[i])],
+			Revision: rev[i],
+		}
+		kvs[i] = &backing[i]
+	}
+	return kvs
+}
+
+func (s *b200Scanner) Range(ctx context.Context, start, end []byte, revision uint64, limit int64) ([]*proto.KeyValue, error) {
+	res, view, err := s.rangeOnce(start, end, revision, limit, C.KB_OUT_HOST)
+	if err != nil {
+		return nil, err
+	}
+	defer C.kb_result_free(s.e.ctx, res)
+	return copyKvs(view), nil
+}
+
+func (s *b200Scanner) Count(ctx context.Context, start, end []byte, revision uint64) (int, error) {
+	res, view, err := s.rangeOnce(start, end, revision, 0, C.KB_OUT_COUNT)
+	if err != nil {
+		return 0, err
+	}
+	defer C.kb_result_free(s.e.ctx, res)
+	return int(*view.req_count), nil
+}
+
+func (s *b200Scanner) RangeStream(ctx context.Context, start, end []byte, revision uint64) chan *proto.StreamRangeResponse {
+	stream := make(chan *proto.StreamRangeResponse, 1000)
+	go func() {
+		defer close(stream)
+		kvs, err := s.Range(ctx, start, end, revision, 0)
+		for i := 0; err == nil && i < len(kvs); i += rangeStreamBatch { // receiver.go:119-138
+			j := i + rangeStreamBatch
+			if j > len(kvs) {
+				j = len(kvs)
+			}
+			stream <- &proto.StreamRangeResponse{RangeResponse: &proto.RangeResponse{
+				Header: &proto.ResponseHeader{Revision: revision}, Kvs: kvs[i:j], More: true}}
+		}
+		end := &proto.StreamRangeResponse{RangeResponse: &proto.RangeResponse{
+			Header: &proto.ResponseHeader{Revision: revision}}} // getListStreamEnd scanner.go:179-192
+		if err != nil {
+			end.Err = err.Error()
+		}
+		stream <- end
+	}()
+	return stream
+}
+
+// Victim is one delete call of the reference's compaction loop, in order.
+type Victim struct {
+	Record uint32
+	Class  uint8 // KB_V_*: 1 superseded, 2 tombstone (store.Del); 3 revision record, 4 ttl revision record (DelCurrent); 5 ttl object
+}
+
+// Sweep classifies; Compact (below) keeps the reference's fire-and-forget signature and hands the victims to Apply.
+func (s *b200Scanner) Sweep(start, end []byte, revision, timeoutRevision uint64, supportTTL bool) ([]Victim, int, error) {
+	var res *C.kb_result
+	ttl := C.int(0)
+	if supportTTL {
+		ttl = 1
+	}
+	s.e.mu.Lock()
+	rc := C.kb_compact_sweep(s.e.ctx, (*C.uint8_t)(unsafe.Pointer(&start[0])), C.uint64_t(len(start)),
+		(*C.uint8_t)(unsafe.Pointer(&end[0])), C.uint64_t(len(end)), C.uint64_t(revision), C.uint64_t(timeoutRevision),
+		ttl, C.KB_OUT_HOST, &res)
+	s.e.mu.Unlock()
+	if rc != 0 {
+		return nil, 0, s.e.err(rc)
+	}
+	defer C.kb_result_free(s.e.ctx, res)
+	var v C.kb_compact_view
+	C.kb_compact_view_get(res, &v)
+	n := int(v.n_victims)
+	out := make([]Victim, n)
+	if n > 0 {
+		idx := unsafe.Slice((*uint32)(unsafe.Pointer(v.victim_idx)), n)
+		cls := unsafe.Slice((*uint8)(unsafe.Pointer(v.victim_class)), n)
+		for i := range out {
+			out[i] = Victim{idx[i], cls[i]}
+		}
+	}
+	return out, int(v.count), nil
+}
+
+// Apply is supplied by the storage adaptor: it deletes the victims in bulk (one engine batch instead of the
+// reference's one transaction per victim, scanner.go:538-564).
+var Apply func(ctx context.Context, victims []Victim) error
+
+func (s *b200Scanner) Compact(ctx context.Context, start, end []byte, revision uint64) {
+	victims, _, err := s.Sweep(start, end, revision, 0, true)
+	if err == nil && Apply != nil {
+		_ = Apply(ctx, victims)
+	}
+}
+
+var errNoWatchers = errors.New("no watchers")
+
+// Match replaces WatcherHub.Stream + processEvents for one collector batch run: it returns, per watcher id, the
+// indices of the events to deliver, in order (pkg/backend/watcherhub.go:78-92, watch.go:119-159).
+func (e *Engine) Match(keys []byte, keyOff, rev, batchOff []uint64) (start []uint64, eventIdx []uint32, err error) {
+	ev := C.kb_events{
+		keys: (*C.uint8_t)(unsafe.Pointer(&keys[0])), key_off: (*C.uint64_t)(unsafe.Pointer(&keyOff[0])),
+		rev: (*C.uint64_t)(unsafe.Pointer(&rev[0])), n: C.uint64_t(len(rev)),
+		batch_off: (*C.uint64_t)(unsafe.Pointer(&batchOff[0])), n_batches: C.uint64_t(len(batchOff) - 1),
+	}
+	var res *C.kb_result
+	e.mu.Lock()
+	rc := C.kb_watch_match(e.ctx, &ev, C.KB_OUT_HOST, &res)
+	e.mu.Unlock()
+	if rc != 0 {
+		return nil, nil, e.err(rc)
+	}
+	defer C.kb_result_free(e.ctx, res)
+	var v C.kb_match_view
+	C.kb_match_view_get(res, &v)
+	start = append([]uint64(nil), unsafe.Slice((*uint64)(unsafe.Pointer(v.start)), int(v.n_watchers)+1)...)
+	if v.n_deliveries > 0 {
+		eventIdx = append([]uint32(nil), unsafe.Slice((*uint32)(unsafe.Pointer(v.event_idx)), int(v.n_deliveries))...)
+	}
+	return start, eventIdx, nil
+}
+
+func (e *Engine) WatchAdd(prefix []byte, minRev uint64) (uint32, error) {
+	var id C.uint32_t
+	var p *C.uint8_t
+	if len(prefix) > 0 {
+		p = (*C.uint8_t)(unsafe.Pointer(&prefix[0]))
+	}
+	e.mu.Lock()
+	defer e.mu.Unlock()
+	return uint32(id), e.err(C.kb_watch_add(e.ctx, p, C.uint64_t(len(prefix)), C.uint64_t(minRev), &id))
+}
+
+func (e *Engine) WatchDel(id uint32) error {
+	e.mu.Lock()
+	defer e.mu.Unlock()
+	return e.err(C.kb_watch_del(e.ctx, C.uint32_t(id)))
+}
