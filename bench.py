@@ -380,12 +380,51 @@ def run_b200(args, rank: int, local_rank: int, world: int):
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(wl)
+        if world == 1 and not args.no_extras:
+            line["extra"] = {"compaction": compaction_extra(local_rank)}
         print(json.dumps(line), flush=True)
     eng.events_free(evh)
     eng.close()
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def compaction_extra(device: int):
+    """BASELINE configs[3] at 1/10 size (not part of the timed step): keep-latest sweep over 1M objects x
+    (1 revision record + 9 versions), Lu=64 -> 10M records, ~8M victims; device-resident victim list"""
+    import torch
+
+    from kubebrain_b200._lib import KB_OUT_DEVICE, Engine
+
+    store, meta = synth.gen_store(1_000_000, 9, 64, 64, 10000, config_id=4, tomb_frac=0.02)
+    eng = Engine(device)
+    eng.load_sorted(store)
+    lo, hi = CODER.encode_object_key(b"/registry/", 0), CODER.encode_object_key(b"/registry0", 0)
+    for _ in range(3):
+        eng.compact_sweep(lo, hi, meta.last_rev, out_mode=KB_OUT_DEVICE).close()
+    stream = torch.cuda.ExternalStream(eng.stream())
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    eng.prof_reset()
+    eng.prof_enable(1)
+    reps = 5
+    torch.cuda.synchronize()
+    a.record(stream)
+    for _ in range(reps):
+        r = eng.compact_sweep(lo, hi, meta.last_rev, out_mode=KB_OUT_DEVICE)
+        nv = r.n_victims
+        r.close()
+    b.record(stream)
+    torch.cuda.synchronize()
+    eng.prof_enable(0)
+    ms = a.elapsed_time(b) / reps
+    kern = {p["name"]: {"avg_us": 1e3 * p["total_ms"] / p["launches"],
+                        "achieved_gbs": (p["alg_bytes"] / p["launches"] / 1e9) / (p["total_ms"] / p["launches"] / 1e3)
+                        if p["total_ms"] > 0 else None}
+            for p in eng.prof_read() if p["launches"] and not p["name"].startswith("host:")}
+    eng.close()
+    return {"workload": "config 4 shape at 1/10: 10M records (Lk=77), compact at max revision", "records": int(store.n),
+            "victims": int(nv), "ms_per_sweep": ms, "records_per_s": store.n / (ms / 1e3), "kernels": kern}
 
 
 def cpu_baseline(wl):
@@ -413,6 +452,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -292,20 +292,27 @@ k_decode_lcp(StoreDev st, const ReqDev *__restrict__ reqs, const TileDev *__rest
     sid += stride;
     issue_stage(st, mode, dB, buf0, lane);
     cp_async_commit();
-    uint32_t it = 0;
-    while (dB.valid) {
-        const SubDesc dC = dB;  // key bytes + value probe in flight since the previous iteration
-        dB = dA;                // directory loaded one iteration ago
-        dA = load_desc(st, tA, lane);
-        tA = fetch_tile(tiles, sid, n_sub);
-        sid += stride;
-        issue_stage(st, mode, dB, buf0 + ((it + 1) & 1) * KB_WARP_STAGE_CHUNKS, lane);
-        cp_async_commit();
-        cp_async_wait<1>();  // everything but the newest group has landed: dC's bytes are in shared memory
-        __syncwarp();
-        process_sub(st, mode, dC, buf0 + (it & 1) * KB_WARP_STAGE_CHUNKS, lane, meta, sub_agg);
-        __syncwarp();
-        it++;
+    // The body is unrolled six times (lcm of the 3 descriptor roles and the 2 stage buffers) so that the role
+    // rotation dC <- dB <- dA is pure register renaming inside the body; moves remain only on the back edge.
+    bool more = dB.valid != 0;
+    while (more) {
+#pragma unroll
+        for (int u = 0; u < 6; u++) {
+            if (more) {
+                const SubDesc dC = dB;  // key bytes + value probe in flight since the previous step
+                dB = dA;                // directory loaded one step ago
+                dA = load_desc(st, tA, lane);
+                tA = fetch_tile(tiles, sid, n_sub);
+                sid += stride;
+                issue_stage(st, mode, dB, buf0 + ((u + 1) & 1) * KB_WARP_STAGE_CHUNKS, lane);
+                cp_async_commit();
+                cp_async_wait<1>();  // everything but the newest group has landed: dC's bytes are in shared memory
+                __syncwarp();
+                process_sub(st, mode, dC, buf0 + (u & 1) * KB_WARP_STAGE_CHUNKS, lane, meta, sub_agg);
+                __syncwarp();
+                more = dB.valid != 0;
+            }
+        }
     }
     cp_async_wait<0>();
 }

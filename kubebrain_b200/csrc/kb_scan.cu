@@ -34,7 +34,19 @@ __device__ __forceinline__ bool key_less(const StoreDev &st, uint32_t rec, const
     const uint4 *a = st.kslab + st.koff16[rec];
     uint32_t la = st.klen[rec];
     uint32_t m = la < blen ? la : blen;
-    for (uint32_t c = 0; c * 16 < m; c++) {
+    // Kubernetes keys share ~30 leading bytes: fetch the first three chunks together instead of one per round trip
+    // (both slabs are padded, so the loads are in bounds; positions at or beyond m are ignored)
+    {
+        uint4 x0 = a[0], x1 = a[1], x2 = a[2];
+        uint4 y0 = b[0], y1 = b[1], y2 = b[2];
+        int p = first_diff16(x0, y0);
+        if (p < 16) return p < (int)m ? byte_of(x0, p) < byte_of(y0, p) : la < blen;
+        p = first_diff16(x1, y1);
+        if (p < 16) return 16 + p < (int)m ? byte_of(x1, p) < byte_of(y1, p) : la < blen;
+        p = first_diff16(x2, y2);
+        if (p < 16) return 32 + p < (int)m ? byte_of(x2, p) < byte_of(y2, p) : la < blen;
+    }
+    for (uint32_t c = 3; c * 16 < m; c++) {
         uint4 x = a[c], y = b[c];
         int p = first_diff16(x, y);
         if (p < 16 && c * 16 + p < m) return byte_of(x, p) < byte_of(y, p);
@@ -713,7 +725,7 @@ int resolve_requests(kb_ctx *ctx, const kb_range_req *reqs, uint64_t nreq, bool 
     for (uint64_t q = 0; q < nreq; q++) {
         if ((!reqs[q].start && reqs[q].start_len) || (!reqs[q].end && reqs[q].end_len)) return KB_EINVAL;
         if (reqs[q].start_len > 65535 || reqs[q].end_len > 65535) return kb_fail(ctx, KB_ELIMIT, "bound key too long");
-        chunks += (reqs[q].start_len + 15) / 16 + (reqs[q].end_len + 15) / 16 + 2;
+        chunks += (reqs[q].start_len + 15) / 16 + (reqs[q].end_len + 15) / 16 + 6;
     }
     const uint64_t nb = 2 * nreq;
     size_t stage_bytes = chunks * 16 + nb * 8 + 64;
@@ -731,22 +743,18 @@ int resolve_requests(kb_ctx *ctx, const kb_range_req *reqs, uint64_t nreq, bool 
             hboff[2 * q + j] = (uint32_t)c;
             hblen[2 * q + j] = (uint32_t)lens[j];
             if (lens[j]) memcpy(hs + c * 16, keys[j], lens[j]);
-            c += (lens[j] + 15) / 16 + 1;
+            c += (lens[j] + 15) / 16 + 3;
         }
     }
-    KB_TRY(dbuf_ensure(ctx, ctx->d_bounds, chunks * 16 + 16));
-    KB_TRY(dbuf_ensure(ctx, ctx->d_boff, nb * 4));
-    KB_TRY(dbuf_ensure(ctx, ctx->d_blen, nb * 4));
+    // one upload: [bound keys | offsets | lengths] are contiguous in the pinned staging buffer
+    KB_TRY(dbuf_ensure(ctx, ctx->d_bounds, chunks * 16 + nb * 8 + 64));
     KB_TRY(dbuf_ensure(ctx, ctx->d_bres, nb * 4));
-    KB_CUDA(ctx, cudaMemcpyAsync(ctx->d_bounds.p, hs, chunks * 16, cudaMemcpyHostToDevice, ctx->stream));
-    KB_CUDA(ctx, cudaMemcpyAsync(ctx->d_boff.p, hboff, nb * 4, cudaMemcpyHostToDevice, ctx->stream));
-    KB_CUDA(ctx, cudaMemcpyAsync(ctx->d_blen.p, hblen, nb * 4, cudaMemcpyHostToDevice, ctx->stream));
+    KB_CUDA(ctx, cudaMemcpyAsync(ctx->d_bounds.p, hs, chunks * 16 + nb * 8, cudaMemcpyHostToDevice, ctx->stream));
+    const uint32_t *d_boff = (const uint32_t *)((const uint8_t *)ctx->d_bounds.p + chunks * 16);
     const unsigned sgrid = (unsigned)((nb * 32 + 127) / 128);
     KB_LAUNCH(ctx, "k_search", nb * 64,
-              (k_search<<<sgrid, 128, 0, ctx->stream>>>(ctx->st, (const uint4 *)ctx->d_bounds.p,
-                                                        (const uint32_t *)ctx->d_boff.p,
-                                                        (const uint32_t *)ctx->d_blen.p, (uint32_t)nb,
-                                                        (uint32_t *)ctx->d_bres.p)));
+              (k_search<<<sgrid, 128, 0, ctx->stream>>>(ctx->st, (const uint4 *)ctx->d_bounds.p, d_boff, d_boff + nb,
+                                                        (uint32_t)nb, (uint32_t *)ctx->d_bres.p)));
     KB_CUDA(ctx, cudaMemcpyAsync(hres, ctx->d_bres.p, nb * 4, cudaMemcpyDeviceToHost, ctx->stream));
     KB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 
@@ -791,8 +799,11 @@ int resolve_requests(kb_ctx *ctx, const kb_range_req *reqs, uint64_t nreq, bool 
 int upload_layout(kb_ctx *ctx, const Resolved &R)
 {
     const size_t nreq = R.reqs.size(), nt = R.tiles.size();
-    KB_TRY(dbuf_ensure(ctx, ctx->d_reqs, std::max<size_t>(nreq, 1) * sizeof(ReqDev)));
-    KB_TRY(dbuf_ensure(ctx, ctx->d_tiles, std::max<size_t>(nt, 1) * sizeof(TileDev)));
+    // requests and tiles travel in one copy; the tile table starts on a 32-byte boundary behind the requests
+    const size_t req_bytes = (nreq * sizeof(ReqDev) + 31) & ~(size_t)31;
+    KB_TRY(dbuf_ensure(ctx, ctx->d_reqs, req_bytes + std::max<size_t>(nt, 1) * sizeof(TileDev) + 64));
+    ctx->d_tiles.p = (uint8_t *)ctx->d_reqs.p + req_bytes;  // alias into d_reqs (never freed on its own)
+    ctx->d_tiles.cap = 0;
     KB_TRY(dbuf_ensure(ctx, ctx->d_meta, std::max<uint64_t>(R.total_flat, 4) * 4));
     KB_TRY(dbuf_ensure(ctx, ctx->d_tgt, std::max<uint64_t>(R.total_flat, 4) * 4 + nreq * 4 + 16));
     KB_TRY(dbuf_ensure(ctx, ctx->d_agg, std::max<size_t>(nt, 1) * 32 * 8));  // one aggregate per 32-record sub-tile
@@ -800,15 +811,12 @@ int upload_layout(kb_ctx *ctx, const Resolved &R)
     KB_TRY(dbuf_ensure(ctx, ctx->d_tscan, (nt + 1) * 16));
     KB_TRY(dbuf_ensure(ctx, ctx->d_reqout, std::max<size_t>(nreq, 1) * sizeof(ReqOut)));
     // pinned staging so the async copies really are asynchronous
-    size_t bytes = nreq * sizeof(ReqDev) + nt * sizeof(TileDev);
+    const size_t bytes = req_bytes + nt * sizeof(TileDev);
     KB_TRY(hbuf_ensure(ctx, ctx->h_stage2, bytes + 64));
     uint8_t *h = (uint8_t *)ctx->h_stage2.p;
     memcpy(h, R.reqs.data(), nreq * sizeof(ReqDev));
-    memcpy(h + nreq * sizeof(ReqDev), R.tiles.data(), nt * sizeof(TileDev));
-    KB_CUDA(ctx, cudaMemcpyAsync(ctx->d_reqs.p, h, nreq * sizeof(ReqDev), cudaMemcpyHostToDevice, ctx->stream));
-    if (nt)
-        KB_CUDA(ctx, cudaMemcpyAsync(ctx->d_tiles.p, h + nreq * sizeof(ReqDev), nt * sizeof(TileDev),
-                                     cudaMemcpyHostToDevice, ctx->stream));
+    memcpy(h + req_bytes, R.tiles.data(), nt * sizeof(TileDev));
+    if (bytes) KB_CUDA(ctx, cudaMemcpyAsync(ctx->d_reqs.p, h, bytes, cudaMemcpyHostToDevice, ctx->stream));
     return KB_OK;
 }
 

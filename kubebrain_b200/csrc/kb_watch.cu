@@ -37,6 +37,7 @@ struct kb_events_dev {
 
 struct WatchTablesDev {
     uint32_t n_ids = 0, n_groups = 0, n_lens = 0, table_size = 0, max_len = 0;
+    uint64_t d_hint = 0;  // deliveries of the previous match (sizes the next output buffer)
     DBuf gprefix, goff16, glen, ghash, gstart, gmember, wgroup, wminrev, lens, table;
     // per-call scratch
     DBuf zeros, gbase, gclass, ematch, seg, seg_sorted, bitmaps, pm, wcnt, wlo, wstart, total;
@@ -474,6 +475,27 @@ k_expand_count(TabDev tb, const uint32_t *__restrict__ gcnt, const uint32_t *__r
                const uint32_t *__restrict__ sorted, const uint64_t *__restrict__ pm,
                const uint32_t *__restrict__ nonmono, uint64_t *__restrict__ wcnt, uint32_t *__restrict__ wlo)
 {
+    if (*nonmono == 0) {
+        // revisions non-decreasing over the whole slab: the survivors are a suffix of the segment -> one thread
+        // per watcher, binary search for the first event at or above min_rev
+        const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+        if (w >= tb.n_ids) return;
+        const uint32_t g = tb.wgroup[w];
+        uint32_t n = 0, lo = 0;
+        if (g != KB_NONE) {
+            n = gcnt[g];
+            const uint32_t *M = sorted + gbase[g];
+            const uint64_t mr = tb.wminrev[w];
+            uint32_t hi = n;
+            while (lo < hi) {
+                const uint32_t mid = (lo + hi) >> 1;
+                if (pm[M[mid]] >= mr) hi = mid; else lo = mid + 1;
+            }
+        }
+        wcnt[w] = n - lo;
+        wlo[w] = lo;
+        return;
+    }
     const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (w >= tb.n_ids) return;
     const uint32_t g = tb.wgroup[w];
@@ -487,19 +509,6 @@ k_expand_count(TabDev tb, const uint32_t *__restrict__ gcnt, const uint32_t *__r
     const uint32_t n = gcnt[g];
     const uint32_t *M = sorted + gbase[g];
     const uint64_t mr = tb.wminrev[w];
-    if (*nonmono == 0) {
-        // revisions non-decreasing over the whole slab: the survivors are a suffix of the segment
-        uint32_t lo = 0, hi = n;
-        while (lo < hi) {
-            const uint32_t mid = (lo + hi) >> 1;
-            if (pm[M[mid]] >= mr) hi = mid; else lo = mid + 1;
-        }
-        if (lane == 0) {
-            wcnt[w] = n - lo;
-            wlo[w] = lo;
-        }
-        return;
-    }
     uint64_t total = 0;
     for (uint32_t c = 0; c < n; c += 32) {
         const uint32_t j = c + lane;
@@ -518,8 +527,8 @@ __device__ __forceinline__ void d_expand_write(const TabDev &tb, const uint32_t 
                                                const uint32_t *__restrict__ wlo, uint64_t n_deliveries,
                                                uint32_t *__restrict__ out)
 {
-    const uint64_t d = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (d >= n_deliveries) return;
+    for (uint64_t d = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; d < n_deliveries;
+         d += (uint64_t)gridDim.x * blockDim.x) {
     uint32_t lo = 0, hi = tb.n_ids;  // last watcher with wstart[w] <= d
     while (hi - lo > 1) {
         const uint32_t mid = (lo + hi) >> 1;
@@ -528,6 +537,7 @@ __device__ __forceinline__ void d_expand_write(const TabDev &tb, const uint32_t 
     const uint32_t w = lo;
     const uint32_t g = tb.wgroup[w];
     out[d] = sorted[gbase[g] + wlo[w] + (uint32_t)(d - wstart[w])];
+    }
 }
 
 // non-monotone revisions (general case): warp per watcher, ordered filtered copy
@@ -561,8 +571,10 @@ __global__ void __launch_bounds__(256)
 k_expand_write(TabDev tb, const uint32_t *__restrict__ gcnt, const uint32_t *__restrict__ gbase,
                const uint32_t *__restrict__ sorted, const uint64_t *__restrict__ pm,
                const uint32_t *__restrict__ nonmono, const uint64_t *__restrict__ wstart,
-               const uint32_t *__restrict__ wlo, uint64_t n_deliveries, uint32_t *__restrict__ out)
+               const uint32_t *__restrict__ wlo, uint64_t capacity, uint32_t *__restrict__ out)
 {
+    const uint64_t n_deliveries = wstart[tb.n_ids];
+    if (n_deliveries > capacity) return;  // the host sees the total, grows the buffer and launches again
     if (*nonmono == 0)
         d_expand_write(tb, gbase, sorted, wstart, wlo, n_deliveries, out);
     else
@@ -891,42 +903,55 @@ static int match_locked(kb_ctx *ctx, const kb_events_dev *d, int out_mode, kb_re
     }
     KB_LAUNCH(ctx, "k_watcher_scan", (uint64_t)W * 16,
               (k_watcher_scan<<<1, 1024, 0, ctx->stream>>>(W, wcnt, wstart, total)));
-    uint64_t D = 0;
+    // Output [start (W+1) x u64][event_idx D x u32].  D is only known on the device; the buffer is sized from the
+    // previous call's D (+25 %) and the write kernel refuses to run when it would not fit, so the steady state needs
+    // no round trip before the write.
     KB_TRY(hbuf_ensure(ctx, ctx->h_stage2, 64));
-    KB_CUDA(ctx, cudaMemcpyAsync(ctx->h_stage2.p, total, 8, cudaMemcpyDeviceToHost, ctx->stream));
-    kb_seg(ctx, "host:match_launch", tseg);
-    KB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    kb_seg(ctx, "host:match_sync_count", tseg);
-    D = *(uint64_t *)ctx->h_stage2.p;
-
-    // output: [start (W+1) x u64][event_idx D x u32]
-    const size_t out_bytes = (size_t)(W + 1) * 8 + D * 4 + 16;
+    uint64_t cap = std::max<uint64_t>(T.d_hint + T.d_hint / 4 + 4096, 1 << 16);
+    uint64_t D = 0;
     DBuf d_out;
-    KB_TRY(pool_get_dev(ctx, out_bytes, &d_out));
-    uint64_t *o_start = (uint64_t *)d_out.p;
-    uint32_t *o_idx = (uint32_t *)(o_start + W + 1);
-    cudaMemcpyAsync(o_start, wstart, (size_t)(W + 1) * 8, cudaMemcpyDeviceToDevice, ctx->stream);
-    if (W && D) {
-        const unsigned wgrid = (unsigned)std::max<uint64_t>((D + 255) / 256, ((uint64_t)W * 32 + 255) / 256);
-        KB_LAUNCH(ctx, "k_expand_write", D * 8,
-                  (k_expand_write<<<wgrid, 256, 0, ctx->stream>>>(tb, gcnt, gbase, sorted, pm, flag, o_start, wlo, D,
-                                                                 o_idx)));
-    }
     HBuf h_out;
     int rc = KB_OK;
+    for (int attempt = 0; attempt < 2; attempt++) {
+        const size_t out_bytes = (size_t)(W + 1) * 8 + cap * 4 + 16;
+        KB_TRY(pool_get_dev(ctx, out_bytes, &d_out));
+        uint64_t *o_start = (uint64_t *)d_out.p;
+        uint32_t *o_idx = (uint32_t *)(o_start + W + 1);
+        cudaMemcpyAsync(o_start, wstart, (size_t)(W + 1) * 8, cudaMemcpyDeviceToDevice, ctx->stream);
+        if (W) {
+            const unsigned wgrid = (unsigned)std::max<uint64_t>(std::min<uint64_t>((cap + 255) / 256, 148 * 16),
+                                                                ((uint64_t)W * 32 + 255) / 256);
+            KB_LAUNCH(ctx, "k_expand_write", cap * 8,
+                      (k_expand_write<<<wgrid, 256, 0, ctx->stream>>>(tb, gcnt, gbase, sorted, pm, flag, wstart, wlo, cap,
+                                                                     o_idx)));
+        }
+        KB_CUDA(ctx, cudaMemcpyAsync(ctx->h_stage2.p, total, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        if (out_mode != KB_OUT_HOST) {  // device-resident result: only the offsets travel, in the same round trip
+            if (!h_out.p) KB_TRY(pool_get_host(ctx, (size_t)(W + 1) * 8 + 16, &h_out));
+            cudaMemcpyAsync(h_out.p, wstart, (size_t)(W + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream);
+        }
+        kb_seg(ctx, "host:match_launch", tseg);
+        cudaError_t e0 = cudaStreamSynchronize(ctx->stream);
+        kb_seg(ctx, "host:match_sync", tseg);
+        if (e0 != cudaSuccess) {
+            pool_put_dev(ctx, d_out);
+            return kb_cuda_fail(ctx, e0, "watch match");
+        }
+        D = *(uint64_t *)ctx->h_stage2.p;
+        T.d_hint = D;
+        if (D <= cap) break;
+        pool_put_dev(ctx, d_out);  // first call or a burst larger than the hint: grow and write again
+        d_out = DBuf();
+        cap = D;
+    }
     if (out_mode == KB_OUT_HOST) {
-        rc = pool_get_host(ctx, out_bytes, &h_out);
+        rc = pool_get_host(ctx, (size_t)(W + 1) * 8 + D * 4 + 16, &h_out);
         if (rc == KB_OK)
             cudaMemcpyAsync(h_out.p, d_out.p, (size_t)(W + 1) * 8 + D * 4, cudaMemcpyDeviceToHost, ctx->stream);
-    } else {
-        // the offsets are always readable on the host
-        rc = pool_get_host(ctx, (size_t)(W + 1) * 8 + 16, &h_out);
-        if (rc == KB_OK) cudaMemcpyAsync(h_out.p, d_out.p, (size_t)(W + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream);
+        cudaError_t e = cudaStreamSynchronize(ctx->stream);
+        kb_seg(ctx, "host:match_d2h", tseg);
+        if (rc == KB_OK && e != cudaSuccess) rc = kb_cuda_fail(ctx, e, "watch match");
     }
-    kb_seg(ctx, "host:match_write_launch", tseg);
-    cudaError_t e = cudaStreamSynchronize(ctx->stream);
-    kb_seg(ctx, "host:match_sync_final", tseg);
-    if (rc == KB_OK && e != cudaSuccess) rc = kb_cuda_fail(ctx, e, "watch match");
     if (rc != KB_OK) {
         pool_put_dev(ctx, d_out);
         pool_put_host(ctx, h_out);

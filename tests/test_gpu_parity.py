@@ -304,6 +304,28 @@ def test_config4_shape_1m(eng):
     eng.set_compact_revision(None)
 
 
+def test_config4_shape_10m(eng):
+    """config 4 at 1/10 size: 1M objects x (1 revision record + 9 versions) = 10M records, 8M superseded victims;
+    exercises >9k tiles, multi-GB slabs and the single-CTA tile scan loop"""
+    store, meta = synth.gen_store(1_000_000, 9, 64, 64, 10000, config_id=4, tomb_frac=0.02)
+    st = ko.OracleStore(store)
+    eng.load_sorted(store)
+    lo, hi = CODER.encode_object_key(b"/registry/", 0), CODER.encode_object_key(b"/registry0", 0)
+    exp = ko.scan(st, [lo, hi], meta.last_rev, compact=True, collect=False)
+    got = eng.compact_sweep(lo, hi, meta.last_rev)
+    assert got.n_victims == len(exp.victims) and got.count == exp.count
+    assert np.array_equal(got.victim_idx.astype(np.uint64), exp.victims)
+    assert np.array_equal(got.victim_class, exp.vclass)
+    assert int((got.victim_class == 1).sum()) == 8_000_000
+    got.close()
+    # and a full Range over the same 10M records at the 90th-percentile revision
+    r = ko.range_(st, lo, hi, meta.read_rev)
+    eng.set_compact_revision(None)
+    res = eng.range_batch([(lo, hi, meta.read_rev, 0)], KB_OUT_HOST)
+    assert np.array_equal(res.rec_idx.astype(np.uint64), r.emit)
+    res.close()
+
+
 # ---- watch fan-out ------------------------------------------------------------------------------------------
 def check_fanout(eng_new, ev: PackedEvents, w: PackedWatchers):
     e = Engine(0)
