@@ -717,6 +717,43 @@ struct Resolved {
     uint64_t total_flat = 0, total_sel = 0, key_bytes = 0, n_records = 0;
 };
 
+// lay the requests ([lo,hi) already known) out as tiles of KB_TILE records that never span two requests
+int layout_requests(kb_ctx *ctx, bool cap_by_limit, Resolved &R)
+{
+    R.tiles.clear();
+    R.n_records = 0;
+    uint64_t flat = 0, selb = 0;
+    for (size_t q = 0; q < R.reqs.size(); q++) {
+        ReqDev &r = R.reqs[q];
+        r.flat0 = (uint32_t)flat;
+        r.tile0 = (uint32_t)R.tiles.size();
+        uint32_t n = r.hi - r.lo;
+        r.ntiles = (n + KB_TILE - 1) / KB_TILE;
+        r.sel_base = (uint32_t)selb;
+        for (uint32_t t = 0; t < r.ntiles; t++) {
+            TileDev td;
+            td.req = (uint32_t)q;
+            td.rec0 = r.lo + t * KB_TILE;
+            td.n = std::min<uint32_t>(KB_TILE, n - t * KB_TILE);
+            td.flat0 = r.flat0 + t * KB_TILE;
+            td.lo = r.lo;
+            td.pad = 0;
+            td.read_rev = r.read_rev;
+            R.tiles.push_back(td);
+        }
+        flat += (uint64_t)r.ntiles * KB_TILE;
+        uint64_t cap = n;
+        if (cap_by_limit && r.limit > 0) cap = std::min<uint64_t>(cap, (uint64_t)r.limit);
+        selb += cap;
+        R.n_records += n;
+        if (flat >= 0xFFFFF000ull || selb >= 0xFFFFF000ull)
+            return kb_fail(ctx, KB_ELIMIT, "batch examines more than 2^32 records; split it");
+    }
+    R.total_flat = flat;
+    R.total_sel = selb;
+    return KB_OK;
+}
+
 // upload the bound keys, run k_search, and lay the requests out as tiles
 int resolve_requests(kb_ctx *ctx, const kb_range_req *reqs, uint64_t nreq, bool cap_by_limit, Resolved &R)
 {
@@ -759,41 +796,14 @@ int resolve_requests(kb_ctx *ctx, const kb_range_req *reqs, uint64_t nreq, bool 
     KB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 
     R.reqs.resize(nreq);
-    R.tiles.clear();
-    uint64_t flat = 0, selb = 0;
     for (uint64_t q = 0; q < nreq; q++) {
         ReqDev &r = R.reqs[q];
         r.lo = hres[2 * q];
         r.hi = std::max(hres[2 * q + 1], r.lo);
-        r.flat0 = (uint32_t)flat;
-        r.tile0 = (uint32_t)R.tiles.size();
-        uint32_t n = r.hi - r.lo;
-        r.ntiles = (n + KB_TILE - 1) / KB_TILE;
-        r.sel_base = (uint32_t)selb;
         r.read_rev = reqs[q].read_rev;
         r.limit = reqs[q].limit;
-        for (uint32_t t = 0; t < r.ntiles; t++) {
-            TileDev td;
-            td.req = (uint32_t)q;
-            td.rec0 = r.lo + t * KB_TILE;
-            td.n = std::min<uint32_t>(KB_TILE, n - t * KB_TILE);
-            td.flat0 = r.flat0 + t * KB_TILE;
-            td.lo = r.lo;
-            td.pad = 0;
-            td.read_rev = r.read_rev;
-            R.tiles.push_back(td);
-        }
-        flat += (uint64_t)r.ntiles * KB_TILE;
-        uint64_t cap = n;
-        if (cap_by_limit && r.limit > 0) cap = std::min<uint64_t>(cap, (uint64_t)r.limit);
-        selb += cap;
-        R.n_records += n;
-        if (flat >= 0xFFFFF000ull || selb >= 0xFFFFF000ull)
-            return kb_fail(ctx, KB_ELIMIT, "batch examines more than 2^32 records; split it");
     }
-    R.total_flat = flat;
-    R.total_sel = selb;
-    return KB_OK;
+    return layout_requests(ctx, cap_by_limit, R);
 }
 
 int upload_layout(kb_ctx *ctx, const Resolved &R)
@@ -843,6 +853,104 @@ static int launch_decode(kb_ctx *ctx, uint32_t ntiles, uint64_t alg_bytes, const
     return KB_OK;
 }
 
+// decode -> emit -> tile scan -> (place) for an uploaded layout; everything stays enqueued on ctx->stream
+static int launch_scan_core(kb_ctx *ctx, const Resolved &R, const ScanMode &mode, bool with_place)
+{
+    const uint32_t nt = (uint32_t)R.tiles.size();
+    const uint32_t nreq = (uint32_t)R.reqs.size();
+    const ReqDev *d_reqs = (const ReqDev *)ctx->d_reqs.p;
+    const TileDev *d_tiles = (const TileDev *)ctx->d_tiles.p;
+    uint32_t *d_meta = (uint32_t *)ctx->d_meta.p;
+    uint32_t *d_tgt = (uint32_t *)ctx->d_tgt.p;
+    uint32_t *d_tail = d_tgt + std::max<uint64_t>(R.total_flat, 4);
+    uint2 *d_agg = (uint2 *)ctx->d_agg.p;
+    uint64_t *d_tcnt = (uint64_t *)ctx->d_tcnt.p;
+    uint64_t *d_tscan = (uint64_t *)ctx->d_tscan.p;
+    ReqOut *d_rout = (ReqOut *)ctx->d_reqout.p;
+    // algorithmic bytes of the decode pass: key bytes of the examined records + 10 B of offsets/lengths each
+    uint64_t kbytes = 0;
+    for (auto &r : R.reqs)
+        kbytes += (uint64_t)(ctx->h_koff16[r.hi] - ctx->h_koff16[r.lo]) * 16 + (uint64_t)(r.hi - r.lo) * 10;
+    if (nt) {
+        KB_TRY(launch_decode(ctx, nt, kbytes, mode, d_reqs, d_tiles, d_meta, d_agg));
+        if (mode.compact) {
+            KB_LAUNCH(ctx, "k_emit_compact", R.n_records * 8,
+                      (k_emit<true><<<nt, 256, 0, ctx->stream>>>(ctx->st, d_reqs, d_tiles, d_agg, d_meta, d_tgt, d_tail,
+                                                                d_tcnt)));
+        } else {
+            KB_LAUNCH(ctx, "k_emit", R.n_records * 8,
+                      (k_emit<false><<<nt, 256, 0, ctx->stream>>>(ctx->st, d_reqs, d_tiles, d_agg, d_meta, d_tgt, d_tail,
+                                                                 d_tcnt)));
+        }
+    }
+    KB_LAUNCH(ctx, "k_tile_scan", (uint64_t)nt * 32,
+              (k_tile_scan<<<1, 256, 0, ctx->stream>>>(d_reqs, nreq, d_tcnt, d_tscan, nt, d_rout)));
+    if (nt && with_place) {
+        KB_LAUNCH(ctx, "k_place", R.n_records * 4,
+                  (k_place<<<nt, 256, 0, ctx->stream>>>(ctx->st, d_reqs, d_tiles, d_tgt, d_tail, d_tscan,
+                                                        (uint32_t *)ctx->d_sel.p, (uint64_t *)ctx->d_slot.p, d_rout)));
+    }
+    KB_CUDA(ctx, cudaGetLastError());
+    return KB_OK;
+}
+
+// `limit` requests over intervals much larger than the limit: find how far the reference's loop would read
+// (worker.run stops pulling from the iterator once the receiver is full, scanner.go:416 / receiver.go:82-87) by
+// scanning geometrically growing windows, then clip the request to exactly those records.  The final pass then
+// sees what the reference saw, with work proportional to the answer instead of to the interval.
+constexpr uint32_t KB_LIMIT_WINDOW_MIN = 8192;
+
+static int probe_limit_windows(kb_ctx *ctx, Resolved &R)
+{
+    struct Todo {
+        uint32_t q, true_hi;
+        uint64_t w;
+    };
+    std::vector<Todo> todo;
+    for (uint32_t q = 0; q < R.reqs.size(); q++) {
+        const ReqDev &r = R.reqs[q];
+        if (r.limit <= 0) continue;
+        uint64_t w0 = std::max<uint64_t>(KB_LIMIT_WINDOW_MIN, (uint64_t)r.limit * 8);
+        w0 = (w0 + KB_TILE - 1) / KB_TILE * KB_TILE;
+        if ((uint64_t)(r.hi - r.lo) > w0) todo.push_back(Todo{q, r.hi, w0});
+    }
+    if (todo.empty()) return KB_OK;
+    ScanMode mode;
+    mode.compact = 0;
+    mode.ttl_scan = 0;
+    mode.timeout_rev = 0;
+    mode.want_sel = 1;
+    while (!todo.empty()) {
+        Resolved P;
+        P.reqs.resize(todo.size());
+        for (size_t i = 0; i < todo.size(); i++) {
+            P.reqs[i] = R.reqs[todo[i].q];
+            P.reqs[i].hi = (uint32_t)std::min<uint64_t>(todo[i].true_hi, (uint64_t)P.reqs[i].lo + todo[i].w);
+        }
+        KB_TRY(layout_requests(ctx, true, P));
+        KB_TRY(upload_layout(ctx, P));
+        KB_TRY(dbuf_ensure(ctx, ctx->d_sel, std::max<uint64_t>(P.total_sel, 1) * 4));
+        KB_TRY(dbuf_ensure(ctx, ctx->d_slot, std::max<uint64_t>(P.total_sel, 1) * 8));
+        KB_TRY(launch_scan_core(ctx, P, mode, true));
+        KB_TRY(hbuf_ensure(ctx, ctx->h_stage, P.reqs.size() * sizeof(ReqOut) + 64));
+        KB_CUDA(ctx, cudaMemcpyAsync(ctx->h_stage.p, ctx->d_reqout.p, P.reqs.size() * sizeof(ReqOut),
+                                     cudaMemcpyDeviceToHost, ctx->stream));
+        KB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        const ReqOut *ro = (const ReqOut *)ctx->h_stage.p;
+        std::vector<Todo> next;
+        for (size_t i = 0; i < todo.size(); i++) {
+            ReqDev &r = R.reqs[todo[i].q];
+            if (ro[i].limit_stop)
+                r.hi = r.lo + ro[i].examined;  // exactly the records the reference's loop pulled
+            else if (P.reqs[i].hi != todo[i].true_hi)
+                next.push_back(Todo{todo[i].q, todo[i].true_hi, todo[i].w * 8});
+            // else: the whole interval was examined and the limit was not reached inside the loop
+        }
+        todo.swap(next);
+    }
+    return layout_requests(ctx, true, R);
+}
+
 extern "C" int kb_range_batch(kb_ctx *ctx, const kb_range_req *reqs, uint64_t nreq, int out_mode, kb_result **out)
 {
     if (!ctx || !out || (nreq && !reqs)) return KB_EINVAL;
@@ -861,46 +969,21 @@ extern "C" int kb_range_batch(kb_ctx *ctx, const kb_range_req *reqs, uint64_t nr
     Resolved R;
     KB_TRY(resolve_requests(ctx, reqs, nreq, true, R));
     kb_seg(ctx, "host:range_resolve+sync", tseg);
+    if (out_mode != KB_OUT_COUNT) {
+        KB_TRY(probe_limit_windows(ctx, R));
+        kb_seg(ctx, "host:range_limit_probe", tseg);
+    }
     KB_TRY(upload_layout(ctx, R));
-    const uint32_t nt = (uint32_t)R.tiles.size();
     KB_TRY(dbuf_ensure(ctx, ctx->d_sel, std::max<uint64_t>(R.total_sel, 1) * 4));
     KB_TRY(dbuf_ensure(ctx, ctx->d_slot, std::max<uint64_t>(R.total_sel, 1) * 8));
-
     const ReqDev *d_reqs = (const ReqDev *)ctx->d_reqs.p;
-    const TileDev *d_tiles = (const TileDev *)ctx->d_tiles.p;
-    uint32_t *d_meta = (uint32_t *)ctx->d_meta.p;
-    uint32_t *d_tgt = (uint32_t *)ctx->d_tgt.p;
-    uint32_t *d_tail = d_tgt + std::max<uint64_t>(R.total_flat, 4);
-    uint2 *d_agg = (uint2 *)ctx->d_agg.p;
-    uint64_t *d_tcnt = (uint64_t *)ctx->d_tcnt.p;
-    uint64_t *d_tscan = (uint64_t *)ctx->d_tscan.p;
     ReqOut *d_rout = (ReqOut *)ctx->d_reqout.p;
-
     ScanMode mode;
     mode.compact = 0;
     mode.ttl_scan = 0;
     mode.timeout_rev = 0;
     mode.want_sel = out_mode != KB_OUT_COUNT;
-    // algorithmic bytes of the decode pass: key bytes of the examined records + 10 B of offsets/lengths each
-    uint64_t kbytes = 0;
-    {
-        std::vector<uint32_t> &ko = host_koff16(ctx);
-        for (auto &r : R.reqs) kbytes += (uint64_t)(ko[r.hi] - ko[r.lo]) * 16 + (uint64_t)(r.hi - r.lo) * 10;
-    }
-    if (nt) {
-        KB_TRY(launch_decode(ctx, nt, kbytes, mode, d_reqs, d_tiles, d_meta, d_agg));
-        KB_LAUNCH(ctx, "k_emit", R.n_records * 8,
-                  (k_emit<false><<<nt, 256, 0, ctx->stream>>>(ctx->st, d_reqs, d_tiles, d_agg, d_meta, d_tgt, d_tail,
-                                                             d_tcnt)));
-    }
-    KB_LAUNCH(ctx, "k_tile_scan", (uint64_t)nt * 32,
-              (k_tile_scan<<<1, 256, 0, ctx->stream>>>(d_reqs, (uint32_t)nreq, d_tcnt, d_tscan, nt, d_rout)));
-    if (nt && out_mode != KB_OUT_COUNT) {
-        KB_LAUNCH(ctx, "k_place", R.n_records * 4,
-                  (k_place<<<nt, 256, 0, ctx->stream>>>(ctx->st, d_reqs, d_tiles, d_tgt, d_tail, d_tscan,
-                                                        (uint32_t *)ctx->d_sel.p, (uint64_t *)ctx->d_slot.p, d_rout)));
-    }
-    KB_CUDA(ctx, cudaGetLastError());
+    KB_TRY(launch_scan_core(ctx, R, mode, out_mode != KB_OUT_COUNT));
 
     // Response arena: sized by an upper bound the host knows without a round trip (all key+value bytes of the examined
     // record intervals), so the gather is enqueued right behind the placement and the only synchronisation left is
