@@ -38,6 +38,27 @@ __device__ __forceinline__ void cp_async_wait()
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
+// ---- bulk (TMA) copy + mbarrier helpers: one instruction moves a whole sub-tile's key bytes into shared memory
+__device__ __forceinline__ uint32_t dsmem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void dmbar_init(uint64_t *bar)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(dsmem_u32(bar)));
+}
+__device__ __forceinline__ void dmbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "KBD_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra KBD_DONE;\n"
+        "bra KBD_WAIT;\n"
+        "KBD_DONE:\n"
+        "}\n" ::"r"(dsmem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
 __device__ __forceinline__ bool contains_events(const uint8_t *uk, uint32_t n)  // bytes.Contains(rawKey, "/events/")
 {
     uint64_t w = 0;
@@ -128,7 +149,7 @@ __device__ __forceinline__ SubDesc load_desc(const StoreDev &st, const TileRef &
 // pipeline stage 2: start the asynchronous copy of the sub-tile's key bytes (plus the record before it) into `buf`
 // and the value probe of the 9-byte values (tombstone literal / deleted-flag revision record)
 __device__ __forceinline__ void issue_stage(const StoreDev &st, const ScanMode &mode, SubDesc &d, uint4 *buf,
-                                            uint32_t lane)
+                                            uint64_t *bar, uint32_t lane)
 {
     if (!d.valid || d.nrec == 0) return;
     const bool halo = d.r0 > d.lo;
@@ -136,8 +157,18 @@ __device__ __forceinline__ void issue_stage(const StoreDev &st, const ScanMode &
     const uint32_t end16 = __shfl_sync(0xffffffffu, d.ko + ((d.kl + 15) >> 4), d.nrec - 1);
     d.span = end16 - d.base16;
     if (d.span <= KB_WARP_STAGE_CHUNKS) {
-        const uint4 *src = st.kslab + d.base16;
-        for (uint32_t c = lane; c < d.span; c += 32) cp_async16(buf + c, src + c);
+        // one bulk (TMA) copy for the whole sub-tile: [base16, base16+span) chunks -> buf.  The buffer was last read
+        // (generic proxy) two steps ago and a __syncwarp separates those reads from this point; the proxy fence orders
+        // them before the async-proxy write.
+        if (lane == 0) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(dsmem_u32(bar)), "r"(d.span * 16)
+                         : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             dsmem_u32(buf)),
+                         "l"(st.kslab + d.base16), "r"(d.span * 16), "r"(dsmem_u32(bar))
+                         : "memory");
+        }
     }
     // only 9-byte values are ever inspected by the range path; the TTL sweep also reads revision-record values
     if (lane < d.nrec && d.vl >= 8 && (d.vl == 9 || mode.ttl_scan)) d.v0 = st.vslab[d.vo];
@@ -281,6 +312,16 @@ k_decode_lcp(StoreDev st, const ReqDev *__restrict__ reqs, const TileDev *__rest
     const uint32_t stride = gridDim.x * DECODE_WARPS;
     uint32_t sid = blockIdx.x * DECODE_WARPS + warp;
 
+    // one mbarrier per stage buffer; the phase of buffer b flips each time it is filled
+    __shared__ uint64_t bars[DECODE_WARPS * DECODE_STAGES];
+    uint64_t *bar0 = bars + warp * DECODE_STAGES;
+    if (lane == 0) {
+        dmbar_init(bar0);
+        dmbar_init(bar0 + 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+
     // prologue: fill the pipeline
     TileRef tA = fetch_tile(tiles, sid, n_sub);
     sid += stride;
@@ -290,8 +331,8 @@ k_decode_lcp(StoreDev st, const ReqDev *__restrict__ reqs, const TileDev *__rest
     SubDesc dA = load_desc(st, tA, lane);
     tA = fetch_tile(tiles, sid, n_sub);
     sid += stride;
-    issue_stage(st, mode, dB, buf0, lane);
-    cp_async_commit();
+    issue_stage(st, mode, dB, buf0, bar0, lane);
+    uint32_t fills0 = 0, fills1 = 0;  // completed-phase counters of the two buffers (parity = count & 1)
     // The body is unrolled six times (lcm of the 3 descriptor roles and the 2 stage buffers) so that the role
     // rotation dC <- dB <- dA is pure register renaming inside the body; moves remain only on the back edge.
     bool more = dB.valid != 0;
@@ -304,17 +345,23 @@ k_decode_lcp(StoreDev st, const ReqDev *__restrict__ reqs, const TileDev *__rest
                 dA = load_desc(st, tA, lane);
                 tA = fetch_tile(tiles, sid, n_sub);
                 sid += stride;
-                issue_stage(st, mode, dB, buf0 + ((u + 1) & 1) * KB_WARP_STAGE_CHUNKS, lane);
-                cp_async_commit();
-                cp_async_wait<1>();  // everything but the newest group has landed: dC's bytes are in shared memory
-                __syncwarp();
+                issue_stage(st, mode, dB, buf0 + ((u + 1) & 1) * KB_WARP_STAGE_CHUNKS, bar0 + ((u + 1) & 1), lane);
+                // wait for dC's bytes (only if a copy was issued for it: real, staged sub-tile)
+                if (dC.nrec != 0 && dC.span <= KB_WARP_STAGE_CHUNKS) {
+                    if ((u & 1) == 0) {
+                        dmbar_wait(bar0, fills0 & 1);
+                        fills0++;
+                    } else {
+                        dmbar_wait(bar0 + 1, fills1 & 1);
+                        fills1++;
+                    }
+                }
                 process_sub(st, mode, dC, buf0 + (u & 1) * KB_WARP_STAGE_CHUNKS, lane, meta, sub_agg);
                 __syncwarp();
                 more = dB.valid != 0;
             }
         }
     }
-    cp_async_wait<0>();
 }
 
 }  // namespace
