@@ -223,6 +223,7 @@ def workload_config(world: int, wl):
         "events_per_gpu": int(wl["events"].n), "read_rev": int(wl["meta"].read_rev),
         "parallelism": f"hash-shard x{world}" if world > 1 else "single GPU",
         "l2": "inputs larger than L2 (>= 0.7 GB streamed from HBM per step)",
+        "overlap": "scan and fan-out run concurrently on two streams of the same GPU (two kb_ctx)",
         "unit_of_work": "records examined + events matched",
     }
 
@@ -243,9 +244,12 @@ def run_b200(args, rank: int, local_rank: int, world: int):
         dist = dist_mod
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     wl = build_workload(rank, world)
+    # two contexts on the same GPU, as in the reference where scans and the watch hub are independent goroutines:
+    # `eng` owns the HBM-resident snapshot (scans), `weng` owns the watcher tables (fan-out); each has its own stream
     eng = Engine(local_rank)
     eng.load_sorted(wl["store"])
-    eng.watch_add_many(wl["watchers"])
+    weng = eng if args.serial else Engine(local_rank)
+    weng.watch_add_many(wl["watchers"])
     # the revision-cursor communicator (one uint64 per rank)
     uid = Engine.nccl_unique_id() if rank == 0 else bytes(128)
     if world > 1:
@@ -253,33 +257,81 @@ def run_b200(args, rank: int, local_rank: int, world: int):
         dist.broadcast(t, 0)
         uid = bytes(t.cpu().tolist())
     eng.nccl_init(uid, rank, world)
-    evh = eng.events_upload(wl["events"])
+    evh = weng.events_upload(wl["events"])
     stream = torch.cuda.ExternalStream(eng.stream())
+    wstream = torch.cuda.ExternalStream(weng.stream())
     reqs = wl["reqs"]
     local_rev = int(wl["meta"].last_rev)
 
-    def step_device():
+    # the fan-out half runs on a long-lived worker thread (ctypes releases the GIL inside the C ABI calls)
+    import queue
+    import threading
+
+    jobs_q, done_q = queue.SimpleQueue(), queue.SimpleQueue()
+
+    def worker():
+        torch.cuda.set_device(local_rank)
+        while True:
+            fn = jobs_q.get()
+            if fn is None:
+                return
+            try:
+                done_q.put(fn())
+            except Exception as e:  # surfaced on the main thread
+                done_q.put(e)
+
+    wthread = None
+    if not args.serial:
+        wthread = threading.Thread(target=worker, daemon=True)
+        wthread.start()
+
+    def fan_device():
+        m = weng.watch_match_dev(evh, KB_OUT_DEVICE)
+        d = m.n_deliveries
+        m.close()
+        return d
+
+    def fan_e2e():
+        m = weng.watch_match(wl["events"], KB_OUT_HOST)
+        d = m.n_deliveries
+        dbytes = d * 4 + (m.n_watchers + 1) * 8
+        m.close()
+        return dbytes
+
+    def both(scan_fn, fan_fn):
+        if args.serial:
+            a = scan_fn()
+            return a, fan_fn()
+        jobs_q.put(fan_fn)
+        a = scan_fn()
+        b = done_q.get()
+        if isinstance(b, Exception):
+            raise b
+        return a, b
+
+    def scan_device():
         _, readable = eng.cursor_allgather(local_rev)
         r = eng.range_batch(reqs, KB_OUT_DEVICE)
         ex = int(r.req_examined.sum())
         nk = r.n_kvs
         r.close()
-        m = eng.watch_match_dev(evh, KB_OUT_DEVICE)
-        d = m.n_deliveries
-        m.close()
-        return ex, nk, d
+        return ex, nk
 
-    def step_e2e():
+    def scan_e2e():
         _, readable = eng.cursor_allgather(local_rev)
         r = eng.range_batch(reqs, KB_OUT_HOST)
         ex = int(r.req_examined.sum())
         nbytes = r.n_bytes + r.n_kvs * 36
         checksum = int(r.arena[:: max(1, r.n_bytes // 4096)].sum()) if r.n_bytes else 0  # the host reads the result
         r.close()
-        m = eng.watch_match(wl["events"], KB_OUT_HOST)
-        d = m.n_deliveries
-        dbytes = d * 4 + (m.n_watchers + 1) * 8
-        m.close()
+        return ex, nbytes, checksum
+
+    def step_device():
+        (ex, nk), d = both(scan_device, fan_device)
+        return ex, nk, d
+
+    def step_e2e():
+        (ex, nbytes, checksum), dbytes = both(scan_e2e, fan_e2e)
         return ex, nbytes + dbytes, checksum
 
     def barrier():
@@ -289,16 +341,17 @@ def run_b200(args, rank: int, local_rank: int, world: int):
 
     def timed(fn, steps):
         barrier()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a, b, bw = (torch.cuda.Event(enable_timing=True) for _ in range(3))
         a.record(stream)
         t0 = time.perf_counter()
         out = None
         for _ in range(steps):
             out = fn()
         b.record(stream)
+        bw.record(wstream)
         barrier()
         wall = time.perf_counter() - t0
-        dev_ms = a.elapsed_time(b)
+        dev_ms = max(a.elapsed_time(b), a.elapsed_time(bw))  # both streams must have drained
         if dist is not None:
             t = torch.tensor([dev_ms, wall * 1e3], dtype=torch.float64, device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -314,18 +367,24 @@ def run_b200(args, rank: int, local_rank: int, world: int):
         sampler.start()
     # timed region: CUDA events bracket only the two HBM-bound kernels (level 2) so the event records do not
     # perturb the step; a second, untimed pass with every kernel bracketed fills the per-kernel table
-    eng.prof_reset()
-    eng.prof_enable(2)
-    l0 = eng.launch_count()
+    engines = [eng] if weng is eng else [eng, weng]
+    for e in engines:
+        e.prof_reset()
+        e.prof_enable(2)
+    l0 = sum(e.launch_count() for e in engines)
     dev_ms, wall_s, (examined, n_kvs, deliveries) = timed(step_device, args.steps)
-    launches = eng.launch_count() - l0
-    eng.prof_enable(0)
-    prof_major = {p["name"]: p for p in eng.prof_read()}
-    eng.prof_reset()
-    eng.prof_enable(1)
+    launches = sum(e.launch_count() for e in engines) - l0
+    prof_major = {}
+    for e in engines:
+        e.prof_enable(0)
+        prof_major.update({p["name"]: p for p in e.prof_read()})
+        e.prof_reset()
+        e.prof_enable(1)
     prof_ms, _, _ = timed(step_device, args.steps)
-    eng.prof_enable(0)
-    prof = eng.prof_read()
+    prof = []
+    for e in engines:
+        e.prof_enable(0)
+        prof += e.prof_read()
     for p in prof:  # the timed-region measurement wins for the kernels it covers
         if p["name"] in prof_major:
             p.update(prof_major[p["name"]])
@@ -357,7 +416,8 @@ def run_b200(args, rank: int, local_rank: int, world: int):
                          "achieved_gbs": (per_launch / 1e9) / (ms / 1e3) if ms > 0 else None,
                          "share": p["total_ms"] / max(dev_ms if p["name"] in prof_major else prof_ms, 1e-9),
                          "timed_region": p["name"] in prof_major})
-        kern.sort(key=lambda k: -k["share"])
+        host_segments = sorted([k for k in kern if k["name"].startswith("host:")], key=lambda k: -k["share"])
+        kern = sorted([k for k in kern if not k["name"].startswith("host:")], key=lambda k: -k["share"])
         dom = kern[0] if kern else None
         roof = None
         if dom:
@@ -373,7 +433,7 @@ def run_b200(args, rank: int, local_rank: int, world: int):
                     "d2h_bytes_per_step": int(d2h_bytes), "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": launches_total,
             "roofline": roof,
-            "kernels": kern,
+            "kernels": kern, "host_segments": host_segments,
             "scan_records_per_step": int(examined), "emitted_kvs_per_step": int(n_kvs),
             "fanout_events_per_step": int(wl["events"].n), "deliveries_per_step": int(deliveries),
             "wall_ms_per_step": wall_s * 1e3 / args.steps, "gen_s": wl["gen_s"],
@@ -383,7 +443,12 @@ def run_b200(args, rank: int, local_rank: int, world: int):
         if world == 1 and not args.no_extras:
             line["extra"] = {"compaction": compaction_extra(local_rank)}
         print(json.dumps(line), flush=True)
-    eng.events_free(evh)
+    if wthread is not None:
+        jobs_q.put(None)
+        wthread.join(timeout=5)
+    weng.events_free(evh)
+    if weng is not eng:
+        weng.close()
     eng.close()
     if dist is not None:
         dist.barrier()
@@ -453,6 +518,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--serial", action="store_true", help="scan and fan-out back to back on one stream")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

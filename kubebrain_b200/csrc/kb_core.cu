@@ -245,9 +245,9 @@ extern "C" void kb_close(kb_ctx *ctx)
     cudaStreamSynchronize(ctx->stream);
     watch_tables_free(ctx);
     DBuf *all[] = {&ctx->d_kslab, &ctx->d_koff16, &ctx->d_klen, &ctx->d_vslab, &ctx->d_voff16, &ctx->d_vlen,
-                   &ctx->d_bounds, &ctx->d_boff, &ctx->d_blen, &ctx->d_bres, &ctx->d_reqs,
+                   &ctx->d_bounds, &ctx->d_bres, &ctx->d_reqs,
                    &ctx->d_meta, &ctx->d_tgt, &ctx->d_agg, &ctx->d_tcnt, &ctx->d_tscan, &ctx->d_reqout,
-                   &ctx->d_sel, &ctx->d_slot, &ctx->d_jobs, &ctx->d_gjobs, &ctx->d_scan_tmp, &ctx->d_flags, &ctx->d_cursor};
+                   &ctx->d_sel, &ctx->d_slot, &ctx->d_jobs, &ctx->d_gjobs, &ctx->d_flags, &ctx->d_cursor};
     for (DBuf *b : all) dfree(*b);
     for (auto &b : ctx->free_dev) cudaFree(b.p);
     for (auto &b : ctx->free_host) cudaFreeHost(b.p);

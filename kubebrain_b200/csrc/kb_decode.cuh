@@ -1,8 +1,8 @@
 // kb_decode.cuh -- k_decode_lcp: the HBM-bound pass of the scan (included by kb_scan.cu).
 //
-// Streams the raw internal keys of every examined record once (coalesced 16-byte transfers into a per-warp
-// shared-memory ring with cp.async, two stages deep so the next sub-tile is in flight while the current one is
-// decoded), and reduces each record to one 32-bit meta word:
+// Streams the raw internal keys of every examined record once (one bulk-TMA copy per 32-record sub-tile into a
+// per-warp shared-memory ring, two stages deep so the next sub-tile is in flight while the current one is decoded),
+// and reduces each record to one 32-bit meta word:
 //   bits 0..15  LCP with the preceding key (common-prefix length, the input of the "same user key" test)
 //   bits 16..23 decode / visibility / tombstone / compaction-class flags (KB_M_*)
 // plus one (last PREVOK slot, min LCP after it) aggregate per 32-record sub-tile for the cross-tile carry.
@@ -12,8 +12,8 @@
 // tombstone test, deleted-flag revision-record test.  Warps are persistent and fully independent (no CTA barrier).
 //
 // Per-warp software pipeline (every stage one iteration apart, so no load is waited for in the iteration that
-// issues it):   tile descriptor -> record directory (koff16/klen/vlen/voff16) -> key bytes (cp.async) + 16-byte
-// value probe of 9-byte values -> decode.
+// issues it):   tile descriptor -> record directory (koff16/klen/vlen/voff16) -> key bytes (cp.async.bulk, completion
+// on an mbarrier) + 16-byte value probe of 9-byte values -> decode.
 #pragma once
 
 #include "kb_internal.cuh"
@@ -25,18 +25,6 @@ constexpr int DECODE_WARPS = 12;
 constexpr int DECODE_STAGES = 2;
 
 __device__ __forceinline__ uint32_t bswap32(uint32_t x) { return __byte_perm(x, 0, 0x0123); }
-
-__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src)
-{
-    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait()
-{
-    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
 
 // ---- bulk (TMA) copy + mbarrier helpers: one instruction moves a whole sub-tile's key bytes into shared memory
 __device__ __forceinline__ uint32_t dsmem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }

@@ -51,7 +51,6 @@ struct ScanMode {
     int      compact;      // workerConfig.compact
     int      ttl_scan;     // !SupportTTL() && timeoutRevision != 0
     uint64_t timeout_rev;
-    int      want_sel;     // 0: count only
 };
 
 // per-record meta word produced by the decode pass
@@ -166,8 +165,8 @@ struct kb_ctx {
     uint64_t compact_rev = 0;
 
     // scratch (grow only)
-    DBuf d_bounds, d_boff, d_blen, d_bres, d_reqs, d_tiles, d_meta, d_tgt, d_agg, d_tcnt, d_tscan, d_reqout, d_sel,
-        d_slot, d_jobs, d_gjobs, d_scan_tmp, d_flags;
+    DBuf d_bounds, d_bres, d_reqs, d_tiles /* alias into d_reqs */, d_meta, d_tgt, d_agg, d_tcnt, d_tscan, d_reqout,
+        d_sel, d_slot, d_jobs, d_gjobs, d_flags;
     HBuf h_stage, h_stage2;
 
     // buffer pools for results
@@ -269,10 +268,6 @@ static inline void kb_seg(kb_ctx *ctx, const char *name, kb_tp &t)
     ctx->prof[i].ms += std::chrono::duration<double, std::milli>(n - t).count();
     t = n;
 }
-
-// generic exclusive scans on the ctx stream (kb_scan_util.cu)
-int scan_exclusive_u32(kb_ctx *ctx, const uint32_t *in, uint32_t *out, uint32_t n, uint32_t *total_dev);
-int scan_exclusive_u64(kb_ctx *ctx, const uint64_t *in, uint64_t *out, uint32_t n, uint64_t *total_dev);
 
 // kb_watch.cu
 void watch_tables_free(kb_ctx *ctx);

@@ -547,7 +547,7 @@ k_gather_jobs(StoreDev st, const ReqDev *__restrict__ reqs, uint32_t nreq, const
 // moved in pieces.  The copy engine generates full-line requests; the SM only issues two or three instructions per
 // 2.5 KB piece.
 constexpr int GATHER_WARPS = 8;
-constexpr int GATHER_STAGES = 6;
+constexpr int GATHER_STAGES = 8;
 constexpr int GATHER_DIST = GATHER_STAGES - 2;   // pieces in flight per warp
 constexpr uint32_t GATHER_PIECE = 160;           // 16-byte chunks per buffer (2560 B)
 
@@ -577,18 +577,22 @@ k_gather(StoreDev st, const GatherJob *__restrict__ jobs, const uint64_t *__rest
     __shared__ uint64_t ring_dst[GATHER_WARPS * GATHER_STAGES];
     __shared__ uint32_t ring_len[GATHER_WARPS * GATHER_STAGES];
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (lane != 0) return;  // one driver lane per warp; the data never passes through registers
+    // Lane 0 drives the copies (the data never passes through registers); the other lanes only help to fetch the
+    // job descriptors: 32 jobs per coalesced load, handed to lane 0 by shuffles, next block prefetched.
     uint4 *buf = gbuf + (size_t)warp * GATHER_STAGES * GATHER_PIECE;
     uint64_t *bar = bars + warp * GATHER_STAGES;
     uint64_t *rdst = ring_dst + warp * GATHER_STAGES;
     uint32_t *rlen = ring_len + warp * GATHER_STAGES;
-    for (int s = 0; s < GATHER_STAGES; s++)
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar + s)));
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    if (lane == 0) {
+        for (int s = 0; s < GATHER_STAGES; s++)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar + s)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
 
     const uint64_t n_kvs = *n_kvs_dev;
     const uint64_t nwarps = (uint64_t)gridDim.x * GATHER_WARPS;
-    uint32_t t_issue = 0, t_store = 0;  // pieces issued / stored by this warp
+    uint32_t t_issue = 0, t_store = 0;  // pieces issued / stored by this warp (lane 0 only)
 
     // wait for the oldest in-flight piece and send it to the arena
     auto retire = [&]() {
@@ -601,44 +605,71 @@ k_gather(StoreDev st, const GatherJob *__restrict__ jobs, const uint64_t *__rest
         t_store++;
     };
 
-    for (uint64_t k = (uint64_t)blockIdx.x * GATHER_WARPS + warp; k < n_kvs; k += nwarps) {
-        const uint4 *jp = (const uint4 *)(jobs + k);
-        const uint4 j0 = __ldg(jp), j1 = __ldg(jp + 1);
-        const uint64_t dst16 = ((uint64_t)j0.y << 32) | j0.x, vsrc16 = ((uint64_t)j0.w << 32) | j0.z;
-        const uint32_t ksrc16 = j1.x, nk = j1.y, nv = j1.z;
-        const uint32_t n = nk + nv;
-        for (uint32_t c0 = 0; c0 < n; c0 += GATHER_PIECE) {
-            const uint32_t len = min(GATHER_PIECE, n - c0);
-            if (t_issue - t_store >= (uint32_t)GATHER_DIST) retire();
-            const uint32_t st_i = t_issue % GATHER_STAGES;
-            // the buffer was last read by the bulk store of piece t_issue - STAGES; at most two younger store groups
-            // can still be pending when it has finished reading shared memory
-            asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory");
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar + st_i)),
-                         "r"(len * 16)
-                         : "memory");
-            uint4 *dstbuf = buf + st_i * GATHER_PIECE;
-            const uint32_t kpart = c0 < nk ? min(nk - c0, len) : 0;  // chunks of this piece that come from the key
-            if (kpart)
-                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                                 smem_u32(dstbuf)),
-                             "l"(st.kslab + ksrc16 + c0), "r"(kpart * 16), "r"(smem_u32(bar + st_i))
-                             : "memory");
-            if (len > kpart) {
-                const uint32_t v0c = (c0 + kpart) - nk;  // first value chunk of this piece
-                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                                 smem_u32(dstbuf + kpart)),
-                             "l"(st.vslab + vsrc16 + v0c), "r"((len - kpart) * 16), "r"(smem_u32(bar + st_i))
-                             : "memory");
+    const uint4 zero4 = make_uint4(0, 0, 0, 0);
+    uint64_t base = ((uint64_t)blockIdx.x * GATHER_WARPS + warp) * 32;
+    uint4 n0 = zero4, n1 = zero4;  // this lane's job of the NEXT block (prefetched)
+    if (base + lane < n_kvs) {
+        const uint4 *jp = (const uint4 *)(jobs + base + lane);
+        n0 = __ldg(jp);
+        n1 = __ldg(jp + 1);
+    }
+    for (; base < n_kvs; base += nwarps * 32) {
+        const uint4 c0j = n0, c1j = n1;
+        const uint64_t nb = base + nwarps * 32;
+        n0 = n1 = zero4;
+        if (nb + lane < n_kvs) {
+            const uint4 *jp = (const uint4 *)(jobs + nb + lane);
+            n0 = __ldg(jp);
+            n1 = __ldg(jp + 1);
+        }
+        const uint64_t left = n_kvs - base;
+        const uint32_t cnt = left < 32 ? (uint32_t)left : 32u;
+        for (uint32_t j = 0; j < cnt; j++) {
+            const uint32_t d_lo = __shfl_sync(0xffffffffu, c0j.x, j), d_hi = __shfl_sync(0xffffffffu, c0j.y, j);
+            const uint32_t v_lo = __shfl_sync(0xffffffffu, c0j.z, j), v_hi = __shfl_sync(0xffffffffu, c0j.w, j);
+            const uint32_t ksrc16 = __shfl_sync(0xffffffffu, c1j.x, j);
+            const uint32_t nk = __shfl_sync(0xffffffffu, c1j.y, j), nv = __shfl_sync(0xffffffffu, c1j.z, j);
+            if (lane == 0) {
+                const uint64_t dst16 = ((uint64_t)d_hi << 32) | d_lo, vsrc16 = ((uint64_t)v_hi << 32) | v_lo;
+                const uint32_t n = nk + nv;
+                for (uint32_t c0 = 0; c0 < n; c0 += GATHER_PIECE) {
+                    const uint32_t len = min(GATHER_PIECE, n - c0);
+                    if (t_issue - t_store >= (uint32_t)GATHER_DIST) retire();
+                    const uint32_t st_i = t_issue % GATHER_STAGES;
+                    // the buffer was last read by the bulk store of piece t_issue - STAGES; at most two younger store
+                    // groups can still be pending when it has finished reading shared memory
+                    asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory");
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar + st_i)),
+                                 "r"(len * 16)
+                                 : "memory");
+                    uint4 *dstbuf = buf + st_i * GATHER_PIECE;
+                    const uint32_t kpart = c0 < nk ? min(nk - c0, len) : 0;  // chunks of this piece from the key
+                    if (kpart)
+                        asm volatile(
+                            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                smem_u32(dstbuf)),
+                            "l"(st.kslab + ksrc16 + c0), "r"(kpart * 16), "r"(smem_u32(bar + st_i))
+                            : "memory");
+                    if (len > kpart) {
+                        const uint32_t v0c = (c0 + kpart) - nk;  // first value chunk of this piece
+                        asm volatile(
+                            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                smem_u32(dstbuf + kpart)),
+                            "l"(st.vslab + vsrc16 + v0c), "r"((len - kpart) * 16), "r"(smem_u32(bar + st_i))
+                            : "memory");
+                    }
+                    rdst[st_i] = dst16 + c0;
+                    rlen[st_i] = len;
+                    t_issue++;
+                }
             }
-            rdst[st_i] = dst16 + c0;
-            rlen[st_i] = len;
-            t_issue++;
         }
     }
-    while (t_store < t_issue) retire();
-    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    if (lane == 0) {
+        while (t_store < t_issue) retire();
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
 }
 
 // single CTA: per-request emitted count / response bytes (limit applied) and their exclusive prefixes over the
@@ -919,7 +950,6 @@ static int probe_limit_windows(kb_ctx *ctx, Resolved &R)
     mode.compact = 0;
     mode.ttl_scan = 0;
     mode.timeout_rev = 0;
-    mode.want_sel = 1;
     while (!todo.empty()) {
         Resolved P;
         P.reqs.resize(todo.size());
@@ -982,7 +1012,6 @@ extern "C" int kb_range_batch(kb_ctx *ctx, const kb_range_req *reqs, uint64_t nr
     mode.compact = 0;
     mode.ttl_scan = 0;
     mode.timeout_rev = 0;
-    mode.want_sel = out_mode != KB_OUT_COUNT;
     KB_TRY(launch_scan_core(ctx, R, mode, out_mode != KB_OUT_COUNT));
 
     // Response arena: sized by an upper bound the host knows without a round trip (all key+value bytes of the examined
@@ -1191,7 +1220,6 @@ extern "C" int kb_compact_sweep(kb_ctx *ctx, const uint8_t *start, uint64_t star
     mode.compact = 1;
     mode.ttl_scan = (!support_ttl && timeout_rev != 0) ? 1 : 0;
     mode.timeout_rev = timeout_rev;
-    mode.want_sel = out_mode != KB_OUT_COUNT;
     uint64_t kbytes = 0;
     {
         std::vector<uint32_t> &ko = host_koff16(ctx);

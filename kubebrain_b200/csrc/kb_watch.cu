@@ -258,27 +258,6 @@ k_watcher_scan(uint32_t n, const uint64_t *__restrict__ wcnt, uint64_t *__restri
     }
 }
 
-// lists layout: [0]=n_medium [1]=n_large [2..2+G) medium groups [2+G..2+2G) large groups
-__global__ void __launch_bounds__(256)
-k_classify(uint32_t n_groups, const uint32_t *__restrict__ gcnt, uint32_t big_t, uint32_t max_large,
-           uint32_t *__restrict__ gclass, uint32_t *__restrict__ lists)
-{
-    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= n_groups) return;
-    const uint32_t n = gcnt[g];
-    uint32_t cls = KB_NONE;  // NONE: small or medium (segment scatter); otherwise the bitmap slot
-    if (n > big_t) {
-        const uint32_t slot = atomicAdd(&lists[1], 1u);
-        if (slot < max_large) {  // cannot overflow: sum(gcnt) <= E * n_lens
-            cls = slot;
-            lists[2 + n_groups + slot] = g;
-        }
-    } else if (n > 32) {
-        lists[2 + atomicAdd(&lists[0], 1u)] = g;
-    }
-    gclass[g] = cls;
-}
-
 __global__ void __launch_bounds__(256)
 k_scatter(uint32_t n_events, uint32_t n_lens, const uint32_t *__restrict__ ematch,
           const uint32_t *__restrict__ gclass, const uint32_t *__restrict__ gbase, uint32_t *__restrict__ gfill,
