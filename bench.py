@@ -309,12 +309,22 @@ def run_b200(args, rank: int, local_rank: int, world: int):
             raise b
         return a, b
 
+    pyt = {"cursor": 0.0, "range_call": 0.0, "range_result": 0.0, "n": 0}
+
     def scan_device():
+        t0 = time.perf_counter()
         _, readable = eng.cursor_allgather(local_rev)
+        t1 = time.perf_counter()
         r = eng.range_batch(reqs, KB_OUT_DEVICE)
+        t2 = time.perf_counter()
         ex = int(r.req_examined.sum())
         nk = r.n_kvs
         r.close()
+        t3 = time.perf_counter()
+        pyt["cursor"] += t1 - t0
+        pyt["range_call"] += t2 - t1
+        pyt["range_result"] += t3 - t2
+        pyt["n"] += 1
         return ex, nk
 
     def scan_e2e():
@@ -437,6 +447,7 @@ def run_b200(args, rank: int, local_rank: int, world: int):
             "scan_records_per_step": int(examined), "emitted_kvs_per_step": int(n_kvs),
             "fanout_events_per_step": int(wl["events"].n), "deliveries_per_step": int(deliveries),
             "wall_ms_per_step": wall_s * 1e3 / args.steps, "gen_s": wl["gen_s"],
+            "host_call_us": {k: 1e6 * v / max(pyt["n"], 1) for k, v in pyt.items() if k != "n"},
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(wl)

@@ -103,6 +103,30 @@ typedef struct kb_range_view {
 int kb_range_batch(kb_ctx *ctx, const kb_range_req *reqs, uint64_t n_req, int out_mode, kb_result **out);
 int kb_range_view_get(const kb_result *res, kb_range_view *view);
 
+/* ---- point reads: replaces backend.get / getInternalVal (pkg/backend/range.go:81-121): a reverse iterator from
+ * EncodeObjectKey(key, revision) down to EncodeObjectKey(key, 0) with limit 1.  revision 0 means "latest". */
+enum { KB_GET_FOUND = 0, KB_GET_NOT_FOUND = 1, KB_GET_TOMBSTONE = 2 /* ErrKeyNotFound, but mod_rev is valid */ };
+
+typedef struct kb_get_req {
+    const uint8_t *key;  uint64_t key_len;   /* USER key */
+    uint64_t revision;
+} kb_get_req;
+
+typedef struct kb_get_view {
+    uint64_t n;
+    const uint8_t  *status;    /* KB_GET_* per request (host)                                     */
+    const uint64_t *mod_rev;   /* revision the returned value was written at (host)               */
+    const uint32_t *rec_idx;   /* store record (host; undefined unless found / tombstone)         */
+    const uint64_t *val_off;   /* offset of the value inside bytes (host; found only)             */
+    const uint32_t *val_len;
+    const uint8_t  *bytes;     /* values (host pinned for KB_OUT_HOST, device for KB_OUT_DEVICE)  */
+    uint64_t n_bytes;
+    int on_device;
+} kb_get_view;
+
+int kb_get_batch(kb_ctx *ctx, const kb_get_req *reqs, uint64_t n, int out_mode, kb_result **out);
+int kb_get_view_get(const kb_result *res, kb_get_view *view);
+
 /* ---- compaction sweep: replaces scanner.Compact -> worker.run(compact=true) --------------------
  * (scanner.go:195-199, 457-491, 538-591; driver pkg/backend/compact.go:31-127).
  * Classifies every record of [start,end) visible at `rev`; the deletes themselves are applied by the

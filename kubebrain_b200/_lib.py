@@ -30,7 +30,7 @@ u64p = C.POINTER(C.c_uint64)
 ABI_SYMBOLS = [
     "kb_abi_version", "kb_open", "kb_close", "kb_last_error", "kb_stream", "kb_sync",
     "kb_load_sorted", "kb_store_info", "kb_set_compact_revision",
-    "kb_range_batch", "kb_range_view_get",
+    "kb_range_batch", "kb_range_view_get", "kb_get_batch", "kb_get_view_get",
     "kb_compact_sweep", "kb_compact_view_get",
     "kb_watch_add", "kb_watch_del", "kb_watch_count", "kb_watch_match", "kb_events_upload", "kb_events_free",
     "kb_watch_match_dev", "kb_match_view_get", "kb_result_free",
@@ -55,6 +55,15 @@ class KbRangeView(C.Structure):
                 ("n_kvs", C.c_uint64), ("rec_idx", u32p), ("rev", u64p), ("key_off", u64p), ("key_len", u32p),
                 ("val_off", u64p), ("val_len", u32p), ("bytes", C.c_void_p), ("n_bytes", C.c_uint64),
                 ("on_device", C.c_int)]
+
+
+class KbGetReq(C.Structure):
+    _fields_ = [("key", C.c_char_p), ("key_len", C.c_uint64), ("revision", C.c_uint64)]
+
+
+class KbGetView(C.Structure):
+    _fields_ = [("n", C.c_uint64), ("status", u8p), ("mod_rev", u64p), ("rec_idx", u32p), ("val_off", u64p),
+                ("val_len", u32p), ("bytes", C.c_void_p), ("n_bytes", C.c_uint64), ("on_device", C.c_int)]
 
 
 class KbCompactView(C.Structure):
@@ -112,6 +121,10 @@ def lib():
     L.kb_range_batch.argtypes = [vp, C.POINTER(KbRangeReq), C.c_uint64, C.c_int, C.POINTER(vp)]
     L.kb_range_view_get.restype = C.c_int
     L.kb_range_view_get.argtypes = [vp, C.POINTER(KbRangeView)]
+    L.kb_get_batch.restype = C.c_int
+    L.kb_get_batch.argtypes = [vp, C.POINTER(KbGetReq), C.c_uint64, C.c_int, C.POINTER(vp)]
+    L.kb_get_view_get.restype = C.c_int
+    L.kb_get_view_get.argtypes = [vp, C.POINTER(KbGetView)]
     L.kb_compact_sweep.restype = C.c_int
     L.kb_compact_sweep.argtypes = [vp, C.c_char_p, C.c_uint64, C.c_char_p, C.c_uint64, C.c_uint64, C.c_uint64,
                                    C.c_int, C.c_int, C.POINTER(vp)]
@@ -208,6 +221,45 @@ class RangeResult:
 
     def rec_indices(self, q: int = 0) -> np.ndarray:
         return self.rec_idx[int(self.req_first[q]) : int(self.req_first[q + 1])].copy()
+
+    def close(self):
+        if self._h:
+            lib().kb_result_free(self._eng._ctx, self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+GET_FOUND, GET_NOT_FOUND, GET_TOMBSTONE = 0, 1, 2
+
+
+class GetResult:
+    """answers of one batch of point reads (backend.get, pkg/backend/range.go:81-121)"""
+
+    def __init__(self, eng: "Engine", handle):
+        self._eng, self._h = eng, handle
+        v = KbGetView()
+        eng._check(lib().kb_get_view_get(handle, C.byref(v)))
+        n = int(v.n)
+        self.n = n
+        self.status = _np(v.status, n, np.uint8).copy()
+        self.mod_rev = _np(v.mod_rev, n, np.uint64).copy()
+        self.rec_idx = _np(v.rec_idx, n, np.uint32).copy()
+        self.val_off = _np(v.val_off, n, np.uint64).copy()
+        self.val_len = _np(v.val_len, n, np.uint32).copy()
+        self.n_bytes = int(v.n_bytes)
+        self.on_device = bool(v.on_device)
+        self.arena = None if self.on_device else (_np(v.bytes, self.n_bytes, np.uint8) if v.bytes else np.zeros(0, np.uint8))
+
+    def value(self, i: int) -> Optional[bytes]:
+        if self.status[i] != GET_FOUND:
+            return None
+        o, l = int(self.val_off[i]), int(self.val_len[i])
+        return self.arena[o : o + l].tobytes()
 
     def close(self):
         if self._h:
@@ -325,6 +377,15 @@ class Engine:
         h = C.c_void_p()
         self._check(lib().kb_range_batch(self._ctx, arr, len(reqs), out_mode, C.byref(h)))
         return RangeResult(self, h)
+
+    def get_batch(self, reqs: Sequence[Tuple[bytes, int]], out_mode: int = KB_OUT_HOST) -> GetResult:
+        """reqs: (user_key, revision) -- revision 0 means latest"""
+        arr = (KbGetReq * max(len(reqs), 1))()
+        for i, (k, rev) in enumerate(reqs):
+            arr[i] = KbGetReq(k, len(k), rev)
+        h = C.c_void_p()
+        self._check(lib().kb_get_batch(self._ctx, arr, len(reqs), out_mode, C.byref(h)))
+        return GetResult(self, h)
 
     def compact_sweep(self, start: bytes, end: bytes, rev: int, timeout_rev: int = 0, support_ttl: bool = True,
                       out_mode: int = KB_OUT_HOST) -> CompactResult:

@@ -117,6 +117,21 @@ class Backend:
         self._revision = rev
 
     # ---- read path ----
+    def get(self, key: bytes, revision: int = 0):
+        """range.go:34-81 Backend.Get: returns (header revision, KeyValue | None).  A missing key, a key created after
+        `revision` and a deleted key (tombstone) all answer with a nil kv."""
+        cur = self.get_current_revision()
+        res = self.engine.get_batch([(key, revision)])
+        try:
+            st, mod = int(res.status[0]), int(res.mod_rev[0])
+            if st != 0:  # storage.ErrKeyNotFound (range.go:49-53)
+                return cur, None
+            if mod > cur:
+                cur = mod
+            return cur, KeyValue(key, res.value(0), mod)
+        finally:
+            res.close()
+
     def list(self, key: bytes, end: bytes, revision: int = 0, limit: int = 0) -> RangeResponse:
         """range.go:124-174"""
         if len(end) == 0:

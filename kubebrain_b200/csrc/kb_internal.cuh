@@ -207,6 +207,9 @@ struct kb_result {
     uint64_t n_victims = 0, count = 0, examined = 0;
     HBuf h_vic;
     DBuf d_vic;
+    // get
+    uint64_t n_gets = 0;
+    HBuf h_get;  // [status u8 n (padded)][mod_rev u64 n][val_off u64 n][rec u32 n][val_len u32 n]
     // match
     uint64_t n_watchers = 0, n_deliveries = 0;
     HBuf h_match;

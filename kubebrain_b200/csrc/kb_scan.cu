@@ -672,6 +672,61 @@ k_gather(StoreDev st, const GatherJob *__restrict__ jobs, const uint64_t *__rest
     }
 }
 
+// ---- k_get_resolve: one warp per point read.  cand = (first record > EncodeObjectKey(key, revision)) - 1 is what the
+// reference's reverse iterator yields first (range.go:97-107); it answers the read iff it decodes to the same user
+// key with a non-zero revision (range.go:109-117); a tombstone value maps to ErrKeyNotFound (range.go:82-86).
+struct GetOut {
+    uint8_t *status;
+    uint64_t *mod_rev;
+    uint32_t *rec;
+    uint32_t *vlen;
+};
+
+__global__ void __launch_bounds__(128)
+k_get_resolve(StoreDev st, const uint4 *__restrict__ bounds, const uint32_t *__restrict__ boff16,
+              const uint32_t *__restrict__ blen, const uint32_t *__restrict__ ub, uint32_t n, GetOut out)
+{
+    const uint32_t g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (g >= n) return;
+    const uint32_t idx = ub[g];
+    uint32_t status = KB_GET_NOT_FOUND, rec = 0, vl = 0;
+    uint64_t mrev = 0;
+    if (idx > 0) {
+        rec = idx - 1;
+        const uint32_t bl = blen[g];           // magic + key + '$' + rev(8) + one 0x00 byte
+        const uint32_t pre = bl - 9;           // magic + key + '$'
+        const uint32_t kl = st.klen[rec];
+        if (kl == pre + 8) {
+            const uint4 *a = st.kslab + st.koff16[rec];
+            const uint4 *b = bounds + boff16[g];
+            bool eq = true;
+            for (uint32_t c = lane; c * 16 < pre; c += 32) {
+                uint4 x = a[c], y = b[c];
+                int p = first_diff16(x, y);
+                if (p < 16 && c * 16 + p < pre) eq = false;
+            }
+            eq = __all_sync(0xffffffffu, eq);
+            if (eq) {
+                mrev = be64_bytes((const uint8_t *)a + kl - 8);
+                if (mrev != 0) {
+                    vl = st.vlen[rec];
+                    status = KB_GET_FOUND;
+                    if (vl == 9) {
+                        const uint4 v0 = st.vslab[st.voff16[rec]];
+                        if (v0.x == 0x626d6f74u && v0.y == 0x6e6f7473u && (v0.z & 0xffu) == 0x65u) status = KB_GET_TOMBSTONE;
+                    }
+                }
+            }
+        }
+    }
+    if (lane == 0) {
+        out.status[g] = (uint8_t)status;
+        out.mod_rev[g] = status == KB_GET_NOT_FOUND ? 0 : mrev;
+        out.rec[g] = rec;
+        out.vlen[g] = vl;
+    }
+}
+
 // single CTA: per-request emitted count / response bytes (limit applied) and their exclusive prefixes over the
 // requests: job_first[q] = first kv of request q, arena_base[q] = first arena byte of request q; [nreq] = totals
 __global__ void __launch_bounds__(256)
@@ -736,6 +791,7 @@ extern "C" void kb_result_free(kb_ctx *ctx, kb_result *res)
         pool_put_dev(ctx, res->d_vic);
         pool_put_host(ctx, res->h_match);
         pool_put_dev(ctx, res->d_match);
+        pool_put_host(ctx, res->h_get);
     }
     delete res;
 }
@@ -1180,6 +1236,168 @@ extern "C" int kb_range_view_get(const kb_result *res, kb_range_view *v)
     v->n_bytes = res->n_bytes;
     v->on_device = res->out_mode == KB_OUT_DEVICE;
     v->bytes = res->out_mode == KB_OUT_DEVICE ? (const uint8_t *)res->d_bytes.p : (const uint8_t *)res->h_bytes.p;
+    return KB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// point reads
+// ------------------------------------------------------------------------------------------------
+extern "C" int kb_get_batch(kb_ctx *ctx, const kb_get_req *reqs, uint64_t n, int out_mode, kb_result **out)
+{
+    if (!ctx || !out || (n && !reqs)) return KB_EINVAL;
+    if (out_mode != KB_OUT_HOST && out_mode != KB_OUT_DEVICE) return KB_EINVAL;
+    *out = nullptr;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    if (!ctx->loaded) return kb_fail(ctx, KB_ESTATE, "no store loaded");
+    cudaSetDevice(ctx->device);
+    if (n >= 0x7FFFFFFFull) return kb_fail(ctx, KB_ELIMIT, "too many point reads in one batch");
+    // bound of read i = EncodeObjectKey(key, revision or MaxUint64) + 0x00: its lower_bound is the first record
+    // strictly greater than the start key of the reference's reverse iterator
+    uint64_t chunks = 0;
+    for (uint64_t i = 0; i < n; i++) {
+        if (!reqs[i].key && reqs[i].key_len) return KB_EINVAL;
+        if (reqs[i].key_len > 65000) return kb_fail(ctx, KB_ELIMIT, "key too long");
+        chunks += (reqs[i].key_len + 14 + 15) / 16 + 3;
+    }
+    KB_TRY(hbuf_ensure(ctx, ctx->h_stage, chunks * 16 + n * 8 + n * 32 + 256));
+    uint8_t *hs = (uint8_t *)ctx->h_stage.p;
+    memset(hs, 0, chunks * 16);
+    uint32_t *hboff = (uint32_t *)(hs + chunks * 16), *hblen = hboff + n;
+    uint64_t c = 0;
+    for (uint64_t i = 0; i < n; i++) {
+        uint8_t *b = hs + c * 16;
+        const uint64_t ul = reqs[i].key_len;
+        const uint64_t rev = reqs[i].revision ? reqs[i].revision : ~0ull;
+        b[0] = 0x57; b[1] = 0xfb; b[2] = 0x80; b[3] = 0x8b;
+        if (ul) memcpy(b + 4, reqs[i].key, ul);
+        b[4 + ul] = 0x24;
+        for (int k = 0; k < 8; k++) b[5 + ul + k] = (uint8_t)(rev >> (8 * (7 - k)));
+        b[13 + ul] = 0;
+        hboff[i] = (uint32_t)c;
+        hblen[i] = (uint32_t)(ul + 14);
+        c += (ul + 14 + 15) / 16 + 3;
+    }
+    KB_TRY(dbuf_ensure(ctx, ctx->d_bounds, chunks * 16 + n * 8 + 64));
+    KB_TRY(dbuf_ensure(ctx, ctx->d_bres, std::max<uint64_t>(n, 1) * 4));
+    // per-read outputs on the device: [mod_rev u64][rec u32][vlen u32][status u8]
+    KB_TRY(dbuf_ensure(ctx, ctx->d_reqout, std::max<uint64_t>(n, 1) * 17 + 64));
+    KB_CUDA(ctx, cudaMemcpyAsync(ctx->d_bounds.p, hs, chunks * 16 + n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    const uint32_t *d_boff = (const uint32_t *)((const uint8_t *)ctx->d_bounds.p + chunks * 16);
+    GetOut go;
+    go.mod_rev = (uint64_t *)ctx->d_reqout.p;
+    go.rec = (uint32_t *)(go.mod_rev + n);
+    go.vlen = go.rec + n;
+    go.status = (uint8_t *)(go.vlen + n);
+    if (n) {
+        KB_LAUNCH(ctx, "k_search", n * 64,
+                  (k_search<<<(unsigned)((n * 32 + 127) / 128), 128, 0, ctx->stream>>>(
+                      ctx->st, (const uint4 *)ctx->d_bounds.p, d_boff, d_boff + n, (uint32_t)n, (uint32_t *)ctx->d_bres.p)));
+        KB_LAUNCH(ctx, "k_get_resolve", n * 320,
+                  (k_get_resolve<<<(unsigned)((n * 32 + 127) / 128), 128, 0, ctx->stream>>>(
+                      ctx->st, (const uint4 *)ctx->d_bounds.p, d_boff, d_boff + n, (const uint32_t *)ctx->d_bres.p,
+                      (uint32_t)n, go)));
+    }
+    // host copy of the per-read outputs (same layout), behind the staging area used above
+    kb_result *res = kb_result_new(4, out_mode);
+    res->n_gets = n;
+    const size_t st_off = (n + 7) & ~(size_t)7;  // h_get: [status (padded to 8)][mod_rev][val_off][rec][val_len]
+    int rc = pool_get_host(ctx, st_off + n * 24 + 64, &res->h_get);
+    if (rc != KB_OK) {
+        kb_result_free(nullptr, res);
+        return rc;
+    }
+    uint8_t *hg = (uint8_t *)res->h_get.p;
+    uint8_t *h_status = hg;
+    uint64_t *h_mrev = (uint64_t *)(hg + st_off), *h_voff = h_mrev + n;
+    uint32_t *h_rec = (uint32_t *)(h_voff + n), *h_vlen = h_rec + n;
+    if (n) {
+        cudaMemcpyAsync(h_mrev, go.mod_rev, n * 8, cudaMemcpyDeviceToHost, ctx->stream);
+        cudaMemcpyAsync(h_rec, go.rec, n * 4, cudaMemcpyDeviceToHost, ctx->stream);
+        cudaMemcpyAsync(h_vlen, go.vlen, n * 4, cudaMemcpyDeviceToHost, ctx->stream);
+        cudaMemcpyAsync(h_status, go.status, n, cudaMemcpyDeviceToHost, ctx->stream);
+    }
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+        kb_result_free(nullptr, res);
+        return kb_cuda_fail(ctx, e, "get resolve");
+    }
+    // copy jobs for the found values (host side: offsets come from the host copies of the directory)
+    std::vector<GatherJob> jobs;
+    uint64_t nbytes = 0;
+    for (uint64_t i = 0; i < n; i++) {
+        h_voff[i] = 0;
+        if (h_status[i] != KB_GET_FOUND) {
+            if (h_status[i] == KB_GET_NOT_FOUND) h_vlen[i] = 0;
+            continue;
+        }
+        GatherJob j;
+        j.dst16 = nbytes / 16;
+        j.vsrc16 = ctx->h_voff16[h_rec[i]];
+        j.ksrc16 = 0;
+        j.nk = 0;
+        j.nv = (h_vlen[i] + 15) / 16;
+        j.kl = 0;
+        h_voff[i] = nbytes;
+        nbytes += (uint64_t)j.nv * 16;
+        if (j.nv) jobs.push_back(j);
+    }
+    res->n_bytes = nbytes;
+    if (!jobs.empty()) {
+        const uint64_t nj = jobs.size();
+        rc = dbuf_ensure(ctx, ctx->d_gjobs, nj * sizeof(GatherJob));
+        if (rc == KB_OK) rc = dbuf_ensure(ctx, ctx->d_jobs, 64);
+        if (rc == KB_OK) rc = pool_get_dev(ctx, nbytes + 64, &res->d_bytes);
+        if (rc == KB_OK) rc = hbuf_ensure(ctx, ctx->h_stage2, nj * sizeof(GatherJob) + 64);
+        if (rc != KB_OK) {
+            kb_result_free(nullptr, res);
+            return rc;
+        }
+        uint8_t *hj = (uint8_t *)ctx->h_stage2.p;
+        memcpy(hj, &nj, 8);
+        memcpy(hj + 64, jobs.data(), nj * sizeof(GatherJob));
+        cudaMemcpyAsync(ctx->d_jobs.p, hj, 8, cudaMemcpyHostToDevice, ctx->stream);
+        cudaMemcpyAsync(ctx->d_gjobs.p, hj + 64, nj * sizeof(GatherJob), cudaMemcpyHostToDevice, ctx->stream);
+        const size_t gsmem = (size_t)GATHER_WARPS * GATHER_STAGES * GATHER_PIECE * 16;
+        cudaFuncSetAttribute(k_gather, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem);
+        const unsigned ggrid = (unsigned)std::min<uint64_t>((nj + GATHER_WARPS * 32 - 1) / (GATHER_WARPS * 32), 148);
+        KB_LAUNCH(ctx, "k_gather", 2 * nbytes,
+                  (k_gather<<<std::max(ggrid, 1u), GATHER_WARPS * 32, gsmem, ctx->stream>>>(
+                      ctx->st, (const GatherJob *)ctx->d_gjobs.p, (const uint64_t *)ctx->d_jobs.p, (uint4 *)res->d_bytes.p)));
+        if (out_mode == KB_OUT_HOST) {
+            rc = pool_get_host(ctx, nbytes + 16, &res->h_bytes);
+            if (rc == KB_OK) cudaMemcpyAsync(res->h_bytes.p, res->d_bytes.p, nbytes, cudaMemcpyDeviceToHost, ctx->stream);
+        }
+        e = cudaStreamSynchronize(ctx->stream);
+        if (rc == KB_OK && e != cudaSuccess) rc = kb_cuda_fail(ctx, e, "get gather");
+        if (rc != KB_OK) {
+            kb_result_free(nullptr, res);
+            return rc;
+        }
+        if (out_mode == KB_OUT_HOST) {
+            pool_put_dev(ctx, res->d_bytes);
+            res->d_bytes = DBuf();
+        }
+    }
+    *out = res;
+    return KB_OK;
+}
+
+extern "C" int kb_get_view_get(const kb_result *res, kb_get_view *v)
+{
+    if (!res || !v || res->type != 4) return KB_EINVAL;
+    memset(v, 0, sizeof(*v));
+    const uint64_t n = res->n_gets;
+    const size_t st_off = (n + 7) & ~(size_t)7;
+    const uint8_t *hg = (const uint8_t *)res->h_get.p;
+    v->n = n;
+    v->status = hg;
+    v->mod_rev = (const uint64_t *)(hg + st_off);
+    v->val_off = v->mod_rev + n;
+    v->rec_idx = (const uint32_t *)(v->val_off + n);
+    v->val_len = v->rec_idx + n;
+    v->n_bytes = res->n_bytes;
+    v->on_device = res->out_mode == KB_OUT_DEVICE;
+    v->bytes = v->on_device ? (const uint8_t *)res->d_bytes.p : (const uint8_t *)res->h_bytes.p;
     return KB_OK;
 }
 

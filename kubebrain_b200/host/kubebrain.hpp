@@ -196,6 +196,7 @@ class Scanner {  // scanner.Scanner
    public:
     static constexpr int kRangeStreamBatch = 300;  // scanner.go:43
     explicit Scanner(Engine &e) : e_(e) {}
+    Engine &engine() { return e_; }
 
     std::vector<KeyValue> Range(const Bytes &start, const Bytes &end, uint64_t revision, int64_t limit)
     {  // scanner.go:83-119
@@ -282,6 +283,26 @@ class Backend {  // the read half of backend.Backend
     }
     uint64_t GetCurrentRevision() const { return rev_; }
     void SetCurrentRevision(uint64_t r) { rev_ = r; }
+
+    // range.go:34-81 Backend.Get: *found=false for a missing key, a key created after `revision`, or a deleted key
+    uint64_t Get(const Bytes &key, uint64_t revision, KeyValue *kv, bool *found)
+    {
+        kb_get_req rq{(const uint8_t *)key.data(), key.size(), revision};
+        kb_result *res = nullptr;
+        scanner_.engine().Check(kb_get_batch(scanner_.engine().ctx(), &rq, 1, KB_OUT_HOST, &res));
+        kb_get_view v;
+        kb_get_view_get(res, &v);
+        uint64_t cur = rev_;
+        *found = v.status[0] == KB_GET_FOUND;
+        if (*found) {
+            kv->Key = key;
+            kv->Value.assign((const char *)v.bytes + v.val_off[0], v.val_len[0]);
+            kv->Revision = v.mod_rev[0];
+            if (v.mod_rev[0] > cur) cur = v.mod_rev[0];
+        }
+        kb_result_free(scanner_.engine().ctx(), res);
+        return cur;
+    }
 
     RangeResponse List(const Bytes &key, const Bytes &end, uint64_t revision = 0, int64_t limit = 0)
     {  // range.go:124-174

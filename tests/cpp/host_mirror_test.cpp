@@ -117,6 +117,15 @@ static void gpu_tests()
     CHECK(r.Kvs == sub(1, inject - 4) && r.More);
     r = be.List(testKey, kb::PrefixEnd(testKey), 0, inject - 5);
     CHECK(r.Kvs == sub(0, inject - 5) && r.More);
+    // get cases (backend_test.go:800-823)
+    kb::KeyValue gkv;
+    bool found = false;
+    CHECK(be.Get(fmt(testKey, inject - 1), 0, &gkv, &found) == init && found && gkv == kvList[inject - 1]);
+    CHECK(be.Get(fmt(testKey, inject - 2), init, &gkv, &found) == init && found && gkv.Revision == init - 1);
+    be.Get(fmt(testKey, inject - 1), 1700000000ull, &gkv, &found);
+    CHECK(!found);
+    be.Get(testKey + "/-0001", 0, &gkv, &found);
+    CHECK(!found);
     CHECK(be.Count(testKey, endKey) == (uint64_t)inject);
     CHECK(be.Count(endKey, kb::PrefixEnd(endKey)) == 0);
     std::vector<kb::KeyValue> got;

@@ -100,6 +100,58 @@ def test_backend_range_table(eng):
     eng.set_compact_revision(None)
 
 
+def check_gets(eng, store, st, reqs):
+    res = eng.get_batch(reqs)
+    for i, (k, rev) in enumerate(reqs):
+        idx, mod = ko.get(st, k, rev)
+        if idx >= 0:
+            assert int(res.status[i]) == 0 and int(res.rec_idx[i]) == idx and int(res.mod_rev[i]) == mod, (i, k, rev)
+            assert res.value(i) == store.vals[idx], (i, k, rev)
+        elif idx == -2:
+            assert int(res.status[i]) == 2 and int(res.mod_rev[i]) == mod, (i, k, rev)
+        else:
+            assert int(res.status[i]) == 1 and int(res.mod_rev[i]) == 0, (i, k, rev)
+    res.close()
+
+
+def test_get_table_and_fuzz(eng):
+    """pkg/backend/backend_test.go:800-823 get cases + point reads on adversarial stores"""
+    mb = MiniBackend(1000)
+    revs = {}
+    for i in range(10):
+        revs[i], _ = mb.create(b"/registry/test/key/%05d" % i, b"val/%05d" % i)
+    mb.update(b"/registry/test/key/00003", b"new", revs[3])
+    mb.delete(b"/registry/test/key/00004")
+    store = mb.snapshot()
+    st = ko.OracleStore(store)
+    eng.load_sorted(store)
+    b = Backend(eng, prefix="/registry/test")
+    b.set_current_revision(mb.rev)
+    assert b.get(b"/registry/test/key/00009") == (mb.rev, KeyValue(b"/registry/test/key/00009", b"val/00009", revs[9]))
+    assert b.get(b"/registry/test/key/00008", mb.rev) == (mb.rev, KeyValue(b"/registry/test/key/00008", b"val/00008", revs[8]))
+    assert b.get(b"/registry/test/key/00009", 1000) == (mb.rev, None)  # revision before it was created
+    assert b.get(b"/registry/test/key/-0001") == (mb.rev, None)  # nonexistent
+    assert b.get(b"/registry/test/key/00003")[1].value == b"new"
+    assert b.get(b"/registry/test/key/00003", revs[3])[1].value == b"val/00003"  # time travel
+    assert b.get(b"/registry/test/key/00004") == (mb.rev, None)  # deleted
+    assert b.get(b"/registry/test/key/00004", revs[4])[1].value == b"val/00004"
+    reqs = [(b"/registry/test/key/%05d" % i, r) for i in range(-1, 11) for r in (0, 1000, 1003, 1005, 1011, 1012, 2**64 - 1)]
+    check_gets(eng, store, st, reqs)
+    for seed in range(6):
+        fstore = fuzz.fuzz_store(300 + seed, n_keys=60)
+        fst = ko.OracleStore(fstore)
+        eng.load_sorted(fstore)
+        uks = set()
+        for k in fstore.keys.tolist():
+            uk, rev, err = ko.decode(k)
+            if err == 0:
+                uks.add(uk)
+                uks.add(uk + b"$")
+                uks.add(uk[:-1])
+        greqs = [(uk, r) for uk in sorted(uks) for r in (0, 1, 17, 40, 59, 2**64 - 1)]
+        check_gets(eng, fstore, fst, greqs)
+
+
 def test_scan_quirks(eng):
     mb = MiniBackend(100)
     r1, _ = mb.create(b"/r/a", b"a1")
