@@ -76,7 +76,9 @@ enum {
 
 typedef struct kb_range_req {
     const uint8_t *start;  uint64_t start_len;   /* internal keys: coder.EncodeObjectKey(key, 0)  */
-    const uint8_t *end;    uint64_t end_len;     /* half-open [start, end)                        */
+    const uint8_t *end;    uint64_t end_len;     /* half-open [start, end); start >= end answers
+                                                     nothing (backend.List refuses such ranges before
+                                                     the scanner is reached, range.go:147-149)     */
     uint64_t read_rev;                            /* workerConfig.revision                         */
     int64_t  limit;                               /* scanner.Range limit; <= 0 means unlimited     */
 } kb_range_req;

@@ -175,6 +175,7 @@ struct kb_ctx {
 
     // watchers
     std::vector<Watcher> watchers;
+    std::vector<uint32_t> free_watch_ids;
     bool watch_dirty = true;
     WatchTablesDev *wt = nullptr;
     struct kb_events_dev *ev_scratch = nullptr;  // grow-only upload slab of kb_watch_match
@@ -190,6 +191,7 @@ struct kb_ctx {
     std::vector<ProfPending> prof_pending;
     std::vector<cudaEvent_t> ev_pool;
     uint64_t launches = 0;
+    bool decode_attr_set = false, gather_attr_set = false;  // per-context (per-device) kernel attributes
 };
 
 struct kb_result {

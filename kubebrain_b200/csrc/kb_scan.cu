@@ -927,10 +927,9 @@ static int launch_decode(kb_ctx *ctx, uint32_t ntiles, uint64_t alg_bytes, const
                          const TileDev *d_tiles, uint32_t *d_meta, uint2 *d_agg)
 {
     const size_t smem = ((size_t)DECODE_WARPS * DECODE_STAGES * KB_WARP_STAGE_CHUNKS + 4) * 16;
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (!ctx->decode_attr_set) {
         KB_CUDA(ctx, cudaFuncSetAttribute(k_decode_lcp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
+        ctx->decode_attr_set = true;
     }
     const uint32_t n_sub = ntiles * 32;
     const uint32_t grid = std::min<uint32_t>((n_sub + DECODE_WARPS - 1) / DECODE_WARPS, 148);
@@ -1111,10 +1110,9 @@ extern "C" int kb_range_batch(kb_ctx *ctx, const kb_range_req *reqs, uint64_t nr
                                                                 (const uint32_t *)ctx->d_sel.p,
                                                                 (const uint64_t *)ctx->d_slot.p, d_gj, go)));
         const size_t gsmem = (size_t)GATHER_WARPS * GATHER_STAGES * GATHER_PIECE * 16;
-        static bool gattr = false;
-        if (!gattr) {
+        if (!ctx->gather_attr_set) {
             cudaFuncSetAttribute(k_gather, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem);
-            gattr = true;
+            ctx->gather_attr_set = true;
         }
         const unsigned ggrid = (unsigned)std::min<uint64_t>((cap_kvs + GATHER_WARPS - 1) / GATHER_WARPS, 148);
         KB_LAUNCH(ctx, "k_gather", 0,

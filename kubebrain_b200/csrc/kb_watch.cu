@@ -731,8 +731,14 @@ extern "C" int kb_watch_add(kb_ctx *ctx, const uint8_t *prefix, uint64_t prefix_
     w.prefix.assign((const char *)prefix, (size_t)prefix_len);
     w.min_rev = min_rev;
     w.live = true;
-    ctx->watchers.push_back(w);
-    *id = (uint32_t)ctx->watchers.size() - 1;
+    if (!ctx->free_watch_ids.empty()) {  // ids of cancelled watches are reused so the id space stays dense
+        *id = ctx->free_watch_ids.back();
+        ctx->free_watch_ids.pop_back();
+        ctx->watchers[*id] = w;
+    } else {
+        ctx->watchers.push_back(w);
+        *id = (uint32_t)ctx->watchers.size() - 1;
+    }
     ctx->watch_dirty = true;
     return KB_OK;
 }
@@ -743,6 +749,7 @@ extern "C" int kb_watch_del(kb_ctx *ctx, uint32_t id)
     std::lock_guard<std::mutex> g(ctx->mu);
     if (id >= ctx->watchers.size() || !ctx->watchers[id].live) return kb_fail(ctx, KB_EINVAL, "unknown watcher %u", id);
     ctx->watchers[id].live = false;
+    ctx->free_watch_ids.push_back(id);
     ctx->watch_dirty = true;
     return KB_OK;
 }
