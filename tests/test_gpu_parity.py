@@ -4,6 +4,7 @@ classes, per-watcher ordered delivery lists.  Run on the B200 box: `pytest -m gp
 from __future__ import annotations
 
 import hashlib
+import os
 import struct
 
 import numpy as np
@@ -376,6 +377,47 @@ def test_config4_shape_10m(eng):
     res = eng.range_batch([(lo, hi, meta.read_rev, 0)], KB_OUT_HOST)
     assert np.array_equal(res.rec_idx.astype(np.uint64), r.emit)
     res.close()
+
+
+@pytest.mark.skipif(os.environ.get("KB_FULL_SIZE") != "1", reason="set KB_FULL_SIZE=1 (needs ~40 GB of host RAM, minutes)")
+def test_config4_full_size_100m():
+    """BASELINE config 4 at FULL size: 10M objects x (1 revision record + 9 versions) = 100M records.  Too large for
+    a direct list comparison in reasonable time, so: counts against the oracle + size-independent properties."""
+    store, meta = synth.gen_store(10_000_000, 9, 64, 64, 50000, config_id=4, tomb_frac=0.02)
+    e = Engine(0)
+    e.load_sorted(store)
+    lo, hi = CODER.encode_object_key(b"/registry/", 0), CODER.encode_object_key(b"/registry0", 0)
+    got = e.compact_sweep(lo, hi, meta.last_rev)
+    st = ko.OracleStore(store)
+    exp = ko.scan(st, [lo, hi], meta.last_rev, compact=True, collect=False)
+    assert got.n_victims == len(exp.victims) and got.count == exp.count and got.examined == store.n
+    assert np.array_equal(got.victim_idx.astype(np.uint64), exp.victims)
+    assert np.array_equal(got.victim_class, exp.vclass)
+    assert int((got.victim_class == 1).sum()) == 80_000_000  # keep-latest: 8 stale versions per object
+    keep = np.ones(store.n, dtype=bool)
+    keep[got.victim_idx] = False
+    assert (keep.reshape(-1, 10)[:, 1:].sum(axis=1) <= 1).all()
+    got.close()
+    e.close()
+
+
+def test_two_gpu_cursor_allgather():
+    """the one collective of the path on real NVLink: 2 ranks, ncclAllGather of the revision cursor + min"""
+    import subprocess
+    import sys
+
+    try:
+        import torch
+
+        if torch.cuda.device_count() < 2:
+            pytest.skip("needs 2 GPUs")
+    except ImportError:
+        pytest.skip("torch missing")
+    worker = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_nccl_worker.py")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29533", worker],
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
 
 
 # ---- watch fan-out ------------------------------------------------------------------------------------------

@@ -113,7 +113,8 @@ __device__ __forceinline__ void bulk_s2g(void *dst, const void *src, uint32_t by
 
 // per-warp bulk-TMA ring. COPY: also store every piece back to dst with a bulk store.
 template <int CH, int STAGES, bool COPY>
-__global__ void k_bulk(const uint4 *__restrict__ src, uint4 *__restrict__ dst, size_t n, uint32_t *out)
+__global__ void k_bulk(const uint4 *__restrict__ src, uint4 *__restrict__ dst, size_t n, uint32_t *out,
+                       size_t src_stride)
 {
     extern __shared__ __align__(128) uint4 sm[];
     __shared__ uint64_t bars[16 * STAGES];
@@ -124,7 +125,8 @@ __global__ void k_bulk(const uint4 *__restrict__ src, uint4 *__restrict__ dst, s
         for (int s = 0; s < STAGES; s++) mbar_init(bar + s, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncwarp();
-    const size_t pieces = n / CH;
+    const size_t sstep = src_stride ? src_stride : CH;  // source pieces every `sstep` chunks (gather shape)
+    const size_t pieces = src_stride ? n / src_stride : n / CH;
     const size_t stride = (size_t)gridDim.x * nw;
     size_t p = (size_t)blockIdx.x * nw + warp;
     uint32_t acc = 0;
@@ -135,7 +137,7 @@ __global__ void k_bulk(const uint4 *__restrict__ src, uint4 *__restrict__ dst, s
             if (COPY) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");  // buffer st was stored 2 its ago
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             mbar_expect_tx(bar + st, CH * 16);
-            bulk_g2s(buf + st * CH, src + piece * CH, CH * 16, bar + st);
+            bulk_g2s(buf + st * CH, src + piece * sstep, CH * 16, bar + st);
         }
     };
     for (int s = 0; s < D; s++) issue(p + s * stride, s);
@@ -219,7 +221,7 @@ int main()
         auto run = [&](auto kern, int warps, int stages, bool copy, const char *name) {
             size_t smem = (size_t)warps * stages * CH * 16;
             CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            float t = timeit([&] { kern<<<148, warps * 32, smem>>>(src, dst, n, out); });
+            float t = timeit([&] { kern<<<148, warps * 32, smem>>>(src, dst, n, out, (size_t)0); });
             printf("%-34s: %8.1f GB/s\n", name, (copy ? 2 : 1) * GB / (t / 1e3));
         };
         run(k_bulk<CH, 2, false>, 12, 2, false, "bulk TMA ring 12w x 2st x 9KB read");
@@ -231,13 +233,25 @@ int main()
         auto run = [&](auto kern, int warps, int stages, const char *name) {
             size_t smem = (size_t)warps * stages * CH * 16;
             CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            float t = timeit([&] { kern<<<148, warps * 32, smem>>>(src, dst, n, out); });
+            float t = timeit([&] { kern<<<148, warps * 32, smem>>>(src, dst, n, out, (size_t)0); });
             printf("%-34s: %8.1f GB/s\n", name, 2 * GB / (t / 1e3));
-            t = timeit([&] { kern<<<148 * 2, warps * 32, smem>>>(src, dst, n, out); });
+            t = timeit([&] { kern<<<148 * 2, warps * 32, smem>>>(src, dst, n, out, (size_t)0); });
             printf("%-34s: %8.1f GB/s (2 CTA/SM)\n", name, 2 * GB / (t / 1e3));
         };
         run(k_bulk<CH, 4, true>, 8, 4, "bulk TMA copy  8w x 4st x 2.5KB");
         run(k_bulk<CH, 6, true>, 8, 6, "bulk TMA copy  8w x 6st x 2.5KB");
+    }
+    {
+        // the gather shape: 2.3 KB pieces read at a 10 KB stride (one winner out of five records), written contiguously
+        constexpr int CH = 145;
+        size_t smem = (size_t)8 * 8 * CH * 16;
+        auto kern = k_bulk<CH, 8, true>;
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const size_t sstride = 648;  // chunks between consecutive source pieces (10368 B)
+        const size_t pieces = n / sstride;
+        float t = timeit([&] { kern<<<148, 8 * 32, smem>>>(src, dst, n, out, sstride); });
+        printf("bulk TMA gather-shaped copy 2320B every 10368B: %8.1f GB/s (r+w of the bytes moved)\n",
+               2.0 * pieces * CH * 16 / 1e9 / (t / 1e3));
     }
     printf("done\n");
     return 0;
