@@ -95,7 +95,7 @@ class ClockSampler:
         try:
             self.f = open(self.path, "w")
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.FIELDS}",
-                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                       "--format=csv,noheader,nounits", "-lms", "20"], stdout=self.f,
                                       stderr=subprocess.DEVNULL)
         except OSError:
             self.p = None
@@ -368,13 +368,15 @@ def run_b200(args, rank: int, local_rank: int, world: int):
             dev_ms, wall = float(t[0]), float(t[1]) / 1e3
         return dev_ms, wall, out
 
+    # clocks / throttle reasons are sampled from the warm-up to the end of the e2e pass (the timed regions last
+    # only tens of milliseconds, so sampling them alone would give one or two points)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     for _ in range(max(args.warmup, 3)):
         step_device()
         step_e2e()
 
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     # timed region: CUDA events bracket only the two HBM-bound kernels (level 2) so the event records do not
     # perturb the step; a second, untimed pass with every kernel bracketed fills the per-kernel table
     engines = [eng] if weng is eng else [eng, weng]

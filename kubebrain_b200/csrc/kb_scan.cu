@@ -779,11 +779,11 @@ kb_result *kb_result_new(int type, int out_mode)
     return r;
 }
 
-extern "C" void kb_result_free(kb_ctx *ctx, kb_result *res)
+// return every pooled buffer of a result; the caller holds ctx->mu
+static void result_release_locked(kb_ctx *ctx, kb_result *res)
 {
     if (!res) return;
     if (ctx) {
-        std::lock_guard<std::mutex> g(ctx->mu);
         pool_put_host(ctx, res->h_meta);
         pool_put_host(ctx, res->h_bytes);
         pool_put_dev(ctx, res->d_bytes);
@@ -794,6 +794,19 @@ extern "C" void kb_result_free(kb_ctx *ctx, kb_result *res)
         pool_put_host(ctx, res->h_get);
     }
     delete res;
+}
+
+void kb_result_release_locked(kb_ctx *ctx, kb_result *res) { result_release_locked(ctx, res); }
+
+extern "C" void kb_result_free(kb_ctx *ctx, kb_result *res)
+{
+    if (!res) return;
+    if (ctx) {
+        std::lock_guard<std::mutex> g(ctx->mu);
+        result_release_locked(ctx, res);
+    } else {
+        delete res;
+    }
 }
 
 namespace {
@@ -1090,7 +1103,7 @@ extern "C" int kb_range_batch(kb_ctx *ctx, const kb_range_req *reqs, uint64_t nr
         if (rc == KB_OK) rc = dbuf_ensure(ctx, ctx->d_gjobs, std::max<uint64_t>(cap_kvs, 1) * sizeof(GatherJob));
         if (rc != KB_OK) {
             pool_put_dev(ctx, d_om);
-            kb_result_free(nullptr, res);
+            result_release_locked(ctx, res);
             return rc;
         }
         uint8_t *om = (uint8_t *)d_om.p;
@@ -1130,7 +1143,7 @@ extern "C" int kb_range_batch(kb_ctx *ctx, const kb_range_req *reqs, uint64_t nr
     kb_seg(ctx, "host:range_sync", tseg);
     if (e1 != cudaSuccess) {
         pool_put_dev(ctx, d_om);
-        kb_result_free(nullptr, res);
+        result_release_locked(ctx, res);
         return kb_cuda_fail(ctx, e1, "range scan");
     }
     if (nreq) memcpy(rout.data(), ctx->h_stage.p, nreq * sizeof(ReqOut));
@@ -1183,7 +1196,7 @@ extern "C" int kb_range_batch(kb_ctx *ctx, const kb_range_req *reqs, uint64_t nr
             if (rc == KB_OK && e != cudaSuccess) rc = kb_cuda_fail(ctx, e, "range D2H");
             if (rc != KB_OK) {
                 pool_put_dev(ctx, d_om);
-                kb_result_free(nullptr, res);
+                result_release_locked(ctx, res);
                 return rc;
             }
             uint8_t *hm = (uint8_t *)res->h_meta.p;
@@ -1301,7 +1314,7 @@ extern "C" int kb_get_batch(kb_ctx *ctx, const kb_get_req *reqs, uint64_t n, int
     const size_t st_off = (n + 7) & ~(size_t)7;  // h_get: [status (padded to 8)][mod_rev][val_off][rec][val_len]
     int rc = pool_get_host(ctx, st_off + n * 24 + 64, &res->h_get);
     if (rc != KB_OK) {
-        kb_result_free(nullptr, res);
+        result_release_locked(ctx, res);
         return rc;
     }
     uint8_t *hg = (uint8_t *)res->h_get.p;
@@ -1316,7 +1329,7 @@ extern "C" int kb_get_batch(kb_ctx *ctx, const kb_get_req *reqs, uint64_t n, int
     }
     cudaError_t e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) {
-        kb_result_free(nullptr, res);
+        result_release_locked(ctx, res);
         return kb_cuda_fail(ctx, e, "get resolve");
     }
     // copy jobs for the found values (host side: offsets come from the host copies of the directory)
@@ -1347,7 +1360,7 @@ extern "C" int kb_get_batch(kb_ctx *ctx, const kb_get_req *reqs, uint64_t n, int
         if (rc == KB_OK) rc = pool_get_dev(ctx, nbytes + 64, &res->d_bytes);
         if (rc == KB_OK) rc = hbuf_ensure(ctx, ctx->h_stage2, nj * sizeof(GatherJob) + 64);
         if (rc != KB_OK) {
-            kb_result_free(nullptr, res);
+            result_release_locked(ctx, res);
             return rc;
         }
         uint8_t *hj = (uint8_t *)ctx->h_stage2.p;
@@ -1368,7 +1381,7 @@ extern "C" int kb_get_batch(kb_ctx *ctx, const kb_get_req *reqs, uint64_t n, int
         e = cudaStreamSynchronize(ctx->stream);
         if (rc == KB_OK && e != cudaSuccess) rc = kb_cuda_fail(ctx, e, "get gather");
         if (rc != KB_OK) {
-            kb_result_free(nullptr, res);
+            result_release_locked(ctx, res);
             return rc;
         }
         if (out_mode == KB_OUT_HOST) {
@@ -1467,7 +1480,7 @@ extern "C" int kb_compact_sweep(kb_ctx *ctx, const uint8_t *start, uint64_t star
         const uint64_t nv = ro.total;
         int rc = pool_get_dev(ctx, nv * 5 + 64, &res->d_vic);
         if (rc != KB_OK) {
-            kb_result_free(nullptr, res);
+            result_release_locked(ctx, res);
             return rc;
         }
         uint32_t *vidx = (uint32_t *)res->d_vic.p;
@@ -1482,7 +1495,7 @@ extern "C" int kb_compact_sweep(kb_ctx *ctx, const uint8_t *start, uint64_t star
         cudaError_t e = cudaStreamSynchronize(ctx->stream);
         if (rc == KB_OK && e != cudaSuccess) rc = kb_cuda_fail(ctx, e, "compact sweep");
         if (rc != KB_OK) {
-            kb_result_free(nullptr, res);
+            result_release_locked(ctx, res);
             return rc;
         }
         if (out_mode == KB_OUT_HOST) {
