@@ -268,6 +268,7 @@ def run_b200(args, rank: int, local_rank: int, world: int):
     import threading
 
     jobs_q, done_q = queue.SimpleQueue(), queue.SimpleQueue()
+    pyt = {"cursor": 0.0, "range_call": 0.0, "range_result": 0.0, "fan_call": 0.0, "n": 0}
 
     def worker():
         torch.cuda.set_device(local_rank)
@@ -286,9 +287,11 @@ def run_b200(args, rank: int, local_rank: int, world: int):
         wthread.start()
 
     def fan_device():
+        t0 = time.perf_counter()
         m = weng.watch_match_dev(evh, KB_OUT_DEVICE)
         d = m.n_deliveries
         m.close()
+        pyt["fan_call"] = pyt.get("fan_call", 0.0) + time.perf_counter() - t0
         return d
 
     def fan_e2e():
@@ -308,8 +311,6 @@ def run_b200(args, rank: int, local_rank: int, world: int):
         if isinstance(b, Exception):
             raise b
         return a, b
-
-    pyt = {"cursor": 0.0, "range_call": 0.0, "range_result": 0.0, "n": 0}
 
     def scan_device():
         t0 = time.perf_counter()
@@ -384,7 +385,10 @@ def run_b200(args, rank: int, local_rank: int, world: int):
         e.prof_reset()
         e.prof_enable(2)
     l0 = sum(e.launch_count() for e in engines)
+    for k in list(pyt):
+        pyt[k] = 0
     dev_ms, wall_s, (examined, n_kvs, deliveries) = timed(step_device, args.steps)
+    host_call_us = {k: 1e6 * v / max(pyt["n"], 1) for k, v in pyt.items() if k != "n"}
     launches = sum(e.launch_count() for e in engines) - l0
     prof_major = {}
     for e in engines:
@@ -449,7 +453,7 @@ def run_b200(args, rank: int, local_rank: int, world: int):
             "scan_records_per_step": int(examined), "emitted_kvs_per_step": int(n_kvs),
             "fanout_events_per_step": int(wl["events"].n), "deliveries_per_step": int(deliveries),
             "wall_ms_per_step": wall_s * 1e3 / args.steps, "gen_s": wl["gen_s"],
-            "host_call_us": {k: 1e6 * v / max(pyt["n"], 1) for k, v in pyt.items() if k != "n"},
+            "host_call_us": host_call_us,
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(wl)
