@@ -60,6 +60,40 @@ func (e *Engine) LoadSorted(keys []byte, keyOff []uint64, vals []byte, valOff []
 		(*C.uint8_t)(unsafe.Pointer(&vals[0])), (*C.uint64_t)(unsafe.Pointer(&valOff[0])), C.uint64_t(n)))
 }
 
+// WriteOp mirrors one Put/Del of a committed storage.BatchWrite (pkg/storage/interface.go:62-84).
+type WriteOp struct {
+	Del      bool
+	Key, Val []byte
+}
+
+// ApplyBatch merges a committed batch into the HBM snapshot; the storage adaptor calls it after Commit succeeds.
+func (e *Engine) ApplyBatch(ops []WriteOp) error {
+	if len(ops) == 0 {
+		return nil
+	}
+	raw := make([]C.kb_write_op, len(ops))
+	pin := runtime.Pinner{}
+	defer pin.Unpin()
+	for i := range ops {
+		if ops[i].Del {
+			raw[i]._type = C.KB_OP_DEL
+		} else {
+			raw[i]._type = C.KB_OP_PUT
+		}
+		if len(ops[i].Key) > 0 {
+			pin.Pin(&ops[i].Key[0])
+			raw[i].key = (*C.uint8_t)(unsafe.Pointer(&ops[i].Key[0]))
+		}
+		raw[i].key_len = C.uint64_t(len(ops[i].Key))
+		if len(ops[i].Val) > 0 {
+			pin.Pin(&ops[i].Val[0])
+			raw[i].val = (*C.uint8_t)(unsafe.Pointer(&ops[i].Val[0]))
+		}
+		raw[i].val_len = C.uint64_t(len(ops[i].Val))
+	}
+	return e.err(C.kb_apply_batch(e.ctx, &raw[0], C.uint64_t(len(raw))))
+}
+
 type b200Scanner struct {
 	e *Engine
 }

@@ -63,6 +63,19 @@ int kb_sync(kb_ctx *ctx);
 int kb_load_sorted(kb_ctx *ctx, const uint8_t *keys, const uint64_t *key_off, const uint8_t *vals,
                    const uint64_t *val_off, uint64_t n);
 int kb_store_info(kb_ctx *ctx, uint64_t *n_records, uint64_t *key_bytes, uint64_t *val_bytes);
+
+/* Incremental maintenance from the write path: one committed storage.BatchWrite (pkg/storage/interface.go:81-106;
+ * the backend issues CAS(revision record) + Put(object record) per write, pkg/backend/txn.go:249-265,
+ * creator/naive.go:53-105) applied to the HBM snapshot.  Keys are INTERNAL keys.  The last op on a key wins;
+ * deleting an absent key is a no-op.  The slab is rebuilt by a device-side merge (O(store bytes) of HBM copy), so
+ * callers batch their commits (e.g. the <=300-event collector batches). */
+enum { KB_OP_PUT = 0, KB_OP_DEL = 1 };
+typedef struct kb_write_op {
+    uint32_t type;                              /* KB_OP_PUT / KB_OP_DEL */
+    const uint8_t *key;  uint64_t key_len;
+    const uint8_t *val;  uint64_t val_len;      /* ignored for KB_OP_DEL */
+} kb_write_op;
+int kb_apply_batch(kb_ctx *ctx, const kb_write_op *ops, uint64_t n);
 /* compact_key record used by checkCompactRace (scanner.go:594-626); present=0 clears it */
 int kb_set_compact_revision(kb_ctx *ctx, int present, uint64_t rev);
 

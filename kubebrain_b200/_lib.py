@@ -27,9 +27,11 @@ u32p = C.POINTER(C.c_uint32)
 u64p = C.POINTER(C.c_uint64)
 
 # every symbol include/kb_b200.h declares (tests/test_abi.py checks the .so exports all of them)
+KB_OP_PUT, KB_OP_DEL = 0, 1
+
 ABI_SYMBOLS = [
     "kb_abi_version", "kb_open", "kb_close", "kb_last_error", "kb_stream", "kb_sync",
-    "kb_load_sorted", "kb_store_info", "kb_set_compact_revision",
+    "kb_load_sorted", "kb_store_info", "kb_apply_batch", "kb_set_compact_revision",
     "kb_range_batch", "kb_range_view_get", "kb_get_batch", "kb_get_view_get",
     "kb_compact_sweep", "kb_compact_view_get",
     "kb_watch_add", "kb_watch_del", "kb_watch_count", "kb_watch_match", "kb_events_upload", "kb_events_free",
@@ -55,6 +57,11 @@ class KbRangeView(C.Structure):
                 ("n_kvs", C.c_uint64), ("rec_idx", u32p), ("rev", u64p), ("key_off", u64p), ("key_len", u32p),
                 ("val_off", u64p), ("val_len", u32p), ("bytes", C.c_void_p), ("n_bytes", C.c_uint64),
                 ("on_device", C.c_int)]
+
+
+class KbWriteOp(C.Structure):
+    _fields_ = [("type", C.c_uint32), ("key", C.c_char_p), ("key_len", C.c_uint64), ("val", C.c_char_p),
+                ("val_len", C.c_uint64)]
 
 
 class KbGetReq(C.Structure):
@@ -116,6 +123,8 @@ def lib():
     L.kb_store_info.restype = C.c_int
     L.kb_store_info.argtypes = [vp, u64p, u64p, u64p]
     L.kb_set_compact_revision.restype = C.c_int
+    L.kb_apply_batch.argtypes = [vp, C.POINTER(KbWriteOp), C.c_uint64]
+    L.kb_apply_batch.restype = C.c_int
     L.kb_set_compact_revision.argtypes = [vp, C.c_int, C.c_uint64]
     L.kb_range_batch.restype = C.c_int
     L.kb_range_batch.argtypes = [vp, C.POINTER(KbRangeReq), C.c_uint64, C.c_int, C.POINTER(vp)]
@@ -359,6 +368,17 @@ class Engine:
         kd, ko, kp, kop = _slab_ptrs(store.keys)
         vd, vo, vp, vop = _slab_ptrs(store.vals)
         self._check(lib().kb_load_sorted(self._ctx, kp, kop, vp, vop, store.n))
+
+    def apply_batch(self, ops: Sequence[Tuple[bytes, Optional[bytes]]]):
+        """One committed BatchWrite (pkg/storage/interface.go:62-84): (internal_key, value) puts, (internal_key, None)
+        deletes, applied in order (the last op on a key wins)."""
+        arr = (KbWriteOp * max(len(ops), 1))()
+        for i, (k, v) in enumerate(ops):
+            arr[i].type = KB_OP_DEL if v is None else KB_OP_PUT
+            arr[i].key, arr[i].key_len = k, len(k)
+            if v is not None:
+                arr[i].val, arr[i].val_len = v, len(v)
+        self._check(lib().kb_apply_batch(self._ctx, arr, len(ops)))
 
     def store_info(self) -> Tuple[int, int, int]:
         a, b, c = C.c_uint64(), C.c_uint64(), C.c_uint64()

@@ -116,6 +116,14 @@ class Backend:
     def set_current_revision(self, rev: int):
         self._revision = rev
 
+    # ---- write hook ----
+    def commit(self, ops: Sequence[Tuple[bytes, Optional[bytes]]]):
+        """The hook a storage adaptor calls after BatchWrite.Commit succeeds (pkg/storage/interface.go:62-84; the txn
+        builders of pkg/backend/txn.go:36-246 and the compaction deletes of scanner.go:538-564 all go through it):
+        (internal_key, value) puts and (internal_key, None) deletes are merged into the HBM snapshot."""
+        if ops:
+            self.engine.apply_batch(list(ops))
+
     # ---- read path ----
     def get(self, key: bytes, revision: int = 0):
         """range.go:34-81 Backend.Get: returns (header revision, KeyValue | None).  A missing key, a key created after

@@ -425,6 +425,8 @@ extern "C" int kb_load_sorted(kb_ctx *ctx, const uint8_t *keys, const uint64_t *
     ctx->st.n = (uint32_t)n;
     ctx->h_koff16 = koff16;
     ctx->h_voff16 = voff16;
+    ctx->h_klen = klen;
+    ctx->h_vlen = vlen;
 
     // the iterator contract: strictly ascending unique keys
     if (n > 1) {

@@ -161,6 +161,8 @@ struct kb_ctx {
     uint64_t key_bytes = 0, val_bytes = 0;
     std::vector<uint32_t> h_koff16;  // host copies of the slab offsets: byte accounting and response-arena bounds
     std::vector<uint64_t> h_voff16;
+    std::vector<uint16_t> h_klen;   // host copy of the whole record directory: kb_apply_batch rebuilds it on the host
+    std::vector<uint32_t> h_vlen;
     bool compact_present = false;
     uint64_t compact_rev = 0;
 

@@ -727,6 +727,59 @@ k_get_resolve(StoreDev st, const uint4 *__restrict__ bounds, const uint32_t *__r
     }
 }
 
+// ---- kb_apply_batch helpers ------------------------------------------------------------------------------
+// exists[i] = 1 iff the record at pos[i] (lower_bound of op key i) carries exactly that key
+__global__ void __launch_bounds__(128)
+k_key_exists(StoreDev st, const uint4 *__restrict__ bounds, const uint32_t *__restrict__ boff16,
+             const uint32_t *__restrict__ blen, const uint32_t *__restrict__ pos, uint32_t n, uint8_t *__restrict__ exists)
+{
+    const uint32_t g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (g >= n) return;
+    const uint32_t r = pos[g];
+    bool eq = r < st.n;
+    if (eq) {
+        const uint32_t bl = blen[g];
+        eq = st.klen[r] == bl;
+        if (eq) {
+            const uint4 *a = st.kslab + st.koff16[r];
+            const uint4 *b = bounds + boff16[g];
+            for (uint32_t c = lane; c * 16 < bl; c += 32) {
+                uint4 x = a[c], y = b[c];
+                int p = first_diff16(x, y);
+                if (p < 16 && c * 16 + p < bl) eq = false;
+            }
+        }
+        eq = __all_sync(0xffffffffu, eq);
+    }
+    if (lane == 0) exists[g] = eq ? 1 : 0;
+}
+
+// one CTA per piece: copy n16 chunks from (sel ? srcB : srcA) + src16 to dst + dst16
+struct CopyPiece {
+    uint64_t src16, dst16;
+    uint32_t n16, sel;
+};
+
+__global__ void __launch_bounds__(256)
+k_seg_copy(const uint4 *__restrict__ srcA, const uint4 *__restrict__ srcB, const CopyPiece *__restrict__ pieces,
+           uint32_t npieces, uint4 *__restrict__ dst)
+{
+    for (uint32_t p = blockIdx.x; p < npieces; p += gridDim.x) {
+        const CopyPiece pc = pieces[p];
+        const uint4 *s = (pc.sel ? srcB : srcA) + pc.src16;
+        uint4 *d = dst + pc.dst16;
+        for (uint32_t c = threadIdx.x; c < pc.n16; c += blockDim.x * 4) {
+            uint4 v[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                if (c + j * blockDim.x < pc.n16) v[j] = ldg_stream(s + c + j * blockDim.x);
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                if (c + j * blockDim.x < pc.n16) stg_stream(d + c + j * blockDim.x, v[j]);
+        }
+    }
+}
+
 // single CTA: per-request emitted count / response bytes (limit applied) and their exclusive prefixes over the
 // requests: job_first[q] = first kv of request q, arena_base[q] = first arena byte of request q; [nreq] = totals
 __global__ void __launch_bounds__(256)
@@ -1523,3 +1576,237 @@ extern "C" int kb_compact_view_get(const kb_result *res, kb_compact_view *v)
     return KB_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// kb_apply_batch: one committed BatchWrite merged into the HBM snapshot
+// ------------------------------------------------------------------------------------------------
+namespace {
+struct ApplyOp {
+    std::string key, val;
+    uint32_t type;
+    uint64_t order;
+};
+
+// append `n16` chunks starting at src16 (of source `sel`) as pieces of at most 4096 chunks
+void push_pieces(std::vector<CopyPiece> &out, uint64_t src16, uint64_t dst16, uint64_t n16, uint32_t sel)
+{
+    while (n16) {
+        const uint32_t k = (uint32_t)std::min<uint64_t>(n16, 4096);
+        out.push_back(CopyPiece{src16, dst16, k, sel});
+        src16 += k;
+        dst16 += k;
+        n16 -= k;
+    }
+}
+}  // namespace
+
+extern "C" int kb_apply_batch(kb_ctx *ctx, const kb_write_op *ops, uint64_t n_ops)
+{
+    if (!ctx || (n_ops && !ops)) return KB_EINVAL;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    if (!ctx->loaded) return kb_fail(ctx, KB_ESTATE, "no store loaded");
+    cudaSetDevice(ctx->device);
+    if (n_ops == 0) return KB_OK;
+    // 1. last op per key wins; sort by key (bytes.Compare order)
+    std::vector<ApplyOp> all(n_ops);
+    for (uint64_t i = 0; i < n_ops; i++) {
+        if ((!ops[i].key && ops[i].key_len) || (ops[i].type == KB_OP_PUT && !ops[i].val && ops[i].val_len)) return KB_EINVAL;
+        if (ops[i].key_len > 65535) return kb_fail(ctx, KB_ELIMIT, "key longer than 65535 bytes");
+        if (ops[i].val_len > 0xFFFFFFFFull) return kb_fail(ctx, KB_ELIMIT, "value too long");
+        if (ops[i].type != KB_OP_PUT && ops[i].type != KB_OP_DEL) return KB_EINVAL;
+        all[i].key.assign((const char *)ops[i].key, ops[i].key_len);
+        if (ops[i].type == KB_OP_PUT) all[i].val.assign((const char *)ops[i].val, ops[i].val_len);
+        all[i].type = ops[i].type;
+        all[i].order = i;
+    }
+    std::sort(all.begin(), all.end(), [](const ApplyOp &a, const ApplyOp &b) {
+        const int c = a.key.compare(b.key);  // std::string::compare is lexicographic on unsigned char via char_traits
+        return c != 0 ? c < 0 : a.order < b.order;
+    });
+    std::vector<ApplyOp> m;
+    for (size_t i = 0; i < all.size(); i++)
+        if (i + 1 == all.size() || all[i + 1].key != all[i].key) m.push_back(std::move(all[i]));
+    const uint64_t M = m.size();
+
+    // 2. op keys (and PUT values) as padded slabs on the device; positions by k_search
+    uint64_t kchunks = 0, vchunks = 0;
+    for (auto &o : m) {
+        kchunks += (o.key.size() + 15) / 16 + 3;
+        if (o.type == KB_OP_PUT) vchunks += (o.val.size() + 15) / 16;
+    }
+    KB_TRY(hbuf_ensure(ctx, ctx->h_stage, kchunks * 16 + M * 8 + vchunks * 16 + 256));
+    uint8_t *hs = (uint8_t *)ctx->h_stage.p;
+    memset(hs, 0, kchunks * 16);
+    uint32_t *hboff = (uint32_t *)(hs + kchunks * 16), *hblen = hboff + M;
+    uint8_t *hv = hs + kchunks * 16 + M * 8;
+    hv = (uint8_t *)(((uintptr_t)hv + 15) & ~(uintptr_t)15);
+    memset(hv, 0, vchunks * 16);
+    std::vector<uint64_t> op_k16(M), op_v16(M);
+    uint64_t kc = 0, vc = 0;
+    for (uint64_t i = 0; i < M; i++) {
+        hboff[i] = (uint32_t)kc;
+        hblen[i] = (uint32_t)m[i].key.size();
+        if (!m[i].key.empty()) memcpy(hs + kc * 16, m[i].key.data(), m[i].key.size());
+        op_k16[i] = kc;
+        kc += (m[i].key.size() + 15) / 16 + 3;
+        op_v16[i] = vc;
+        if (m[i].type == KB_OP_PUT) {
+            if (!m[i].val.empty()) memcpy(hv + vc * 16, m[i].val.data(), m[i].val.size());
+            vc += (m[i].val.size() + 15) / 16;
+        }
+    }
+    DBuf d_opv;
+    KB_TRY(dbuf_ensure(ctx, ctx->d_bounds, kchunks * 16 + M * 8 + 64));
+    KB_TRY(dbuf_ensure(ctx, ctx->d_bres, M * 4 + M + 64));
+    KB_TRY(dbuf_ensure(ctx, d_opv, vchunks * 16 + 64));
+    KB_CUDA(ctx, cudaMemcpyAsync(ctx->d_bounds.p, hs, kchunks * 16 + M * 8, cudaMemcpyHostToDevice, ctx->stream));
+    if (vchunks) KB_CUDA(ctx, cudaMemcpyAsync(d_opv.p, hv, vchunks * 16, cudaMemcpyHostToDevice, ctx->stream));
+    const uint32_t *d_boff = (const uint32_t *)((const uint8_t *)ctx->d_bounds.p + kchunks * 16);
+    uint32_t *d_pos = (uint32_t *)ctx->d_bres.p;
+    uint8_t *d_exists = (uint8_t *)(d_pos + M);
+    const unsigned sg = (unsigned)((M * 32 + 127) / 128);
+    KB_LAUNCH(ctx, "k_search", M * 64,
+              (k_search<<<sg, 128, 0, ctx->stream>>>(ctx->st, (const uint4 *)ctx->d_bounds.p, d_boff, d_boff + M, (uint32_t)M,
+                                                     d_pos)));
+    KB_LAUNCH(ctx, "k_key_exists", M * 320,
+              (k_key_exists<<<sg, 128, 0, ctx->stream>>>(ctx->st, (const uint4 *)ctx->d_bounds.p, d_boff, d_boff + M, d_pos,
+                                                         (uint32_t)M, d_exists)));
+    std::vector<uint32_t> pos(M);
+    std::vector<uint8_t> exists(M);
+    KB_CUDA(ctx, cudaMemcpyAsync(pos.data(), d_pos, M * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    KB_CUDA(ctx, cudaMemcpyAsync(exists.data(), d_exists, M, cudaMemcpyDeviceToHost, ctx->stream));
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+        cudaFree(d_opv.p);
+        return kb_cuda_fail(ctx, e, "apply: search");
+    }
+
+    // 3. merge the record directory on the host; emit the slab copies as pieces
+    const uint64_t N = ctx->st.n;
+    uint64_t n_ins = 0, n_del = 0;
+    for (uint64_t i = 0; i < M; i++) {
+        n_ins += m[i].type == KB_OP_PUT;
+        n_del += exists[i];
+    }
+    const uint64_t N2 = N + n_ins - n_del;
+    if (N2 >= 0xFFFFFFFEull) {
+        cudaFree(d_opv.p);
+        return kb_fail(ctx, KB_ELIMIT, "too many records");
+    }
+    std::vector<uint32_t> koff2(N2 + 1), vlen2(std::max<uint64_t>(N2, 1));
+    std::vector<uint16_t> klen2(std::max<uint64_t>(N2, 1));
+    std::vector<uint64_t> voff2(N2 + 1);
+    std::vector<CopyPiece> kp, vp;
+    uint64_t kacc = 0, vacc = 0, w = 0;
+    auto copy_base = [&](uint64_t a, uint64_t b) {  // surviving base records [a, b)
+        if (a >= b) return;
+        const uint64_t k0 = ctx->h_koff16[a], k1 = ctx->h_koff16[b], v0 = ctx->h_voff16[a], v1 = ctx->h_voff16[b];
+        push_pieces(kp, k0, kacc, k1 - k0, 0);
+        push_pieces(vp, v0, vacc, v1 - v0, 0);
+        for (uint64_t r = a; r < b; r++, w++) {
+            koff2[w] = (uint32_t)(kacc + (ctx->h_koff16[r] - k0));
+            voff2[w] = vacc + (ctx->h_voff16[r] - v0);
+            klen2[w] = ctx->h_klen[r];
+            vlen2[w] = ctx->h_vlen[r];
+        }
+        kacc += k1 - k0;
+        vacc += v1 - v0;
+    };
+    uint64_t next_base = 0;
+    for (uint64_t i = 0; i < M; i++) {
+        copy_base(next_base, pos[i]);
+        next_base = pos[i] + (exists[i] ? 1 : 0);  // the matched base record is replaced or dropped
+        if (m[i].type == KB_OP_PUT) {
+            const uint64_t nk = (m[i].key.size() + 15) / 16, nv = (m[i].val.size() + 15) / 16;
+            push_pieces(kp, op_k16[i], kacc, nk, 1);
+            push_pieces(vp, op_v16[i], vacc, nv, 1);
+            koff2[w] = (uint32_t)kacc;
+            voff2[w] = vacc;
+            klen2[w] = (uint16_t)m[i].key.size();
+            vlen2[w] = (uint32_t)m[i].val.size();
+            w++;
+            kacc += nk;
+            vacc += nv;
+            if (kacc > 0xFFFFFFF0ull) {
+                cudaFree(d_opv.p);
+                return kb_fail(ctx, KB_ELIMIT, "key slab exceeds 64 GiB");
+            }
+        }
+    }
+    copy_base(next_base, N);
+    koff2[N2] = (uint32_t)kacc;
+    voff2[N2] = vacc;
+
+    // 4. new slabs on the device: segmented copy from the old slab (sel 0) and the op slabs (sel 1)
+    DBuf nk_slab, nv_slab, d_pieces;
+    int rc = dbuf_ensure(ctx, nk_slab, kacc * 16 + 64);
+    if (rc == KB_OK) rc = dbuf_ensure(ctx, nv_slab, vacc * 16 + 64);
+    if (rc == KB_OK) rc = dbuf_ensure(ctx, d_pieces, (kp.size() + vp.size() + 1) * sizeof(CopyPiece));
+    if (rc != KB_OK) {  // nothing of the live store has been touched yet
+        cudaFree(d_opv.p);
+        if (nk_slab.p) cudaFree(nk_slab.p);
+        if (nv_slab.p) cudaFree(nv_slab.p);
+        if (d_pieces.p) cudaFree(d_pieces.p);
+        return rc;
+    }
+    // the directory arrays grow in place (their old contents are about to be overwritten anyway)
+    rc = dbuf_ensure(ctx, ctx->d_koff16, (N2 + 1) * 4);
+    if (rc == KB_OK) rc = dbuf_ensure(ctx, ctx->d_klen, (N2 + 1) * 2);
+    if (rc == KB_OK) rc = dbuf_ensure(ctx, ctx->d_voff16, (N2 + 1) * 8);
+    if (rc == KB_OK) rc = dbuf_ensure(ctx, ctx->d_vlen, (N2 + 1) * 4);
+    if (rc != KB_OK) {
+        cudaFree(d_opv.p);
+        cudaFree(nk_slab.p);
+        cudaFree(nv_slab.p);
+        cudaFree(d_pieces.p);
+        ctx->loaded = false;  // a directory array may have been released: the caller reloads
+        return rc;
+    }
+    cudaMemsetAsync((uint8_t *)nk_slab.p + kacc * 16, 0, 64, ctx->stream);
+    cudaMemsetAsync((uint8_t *)nv_slab.p + vacc * 16, 0, 64, ctx->stream);
+    CopyPiece *dp = (CopyPiece *)d_pieces.p;
+    cudaMemcpyAsync(dp, kp.data(), kp.size() * sizeof(CopyPiece), cudaMemcpyHostToDevice, ctx->stream);
+    cudaMemcpyAsync(dp + kp.size(), vp.data(), vp.size() * sizeof(CopyPiece), cudaMemcpyHostToDevice, ctx->stream);
+    if (!kp.empty()) {
+        KB_LAUNCH(ctx, "k_seg_copy", 2 * kacc * 16,
+                  (k_seg_copy<<<(unsigned)std::min<size_t>(kp.size(), 148 * 16), 256, 0, ctx->stream>>>(
+                      ctx->st.kslab, (const uint4 *)ctx->d_bounds.p, dp, (uint32_t)kp.size(), (uint4 *)nk_slab.p)));
+    }
+    if (!vp.empty()) {
+        KB_LAUNCH(ctx, "k_seg_copy", 2 * vacc * 16,
+                  (k_seg_copy<<<(unsigned)std::min<size_t>(vp.size(), 148 * 16), 256, 0, ctx->stream>>>(
+                      ctx->st.vslab, (const uint4 *)d_opv.p, dp + kp.size(), (uint32_t)vp.size(), (uint4 *)nv_slab.p)));
+    }
+    cudaMemcpyAsync(ctx->d_koff16.p, koff2.data(), (N2 + 1) * 4, cudaMemcpyHostToDevice, ctx->stream);
+    cudaMemcpyAsync(ctx->d_klen.p, klen2.data(), N2 * 2, cudaMemcpyHostToDevice, ctx->stream);
+    cudaMemcpyAsync(ctx->d_voff16.p, voff2.data(), (N2 + 1) * 8, cudaMemcpyHostToDevice, ctx->stream);
+    cudaMemcpyAsync(ctx->d_vlen.p, vlen2.data(), N2 * 4, cudaMemcpyHostToDevice, ctx->stream);
+    e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_opv.p);
+    cudaFree(d_pieces.p);
+    if (e != cudaSuccess) {
+        cudaFree(nk_slab.p);
+        cudaFree(nv_slab.p);
+        ctx->loaded = false;  // the directory on the device may be half written
+        return kb_cuda_fail(ctx, e, "apply: merge");
+    }
+    // 5. swap
+    cudaFree(ctx->d_kslab.p);
+    cudaFree(ctx->d_vslab.p);
+    ctx->d_kslab = nk_slab;
+    ctx->d_vslab = nv_slab;
+    ctx->st.kslab = (const uint4 *)ctx->d_kslab.p;
+    ctx->st.vslab = (const uint4 *)ctx->d_vslab.p;
+    ctx->st.koff16 = (const uint32_t *)ctx->d_koff16.p;
+    ctx->st.klen = (const uint16_t *)ctx->d_klen.p;
+    ctx->st.voff16 = (const uint64_t *)ctx->d_voff16.p;
+    ctx->st.vlen = (const uint32_t *)ctx->d_vlen.p;
+    ctx->st.n = (uint32_t)N2;
+    ctx->h_koff16.swap(koff2);
+    ctx->h_voff16.swap(voff2);
+    ctx->h_klen.swap(klen2);
+    ctx->h_vlen.swap(vlen2);
+    ctx->key_bytes = kacc * 16;
+    ctx->val_bytes = vacc * 16;
+    return KB_OK;
+}

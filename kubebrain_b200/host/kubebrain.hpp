@@ -175,6 +175,23 @@ class Engine {
         Check(kb_load_sorted(ctx_, keys.empty() ? &z : (const uint8_t *)keys.data(), ko.data(),
                              vals.empty() ? &z : (const uint8_t *)vals.data(), vo.data(), items.size()));
     }
+    // one committed storage.BatchWrite (pkg/storage/interface.go:62-84): Put / Del in order, last op on a key wins
+    struct WriteOp {
+        bool del;
+        Bytes key, val;
+    };
+    void ApplyBatch(const std::vector<WriteOp> &ops)
+    {
+        std::vector<kb_write_op> raw(ops.size());
+        for (size_t i = 0; i < ops.size(); i++) {
+            raw[i].type = ops[i].del ? KB_OP_DEL : KB_OP_PUT;
+            raw[i].key = (const uint8_t *)ops[i].key.data();
+            raw[i].key_len = ops[i].key.size();
+            raw[i].val = (const uint8_t *)ops[i].val.data();
+            raw[i].val_len = ops[i].val.size();
+        }
+        Check(kb_apply_batch(ctx_, raw.data(), raw.size()));
+    }
 
    private:
     kb_ctx *ctx_ = nullptr;

@@ -137,6 +137,27 @@ static void gpu_tests()
     // compaction at the current revision: nothing to delete (every object has exactly one live version)
     auto victims = be.Compact(init);
     CHECK(victims.size() == 1 && victims[0].empty());
+    // incremental maintenance: update key 3 and delete key 4 through the BatchWrite hook, no reload
+    auto be64 = [](uint64_t v) {
+        Bytes rb;
+        for (int s = 7; s >= 0; s--) rb.push_back((char)((v >> (8 * s)) & 0xff));
+        return rb;
+    };
+    std::vector<kb::Engine::WriteOp> ops;
+    ops.push_back({false, c.EncodeRevisionKey(fmt(testKey, 3)), be64(init + 1)});
+    ops.push_back({false, c.EncodeObjectKey(fmt(testKey, 3), init + 1), "new"});
+    ops.push_back({false, c.EncodeRevisionKey(fmt(testKey, 4)), be64(init + 2) + Bytes(1, '\0')});
+    ops.push_back({false, c.EncodeObjectKey(fmt(testKey, 4), init + 2), "tombstone"});
+    ops.push_back({true, c.EncodeObjectKey(fmt(testKey, 9), init), ""});  // drop the only version of key 9
+    eng.ApplyBatch(ops);
+    be.SetCurrentRevision(init + 2);
+    r = be.List(testKey, endKey);
+    CHECK(r.Kvs.size() == (size_t)inject - 2 && r.Kvs[3].Value == "new" && r.Kvs[3].Revision == init + 1 &&
+          r.Kvs[4].Key == fmt(testKey, 5));
+    r = be.List(testKey, endKey, init);  // time travel still sees the old versions of 3 and 4 (9 was removed)
+    CHECK(r.Kvs.size() == (size_t)inject - 1 && r.Kvs[3].Value == fmt("val", 3) && r.Kvs[4].Value == fmt("val", 4));
+    be.Get(fmt(testKey, 4), 0, &gkv, &found);
+    CHECK(!found);
     std::printf("gpu ok\n");
 }
 

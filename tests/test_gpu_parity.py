@@ -192,6 +192,159 @@ def test_fuzz_range(eng, seed):
     check_ranges(eng, store, st, reqs)
 
 
+def _apply_ops(items: dict, ops):
+    for k, v in ops:
+        if v is None:
+            items.pop(k, None)
+        else:
+            items[k] = v
+
+
+def _fuzz_ops(rng, items: dict, n: int):
+    """a BatchWrite: overwrites (shorter/longer/empty values), deletes of present and absent keys, inserts before
+    the first / after the last record and between neighbours, repeated ops on one key (last wins)"""
+    keys = sorted(items)
+    ops = []
+    for _ in range(n):
+        r = rng.random()
+        k = rng.choice(keys) if keys else fuzz.MAGIC + b"k$" + b"\x00" * 8
+        if r < 0.25:
+            ops.append((k, bytes(rng.randrange(256) for _ in range(rng.choice([0, 1, 9, 16, 17, 40, 300])))))
+        elif r < 0.45:
+            ops.append((k, None))
+        elif r < 0.55:
+            ops.append((k + bytes([rng.randrange(256)]), None))  # absent key: no-op
+        elif r < 0.75:
+            cut = rng.randint(0, len(k))
+            nk = k[:cut] + bytes(rng.randrange(256) for _ in range(rng.randint(1, 24)))
+            ops.append((nk, fuzz.TOMB if rng.random() < 0.3 else bytes(rng.randrange(256) for _ in range(rng.randint(0, 64)))))
+        elif r < 0.85:
+            uk = rng.choice([b"a", b"/events/x", b"zz/new", b""]) + bytes([rng.randrange(97, 123)])
+            rev = rng.randint(0, 70)
+            val = struct.pack(">Q", rng.randint(1, 70)) + (b"\x00" if rng.random() < 0.3 else b"") if rev == 0 else \
+                bytes(rng.randrange(256) for _ in range(rng.randint(0, 30)))
+            ops.append((fuzz.MAGIC + uk + b"$" + struct.pack(">Q", rev), val))
+        elif r < 0.9:
+            ops.append((b"\x00" * rng.randint(0, 3), b"front"))
+        elif r < 0.95:
+            ops.append((b"\xff" * rng.randint(1, 40), b"back"))
+        else:
+            ops.append((rng.choice(ops)[0] if ops else k, b"again" * rng.randint(0, 5)))
+    # Go panics on value[:8] of a short revision-record value under /events/ (compactIfExpired): keep those >= 8 bytes
+    return [(k, struct.pack(">Q", 9) if v is not None and len(v) < 8 and k.endswith(b"$" + b"\x00" * 8) and
+             b"/events/" in k else v) for k, v in ops]
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_apply_batch_fuzz(eng, seed):
+    """kb_apply_batch == rebuilding the snapshot from the updated map (storage.BatchWrite semantics,
+    pkg/storage/interface.go:62-84): every scan / get / compaction answer afterwards equals the oracle's on the
+    reloaded store"""
+    import random
+    rng = random.Random(1000 + seed)
+    store = fuzz.fuzz_store(seed, n_keys=30 + 20 * seed)
+    items = dict(zip(store.keys.tolist(), store.vals.tolist()))
+    eng.load_sorted(store)
+    eng.set_compact_revision(None)
+    for rnd in range(4):
+        ops = _fuzz_ops(rng, items, rng.choice([1, 5, 40, 200]))
+        eng.apply_batch(ops)
+        _apply_ops(items, ops)
+        cur = PackedStore.from_items(list(items.items()))
+        n, kb, vb = eng.store_info()
+        assert n == cur.n
+        st = ko.OracleStore(cur)
+        reqs = []
+        for s, e in fuzz.fuzz_bounds(cur, seed * 10 + rnd):
+            for rev in (0, 23, 60, 2**64 - 1):
+                for lim in (0, 3):
+                    reqs.append((s, e, rev, lim))
+        check_ranges(eng, cur, st, reqs)
+        check_compact(eng, cur, st, b"\x00", b"\xff" * 4, 35)
+    # deleting everything leaves an empty, still usable store
+    eng.apply_batch([(k, None) for k in items])
+    assert eng.store_info()[0] == 0
+    res = eng.range_batch([(b"\x00", b"\xff", 0, 0)], KB_OUT_HOST)
+    assert int(res.req_count[0]) == 0
+    res.close()
+    eng.apply_batch([(fuzz.MAGIC + b"a$" + struct.pack(">Q", 5), b"v")])
+    assert eng.store_info()[0] == 1
+
+
+def test_apply_batch_large(eng):
+    """100k-record store, 3 batches of 20k ops: the segmented slab copy spans many pieces"""
+    import random
+    store, meta = synth.gen_store(n_objects=20_000, versions=4, lu=64, lv=256, n_namespaces=20, config_id=2,
+                                  tomb_frac=0.1)
+    eng.load_sorted(store)
+    eng.set_compact_revision(None)
+    keys = store.keys.tolist()
+    items = dict(zip(keys, store.vals.tolist()))
+    rng = random.Random(5)
+    for rnd in range(3):
+        ops = []
+        for k in rng.sample(keys, 10_000):
+            r = rng.random()
+            if r < 0.4:
+                ops.append((k, None))
+            elif r < 0.7:
+                ops.append((k, bytes([rnd]) * rng.randint(0, 600)))
+            else:
+                ops.append((k[:-8] + struct.pack(">Q", rng.randint(1, 2**40)), bytes([rnd + 7]) * rng.randint(1, 300)))
+        eng.apply_batch(ops)
+        _apply_ops(items, ops)
+        keys = sorted(items)
+    cur = PackedStore.from_items(list(items.items()))
+    st = ko.OracleStore(cur)
+    assert eng.store_info()[0] == cur.n
+    reqs = [(b"\x00", b"\xff" * 4, 0, 0), (b"\x00", b"\xff" * 4, meta.read_rev, 0)] + _ns_requests(meta, 8, 501)
+    check_ranges(eng, cur, st, reqs)
+
+
+def test_incremental_lifecycle(eng):
+    """create / update / delete / compact through the reference write model, the snapshot maintained only by
+    Backend.commit (never reloaded): List / Get / Count stay equal to the oracle on the model's current map"""
+    import random
+    rng = random.Random(77)
+    mb = MiniBackend(10)
+    be = Backend(eng)
+    eng.load_sorted(PackedStore.from_items([]))
+    eng.set_compact_revision(None)
+    keys = [b"/registry/%s/ns-%d/o%03d" % (r, n, i) for r in (b"pods", b"events", b"secrets") for n in range(3)
+            for i in range(12)]
+    lo, hi = CODER.encode_object_key(b"/registry/", 0), CODER.encode_object_key(b"/registry0", 0)
+    for rnd in range(12):
+        before = dict(mb.kv)
+        for _ in range(rng.randint(1, 60)):
+            k = rng.choice(keys)
+            val, mod = mb._latest(k)
+            r = rng.random()
+            if val is None:
+                mb.create(k, b"v%d" % mb.rev * rng.randint(1, 30))
+            elif r < 0.6:
+                mb.update(k, b"u%d" % mb.rev * rng.randint(1, 30), mod)
+            else:
+                mb.delete(k)
+        ops = [(k, v) for k, v in mb.kv.items() if before.get(k) != v]
+        be.commit(ops)
+        be.set_current_revision(mb.rev)
+        if rnd % 4 == 3:  # compaction: the victims' deletes go through the same hook
+            cur = mb.snapshot()
+            _, outs = be.compact(mb.rev - rng.randint(0, 20))
+            dels = []
+            for got in outs:
+                dels += [(cur.keys[int(i)], None) for i in got.victim_idx]
+                got.close()
+            be.commit(dels)
+            for k, _ in dels:
+                mb.kv.pop(k, None)
+        cur = mb.snapshot()
+        st = ko.OracleStore(cur)
+        assert eng.store_info()[0] == cur.n
+        check_ranges(eng, cur, st, [(lo, hi, 0, 0), (lo, hi, mb.rev, 0), (lo, hi, mb.rev - 5, 7), (lo, hi, 12, 0)])
+        check_gets(eng, cur, st, [(k, 0) for k in keys[::5]] + [(k, mb.rev - 3) for k in keys[::7]])
+
+
 def test_unsorted_store_rejected(eng):
     store = PackedStore(Slab.from_list([b"b" * 20, b"a" * 20]), Slab.from_list([b"1", b"2"]))
     with pytest.raises(KbError) as ei:
