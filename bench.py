@@ -260,7 +260,8 @@ def run_b200(args, rank: int, local_rank: int, world: int):
     evh = weng.events_upload(wl["events"])
     stream = torch.cuda.ExternalStream(eng.stream())
     wstream = torch.cuda.ExternalStream(weng.stream())
-    reqs = wl["reqs"]
+    # the kb_range_req[] a C / cgo caller passes directly; marshalled once so the timed call is the C-ABI call itself
+    reqs = Engine.pack_range_reqs(wl["reqs"])
     local_rev = int(wl["meta"].last_rev)
 
     # the fan-out half runs on a long-lived worker thread (ctypes releases the GIL inside the C ABI calls)
@@ -417,7 +418,7 @@ def run_b200(args, rank: int, local_rank: int, world: int):
     ms_per_step = dev_ms / args.steps
     value = events_total / (ms_per_step / 1e3)
     e2e_value = events_total / (e2e_ms / args.steps / 1e3)
-    h2d_bytes = wl["events"].n * (32 + 12) + len(reqs) * 2 * 300
+    h2d_bytes = wl["events"].n * (32 + 12) + reqs.n * 2 * 300
 
     if rank == 0:
         peak, peak_src = measured_hbm_peak()

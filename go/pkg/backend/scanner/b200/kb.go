@@ -161,6 +161,31 @@ func (s *b200Scanner) Range(ctx context.Context, start, end []byte, revision uin
 	return copyKvs(view), nil
 }
 
+// RangeResponseWire returns the serialised etcdserverpb.RangeResponse of a List (what backendShim.List builds per kv on
+// the CPU, pkg/server/etcd/backendshim.go:269-282): the kv elements are written by the device, head and tail added here.
+// The etcd gRPC handler sends it through a pass-through codec (grpc.PreparedMsg / encoding.Codec on []byte).
+func (s *b200Scanner) RangeResponseWire(start, end []byte, revision uint64, limit int64, headerRev uint64, more bool) ([]byte, error) {
+	res, view, err := s.rangeOnce(start, end, revision, limit, C.KB_OUT_HOST|C.KB_WIRE_ETCD_KVS)
+	if err != nil {
+		return nil, err
+	}
+	defer C.kb_result_free(s.e.ctx, res)
+	var head, tail [32]C.uint8_t
+	nh := C.kb_wire_range_head(C.uint64_t(headerRev), &head[0])
+	m, count := C.int(0), C.int64_t(view.n_kvs)
+	if more {
+		m, count = 1, count+1
+	}
+	nt := C.kb_wire_range_tail(m, count, &tail[0])
+	out := make([]byte, 0, int(nh)+int(view.n_bytes)+int(nt))
+	out = append(out, C.GoBytes(unsafe.Pointer(&head[0]), C.int(nh))...)
+	if view.n_bytes > 0 {
+		out = append(out, unsafe.Slice((*byte)(unsafe.Pointer(view.bytes)), int(view.n_bytes))...)
+	}
+	out = append(out, C.GoBytes(unsafe.Pointer(&tail[0]), C.int(nt))...)
+	return out, nil
+}
+
 func (s *b200Scanner) Count(ctx context.Context, start, end []byte, revision uint64) (int, error) {
 	res, view, err := s.rangeOnce(start, end, revision, 0, C.KB_OUT_COUNT)
 	if err != nil {
@@ -181,7 +206,7 @@ func (s *b200Scanner) RangeStream(ctx context.Context, start, end []byte, revisi
 				j = len(kvs)
 			}
 			stream <- &proto.StreamRangeResponse{RangeResponse: &proto.RangeResponse{
-				Header: &proto.ResponseHeader{Revision: revision}, Kvs: kvs[i:j], More: true}}
+				Header: &proto.ResponseHeader{Revision: 0}, Kvs: kvs[i:j], More: true}} // forked receiver: readRev unset (receiver.go:162-166)
 		}
 		end := &proto.StreamRangeResponse{RangeResponse: &proto.RangeResponse{
 			Header: &proto.ResponseHeader{Revision: revision}}} // getListStreamEnd scanner.go:179-192

@@ -84,7 +84,15 @@ int kb_set_compact_revision(kb_ctx *ctx, int present, uint64_t rev);
 enum {
     KB_OUT_HOST = 0,    /* results copied to pinned host memory inside the call                    */
     KB_OUT_DEVICE = 1,  /* results stay in HBM; the view holds device pointers                      */
-    KB_OUT_COUNT = 2    /* emptyResultReceiver: counts only (scanner.Count)                         */
+    KB_OUT_COUNT = 2,   /* emptyResultReceiver: counts only (scanner.Count)                         */
+    /* OR-ed into KB_OUT_HOST / KB_OUT_DEVICE: the arena holds the answer as etcd protobuf elements, one per
+     * emitted kv in emission order, ready to be framed and sent (go.etcd.io/etcd/api/v3 v3.5.2 field numbers):
+     *   KVS:    etcdserverpb.RangeResponse.kvs elements -- replaces kvToEtcdKv + Marshal of the List answer
+     *           (pkg/server/etcd/backendshim.go:269-282, 427-436)
+     *   EVENTS: etcdserverpb.WatchResponse.events elements, mvccpb.Event{kv} -- the range-stream answer
+     *           (backendshim.go:349-363); batches are cut at elem_off[300*i] (receiver.go:119-138)            */
+    KB_WIRE_ETCD_KVS = 0x10,
+    KB_WIRE_ETCD_EVENTS = 0x20
 };
 
 typedef struct kb_range_req {
@@ -112,11 +120,25 @@ typedef struct kb_range_view {
     const uint8_t  *bytes;      /* arena (host pinned for KB_OUT_HOST, device for KB_OUT_DEVICE)   */
     uint64_t n_bytes;
     int on_device;              /* 1: bytes AND the per-kv arrays are device pointers (req_* stay host) */
+    /* wire modes: element k is bytes[elem_off[k] .. elem_off[k+1]); key_off / val_off point at the raw user-key and
+     * value bytes inside it; the elements of request q are contiguous: elem_off[req_first[q]] .. elem_off[req_first[q+1]] */
+    const uint64_t *elem_off;   /* n_kvs+1, NULL in the arena modes or when n_kvs == 0             */
+    int wire;                   /* 0, KB_WIRE_ETCD_KVS or KB_WIRE_ETCD_EVENTS                       */
 } kb_range_view;
 
 /* One call = one batch of independent scanner.Range requests answered on one snapshot. */
 int kb_range_batch(kb_ctx *ctx, const kb_range_req *reqs, uint64_t n_req, int out_mode, kb_result **out);
 int kb_range_view_get(const kb_result *res, kb_range_view *view);
+
+/* Framing around the wire elements (host side, a few bytes each; return the byte count written, out >= 32 bytes
+ * [+ reason_len for the watch head]):
+ *   RangeResponse  = kb_wire_range_head(header.revision) | KVS elements | kb_wire_range_tail(more, count)
+ *                    (backendshim.go:269-277: count = len(kvs) + (more ? 1 : 0))
+ *   WatchResponse  = kb_wire_watch_head(header.revision, 0, NULL, 0) | EVENTS elements of one batch
+ *   end of stream  = kb_wire_watch_head(revision, 1, err, len)       (backendshim.go:353-355, scanner.go:179-192) */
+uint64_t kb_wire_range_head(uint64_t header_rev, uint8_t *out);
+uint64_t kb_wire_range_tail(int more, int64_t count, uint8_t *out);
+uint64_t kb_wire_watch_head(uint64_t header_rev, int canceled, const uint8_t *reason, uint64_t reason_len, uint8_t *out);
 
 /* ---- point reads: replaces backend.get / getInternalVal (pkg/backend/range.go:81-121): a reverse iterator from
  * EncodeObjectKey(key, revision) down to EncodeObjectKey(key, 0) with limit 1.  revision 0 means "latest". */

@@ -18,6 +18,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libkbb200.so")
 
 KB_OUT_HOST, KB_OUT_DEVICE, KB_OUT_COUNT = 0, 1, 2
+KB_WIRE_ETCD_KVS, KB_WIRE_ETCD_EVENTS = 0x10, 0x20  # OR-ed into KB_OUT_HOST / KB_OUT_DEVICE
 KB_OK, KB_EINVAL, KB_ECUDA, KB_ENOMEM, KB_EUNSORTED, KB_ECOMPACTED, KB_ESTATE, KB_ENCCL, KB_ELIMIT = (
     0, -1, -2, -3, -4, -5, -6, -7, -8)
 NCCL_ID_BYTES = 128
@@ -32,7 +33,8 @@ KB_OP_PUT, KB_OP_DEL = 0, 1
 ABI_SYMBOLS = [
     "kb_abi_version", "kb_open", "kb_close", "kb_last_error", "kb_stream", "kb_sync",
     "kb_load_sorted", "kb_store_info", "kb_apply_batch", "kb_set_compact_revision",
-    "kb_range_batch", "kb_range_view_get", "kb_get_batch", "kb_get_view_get",
+    "kb_range_batch", "kb_range_view_get", "kb_wire_range_head", "kb_wire_range_tail", "kb_wire_watch_head",
+    "kb_get_batch", "kb_get_view_get",
     "kb_compact_sweep", "kb_compact_view_get",
     "kb_watch_add", "kb_watch_del", "kb_watch_count", "kb_watch_match", "kb_events_upload", "kb_events_free",
     "kb_watch_match_dev", "kb_match_view_get", "kb_result_free",
@@ -56,7 +58,7 @@ class KbRangeView(C.Structure):
     _fields_ = [("n_req", C.c_uint64), ("req_first", u64p), ("req_count", u64p), ("req_examined", u64p),
                 ("n_kvs", C.c_uint64), ("rec_idx", u32p), ("rev", u64p), ("key_off", u64p), ("key_len", u32p),
                 ("val_off", u64p), ("val_len", u32p), ("bytes", C.c_void_p), ("n_bytes", C.c_uint64),
-                ("on_device", C.c_int)]
+                ("on_device", C.c_int), ("elem_off", u64p), ("wire", C.c_int)]
 
 
 class KbWriteOp(C.Structure):
@@ -130,6 +132,12 @@ def lib():
     L.kb_range_batch.argtypes = [vp, C.POINTER(KbRangeReq), C.c_uint64, C.c_int, C.POINTER(vp)]
     L.kb_range_view_get.restype = C.c_int
     L.kb_range_view_get.argtypes = [vp, C.POINTER(KbRangeView)]
+    L.kb_wire_range_head.restype = C.c_uint64
+    L.kb_wire_range_head.argtypes = [C.c_uint64, u8p]
+    L.kb_wire_range_tail.restype = C.c_uint64
+    L.kb_wire_range_tail.argtypes = [C.c_int, C.c_int64, u8p]
+    L.kb_wire_watch_head.restype = C.c_uint64
+    L.kb_wire_watch_head.argtypes = [C.c_uint64, C.c_int, C.c_char_p, C.c_uint64, u8p]
     L.kb_get_batch.restype = C.c_int
     L.kb_get_batch.argtypes = [vp, C.POINTER(KbGetReq), C.c_uint64, C.c_int, C.POINTER(vp)]
     L.kb_get_view_get.restype = C.c_int
@@ -205,12 +213,16 @@ class RangeResult:
         self.n_bytes = int(v.n_bytes)
         self.on_device = bool(v.on_device)
         self.bytes_ptr = v.bytes
+        self.wire = int(v.wire)
         n = self.n_kvs
+        self.elem_off = None
         if self.on_device:
             # KB_OUT_DEVICE: the arena and the per-kv arrays stay in HBM (device pointers)
             self.arena = None
             self.rec_idx = self.rev = self.key_off = self.key_len = self.val_off = self.val_len = None
         else:
+            if self.wire:
+                self.elem_off = _np(v.elem_off, n + 1, np.uint64) if n else np.zeros(1, np.uint64)
             self.rec_idx = _np(v.rec_idx, n, np.uint32)
             self.rev = _np(v.rev, n, np.uint64)
             self.key_off = _np(v.key_off, n, np.uint64)
@@ -230,6 +242,14 @@ class RangeResult:
 
     def rec_indices(self, q: int = 0) -> np.ndarray:
         return self.rec_idx[int(self.req_first[q]) : int(self.req_first[q + 1])].copy()
+
+    def elements(self, q: int = 0, first: int = 0, count: Optional[int] = None) -> memoryview:
+        """wire modes: the protobuf elements [first, first+count) of request q, as one contiguous slice of the arena"""
+        assert self.wire and self.arena is not None
+        a, b = int(self.req_first[q]), int(self.req_first[q + 1])
+        lo = min(a + first, b)
+        hi = b if count is None else min(lo + count, b)
+        return memoryview(self.arena)[int(self.elem_off[lo]) : int(self.elem_off[hi])]
 
     def close(self):
         if self._h:
@@ -337,6 +357,17 @@ class MatchResult:
             pass
 
 
+class PackedRangeReqs:
+    """A kb_range_req[] built once; keeps the bound keys alive."""
+
+    def __init__(self, reqs: Sequence[Tuple[bytes, bytes, int, int]]):
+        self.n = len(reqs)
+        self._keep = list(reqs)
+        self.arr = (KbRangeReq * max(self.n, 1))()
+        for i, (s, e, rev, lim) in enumerate(self._keep):
+            self.arr[i] = KbRangeReq(s, len(s), e, len(e), rev, lim)
+
+
 class Engine:
     """A kb_ctx: one HBM-resident snapshot + watcher table on one GPU."""
 
@@ -389,13 +420,16 @@ class Engine:
         self._check(lib().kb_set_compact_revision(self._ctx, int(rev is not None), rev or 0))
 
     # ---- scans ----
-    def range_batch(self, reqs: Sequence[Tuple[bytes, bytes, int, int]], out_mode: int = KB_OUT_HOST) -> RangeResult:
-        """reqs: (start_internal_key, end_internal_key, read_rev, limit)"""
-        arr = (KbRangeReq * max(len(reqs), 1))()
-        for i, (s, e, rev, lim) in enumerate(reqs):
-            arr[i] = KbRangeReq(s, len(s), e, len(e), rev, lim)
+    @staticmethod
+    def pack_range_reqs(reqs: Sequence[Tuple[bytes, bytes, int, int]]) -> "PackedRangeReqs":
+        """marshal once what a C / cgo caller passes directly: a kb_range_req array (reusable across calls)"""
+        return PackedRangeReqs(reqs)
+
+    def range_batch(self, reqs, out_mode: int = KB_OUT_HOST) -> RangeResult:
+        """reqs: sequence of (start_internal_key, end_internal_key, read_rev, limit), or a PackedRangeReqs"""
+        pk = reqs if isinstance(reqs, PackedRangeReqs) else PackedRangeReqs(reqs)
         h = C.c_void_p()
-        self._check(lib().kb_range_batch(self._ctx, arr, len(reqs), out_mode, C.byref(h)))
+        self._check(lib().kb_range_batch(self._ctx, pk.arr, pk.n, out_mode, C.byref(h)))
         return RangeResult(self, h)
 
     def get_batch(self, reqs: Sequence[Tuple[bytes, int]], out_mode: int = KB_OUT_HOST) -> GetResult:

@@ -51,7 +51,9 @@ struct ScanMode {
     int      compact;      // workerConfig.compact
     int      ttl_scan;     // !SupportTTL() && timeoutRevision != 0
     uint64_t timeout_rev;
+    int      wire;         // 0: padded [key][value] arena; KB_WIRE_KVS_I / KB_WIRE_EVENTS_I: etcd protobuf elements
 };
+enum { KB_WIRE_NONE_I = 0, KB_WIRE_KVS_I = 1, KB_WIRE_EVENTS_I = 2 };
 
 // per-record meta word produced by the decode pass
 #define KB_M_LCP_MASK 0x0000FFFFu
@@ -207,6 +209,8 @@ struct kb_result {
     const uint32_t *rec_idx = nullptr;
     const uint64_t *rev = nullptr, *key_off = nullptr, *val_off = nullptr;
     const uint32_t *key_len = nullptr, *val_len = nullptr;
+    int wire = 0;                          // KB_WIRE_*_I
+    const uint64_t *elem_off = nullptr;    // wire modes: n_kvs + 1 element offsets into the arena
     // compact
     uint64_t n_victims = 0, count = 0, examined = 0;
     HBuf h_vic;

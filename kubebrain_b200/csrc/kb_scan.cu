@@ -20,6 +20,7 @@
 
 #include "kb_internal.cuh"
 #include "kb_decode.cuh"
+#include "kb_wire.cuh"
 
 namespace {
 
@@ -189,7 +190,7 @@ template <bool COMPACT>
 __global__ void __launch_bounds__(256)
 k_emit(StoreDev st, const ReqDev *__restrict__ reqs, const TileDev *__restrict__ tiles,
        const uint2 *__restrict__ sub_agg, const uint32_t *__restrict__ meta, uint32_t *__restrict__ tgt,
-       uint32_t *__restrict__ tail_tgt, uint64_t *__restrict__ tcnt)
+       uint32_t *__restrict__ tail_tgt, uint64_t *__restrict__ tcnt, int wire)
 {
     __shared__ LM warp_tot[8];
     __shared__ LM carry_s;
@@ -259,7 +260,7 @@ k_emit(StoreDev st, const ReqDev *__restrict__ reqs, const TileDev *__restrict__
                         } else {
                             t = x.L;
                             cnt++;
-                            aux += pad16(pkl) + pad16(st.vlen[prec]);
+                            aux += kv_resp_bytes(st, prec, wire);
                         }
                     }
                 } else if (COMPACT && !(pw & KB_M_REV0)) {
@@ -292,7 +293,7 @@ k_emit(StoreDev st, const ReqDev *__restrict__ reqs, const TileDev *__restrict__
                         const uint32_t prec = req.lo + (x.L - req.flat0);
                         tt = x.L;
                         cnt++;
-                        aux += pad16(st.klen[prec]) + pad16(st.vlen[prec]);
+                        aux += kv_resp_bytes(st, prec, wire);
                     }
                 }
             }
@@ -371,7 +372,7 @@ __global__ void __launch_bounds__(256)
 k_place(StoreDev st, const ReqDev *__restrict__ reqs, const TileDev *__restrict__ tiles,
         const uint32_t *__restrict__ tgt, const uint32_t *__restrict__ tail_tgt,
         const uint64_t *__restrict__ tscan, uint32_t *__restrict__ sel, uint64_t *__restrict__ slot,
-        ReqOut *__restrict__ rout)
+        ReqOut *__restrict__ rout, int wire)
 {
     __shared__ uint64_t ws2[18];
     const TileDev tile = tiles[blockIdx.x];
@@ -399,7 +400,7 @@ k_place(StoreDev st, const ReqDev *__restrict__ reqs, const TileDev *__restrict_
     for (int k = 0; k < 5; k++) {
         if (t[k] != KB_NONE) {
             const uint32_t prec = req.lo + (t[k] - req.flat0);
-            sz[k] = pad16(st.klen[prec]) + pad16(st.vlen[prec]);
+            sz[k] = (uint32_t)kv_resp_bytes(st, prec, wire);
             cnt++;
             bytes += sz[k];
         }
@@ -1028,11 +1029,11 @@ static int launch_scan_core(kb_ctx *ctx, const Resolved &R, const ScanMode &mode
         if (mode.compact) {
             KB_LAUNCH(ctx, "k_emit_compact", R.n_records * 8,
                       (k_emit<true><<<nt, 256, 0, ctx->stream>>>(ctx->st, d_reqs, d_tiles, d_agg, d_meta, d_tgt, d_tail,
-                                                                d_tcnt)));
+                                                                d_tcnt, 0)));
         } else {
             KB_LAUNCH(ctx, "k_emit", R.n_records * 8,
                       (k_emit<false><<<nt, 256, 0, ctx->stream>>>(ctx->st, d_reqs, d_tiles, d_agg, d_meta, d_tgt, d_tail,
-                                                                 d_tcnt)));
+                                                                 d_tcnt, mode.wire)));
         }
     }
     KB_LAUNCH(ctx, "k_tile_scan", (uint64_t)nt * 32,
@@ -1040,7 +1041,8 @@ static int launch_scan_core(kb_ctx *ctx, const Resolved &R, const ScanMode &mode
     if (nt && with_place) {
         KB_LAUNCH(ctx, "k_place", R.n_records * 4,
                   (k_place<<<nt, 256, 0, ctx->stream>>>(ctx->st, d_reqs, d_tiles, d_tgt, d_tail, d_tscan,
-                                                        (uint32_t *)ctx->d_sel.p, (uint64_t *)ctx->d_slot.p, d_rout)));
+                                                        (uint32_t *)ctx->d_sel.p, (uint64_t *)ctx->d_slot.p, d_rout,
+                                                        mode.wire)));
     }
     KB_CUDA(ctx, cudaGetLastError());
     return KB_OK;
@@ -1071,6 +1073,7 @@ static int probe_limit_windows(kb_ctx *ctx, Resolved &R)
     mode.compact = 0;
     mode.ttl_scan = 0;
     mode.timeout_rev = 0;
+    mode.wire = 0;
     while (!todo.empty()) {
         Resolved P;
         P.reqs.resize(todo.size());
@@ -1105,7 +1108,12 @@ static int probe_limit_windows(kb_ctx *ctx, Resolved &R)
 extern "C" int kb_range_batch(kb_ctx *ctx, const kb_range_req *reqs, uint64_t nreq, int out_mode, kb_result **out)
 {
     if (!ctx || !out || (nreq && !reqs)) return KB_EINVAL;
+    // wire modes: the arena holds etcd protobuf elements instead of padded [key][value] pairs (kb_wire.cuh)
+    const int wire_flags = out_mode & (KB_WIRE_ETCD_KVS | KB_WIRE_ETCD_EVENTS);
+    out_mode &= ~(KB_WIRE_ETCD_KVS | KB_WIRE_ETCD_EVENTS);
     if (out_mode != KB_OUT_HOST && out_mode != KB_OUT_DEVICE && out_mode != KB_OUT_COUNT) return KB_EINVAL;
+    if (wire_flags == (KB_WIRE_ETCD_KVS | KB_WIRE_ETCD_EVENTS) || (wire_flags && out_mode == KB_OUT_COUNT)) return KB_EINVAL;
+    const int wire = wire_flags == KB_WIRE_ETCD_KVS ? KB_WIRE_KVS_I : wire_flags == KB_WIRE_ETCD_EVENTS ? KB_WIRE_EVENTS_I : 0;
     *out = nullptr;
     std::lock_guard<std::mutex> g(ctx->mu);
     if (!ctx->loaded) return kb_fail(ctx, KB_ESTATE, "no store loaded");
@@ -1133,6 +1141,7 @@ extern "C" int kb_range_batch(kb_ctx *ctx, const kb_range_req *reqs, uint64_t nr
     mode.compact = 0;
     mode.ttl_scan = 0;
     mode.timeout_rev = 0;
+    mode.wire = wire;
     KB_TRY(launch_scan_core(ctx, R, mode, out_mode != KB_OUT_COUNT));
 
     // Response arena: sized by an upper bound the host knows without a round trip (all key+value bytes of the examined
@@ -1142,12 +1151,16 @@ extern "C" int kb_range_batch(kb_ctx *ctx, const kb_range_req *reqs, uint64_t nr
     uint64_t ub_bytes = 0;
     for (auto &r : R.reqs)
         ub_bytes += ((uint64_t)(ctx->h_koff16[r.hi] - ctx->h_koff16[r.lo]) + (ctx->h_voff16[r.hi] - ctx->h_voff16[r.lo])) * 16;
+    // a wire element is at most 48 bytes of tags / varints longer than its key + value (and the key loses 13)
+    if (wire) ub_bytes += (uint64_t)R.total_sel * 48;
     kb_result *res = kb_result_new(1, out_mode);
+    res->wire = wire;
     DBuf d_om;
     GatherOut go;
     memset(&go, 0, sizeof(go));
     const uint64_t cap_kvs = R.total_sel;
-    const size_t meta_cap = cap_kvs * 36 + 64;
+    uint64_t *d_elem_off = nullptr;
+    const size_t meta_cap = cap_kvs * (wire ? 44 : 36) + 64 + 8;
     int rc = KB_OK;
     if (want_kvs) {
         rc = pool_get_dev(ctx, meta_cap, &d_om);
@@ -1163,7 +1176,8 @@ extern "C" int kb_range_batch(kb_ctx *ctx, const kb_range_req *reqs, uint64_t nr
         go.rev = (uint64_t *)om;
         go.key_off = go.rev + cap_kvs;
         go.val_off = go.key_off + cap_kvs;
-        go.rec_idx = (uint32_t *)(go.val_off + cap_kvs);
+        d_elem_off = go.val_off + cap_kvs;  // wire modes only: cap_kvs + 1 entries
+        go.rec_idx = (uint32_t *)(wire ? d_elem_off + cap_kvs + 1 : d_elem_off);
         go.key_len = go.rec_idx + cap_kvs;
         go.val_len = go.key_len + cap_kvs;
         uint64_t *d_jobfirst = (uint64_t *)ctx->d_jobs.p, *d_arenabase = d_jobfirst + nreq + 1;
@@ -1171,6 +1185,31 @@ extern "C" int kb_range_batch(kb_ctx *ctx, const kb_range_req *reqs, uint64_t nr
         KB_LAUNCH(ctx, "k_req_finalize", nreq * 64,
                   (k_req_finalize<<<1, 256, 0, ctx->stream>>>(d_reqs, (uint32_t)nreq, d_rout, d_jobfirst, d_arenabase)));
         const unsigned jgrid = (unsigned)std::min<uint64_t>((cap_kvs + 255) / 256, 148 * 8);
+        if (wire) {
+            rc = dbuf_ensure(ctx, ctx->d_gjobs, std::max<uint64_t>(cap_kvs, 1) * sizeof(WireJob));
+            if (rc != KB_OK) {
+                pool_put_dev(ctx, d_om);
+                result_release_locked(ctx, res);
+                return rc;
+            }
+            WireOut wo;
+            wo.rec_idx = go.rec_idx;
+            wo.rev = go.rev;
+            wo.key_off = go.key_off;
+            wo.key_len = go.key_len;
+            wo.val_off = go.val_off;
+            wo.val_len = go.val_len;
+            wo.elem_off = d_elem_off;
+            WireJob *d_wj = (WireJob *)ctx->d_gjobs.p;
+            KB_LAUNCH(ctx, "k_wire_jobs", cap_kvs * 20,
+                      (k_wire_jobs<<<jgrid, 256, 0, ctx->stream>>>(ctx->st, d_reqs, (uint32_t)nreq, d_jobfirst, d_arenabase,
+                                                                  (const uint32_t *)ctx->d_sel.p,
+                                                                  (const uint64_t *)ctx->d_slot.p, wire, d_wj, wo)));
+            const unsigned wgrid = (unsigned)std::min<uint64_t>((cap_kvs + WIRE_WARPS - 1) / WIRE_WARPS, 148 * 8);
+            KB_LAUNCH(ctx, "k_wire_copy", 0,
+                      (k_wire_copy<<<wgrid, WIRE_WARPS * 32, 0, ctx->stream>>>(ctx->st, d_wj, d_jobfirst + nreq, wire,
+                                                                             (uint8_t *)res->d_bytes.p)));
+        } else {
         KB_LAUNCH(ctx, "k_gather_jobs", cap_kvs * 20,
                   (k_gather_jobs<<<jgrid, 256, 0, ctx->stream>>>(ctx->st, d_reqs, (uint32_t)nreq, d_jobfirst, d_arenabase,
                                                                 (const uint32_t *)ctx->d_sel.p,
@@ -1184,6 +1223,7 @@ extern "C" int kb_range_batch(kb_ctx *ctx, const kb_range_req *reqs, uint64_t nr
         KB_LAUNCH(ctx, "k_gather", 0,
                   (k_gather<<<ggrid, GATHER_WARPS * 32, gsmem, ctx->stream>>>(ctx->st, d_gj, d_jobfirst + nreq,
                                                                               (uint4 *)res->d_bytes.p)));
+        }
     }
     std::vector<ReqOut> rout(std::max<uint64_t>(nreq, 1));
     if (nreq) {
@@ -1224,23 +1264,24 @@ extern "C" int kb_range_batch(kb_ctx *ctx, const kb_range_req *reqs, uint64_t nr
     res->n_kvs = nk;
     res->n_bytes = nbytes;
     if (ctx->prof_on) {  // the gather's algorithmic bytes are only known now
-        int gi = prof_index(ctx, "k_gather");
+        int gi = prof_index(ctx, wire ? "k_wire_copy" : "k_gather");
         ctx->prof[gi].bytes += 2 * nbytes + nk * 40;
     }
 
     if (want_kvs && nk > 0) {
         if (out_mode == KB_OUT_HOST) {
             // per-kv arrays: six strided pieces of the capacity-sized device layout -> one compact host layout
-            rc = pool_get_host(ctx, nk * 36 + 64, &res->h_meta);
+            rc = pool_get_host(ctx, nk * 44 + 64 + 8, &res->h_meta);
             if (rc == KB_OK) rc = pool_get_host(ctx, nbytes + 16, &res->h_bytes);
             if (rc == KB_OK) {
                 uint8_t *hm = (uint8_t *)res->h_meta.p;
-                const void *srcs[6] = {go.rev, go.key_off, go.val_off, go.rec_idx, go.key_len, go.val_len};
-                const size_t esz[6] = {8, 8, 8, 4, 4, 4};
+                const void *srcs[7] = {go.rev, go.key_off, go.val_off, d_elem_off, go.rec_idx, go.key_len, go.val_len};
+                const size_t cnt[7] = {nk, nk, nk, wire ? nk + 1 : 0, nk, nk, nk};
+                const size_t esz[7] = {8, 8, 8, 8, 4, 4, 4};
                 size_t off = 0;
-                for (int i = 0; i < 6; i++) {
-                    cudaMemcpyAsync(hm + off, srcs[i], nk * esz[i], cudaMemcpyDeviceToHost, ctx->stream);
-                    off += nk * esz[i];
+                for (int i = 0; i < 7; i++) {
+                    if (cnt[i]) cudaMemcpyAsync(hm + off, srcs[i], cnt[i] * esz[i], cudaMemcpyDeviceToHost, ctx->stream);
+                    off += cnt[i] * esz[i];
                 }
                 cudaMemcpyAsync(res->h_bytes.p, res->d_bytes.p, nbytes, cudaMemcpyDeviceToHost, ctx->stream);
             }
@@ -1256,7 +1297,8 @@ extern "C" int kb_range_batch(kb_ctx *ctx, const kb_range_req *reqs, uint64_t nr
             res->rev = (const uint64_t *)hm;
             res->key_off = res->rev + nk;
             res->val_off = res->key_off + nk;
-            res->rec_idx = (const uint32_t *)(res->val_off + nk);
+            res->elem_off = wire ? res->val_off + nk : nullptr;
+            res->rec_idx = (const uint32_t *)(res->val_off + nk + (wire ? nk + 1 : 0));
             res->key_len = res->rec_idx + nk;
             res->val_len = res->key_len + nk;
             pool_put_dev(ctx, d_om);
@@ -1269,6 +1311,7 @@ extern "C" int kb_range_batch(kb_ctx *ctx, const kb_range_req *reqs, uint64_t nr
             res->rec_idx = go.rec_idx;
             res->key_len = go.key_len;
             res->val_len = go.val_len;
+            res->elem_off = wire ? d_elem_off : nullptr;
             res->d_vic = d_om;  // owned by the result (returned to the pool by kb_result_free)
         }
     } else {
@@ -1298,9 +1341,77 @@ extern "C" int kb_range_view_get(const kb_result *res, kb_range_view *v)
     v->val_off = res->val_off;
     v->val_len = res->val_len;
     v->n_bytes = res->n_bytes;
+    v->elem_off = res->elem_off;
+    v->wire = res->wire == KB_WIRE_KVS_I ? KB_WIRE_ETCD_KVS : res->wire == KB_WIRE_EVENTS_I ? KB_WIRE_ETCD_EVENTS : 0;
     v->on_device = res->out_mode == KB_OUT_DEVICE;
     v->bytes = res->out_mode == KB_OUT_DEVICE ? (const uint8_t *)res->d_bytes.p : (const uint8_t *)res->h_bytes.p;
     return KB_OK;
+}
+
+// ---- framing of the wire elements (host): etcdserverpb.ResponseHeader{revision} (pkg/server/etcd/kv.go:253-257) is
+// field 1 of both responses; a header with revision 0 is still emitted (non-nil message of length 0)
+static uint64_t host_put_varint(uint8_t *out, uint64_t v)
+{
+    uint64_t n = 0;
+    while (v >= 0x80) {
+        out[n++] = (uint8_t)(v | 0x80);
+        v >>= 7;
+    }
+    out[n++] = (uint8_t)v;
+    return n;
+}
+
+static uint64_t host_put_header(uint64_t header_rev, uint8_t *out)
+{
+    uint8_t body[12];
+    uint64_t nb = 0;
+    if (header_rev) {
+        body[nb++] = 0x18;  // ResponseHeader.revision = 3, varint
+        nb += host_put_varint(body + nb, header_rev);
+    }
+    uint64_t w = 0;
+    out[w++] = 0x0a;  // field 1, length-delimited
+    w += host_put_varint(out + w, nb);
+    memcpy(out + w, body, nb);
+    return w + nb;
+}
+
+extern "C" uint64_t kb_wire_range_head(uint64_t header_rev, uint8_t *out)
+{
+    return out ? host_put_header(header_rev, out) : 0;
+}
+
+extern "C" uint64_t kb_wire_range_tail(int more, int64_t count, uint8_t *out)
+{
+    if (!out) return 0;
+    uint64_t w = 0;
+    if (more) {  // RangeResponse.more = 3
+        out[w++] = 0x18;
+        out[w++] = 1;
+    }
+    if (count) {  // RangeResponse.count = 4
+        out[w++] = 0x20;
+        w += host_put_varint(out + w, (uint64_t)count);
+    }
+    return w;
+}
+
+extern "C" uint64_t kb_wire_watch_head(uint64_t header_rev, int canceled, const uint8_t *reason, uint64_t reason_len,
+                                       uint8_t *out)
+{
+    if (!out || (reason_len && !reason)) return 0;
+    uint64_t w = host_put_header(header_rev, out);
+    if (canceled) {  // WatchResponse.canceled = 4
+        out[w++] = 0x20;
+        out[w++] = 1;
+    }
+    if (reason_len) {  // WatchResponse.cancel_reason = 6
+        out[w++] = 0x32;
+        w += host_put_varint(out + w, reason_len);
+        memcpy(out + w, reason, reason_len);
+        w += reason_len;
+    }
+    return w;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1502,6 +1613,7 @@ extern "C" int kb_compact_sweep(kb_ctx *ctx, const uint8_t *start, uint64_t star
     mode.compact = 1;
     mode.ttl_scan = (!support_ttl && timeout_rev != 0) ? 1 : 0;
     mode.timeout_rev = timeout_rev;
+    mode.wire = 0;
     uint64_t kbytes = 0;
     {
         std::vector<uint32_t> &ko = host_koff16(ctx);
@@ -1511,7 +1623,7 @@ extern "C" int kb_compact_sweep(kb_ctx *ctx, const uint8_t *start, uint64_t star
         KB_TRY(launch_decode(ctx, nt, kbytes, mode, d_reqs, d_tiles, d_meta, d_agg));
         KB_LAUNCH(ctx, "k_emit_compact", R.n_records * 8,
                   (k_emit<true><<<nt, 256, 0, ctx->stream>>>(ctx->st, d_reqs, d_tiles, d_agg, d_meta, d_tgt, d_tail,
-                                                            d_tcnt)));
+                                                            d_tcnt, 0)));
     }
     KB_LAUNCH(ctx, "k_tile_scan", (uint64_t)nt * 32,
               (k_tile_scan<<<1, 256, 0, ctx->stream>>>(d_reqs, 1u, d_tcnt, d_tscan, nt, d_rout)));

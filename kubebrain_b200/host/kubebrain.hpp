@@ -232,6 +232,56 @@ class Scanner {  // scanner.Scanner
         return out;
     }
 
+    // The etcd-compatible answers, serialised: what backendShim.List (pkg/server/etcd/backendshim.go:269-282) hands to
+    // gRPC as an etcdserverpb.RangeResponse; the kv elements are written by the device, only head and tail are added here.
+    Bytes RangeResponseWire(const Bytes &start, const Bytes &end, uint64_t revision, int64_t limit, uint64_t headerRev,
+                            bool more)
+    {
+        kb_range_req rq{(const uint8_t *)start.data(), start.size(), (const uint8_t *)end.data(), end.size(), revision, limit};
+        kb_result *res = nullptr;
+        e_.Check(kb_range_batch(e_.ctx(), &rq, 1, KB_OUT_HOST | KB_WIRE_ETCD_KVS, &res));
+        kb_range_view v;
+        kb_range_view_get(res, &v);
+        uint8_t head[32], tail[32];
+        const uint64_t nh = kb_wire_range_head(headerRev, head);
+        const uint64_t nt = kb_wire_range_tail(more ? 1 : 0, (int64_t)v.n_kvs + (more ? 1 : 0), tail);
+        Bytes out((const char *)head, nh);
+        if (v.n_bytes) out.append((const char *)v.bytes, v.n_bytes);
+        out.append((const char *)tail, nt);
+        kb_result_free(e_.ctx(), res);
+        return out;
+    }
+
+    // ... and the range stream (backendshim.go:329-368): one serialised etcdserverpb.WatchResponse per 300-kv batch
+    // (header revision 0: forked receivers never get readRev, receiver.go:162-166), then the cancel message
+    std::vector<Bytes> RangeStreamWire(const Bytes &start, const Bytes &end, uint64_t revision)
+    {
+        std::vector<Bytes> out;
+        uint8_t head[64];
+        kb_range_req rq{(const uint8_t *)start.data(), start.size(), (const uint8_t *)end.data(), end.size(), revision, 0};
+        kb_result *res = nullptr;
+        std::string err;
+        int rc = kb_range_batch(e_.ctx(), &rq, 1, KB_OUT_HOST | KB_WIRE_ETCD_EVENTS, &res);
+        if (rc != KB_OK) {
+            err = kb_last_error(e_.ctx());
+        } else {
+            kb_range_view v;
+            kb_range_view_get(res, &v);
+            const uint64_t nh = kb_wire_watch_head(0, 0, nullptr, 0, head);
+            for (uint64_t i = 0; i < v.n_kvs; i += kRangeStreamBatch) {
+                const uint64_t j = std::min<uint64_t>(v.n_kvs, i + kRangeStreamBatch);
+                Bytes m((const char *)head, nh);
+                m.append((const char *)v.bytes + v.elem_off[i], v.elem_off[j] - v.elem_off[i]);
+                out.push_back(std::move(m));
+            }
+            kb_result_free(e_.ctx(), res);
+        }
+        std::vector<uint8_t> endm(64 + err.size());
+        const uint64_t ne = kb_wire_watch_head(revision, 1, (const uint8_t *)err.data(), err.size(), endm.data());
+        out.emplace_back((const char *)endm.data(), ne);
+        return out;
+    }
+
     int Count(const Bytes &start, const Bytes &end, uint64_t revision)
     {  // scanner.go:121-126
         kb_range_req rq{(const uint8_t *)start.data(), start.size(), (const uint8_t *)end.data(), end.size(), revision, 0};
@@ -244,7 +294,8 @@ class Scanner {  // scanner.Scanner
         return c;
     }
 
-    // scanner.go:129-145: 300-kv batches with More=true, then the end marker
+    // scanner.go:129-145: 300-kv batches with More=true, then the end marker.  The batches come from forked receivers
+    // whose readRev is never set (receiver.go:162-166): their header revision is 0 (Q7).
     std::vector<StreamRangeResponse> RangeStream(const Bytes &start, const Bytes &end, uint64_t revision)
     {
         std::vector<StreamRangeResponse> out;
@@ -254,7 +305,7 @@ class Scanner {  // scanner.Scanner
             auto kvs = Range(start, end, revision, 0);
             for (size_t i = 0; i < kvs.size(); i += kRangeStreamBatch) {
                 StreamRangeResponse r;
-                r.Revision = revision;
+                r.Revision = 0;
                 r.More = true;
                 r.Kvs.assign(kvs.begin() + i, kvs.begin() + std::min(kvs.size(), i + kRangeStreamBatch));
                 out.push_back(std::move(r));

@@ -57,14 +57,16 @@ class Scanner:
             res.close()
 
     def range_stream(self, start: bytes, end: bytes, revision: int) -> Iterator[StreamRangeResponse]:
-        """scanner.go:129-145: batches of 300 kvs with More=true, then the end marker (More=false)"""
+        """scanner.go:129-145: batches of 300 kvs with More=true, then the end marker (More=false).  Q7: the batches are
+        sent by *forked* receivers, and fork() does not copy readRev (receiver.go:162-166), so their header revision
+        is 0; only the end marker (getListStreamEnd, scanner.go:179-192) carries the read revision."""
         try:
             kvs = self.range(start, end, revision, 0)
         except Exception as e:  # getListStreamEnd carries the error text (scanner.go:179-192)
             yield StreamRangeResponse(revision, [], False, str(e))
             return
         for i in range(0, len(kvs), RANGE_STREAM_BATCH):
-            yield StreamRangeResponse(revision, kvs[i : i + RANGE_STREAM_BATCH], True)
+            yield StreamRangeResponse(0, kvs[i : i + RANGE_STREAM_BATCH], True)
         yield StreamRangeResponse(revision, [], False)
 
     def compact(self, start: bytes, end: bytes, revision: int, timeout_revision: int = 0,

@@ -347,3 +347,58 @@ def bench_scan(st: OracleStore, start: bytes, end: bytes, read_rev: int, limit: 
     n = lib().ko_bench_scan(C.byref(st.c), start, len(start), end, len(end), read_rev, limit, int(faithful),
                             threads, C.byref(ex), C.byref(cs))
     return int(n), int(ex.value), int(cs.value)
+
+
+# ---- etcd wire encoding (kb_oracle.h "etcd wire encoding") ---------------------------------------------
+WIRE_KVS, WIRE_EVENTS = 1, 2
+
+
+def _wire_sigs():
+    L = lib()
+    if getattr(L, "_wire_ready", False):
+        return L
+    L.ko_wire_elem_size.restype = C.c_uint64
+    L.ko_wire_elem_size.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_int]
+    L.ko_wire_encode.restype = C.c_uint64
+    L.ko_wire_encode.argtypes = [C.POINTER(KoStore), u64p, C.c_uint64, C.c_int, u8p, u64p]
+    L.ko_wire_range_head.restype = C.c_uint64
+    L.ko_wire_range_head.argtypes = [C.c_uint64, u8p]
+    L.ko_wire_range_tail.restype = C.c_uint64
+    L.ko_wire_range_tail.argtypes = [C.c_int, C.c_int64, u8p]
+    L.ko_wire_watch_head.restype = C.c_uint64
+    L.ko_wire_watch_head.argtypes = [C.c_uint64, C.c_int, C.c_char_p, C.c_uint64, u8p]
+    L._wire_ready = True
+    return L
+
+
+def wire_elem_size(uk_len: int, val_len: int, rev: int, mode: int) -> int:
+    return int(_wire_sigs().ko_wire_elem_size(uk_len, val_len, rev, mode))
+
+
+def wire_encode(st: OracleStore, rec: Sequence[int], mode: int) -> Tuple[bytes, np.ndarray]:
+    """the emitted records `rec` as consecutive repeated-field elements + n+1 element offsets"""
+    L = _wire_sigs()
+    r = np.ascontiguousarray(np.asarray(rec, dtype=np.uint64))
+    off = np.zeros(len(r) + 1, np.uint64)
+    total = int(L.ko_wire_encode(C.byref(st.c), _p64(r), len(r), mode, None, _p64(off)))
+    out = np.zeros(max(total, 1), np.uint8)
+    L.ko_wire_encode(C.byref(st.c), _p64(r), len(r), mode, _p8(out), _p64(off))
+    return out[:total].tobytes(), off
+
+
+def _wire_small(fn, *a) -> bytes:
+    buf = np.zeros(int(fn(*a, None)) + 1, np.uint8)
+    n = int(fn(*a, _p8(buf)))
+    return buf[:n].tobytes()
+
+
+def wire_range_head(header_rev: int) -> bytes:
+    return _wire_small(_wire_sigs().ko_wire_range_head, header_rev)
+
+
+def wire_range_tail(more: bool, count: int) -> bytes:
+    return _wire_small(_wire_sigs().ko_wire_range_tail, int(more), count)
+
+
+def wire_watch_head(header_rev: int, canceled: bool = False, reason: bytes = b"") -> bytes:
+    return _wire_small(_wire_sigs().ko_wire_watch_head, header_rev, int(canceled), reason, len(reason))

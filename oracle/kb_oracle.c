@@ -1036,3 +1036,148 @@ int64_t ko_bench_scan(const ko_store *s, const uint8_t *start, size_t slen, cons
     free(th);
     return emitted;
 }
+
+/* ============================================================================================
+ * etcd wire encoding (see kb_oracle.h): protobuf base-128 varints, length-delimited fields
+ * ============================================================================================ */
+static uint64_t varint_len(uint64_t v)
+{
+    uint64_t n = 1;
+    while (v >= 0x80) {
+        v >>= 7;
+        n++;
+    }
+    return n;
+}
+
+static uint64_t put_varint(uint8_t *out, uint64_t v)
+{
+    uint64_t n = 0;
+    while (v >= 0x80) {
+        if (out) out[n] = (uint8_t)(v | 0x80);
+        v >>= 7;
+        n++;
+    }
+    if (out) out[n] = (uint8_t)v;
+    return n + 1;
+}
+
+/* mvccpb.KeyValue{Key, Value, ModRevision} body (backendshim.go:427-436) */
+static uint64_t kv_body_size(uint64_t uk_len, uint64_t val_len, uint64_t rev)
+{
+    uint64_t n = 0;
+    if (uk_len) n += 1 + varint_len(uk_len) + uk_len;   /* field 1, bytes  */
+    if (rev) n += 1 + varint_len(rev);                  /* field 3, int64 (two's complement varint) */
+    if (val_len) n += 1 + varint_len(val_len) + val_len; /* field 5, bytes */
+    return n;
+}
+
+uint64_t ko_wire_elem_size(uint64_t uk_len, uint64_t val_len, uint64_t rev, int mode)
+{
+    const uint64_t body = kv_body_size(uk_len, val_len, rev);
+    const uint64_t kv = 1 + varint_len(body) + body; /* RangeResponse.kvs (2) / Event.kv (2): tag 0x12 */
+    if (mode == KO_WIRE_KVS) return kv;
+    return 1 + varint_len(kv) + kv; /* WatchResponse.events (11): tag 0x5a around Event{kv} */
+}
+
+uint64_t ko_wire_encode(const ko_store *s, const uint64_t *rec, uint64_t n, int mode, uint8_t *out,
+                        uint64_t *elem_off)
+{
+    uint64_t w = 0;
+    for (uint64_t i = 0; i < n; i++) {
+        const uint64_t r = rec[i];
+        const uint8_t *k = s->keys + s->koff[r];
+        const uint64_t kl = s->koff[r + 1] - s->koff[r], vl = s->voff[r + 1] - s->voff[r];
+        const uint8_t *v = s->vals + s->voff[r];
+        const uint64_t ul = kl - 13, rev = be64(k + kl - 8);
+        const uint64_t body = kv_body_size(ul, vl, rev);
+        if (elem_off) elem_off[i] = w;
+        if (mode == KO_WIRE_EVENTS) {
+            if (out) out[w] = 0x5a;
+            w += 1;
+            w += put_varint(out ? out + w : NULL, 1 + varint_len(body) + body);
+        }
+        if (out) out[w] = 0x12;
+        w += 1;
+        w += put_varint(out ? out + w : NULL, body);
+        if (ul) {
+            if (out) out[w] = 0x0a;
+            w += 1;
+            w += put_varint(out ? out + w : NULL, ul);
+            if (out) memcpy(out + w, k + 4, ul);
+            w += ul;
+        }
+        if (rev) {
+            if (out) out[w] = 0x18;
+            w += 1;
+            w += put_varint(out ? out + w : NULL, rev);
+        }
+        if (vl) {
+            if (out) out[w] = 0x2a;
+            w += 1;
+            w += put_varint(out ? out + w : NULL, vl);
+            if (out) memcpy(out + w, v, vl);
+            w += vl;
+        }
+    }
+    if (elem_off) elem_off[n] = w;
+    return w;
+}
+
+/* etcdserverpb.ResponseHeader{Revision} as field 1 of the enclosing response (kv.go:253-257 txnHeader); a header
+ * with revision 0 is still a non-nil message: tag + zero length */
+static uint64_t put_header(uint64_t header_rev, uint8_t *out)
+{
+    uint64_t w = 0;
+    const uint64_t body = header_rev ? 1 + varint_len(header_rev) : 0;
+    if (out) out[w] = 0x0a;
+    w += 1;
+    w += put_varint(out ? out + w : NULL, body);
+    if (header_rev) {
+        if (out) out[w] = 0x18;
+        w += 1;
+        w += put_varint(out ? out + w : NULL, header_rev);
+    }
+    return w;
+}
+
+uint64_t ko_wire_range_head(uint64_t header_rev, uint8_t *out) { return put_header(header_rev, out); }
+
+uint64_t ko_wire_range_tail(int more, int64_t count, uint8_t *out)
+{
+    uint64_t w = 0;
+    if (more) {
+        if (out) {
+            out[w] = 0x18;
+            out[w + 1] = 1;
+        }
+        w += 2;
+    }
+    if (count) {
+        if (out) out[w] = 0x20;
+        w += 1;
+        w += put_varint(out ? out + w : NULL, (uint64_t)count);
+    }
+    return w;
+}
+
+uint64_t ko_wire_watch_head(uint64_t header_rev, int canceled, const uint8_t *reason, uint64_t reason_len,
+                            uint8_t *out)
+{
+    uint64_t w = put_header(header_rev, out);
+    if (canceled) {
+        if (out) {
+            out[w] = 0x20;
+            out[w + 1] = 1;
+        }
+        w += 2;
+    }
+    if (reason_len) {
+        if (out) out[w] = 0x32;
+        w += 1;
+        w += put_varint(out ? out + w : NULL, reason_len);
+        if (out) memcpy(out + w, reason, reason_len);
+        w += reason_len;
+    }
+    return w;
+}

@@ -182,6 +182,30 @@ int ko_watch_register(const ko_ring *ring, const ko_events *ev, const uint8_t *p
 /* watch.go:102-117 catchUpEvents chunk sizes; returns number of chunks, sizes[] filled (cap entries) */
 uint64_t ko_catchup_chunks(uint64_t n_events, uint64_t *sizes, uint64_t cap);
 
+/* ---- etcd wire encoding of a scan answer ---------------------------------------
+ * The etcd-compatible server turns every emitted kv into mvccpb.KeyValue{Key, Value, ModRevision}
+ * (pkg/server/etcd/backendshim.go:427-436 kvToEtcdKv) inside etcdserverpb.RangeResponse.kvs (List,
+ * backendshim.go:269-282) or inside mvccpb.Event{Kv} of etcdserverpb.WatchResponse.events (range stream,
+ * backendshim.go:349-363).  The message schemas live in the absent dependency go.etcd.io/etcd/api/v3 v3.5.2
+ * (go.mod:28); their published field numbers are restated here and pinned in tests/test_wire.py against the
+ * protobuf runtime: KeyValue{key=1 bytes, create_revision=2, mod_revision=3, version=4, value=5 bytes, lease=6},
+ * Event{type=1, kv=2, prev_kv=3}, ResponseHeader{cluster_id=1, member_id=2, revision=3, raft_term=4},
+ * RangeResponse{header=1, kvs=2, more=3, count=4}, WatchResponse{header=1, watch_id=2, created=3, canceled=4,
+ * compact_revision=5, cancel_reason=6, fragment=7, events=11}.  proto3: zero / empty fields are not emitted,
+ * fields appear in field-number order. */
+enum { KO_WIRE_KVS = 1 /* RangeResponse.kvs element */, KO_WIRE_EVENTS = 2 /* WatchResponse.events element */ };
+/* bytes of one repeated-field element (tag + length + message) */
+uint64_t ko_wire_elem_size(uint64_t uk_len, uint64_t val_len, uint64_t rev, int mode);
+/* encode the records rec[0..n) of `s` (their user key, value and key revision) as consecutive elements;
+ * elem_off gets n+1 byte offsets; out may be NULL to size only.  Returns the total byte count. */
+uint64_t ko_wire_encode(const ko_store *s, const uint64_t *rec, uint64_t n, int mode, uint8_t *out,
+                        uint64_t *elem_off);
+/* message framing around the elements: each returns the byte count written to out (out may be NULL) */
+uint64_t ko_wire_range_head(uint64_t header_rev, uint8_t *out);               /* RangeResponse.header           */
+uint64_t ko_wire_range_tail(int more, int64_t count, uint8_t *out);           /* RangeResponse.more / .count    */
+uint64_t ko_wire_watch_head(uint64_t header_rev, int canceled, const uint8_t *reason, uint64_t reason_len,
+                            uint8_t *out);                                     /* WatchResponse fields 1..6      */
+
 /* ---- CPU-baseline timing variants (bench.py only) ------------------------------------------ */
 /* faithful=1 performs the per-record heap copies the badger iterator performs
  * (iter.go:85-92 KeyCopy/ValueCopy; scanner.go:441,495 call Val() twice). Returns emitted count. */

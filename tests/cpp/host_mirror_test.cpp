@@ -158,6 +158,27 @@ static void gpu_tests()
     CHECK(r.Kvs.size() == (size_t)inject - 1 && r.Kvs[3].Value == fmt("val", 3) && r.Kvs[4].Value == fmt("val", 4));
     be.Get(fmt(testKey, 4), 0, &gkv, &found);
     CHECK(!found);
+    // etcd wire path: one kv, bytes checked by hand against the protobuf encoding
+    //   RangeResponse{header{revision: 7}, kvs:[{key:"/registry/test/key/00000", mod_revision: R, value:"val/00000"}], count: 1}
+    {
+        kb::Scanner sc(eng);
+        const uint64_t R = 1700000001ull;
+        Bytes wire = sc.RangeResponseWire(c.EncodeObjectKey(fmt(testKey, 0), 0), c.EncodeObjectKey(fmt(testKey, 1), 0),
+                                          init + 2, 0, 7, false);
+        Bytes kvb;
+        kvb += "\x0a\x18" + fmt(testKey, 0);  // key = 1, 24 bytes
+        kvb += "\x18";                          // mod_revision = 3
+        for (uint64_t v = R; ; v >>= 7) {
+            if (v >= 0x80) kvb.push_back((char)(v | 0x80)); else { kvb.push_back((char)v); break; }
+        }
+        kvb += "\x2a\x09" + fmt("val", 0);      // value = 5, 9 bytes
+        Bytes exp = Bytes("\x0a\x02\x18\x07", 4) + "\x12" + Bytes(1, (char)kvb.size()) + kvb + Bytes("\x20\x01", 2);
+        CHECK(wire == exp);
+        auto msgs = sc.RangeStreamWire(c.EncodeObjectKey(testKey, 0), c.EncodeObjectKey(endKey, 0), init + 2);
+        CHECK(msgs.size() == 2);  // one batch (8 live keys) + the cancel message
+        CHECK(msgs[0].substr(0, 3) == Bytes("\x0a\x00\x5a", 3));
+        CHECK(msgs[1][0] == 0x0a && msgs[1].substr(msgs[1].size() - 2) == Bytes("\x20\x01", 2));
+    }
     std::printf("gpu ok\n");
 }
 
