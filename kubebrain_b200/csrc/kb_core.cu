@@ -247,7 +247,7 @@ extern "C" void kb_close(kb_ctx *ctx)
     DBuf *all[] = {&ctx->d_kslab, &ctx->d_koff16, &ctx->d_klen, &ctx->d_vslab, &ctx->d_voff16, &ctx->d_vlen,
                    &ctx->d_bounds, &ctx->d_bres, &ctx->d_reqs,
                    &ctx->d_meta, &ctx->d_tgt, &ctx->d_agg, &ctx->d_tcnt, &ctx->d_tscan, &ctx->d_reqout,
-                   &ctx->d_sel, &ctx->d_slot, &ctx->d_jobs, &ctx->d_gjobs, &ctx->d_flags, &ctx->d_cursor};
+                   &ctx->d_sel, &ctx->d_slot, &ctx->d_jobs, &ctx->d_gjobs, &ctx->d_flags, &ctx->d_cursor, &ctx->d_ctrs};
     for (DBuf *b : all) dfree(*b);
     for (auto &b : ctx->free_dev) cudaFree(b.p);
     for (auto &b : ctx->free_host) cudaFreeHost(b.p);
@@ -331,7 +331,7 @@ extern "C" int kb_load_sorted(kb_ctx *ctx, const uint8_t *keys, const uint64_t *
     std::vector<uint16_t> klen(n ? n : 1);
     std::vector<uint64_t> voff16(n + 1);
     std::vector<uint32_t> vlen(n ? n : 1);
-    uint64_t kacc = 0, vacc = 0;
+    uint64_t kacc = 0, vacc = 0, max_kv = 0;
     for (uint64_t i = 0; i < n; i++) {
         uint64_t kl = key_off[i + 1] - key_off[i], vl = val_off[i + 1] - val_off[i];
         if (kl > 65535) return kb_fail(ctx, KB_ELIMIT, "key %llu longer than 65535 bytes", (unsigned long long)i);
@@ -342,12 +342,14 @@ extern "C" int kb_load_sorted(kb_ctx *ctx, const uint8_t *keys, const uint64_t *
         vlen[i] = (uint32_t)vl;
         kacc += (kl + 15) / 16;
         vacc += (vl + 15) / 16;
+        max_kv = std::max<uint64_t>(max_kv, (kl + 15) / 16 + (vl + 15) / 16);
         if (kacc > 0xFFFFFFF0ull) return kb_fail(ctx, KB_ELIMIT, "key slab exceeds 64 GiB");
     }
     koff16[n] = (uint32_t)kacc;
     voff16[n] = vacc;
     ctx->key_bytes = kacc * 16;
     ctx->val_bytes = vacc * 16;
+    ctx->max_kv_chunks = (uint32_t)std::min<uint64_t>(max_kv, 0xFFFFFFFFu);
 
     KB_TRY(dbuf_ensure(ctx, ctx->d_kslab, kacc * 16 + 64));
     KB_TRY(dbuf_ensure(ctx, ctx->d_vslab, vacc * 16 + 16));

@@ -292,13 +292,19 @@ __device__ __forceinline__ void process_sub(const StoreDev &st, const ScanMode &
 
 __global__ void __launch_bounds__(DECODE_WARPS * 32, 1)
 k_decode_lcp(StoreDev st, const ReqDev *__restrict__ reqs, const TileDev *__restrict__ tiles, uint32_t n_sub,
-             ScanMode mode, uint32_t *__restrict__ meta, uint2 *__restrict__ sub_agg)
+             ScanMode mode, uint32_t *__restrict__ meta, uint2 *__restrict__ sub_agg, unsigned int *__restrict__ work_ctr)
 {
     extern __shared__ uint4 stage[];  // DECODE_WARPS x DECODE_STAGES x KB_WARP_STAGE_CHUNKS (+ 4 chunks of slack)
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint4 *buf0 = stage + (size_t)warp * DECODE_STAGES * KB_WARP_STAGE_CHUNKS;
+    // The first three sub-tiles of a warp are assigned statically (they fill the pipeline); the rest are handed out
+    // through a global counter (left at zero by k_emit, which follows every decode pass), so a CTA that starts late --
+    // its SM was still busy with another stream's kernel -- simply takes fewer.  The atomic is issued one step before
+    // its result is used: lane 0 keeps the raw value and the warp picks it up with a shuffle at the next step.
     const uint32_t stride = gridDim.x * DECODE_WARPS;
+    const uint32_t dyn_base = 3 * stride;
     uint32_t sid = blockIdx.x * DECODE_WARPS + warp;
+    uint32_t raw = 0;
 
     // one mbarrier per stage buffer; the phase of buffer b flips each time it is filled
     __shared__ uint64_t bars[DECODE_WARPS * DECODE_STAGES];
@@ -318,7 +324,7 @@ k_decode_lcp(StoreDev st, const ReqDev *__restrict__ reqs, const TileDev *__rest
     sid += stride;
     SubDesc dA = load_desc(st, tA, lane);
     tA = fetch_tile(tiles, sid, n_sub);
-    sid += stride;
+    if (lane == 0) raw = atomicAdd(work_ctr, 1u);
     issue_stage(st, mode, dB, buf0, bar0, lane);
     uint32_t fills0 = 0, fills1 = 0;  // completed-phase counters of the two buffers (parity = count & 1)
     // The body is unrolled six times (lcm of the 3 descriptor roles and the 2 stage buffers) so that the role
@@ -331,8 +337,9 @@ k_decode_lcp(StoreDev st, const ReqDev *__restrict__ reqs, const TileDev *__rest
                 const SubDesc dC = dB;  // key bytes + value probe in flight since the previous step
                 dB = dA;                // directory loaded one step ago
                 dA = load_desc(st, tA, lane);
+                sid = dyn_base + __shfl_sync(0xffffffffu, raw, 0);
                 tA = fetch_tile(tiles, sid, n_sub);
-                sid += stride;
+                if (lane == 0) raw = atomicAdd(work_ctr, 1u);
                 issue_stage(st, mode, dB, buf0 + ((u + 1) & 1) * KB_WARP_STAGE_CHUNKS, bar0 + ((u + 1) & 1), lane);
                 // wait for dC's bytes (only if a copy was issued for it: real, staged sub-tile)
                 if (dC.nrec != 0 && dC.span <= KB_WARP_STAGE_CHUNKS) {

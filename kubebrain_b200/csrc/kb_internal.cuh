@@ -161,6 +161,7 @@ struct kb_ctx {
     StoreDev st{};
     DBuf d_kslab, d_koff16, d_klen, d_vslab, d_voff16, d_vlen;
     uint64_t key_bytes = 0, val_bytes = 0;
+    uint32_t max_kv_chunks = 0;  // largest padded [key][value] pair, in 16-byte chunks: sizes the gather's ring buffers
     std::vector<uint32_t> h_koff16;  // host copies of the slab offsets: byte accounting and response-arena bounds
     std::vector<uint64_t> h_voff16;
     std::vector<uint16_t> h_klen;   // host copy of the whole record directory: kb_apply_batch rebuilds it on the host
@@ -170,7 +171,7 @@ struct kb_ctx {
 
     // scratch (grow only)
     DBuf d_bounds, d_bres, d_reqs, d_tiles /* alias into d_reqs */, d_meta, d_tgt, d_agg, d_tcnt, d_tscan, d_reqout,
-        d_sel, d_slot, d_jobs, d_gjobs, d_flags;
+        d_sel, d_slot, d_jobs, d_gjobs, d_flags, d_ctrs /* work-queue counters, kept at zero between kernels */;
     HBuf h_stage, h_stage2;
 
     // buffer pools for results

@@ -190,8 +190,9 @@ template <bool COMPACT>
 __global__ void __launch_bounds__(256)
 k_emit(StoreDev st, const ReqDev *__restrict__ reqs, const TileDev *__restrict__ tiles,
        const uint2 *__restrict__ sub_agg, const uint32_t *__restrict__ meta, uint32_t *__restrict__ tgt,
-       uint32_t *__restrict__ tail_tgt, uint64_t *__restrict__ tcnt, int wire)
+       uint32_t *__restrict__ tail_tgt, uint64_t *__restrict__ tcnt, int wire, unsigned int *__restrict__ decode_ctr)
 {
+    if (blockIdx.x == 0 && threadIdx.x == 0) *decode_ctr = 0;  // leave k_decode_lcp's work counter at zero
     __shared__ LM warp_tot[8];
     __shared__ LM carry_s;
     __shared__ uint64_t ws2[18];
@@ -548,9 +549,9 @@ k_gather_jobs(StoreDev st, const ReqDev *__restrict__ reqs, uint32_t nreq, const
 // moved in pieces.  The copy engine generates full-line requests; the SM only issues two or three instructions per
 // 2.5 KB piece.
 constexpr int GATHER_WARPS = 8;
-constexpr int GATHER_STAGES = 8;
-constexpr int GATHER_DIST = GATHER_STAGES - 2;   // pieces in flight per warp
-constexpr uint32_t GATHER_PIECE = 160;           // 16-byte chunks per buffer (2560 B)
+constexpr int GATHER_MAX_STAGES = 8;
+constexpr uint32_t GATHER_MAX_PIECE = 160;       // 16-byte chunks per buffer (2560 B)
+constexpr uint32_t GATHER_WARP_CHUNKS = 880;     // shared memory per warp (13.75 KiB): two CTAs of 8 warps per SM
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -569,54 +570,68 @@ __device__ __forceinline__ void mbar_wait_parity(uint64_t *bar, uint32_t parity)
         : "memory");
 }
 
-__global__ void __launch_bounds__(GATHER_WARPS * 32, 1)
+// `piece` (chunks per ring buffer) and `stages` (buffers per warp) are chosen by the host from the store's largest
+// [key][value] pair so that a typical kv is exactly one piece and two CTAs fit per SM.  Blocks of 32 jobs are handed
+// out through a global counter (zeroed by the kernel that builds the jobs), so a CTA that starts late -- the SM was
+// still busy with another stream's kernel -- simply takes fewer blocks.
+__global__ void __launch_bounds__(GATHER_WARPS * 32, 2)
 k_gather(StoreDev st, const GatherJob *__restrict__ jobs, const uint64_t *__restrict__ n_kvs_dev,
-         uint4 *__restrict__ arena)
+         uint4 *__restrict__ arena, uint32_t piece, uint32_t stages, unsigned long long *__restrict__ work_ctr)
 {
-    extern __shared__ __align__(128) uint4 gbuf[];  // GATHER_WARPS x GATHER_STAGES x GATHER_PIECE
-    __shared__ uint64_t bars[GATHER_WARPS * GATHER_STAGES];
-    __shared__ uint64_t ring_dst[GATHER_WARPS * GATHER_STAGES];
-    __shared__ uint32_t ring_len[GATHER_WARPS * GATHER_STAGES];
+    extern __shared__ __align__(128) uint4 gbuf[];  // GATHER_WARPS x stages x piece
+    __shared__ uint64_t bars[GATHER_WARPS * GATHER_MAX_STAGES];
+    __shared__ uint64_t ring_dst[GATHER_WARPS * GATHER_MAX_STAGES];
+    __shared__ uint32_t ring_len[GATHER_WARPS * GATHER_MAX_STAGES];
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // Lane 0 drives the copies (the data never passes through registers); the other lanes only help to fetch the
     // job descriptors: 32 jobs per coalesced load, handed to lane 0 by shuffles, next block prefetched.
-    uint4 *buf = gbuf + (size_t)warp * GATHER_STAGES * GATHER_PIECE;
-    uint64_t *bar = bars + warp * GATHER_STAGES;
-    uint64_t *rdst = ring_dst + warp * GATHER_STAGES;
-    uint32_t *rlen = ring_len + warp * GATHER_STAGES;
+    uint4 *buf = gbuf + (size_t)warp * stages * piece;
+    uint64_t *bar = bars + warp * GATHER_MAX_STAGES;
+    uint64_t *rdst = ring_dst + warp * GATHER_MAX_STAGES;
+    uint32_t *rlen = ring_len + warp * GATHER_MAX_STAGES;
     if (lane == 0) {
-        for (int s = 0; s < GATHER_STAGES; s++)
+        for (uint32_t s = 0; s < stages; s++)
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar + s)));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
 
     const uint64_t n_kvs = *n_kvs_dev;
-    const uint64_t nwarps = (uint64_t)gridDim.x * GATHER_WARPS;
-    uint32_t t_issue = 0, t_store = 0;  // pieces issued / stored by this warp (lane 0 only)
+    const uint32_t dist = stages - 2;   // pieces in flight per warp
+    uint32_t in_flight = 0;             // pieces issued and not yet stored (lane 0 only)
+    uint32_t si = 0, ss = 0, ph = 0;    // issue slot, store slot, parity of the store slot's current fill
 
     // wait for the oldest in-flight piece and send it to the arena
     auto retire = [&]() {
-        const uint32_t st_i = t_store % GATHER_STAGES;
-        mbar_wait_parity(bar + st_i, (t_store / GATHER_STAGES) & 1);
-        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(arena + rdst[st_i]),
-                     "r"(smem_u32(buf + st_i * GATHER_PIECE)), "r"(rlen[st_i] * 16)
+        mbar_wait_parity(bar + ss, ph);
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(arena + rdst[ss]),
+                     "r"(smem_u32(buf + ss * piece)), "r"(rlen[ss] * 16)
                      : "memory");
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        t_store++;
+        if (++ss == stages) {
+            ss = 0;
+            ph ^= 1;
+        }
+        in_flight--;
+    };
+    auto grab = [&]() -> uint64_t {  // next block of 32 jobs
+        unsigned long long b = 0;
+        if (lane == 0) b = atomicAdd(work_ctr, 32ull);
+        const uint32_t lo = __shfl_sync(0xffffffffu, (uint32_t)b, 0), hi = __shfl_sync(0xffffffffu, (uint32_t)(b >> 32), 0);
+        return ((uint64_t)hi << 32) | lo;
     };
 
     const uint4 zero4 = make_uint4(0, 0, 0, 0);
-    uint64_t base = ((uint64_t)blockIdx.x * GATHER_WARPS + warp) * 32;
+    uint64_t base = grab();
     uint4 n0 = zero4, n1 = zero4;  // this lane's job of the NEXT block (prefetched)
     if (base + lane < n_kvs) {
         const uint4 *jp = (const uint4 *)(jobs + base + lane);
         n0 = __ldg(jp);
         n1 = __ldg(jp + 1);
     }
-    for (; base < n_kvs; base += nwarps * 32) {
+    while (base < n_kvs) {
         const uint4 c0j = n0, c1j = n1;
-        const uint64_t nb = base + nwarps * 32;
+        const uint64_t nb = grab();
         n0 = n1 = zero4;
         if (nb + lane < n_kvs) {
             const uint4 *jp = (const uint4 *)(jobs + nb + lane);
@@ -633,44 +648,54 @@ k_gather(StoreDev st, const GatherJob *__restrict__ jobs, const uint64_t *__rest
             if (lane == 0) {
                 const uint64_t dst16 = ((uint64_t)d_hi << 32) | d_lo, vsrc16 = ((uint64_t)v_hi << 32) | v_lo;
                 const uint32_t n = nk + nv;
-                for (uint32_t c0 = 0; c0 < n; c0 += GATHER_PIECE) {
-                    const uint32_t len = min(GATHER_PIECE, n - c0);
-                    if (t_issue - t_store >= (uint32_t)GATHER_DIST) retire();
-                    const uint32_t st_i = t_issue % GATHER_STAGES;
-                    // the buffer was last read by the bulk store of piece t_issue - STAGES; at most two younger store
-                    // groups can still be pending when it has finished reading shared memory
+                for (uint32_t c0 = 0; c0 < n; c0 += piece) {
+                    const uint32_t len = min(piece, n - c0);
+                    if (in_flight >= dist) retire();
+                    // the buffer was last read by the bulk store of the piece `stages` issues ago; at most two younger
+                    // store groups can still be pending when it has finished reading shared memory
                     asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory");
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar + st_i)),
+                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar + si)),
                                  "r"(len * 16)
                                  : "memory");
-                    uint4 *dstbuf = buf + st_i * GATHER_PIECE;
+                    uint4 *dstbuf = buf + si * piece;
                     const uint32_t kpart = c0 < nk ? min(nk - c0, len) : 0;  // chunks of this piece from the key
                     if (kpart)
                         asm volatile(
                             "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                                 smem_u32(dstbuf)),
-                            "l"(st.kslab + ksrc16 + c0), "r"(kpart * 16), "r"(smem_u32(bar + st_i))
+                            "l"(st.kslab + ksrc16 + c0), "r"(kpart * 16), "r"(smem_u32(bar + si))
                             : "memory");
                     if (len > kpart) {
                         const uint32_t v0c = (c0 + kpart) - nk;  // first value chunk of this piece
                         asm volatile(
                             "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                                 smem_u32(dstbuf + kpart)),
-                            "l"(st.vslab + vsrc16 + v0c), "r"((len - kpart) * 16), "r"(smem_u32(bar + st_i))
+                            "l"(st.vslab + vsrc16 + v0c), "r"((len - kpart) * 16), "r"(smem_u32(bar + si))
                             : "memory");
                     }
-                    rdst[st_i] = dst16 + c0;
-                    rlen[st_i] = len;
-                    t_issue++;
+                    rdst[si] = dst16 + c0;
+                    rlen[si] = len;
+                    if (++si == stages) si = 0;
+                    in_flight++;
                 }
             }
         }
+        base = nb;
     }
     if (lane == 0) {
-        while (t_store < t_issue) retire();
+        while (in_flight) retire();
         asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
+}
+
+// ring geometry for a store whose largest padded [key][value] pair is `max_kv_chunks`
+static inline void gather_geometry(uint32_t max_kv_chunks, uint32_t *piece, uint32_t *stages)
+{
+    uint32_t p = std::min<uint32_t>(std::max<uint32_t>(max_kv_chunks, 32), GATHER_MAX_PIECE);
+    uint32_t s = std::min<uint32_t>(std::max<uint32_t>(GATHER_WARP_CHUNKS / p, 3), GATHER_MAX_STAGES);
+    *piece = p;
+    *stages = s;
 }
 
 // ---- k_get_resolve: one warp per point read.  cand = (first record > EncodeObjectKey(key, revision)) - 1 is what the
@@ -785,8 +810,10 @@ k_seg_copy(const uint4 *__restrict__ srcA, const uint4 *__restrict__ srcB, const
 // requests: job_first[q] = first kv of request q, arena_base[q] = first arena byte of request q; [nreq] = totals
 __global__ void __launch_bounds__(256)
 k_req_finalize(const ReqDev *__restrict__ reqs, uint32_t nreq, const ReqOut *__restrict__ rout,
-               uint64_t *__restrict__ job_first, uint64_t *__restrict__ arena_base)
+               uint64_t *__restrict__ job_first, uint64_t *__restrict__ arena_base,
+               unsigned long long *__restrict__ work_ctr)
 {
+    if (threadIdx.x == 0) *work_ctr = 0;  // the gather's block counter
     __shared__ uint64_t ws2[18];
     __shared__ uint64_t carry[2];
     if (threadIdx.x == 0) carry[0] = carry[1] = 0;
@@ -998,11 +1025,35 @@ static int launch_decode(kb_ctx *ctx, uint32_t ntiles, uint64_t alg_bytes, const
         KB_CUDA(ctx, cudaFuncSetAttribute(k_decode_lcp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         ctx->decode_attr_set = true;
     }
+    if (!ctx->d_ctrs.p) {  // work counters: zero once, every consumer leaves them at zero
+        KB_TRY(dbuf_ensure(ctx, ctx->d_ctrs, 256));
+        KB_CUDA(ctx, cudaMemsetAsync(ctx->d_ctrs.p, 0, 256, ctx->stream));
+    }
     const uint32_t n_sub = ntiles * 32;
     const uint32_t grid = std::min<uint32_t>((n_sub + DECODE_WARPS - 1) / DECODE_WARPS, 148);
     KB_LAUNCH(ctx, "k_decode_lcp", alg_bytes,
               (k_decode_lcp<<<grid, DECODE_WARPS * 32, smem, ctx->stream>>>(ctx->st, d_reqs, d_tiles, n_sub, mode, d_meta,
-                                                                          d_agg)));
+                                                                          d_agg, (unsigned int *)ctx->d_ctrs.p)));
+    return KB_OK;
+}
+
+// bulk-TMA gather of `n_jobs` (upper bound) copy jobs into `arena`
+static int launch_gather(kb_ctx *ctx, const GatherJob *d_jobs, const uint64_t *d_njobs, unsigned long long *d_ctr,
+                         uint4 *arena, uint64_t n_jobs, uint64_t alg_bytes)
+{
+    uint32_t piece, stages;
+    gather_geometry(ctx->max_kv_chunks, &piece, &stages);
+    const size_t gsmem = (size_t)GATHER_WARPS * stages * piece * 16;
+    if (!ctx->gather_attr_set) {
+        KB_CUDA(ctx, cudaFuncSetAttribute(k_gather, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)(GATHER_WARPS * GATHER_WARP_CHUNKS * 16)));
+        ctx->gather_attr_set = true;
+    }
+    const unsigned ggrid =
+        (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((n_jobs + GATHER_WARPS * 32 - 1) / (GATHER_WARPS * 32), 2 * 148));
+    KB_LAUNCH(ctx, "k_gather", alg_bytes,
+              (k_gather<<<ggrid, GATHER_WARPS * 32, gsmem, ctx->stream>>>(ctx->st, d_jobs, d_njobs, arena, piece, stages,
+                                                                          d_ctr)));
     return KB_OK;
 }
 
@@ -1029,11 +1080,11 @@ static int launch_scan_core(kb_ctx *ctx, const Resolved &R, const ScanMode &mode
         if (mode.compact) {
             KB_LAUNCH(ctx, "k_emit_compact", R.n_records * 8,
                       (k_emit<true><<<nt, 256, 0, ctx->stream>>>(ctx->st, d_reqs, d_tiles, d_agg, d_meta, d_tgt, d_tail,
-                                                                d_tcnt, 0)));
+                                                                d_tcnt, 0, (unsigned int *)ctx->d_ctrs.p)));
         } else {
             KB_LAUNCH(ctx, "k_emit", R.n_records * 8,
                       (k_emit<false><<<nt, 256, 0, ctx->stream>>>(ctx->st, d_reqs, d_tiles, d_agg, d_meta, d_tgt, d_tail,
-                                                                 d_tcnt, mode.wire)));
+                                                                 d_tcnt, mode.wire, (unsigned int *)ctx->d_ctrs.p)));
         }
     }
     KB_LAUNCH(ctx, "k_tile_scan", (uint64_t)nt * 32,
@@ -1165,7 +1216,7 @@ extern "C" int kb_range_batch(kb_ctx *ctx, const kb_range_req *reqs, uint64_t nr
     if (want_kvs) {
         rc = pool_get_dev(ctx, meta_cap, &d_om);
         if (rc == KB_OK) rc = pool_get_dev(ctx, ub_bytes + 64, &res->d_bytes);
-        if (rc == KB_OK) rc = dbuf_ensure(ctx, ctx->d_jobs, (nreq + 1) * 16);
+        if (rc == KB_OK) rc = dbuf_ensure(ctx, ctx->d_jobs, (nreq + 1) * 16 + 8);
         if (rc == KB_OK) rc = dbuf_ensure(ctx, ctx->d_gjobs, std::max<uint64_t>(cap_kvs, 1) * sizeof(GatherJob));
         if (rc != KB_OK) {
             pool_put_dev(ctx, d_om);
@@ -1181,9 +1232,11 @@ extern "C" int kb_range_batch(kb_ctx *ctx, const kb_range_req *reqs, uint64_t nr
         go.key_len = go.rec_idx + cap_kvs;
         go.val_len = go.key_len + cap_kvs;
         uint64_t *d_jobfirst = (uint64_t *)ctx->d_jobs.p, *d_arenabase = d_jobfirst + nreq + 1;
+        unsigned long long *d_workctr = (unsigned long long *)(d_arenabase + nreq + 1);  // zeroed by k_req_finalize
         GatherJob *d_gj = (GatherJob *)ctx->d_gjobs.p;
         KB_LAUNCH(ctx, "k_req_finalize", nreq * 64,
-                  (k_req_finalize<<<1, 256, 0, ctx->stream>>>(d_reqs, (uint32_t)nreq, d_rout, d_jobfirst, d_arenabase)));
+                  (k_req_finalize<<<1, 256, 0, ctx->stream>>>(d_reqs, (uint32_t)nreq, d_rout, d_jobfirst, d_arenabase,
+                                                              d_workctr)));
         const unsigned jgrid = (unsigned)std::min<uint64_t>((cap_kvs + 255) / 256, 148 * 8);
         if (wire) {
             rc = dbuf_ensure(ctx, ctx->d_gjobs, std::max<uint64_t>(cap_kvs, 1) * sizeof(WireJob));
@@ -1214,15 +1267,7 @@ extern "C" int kb_range_batch(kb_ctx *ctx, const kb_range_req *reqs, uint64_t nr
                   (k_gather_jobs<<<jgrid, 256, 0, ctx->stream>>>(ctx->st, d_reqs, (uint32_t)nreq, d_jobfirst, d_arenabase,
                                                                 (const uint32_t *)ctx->d_sel.p,
                                                                 (const uint64_t *)ctx->d_slot.p, d_gj, go)));
-        const size_t gsmem = (size_t)GATHER_WARPS * GATHER_STAGES * GATHER_PIECE * 16;
-        if (!ctx->gather_attr_set) {
-            cudaFuncSetAttribute(k_gather, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem);
-            ctx->gather_attr_set = true;
-        }
-        const unsigned ggrid = (unsigned)std::min<uint64_t>((cap_kvs + GATHER_WARPS - 1) / GATHER_WARPS, 148);
-        KB_LAUNCH(ctx, "k_gather", 0,
-                  (k_gather<<<ggrid, GATHER_WARPS * 32, gsmem, ctx->stream>>>(ctx->st, d_gj, d_jobfirst + nreq,
-                                                                              (uint4 *)res->d_bytes.p)));
+        KB_TRY(launch_gather(ctx, d_gj, d_jobfirst + nreq, d_workctr, (uint4 *)res->d_bytes.p, cap_kvs, 0));
         }
     }
     std::vector<ReqOut> rout(std::max<uint64_t>(nreq, 1));
@@ -1529,15 +1574,16 @@ extern "C" int kb_get_batch(kb_ctx *ctx, const kb_get_req *reqs, uint64_t n, int
         }
         uint8_t *hj = (uint8_t *)ctx->h_stage2.p;
         memcpy(hj, &nj, 8);
+        memset(hj + 8, 0, 8);  // the gather's block counter
         memcpy(hj + 64, jobs.data(), nj * sizeof(GatherJob));
-        cudaMemcpyAsync(ctx->d_jobs.p, hj, 8, cudaMemcpyHostToDevice, ctx->stream);
+        cudaMemcpyAsync(ctx->d_jobs.p, hj, 16, cudaMemcpyHostToDevice, ctx->stream);
         cudaMemcpyAsync(ctx->d_gjobs.p, hj + 64, nj * sizeof(GatherJob), cudaMemcpyHostToDevice, ctx->stream);
-        const size_t gsmem = (size_t)GATHER_WARPS * GATHER_STAGES * GATHER_PIECE * 16;
-        cudaFuncSetAttribute(k_gather, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem);
-        const unsigned ggrid = (unsigned)std::min<uint64_t>((nj + GATHER_WARPS * 32 - 1) / (GATHER_WARPS * 32), 148);
-        KB_LAUNCH(ctx, "k_gather", 2 * nbytes,
-                  (k_gather<<<std::max(ggrid, 1u), GATHER_WARPS * 32, gsmem, ctx->stream>>>(
-                      ctx->st, (const GatherJob *)ctx->d_gjobs.p, (const uint64_t *)ctx->d_jobs.p, (uint4 *)res->d_bytes.p)));
+        rc = launch_gather(ctx, (const GatherJob *)ctx->d_gjobs.p, (const uint64_t *)ctx->d_jobs.p,
+                           (unsigned long long *)ctx->d_jobs.p + 1, (uint4 *)res->d_bytes.p, nj, 2 * nbytes);
+        if (rc != KB_OK) {
+            result_release_locked(ctx, res);
+            return rc;
+        }
         if (out_mode == KB_OUT_HOST) {
             rc = pool_get_host(ctx, nbytes + 16, &res->h_bytes);
             if (rc == KB_OK) cudaMemcpyAsync(res->h_bytes.p, res->d_bytes.p, nbytes, cudaMemcpyDeviceToHost, ctx->stream);
@@ -1623,7 +1669,7 @@ extern "C" int kb_compact_sweep(kb_ctx *ctx, const uint8_t *start, uint64_t star
         KB_TRY(launch_decode(ctx, nt, kbytes, mode, d_reqs, d_tiles, d_meta, d_agg));
         KB_LAUNCH(ctx, "k_emit_compact", R.n_records * 8,
                   (k_emit<true><<<nt, 256, 0, ctx->stream>>>(ctx->st, d_reqs, d_tiles, d_agg, d_meta, d_tgt, d_tail,
-                                                            d_tcnt, 0)));
+                                                            d_tcnt, 0, (unsigned int *)ctx->d_ctrs.p)));
     }
     KB_LAUNCH(ctx, "k_tile_scan", (uint64_t)nt * 32,
               (k_tile_scan<<<1, 256, 0, ctx->stream>>>(d_reqs, 1u, d_tcnt, d_tscan, nt, d_rout)));
@@ -1832,6 +1878,7 @@ extern "C" int kb_apply_batch(kb_ctx *ctx, const kb_write_op *ops, uint64_t n_op
             const uint64_t nk = (m[i].key.size() + 15) / 16, nv = (m[i].val.size() + 15) / 16;
             push_pieces(kp, op_k16[i], kacc, nk, 1);
             push_pieces(vp, op_v16[i], vacc, nv, 1);
+            ctx->max_kv_chunks = std::max<uint32_t>(ctx->max_kv_chunks, (uint32_t)std::min<uint64_t>(nk + nv, 0xFFFFFFFFu));
             koff2[w] = (uint32_t)kacc;
             voff2[w] = vacc;
             klen2[w] = (uint16_t)m[i].key.size();
