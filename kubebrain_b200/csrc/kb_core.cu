@@ -244,7 +244,7 @@ extern "C" void kb_close(kb_ctx *ctx)
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     watch_tables_free(ctx);
-    DBuf *all[] = {&ctx->d_kslab, &ctx->d_koff16, &ctx->d_klen, &ctx->d_vslab, &ctx->d_voff16, &ctx->d_vlen,
+    DBuf *all[] = {&ctx->d_kslab, &ctx->d_koff16, &ctx->d_klen, &ctx->d_vslab, &ctx->d_voff16, &ctx->d_vlen, &ctx->d_dir,
                    &ctx->d_bounds, &ctx->d_bres, &ctx->d_reqs,
                    &ctx->d_meta, &ctx->d_tgt, &ctx->d_agg, &ctx->d_tcnt, &ctx->d_tscan, &ctx->d_reqout,
                    &ctx->d_sel, &ctx->d_slot, &ctx->d_jobs, &ctx->d_gjobs, &ctx->d_flags, &ctx->d_cursor, &ctx->d_ctrs};
@@ -315,6 +315,27 @@ __global__ void k_check_sorted(StoreDev st, uint32_t *bad)
         }
     }
     if (!less) atomicMin(bad, i);
+}
+
+__global__ void __launch_bounds__(256) k_pack_dir(StoreDev st, uint4 *__restrict__ dir)
+{
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= st.n) return;
+    const uint64_t vo = st.voff16[r];
+    dir[r] = make_uint4(st.koff16[r], (uint32_t)st.klen[r] | ((uint32_t)(vo >> 32) << 16), st.vlen[r], (uint32_t)vo);
+}
+
+int store_pack_dir(kb_ctx *ctx)
+{
+    const uint64_t n = ctx->st.n;
+    // value offsets are 16-byte units: 48 bits cover 4 PiB
+    KB_TRY(dbuf_ensure(ctx, ctx->d_dir, (n + 1) * 16));
+    ctx->st.dir = (const uint4 *)ctx->d_dir.p;
+    if (n) {
+        k_pack_dir<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->st, (uint4 *)ctx->d_dir.p);
+        KB_CUDA(ctx, cudaGetLastError());
+    }
+    return KB_OK;
 }
 
 extern "C" int kb_load_sorted(kb_ctx *ctx, const uint8_t *keys, const uint64_t *key_off, const uint8_t *vals,
@@ -425,6 +446,7 @@ extern "C" int kb_load_sorted(kb_ctx *ctx, const uint8_t *keys, const uint64_t *
     ctx->st.voff16 = (const uint64_t *)ctx->d_voff16.p;
     ctx->st.vlen = (const uint32_t *)ctx->d_vlen.p;
     ctx->st.n = (uint32_t)n;
+    KB_TRY(store_pack_dir(ctx));
     ctx->h_koff16 = koff16;
     ctx->h_voff16 = voff16;
     ctx->h_klen = klen;

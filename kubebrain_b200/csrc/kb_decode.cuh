@@ -47,6 +47,15 @@ __device__ __forceinline__ void dmbar_wait(uint64_t *bar, uint32_t parity)
         : "memory");
 }
 
+// one plain atomic by the calling lane.  Written in PTX because nvcc turns `if (lane == 0) atomicAdd(...)` into its
+// warp-aggregated form, whose result broadcast (SHFL) waits for the atomic at once and defeats issuing it a step early.
+__device__ __forceinline__ uint32_t atom_add_u32_raw(unsigned int *p, uint32_t v)
+{
+    uint32_t r;
+    asm volatile("atom.global.add.u32 %0, [%1], %2;" : "=r"(r) : "l"(p), "r"(v));
+    return r;
+}
+
 __device__ __forceinline__ bool contains_events(const uint8_t *uk, uint32_t n)  // bytes.Contains(rawKey, "/events/")
 {
     uint64_t w = 0;
@@ -120,16 +129,18 @@ __device__ __forceinline__ SubDesc load_desc(const StoreDev &st, const TileRef &
     d.nrec = min(32u, tr.t.n - sub * 32);
     d.lo = tr.t.lo;
     d.read_rev = tr.t.read_rev;
+    // one 16-byte packed directory entry per record (a single long-latency load per lane, see StoreDev::dir)
     if (lane < d.nrec) {
-        const uint32_t r = d.r0 + lane;
-        d.ko = st.koff16[r];
-        d.kl = st.klen[r];
-        d.vl = st.vlen[r];
-        d.vo = st.voff16[r];
+        const uint4 e = __ldg(st.dir + d.r0 + lane);
+        d.ko = e.x;
+        d.kl = e.y & 0xffffu;
+        d.vl = e.z;
+        d.vo = ((uint64_t)(e.y >> 16) << 32) | e.w;
     }
     if (lane == 0 && d.r0 > d.lo) {
-        d.pko = st.koff16[d.r0 - 1];
-        d.pkl = st.klen[d.r0 - 1];
+        const uint4 e = __ldg(st.dir + d.r0 - 1);
+        d.pko = e.x;
+        d.pkl = e.y & 0xffffu;
     }
     return d;
 }
@@ -324,7 +335,7 @@ k_decode_lcp(StoreDev st, const ReqDev *__restrict__ reqs, const TileDev *__rest
     sid += stride;
     SubDesc dA = load_desc(st, tA, lane);
     tA = fetch_tile(tiles, sid, n_sub);
-    if (lane == 0) raw = atomicAdd(work_ctr, 1u);
+    if (lane == 0) raw = atom_add_u32_raw(work_ctr, 1u);
     issue_stage(st, mode, dB, buf0, bar0, lane);
     uint32_t fills0 = 0, fills1 = 0;  // completed-phase counters of the two buffers (parity = count & 1)
     // The body is unrolled six times (lcm of the 3 descriptor roles and the 2 stage buffers) so that the role
@@ -339,7 +350,7 @@ k_decode_lcp(StoreDev st, const ReqDev *__restrict__ reqs, const TileDev *__rest
                 dA = load_desc(st, tA, lane);
                 sid = dyn_base + __shfl_sync(0xffffffffu, raw, 0);
                 tA = fetch_tile(tiles, sid, n_sub);
-                if (lane == 0) raw = atomicAdd(work_ctr, 1u);
+                if (lane == 0) raw = atom_add_u32_raw(work_ctr, 1u);
                 issue_stage(st, mode, dB, buf0 + ((u + 1) & 1) * KB_WARP_STAGE_CHUNKS, bar0 + ((u + 1) & 1), lane);
                 // wait for dC's bytes (only if a copy was issued for it: real, staged sub-tile)
                 if (dC.nrec != 0 && dC.span <= KB_WARP_STAGE_CHUNKS) {

@@ -23,8 +23,13 @@ struct StoreDev {
     const uint4    *vslab;   // values, 16-byte aligned, zero padded
     const uint64_t *voff16;  // n+1 offsets in 16-byte units
     const uint32_t *vlen;    // n exact value lengths
+    const uint4    *dir;     // n packed directory entries for the decode pass (one 16-byte load per record):
+                             // {koff16, klen | (voff16 >> 32) << 16, vlen, (uint32_t)voff16}
     uint32_t        n;
 };
+
+// fills StoreDev::dir from the four directory arrays (kb_core.cu); enqueued on ctx->stream
+int store_pack_dir(struct kb_ctx *ctx);
 
 // one scanner.Range / Count / Compact request, resolved to record indices
 struct ReqDev {
@@ -159,7 +164,7 @@ struct kb_ctx {
     // store
     bool loaded = false;
     StoreDev st{};
-    DBuf d_kslab, d_koff16, d_klen, d_vslab, d_voff16, d_vlen;
+    DBuf d_kslab, d_koff16, d_klen, d_vslab, d_voff16, d_vlen, d_dir;
     uint64_t key_bytes = 0, val_bytes = 0;
     uint32_t max_kv_chunks = 0;  // largest padded [key][value] pair, in 16-byte chunks: sizes the gather's ring buffers
     std::vector<uint32_t> h_koff16;  // host copies of the slab offsets: byte accounting and response-arena bounds

@@ -1961,6 +1961,14 @@ extern "C" int kb_apply_batch(kb_ctx *ctx, const kb_write_op *ops, uint64_t n_op
     ctx->st.voff16 = (const uint64_t *)ctx->d_voff16.p;
     ctx->st.vlen = (const uint32_t *)ctx->d_vlen.p;
     ctx->st.n = (uint32_t)N2;
+    {
+        int prc = store_pack_dir(ctx);
+        if (prc == KB_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) prc = KB_ECUDA;
+        if (prc != KB_OK) {
+            ctx->loaded = false;
+            return prc;
+        }
+    }
     ctx->h_koff16.swap(koff2);
     ctx->h_voff16.swap(voff2);
     ctx->h_klen.swap(klen2);

@@ -29,7 +29,7 @@ def fuzz_store(seed: int, n_keys: int = 60, max_rev: int = 60) -> PackedStore:
             uk = uk + b"x" * rng.randint(20, 300)  # long keys (several 16-byte chunks, > staging stride)
         user_keys.add(uk)
     items = {}
-    for uk in user_keys:
+    for uk in sorted(user_keys):  # sorted: set order depends on the per-process hash seed
         revs = sorted(rng.sample(range(1, max_rev), rng.randint(0, 5)))
         if rng.random() < 0.85:
             r = rng.random()
@@ -79,9 +79,9 @@ def fuzz_bounds(store: PackedStore, seed: int, n: int = 8) -> List[Tuple[bytes, 
     for _ in range(n):
         a, b = rng.choice(keys), rng.choice(keys)
         if rng.random() < 0.5:
-            a = a[: rng.randint(1, len(a))]
+            a = a[: rng.randint(1, max(len(a), 1))]
         if rng.random() < 0.5:
-            b = b[: rng.randint(1, len(b))] + b"\xff"
+            b = b[: rng.randint(1, max(len(b), 1))] + b"\xff"
         if a > b:
             a, b = b, a
         out.append((a, b))
