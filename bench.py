@@ -246,7 +246,7 @@ def run_b200(args, rank: int, local_rank: int, world: int):
     wl = build_workload(rank, world)
     # two contexts on the same GPU, as in the reference where scans and the watch hub are independent goroutines:
     # `eng` owns the HBM-resident snapshot (scans), `weng` owns the watcher tables (fan-out); each has its own stream
-    eng = Engine(local_rank)
+    eng = Engine(local_rank, high_priority=not args.serial)  # the scan chain is the critical path of a step
     eng.load_sorted(wl["store"])
     weng = eng if args.serial else Engine(local_rank)
     weng.watch_add_many(wl["watchers"])

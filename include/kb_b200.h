@@ -35,7 +35,8 @@ typedef enum kb_status {
     KB_ECOMPACTED = -5,  /* range revision below the compact revision (scanner.go:618-624)        */
     KB_ESTATE = -6,      /* call out of order (no store loaded, NCCL not initialised, ...)         */
     KB_ENCCL = -7,
-    KB_ELIMIT = -8       /* input exceeds a documented format limit (key > 65535 B, n >= 2^32-1)   */
+    KB_ELIMIT = -8,      /* input exceeds a documented format limit (key > 65535 B, n >= 2^32-1)   */
+    KB_EIO = -9          /* kb_dump / kb_restore: file could not be opened, read or written        */
 } kb_status;
 
 typedef struct kb_ctx kb_ctx;
@@ -44,8 +45,11 @@ typedef struct kb_events_dev kb_events_dev;
 
 typedef struct kb_config {
     uint32_t struct_size;   /* sizeof(kb_config), for forward compatibility */
-    uint32_t flags;         /* reserved, 0 */
+    uint32_t flags;         /* KB_CFG_* */
 } kb_config;
+/* the ctx's stream gets the highest CUDA stream priority: its kernels are scheduled ahead of those of other contexts
+ * sharing the GPU (e.g. the latency-critical scan context next to a fan-out context) */
+#define KB_CFG_HIGH_PRIORITY 1u
 
 /* ---- lifecycle ------------------------------------------------------------------------------ */
 int kb_abi_version(void);
@@ -63,6 +67,14 @@ int kb_sync(kb_ctx *ctx);
 int kb_load_sorted(kb_ctx *ctx, const uint8_t *keys, const uint64_t *key_off, const uint8_t *vals,
                    const uint64_t *val_off, uint64_t n);
 int kb_store_info(kb_ctx *ctx, uint64_t *n_records, uint64_t *key_bytes, uint64_t *val_bytes);
+
+/* Durable dump / restore of the HBM snapshot (restart without re-iterating the engine; the on-disk format of the
+ * engine itself -- badger / TiKV, pkg/storage/badger/badger.go:33-39 -- is untouched).  The file holds the record
+ * directory and both slabs in device layout plus the compact-revision record, each section with an FNV-1a 64 checksum;
+ * kb_restore validates header, sizes, checksums and the iterator contract (ascending unique keys) before the snapshot
+ * becomes visible.  KB_EIO on file errors, KB_EINVAL on a corrupt or foreign file. */
+int kb_dump(kb_ctx *ctx, const char *path);
+int kb_restore(kb_ctx *ctx, const char *path);
 
 /* Incremental maintenance from the write path: one committed storage.BatchWrite (pkg/storage/interface.go:81-106;
  * the backend issues CAS(revision record) + Put(object record) per write, pkg/backend/txn.go:249-265,

@@ -32,7 +32,7 @@ KB_OP_PUT, KB_OP_DEL = 0, 1
 
 ABI_SYMBOLS = [
     "kb_abi_version", "kb_open", "kb_close", "kb_last_error", "kb_stream", "kb_sync",
-    "kb_load_sorted", "kb_store_info", "kb_apply_batch", "kb_set_compact_revision",
+    "kb_load_sorted", "kb_store_info", "kb_dump", "kb_restore", "kb_apply_batch", "kb_set_compact_revision",
     "kb_range_batch", "kb_range_view_get", "kb_wire_range_head", "kb_wire_range_tail", "kb_wire_watch_head",
     "kb_get_batch", "kb_get_view_get",
     "kb_compact_sweep", "kb_compact_view_get",
@@ -47,6 +47,13 @@ class KbError(RuntimeError):
     def __init__(self, code: int, msg: str):
         super().__init__(f"kb_b200 error {code}: {msg}")
         self.code = code
+
+
+KB_CFG_HIGH_PRIORITY = 1
+
+
+class KbConfig(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("flags", C.c_uint32)]
 
 
 class KbRangeReq(C.Structure):
@@ -125,6 +132,10 @@ def lib():
     L.kb_store_info.restype = C.c_int
     L.kb_store_info.argtypes = [vp, u64p, u64p, u64p]
     L.kb_set_compact_revision.restype = C.c_int
+    L.kb_dump.restype = C.c_int
+    L.kb_dump.argtypes = [vp, C.c_char_p]
+    L.kb_restore.restype = C.c_int
+    L.kb_restore.argtypes = [vp, C.c_char_p]
     L.kb_apply_batch.argtypes = [vp, C.POINTER(KbWriteOp), C.c_uint64]
     L.kb_apply_batch.restype = C.c_int
     L.kb_set_compact_revision.argtypes = [vp, C.c_int, C.c_uint64]
@@ -371,9 +382,10 @@ class PackedRangeReqs:
 class Engine:
     """A kb_ctx: one HBM-resident snapshot + watcher table on one GPU."""
 
-    def __init__(self, device: int = 0):
+    def __init__(self, device: int = 0, high_priority: bool = False):
         self._ctx = C.c_void_p()
-        rc = lib().kb_open(device, None, C.byref(self._ctx))
+        cfg = KbConfig(C.sizeof(KbConfig), KB_CFG_HIGH_PRIORITY if high_priority else 0)
+        rc = lib().kb_open(device, C.byref(cfg), C.byref(self._ctx))
         if rc != 0:
             raise KbError(rc, "kb_open failed: no usable CUDA device (kubebrain_b200 has no CPU fallback)")
         self.device = device
@@ -410,6 +422,14 @@ class Engine:
             if v is not None:
                 arr[i].val, arr[i].val_len = v, len(v)
         self._check(lib().kb_apply_batch(self._ctx, arr, len(ops)))
+
+    def dump(self, path: str):
+        """write the snapshot (directory, slabs, compact revision) to `path` (atomically: tmp file + rename)"""
+        self._check(lib().kb_dump(self._ctx, os.fsencode(path)))
+
+    def restore(self, path: str):
+        """replace the snapshot with the one in `path` (validated: header, checksums, directory, key order)"""
+        self._check(lib().kb_restore(self._ctx, os.fsencode(path)))
 
     def store_info(self) -> Tuple[int, int, int]:
         a, b, c = C.c_uint64(), C.c_uint64(), C.c_uint64()

@@ -211,8 +211,8 @@ extern "C" int kb_abi_version(void) { return KB_ABI_VERSION; }
 
 extern "C" int kb_open(int device_ordinal, const kb_config *cfg, kb_ctx **out)
 {
-    (void)cfg;
     if (!out) return KB_EINVAL;
+    const bool high = cfg && cfg->struct_size >= sizeof(kb_config) && (cfg->flags & KB_CFG_HIGH_PRIORITY);
     *out = nullptr;
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -222,8 +222,10 @@ extern "C" int kb_open(int device_ordinal, const kb_config *cfg, kb_ctx **out)
     }
     kb_ctx *ctx = new kb_ctx();
     ctx->device = device_ordinal;
+    int prio_lo = 0, prio_hi = 0;
     if (cudaSetDevice(device_ordinal) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi) != cudaSuccess ||
+        cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, high ? prio_hi : prio_lo) != cudaSuccess) {
         delete ctx;
         return KB_ECUDA;
     }
@@ -474,6 +476,202 @@ extern "C" int kb_store_info(kb_ctx *ctx, uint64_t *n_records, uint64_t *key_byt
     if (n_records) *n_records = ctx->st.n;
     if (key_bytes) *key_bytes = ctx->key_bytes;
     if (val_bytes) *val_bytes = ctx->val_bytes;
+    return KB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// durable dump / restore of the snapshot (device layout, so restore is file -> pinned staging -> HBM with no repack)
+// ------------------------------------------------------------------------------------------------
+namespace {
+struct DumpHeader {
+    char     magic[8];  // "KBB200D1"
+    uint32_t version, header_bytes;
+    uint64_t n, key_chunks, val_chunks;
+    uint64_t compact_present, compact_rev;
+    uint32_t max_kv_chunks, pad;
+    uint64_t sum_dir, sum_keys, sum_vals;  // FNV-1a 64 of the directory section and of the two slabs
+};
+constexpr size_t DUMP_STAGE = 64u << 20;  // bytes per host <-> device hop
+
+inline uint64_t fnv1a64_update(uint64_t h, const uint8_t *p, size_t n)
+{
+    // 8 bytes per step (word-wise FNV-1a variant): the checksum only has to detect torn or foreign files
+    size_t i = 0;
+    for (; i + 8 <= n; i += 8) {
+        uint64_t w;
+        memcpy(&w, p + i, 8);
+        h = (h ^ w) * 0x100000001b3ull;
+    }
+    for (; i < n; i++) h = (h ^ p[i]) * 0x100000001b3ull;
+    return h;
+}
+
+// device -> file through the pinned staging buffer; returns the checksum of the bytes written
+int dump_section(kb_ctx *ctx, FILE *f, const void *dev, uint64_t bytes, uint64_t *sum)
+{
+    uint64_t h = 0xcbf29ce484222325ull;
+    for (uint64_t off = 0; off < bytes; off += DUMP_STAGE) {
+        const size_t n = (size_t)std::min<uint64_t>(DUMP_STAGE, bytes - off);
+        KB_CUDA(ctx, cudaMemcpyAsync(ctx->h_stage.p, (const uint8_t *)dev + off, n, cudaMemcpyDeviceToHost, ctx->stream));
+        KB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        h = fnv1a64_update(h, (const uint8_t *)ctx->h_stage.p, n);
+        if (fwrite(ctx->h_stage.p, 1, n, f) != n) return kb_fail(ctx, KB_EIO, "dump: short write");
+    }
+    *sum = h;
+    return KB_OK;
+}
+
+int restore_section(kb_ctx *ctx, FILE *f, void *dev, uint64_t bytes, uint64_t *sum)
+{
+    uint64_t h = 0xcbf29ce484222325ull;
+    for (uint64_t off = 0; off < bytes; off += DUMP_STAGE) {
+        const size_t n = (size_t)std::min<uint64_t>(DUMP_STAGE, bytes - off);
+        if (fread(ctx->h_stage.p, 1, n, f) != n) return kb_fail(ctx, KB_EINVAL, "restore: file truncated");
+        h = fnv1a64_update(h, (const uint8_t *)ctx->h_stage.p, n);
+        KB_CUDA(ctx, cudaMemcpyAsync((uint8_t *)dev + off, ctx->h_stage.p, n, cudaMemcpyHostToDevice, ctx->stream));
+        KB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // the staging buffer is reused by the next hop
+    }
+    *sum = h;
+    return KB_OK;
+}
+}  // namespace
+
+extern "C" int kb_dump(kb_ctx *ctx, const char *path)
+{
+    if (!ctx || !path) return KB_EINVAL;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    if (!ctx->loaded) return kb_fail(ctx, KB_ESTATE, "no store loaded");
+    cudaSetDevice(ctx->device);
+    KB_TRY(hbuf_ensure(ctx, ctx->h_stage, DUMP_STAGE));
+    const std::string tmp = std::string(path) + ".tmp";
+    FILE *f = fopen(tmp.c_str(), "wb");
+    if (!f) return kb_fail(ctx, KB_EIO, "dump: cannot create %s", tmp.c_str());
+    const uint64_t n = ctx->st.n;
+    DumpHeader h;
+    memset(&h, 0, sizeof(h));
+    memcpy(h.magic, "KBB200D1", 8);
+    h.version = 1;
+    h.header_bytes = (uint32_t)sizeof(DumpHeader);
+    h.n = n;
+    h.key_chunks = ctx->key_bytes / 16;
+    h.val_chunks = ctx->val_bytes / 16;
+    h.compact_present = ctx->compact_present ? 1 : 0;
+    h.compact_rev = ctx->compact_rev;
+    h.max_kv_chunks = ctx->max_kv_chunks;
+    int rc = KB_OK;
+    if (fwrite(&h, 1, sizeof(h), f) != sizeof(h)) rc = kb_fail(ctx, KB_EIO, "dump: short write");
+    // directory section: the host copies are authoritative (kb_load_sorted / kb_apply_batch maintain them)
+    uint64_t hd = 0xcbf29ce484222325ull;
+    auto put = [&](const void *p, size_t bytes) {
+        if (rc != KB_OK) return;
+        hd = fnv1a64_update(hd, (const uint8_t *)p, bytes);
+        if (bytes && fwrite(p, 1, bytes, f) != bytes) rc = kb_fail(ctx, KB_EIO, "dump: short write");
+    };
+    put(ctx->h_koff16.data(), (n + 1) * 4);
+    put(ctx->h_klen.data(), n * 2);
+    put(ctx->h_voff16.data(), (n + 1) * 8);
+    put(ctx->h_vlen.data(), n * 4);
+    h.sum_dir = hd;
+    if (rc == KB_OK) rc = dump_section(ctx, f, ctx->d_kslab.p, ctx->key_bytes, &h.sum_keys);
+    if (rc == KB_OK) rc = dump_section(ctx, f, ctx->d_vslab.p, ctx->val_bytes, &h.sum_vals);
+    if (rc == KB_OK && (fseek(f, 0, SEEK_SET) != 0 || fwrite(&h, 1, sizeof(h), f) != sizeof(h)))
+        rc = kb_fail(ctx, KB_EIO, "dump: cannot finish the header");
+    if (fclose(f) != 0 && rc == KB_OK) rc = kb_fail(ctx, KB_EIO, "dump: close failed");
+    if (rc == KB_OK && rename(tmp.c_str(), path) != 0) rc = kb_fail(ctx, KB_EIO, "dump: cannot rename to %s", path);
+    if (rc != KB_OK) remove(tmp.c_str());
+    return rc;
+}
+
+extern "C" int kb_restore(kb_ctx *ctx, const char *path)
+{
+    if (!ctx || !path) return KB_EINVAL;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    cudaSetDevice(ctx->device);
+    FILE *f = fopen(path, "rb");
+    if (!f) return kb_fail(ctx, KB_EIO, "restore: cannot open %s", path);
+    struct Closer {
+        FILE *f;
+        ~Closer() { fclose(f); }
+    } closer{f};
+    DumpHeader h;
+    if (fread(&h, 1, sizeof(h), f) != sizeof(h) || memcmp(h.magic, "KBB200D1", 8) != 0 || h.version != 1 ||
+        h.header_bytes != sizeof(DumpHeader))
+        return kb_fail(ctx, KB_EINVAL, "restore: %s is not a kb_b200 dump (version 1)", path);
+    const uint64_t n = h.n;
+    if (n >= 0xFFFFFFFEull || h.key_chunks > 0xFFFFFFF0ull) return kb_fail(ctx, KB_ELIMIT, "restore: dump exceeds the format limits");
+    ctx->loaded = false;
+    std::vector<uint32_t> koff16(n + 1), vlen(n ? n : 1);
+    std::vector<uint16_t> klen(n ? n : 1);
+    std::vector<uint64_t> voff16(n + 1);
+    uint64_t hd = 0xcbf29ce484222325ull;
+    bool ok = true;
+    auto get = [&](void *p, size_t bytes) {
+        if (!ok) return;
+        if (bytes && fread(p, 1, bytes, f) != bytes) ok = false;
+        else hd = fnv1a64_update(hd, (const uint8_t *)p, bytes);
+    };
+    get(koff16.data(), (n + 1) * 4);
+    get(klen.data(), n * 2);
+    get(voff16.data(), (n + 1) * 8);
+    get(vlen.data(), n * 4);
+    if (!ok) return kb_fail(ctx, KB_EINVAL, "restore: file truncated");
+    if (hd != h.sum_dir) return kb_fail(ctx, KB_EINVAL, "restore: directory checksum mismatch");
+    // the directory must describe exactly the slabs that follow: monotone offsets, every record inside its slab
+    if (koff16[0] != 0 || voff16[0] != 0 || koff16[n] != h.key_chunks || voff16[n] != h.val_chunks) ok = false;
+    uint64_t max_kv = 0;
+    for (uint64_t i = 0; ok && i < n; i++) {
+        const uint64_t nk = ((uint32_t)klen[i] + 15) / 16, nv = ((uint64_t)vlen[i] + 15) / 16;
+        if (koff16[i + 1] < koff16[i] || koff16[i + 1] - koff16[i] != nk) ok = false;
+        if (voff16[i + 1] < voff16[i] || voff16[i + 1] - voff16[i] != nv) ok = false;
+        max_kv = std::max(max_kv, nk + nv);
+    }
+    if (!ok) return kb_fail(ctx, KB_EINVAL, "restore: inconsistent record directory");
+    KB_TRY(hbuf_ensure(ctx, ctx->h_stage, DUMP_STAGE));
+    KB_TRY(dbuf_ensure(ctx, ctx->d_kslab, h.key_chunks * 16 + 64));
+    KB_TRY(dbuf_ensure(ctx, ctx->d_vslab, h.val_chunks * 16 + 64));
+    KB_TRY(dbuf_ensure(ctx, ctx->d_koff16, (n + 1) * 4));
+    KB_TRY(dbuf_ensure(ctx, ctx->d_klen, (n + 1) * 2));
+    KB_TRY(dbuf_ensure(ctx, ctx->d_voff16, (n + 1) * 8));
+    KB_TRY(dbuf_ensure(ctx, ctx->d_vlen, (n + 1) * 4));
+    KB_CUDA(ctx, cudaMemsetAsync((uint8_t *)ctx->d_kslab.p + h.key_chunks * 16, 0, 64, ctx->stream));
+    KB_CUDA(ctx, cudaMemsetAsync((uint8_t *)ctx->d_vslab.p + h.val_chunks * 16, 0, 64, ctx->stream));
+    uint64_t sk = 0, sv = 0;
+    KB_TRY(restore_section(ctx, f, ctx->d_kslab.p, h.key_chunks * 16, &sk));
+    KB_TRY(restore_section(ctx, f, ctx->d_vslab.p, h.val_chunks * 16, &sv));
+    if (sk != h.sum_keys || sv != h.sum_vals) return kb_fail(ctx, KB_EINVAL, "restore: slab checksum mismatch");
+    KB_CUDA(ctx, cudaMemcpyAsync(ctx->d_koff16.p, koff16.data(), (n + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
+    KB_CUDA(ctx, cudaMemcpyAsync(ctx->d_klen.p, klen.data(), n * 2, cudaMemcpyHostToDevice, ctx->stream));
+    KB_CUDA(ctx, cudaMemcpyAsync(ctx->d_voff16.p, voff16.data(), (n + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    KB_CUDA(ctx, cudaMemcpyAsync(ctx->d_vlen.p, vlen.data(), n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->st.kslab = (const uint4 *)ctx->d_kslab.p;
+    ctx->st.koff16 = (const uint32_t *)ctx->d_koff16.p;
+    ctx->st.klen = (const uint16_t *)ctx->d_klen.p;
+    ctx->st.vslab = (const uint4 *)ctx->d_vslab.p;
+    ctx->st.voff16 = (const uint64_t *)ctx->d_voff16.p;
+    ctx->st.vlen = (const uint32_t *)ctx->d_vlen.p;
+    ctx->st.n = (uint32_t)n;
+    KB_TRY(store_pack_dir(ctx));
+    if (n > 1) {  // the iterator contract, as in kb_load_sorted
+        KB_TRY(dbuf_ensure(ctx, ctx->d_flags, 64));
+        uint32_t init = 0xFFFFFFFFu, bad = 0;
+        KB_CUDA(ctx, cudaMemcpyAsync(ctx->d_flags.p, &init, 4, cudaMemcpyHostToDevice, ctx->stream));
+        k_check_sorted<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->st, (uint32_t *)ctx->d_flags.p);
+        KB_CUDA(ctx, cudaMemcpyAsync(&bad, ctx->d_flags.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        KB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (bad != 0xFFFFFFFFu) return kb_fail(ctx, KB_EUNSORTED, "restore: record %u is not greater than its predecessor", bad);
+    } else {
+        KB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    ctx->h_koff16.swap(koff16);
+    ctx->h_voff16.swap(voff16);
+    ctx->h_klen.swap(klen);
+    ctx->h_vlen.swap(vlen);
+    ctx->key_bytes = h.key_chunks * 16;
+    ctx->val_bytes = h.val_chunks * 16;
+    ctx->max_kv_chunks = (uint32_t)std::min<uint64_t>(max_kv, 0xFFFFFFFFu);
+    ctx->compact_present = h.compact_present != 0;
+    ctx->compact_rev = h.compact_rev;
+    ctx->loaded = true;
     return KB_OK;
 }
 

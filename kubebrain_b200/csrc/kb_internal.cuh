@@ -273,12 +273,12 @@ void prof_end(kb_ctx *ctx);
         if (_p) prof_end((ctx));                              \
     } while (0)
 
-// host wall-clock segments (only with kb_prof_enable(ctx, 1)): where the non-kernel time of a call goes
+// host wall-clock segments (with kb_prof_enable(ctx, 1 or 2)): where the non-kernel time of a call goes
 typedef std::chrono::steady_clock::time_point kb_tp;
 static inline kb_tp kb_now() { return std::chrono::steady_clock::now(); }
 static inline void kb_seg(kb_ctx *ctx, const char *name, kb_tp &t)
 {
-    if (ctx->prof_on != 1) return;
+    if (ctx->prof_on == 0) return;
     kb_tp n = kb_now();
     int i = prof_index(ctx, name);
     ctx->prof[i].launches++;

@@ -936,7 +936,8 @@ int layout_requests(kb_ctx *ctx, bool cap_by_limit, Resolved &R)
 }
 
 // upload the bound keys, run k_search, and lay the requests out as tiles
-int resolve_requests(kb_ctx *ctx, const kb_range_req *reqs, uint64_t nreq, bool cap_by_limit, Resolved &R)
+int resolve_requests(kb_ctx *ctx, const kb_range_req *reqs, uint64_t nreq, bool cap_by_limit, Resolved &R,
+                     kb_tp *tseg = nullptr)
 {
     // bound slab: 2 keys per request, each padded to 16 bytes
     uint64_t chunks = 0;
@@ -974,7 +975,9 @@ int resolve_requests(kb_ctx *ctx, const kb_range_req *reqs, uint64_t nreq, bool 
               (k_search<<<sgrid, 128, 0, ctx->stream>>>(ctx->st, (const uint4 *)ctx->d_bounds.p, d_boff, d_boff + nb,
                                                         (uint32_t)nb, (uint32_t *)ctx->d_bres.p)));
     KB_CUDA(ctx, cudaMemcpyAsync(hres, ctx->d_bres.p, nb * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (tseg) kb_seg(ctx, "host:range_search_enqueue", *tseg);
     KB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (tseg) kb_seg(ctx, "host:range_search_sync", *tseg);
 
     R.reqs.resize(nreq);
     for (uint64_t q = 0; q < nreq; q++) {
@@ -1177,8 +1180,8 @@ extern "C" int kb_range_batch(kb_ctx *ctx, const kb_range_req *reqs, uint64_t nr
     }
     kb_tp tseg = kb_now();
     Resolved R;
-    KB_TRY(resolve_requests(ctx, reqs, nreq, true, R));
-    kb_seg(ctx, "host:range_resolve+sync", tseg);
+    KB_TRY(resolve_requests(ctx, reqs, nreq, true, R, &tseg));
+    kb_seg(ctx, "host:range_layout", tseg);
     if (out_mode != KB_OUT_COUNT) {
         KB_TRY(probe_limit_windows(ctx, R));
         kb_seg(ctx, "host:range_limit_probe", tseg);
@@ -1367,6 +1370,7 @@ extern "C" int kb_range_batch(kb_ctx *ctx, const kb_range_req *reqs, uint64_t nr
         }
     }
     *out = res;
+    kb_seg(ctx, "host:range_finish", tseg);
     return KB_OK;
 }
 
