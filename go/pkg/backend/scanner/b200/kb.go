@@ -60,6 +60,19 @@ func (e *Engine) LoadSorted(keys []byte, keyOff []uint64, vals []byte, valOff []
 		(*C.uint8_t)(unsafe.Pointer(&vals[0])), (*C.uint64_t)(unsafe.Pointer(&valOff[0])), C.uint64_t(n)))
 }
 
+// Dump / Restore persist the HBM snapshot (device layout, checksummed) so a restart need not re-iterate the engine.
+func (e *Engine) Dump(path string) error {
+	cs := C.CString(path)
+	defer C.free(unsafe.Pointer(cs))
+	return e.err(C.kb_dump(e.ctx, cs))
+}
+
+func (e *Engine) Restore(path string) error {
+	cs := C.CString(path)
+	defer C.free(unsafe.Pointer(cs))
+	return e.err(C.kb_restore(e.ctx, cs))
+}
+
 // WriteOp mirrors one Put/Del of a committed storage.BatchWrite (pkg/storage/interface.go:62-84).
 type WriteOp struct {
 	Del      bool

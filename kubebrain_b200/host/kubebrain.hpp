@@ -175,6 +175,9 @@ class Engine {
         Check(kb_load_sorted(ctx_, keys.empty() ? &z : (const uint8_t *)keys.data(), ko.data(),
                              vals.empty() ? &z : (const uint8_t *)vals.data(), vo.data(), items.size()));
     }
+    // snapshot file in device layout (restart without re-iterating the engine)
+    void Dump(const std::string &path) { Check(kb_dump(ctx_, path.c_str())); }
+    void Restore(const std::string &path) { Check(kb_restore(ctx_, path.c_str())); }
     // one committed storage.BatchWrite (pkg/storage/interface.go:62-84): Put / Del in order, last op on a key wins
     struct WriteOp {
         bool del;
