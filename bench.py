@@ -459,7 +459,7 @@ def run_b200(args, rank: int, local_rank: int, world: int):
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(wl)
         if world == 1 and not args.no_extras:
-            line["extra"] = {"compaction": compaction_extra(local_rank)}
+            line["extra"] = {"compaction": compaction_extra(local_rank), "wire": wire_extra(eng, wl)}
         print(json.dumps(line), flush=True)
     if wthread is not None:
         jobs_q.put(None)
@@ -471,6 +471,30 @@ def run_b200(args, rank: int, local_rank: int, world: int):
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def wire_extra(eng, wl):
+    """extra (not part of the headline): the full-range answer written as etcd protobuf elements by the device
+    (KB_WIRE_ETCD_EVENTS, the range-stream shape) instead of padded [key][value] pairs"""
+    from kubebrain_b200._lib import KB_OUT_DEVICE, KB_WIRE_ETCD_EVENTS, Engine
+
+    reqs = Engine.pack_range_reqs(wl["reqs"][:1])
+    for _ in range(3):
+        eng.range_batch(reqs, KB_OUT_DEVICE | KB_WIRE_ETCD_EVENTS).close()
+    eng.prof_reset()
+    eng.prof_enable(1)
+    reps = 5
+    for _ in range(reps):
+        r = eng.range_batch(reqs, KB_OUT_DEVICE | KB_WIRE_ETCD_EVENTS)
+        nk, nb = r.n_kvs, r.n_bytes
+        r.close()
+    eng.prof_enable(0)
+    kern = {p["name"]: {"avg_us": 1e3 * p["total_ms"] / p["launches"],
+                        "achieved_gbs": (p["alg_bytes"] / p["launches"] / 1e9) / (p["total_ms"] / p["launches"] / 1e3)
+                        if p["total_ms"] > 0 else None}
+            for p in eng.prof_read() if p["launches"] and p["name"] in ("k_wire_copy", "k_wire_jobs", "k_decode_lcp", "k_emit")}
+    return {"workload": "1 full Range of the bench store as WatchResponse.events elements, device resident",
+            "kvs": int(nk), "wire_bytes": int(nb), "kernels": kern}
 
 
 def compaction_extra(device: int):

@@ -1210,6 +1210,19 @@ extern "C" int kb_range_batch(kb_ctx *ctx, const kb_range_req *reqs, uint64_t nr
     kb_result *res = kb_result_new(1, out_mode);
     res->wire = wire;
     DBuf d_om;
+    // every early return below hands the pooled buffers back (the stream keeps later reuse ordered behind this call)
+    struct Guard {
+        kb_ctx *ctx;
+        kb_result *&res;
+        DBuf &d_om;
+        bool armed = true;
+        ~Guard()
+        {
+            if (!armed) return;
+            pool_put_dev(ctx, d_om);
+            result_release_locked(ctx, res);
+        }
+    } guard{ctx, res, d_om};
     GatherOut go;
     memset(&go, 0, sizeof(go));
     const uint64_t cap_kvs = R.total_sel;
@@ -1221,11 +1234,7 @@ extern "C" int kb_range_batch(kb_ctx *ctx, const kb_range_req *reqs, uint64_t nr
         if (rc == KB_OK) rc = pool_get_dev(ctx, ub_bytes + 64, &res->d_bytes);
         if (rc == KB_OK) rc = dbuf_ensure(ctx, ctx->d_jobs, (nreq + 1) * 16 + 8);
         if (rc == KB_OK) rc = dbuf_ensure(ctx, ctx->d_gjobs, std::max<uint64_t>(cap_kvs, 1) * sizeof(GatherJob));
-        if (rc != KB_OK) {
-            pool_put_dev(ctx, d_om);
-            result_release_locked(ctx, res);
-            return rc;
-        }
+        if (rc != KB_OK) return rc;
         uint8_t *om = (uint8_t *)d_om.p;
         go.rev = (uint64_t *)om;
         go.key_off = go.rev + cap_kvs;
@@ -1243,11 +1252,7 @@ extern "C" int kb_range_batch(kb_ctx *ctx, const kb_range_req *reqs, uint64_t nr
         const unsigned jgrid = (unsigned)std::min<uint64_t>((cap_kvs + 255) / 256, 148 * 8);
         if (wire) {
             rc = dbuf_ensure(ctx, ctx->d_gjobs, std::max<uint64_t>(cap_kvs, 1) * sizeof(WireJob));
-            if (rc != KB_OK) {
-                pool_put_dev(ctx, d_om);
-                result_release_locked(ctx, res);
-                return rc;
-            }
+            if (rc != KB_OK) return rc;
             WireOut wo;
             wo.rec_idx = go.rec_idx;
             wo.rev = go.rev;
@@ -1282,11 +1287,7 @@ extern "C" int kb_range_batch(kb_ctx *ctx, const kb_range_req *reqs, uint64_t nr
     kb_seg(ctx, "host:range_launch", tseg);
     cudaError_t e1 = cudaStreamSynchronize(ctx->stream);
     kb_seg(ctx, "host:range_sync", tseg);
-    if (e1 != cudaSuccess) {
-        pool_put_dev(ctx, d_om);
-        result_release_locked(ctx, res);
-        return kb_cuda_fail(ctx, e1, "range scan");
-    }
+    if (e1 != cudaSuccess) return kb_cuda_fail(ctx, e1, "range scan");
     if (nreq) memcpy(rout.data(), ctx->h_stage.p, nreq * sizeof(ReqOut));
 
     res->req_first.resize(nreq + 1);
@@ -1336,11 +1337,7 @@ extern "C" int kb_range_batch(kb_ctx *ctx, const kb_range_req *reqs, uint64_t nr
             cudaError_t e = cudaStreamSynchronize(ctx->stream);
             kb_seg(ctx, "host:range_d2h", tseg);
             if (rc == KB_OK && e != cudaSuccess) rc = kb_cuda_fail(ctx, e, "range D2H");
-            if (rc != KB_OK) {
-                pool_put_dev(ctx, d_om);
-                result_release_locked(ctx, res);
-                return rc;
-            }
+            if (rc != KB_OK) return rc;
             uint8_t *hm = (uint8_t *)res->h_meta.p;
             res->rev = (const uint64_t *)hm;
             res->key_off = res->rev + nk;
@@ -1350,6 +1347,7 @@ extern "C" int kb_range_batch(kb_ctx *ctx, const kb_range_req *reqs, uint64_t nr
             res->key_len = res->rec_idx + nk;
             res->val_len = res->key_len + nk;
             pool_put_dev(ctx, d_om);
+            d_om = DBuf();
             pool_put_dev(ctx, res->d_bytes);
             res->d_bytes = DBuf();
         } else {
@@ -1361,14 +1359,17 @@ extern "C" int kb_range_batch(kb_ctx *ctx, const kb_range_req *reqs, uint64_t nr
             res->val_len = go.val_len;
             res->elem_off = wire ? d_elem_off : nullptr;
             res->d_vic = d_om;  // owned by the result (returned to the pool by kb_result_free)
+            d_om = DBuf();
         }
     } else {
         pool_put_dev(ctx, d_om);
+        d_om = DBuf();
         if (res->d_bytes.p) {
             pool_put_dev(ctx, res->d_bytes);
             res->d_bytes = DBuf();
         }
     }
+    guard.armed = false;
     *out = res;
     kb_seg(ctx, "host:range_finish", tseg);
     return KB_OK;
@@ -1817,7 +1818,16 @@ extern "C" int kb_apply_batch(kb_ctx *ctx, const kb_write_op *ops, uint64_t n_op
             vc += (m[i].val.size() + 15) / 16;
         }
     }
-    DBuf d_opv;
+    // temporaries of this call: released on every path out (the new slabs only until they are adopted)
+    struct Temps {
+        DBuf opv, nk_slab, nv_slab, pieces;
+        ~Temps()
+        {
+            for (DBuf *b : {&opv, &nk_slab, &nv_slab, &pieces})
+                if (b->p) cudaFree(b->p);
+        }
+    } T;
+    DBuf &d_opv = T.opv;
     KB_TRY(dbuf_ensure(ctx, ctx->d_bounds, kchunks * 16 + M * 8 + 64));
     KB_TRY(dbuf_ensure(ctx, ctx->d_bres, M * 4 + M + 64));
     KB_TRY(dbuf_ensure(ctx, d_opv, vchunks * 16 + 64));
@@ -1838,10 +1848,7 @@ extern "C" int kb_apply_batch(kb_ctx *ctx, const kb_write_op *ops, uint64_t n_op
     KB_CUDA(ctx, cudaMemcpyAsync(pos.data(), d_pos, M * 4, cudaMemcpyDeviceToHost, ctx->stream));
     KB_CUDA(ctx, cudaMemcpyAsync(exists.data(), d_exists, M, cudaMemcpyDeviceToHost, ctx->stream));
     cudaError_t e = cudaStreamSynchronize(ctx->stream);
-    if (e != cudaSuccess) {
-        cudaFree(d_opv.p);
-        return kb_cuda_fail(ctx, e, "apply: search");
-    }
+    if (e != cudaSuccess) return kb_cuda_fail(ctx, e, "apply: search");
 
     // 3. merge the record directory on the host; emit the slab copies as pieces
     const uint64_t N = ctx->st.n;
@@ -1851,10 +1858,7 @@ extern "C" int kb_apply_batch(kb_ctx *ctx, const kb_write_op *ops, uint64_t n_op
         n_del += exists[i];
     }
     const uint64_t N2 = N + n_ins - n_del;
-    if (N2 >= 0xFFFFFFFEull) {
-        cudaFree(d_opv.p);
-        return kb_fail(ctx, KB_ELIMIT, "too many records");
-    }
+    if (N2 >= 0xFFFFFFFEull) return kb_fail(ctx, KB_ELIMIT, "too many records");
     std::vector<uint32_t> koff2(N2 + 1), vlen2(std::max<uint64_t>(N2, 1));
     std::vector<uint16_t> klen2(std::max<uint64_t>(N2, 1));
     std::vector<uint64_t> voff2(N2 + 1);
@@ -1890,10 +1894,7 @@ extern "C" int kb_apply_batch(kb_ctx *ctx, const kb_write_op *ops, uint64_t n_op
             w++;
             kacc += nk;
             vacc += nv;
-            if (kacc > 0xFFFFFFF0ull) {
-                cudaFree(d_opv.p);
-                return kb_fail(ctx, KB_ELIMIT, "key slab exceeds 64 GiB");
-            }
+            if (kacc > 0xFFFFFFF0ull) return kb_fail(ctx, KB_ELIMIT, "key slab exceeds 64 GiB");
         }
     }
     copy_base(next_base, N);
@@ -1901,27 +1902,17 @@ extern "C" int kb_apply_batch(kb_ctx *ctx, const kb_write_op *ops, uint64_t n_op
     voff2[N2] = vacc;
 
     // 4. new slabs on the device: segmented copy from the old slab (sel 0) and the op slabs (sel 1)
-    DBuf nk_slab, nv_slab, d_pieces;
+    DBuf &nk_slab = T.nk_slab, &nv_slab = T.nv_slab, &d_pieces = T.pieces;
     int rc = dbuf_ensure(ctx, nk_slab, kacc * 16 + 64);
     if (rc == KB_OK) rc = dbuf_ensure(ctx, nv_slab, vacc * 16 + 64);
     if (rc == KB_OK) rc = dbuf_ensure(ctx, d_pieces, (kp.size() + vp.size() + 1) * sizeof(CopyPiece));
-    if (rc != KB_OK) {  // nothing of the live store has been touched yet
-        cudaFree(d_opv.p);
-        if (nk_slab.p) cudaFree(nk_slab.p);
-        if (nv_slab.p) cudaFree(nv_slab.p);
-        if (d_pieces.p) cudaFree(d_pieces.p);
-        return rc;
-    }
+    if (rc != KB_OK) return rc;  // nothing of the live store has been touched yet
     // the directory arrays grow in place (their old contents are about to be overwritten anyway)
     rc = dbuf_ensure(ctx, ctx->d_koff16, (N2 + 1) * 4);
     if (rc == KB_OK) rc = dbuf_ensure(ctx, ctx->d_klen, (N2 + 1) * 2);
     if (rc == KB_OK) rc = dbuf_ensure(ctx, ctx->d_voff16, (N2 + 1) * 8);
     if (rc == KB_OK) rc = dbuf_ensure(ctx, ctx->d_vlen, (N2 + 1) * 4);
     if (rc != KB_OK) {
-        cudaFree(d_opv.p);
-        cudaFree(nk_slab.p);
-        cudaFree(nv_slab.p);
-        cudaFree(d_pieces.p);
         ctx->loaded = false;  // a directory array may have been released: the caller reloads
         return rc;
     }
@@ -1945,19 +1936,13 @@ extern "C" int kb_apply_batch(kb_ctx *ctx, const kb_write_op *ops, uint64_t n_op
     cudaMemcpyAsync(ctx->d_voff16.p, voff2.data(), (N2 + 1) * 8, cudaMemcpyHostToDevice, ctx->stream);
     cudaMemcpyAsync(ctx->d_vlen.p, vlen2.data(), N2 * 4, cudaMemcpyHostToDevice, ctx->stream);
     e = cudaStreamSynchronize(ctx->stream);
-    cudaFree(d_opv.p);
-    cudaFree(d_pieces.p);
     if (e != cudaSuccess) {
-        cudaFree(nk_slab.p);
-        cudaFree(nv_slab.p);
         ctx->loaded = false;  // the directory on the device may be half written
         return kb_cuda_fail(ctx, e, "apply: merge");
     }
-    // 5. swap
-    cudaFree(ctx->d_kslab.p);
-    cudaFree(ctx->d_vslab.p);
-    ctx->d_kslab = nk_slab;
-    ctx->d_vslab = nv_slab;
+    // 5. swap: the context adopts the new slabs, the old ones become the temporaries that are released on return
+    std::swap(ctx->d_kslab, nk_slab);
+    std::swap(ctx->d_vslab, nv_slab);
     ctx->st.kslab = (const uint4 *)ctx->d_kslab.p;
     ctx->st.vslab = (const uint4 *)ctx->d_vslab.p;
     ctx->st.koff16 = (const uint32_t *)ctx->d_koff16.p;
