@@ -201,7 +201,7 @@ struct kb_ctx {
     std::vector<ProfPending> prof_pending;
     std::vector<cudaEvent_t> ev_pool;
     uint64_t launches = 0;
-    bool decode_attr_set = false, gather_attr_set = false;  // per-context (per-device) kernel attributes
+    bool decode_attr_set = false, gather_attr_set = false, wire_attr_set = false;  // per-context (per-device) kernel attributes
 };
 
 struct kb_result {

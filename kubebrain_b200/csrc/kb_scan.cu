@@ -1266,10 +1266,20 @@ extern "C" int kb_range_batch(kb_ctx *ctx, const kb_range_req *reqs, uint64_t nr
                       (k_wire_jobs<<<jgrid, 256, 0, ctx->stream>>>(ctx->st, d_reqs, (uint32_t)nreq, d_jobfirst, d_arenabase,
                                                                   (const uint32_t *)ctx->d_sel.p,
                                                                   (const uint64_t *)ctx->d_slot.p, wire, d_wj, wo)));
-            const unsigned wgrid = (unsigned)std::min<uint64_t>((cap_kvs + WIRE_WARPS - 1) / WIRE_WARPS, 148 * 8);
+            uint32_t slot_chunks, wstages;
+            wire_geometry(ctx->max_kv_chunks, &slot_chunks, &wstages);
+            const size_t wsmem = (size_t)WIRE_WARPS * wstages * slot_chunks * 16;
+            if (!ctx->wire_attr_set) {
+                cudaFuncSetAttribute(k_wire_copy, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)(WIRE_WARPS * WIRE_WARP_CHUNKS * 16));
+                ctx->wire_attr_set = true;
+            }
+            const unsigned wgrid =
+                (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((cap_kvs + WIRE_WARPS - 1) / WIRE_WARPS, 2 * 148));
             KB_LAUNCH(ctx, "k_wire_copy", 0,
-                      (k_wire_copy<<<wgrid, WIRE_WARPS * 32, 0, ctx->stream>>>(ctx->st, d_wj, d_jobfirst + nreq, wire,
-                                                                             (uint8_t *)res->d_bytes.p)));
+                      (k_wire_copy<<<wgrid, WIRE_WARPS * 32, wsmem, ctx->stream>>>(ctx->st, d_wj, d_jobfirst + nreq,
+                                                                                 (uint8_t *)res->d_bytes.p, slot_chunks,
+                                                                                 wstages)));
         } else {
         KB_LAUNCH(ctx, "k_gather_jobs", cap_kvs * 20,
                   (k_gather_jobs<<<jgrid, 256, 0, ctx->stream>>>(ctx->st, d_reqs, (uint32_t)nreq, d_jobfirst, d_arenabase,
