@@ -260,6 +260,11 @@ extern "C" void kb_close(kb_ctx *ctx)
         cudaEventDestroy(p.b);
     }
     for (auto e : ctx->ev_pool) cudaEventDestroy(e);
+    for (size_t r = 0; r < ctx->p2p_peer.size(); r++)
+        if (ctx->p2p_peer[r] && ctx->p2p_peer[r] != ctx->p2p_mine) cudaIpcCloseMemHandle(ctx->p2p_peer[r]);
+    if (ctx->p2p_mine) cudaFree(ctx->p2p_mine);
+    if (ctx->d_p2p_ptrs.p) cudaFree(ctx->d_p2p_ptrs.p);
+    if (ctx->h_p2p_out) cudaFreeHost(ctx->h_p2p_out);
     if (ctx->nccl_comm) {
         void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
         if (h) {
@@ -734,6 +739,117 @@ extern "C" int kb_nccl_unique_id(uint8_t id[KB_NCCL_ID_BYTES])
     return KB_OK;
 }
 
+// ---- peer-memory cursor exchange ------------------------------------------------------------------------------
+// The one collective of the path moves 8 bytes per rank; ncclAllGather spends ~40 us of launch and protocol latency
+// on it.  Here every rank owns a small slot buffer that all peers map (cudaIpc over NVLink / NVSwitch): a rank stores
+// its cursor and then an epoch flag straight into every peer's buffer and spins on its own buffer until all flags
+// of the epoch have arrived.  Two slot sets alternate by epoch parity: a rank can be at most one exchange ahead of
+// the slowest peer (it needs that peer's flag to finish), so it never overwrites a set that is still being read.
+constexpr int KB_P2P_MAX_RANKS = 1024;
+
+__global__ void __launch_bounds__(KB_P2P_MAX_RANKS)
+k_cursor_p2p(uint64_t *const *__restrict__ peers, int me, int n, uint64_t epoch, uint64_t local, uint64_t *out)
+{
+    __shared__ unsigned long long smin;
+    __shared__ int failed;
+    const int r = threadIdx.x;
+    if (r == 0) {
+        smin = ~0ull;
+        failed = 0;
+    }
+    __syncthreads();
+    const size_t set = (size_t)(epoch & 1) * n * 2;
+    if (r < n) {
+        volatile uint64_t *p = peers[r] + set + (size_t)me * 2;
+        p[0] = local;
+        __threadfence_system();
+        p[1] = epoch;
+        volatile uint64_t *mine = peers[me] + set + (size_t)r * 2;
+        const long long t0 = clock64();
+        bool ok = true;
+        while (mine[1] != epoch) {
+            if (clock64() - t0 > 8000000000ll) {  // ~4 s: a peer never joined this exchange
+                ok = false;
+                break;
+            }
+        }
+        __threadfence_system();
+        const uint64_t v = mine[0];
+        out[r] = v;
+        if (ok) atomicMin(&smin, (unsigned long long)v);
+        else atomicExch(&failed, 1);
+    }
+    __syncthreads();
+    if (r == 0) {
+        out[n] = smin;
+        out[n + 1] = failed ? 2 : 1;  // status: 1 done, 2 timed out
+    }
+}
+
+static void p2p_setup(kb_ctx *ctx, NcclApi *a)
+{
+    const int n = ctx->nccl_nranks, me = ctx->nccl_rank;
+    if (n > KB_P2P_MAX_RANKS) return;
+    const size_t slot_bytes = (size_t)2 * n * 2 * 8;
+    void *mine = nullptr, *d_handles = nullptr;
+    std::vector<cudaIpcMemHandle_t> handles(n);
+    std::vector<void *> peer(n, nullptr);
+    bool ok = cudaMalloc(&mine, slot_bytes) == cudaSuccess && cudaMemset(mine, 0, slot_bytes) == cudaSuccess &&
+              cudaMalloc(&d_handles, (size_t)(n + 1) * sizeof(cudaIpcMemHandle_t) + 64) == cudaSuccess;
+    cudaIpcMemHandle_t my_h;
+    memset(&my_h, 0, sizeof(my_h));
+    // a rank that cannot export its buffer still takes part in the handle all-gather (it is collective) and sends zeros
+    const bool exported = ok && cudaIpcGetMemHandle(&my_h, mine) == cudaSuccess;
+    if (d_handles) {
+        uint8_t *dh = (uint8_t *)d_handles;
+        cudaMemcpyAsync(dh, &my_h, sizeof(my_h), cudaMemcpyHostToDevice, ctx->stream);
+        int rc = a->AllGather(dh, dh + sizeof(my_h), sizeof(my_h), /*ncclUint8*/ 1, ctx->nccl_comm, ctx->stream);
+        if (rc != 0) ok = false;
+        cudaMemcpyAsync(handles.data(), dh + sizeof(my_h), (size_t)n * sizeof(my_h), cudaMemcpyDeviceToHost, ctx->stream);
+        if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) ok = false;
+    }
+    ok = ok && exported;
+    static const cudaIpcMemHandle_t zero_h = {};
+    for (int r = 0; ok && r < n; r++) {
+        if (memcmp(&handles[r], &zero_h, sizeof(zero_h)) == 0) {
+            ok = false;  // that peer could not export
+        } else if (r == me) {
+            peer[r] = mine;
+        } else if (cudaIpcOpenMemHandle(&peer[r], handles[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+            peer[r] = nullptr;
+            ok = false;
+        }
+    }
+    if (ok) ok = dbuf_ensure(ctx, ctx->d_p2p_ptrs, (size_t)n * sizeof(void *)) == KB_OK &&
+                 cudaMemcpy(ctx->d_p2p_ptrs.p, peer.data(), (size_t)n * sizeof(void *), cudaMemcpyHostToDevice) == cudaSuccess &&
+                 cudaHostAlloc((void **)&ctx->h_p2p_out, (size_t)(n + 2) * 8, cudaHostAllocMapped) == cudaSuccess;
+    // all ranks must take the same path: agree on the outcome (one more tiny all-gather, still collective on failure)
+    if (d_handles) {
+        uint8_t *dh = (uint8_t *)d_handles;
+        const uint8_t mine_ok = ok ? 1 : 0;
+        std::vector<uint8_t> all_ok(n, 0);
+        cudaMemcpyAsync(dh, &mine_ok, 1, cudaMemcpyHostToDevice, ctx->stream);
+        int rc = a->AllGather(dh, dh + 16, 1, /*ncclUint8*/ 1, ctx->nccl_comm, ctx->stream);
+        cudaMemcpyAsync(all_ok.data(), dh + 16, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream);
+        if (rc != 0 || cudaStreamSynchronize(ctx->stream) != cudaSuccess) ok = false;
+        for (int r = 0; r < n; r++) ok = ok && all_ok[r] == 1;
+        cudaFree(d_handles);
+    } else {
+        ok = false;
+    }
+    cudaGetLastError();  // a failed IPC call must not poison later error checks
+    if (!ok) {
+        for (int r = 0; r < n; r++)
+            if (peer[r] && peer[r] != mine) cudaIpcCloseMemHandle(peer[r]);
+        if (mine) cudaFree(mine);
+        return;
+    }
+    ctx->p2p_mine = mine;
+    ctx->p2p_peer = peer;
+    ctx->p2p_epoch = 0;
+    ctx->p2p_ready = true;
+}
+
 extern "C" int kb_nccl_init(kb_ctx *ctx, const uint8_t id[KB_NCCL_ID_BYTES], int rank, int nranks)
 {
     if (!ctx || !id || rank < 0 || rank >= nranks) return KB_EINVAL;
@@ -747,6 +863,7 @@ extern "C" int kb_nccl_init(kb_ctx *ctx, const uint8_t id[KB_NCCL_ID_BYTES], int
     if (rc != 0) return kb_fail(ctx, KB_ENCCL, "ncclCommInitRank: %s", a->GetErrorString ? a->GetErrorString(rc) : "?");
     ctx->nccl_rank = rank;
     ctx->nccl_nranks = nranks;
+    if (nranks > 1) p2p_setup(ctx, a);  // best effort: without it the cursor exchange stays on ncclAllGather
     return KB_OK;
 }
 
@@ -769,6 +886,27 @@ extern "C" int kb_cursor_allgather(kb_ctx *ctx, uint64_t local_rev, uint64_t *al
         // a single shard has nobody to exchange with: the readable revision is its own cursor
         if (all_revs) all_revs[0] = local_rev;
         if (min_rev) *min_rev = local_rev;
+        return KB_OK;
+    }
+    if (ctx->p2p_ready) {
+        const uint64_t epoch = ++ctx->p2p_epoch;
+        volatile uint64_t *out = ctx->h_p2p_out;
+        out[n + 1] = 0;
+        const int threads = ((n + 31) / 32) * 32;
+        KB_LAUNCH(ctx, "k_cursor_p2p", (uint64_t)n * 16,
+                  (k_cursor_p2p<<<1, threads, 0, ctx->stream>>>((uint64_t *const *)ctx->d_p2p_ptrs.p, ctx->nccl_rank, n, epoch,
+                                                              local_rev, ctx->h_p2p_out)));
+        // the kernel's last store is the status word in mapped pinned memory: polling it is a few microseconds cheaper
+        // than a stream synchronisation; a launch failure or a hung device still ends in the synchronise below
+        const auto t0 = std::chrono::steady_clock::now();
+        while (out[n + 1] == 0) {
+            if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(6)) break;
+        }
+        if (out[n + 1] == 0) KB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (out[n + 1] != 1) return kb_fail(ctx, KB_ENCCL, "cursor exchange: a peer did not join epoch %llu", (unsigned long long)epoch);
+        if (all_revs)
+            for (int r = 0; r < n; r++) all_revs[r] = out[r];
+        if (min_rev) *min_rev = out[n];
         return KB_OK;
     }
     KB_TRY(dbuf_ensure(ctx, ctx->d_cursor, (size_t)(n + 2) * 8));

@@ -194,6 +194,13 @@ struct kb_ctx {
     void *nccl_comm = nullptr;
     int nccl_rank = -1, nccl_nranks = 0;
     DBuf d_cursor;
+    // peer-memory cursor exchange (set up by kb_nccl_init when every peer's slot buffer can be mapped over NVLink)
+    bool p2p_ready = false;
+    uint64_t p2p_epoch = 0;
+    void *p2p_mine = nullptr;                 // this rank's slot buffer: 2 epochs x nranks x {value, flag}
+    std::vector<void *> p2p_peer;             // every rank's slot buffer as seen from this device (own entry = p2p_mine)
+    DBuf d_p2p_ptrs;                          // the same pointers on the device
+    uint64_t *h_p2p_out = nullptr;            // pinned: [nranks] gathered cursors, [nranks] min, [nranks+1] status
 
     // profiling
     int prof_on = 0;  // 0 off, 1 every kernel, 2 only the two HBM-bound kernels (k_decode_lcp, k_gather)

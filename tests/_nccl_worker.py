@@ -16,11 +16,23 @@ t = torch.tensor(list(uid), dtype=torch.uint8, device="cuda")
 dist.broadcast(t, 0)
 e = Engine(r)
 e.nccl_init(bytes(t.cpu().tolist()), r, 2)
-for k in range(3):
+import time  # noqa: E402
+
+e.prof_enable(1)
+for k in range(200):  # many epochs: the peer-memory exchange alternates between its two slot sets
     a, m = e.cursor_allgather(1000 + 7 * r + k)
     assert a.tolist() == [1000 + k, 1007 + k] and m == 1000 + k, (a, m)
+    if k % 50 == r:  # skew the ranks against each other
+        time.sleep(0.002)
+e.prof_enable(0)
+names = {p["name"] for p in e.prof_read() if p["launches"]}
+dist.barrier()
+t0 = time.perf_counter()
+for k in range(200):
+    e.cursor_allgather(5000 + k)
+dt = (time.perf_counter() - t0) / 200
 dist.barrier()
 if r == 0:
-    print("OK")
+    print("OK mode=%s %.1f us per exchange" % ("p2p" if "k_cursor_p2p" in names else "nccl", dt * 1e6))
 e.close()
 dist.destroy_process_group()
