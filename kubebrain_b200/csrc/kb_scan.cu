@@ -544,7 +544,7 @@ k_gather_jobs(StoreDev st, const ReqDev *__restrict__ reqs, uint32_t nreq, const
 }
 
 // ---- k_gather: bulk-TMA copy of every winner's [internal key, padded][value, padded] into the response arena.
-// One elected lane per warp drives a ring of GATHER_STAGES shared-memory buffers: cp.async.bulk global->shared
+// One elected lane per warp drives a ring of `stages` shared-memory buffers: cp.async.bulk global->shared
 // (completion on an mbarrier), then cp.async.bulk shared->global into the arena.  A kv larger than one buffer is
 // moved in pieces.  The copy engine generates full-line requests; the SM only issues two or three instructions per
 // 2.5 KB piece.
@@ -1019,7 +1019,7 @@ int upload_layout(kb_ctx *ctx, const Resolved &R)
 // host copy of the slab offsets, kept for algorithmic-byte accounting only
 static inline std::vector<uint32_t> &host_koff16(kb_ctx *ctx) { return ctx->h_koff16; }
 
-// persistent decode pass: one CTA per SM, 8 independent warps each
+// persistent decode pass: one CTA per SM, DECODE_WARPS independent warps each
 static int launch_decode(kb_ctx *ctx, uint32_t ntiles, uint64_t alg_bytes, const ScanMode &mode, const ReqDev *d_reqs,
                          const TileDev *d_tiles, uint32_t *d_meta, uint2 *d_agg)
 {
