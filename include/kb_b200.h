@@ -95,7 +95,11 @@ int kb_set_compact_revision(kb_ctx *ctx, int present, uint64_t rev);
  * (pkg/backend/scanner/scanner.go:83-145, 389-516; receivers scanner/receiver.go:62-103) */
 enum {
     KB_OUT_HOST = 0,    /* results copied to pinned host memory inside the call                    */
-    KB_OUT_DEVICE = 1,  /* results stay in HBM; the view holds device pointers                      */
+    KB_OUT_DEVICE = 1,  /* results stay in HBM; the view holds device pointers.  kb_range_batch returns as soon
+                           as the per-request counts are known, while the copy into the arena may still be
+                           running: the arena and the per-kv arrays are valid IN STREAM ORDER on kb_stream(ctx)
+                           (launch consumers there, or make another stream wait on an event recorded there);
+                           call kb_sync(ctx) before touching them from the host or from an unrelated stream      */
     KB_OUT_COUNT = 2,   /* emptyResultReceiver: counts only (scanner.Count)                         */
     /* OR-ed into KB_OUT_HOST / KB_OUT_DEVICE: the arena holds the answer as etcd protobuf elements, one per
      * emitted kv in emission order, ready to be framed and sent (go.etcd.io/etcd/api/v3 v3.5.2 field numbers):

@@ -103,6 +103,25 @@ class KbProfEntry(C.Structure):
 
 
 _lib = None
+_rt = None
+
+
+def _cudart():
+    """the CUDA runtime libkbb200.so itself is linked against (tests read device-resident results through it)"""
+    global _rt
+    if _rt is None:
+        lib()
+        for name in ("libcudart.so.12", "libcudart.so"):
+            try:
+                _rt = C.CDLL(name)
+                break
+            except OSError:
+                continue
+        if _rt is None:
+            raise RuntimeError("libcudart not loadable")
+        _rt.cudaMemcpy.restype = C.c_int
+        _rt.cudaMemcpy.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]
+    return _rt
 
 
 def lib():
@@ -539,6 +558,18 @@ class Engine:
 
     def sync(self):
         self._check(lib().kb_sync(self._ctx))
+
+    def read_device(self, ptr: int, nbytes: int) -> bytes:
+        """copy `nbytes` of a KB_OUT_DEVICE result to the host (after kb_sync: device results are valid in stream order)"""
+        self.sync()
+        if nbytes == 0:
+            return b""
+        rt = _cudart()
+        buf = (C.c_uint8 * nbytes)()
+        rc = rt.cudaMemcpy(buf, C.c_void_p(ptr), C.c_size_t(nbytes), 2)  # cudaMemcpyDeviceToHost
+        if rc != 0:
+            raise KbError(KB_ECUDA, f"cudaMemcpy failed with {rc}")
+        return bytes(buf)
 
     def prof_enable(self, level: int):
         """0 off, 1 every kernel, 2 only the two HBM-bound kernels"""

@@ -225,7 +225,8 @@ extern "C" int kb_open(int device_ordinal, const kb_config *cfg, kb_ctx **out)
     int prio_lo = 0, prio_hi = 0;
     if (cudaSetDevice(device_ordinal) != cudaSuccess ||
         cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi) != cudaSuccess ||
-        cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, high ? prio_hi : prio_lo) != cudaSuccess) {
+        cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, high ? prio_hi : prio_lo) != cudaSuccess ||
+        cudaStreamCreateWithPriority(&ctx->stream2, cudaStreamNonBlocking, high ? prio_hi : prio_lo) != cudaSuccess) {
         delete ctx;
         return KB_ECUDA;
     }
@@ -273,6 +274,8 @@ extern "C" void kb_close(kb_ctx *ctx)
             if (f) f(ctx->nccl_comm);
         }
     }
+    if (ctx->h_rout) cudaFreeHost(ctx->h_rout);
+    if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }

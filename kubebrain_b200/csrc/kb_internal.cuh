@@ -158,6 +158,11 @@ struct WatchTablesDev;  // kb_watch.cu
 struct kb_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t stream2 = nullptr;  // bound search of a range batch: runs beside the tail (gather) of the previous batch
+    // per-request results (ReqOut) published by the device into mapped pinned memory: [flag u64 | pad to 64 | rows]
+    uint8_t *h_rout = nullptr;
+    size_t   h_rout_cap = 0;
+    uint64_t rout_epoch = 0;
     std::string err;
     std::mutex mu;
 

@@ -806,12 +806,34 @@ k_seg_copy(const uint4 *__restrict__ srcA, const uint4 *__restrict__ srcB, const
     }
 }
 
+// The per-request rows are the only thing the host needs before it can return a device-resident answer: the device
+// stores them into mapped pinned memory and then raises the epoch flag, the host polls the flag -- no copy, no stream
+// synchronisation, and the gather that follows keeps running after the call has returned.
+__device__ __forceinline__ void publish_rout(const ReqOut *__restrict__ rout, uint32_t nreq, uint8_t *host, uint64_t epoch)
+{
+    const uint4 *src = (const uint4 *)rout;
+    uint4 *dst = (uint4 *)(host + 64);
+    for (uint32_t i = threadIdx.x; i < nreq * 2; i += blockDim.x) dst[i] = src[i];
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        *(volatile uint64_t *)host = epoch;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_publish_rout(const ReqOut *__restrict__ rout, uint32_t nreq, uint8_t *host,
+                                                      uint64_t epoch)
+{
+    publish_rout(rout, nreq, host, epoch);
+}
+
 // single CTA: per-request emitted count / response bytes (limit applied) and their exclusive prefixes over the
 // requests: job_first[q] = first kv of request q, arena_base[q] = first arena byte of request q; [nreq] = totals
 __global__ void __launch_bounds__(256)
 k_req_finalize(const ReqDev *__restrict__ reqs, uint32_t nreq, const ReqOut *__restrict__ rout,
                uint64_t *__restrict__ job_first, uint64_t *__restrict__ arena_base,
-               unsigned long long *__restrict__ work_ctr)
+               unsigned long long *__restrict__ work_ctr, uint8_t *host_rout, uint64_t epoch)
 {
     if (threadIdx.x == 0) *work_ctr = 0;  // the gather's block counter
     __shared__ uint64_t ws2[18];
@@ -845,6 +867,7 @@ k_req_finalize(const ReqDev *__restrict__ reqs, uint32_t nreq, const ReqOut *__r
         job_first[nreq] = carry[0];
         arena_base[nreq] = carry[1];
     }
+    publish_rout(rout, nreq, host_rout, epoch);
 }
 
 }  // namespace
@@ -968,15 +991,19 @@ int resolve_requests(kb_ctx *ctx, const kb_range_req *reqs, uint64_t nreq, bool 
     // one upload: [bound keys | offsets | lengths] are contiguous in the pinned staging buffer
     KB_TRY(dbuf_ensure(ctx, ctx->d_bounds, chunks * 16 + nb * 8 + 64));
     KB_TRY(dbuf_ensure(ctx, ctx->d_bres, nb * 4));
-    KB_CUDA(ctx, cudaMemcpyAsync(ctx->d_bounds.p, hs, chunks * 16 + nb * 8, cudaMemcpyHostToDevice, ctx->stream));
+    // The search only reads the snapshot and its own bound slab, so it runs on the second stream: while the previous
+    // batch's gather is still draining on the main stream the host already learns the record intervals of this one.
+    // (With every kernel bracketed by profiling events -- level 1 -- it stays on the main stream.)
+    cudaStream_t ss = ctx->prof_on == 1 ? ctx->stream : ctx->stream2;
+    KB_CUDA(ctx, cudaMemcpyAsync(ctx->d_bounds.p, hs, chunks * 16 + nb * 8, cudaMemcpyHostToDevice, ss));
     const uint32_t *d_boff = (const uint32_t *)((const uint8_t *)ctx->d_bounds.p + chunks * 16);
     const unsigned sgrid = (unsigned)((nb * 32 + 127) / 128);
     KB_LAUNCH(ctx, "k_search", nb * 64,
-              (k_search<<<sgrid, 128, 0, ctx->stream>>>(ctx->st, (const uint4 *)ctx->d_bounds.p, d_boff, d_boff + nb,
-                                                        (uint32_t)nb, (uint32_t *)ctx->d_bres.p)));
-    KB_CUDA(ctx, cudaMemcpyAsync(hres, ctx->d_bres.p, nb * 4, cudaMemcpyDeviceToHost, ctx->stream));
+              (k_search<<<sgrid, 128, 0, ss>>>(ctx->st, (const uint4 *)ctx->d_bounds.p, d_boff, d_boff + nb, (uint32_t)nb,
+                                               (uint32_t *)ctx->d_bres.p)));
+    KB_CUDA(ctx, cudaMemcpyAsync(hres, ctx->d_bres.p, nb * 4, cudaMemcpyDeviceToHost, ss));
     if (tseg) kb_seg(ctx, "host:range_search_enqueue", *tseg);
-    KB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    KB_CUDA(ctx, cudaStreamSynchronize(ss));
     if (tseg) kb_seg(ctx, "host:range_search_sync", *tseg);
 
     R.reqs.resize(nreq);
@@ -1159,6 +1186,40 @@ static int probe_limit_windows(kb_ctx *ctx, Resolved &R)
     return layout_requests(ctx, true, R);
 }
 
+static_assert(sizeof(ReqOut) == 32, "publish_rout copies ReqOut rows as two 16-byte words");
+
+static int rout_map_ensure(kb_ctx *ctx, uint64_t nreq)
+{
+    const size_t need = 64 + std::max<uint64_t>(nreq, 1) * sizeof(ReqOut);
+    if (ctx->h_rout && ctx->h_rout_cap >= need) return KB_OK;
+    if (ctx->h_rout) {
+        KB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        cudaFreeHost(ctx->h_rout);
+        ctx->h_rout = nullptr;
+        ctx->h_rout_cap = 0;
+    }
+    const size_t cap = need + need / 2;
+    KB_CUDA(ctx, cudaHostAlloc((void **)&ctx->h_rout, cap, cudaHostAllocMapped));
+    memset(ctx->h_rout, 0, cap);
+    ctx->h_rout_cap = cap;
+    return KB_OK;
+}
+
+// wait until the device has published the rows of `epoch`; the stream is only consulted now and then, to notice a
+// failed launch or kernel instead of spinning forever
+static int rout_wait(kb_ctx *ctx, uint64_t epoch)
+{
+    volatile uint64_t *flag = (volatile uint64_t *)ctx->h_rout;
+    for (uint64_t spins = 1;; spins++) {
+        if (*flag == epoch) return KB_OK;
+        if ((spins & 0xFFFF) == 0) {
+            const cudaError_t q = cudaStreamQuery(ctx->stream);
+            if (q == cudaSuccess) return *flag == epoch ? KB_OK : kb_fail(ctx, KB_ECUDA, "range scan: results were not published");
+            if (q != cudaErrorNotReady) return kb_cuda_fail(ctx, q, "range scan");
+        }
+    }
+}
+
 extern "C" int kb_range_batch(kb_ctx *ctx, const kb_range_req *reqs, uint64_t nreq, int out_mode, kb_result **out)
 {
     if (!ctx || !out || (nreq && !reqs)) return KB_EINVAL;
@@ -1197,6 +1258,8 @@ extern "C" int kb_range_batch(kb_ctx *ctx, const kb_range_req *reqs, uint64_t nr
     mode.timeout_rev = 0;
     mode.wire = wire;
     KB_TRY(launch_scan_core(ctx, R, mode, out_mode != KB_OUT_COUNT));
+    KB_TRY(rout_map_ensure(ctx, nreq));
+    const uint64_t epoch = ++ctx->rout_epoch;
 
     // Response arena: sized by an upper bound the host knows without a round trip (all key+value bytes of the examined
     // record intervals), so the gather is enqueued right behind the placement and the only synchronisation left is
@@ -1248,7 +1311,7 @@ extern "C" int kb_range_batch(kb_ctx *ctx, const kb_range_req *reqs, uint64_t nr
         GatherJob *d_gj = (GatherJob *)ctx->d_gjobs.p;
         KB_LAUNCH(ctx, "k_req_finalize", nreq * 64,
                   (k_req_finalize<<<1, 256, 0, ctx->stream>>>(d_reqs, (uint32_t)nreq, d_rout, d_jobfirst, d_arenabase,
-                                                              d_workctr)));
+                                                              d_workctr, ctx->h_rout, epoch)));
         const unsigned jgrid = (unsigned)std::min<uint64_t>((cap_kvs + 255) / 256, 148 * 8);
         if (wire) {
             rc = dbuf_ensure(ctx, ctx->d_gjobs, std::max<uint64_t>(cap_kvs, 1) * sizeof(WireJob));
@@ -1289,16 +1352,16 @@ extern "C" int kb_range_batch(kb_ctx *ctx, const kb_range_req *reqs, uint64_t nr
         }
     }
     std::vector<ReqOut> rout(std::max<uint64_t>(nreq, 1));
-    if (nreq) {
-        KB_TRY(hbuf_ensure(ctx, ctx->h_stage, nreq * sizeof(ReqOut) + 64));
-        KB_CUDA(ctx, cudaMemcpyAsync(ctx->h_stage.p, d_rout, nreq * sizeof(ReqOut), cudaMemcpyDeviceToHost,
-                                     ctx->stream));
+    if (!want_kvs && nreq) {  // count-only / empty answers: nothing ran k_req_finalize, publish the rows directly
+        KB_LAUNCH(ctx, "k_publish_rout", nreq * 32,
+                  (k_publish_rout<<<1, 256, 0, ctx->stream>>>(d_rout, (uint32_t)nreq, ctx->h_rout, epoch)));
     }
     kb_seg(ctx, "host:range_launch", tseg);
-    cudaError_t e1 = cudaStreamSynchronize(ctx->stream);
+    if (nreq) {
+        KB_TRY(rout_wait(ctx, epoch));
+        memcpy(rout.data(), ctx->h_rout + 64, nreq * sizeof(ReqOut));
+    }
     kb_seg(ctx, "host:range_sync", tseg);
-    if (e1 != cudaSuccess) return kb_cuda_fail(ctx, e1, "range scan");
-    if (nreq) memcpy(rout.data(), ctx->h_stage.p, nreq * sizeof(ReqOut));
 
     res->req_first.resize(nreq + 1);
     res->req_count.resize(nreq);

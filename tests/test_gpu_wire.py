@@ -152,3 +152,26 @@ def test_wire_rejects_count_mode(eng):
         eng.range_batch([(b"\x00", b"\xff", 0, 0)], KB_OUT_COUNT | KB_WIRE_ETCD_KVS)
     with pytest.raises(KbError):
         eng.range_batch([(b"\x00", b"\xff", 0, 0)], KB_OUT_HOST | KB_WIRE_ETCD_KVS | KB_WIRE_ETCD_EVENTS)
+
+
+def test_device_resident_results_match_host_results(eng):
+    """KB_OUT_DEVICE returns before the copy into the arena has finished (stream-ordered results): after kb_sync the
+    arena holds exactly the bytes KB_OUT_HOST returns, in the arena and in both wire modes, call after call"""
+    store, meta = synth.gen_store(20000, 4, 256, 2048, 50, config_id=2)
+    eng.load_sorted(store)
+    eng.set_compact_revision(None)
+    lo, hi = CODER.encode_object_key(b"/registry/", 0), CODER.encode_object_key(b"/registry0", 0)
+    p = b"/registry/pods/"
+    reqs = [(lo, hi, meta.read_rev, 0), (CODER.encode_object_key(p, 0), CODER.encode_object_key(prefix_end(p), 0),
+                                         meta.read_rev, 501)]
+    for mode in (0, KB_WIRE_ETCD_KVS, KB_WIRE_ETCD_EVENTS):
+        host = eng.range_batch(reqs, KB_OUT_HOST | mode)
+        want = host.arena.tobytes()
+        # several device-resident calls back to back: each one starts while the previous gather may still be running
+        devs = [eng.range_batch(reqs, KB_OUT_DEVICE | mode) for _ in range(4)]
+        for d in devs:
+            assert (d.n_kvs, d.n_bytes) == (host.n_kvs, host.n_bytes)
+            assert d.req_count.tolist() == host.req_count.tolist()
+            assert eng.read_device(d.bytes_ptr, d.n_bytes) == want
+            d.close()
+        host.close()
