@@ -223,7 +223,8 @@ def workload_config(world: int, wl):
         "events_per_gpu": int(wl["events"].n), "read_rev": int(wl["meta"].read_rev),
         "parallelism": f"hash-shard x{world}" if world > 1 else "single GPU",
         "l2": "inputs larger than L2 (>= 0.7 GB streamed from HBM per step)",
-        "overlap": "scan and fan-out run concurrently on two streams of the same GPU (two kb_ctx)",
+        "overlap": "scan and fan-out run concurrently on two kb_ctx of the same GPU; device-resident answers are "
+                   "stream ordered, so a batch's copy into the arena overlaps the next batch's decode",
         "unit_of_work": "records examined + events matched",
     }
 
@@ -246,9 +247,10 @@ def run_b200(args, rank: int, local_rank: int, world: int):
     wl = build_workload(rank, world)
     # two contexts on the same GPU, as in the reference where scans and the watch hub are independent goroutines:
     # `eng` owns the HBM-resident snapshot (scans), `weng` owns the watcher tables (fan-out); each has its own stream
-    eng = Engine(local_rank, high_priority=not args.serial)  # the scan chain is the critical path of a step
+    prio = os.environ.get("KB_BENCH_PRIO", "scan")  # which context gets the high-priority streams: scan | fanout | none
+    eng = Engine(local_rank, high_priority=(prio == "scan" and not args.serial))
     eng.load_sorted(wl["store"])
-    weng = eng if args.serial else Engine(local_rank)
+    weng = eng if args.serial else Engine(local_rank, high_priority=(prio == "fanout"))
     weng.watch_add_many(wl["watchers"])
     # the revision-cursor communicator (one uint64 per rank)
     uid = Engine.nccl_unique_id() if rank == 0 else bytes(128)
@@ -359,6 +361,11 @@ def run_b200(args, rank: int, local_rank: int, world: int):
         out = None
         for _ in range(steps):
             out = fn()
+        # device-resident answers return while their last copy is still running on the context's copy stream:
+        # drain both contexts before the end events so that the timed region holds ALL the work of the K steps
+        eng.sync()
+        if weng is not eng:
+            weng.sync()
         b.record(stream)
         bw.record(wstream)
         barrier()

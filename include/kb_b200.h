@@ -97,9 +97,9 @@ enum {
     KB_OUT_HOST = 0,    /* results copied to pinned host memory inside the call                    */
     KB_OUT_DEVICE = 1,  /* results stay in HBM; the view holds device pointers.  kb_range_batch returns as soon
                            as the per-request counts are known, while the copy into the arena may still be
-                           running: the arena and the per-kv arrays are valid IN STREAM ORDER on kb_stream(ctx)
-                           (launch consumers there, or make another stream wait on an event recorded there);
-                           call kb_sync(ctx) before touching them from the host or from an unrelated stream      */
+                           running on the context's copy stream: order consumers behind it with
+                           kb_result_wait(ctx, res, their_stream), or call kb_result_wait(ctx, res, NULL) /
+                           kb_sync(ctx) before touching the arena or the per-kv arrays from the host              */
     KB_OUT_COUNT = 2,   /* emptyResultReceiver: counts only (scanner.Count)                         */
     /* OR-ed into KB_OUT_HOST / KB_OUT_DEVICE: the arena holds the answer as etcd protobuf elements, one per
      * emitted kv in emission order, ready to be framed and sent (go.etcd.io/etcd/api/v3 v3.5.2 field numbers):
@@ -145,6 +145,9 @@ typedef struct kb_range_view {
 /* One call = one batch of independent scanner.Range requests answered on one snapshot. */
 int kb_range_batch(kb_ctx *ctx, const kb_range_req *reqs, uint64_t n_req, int out_mode, kb_result **out);
 int kb_range_view_get(const kb_result *res, kb_range_view *view);
+/* Completion of a KB_OUT_DEVICE range answer: cuda_stream (a cudaStream_t) is made to wait for it on the device;
+ * with cuda_stream == NULL the calling host thread blocks until it is complete.  No-op for host-resident results. */
+int kb_result_wait(kb_ctx *ctx, const kb_result *res, void *cuda_stream);
 
 /* Framing around the wire elements (host side, a few bytes each; return the byte count written, out >= 32 bytes
  * [+ reason_len for the watch head]):

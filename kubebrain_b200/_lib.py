@@ -33,7 +33,7 @@ KB_OP_PUT, KB_OP_DEL = 0, 1
 ABI_SYMBOLS = [
     "kb_abi_version", "kb_open", "kb_close", "kb_last_error", "kb_stream", "kb_sync",
     "kb_load_sorted", "kb_store_info", "kb_dump", "kb_restore", "kb_apply_batch", "kb_set_compact_revision",
-    "kb_range_batch", "kb_range_view_get", "kb_wire_range_head", "kb_wire_range_tail", "kb_wire_watch_head",
+    "kb_range_batch", "kb_range_view_get", "kb_result_wait", "kb_wire_range_head", "kb_wire_range_tail", "kb_wire_watch_head",
     "kb_get_batch", "kb_get_view_get",
     "kb_compact_sweep", "kb_compact_view_get",
     "kb_watch_add", "kb_watch_del", "kb_watch_count", "kb_watch_match", "kb_events_upload", "kb_events_free",
@@ -162,6 +162,8 @@ def lib():
     L.kb_range_batch.argtypes = [vp, C.POINTER(KbRangeReq), C.c_uint64, C.c_int, C.POINTER(vp)]
     L.kb_range_view_get.restype = C.c_int
     L.kb_range_view_get.argtypes = [vp, C.POINTER(KbRangeView)]
+    L.kb_result_wait.restype = C.c_int
+    L.kb_result_wait.argtypes = [vp, vp, vp]
     L.kb_wire_range_head.restype = C.c_uint64
     L.kb_wire_range_head.argtypes = [C.c_uint64, u8p]
     L.kb_wire_range_tail.restype = C.c_uint64
@@ -269,6 +271,10 @@ class RangeResult:
             ko, kl, vo, vl = int(self.key_off[k]), int(self.key_len[k]), int(self.val_off[k]), int(self.val_len[k])
             out.append((self.arena[ko : ko + kl].tobytes(), self.arena[vo : vo + vl].tobytes(), int(self.rev[k])))
         return out
+
+    def wait(self, cuda_stream: int = 0):
+        """KB_OUT_DEVICE answers: order `cuda_stream` behind the copy into the arena (0: block the host instead)"""
+        self._eng._check(lib().kb_result_wait(self._eng._ctx, self._h, C.c_void_p(cuda_stream or None)))
 
     def rec_indices(self, q: int = 0) -> np.ndarray:
         return self.rec_idx[int(self.req_first[q]) : int(self.req_first[q + 1])].copy()
@@ -559,9 +565,11 @@ class Engine:
     def sync(self):
         self._check(lib().kb_sync(self._ctx))
 
-    def read_device(self, ptr: int, nbytes: int) -> bytes:
-        """copy `nbytes` of a KB_OUT_DEVICE result to the host (after kb_sync: device results are valid in stream order)"""
-        self.sync()
+    def read_device(self, ptr: int, nbytes: int, sync: bool = True) -> bytes:
+        """copy `nbytes` of a KB_OUT_DEVICE result to the host, after kb_sync (sync=False: the caller has already waited
+        for the answer with RangeResult.wait)"""
+        if sync:
+            self.sync()
         if nbytes == 0:
             return b""
         rt = _cudart()

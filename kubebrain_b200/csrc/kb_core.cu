@@ -36,6 +36,7 @@ int dbuf_ensure(kb_ctx *ctx, DBuf &b, size_t bytes)
     want = (want + 255) & ~(size_t)255;
     if (b.p) {
         KB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (ctx->stream_g) KB_CUDA(ctx, cudaStreamSynchronize(ctx->stream_g));
         cudaFree(b.p);
         b.p = nullptr;
         b.cap = 0;
@@ -51,6 +52,7 @@ int hbuf_ensure(kb_ctx *ctx, HBuf &b, size_t bytes)
     size_t want = std::max(bytes + bytes / 4, (size_t)4096);
     if (b.p) {
         KB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (ctx->stream_g) KB_CUDA(ctx, cudaStreamSynchronize(ctx->stream_g));
         cudaFreeHost(b.p);
         b.p = nullptr;
         b.cap = 0;
@@ -89,6 +91,32 @@ int pool_get_host(kb_ctx *ctx, size_t bytes, HBuf *out)
     HBuf b;
     KB_TRY(hbuf_ensure(ctx, b, bytes));
     *out = b;
+    return KB_OK;
+}
+
+int pool_get_arena(kb_ctx *ctx, size_t bytes, DBuf *out)
+{
+    if (bytes == 0) bytes = 16;
+    if (pool_take(ctx->free_arena, bytes, out)) return KB_OK;
+    DBuf b;
+    KB_TRY(dbuf_ensure(ctx, b, bytes));
+    *out = b;
+    return KB_OK;
+}
+
+void pool_put_arena(kb_ctx *ctx, DBuf b)
+{
+    if (!b.p) return;
+    if (ctx->free_arena.size() >= 8) {
+        cudaFree(b.p);  // implicit device synchronisation: nothing can still be writing it
+        return;
+    }
+    ctx->free_arena.push_back(b);
+}
+
+int ctx_quiesce(kb_ctx *ctx)
+{
+    if (ctx->stream_g) KB_CUDA(ctx, cudaStreamSynchronize(ctx->stream_g));
     return KB_OK;
 }
 
@@ -137,24 +165,25 @@ static cudaEvent_t ev_get(kb_ctx *ctx)
     return e;
 }
 
-void prof_begin(kb_ctx *ctx, int idx, uint64_t alg_bytes)
+void prof_begin(kb_ctx *ctx, int idx, uint64_t alg_bytes, cudaStream_t strm)
 {
     ProfPending p;
     p.idx = idx;
     p.a = ev_get(ctx);
     p.b = ev_get(ctx);
-    cudaEventRecord(p.a, ctx->stream);
+    cudaEventRecord(p.a, strm);
     ctx->prof_pending.push_back(p);
     ctx->prof[idx].launches++;
     ctx->prof[idx].bytes += alg_bytes;
 }
 
-void prof_end(kb_ctx *ctx) { cudaEventRecord(ctx->prof_pending.back().b, ctx->stream); }
+void prof_end(kb_ctx *ctx, cudaStream_t strm) { cudaEventRecord(ctx->prof_pending.back().b, strm); }
 
 static void prof_resolve(kb_ctx *ctx)
 {
     if (ctx->prof_pending.empty()) return;
     cudaStreamSynchronize(ctx->stream);
+    if (ctx->stream_g) cudaStreamSynchronize(ctx->stream_g);
     for (auto &p : ctx->prof_pending) {
         float ms = 0;
         if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) ctx->prof[p.idx].ms += ms;
@@ -226,7 +255,11 @@ extern "C" int kb_open(int device_ordinal, const kb_config *cfg, kb_ctx **out)
     if (cudaSetDevice(device_ordinal) != cudaSuccess ||
         cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi) != cudaSuccess ||
         cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, high ? prio_hi : prio_lo) != cudaSuccess ||
-        cudaStreamCreateWithPriority(&ctx->stream2, cudaStreamNonBlocking, high ? prio_hi : prio_lo) != cudaSuccess) {
+        cudaStreamCreateWithPriority(&ctx->stream2, cudaStreamNonBlocking, high ? prio_hi : prio_lo) != cudaSuccess ||
+        cudaStreamCreateWithPriority(&ctx->stream_g, cudaStreamNonBlocking, high ? prio_hi : prio_lo) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_jobs, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_gather[0], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_gather[1], cudaEventDisableTiming) != cudaSuccess) {
         delete ctx;
         return KB_ECUDA;
     }
@@ -246,11 +279,14 @@ extern "C" void kb_close(kb_ctx *ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    if (ctx->stream_g) cudaStreamSynchronize(ctx->stream_g);
+    if (ctx->stream2) cudaStreamSynchronize(ctx->stream2);
     watch_tables_free(ctx);
     DBuf *all[] = {&ctx->d_kslab, &ctx->d_koff16, &ctx->d_klen, &ctx->d_vslab, &ctx->d_voff16, &ctx->d_vlen, &ctx->d_dir,
                    &ctx->d_bounds, &ctx->d_bres, &ctx->d_reqs,
                    &ctx->d_meta, &ctx->d_tgt, &ctx->d_agg, &ctx->d_tcnt, &ctx->d_tscan, &ctx->d_reqout,
-                   &ctx->d_sel, &ctx->d_slot, &ctx->d_jobs, &ctx->d_gjobs, &ctx->d_flags, &ctx->d_cursor, &ctx->d_ctrs};
+                   &ctx->d_sel, &ctx->d_slot, &ctx->d_jobs, &ctx->d_gjobs, &ctx->d_jobs2, &ctx->d_gjobs2, &ctx->d_flags, &ctx->d_cursor,
+                   &ctx->d_ctrs};
     for (DBuf *b : all) dfree(*b);
     for (auto &b : ctx->free_dev) cudaFree(b.p);
     for (auto &b : ctx->free_host) cudaFreeHost(b.p);
@@ -275,6 +311,11 @@ extern "C" void kb_close(kb_ctx *ctx)
         }
     }
     if (ctx->h_rout) cudaFreeHost(ctx->h_rout);
+    for (auto &b : ctx->free_arena) cudaFree(b.p);
+    if (ctx->ev_jobs) cudaEventDestroy(ctx->ev_jobs);
+    for (int i = 0; i < 2; i++)
+        if (ctx->ev_gather[i]) cudaEventDestroy(ctx->ev_gather[i]);
+    if (ctx->stream_g) cudaStreamDestroy(ctx->stream_g);
     if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -286,7 +327,9 @@ extern "C" void *kb_stream(kb_ctx *ctx) { return ctx ? (void *)ctx->stream : nul
 extern "C" int kb_sync(kb_ctx *ctx)
 {
     if (!ctx) return KB_EINVAL;
+    std::lock_guard<std::mutex> g(ctx->mu);
     KB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->stream_g) KB_CUDA(ctx, cudaStreamSynchronize(ctx->stream_g));
     return KB_OK;
 }
 
@@ -354,6 +397,7 @@ extern "C" int kb_load_sorted(kb_ctx *ctx, const uint8_t *keys, const uint64_t *
     if (!ctx || (n && (!keys || !key_off || !vals || !val_off))) return KB_EINVAL;
     std::lock_guard<std::mutex> g(ctx->mu);
     cudaSetDevice(ctx->device);
+    KB_TRY(ctx_quiesce(ctx));
     if (n >= 0xFFFFFFFEull) return kb_fail(ctx, KB_ELIMIT, "too many records (%llu)", (unsigned long long)n);
     ctx->loaded = false;
 
@@ -550,6 +594,7 @@ extern "C" int kb_dump(kb_ctx *ctx, const char *path)
     std::lock_guard<std::mutex> g(ctx->mu);
     if (!ctx->loaded) return kb_fail(ctx, KB_ESTATE, "no store loaded");
     cudaSetDevice(ctx->device);
+    KB_TRY(ctx_quiesce(ctx));
     KB_TRY(hbuf_ensure(ctx, ctx->h_stage, DUMP_STAGE));
     const std::string tmp = std::string(path) + ".tmp";
     FILE *f = fopen(tmp.c_str(), "wb");
@@ -595,6 +640,7 @@ extern "C" int kb_restore(kb_ctx *ctx, const char *path)
     if (!ctx || !path) return KB_EINVAL;
     std::lock_guard<std::mutex> g(ctx->mu);
     cudaSetDevice(ctx->device);
+    KB_TRY(ctx_quiesce(ctx));
     FILE *f = fopen(path, "rb");
     if (!f) return kb_fail(ctx, KB_EIO, "restore: cannot open %s", path);
     struct Closer {

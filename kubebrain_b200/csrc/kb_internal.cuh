@@ -159,6 +159,12 @@ struct kb_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t stream2 = nullptr;  // bound search of a range batch: runs beside the tail (gather) of the previous batch
+    // The gather / wire copy of a range batch runs on its own stream, so the next batch's decode .. placement (main
+    // stream) overlaps it.  Two sets of job buffers alternate between consecutive batches; ev_gather[set] marks the end
+    // of the last gather that read a set, ev_jobs the end of the current batch's job construction.
+    cudaStream_t stream_g = nullptr;
+    cudaEvent_t ev_jobs = nullptr, ev_gather[2] = {nullptr, nullptr};
+    uint64_t batch_seq = 0;
     // per-request results (ReqOut) published by the device into mapped pinned memory: [flag u64 | pad to 64 | rows]
     uint8_t *h_rout = nullptr;
     size_t   h_rout_cap = 0;
@@ -181,11 +187,13 @@ struct kb_ctx {
 
     // scratch (grow only)
     DBuf d_bounds, d_bres, d_reqs, d_tiles /* alias into d_reqs */, d_meta, d_tgt, d_agg, d_tcnt, d_tscan, d_reqout,
-        d_sel, d_slot, d_jobs, d_gjobs, d_flags, d_ctrs /* work-queue counters, kept at zero between kernels */;
+        d_sel, d_slot, d_jobs, d_gjobs, d_jobs2, d_gjobs2 /* second job-buffer set */, d_flags,
+        d_ctrs /* work-queue counters, kept at zero between kernels */;
     HBuf h_stage, h_stage2;
 
     // buffer pools for results
     std::vector<DBuf> free_dev;
+    std::vector<DBuf> free_arena;  // response arenas: only ever written by the gather stream (or after ctx_quiesce)
     std::vector<HBuf> free_host;
 
     // watchers
@@ -227,6 +235,7 @@ struct kb_result {
     const uint32_t *rec_idx = nullptr;
     const uint64_t *rev = nullptr, *key_off = nullptr, *val_off = nullptr;
     const uint32_t *key_len = nullptr, *val_len = nullptr;
+    cudaEvent_t done_ev = nullptr;         // recorded behind the gather on ctx->stream_g (device-resident range answers)
     int wire = 0;                          // KB_WIRE_*_I
     const uint64_t *elem_off = nullptr;    // wire modes: n_kvs + 1 element offsets into the arena
     // compact
@@ -262,6 +271,10 @@ int kb_cuda_fail(kb_ctx *ctx, cudaError_t e, const char *what);
 int dbuf_ensure(kb_ctx *ctx, DBuf &b, size_t bytes);
 int hbuf_ensure(kb_ctx *ctx, HBuf &b, size_t bytes);
 int pool_get_dev(kb_ctx *ctx, size_t bytes, DBuf *out);
+int pool_get_arena(kb_ctx *ctx, size_t bytes, DBuf *out);
+void pool_put_arena(kb_ctx *ctx, DBuf b);
+// wait for the gather stream: every entry point other than kb_range_batch starts with it
+int ctx_quiesce(kb_ctx *ctx);
 int pool_get_host(kb_ctx *ctx, size_t bytes, HBuf *out);
 void pool_put_dev(kb_ctx *ctx, DBuf b);
 void pool_put_host(kb_ctx *ctx, HBuf b);
@@ -269,21 +282,22 @@ void pool_put_host(kb_ctx *ctx, HBuf b);
 // profiling: bracket a kernel launch with events when enabled
 int prof_index(kb_ctx *ctx, const char *name);
 static inline bool prof_major(const char *n) { return n[0] == 'k' && n[1] == '_' && ((n[2] == 'd' && n[3] == 'e') || (n[2] == 'g' && n[3] == 'a' && n[8] == 0)); }
-void prof_begin(kb_ctx *ctx, int idx, uint64_t alg_bytes);
-void prof_end(kb_ctx *ctx);
+void prof_begin(kb_ctx *ctx, int idx, uint64_t alg_bytes, cudaStream_t strm);
+void prof_end(kb_ctx *ctx, cudaStream_t strm);
 
-#define KB_LAUNCH(ctx, name, bytes, ...)                      \
+#define KB_LAUNCH_S(ctx, strm, name, bytes, ...)              \
     do {                                                      \
         static thread_local int _pi = -1;                     \
         const bool _p = (ctx)->prof_on == 1 || ((ctx)->prof_on == 2 && prof_major(name)); \
         if (_p) {                                             \
             _pi = prof_index((ctx), (name));                  \
-            prof_begin((ctx), _pi, (bytes));                  \
+            prof_begin((ctx), _pi, (bytes), (strm));          \
         }                                                     \
         __VA_ARGS__;                                          \
         (ctx)->launches++;                                    \
-        if (_p) prof_end((ctx));                              \
+        if (_p) prof_end((ctx), (strm));                      \
     } while (0)
+#define KB_LAUNCH(ctx, name, bytes, ...) KB_LAUNCH_S(ctx, (ctx)->stream, name, bytes, __VA_ARGS__)
 
 // host wall-clock segments (with kb_prof_enable(ctx, 1 or 2)): where the non-kernel time of a call goes
 typedef std::chrono::steady_clock::time_point kb_tp;

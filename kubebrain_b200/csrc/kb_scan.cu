@@ -890,7 +890,8 @@ static void result_release_locked(kb_ctx *ctx, kb_result *res)
     if (ctx) {
         pool_put_host(ctx, res->h_meta);
         pool_put_host(ctx, res->h_bytes);
-        pool_put_dev(ctx, res->d_bytes);
+        pool_put_arena(ctx, res->d_bytes);
+        if (res->done_ev) ctx->ev_pool.push_back(res->done_ev);
         pool_put_host(ctx, res->h_vic);
         pool_put_dev(ctx, res->d_vic);
         pool_put_host(ctx, res->h_match);
@@ -1068,8 +1069,8 @@ static int launch_decode(kb_ctx *ctx, uint32_t ntiles, uint64_t alg_bytes, const
 }
 
 // bulk-TMA gather of `n_jobs` (upper bound) copy jobs into `arena`
-static int launch_gather(kb_ctx *ctx, const GatherJob *d_jobs, const uint64_t *d_njobs, unsigned long long *d_ctr,
-                         uint4 *arena, uint64_t n_jobs, uint64_t alg_bytes)
+static int launch_gather(kb_ctx *ctx, cudaStream_t strm, const GatherJob *d_jobs, const uint64_t *d_njobs,
+                         unsigned long long *d_ctr, uint4 *arena, uint64_t n_jobs, uint64_t alg_bytes)
 {
     uint32_t piece, stages;
     gather_geometry(ctx->max_kv_chunks, &piece, &stages);
@@ -1081,9 +1082,8 @@ static int launch_gather(kb_ctx *ctx, const GatherJob *d_jobs, const uint64_t *d
     }
     const unsigned ggrid =
         (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((n_jobs + GATHER_WARPS * 32 - 1) / (GATHER_WARPS * 32), 2 * 148));
-    KB_LAUNCH(ctx, "k_gather", alg_bytes,
-              (k_gather<<<ggrid, GATHER_WARPS * 32, gsmem, ctx->stream>>>(ctx->st, d_jobs, d_njobs, arena, piece, stages,
-                                                                          d_ctr)));
+    KB_LAUNCH_S(ctx, strm, "k_gather", alg_bytes,
+                (k_gather<<<ggrid, GATHER_WARPS * 32, gsmem, strm>>>(ctx->st, d_jobs, d_njobs, arena, piece, stages, d_ctr)));
     return KB_OK;
 }
 
@@ -1292,11 +1292,19 @@ extern "C" int kb_range_batch(kb_ctx *ctx, const kb_range_req *reqs, uint64_t nr
     uint64_t *d_elem_off = nullptr;
     const size_t meta_cap = cap_kvs * (wire ? 44 : 36) + 64 + 8;
     int rc = KB_OK;
+    // The copy into the arena runs on the gather stream.  Consecutive batches alternate between two sets of job
+    // buffers, so this batch's job construction (main stream) may overlap the previous batch's copy; it only has to
+    // wait for the copy that last READ this set (two batches ago).
+    const int set = (int)(ctx->batch_seq++ & 1);
+    DBuf &jb = set ? ctx->d_jobs2 : ctx->d_jobs;
+    DBuf &gb = set ? ctx->d_gjobs2 : ctx->d_gjobs;
+    cudaStream_t sg = ctx->stream_g;
     if (want_kvs) {
         rc = pool_get_dev(ctx, meta_cap, &d_om);
-        if (rc == KB_OK) rc = pool_get_dev(ctx, ub_bytes + 64, &res->d_bytes);
-        if (rc == KB_OK) rc = dbuf_ensure(ctx, ctx->d_jobs, (nreq + 1) * 16 + 8);
-        if (rc == KB_OK) rc = dbuf_ensure(ctx, ctx->d_gjobs, std::max<uint64_t>(cap_kvs, 1) * sizeof(GatherJob));
+        if (rc == KB_OK) rc = pool_get_arena(ctx, ub_bytes + 64, &res->d_bytes);
+        if (rc == KB_OK) rc = dbuf_ensure(ctx, jb, (nreq + 1) * 16 + 8);
+        if (rc == KB_OK)
+            rc = dbuf_ensure(ctx, gb, std::max<uint64_t>(cap_kvs, 1) * (wire ? sizeof(WireJob) : sizeof(GatherJob)));
         if (rc != KB_OK) return rc;
         uint8_t *om = (uint8_t *)d_om.p;
         go.rev = (uint64_t *)om;
@@ -1306,16 +1314,14 @@ extern "C" int kb_range_batch(kb_ctx *ctx, const kb_range_req *reqs, uint64_t nr
         go.rec_idx = (uint32_t *)(wire ? d_elem_off + cap_kvs + 1 : d_elem_off);
         go.key_len = go.rec_idx + cap_kvs;
         go.val_len = go.key_len + cap_kvs;
-        uint64_t *d_jobfirst = (uint64_t *)ctx->d_jobs.p, *d_arenabase = d_jobfirst + nreq + 1;
+        uint64_t *d_jobfirst = (uint64_t *)jb.p, *d_arenabase = d_jobfirst + nreq + 1;
         unsigned long long *d_workctr = (unsigned long long *)(d_arenabase + nreq + 1);  // zeroed by k_req_finalize
-        GatherJob *d_gj = (GatherJob *)ctx->d_gjobs.p;
+        KB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_gather[set], 0));
         KB_LAUNCH(ctx, "k_req_finalize", nreq * 64,
                   (k_req_finalize<<<1, 256, 0, ctx->stream>>>(d_reqs, (uint32_t)nreq, d_rout, d_jobfirst, d_arenabase,
                                                               d_workctr, ctx->h_rout, epoch)));
         const unsigned jgrid = (unsigned)std::min<uint64_t>((cap_kvs + 255) / 256, 148 * 8);
         if (wire) {
-            rc = dbuf_ensure(ctx, ctx->d_gjobs, std::max<uint64_t>(cap_kvs, 1) * sizeof(WireJob));
-            if (rc != KB_OK) return rc;
             WireOut wo;
             wo.rec_idx = go.rec_idx;
             wo.rev = go.rev;
@@ -1324,11 +1330,13 @@ extern "C" int kb_range_batch(kb_ctx *ctx, const kb_range_req *reqs, uint64_t nr
             wo.val_off = go.val_off;
             wo.val_len = go.val_len;
             wo.elem_off = d_elem_off;
-            WireJob *d_wj = (WireJob *)ctx->d_gjobs.p;
+            WireJob *d_wj = (WireJob *)gb.p;
             KB_LAUNCH(ctx, "k_wire_jobs", cap_kvs * 20,
                       (k_wire_jobs<<<jgrid, 256, 0, ctx->stream>>>(ctx->st, d_reqs, (uint32_t)nreq, d_jobfirst, d_arenabase,
                                                                   (const uint32_t *)ctx->d_sel.p,
                                                                   (const uint64_t *)ctx->d_slot.p, wire, d_wj, wo)));
+            KB_CUDA(ctx, cudaEventRecord(ctx->ev_jobs, ctx->stream));
+            KB_CUDA(ctx, cudaStreamWaitEvent(sg, ctx->ev_jobs, 0));
             uint32_t slot_chunks, wstages;
             wire_geometry(ctx->max_kv_chunks, &slot_chunks, &wstages);
             const size_t wsmem = (size_t)WIRE_WARPS * wstages * slot_chunks * 16;
@@ -1339,17 +1347,29 @@ extern "C" int kb_range_batch(kb_ctx *ctx, const kb_range_req *reqs, uint64_t nr
             }
             const unsigned wgrid =
                 (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((cap_kvs + WIRE_WARPS - 1) / WIRE_WARPS, 2 * 148));
-            KB_LAUNCH(ctx, "k_wire_copy", 0,
-                      (k_wire_copy<<<wgrid, WIRE_WARPS * 32, wsmem, ctx->stream>>>(ctx->st, d_wj, d_jobfirst + nreq,
-                                                                                 (uint8_t *)res->d_bytes.p, slot_chunks,
-                                                                                 wstages)));
+            KB_LAUNCH_S(ctx, sg, "k_wire_copy", 0,
+                        (k_wire_copy<<<wgrid, WIRE_WARPS * 32, wsmem, sg>>>(ctx->st, d_wj, d_jobfirst + nreq,
+                                                                          (uint8_t *)res->d_bytes.p, slot_chunks, wstages)));
         } else {
-        KB_LAUNCH(ctx, "k_gather_jobs", cap_kvs * 20,
-                  (k_gather_jobs<<<jgrid, 256, 0, ctx->stream>>>(ctx->st, d_reqs, (uint32_t)nreq, d_jobfirst, d_arenabase,
-                                                                (const uint32_t *)ctx->d_sel.p,
-                                                                (const uint64_t *)ctx->d_slot.p, d_gj, go)));
-        KB_TRY(launch_gather(ctx, d_gj, d_jobfirst + nreq, d_workctr, (uint4 *)res->d_bytes.p, cap_kvs, 0));
+            GatherJob *d_gj = (GatherJob *)gb.p;
+            KB_LAUNCH(ctx, "k_gather_jobs", cap_kvs * 20,
+                      (k_gather_jobs<<<jgrid, 256, 0, ctx->stream>>>(ctx->st, d_reqs, (uint32_t)nreq, d_jobfirst, d_arenabase,
+                                                                    (const uint32_t *)ctx->d_sel.p,
+                                                                    (const uint64_t *)ctx->d_slot.p, d_gj, go)));
+            KB_CUDA(ctx, cudaEventRecord(ctx->ev_jobs, ctx->stream));
+            KB_CUDA(ctx, cudaStreamWaitEvent(sg, ctx->ev_jobs, 0));
+            KB_TRY(launch_gather(ctx, sg, d_gj, d_jobfirst + nreq, d_workctr, (uint4 *)res->d_bytes.p, cap_kvs, 0));
         }
+        KB_CUDA(ctx, cudaEventRecord(ctx->ev_gather[set], sg));
+        // the answer is complete when this event has fired (kb_result_wait, kb_sync)
+        res->done_ev = nullptr;
+        if (!ctx->ev_pool.empty()) {
+            res->done_ev = ctx->ev_pool.back();
+            ctx->ev_pool.pop_back();
+        } else {
+            KB_CUDA(ctx, cudaEventCreate(&res->done_ev));
+        }
+        KB_CUDA(ctx, cudaEventRecord(res->done_ev, sg));
     }
     std::vector<ReqOut> rout(std::max<uint64_t>(nreq, 1));
     if (!want_kvs && nreq) {  // count-only / empty answers: nothing ran k_req_finalize, publish the rows directly
@@ -1402,12 +1422,12 @@ extern "C" int kb_range_batch(kb_ctx *ctx, const kb_range_req *reqs, uint64_t nr
                 const size_t esz[7] = {8, 8, 8, 8, 4, 4, 4};
                 size_t off = 0;
                 for (int i = 0; i < 7; i++) {
-                    if (cnt[i]) cudaMemcpyAsync(hm + off, srcs[i], cnt[i] * esz[i], cudaMemcpyDeviceToHost, ctx->stream);
+                    if (cnt[i]) cudaMemcpyAsync(hm + off, srcs[i], cnt[i] * esz[i], cudaMemcpyDeviceToHost, sg);
                     off += cnt[i] * esz[i];
                 }
-                cudaMemcpyAsync(res->h_bytes.p, res->d_bytes.p, nbytes, cudaMemcpyDeviceToHost, ctx->stream);
+                cudaMemcpyAsync(res->h_bytes.p, res->d_bytes.p, nbytes, cudaMemcpyDeviceToHost, sg);
             }
-            cudaError_t e = cudaStreamSynchronize(ctx->stream);
+            cudaError_t e = cudaStreamSynchronize(sg);  // behind the gather (which waited for the per-kv arrays)
             kb_seg(ctx, "host:range_d2h", tseg);
             if (rc == KB_OK && e != cudaSuccess) rc = kb_cuda_fail(ctx, e, "range D2H");
             if (rc != KB_OK) return rc;
@@ -1421,7 +1441,7 @@ extern "C" int kb_range_batch(kb_ctx *ctx, const kb_range_req *reqs, uint64_t nr
             res->val_len = res->key_len + nk;
             pool_put_dev(ctx, d_om);
             d_om = DBuf();
-            pool_put_dev(ctx, res->d_bytes);
+            pool_put_arena(ctx, res->d_bytes);
             res->d_bytes = DBuf();
         } else {
             res->rev = go.rev;
@@ -1438,13 +1458,26 @@ extern "C" int kb_range_batch(kb_ctx *ctx, const kb_range_req *reqs, uint64_t nr
         pool_put_dev(ctx, d_om);
         d_om = DBuf();
         if (res->d_bytes.p) {
-            pool_put_dev(ctx, res->d_bytes);
+            pool_put_arena(ctx, res->d_bytes);
             res->d_bytes = DBuf();
         }
     }
     guard.armed = false;
     *out = res;
     kb_seg(ctx, "host:range_finish", tseg);
+    return KB_OK;
+}
+
+extern "C" int kb_result_wait(kb_ctx *ctx, const kb_result *res, void *cuda_stream)
+{
+    if (!ctx || !res) return KB_EINVAL;
+    if (!res->done_ev) return KB_OK;
+    cudaSetDevice(ctx->device);
+    if (cuda_stream) {
+        KB_CUDA(ctx, cudaStreamWaitEvent((cudaStream_t)cuda_stream, res->done_ev, 0));
+    } else {
+        KB_CUDA(ctx, cudaEventSynchronize(res->done_ev));
+    }
     return KB_OK;
 }
 
@@ -1548,6 +1581,7 @@ extern "C" int kb_get_batch(kb_ctx *ctx, const kb_get_req *reqs, uint64_t n, int
     std::lock_guard<std::mutex> g(ctx->mu);
     if (!ctx->loaded) return kb_fail(ctx, KB_ESTATE, "no store loaded");
     cudaSetDevice(ctx->device);
+    KB_TRY(ctx_quiesce(ctx));
     if (n >= 0x7FFFFFFFull) return kb_fail(ctx, KB_ELIMIT, "too many point reads in one batch");
     // bound of read i = EncodeObjectKey(key, revision or MaxUint64) + 0x00: its lower_bound is the first record
     // strictly greater than the start key of the reference's reverse iterator
@@ -1644,7 +1678,7 @@ extern "C" int kb_get_batch(kb_ctx *ctx, const kb_get_req *reqs, uint64_t n, int
         const uint64_t nj = jobs.size();
         rc = dbuf_ensure(ctx, ctx->d_gjobs, nj * sizeof(GatherJob));
         if (rc == KB_OK) rc = dbuf_ensure(ctx, ctx->d_jobs, 64);
-        if (rc == KB_OK) rc = pool_get_dev(ctx, nbytes + 64, &res->d_bytes);
+        if (rc == KB_OK) rc = pool_get_arena(ctx, nbytes + 64, &res->d_bytes);
         if (rc == KB_OK) rc = hbuf_ensure(ctx, ctx->h_stage2, nj * sizeof(GatherJob) + 64);
         if (rc != KB_OK) {
             result_release_locked(ctx, res);
@@ -1656,7 +1690,7 @@ extern "C" int kb_get_batch(kb_ctx *ctx, const kb_get_req *reqs, uint64_t n, int
         memcpy(hj + 64, jobs.data(), nj * sizeof(GatherJob));
         cudaMemcpyAsync(ctx->d_jobs.p, hj, 16, cudaMemcpyHostToDevice, ctx->stream);
         cudaMemcpyAsync(ctx->d_gjobs.p, hj + 64, nj * sizeof(GatherJob), cudaMemcpyHostToDevice, ctx->stream);
-        rc = launch_gather(ctx, (const GatherJob *)ctx->d_gjobs.p, (const uint64_t *)ctx->d_jobs.p,
+        rc = launch_gather(ctx, ctx->stream, (const GatherJob *)ctx->d_gjobs.p, (const uint64_t *)ctx->d_jobs.p,
                            (unsigned long long *)ctx->d_jobs.p + 1, (uint4 *)res->d_bytes.p, nj, 2 * nbytes);
         if (rc != KB_OK) {
             result_release_locked(ctx, res);
@@ -1673,7 +1707,7 @@ extern "C" int kb_get_batch(kb_ctx *ctx, const kb_get_req *reqs, uint64_t n, int
             return rc;
         }
         if (out_mode == KB_OUT_HOST) {
-            pool_put_dev(ctx, res->d_bytes);
+            pool_put_arena(ctx, res->d_bytes);
             res->d_bytes = DBuf();
         }
     }
@@ -1713,6 +1747,7 @@ extern "C" int kb_compact_sweep(kb_ctx *ctx, const uint8_t *start, uint64_t star
     std::lock_guard<std::mutex> g(ctx->mu);
     if (!ctx->loaded) return kb_fail(ctx, KB_ESTATE, "no store loaded");
     cudaSetDevice(ctx->device);
+    KB_TRY(ctx_quiesce(ctx));
     kb_range_req rq;
     rq.start = start;
     rq.start_len = start_len;
@@ -1842,6 +1877,7 @@ extern "C" int kb_apply_batch(kb_ctx *ctx, const kb_write_op *ops, uint64_t n_op
     std::lock_guard<std::mutex> g(ctx->mu);
     if (!ctx->loaded) return kb_fail(ctx, KB_ESTATE, "no store loaded");
     cudaSetDevice(ctx->device);
+    KB_TRY(ctx_quiesce(ctx));
     if (n_ops == 0) return KB_OK;
     // 1. last op per key wins; sort by key (bytes.Compare order)
     std::vector<ApplyOp> all(n_ops);

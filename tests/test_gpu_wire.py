@@ -169,6 +169,8 @@ def test_device_resident_results_match_host_results(eng):
         want = host.arena.tobytes()
         # several device-resident calls back to back: each one starts while the previous gather may still be running
         devs = [eng.range_batch(reqs, KB_OUT_DEVICE | mode) for _ in range(4)]
+        devs[0].wait()  # the first answer alone (host-blocking form of kb_result_wait)
+        assert eng.read_device(devs[0].bytes_ptr, devs[0].n_bytes, sync=False) == want
         for d in devs:
             assert (d.n_kvs, d.n_bytes) == (host.n_kvs, host.n_bytes)
             assert d.req_count.tolist() == host.req_count.tolist()
