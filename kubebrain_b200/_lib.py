@@ -377,6 +377,13 @@ class MatchResult:
         self.start = _np(v.start, self.n_watchers + 1, np.uint64).copy()
         self.event_idx = (_np(v.event_idx, self.n_deliveries, np.uint32).copy()
                           if not self.on_device else np.zeros(0, np.uint32))
+        # KB_OUT_DEVICE: the delivery lists stay in HBM and may still be being written when the call returns (they are
+        # valid in stream order on kb_stream(ctx); kb_sync before reading them from the host)
+        self.event_idx_ptr = int(v.event_idx or 0) if self.on_device else 0
+
+    def device_event_idx(self) -> np.ndarray:
+        raw = self._eng.read_device(self.event_idx_ptr, self.n_deliveries * 4)
+        return np.frombuffer(raw, dtype=np.uint32).copy()
 
     def deliveries(self, watcher_id: int) -> np.ndarray:
         return self.event_idx[int(self.start[watcher_id]) : int(self.start[watcher_id + 1])]

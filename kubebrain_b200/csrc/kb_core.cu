@@ -311,6 +311,7 @@ extern "C" void kb_close(kb_ctx *ctx)
         }
     }
     if (ctx->h_rout) cudaFreeHost(ctx->h_rout);
+    if (ctx->h_wpub) cudaFreeHost(ctx->h_wpub);
     for (auto &b : ctx->free_arena) cudaFree(b.p);
     if (ctx->ev_jobs) cudaEventDestroy(ctx->ev_jobs);
     for (int i = 0; i < 2; i++)

@@ -169,6 +169,8 @@ struct kb_ctx {
     uint8_t *h_rout = nullptr;
     size_t   h_rout_cap = 0;
     uint64_t rout_epoch = 0;
+    uint64_t *h_wpub = nullptr;      // watch match: [0] epoch flag, [1] total deliveries (mapped pinned, device-written)
+    uint64_t wpub_epoch = 0;
     std::string err;
     std::mutex mu;
 

@@ -793,6 +793,30 @@ extern "C" void kb_events_free(kb_ctx *ctx, kb_events_dev *ev)
     delete ev;
 }
 
+// the delivery total, handed to the host through mapped pinned memory as soon as it is known (behind the offsets copy,
+// in front of the write kernel): a device-resident match returns while its delivery lists are still being written
+__global__ void k_publish_total(const uint64_t *__restrict__ total, uint64_t *host, uint64_t epoch)
+{
+    if (threadIdx.x == 0) {
+        host[1] = *total;
+        __threadfence_system();
+        *(volatile uint64_t *)host = epoch;
+    }
+}
+
+static int wpub_wait(kb_ctx *ctx, uint64_t epoch)
+{
+    volatile uint64_t *flag = ctx->h_wpub;
+    for (uint64_t spins = 1;; spins++) {
+        if (*flag == epoch) return KB_OK;
+        if ((spins & 0xFFFF) == 0) {
+            const cudaError_t q = cudaStreamQuery(ctx->stream);
+            if (q == cudaSuccess) return *flag == epoch ? KB_OK : kb_fail(ctx, KB_ECUDA, "watch match: total was not published");
+            if (q != cudaErrorNotReady) return kb_cuda_fail(ctx, q, "watch match");
+        }
+    }
+}
+
 static int match_locked(kb_ctx *ctx, const kb_events_dev *d, int out_mode, kb_result **out)
 {
     kb_tp tseg = kb_now();
@@ -893,6 +917,10 @@ static int match_locked(kb_ctx *ctx, const kb_events_dev *d, int out_mode, kb_re
     // previous call's D (+25 %) and the write kernel refuses to run when it would not fit, so the steady state needs
     // no round trip before the write.
     KB_TRY(hbuf_ensure(ctx, ctx->h_stage2, 64));
+    if (!ctx->h_wpub) {
+        KB_CUDA(ctx, cudaHostAlloc((void **)&ctx->h_wpub, 64, cudaHostAllocMapped));
+        memset(ctx->h_wpub, 0, 64);
+    }
     uint64_t cap = std::max<uint64_t>(T.d_hint + T.d_hint / 4 + 4096, 1 << 16);
     uint64_t D = 0;
     DBuf d_out;
@@ -904,6 +932,13 @@ static int match_locked(kb_ctx *ctx, const kb_events_dev *d, int out_mode, kb_re
         uint64_t *o_start = (uint64_t *)d_out.p;
         uint32_t *o_idx = (uint32_t *)(o_start + W + 1);
         cudaMemcpyAsync(o_start, wstart, (size_t)(W + 1) * 8, cudaMemcpyDeviceToDevice, ctx->stream);
+        uint64_t wepoch = 0;
+        if (out_mode != KB_OUT_HOST) {
+            if (!h_out.p) KB_TRY(pool_get_host(ctx, (size_t)(W + 1) * 8 + 16, &h_out));
+            cudaMemcpyAsync(h_out.p, wstart, (size_t)(W + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream);
+            wepoch = ++ctx->wpub_epoch;
+            k_publish_total<<<1, 32, 0, ctx->stream>>>(total, ctx->h_wpub, wepoch);
+        }
         if (W) {
             const unsigned wgrid = (unsigned)std::max<uint64_t>(std::min<uint64_t>((cap + 255) / 256, 148 * 16),
                                                                 ((uint64_t)W * 32 + 255) / 256);
@@ -911,19 +946,30 @@ static int match_locked(kb_ctx *ctx, const kb_events_dev *d, int out_mode, kb_re
                       (k_expand_write<<<wgrid, 256, 0, ctx->stream>>>(tb, gcnt, gbase, sorted, pm, flag, wstart, wlo, cap,
                                                                      o_idx)));
         }
-        KB_CUDA(ctx, cudaMemcpyAsync(ctx->h_stage2.p, total, 8, cudaMemcpyDeviceToHost, ctx->stream));
-        if (out_mode != KB_OUT_HOST) {  // device-resident result: only the offsets travel, in the same round trip
-            if (!h_out.p) KB_TRY(pool_get_host(ctx, (size_t)(W + 1) * 8 + 16, &h_out));
-            cudaMemcpyAsync(h_out.p, wstart, (size_t)(W + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream);
+        cudaError_t e0 = cudaSuccess;
+        if (out_mode != KB_OUT_HOST) {
+            // device-resident result: the offsets have travelled and the total is published in front of the write
+            // kernel; the host returns on the flag while the delivery lists are still being written (stream order)
+            kb_seg(ctx, "host:match_launch", tseg);
+            rc = wpub_wait(ctx, wepoch);
+            kb_seg(ctx, "host:match_sync", tseg);
+            if (rc != KB_OK) {
+                pool_put_dev(ctx, d_out);
+                pool_put_host(ctx, h_out);
+                return rc;
+            }
+            D = ctx->h_wpub[1];
+        } else {
+            KB_CUDA(ctx, cudaMemcpyAsync(ctx->h_stage2.p, total, 8, cudaMemcpyDeviceToHost, ctx->stream));
+            kb_seg(ctx, "host:match_launch", tseg);
+            e0 = cudaStreamSynchronize(ctx->stream);
+            kb_seg(ctx, "host:match_sync", tseg);
+            if (e0 != cudaSuccess) {
+                pool_put_dev(ctx, d_out);
+                return kb_cuda_fail(ctx, e0, "watch match");
+            }
+            D = *(uint64_t *)ctx->h_stage2.p;
         }
-        kb_seg(ctx, "host:match_launch", tseg);
-        cudaError_t e0 = cudaStreamSynchronize(ctx->stream);
-        kb_seg(ctx, "host:match_sync", tseg);
-        if (e0 != cudaSuccess) {
-            pool_put_dev(ctx, d_out);
-            return kb_cuda_fail(ctx, e0, "watch match");
-        }
-        D = *(uint64_t *)ctx->h_stage2.p;
         T.d_hint = D;
         if (D <= cap) break;
         pool_put_dev(ctx, d_out);  // first call or a burst larger than the hint: grow and write again

@@ -588,9 +588,11 @@ def check_fanout(eng_new, ev: PackedEvents, w: PackedWatchers):
         assert got.event_idx.tolist() == idx.tolist()
         # device-resident slab, device-resident result: same offsets
         h = e.events_upload(ev)
-        d = e.watch_match_dev(h, KB_OUT_DEVICE)
-        assert d.start.tolist() == start.tolist()
-        d.close()
+        ds = [e.watch_match_dev(h, KB_OUT_DEVICE) for _ in range(3)]  # returns before the lists are fully written
+        for d in ds:
+            assert d.start.tolist() == start.tolist() and d.n_deliveries == len(idx)
+            assert d.device_event_idx().tolist() == idx.tolist()
+            d.close()
         e.events_free(h)
         got.close()
     finally:
