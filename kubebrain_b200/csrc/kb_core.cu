@@ -949,8 +949,9 @@ extern "C" int kb_cursor_allgather(kb_ctx *ctx, uint64_t local_rev, uint64_t *al
         // the kernel's last store is the status word in mapped pinned memory: polling it is a few microseconds cheaper
         // than a stream synchronisation; a launch failure or a hung device still ends in the synchronise below
         const auto t0 = std::chrono::steady_clock::now();
-        while (out[n + 1] == 0) {
-            if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(6)) break;
+        for (uint64_t spins = 1; out[n + 1] == 0; spins++) {
+            kb_cpu_relax();
+            if ((spins & 0xFFFF) == 0 && std::chrono::steady_clock::now() - t0 > std::chrono::seconds(6)) break;
         }
         if (out[n + 1] == 0) KB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         if (out[n + 1] != 1) return kb_fail(ctx, KB_ENCCL, "cursor exchange: a peer did not join epoch %llu", (unsigned long long)epoch);

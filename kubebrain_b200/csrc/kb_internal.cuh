@@ -301,6 +301,14 @@ void prof_end(kb_ctx *ctx, cudaStream_t strm);
     } while (0)
 #define KB_LAUNCH(ctx, name, bytes, ...) KB_LAUNCH_S(ctx, (ctx)->stream, name, bytes, __VA_ARGS__)
 
+// one polite spin of a host polling loop (the device publishes results into mapped pinned memory)
+static inline void kb_cpu_relax()
+{
+#if defined(__x86_64__) || defined(__i386__)
+    __builtin_ia32_pause();
+#endif
+}
+
 // host wall-clock segments (with kb_prof_enable(ctx, 1 or 2)): where the non-kernel time of a call goes
 typedef std::chrono::steady_clock::time_point kb_tp;
 static inline kb_tp kb_now() { return std::chrono::steady_clock::now(); }

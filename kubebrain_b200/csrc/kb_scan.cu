@@ -1212,6 +1212,7 @@ static int rout_wait(kb_ctx *ctx, uint64_t epoch)
     volatile uint64_t *flag = (volatile uint64_t *)ctx->h_rout;
     for (uint64_t spins = 1;; spins++) {
         if (*flag == epoch) return KB_OK;
+        kb_cpu_relax();
         if ((spins & 0xFFFF) == 0) {
             const cudaError_t q = cudaStreamQuery(ctx->stream);
             if (q == cudaSuccess) return *flag == epoch ? KB_OK : kb_fail(ctx, KB_ECUDA, "range scan: results were not published");

@@ -809,6 +809,7 @@ static int wpub_wait(kb_ctx *ctx, uint64_t epoch)
     volatile uint64_t *flag = ctx->h_wpub;
     for (uint64_t spins = 1;; spins++) {
         if (*flag == epoch) return KB_OK;
+        kb_cpu_relax();
         if ((spins & 0xFFFF) == 0) {
             const cudaError_t q = cudaStreamQuery(ctx->stream);
             if (q == cudaSuccess) return *flag == epoch ? KB_OK : kb_fail(ctx, KB_ECUDA, "watch match: total was not published");
