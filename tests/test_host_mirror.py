@@ -78,3 +78,45 @@ def test_compact_borders_g4():
     assert b.get_compact_borders() == ko.compact_borders(b"/registry/test", [b"/registry/test/pods", b"/registry/test/events"])
     b.skipped_prefixes = []
     assert b.get_compact_borders() == ko.compact_borders(b"/registry/test")
+
+
+# ---- range stream host logic with a stub engine (no device): receiver.go:105-166, scanner.go:129-145,179-192 -----------
+class _StubResult:
+    def __init__(self, kvs):
+        self._kvs = kvs
+
+    def kvs(self, q):
+        return self._kvs
+
+    def close(self):
+        pass
+
+
+class _StubEngine:
+    """answers every range with n synthetic kvs, or raises the error a compacted revision raises"""
+
+    def __init__(self, n, fail=None):
+        self.n, self.fail = n, fail
+
+    def range_batch(self, reqs, mode):
+        if self.fail:
+            raise self.fail
+        return _StubResult([(b"/k/%05d" % i, b"v%d" % i, 100 + i) for i in range(self.n)])
+
+
+def test_range_stream_batches_and_end_marker():
+    from kubebrain_b200._lib import KbError
+    from kubebrain_b200.scanner import Scanner
+
+    for n in (0, 1, 299, 300, 301, 650):
+        msgs = list(Scanner(_StubEngine(n)).range_stream(b"a", b"b", 777))
+        batches, end = msgs[:-1], msgs[-1]
+        assert [len(m.kvs) for m in batches] == [300] * (n // 300) + ([n % 300] if n % 300 else [])
+        assert all(m.more for m in batches)
+        # Q7: batches come from forked receivers whose readRev is never set (receiver.go:162-166) -> revision 0
+        assert all(m.revision == 0 for m in batches)
+        assert (end.revision, end.kvs, end.more, end.err) == (777, [], False, "")  # getListStreamEnd, scanner.go:179-192
+        assert [kv.key for m in batches for kv in m.kvs] == [b"/k/%05d" % i for i in range(n)]
+    err = KbError(-5, "range stream revision 3 less than compact revision 9")
+    msgs = list(Scanner(_StubEngine(5, fail=err)).range_stream(b"a", b"b", 3))
+    assert len(msgs) == 1 and msgs[0].more is False and "compact revision 9" in msgs[0].err and msgs[0].revision == 3
