@@ -6,16 +6,21 @@
 //   worker.run (range + compact)        pkg/backend/scanner/scanner.go:389-516  -> k_decode_lcp, k_emit, k_place
 //   commonResultReceiver (limit)        pkg/backend/scanner/receiver.go:62-103  -> k_tile_scan, k_place, k_gather
 //
-// Kernel pipeline for one batch of requests (all on ctx->stream):
-//   k_search      lower_bound of every [start,end) bound in the sorted slab (warp per bound, 32-ary)
-//   k_decode_lcp  HBM-bound pass: stream the raw internal keys (16-byte loads, per-warp shared-memory
-//                 staging), decode magic/split/revision, visibility, tombstone probe, and the common-prefix
-//                 length with the preceding key -> one 32-bit meta word per record + per-tile aggregates
-//   k_emit        per tile: segmented "last visible version" scan over the meta words (prev pointer +
+// Kernel pipeline for one batch of requests (streams: S2 = bound search, S = main, SG = copy stream):
+//   k_search      [S2] lower_bound of every [start,end) bound in the sorted slab (warp per bound, 32-ary); the only
+//                 step the host waits for before it lays the requests out as tiles
+//   k_decode_lcp  [S] HBM-bound pass: stream the raw internal keys (one bulk-TMA copy per 32-record sub-tile into a
+//                 per-warp shared-memory ring), decode magic/split/revision, visibility, tombstone probe, and the
+//                 common-prefix length with the preceding key -> one 32-bit meta word per record + sub-tile aggregates
+//   k_emit        [S] per tile: segmented "last visible version" scan over the meta words (prev pointer +
 //                 running min-LCP), decides which record every key change emits / supersedes
-//   k_tile_scan   prefix sums of per-tile counts/bytes, per-request totals
-//   k_place       ordered placement of the selection (limit applied) / ordered victim list
-//   k_gather      copy the winners' key+value into the response arena (16-byte vector copies)
+//   k_tile_scan   [S] prefix sums of per-tile counts/bytes, per-request totals
+//   k_place       [S] ordered placement of the selection (limit applied) / ordered victim list
+//   k_req_finalize [S] per-request prefix sums; publishes the per-request rows to mapped pinned memory (the host
+//                 returns device-resident answers on that flag)
+//   k_gather_jobs / k_wire_jobs [S] one copy job per emitted kv + the per-kv view arrays
+//   k_gather / k_wire_copy [SG] bulk-TMA copy of the winners' key+value into the response arena (padded pairs, or
+//                 etcd protobuf elements); overlaps the next batch's k_decode_lcp .. k_place
 #include <algorithm>
 
 #include "kb_internal.cuh"
