@@ -103,3 +103,25 @@ def worker_run(keys: Sequence[bytes], vals: Sequence[bytes], start: bytes, end: 
             out.emit.append(prev_idx)
         out.count += 1
     return out
+
+
+def fanout(event_keys: Sequence[bytes], event_revs: Sequence[int], batch_off: Sequence[int],
+           prefixes: Sequence[bytes], min_revs: Sequence[int]):
+    """WatcherHub.Stream (watcherhub.go:78-92) hands every batch to every watcher; each watcher applies
+    filterByRevision (drops only the LEADING events below its revision, watch.go:152-159) and then filterByPrefix
+    (watch.go:139-149) and forwards the batch if anything is left (watch.go:126-131).  Returns the per-watcher ordered
+    event index lists and the total number of forwarded messages."""
+    lists, messages = [], 0
+    for prefix, rev in zip(prefixes, min_revs):
+        got: List[int] = []
+        for b in range(len(batch_off) - 1):
+            lo, hi = int(batch_off[b]), int(batch_off[b + 1])
+            i = lo
+            while i < hi and event_revs[i] < rev:
+                i += 1
+            kept = [j for j in range(i, hi) if event_keys[j].startswith(prefix)]
+            if kept:
+                got.extend(kept)
+                messages += 1
+        lists.append(got)
+    return lists, messages

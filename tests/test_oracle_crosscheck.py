@@ -52,3 +52,17 @@ def test_decode_agrees():
             assert err == 0 and (uk, rev) == (euk, erev), k
         except pyref.DecodeError:
             assert err != 0, k
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_fanout_agrees(seed):
+    ev = fuzz.fuzz_events(40 + seed, n=80 + 50 * seed, monotone=(seed % 2 == 0))
+    w = fuzz.fuzz_watchers(ev, seed, n=8 + 6 * seed)
+    lists, messages = pyref.fanout(ev.keys.tolist(), ev.rev.tolist(), ev.batch_off.tolist(), w.prefixes.tolist(),
+                                   w.min_rev.tolist())
+    start, idx, msgs = ko.fanout(ev, w)
+    assert msgs == messages
+    for i, exp in enumerate(lists):
+        assert idx[int(start[i]) : int(start[i + 1])].tolist() == exp, i
+    start4, idx4, msgs4 = ko.fanout(ev, w, threads=4, alloc_per_batch=True)  # the timing variant gives the same answer
+    assert (start4.tolist(), idx4.tolist(), msgs4) == (start.tolist(), idx.tolist(), msgs)
