@@ -125,3 +125,28 @@ def fanout(event_keys: Sequence[bytes], event_revs: Sequence[int], batch_off: Se
                 messages += 1
         lists.append(got)
     return lists, messages
+
+
+def get(keys: Sequence[bytes], vals: Sequence[bytes], user_key: bytes, revision: int) -> Tuple[int, int]:
+    """backend.get / getInternalVal (pkg/backend/range.go:81-121): a REVERSE iterator (start > end: seek to the largest
+    key <= start, in range while key > end; pkg/storage/badger/iter.go:39-75) from EncodeObjectKey(key, revision) down
+    to EncodeObjectKey(key, 0), limit 1.  Returns (record index, mod revision); index -1 = ErrKeyNotFound, -2 = the
+    record is a tombstone (ErrKeyNotFound with a non-zero mod revision)."""
+    from bisect import bisect_right
+
+    if revision == 0:
+        revision = 2**64 - 1
+    start = MAGIC + user_key + b"$" + struct.pack(">Q", revision)
+    end = MAGIC + user_key + b"$" + struct.pack(">Q", 0)
+    pos = bisect_right(keys, start) - 1
+    if pos < 0 or not keys[pos] > end:
+        return -1, 0
+    try:
+        uk, mod_rev = decode(keys[pos])
+    except DecodeError:
+        return -1, 0  # Decode's error is ignored by the reference: userKey nil, modRev 0 -> not found
+    if mod_rev == 0 or uk != user_key:
+        return -1, 0
+    if vals[pos] == TOMBSTONE:
+        return -2, mod_rev
+    return pos, mod_rev

@@ -66,3 +66,20 @@ def test_fanout_agrees(seed):
         assert idx[int(start[i]) : int(start[i + 1])].tolist() == exp, i
     start4, idx4, msgs4 = ko.fanout(ev, w, threads=4, alloc_per_batch=True)  # the timing variant gives the same answer
     assert (start4.tolist(), idx4.tolist(), msgs4) == (start.tolist(), idx.tolist(), msgs)
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_get_agrees(seed):
+    store = fuzz.fuzz_store(7100 + seed, n_keys=40 + 10 * seed)
+    st = ko.OracleStore(store)
+    keys, vals = store.keys.tolist(), store.vals.tolist()
+    uks = set()
+    for k in keys:
+        try:
+            uk, _ = pyref.decode(k)
+        except pyref.DecodeError:
+            continue
+        uks.update((uk, uk + b"$", uk[:-1], uk + b"\x00"))
+    for uk in sorted(uks):
+        for rev in (0, 1, 9, 17, 33, 58, 59, 2**63, 2**64 - 1):
+            assert ko.get(st, uk, rev) == pyref.get(keys, vals, uk, rev), (uk, rev)
