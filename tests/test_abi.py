@@ -59,3 +59,44 @@ def test_product_does_not_touch_the_oracle():
                 assert "oracle" not in text.lower() or f == "synth.py", os.path.join(dirpath, f)
     out = os.popen(f"ldd {_lib.LIB_PATH} 2>/dev/null").read() if os.path.exists(_lib.LIB_PATH) else ""
     assert "kboracle" not in out
+
+
+def test_header_is_plain_c():
+    """the boundary is a C ABI: the header must compile as C99 (what cgo feeds it to) and as C++"""
+    import shutil
+    import subprocess
+
+    hdr = os.path.join(ROOT, "include", "kb_b200.h")
+    gcc = shutil.which("gcc")
+    if not gcc:
+        pytest.skip("no gcc")
+    subprocess.check_call([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-x", "c", hdr])
+    gxx = shutil.which("g++")
+    if gxx:
+        subprocess.check_call([gxx, "-std=c++17", "-Wall", "-Werror", "-fsyntax-only", "-x", "c++", hdr])
+
+
+def test_ctypes_structs_match_the_header_layout():
+    """sizes of the structs that cross the boundary by value or by array, as a C compiler lays them out"""
+    import shutil
+    import subprocess
+    import tempfile
+
+    gcc = shutil.which("gcc")
+    if not gcc:
+        pytest.skip("no gcc")
+    from kubebrain_b200 import _lib
+
+    src = '#include <stdio.h>\n#include "kb_b200.h"\nint main(void){printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n",' \
+          'sizeof(kb_config),sizeof(kb_range_req),sizeof(kb_range_view),sizeof(kb_write_op),sizeof(kb_get_req),' \
+          'sizeof(kb_get_view),sizeof(kb_compact_view),sizeof(kb_match_view));return 0;}\n'
+    with tempfile.TemporaryDirectory() as d:
+        c, exe = os.path.join(d, "s.c"), os.path.join(d, "s")
+        with open(c, "w") as f:
+            f.write(src)
+        subprocess.check_call([gcc, "-std=c99", "-I", os.path.join(ROOT, "include"), c, "-o", exe])
+        sizes = [int(x) for x in subprocess.check_output([exe]).split()]
+    import ctypes as C
+    got = [C.sizeof(t) for t in (_lib.KbConfig, _lib.KbRangeReq, _lib.KbRangeView, _lib.KbWriteOp, _lib.KbGetReq,
+                                 _lib.KbGetView, _lib.KbCompactView, _lib.KbMatchView)]
+    assert got == sizes
