@@ -100,3 +100,37 @@ def test_ctypes_structs_match_the_header_layout():
     got = [C.sizeof(t) for t in (_lib.KbConfig, _lib.KbRangeReq, _lib.KbRangeView, _lib.KbWriteOp, _lib.KbGetReq,
                                  _lib.KbGetView, _lib.KbCompactView, _lib.KbMatchView)]
     assert got == sizes
+
+
+def test_plain_c_program_links_and_calls_the_library(tmp_path):
+    """a C99 translation unit links libkbb200.so and calls the host-side entry points (no device needed)"""
+    import shutil
+    import subprocess
+
+    gcc = shutil.which("gcc")
+    if not gcc:
+        pytest.skip("no gcc")
+    src = r'''
+#include <stdio.h>
+#include <string.h>
+#include "kb_b200.h"
+int main(void) {
+    unsigned char b[64];
+    unsigned long long n = kb_wire_range_head(5, b);
+    if (n != 4 || memcmp(b, "\x0a\x02\x18\x05", 4) != 0) return 1;
+    n = kb_wire_range_tail(1, 300, b);
+    if (n != 5 || memcmp(b, "\x18\x01\x20\xac\x02", 5) != 0) return 2;
+    n = kb_wire_watch_head(0, 1, (const unsigned char *)"eof", 3, b);
+    if (n != 9 || memcmp(b, "\x0a\x00\x20\x01\x32\x03" "eof", 9) != 0) return 3;
+    printf("%d\n", kb_abi_version());
+    return 0;
+}
+'''
+    c, exe = str(tmp_path / "link.c"), str(tmp_path / "link")
+    with open(c, "w") as f:
+        f.write(src)
+    libdir = os.path.join(ROOT, "kubebrain_b200")
+    subprocess.check_call([gcc, "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), c, "-o", exe,
+                           "-L", libdir, "-lkbb200", "-Wl,-rpath," + libdir])
+    out = subprocess.check_output([exe]).decode().strip()
+    assert int(out) == _lib.lib().kb_abi_version()
