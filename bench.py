@@ -47,36 +47,73 @@ BURST_START = 2_000_000
 ns_shard = synth.ns_shard
 
 
-def build_workload(rank: int, world: int):
-    """per-rank shard of the synthetic: store, list requests, watchers, event burst"""
+def build_workload(rank: int, world: int, mode: str = "weak"):
+    """per-rank shard of the synthetic: store, list requests, watchers, event burst.
+    weak  : every GPU gets ~1M records / ~10k watchers / ~100k events (the data set grows with N);
+    strong: BASELINE configs[4] as written -- 8M records (1.6M objects), 50k namespace watchers (+16 cluster-wide,
+            replicated) and ONE 100k-event burst in total, hash-sharded over the N GPUs."""
     t0 = time.time()
-    store, meta = synth.gen_store(N_OBJECTS * world, VERSIONS, LU, LV, NS_STORE * world, config_id=2,
+    if mode == "strong":
+        n_obj, n_ns, n_nsw, n_ev, ns_ev = 1_600_000, 50_000, 50_000, N_EVENTS, 55_000
+    else:
+        n_obj, n_ns, n_nsw, n_ev, ns_ev = N_OBJECTS * world, NS_STORE * world, N_NS_WATCH * world, N_EVENTS * world, \
+            NS_EVENTS * world
+    store, meta = synth.gen_store(n_obj, VERSIONS, LU, LV, n_ns, config_id=2,
                                   shard=(rank, world) if world > 1 else None)
     lo, hi = CODER.encode_object_key(b"/registry/", 0), CODER.encode_object_key(b"/registry0", 0)
     reqs = [(lo, hi, meta.read_rev, 0)]
-    owned = np.nonzero(ns_shard(np.arange(NS_STORE * world), world) == rank)[0]
+    owned = np.nonzero(ns_shard(np.arange(n_ns), world) == rank)[0]
     resn = [b"pods", b"configmaps", b"secrets", b"services", b"deployments", b"events"]
     for i in range(Q_LISTS):
         p = b"/registry/" + resn[i % 6] + b"/ns-%05d/" % int(owned[(i * 7) % len(owned)])
         reqs.append((CODER.encode_object_key(p, 0), CODER.encode_object_key(prefix_end(p), 0), meta.read_rev, 10001))
     # watchers: namespace watchers of the namespaces this rank owns + the cluster-wide ones (replicated)
-    w_all = synth.gen_watchers(N_NS_WATCH * world, N_CLUSTER_WATCH, BURST_START, BURST_START + N_EVENTS // 2)
-    ns_ids = np.arange(N_NS_WATCH * world)
+    w_all = synth.gen_watchers(n_nsw, N_CLUSTER_WATCH, BURST_START, BURST_START + n_ev // 2)
+    ns_ids = np.arange(n_nsw)
     keep = np.concatenate([ns_shard(ns_ids, world) == rank, np.ones(N_CLUSTER_WATCH, dtype=bool)])
     idx = np.nonzero(keep)[0]
-    watchers = PackedWatchers(w_all.prefixes.take(idx), w_all.min_rev[idx])
+    watchers = w_all if world == 1 else PackedWatchers(w_all.prefixes.take(idx), w_all.min_rev[idx])
     # events: the burst routed by the same hash
-    ev_all = synth.gen_events(N_EVENTS * world, LU, NS_EVENTS * world, BURST_START)
+    ev_all = synth.gen_events(n_ev, LU, ns_ev, BURST_START)
     if world > 1:
-        ev_ns = np.array([int(ev_all.keys.data[int(o) + 18 : int(o) + 23].tobytes()) for o in ev_all.keys.off[:-1]])
+        mat = ev_all.keys.data.reshape(-1, LU)
+        digits = mat[:, 18:23].astype(np.int64) - 48  # "/registry/pods/ns-%05d/": the namespace number
+        ev_ns = digits @ np.array([10000, 1000, 100, 10, 1], dtype=np.int64)
         sel = np.nonzero(ns_shard(ev_ns, world) == rank)[0]
-        mat = ev_all.keys.data.reshape(-1, LU)[sel]
         n = len(sel)
-        ev = PackedEvents(Slab.from_fixed(mat), ev_all.rev[sel],
+        ev = PackedEvents(Slab.from_fixed(mat[sel]), ev_all.rev[sel],
                           np.array(list(range(0, n, 300)) + [n], dtype=np.uint64))
     else:
         ev = ev_all
-    return dict(store=store, meta=meta, reqs=reqs, watchers=watchers, events=ev, gen_s=time.time() - t0)
+    return dict(store=store, meta=meta, reqs=reqs, watchers=watchers, events=ev, gen_s=time.time() - t0, mode=mode)
+
+
+def bind_to_gpu_numa_node(local_rank: int):
+    """Pin this process to the CPUs of the NUMA node its GPU hangs off BEFORE any pinned host memory is allocated, so
+    the response pools are node-local (round 1: at N=8 the 8 x 484 MB of pinned-host writes per step reached only
+    ~160 GB/s in aggregate).  Returns (original affinity, description) -- the caller restores the mask for CPU legs."""
+    try:
+        orig = os.sched_getaffinity(0)
+    except AttributeError:
+        return None, "no sched_getaffinity"
+    try:
+        import torch
+
+        pr = torch.cuda.get_device_properties(local_rank)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        base = f"/sys/bus/pci/devices/{bdf}/"
+        node = int(open(base + "numa_node").read().strip())
+        cpus = set()
+        for part in open(base + "local_cpulist").read().strip().split(","):
+            lo_, _, hi_ = part.partition("-")
+            cpus.update(range(int(lo_), int(hi_ or lo_) + 1))
+        cpus &= orig
+        if node < 0 or not cpus:
+            return orig, f"gpu {bdf}: no NUMA information"
+        os.sched_setaffinity(0, cpus)
+        return orig, f"gpu {bdf} -> numa node {node}, {len(cpus)} cpus"
+    except Exception as e:  # sysfs layout differs, attribute missing: run unbound
+        return orig, f"unbound ({type(e).__name__})"
 
 
 class ClockSampler:
@@ -156,22 +193,80 @@ def ncu_traffic(kernel: str):
 
 
 # ---------------------------------------------------------------------------------------------------------
-# reference arm: the reference's own CPU implementation of the path (C restatement, all host threads)
+# reference arm: the reference's own CPU implementation of the path (C restatement, all usable host threads)
 # ---------------------------------------------------------------------------------------------------------
-def cpu_step(ost, wl, threads: int, faithful: bool = True):
+def host_threads() -> int:
+    """threads this process may really use: the scheduler affinity mask bounded by the cgroup CPU quota (os.cpu_count()
+    reports the machine, not the container -- the round-1 reference arm oversubscribed a quota-limited box 5x)"""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    try:  # cgroup v2
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if q != "max":
+            n = min(n, max(1, int(float(q) / float(per) + 0.5)))
+    except (OSError, ValueError):
+        try:  # cgroup v1
+            q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0 and per > 0:
+                n = min(n, max(1, int(q / per + 0.5)))
+        except (OSError, ValueError):
+            pass
+    return max(1, n)
+
+
+CPU_LEGS = ("scan_faithful_s", "scan_zero_copy_s", "lists_s", "fanout_alloc_s", "fanout_prealloc_s")
+
+
+def cpu_legs(ost, wl, threads: int):
+    """one pass of the step's work on the host, every leg timed on its own:
+      scan, faithful   : partition-parallel worker.run WITH the badger iterator's per-record copies (KeyCopy + 2x ValueCopy,
+                         reference pkg/storage/badger/iter.go:85-92, scanner.go:441,495), P = threads (TiKV shape)
+      scan, zero copy  : the same loop over borrowed slices (no per-record copies), P = threads
+      lists            : 256 x List(limit 10001), one goroutine each (run back to back on one thread: ~170 records each)
+      fan-out          : every watcher runs filterByRevision + filterByPrefix over all batches, watchers sharded over
+                         `threads`; with (watch.go:141) and without the per-batch output allocation"""
     from oracle import binding as ko
 
-    examined = 0
-    s, e, rev, lim = wl["reqs"][0]
-    n, ex, _ = ko.bench_scan(ost, s, e, rev, 0, faithful, threads)
-    examined += ex
-    emitted = n
+    t = {}
+    s, e, rev, _ = wl["reqs"][0]
+    t0 = time.perf_counter()
+    n_f, ex_f, _ = ko.bench_scan(ost, s, e, rev, 0, True, threads)
+    t["scan_faithful_s"] = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    n_z, ex_z, _ = ko.bench_scan(ost, s, e, rev, 0, False, threads)
+    t["scan_zero_copy_s"] = time.perf_counter() - t0
+    assert (n_f, ex_f) == (n_z, ex_z)
+    examined, emitted = ex_f, n_f
+    t0 = time.perf_counter()
     for s, e, rev, lim in wl["reqs"][1:]:
-        n, ex, _ = ko.bench_scan(ost, s, e, rev, lim, faithful, 1)
+        n, ex, _ = ko.bench_scan(ost, s, e, rev, lim, False, 1)
         examined += ex
         emitted += n
-    start, idx, msgs = ko.fanout(wl["events"], wl["watchers"], threads=threads, alloc_per_batch=True)
-    return examined, emitted, len(idx)
+    t["lists_s"] = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    _, idx, _ = ko.fanout(wl["events"], wl["watchers"], threads=threads, alloc_per_batch=True)
+    t["fanout_alloc_s"] = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    _, idx2, _ = ko.fanout(wl["events"], wl["watchers"], threads=threads, alloc_per_batch=False)
+    t["fanout_prealloc_s"] = time.perf_counter() - t0
+    assert len(idx) == len(idx2)
+    return t, examined, emitted, len(idx)
+
+
+def cpu_summary(legs_mean, events: int, threads: int):
+    fastest = (min(legs_mean["scan_faithful_s"], legs_mean["scan_zero_copy_s"]) + legs_mean["lists_s"] +
+               min(legs_mean["fanout_alloc_s"], legs_mean["fanout_prealloc_s"]))
+    faithful = legs_mean["scan_faithful_s"] + legs_mean["lists_s"] + legs_mean["fanout_alloc_s"]
+    return {
+        "value": events / fastest, "unit": "events/s", "cores": threads, "kind": "port",
+        "s_per_step": fastest, "legs_s": {k: legs_mean[k] for k in CPU_LEGS},
+        "value_faithful": events / faithful, "s_per_step_faithful": faithful,
+        "variant": "fastest of each leg: scan = min(faithful copies, zero copy) at P = cores; fan-out = min(per-batch "
+                   "allocation, preallocated); `value_faithful` keeps the badger-style copies and watch.go:141 allocation",
+    }
 
 
 def run_reference(args, rank: int, world: int):
@@ -181,44 +276,44 @@ def run_reference(args, rank: int, world: int):
 
     wl = build_workload(0, 1)
     ost = ko.OracleStore(wl["store"])
-    threads = os.cpu_count() or 1
+    threads = host_threads()
     for _ in range(max(args.warmup, 1)):
-        cpu_step(ost, wl, threads)
-    t0 = time.perf_counter()
+        cpu_legs(ost, wl, threads)
+    acc = {k: 0.0 for k in CPU_LEGS}
     for _ in range(args.steps):
-        examined, emitted, deliveries = cpu_step(ost, wl, threads)
-    dt = (time.perf_counter() - t0) / args.steps
+        legs, examined, emitted, deliveries = cpu_legs(ost, wl, threads)
+        for k in CPU_LEGS:
+            acc[k] += legs[k]
+    mean = {k: v / args.steps for k, v in acc.items()}
     events = examined + wl["events"].n
-    # context: the badger shape (single partition => the full scan is one goroutine) and the zero-copy variant
+    summ = cpu_summary(mean, events, threads)
+    # context: the badger shape (a single partition => the full scan is ONE goroutine, badger.go:52-54)
     t1 = time.perf_counter()
     s, e, rev, _ = wl["reqs"][0]
     ko.bench_scan(ost, s, e, rev, 0, True, 1)
-    badger_scan_s = time.perf_counter() - t1
-    t1 = time.perf_counter()
-    ko.bench_scan(ost, s, e, rev, 0, False, threads)
-    zero_copy_s = time.perf_counter() - t1
-    value = events / dt
+    summ["badger_single_partition_scan_s"] = time.perf_counter() - t1
+    summ["sample"] = (f"{args.steps} full steps, every leg timed separately on {threads} threads (affinity mask bounded by the "
+                      "cgroup quota): 1 unlimited Range over 1M records + 256 List(limit 10001) + 100k-event burst x 10k "
+                      "watchers; value = fastest variant of each leg (BASELINE.md section 3)")
+    value = summ["value"]
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "events/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": summ["s_per_step"] * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
         "config": workload_config(1, wl),
-        "cpu_baseline": {
-            "value": value, "unit": "events/s", "cores": threads, "kind": "port",
-            "sample": "full step: 1 unlimited Range over 1M records partition-parallel on all cores WITH the badger "
-                      "iterator's per-record copies (KeyCopy + 2x ValueCopy) + 256 List(limit 10001) + 100k-event "
-                      "burst x 10k watchers (watchers sharded over all cores, per-batch allocation)",
-            "badger_single_partition_scan_s": badger_scan_s, "zero_copy_all_cores_scan_s": zero_copy_s,
-        },
+        "cpu_baseline": summ,
         "e2e": {"value": value, "unit": "events/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
 
 
 def workload_config(world: int, wl):
+    strong = wl.get("mode") == "strong"
     return {
-        "workload": "configs[1]+[2]: 1M MVCC records/GPU (256B key, 2KB val), 1 full Range + 256 List(limit 10001), "
-                    "100k-event burst x 10k watchers/GPU",
+        "workload": ("configs[4]: 8M MVCC records (256B key, 2KB val) + 50k watchers + one 100k-event burst hash-sharded over "
+                     "the GPUs, per GPU 1 full Range + 256 List(limit 10001)") if strong else
+                    ("configs[1]+[2]: 1M MVCC records/GPU (256B key, 2KB val), 1 full Range + 256 List(limit 10001), "
+                     "100k-event burst x 10k watchers/GPU"),
         "records_per_gpu": int(wl["store"].n), "list_requests": Q_LISTS, "watchers_per_gpu": int(wl["watchers"].n),
         "events_per_gpu": int(wl["events"].n), "read_rev": int(wl["meta"].read_rev),
         "parallelism": f"hash-shard x{world}" if world > 1 else "single GPU",
@@ -238,13 +333,14 @@ def run_b200(args, rank: int, local_rank: int, world: int):
     from kubebrain_b200._lib import KB_OUT_DEVICE, KB_OUT_HOST, Engine
 
     torch.cuda.set_device(local_rank)
+    orig_affinity, numa_note = bind_to_gpu_numa_node(local_rank)
     dist = None
     if world > 1:
         import torch.distributed as dist_mod
 
         dist = dist_mod
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    wl = build_workload(rank, world)
+    wl = build_workload(rank, world, args.mode)
     # two contexts on the same GPU, as in the reference where scans and the watch hub are independent goroutines:
     # `eng` owns the HBM-resident snapshot (scans), `weng` owns the watcher tables (fan-out); each has its own stream
     prio = os.environ.get("KB_BENCH_PRIO", "fanout")  # which context gets the high-priority streams: scan | fanout | none
@@ -416,6 +512,28 @@ def run_b200(args, rank: int, local_rank: int, world: int):
             p.update(prof_major[p["name"]])
     e2e_ms, e2e_wall, (examined2, d2h_bytes, _) = timed(step_e2e, args.steps)
     clocks = sampler.stop() if rank == 0 else None
+    # the cursor exchange on its own, both transports (the timed loop uses the peer-memory kernel when peers map)
+    cursor_us = {}
+    if world > 1:
+        for name, force_nccl in (("p2p" if eng.cursor_mode() == "p2p" else "nccl", False), ("nccl", True)):
+            if name in cursor_us:
+                continue
+            eng.cursor_force_nccl(force_nccl)
+            for _ in range(5):
+                eng.cursor_allgather(local_rev)
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(50):
+                eng.cursor_allgather(local_rev)
+            cursor_us[name] = (time.perf_counter() - t0) / 50 * 1e6
+        eng.cursor_force_nccl(False)
+        t = torch.tensor([cursor_us.get("p2p", 0.0), cursor_us.get("nccl", 0.0)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        cursor_us = {k: float(v) for k, v in zip(("p2p", "nccl"), t.tolist()) if v > 0}
+    # parity of the very answers that were timed, on every rank (raises -> rc != 0)
+    parity = None if args.no_parity else parity_check(eng, weng, wl, evh, reqs, rank, world, dist)
+    if orig_affinity is not None:
+        os.sched_setaffinity(0, orig_affinity)  # CPU legs below use every core the container has
 
     events_local = examined + wl["events"].n
     if dist is not None:
@@ -456,7 +574,7 @@ def run_b200(args, rank: int, local_rank: int, world: int):
             roof["share_of_kernel_time"] = dom["avg_us"] * dom["launches_per_step"] / ksum if ksum else None
         line = {
             "metric": METRIC, "value": value, "unit": "events/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.mode,
             "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": workload_config(world, wl),
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "events/s", "h2d_bytes_per_step": int(h2d_bytes),
@@ -467,12 +585,19 @@ def run_b200(args, rank: int, local_rank: int, world: int):
             "scan_records_per_step": int(examined), "emitted_kvs_per_step": int(n_kvs),
             "fanout_events_per_step": int(wl["events"].n), "deliveries_per_step": int(deliveries),
             "wall_ms_per_step": wall_s * 1e3 / args.steps, "gen_s": wl["gen_s"],
-            "host_call_us": host_call_us,
+            "host_call_us": host_call_us, "numa": numa_note,
+            "parity_checked": bool(parity and parity.get("parity_checked")), "parity": parity,
         }
+        if cursor_us:
+            line["cursor_exchange_us"] = cursor_us
+        if world == 1 and not args.no_extras:
+            line["latency"] = latency_probe(eng, wl)
+            line["fanout_alone"] = fanout_alone(weng, evh, wl, peak)
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(wl)
         if world == 1 and not args.no_extras:
-            line["extra"] = {"compaction": compaction_extra(local_rank), "wire": wire_extra(eng, wl)}
+            line["extra"] = {"compaction": compaction_extra(local_rank, peak, full=not args.small_compaction),
+                             "wire": wire_extra(eng, wl)}
         print(json.dumps(line), flush=True)
     if wthread is not None:
         jobs_q.put(None)
@@ -484,6 +609,207 @@ def run_b200(args, rank: int, local_rank: int, world: int):
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# parity of the timed answers (every rank, every N): the GPU answers of the bench workload against the oracle
+# ---------------------------------------------------------------------------------------------------------
+MASK64 = (1 << 64) - 1
+
+
+def _dev_bytes(ptr: int, nbytes: int):
+    """a torch uint8 view of raw device memory owned by libkbb200 (no copy)"""
+    import torch
+
+    class _H:
+        pass
+
+    h = _H()
+    h.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (int(ptr), False), "version": 3}
+    return torch.as_tensor(h, device="cuda")
+
+
+def _digest_device(ptr: int, nbytes: int) -> int:
+    """position-weighted checksum of ALL arena bytes, computed on the device: sum_i word_i * (2i+1) mod 2^64"""
+    import torch
+
+    assert nbytes % 8 == 0
+    w = _dev_bytes(ptr, nbytes).view(torch.int64)
+    tot = 0
+    step = 1 << 24
+    for a in range(0, w.numel(), step):  # chunked: bounds the temporaries to 128 MB
+        b = min(a + step, w.numel())
+        wt = torch.arange(a, b, device="cuda", dtype=torch.int64) * 2 + 1
+        tot = (tot + int((w[a:b] * wt).sum().item())) & MASK64
+    return tot
+
+
+def _digest_expected(store, rec_idx: np.ndarray) -> int:
+    """the same checksum of the arena the reference's answer would fill: per emitted kv [internal key, zero padded to
+    16][value, zero padded to 16], in emission order"""
+    koff, voff = store.keys.off.astype(np.int64), store.vals.off.astype(np.int64)
+    idx = rec_idx.astype(np.int64)
+    kl, vl = koff[idx + 1] - koff[idx], voff[idx + 1] - voff[idx]
+    assert len(idx) == 0 or (kl.min() == kl.max() and vl.min() == vl.max()), "bench store emits fixed-size kvs"
+    if len(idx) == 0:
+        return 0
+    klen, vlen = int(kl[0]), int(vl[0])
+    kp, vp = (klen + 15) // 16 * 16, (vlen + 15) // 16 * 16
+    slot_words = (kp + vp) // 8
+    tot = 0
+    rows = 4096
+    with np.errstate(over="ignore"):
+        for a in range(0, len(idx), rows):
+            sl = idx[a : a + rows]
+            m = np.zeros((len(sl), kp + vp), dtype=np.uint8)
+            m[:, :klen] = store.keys.data[koff[sl][:, None] + np.arange(klen)]
+            m[:, kp : kp + vlen] = store.vals.data[voff[sl][:, None] + np.arange(vlen)]
+            w = m.view("<u8").reshape(-1)
+            wt = (np.arange(a * slot_words, a * slot_words + w.size, dtype=np.uint64) * np.uint64(2) + np.uint64(1))
+            tot = (tot + int((w * wt).sum(dtype=np.uint64))) & MASK64
+    return tot
+
+
+def parity_check(eng, weng, wl, evh, reqs, rank: int, world: int, dist):
+    """After the timed region: (1) this rank's GPU answers of the step -- emitted record indices, examined / object counts,
+    a device-computed digest of ALL arena bytes, the per-watcher delivery lists -- against the oracle on this rank's
+    shard; (2) N > 1: one broad List answered by every shard, merged by sharded.merge_list_runs, against the oracle on the
+    unsharded store.  Any mismatch raises (the bench exits non-zero)."""
+    from kubebrain_b200 import sharded
+    from kubebrain_b200._lib import KB_OUT_DEVICE, KB_OUT_HOST
+    from oracle import binding as ko
+
+    t0 = time.perf_counter()
+    ost = ko.OracleStore(wl["store"])
+    r = eng.range_batch(reqs, KB_OUT_DEVICE)
+    rec = r.device_array("rec_idx", np.uint32)
+    exp_all = []
+    for q, (s, e, rev, lim) in enumerate(wl["reqs"]):
+        exp = ko.range_(ost, s, e, rev, lim)
+        a, b = int(r.req_first[q]), int(r.req_first[q + 1])
+        if not np.array_equal(rec[a:b].astype(np.uint64), exp.emit):
+            raise AssertionError(f"rank {rank}: request {q}: emitted records differ from the oracle")
+        if int(r.req_examined[q]) != exp.examined or int(r.req_count[q]) != exp.count:
+            raise AssertionError(f"rank {rank}: request {q}: examined / count differ from the oracle")
+        exp_all.append(exp.emit)
+    exp_idx = np.concatenate(exp_all) if exp_all else np.zeros(0, np.uint64)
+    d_dev = _digest_device(r.bytes_ptr, r.n_bytes) if r.n_bytes else 0
+    d_exp = _digest_expected(wl["store"], exp_idx)
+    if d_dev != d_exp:
+        raise AssertionError(f"rank {rank}: arena digest {d_dev:#x} differs from the oracle's {d_exp:#x}")
+    n_kvs, n_bytes = r.n_kvs, r.n_bytes
+    r.close()
+    start, idx, _ = ko.fanout(wl["events"], wl["watchers"], threads=host_threads())
+    m = weng.watch_match_dev(evh, KB_OUT_DEVICE)
+    if m.start.tolist() != start.tolist() or not np.array_equal(m.device_event_idx(), idx.astype(np.uint32)):
+        raise AssertionError(f"rank {rank}: fan-out delivery lists differ from the oracle")
+    deliveries = m.n_deliveries
+    m.close()
+    out = {"parity_checked": True, "kvs": int(n_kvs), "arena_bytes_digested": int(n_bytes), "deliveries": int(deliveries),
+           "requests": len(wl["reqs"])}
+    if world > 1:
+        broad = b"/registry/services/"
+        assert sharded.owner_of_prefix(broad, world) is None
+        blo, bhi = CODER.encode_object_key(broad, 0), CODER.encode_object_key(prefix_end(broad), 0)
+        rev = int(wl["meta"].read_rev)
+        g = eng.range_batch([(blo, bhi, rev, 0)], KB_OUT_HOST)
+        run = [(k, len(v), rv) for k, v, rv in g.kvs(0)]
+        g.close()
+        runs = [None] * world
+        dist.all_gather_object(runs, run)
+        if rank == 0:
+            # the unsharded store with short values: keys, revisions and tombstones do not depend on Lv
+            gstore, gmeta = synth.gen_store(N_OBJECTS * world, VERSIONS, LU, 16, NS_STORE * world, config_id=2)
+            gst = ko.OracleStore(gstore)
+            assert gmeta.read_rev == rev
+            for limit in (0, 5000):
+                exp = ko.range_(gst, blo, bhi, rev, limit + 1 if limit else 0)  # backend.List asks for limit + 1
+                exp_kv = [(k, rv) for k, _, rv in exp.kvs(gstore)]
+                got, more = sharded.merge_list_runs(runs, limit)
+                if [(k, rv) for k, _, rv in got] != (exp_kv[:limit] if limit else exp_kv) or \
+                        more != (limit > 0 and len(exp_kv) > limit) or any(vl != LV for _, vl, _ in got):
+                    raise AssertionError(f"merged broad List (limit {limit}) differs from the oracle on the unsharded store")
+            out["merged_list_kvs"] = len(exp_kv)
+        ok = [None] * world
+        dist.all_gather_object(ok, True)  # every rank reached this point without raising
+    out["seconds"] = time.perf_counter() - t0
+    return out
+
+
+def latency_probe(eng, wl):
+    """SURVEY 8d config 2 latency run: ONE List(limit 10 000) over the whole prefix (backend.List asks the scanner for
+    10 001, pkg/backend/range.go:153-171; worker.run stops pulling once the receiver is full).  Reported in microseconds:
+    device-resident answer complete, host-resident answer complete (e2e), and the CPU port on one thread."""
+    from kubebrain_b200._lib import KB_OUT_DEVICE, KB_OUT_HOST, Engine
+    from oracle import binding as ko
+
+    p = b"/registry/"
+    s, e = CODER.encode_object_key(p, 0), CODER.encode_object_key(prefix_end(p), 0)
+    rev = int(wl["meta"].read_rev)
+    pk = Engine.pack_range_reqs([(s, e, rev, 10001)])
+    ost = ko.OracleStore(wl["store"])
+    exp = ko.range_(ost, s, e, rev, 10001)
+    r = eng.range_batch(pk, KB_OUT_HOST)
+    assert np.array_equal(r.rec_idx.astype(np.uint64), exp.emit) and int(r.req_examined[0]) == exp.examined
+    n_bytes = r.n_bytes
+    r.close()
+
+    def rep(mode, n=40):
+        ts = []
+        for _ in range(n):
+            eng.sync()
+            t0 = time.perf_counter()
+            r = eng.range_batch(pk, mode)
+            if mode == KB_OUT_DEVICE:
+                r.wait()
+            ts.append(time.perf_counter() - t0)
+            r.close()
+        return statistics.median(ts[5:]) * 1e6
+
+    dev_us, e2e_us = rep(KB_OUT_DEVICE), rep(KB_OUT_HOST)
+    cpu = []
+    for faithful in (True, False):
+        ts = []
+        for _ in range(7):
+            t0 = time.perf_counter()
+            ko.bench_scan(ost, s, e, rev, 10001, faithful, 1)
+            ts.append(time.perf_counter() - t0)
+        cpu.append(statistics.median(ts) * 1e6)
+    return {"request": "List(/registry/ .. prefix end, limit 10000 -> 10001 asked)", "examined": int(exp.examined),
+            "emitted": int(len(exp.emit)), "answer_bytes": int(n_bytes), "device_us": dev_us, "e2e_us": e2e_us,
+            "cpu_port_faithful_us": cpu[0], "cpu_port_zero_copy_us": cpu[1], "parity_checked": True}
+
+
+def fanout_alone(weng, evh, wl, peak: float, reps: int = 30):
+    """BASELINE configs[2] on its own (no scan beside it): one 100k-event burst against the 10k watchers, device resident;
+    roofline against SURVEY 8d's algorithmic bytes E*(Lu+8+4) + W*44 + D*8"""
+    import torch
+
+    from kubebrain_b200._lib import KB_OUT_DEVICE
+
+    ws = torch.cuda.ExternalStream(weng.stream())
+    for _ in range(5):
+        weng.watch_match_dev(evh, KB_OUT_DEVICE).close()
+    weng.sync()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = weng.launch_count()
+    a.record(ws)
+    for _ in range(reps):
+        m = weng.watch_match_dev(evh, KB_OUT_DEVICE)
+        d = m.n_deliveries
+        m.close()
+    weng.sync()
+    b.record(ws)
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / reps
+    E, W = int(wl["events"].n), int(wl["watchers"].n)
+    alg = E * (LU + 12) + W * 44 + d * 8
+    return {"workload": "configs[2] alone: 100k-event burst x 10k watchers, device-resident slab and answer",
+            "us_per_burst": ms * 1e3, "events_per_s": E / (ms / 1e3), "deliveries_per_s": d / (ms / 1e3),
+            "launches_per_burst": (weng.launch_count() - l0) / reps,
+            "roofline": {"bound": "hbm", "achieved": alg / 1e9 / (ms / 1e3), "peak": peak, "unit": "GB/s",
+                         "frac": alg / 1e9 / (ms / 1e3) / peak, "alg_bytes": alg,
+                         "note": "latency bound: 41 MB of algorithmic traffic per burst"}}
 
 
 def wire_extra(eng, wl):
@@ -510,24 +836,32 @@ def wire_extra(eng, wl):
             "kvs": int(nk), "wire_bytes": int(nb), "kernels": kern}
 
 
-def compaction_extra(device: int):
-    """BASELINE configs[3] at 1/10 size (not part of the timed step): keep-latest sweep over 1M objects x
-    (1 revision record + 9 versions), Lu=64 -> 10M records, ~8M victims; device-resident victim list"""
+def compaction_extra(device: int, peak: float, full: bool = True):
+    """BASELINE configs[3] (not part of the timed step): keep-latest sweep over 10M objects x (1 revision record + 9
+    versions), Lu=64 -> 100M records, ~80M victims, device-resident victim list; the same sweep's ordered victim list is
+    compared with the oracle in this run.  Falls back to 1/10 size when the host cannot hold the synthetic."""
     import torch
 
-    from kubebrain_b200._lib import KB_OUT_DEVICE, Engine
+    from kubebrain_b200._lib import KB_OUT_DEVICE, KB_OUT_HOST, Engine
+    from oracle import binding as ko
 
-    store, meta = synth.gen_store(1_000_000, 9, 64, 64, 10000, config_id=4, tomb_frac=0.02)
+    if full:
+        try:
+            import psutil
+
+            full = psutil.virtual_memory().available > 48 * 2**30
+        except Exception:
+            full = False
+    n_obj, n_ns = (10_000_000, 50_000) if full else (1_000_000, 10_000)
+    store, meta = synth.gen_store(n_obj, 9, 64, 64, n_ns, config_id=4, tomb_frac=0.02)
     eng = Engine(device)
     eng.load_sorted(store)
     lo, hi = CODER.encode_object_key(b"/registry/", 0), CODER.encode_object_key(b"/registry0", 0)
-    for _ in range(3):
+    for _ in range(2):
         eng.compact_sweep(lo, hi, meta.last_rev, out_mode=KB_OUT_DEVICE).close()
     stream = torch.cuda.ExternalStream(eng.stream())
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    eng.prof_reset()
-    eng.prof_enable(1)
-    reps = 5
+    reps = 4
     torch.cuda.synchronize()
     a.record(stream)
     for _ in range(reps):
@@ -536,33 +870,54 @@ def compaction_extra(device: int):
         r.close()
     b.record(stream)
     torch.cuda.synchronize()
-    eng.prof_enable(0)
     ms = a.elapsed_time(b) / reps
+    # per-kernel times in a separate pass (the event pairs add gaps)
+    eng.prof_reset()
+    eng.prof_enable(1)
+    for _ in range(2):
+        eng.compact_sweep(lo, hi, meta.last_rev, out_mode=KB_OUT_DEVICE).close()
+    eng.prof_enable(0)
     kern = {p["name"]: {"avg_us": 1e3 * p["total_ms"] / p["launches"],
                         "achieved_gbs": (p["alg_bytes"] / p["launches"] / 1e9) / (p["total_ms"] / p["launches"] / 1e3)
                         if p["total_ms"] > 0 else None}
             for p in eng.prof_read() if p["launches"] and not p["name"].startswith("host:")}
+    # parity in the same run: the ordered victim list with classes against the oracle
+    got = eng.compact_sweep(lo, hi, meta.last_rev, out_mode=KB_OUT_HOST)
+    exp = ko.scan(ko.OracleStore(store), [lo, hi], meta.last_rev, compact=True, collect=False)
+    ok = (got.n_victims == len(exp.victims) and got.count == exp.count and
+          np.array_equal(got.victim_idx.astype(np.uint64), exp.victims) and np.array_equal(got.victim_class, exp.vclass))
+    got.close()
     eng.close()
-    return {"workload": "config 4 shape at 1/10: 10M records (Lk=77), compact at max revision", "records": int(store.n),
-            "victims": int(nv), "ms_per_sweep": ms, "records_per_s": store.n / (ms / 1e3), "kernels": kern}
+    if not ok:
+        raise AssertionError("compaction sweep differs from the oracle")
+    # per record Lk + 4 + 4 = 85 B, + 9 B for every 9-byte value and every revision record
+    vl = store.vals.lengths()
+    alg = int(store.n) * 85 + int(((vl == 9) | (np.arange(store.n) % 10 == 0)).sum()) * 9 + (int(store.n) + 7) // 8
+    return {"workload": f"config 4 {'FULL size' if full else 'at 1/10'}: {store.n / 1e6:.0f}M records (Lk=77), compact at max revision",
+            "records": int(store.n), "victims": int(nv), "ms_per_sweep": ms, "records_per_s": store.n / (ms / 1e3),
+            "parity_checked": True,
+            "roofline": {"bound": "hbm", "achieved": alg / 1e9 / (ms / 1e3), "peak": peak, "unit": "GB/s",
+                         "frac": alg / 1e9 / (ms / 1e3) / peak, "alg_bytes": alg},
+            "kernels": kern}
 
 
 def cpu_baseline(wl):
-    """the oracle port timed on this box's host cores on the same workload (bounded: 2 full steps)"""
+    """the oracle port timed on this box's host cores on the same workload (bounded: 2 full steps, legs timed apart)"""
     from oracle import binding as ko
 
     ost = ko.OracleStore(wl["store"])
-    threads = os.cpu_count() or 1
-    cpu_step(ost, wl, threads)
-    t0 = time.perf_counter()
+    threads = host_threads()
+    cpu_legs(ost, wl, threads)
     reps = 2
+    acc = {k: 0.0 for k in CPU_LEGS}
     for _ in range(reps):
-        examined, emitted, deliveries = cpu_step(ost, wl, threads)
-    dt = (time.perf_counter() - t0) / reps
-    return {"value": (examined + wl["events"].n) / dt, "unit": "events/s", "cores": threads, "kind": "port",
-            "sample": f"{reps} full steps (1M-record Range with badger-style per-record copies partition-parallel on "
-                      f"{threads} threads + 256 Lists + 100k events x 10k watchers on {threads} threads)",
-            "s_per_step": dt}
+        legs, examined, emitted, deliveries = cpu_legs(ost, wl, threads)
+        for k in CPU_LEGS:
+            acc[k] += legs[k]
+    summ = cpu_summary({k: v / reps for k, v in acc.items()}, examined + wl["events"].n, threads)
+    summ["sample"] = (f"{reps} full steps on {threads} threads, legs timed separately (1M-record Range faithful / zero copy, "
+                      "256 Lists, 100k events x 10k watchers with / without the per-batch allocation)")
+    return summ
 
 
 def main():
@@ -574,6 +929,11 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--serial", action="store_true", help="scan and fan-out back to back on one stream")
+    ap.add_argument("--mode", default="weak", choices=["weak", "strong"],
+                    help="weak: ~1M records / 10k watchers / 100k events per GPU; strong: configs[4] as written, 8M records + "
+                         "50k watchers + one 100k burst in total")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle comparison of the timed answers")
+    ap.add_argument("--small-compaction", action="store_true", help="extra: config 4 at 1/10 size instead of 100M records")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -246,6 +246,12 @@ void kb_result_free(kb_ctx *ctx, kb_result *res);
 int kb_nccl_unique_id(uint8_t id[KB_NCCL_ID_BYTES]);
 int kb_nccl_init(kb_ctx *ctx, const uint8_t id[KB_NCCL_ID_BYTES], int rank, int nranks);
 int kb_cursor_allgather(kb_ctx *ctx, uint64_t local_rev, uint64_t *all_revs /* nranks */, uint64_t *min_rev);
+/* which transport kb_cursor_allgather uses: stores into peer memory over NVLink (every peer's slot buffer could be
+ * mapped at kb_nccl_init), ncclAllGather otherwise.  kb_cursor_force_nccl(ctx, 1) selects the NCCL path although peers
+ * map -- collective: every rank has to switch before the next exchange. */
+enum { KB_CURSOR_NONE = 0, KB_CURSOR_SINGLE = 1, KB_CURSOR_NCCL = 2, KB_CURSOR_P2P = 3 };
+int kb_cursor_transport(kb_ctx *ctx);
+int kb_cursor_force_nccl(kb_ctx *ctx, int on);
 
 /* ---- measurement hooks (bench.py): per-kernel CUDA-event timing on the ctx stream -------------- */
 typedef struct kb_prof_entry {

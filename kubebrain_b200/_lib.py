@@ -38,7 +38,7 @@ ABI_SYMBOLS = [
     "kb_compact_sweep", "kb_compact_view_get",
     "kb_watch_add", "kb_watch_del", "kb_watch_count", "kb_watch_match", "kb_events_upload", "kb_events_free",
     "kb_watch_match_dev", "kb_match_view_get", "kb_result_free",
-    "kb_nccl_unique_id", "kb_nccl_init", "kb_cursor_allgather",
+    "kb_nccl_unique_id", "kb_nccl_init", "kb_cursor_allgather", "kb_cursor_transport", "kb_cursor_force_nccl",
     "kb_prof_enable", "kb_prof_reset", "kb_prof_read", "kb_launch_count",
 ]
 
@@ -203,6 +203,10 @@ def lib():
     L.kb_nccl_init.argtypes = [vp, u8p, C.c_int, C.c_int]
     L.kb_cursor_allgather.restype = C.c_int
     L.kb_cursor_allgather.argtypes = [vp, C.c_uint64, u64p, u64p]
+    L.kb_cursor_transport.restype = C.c_int
+    L.kb_cursor_transport.argtypes = [vp]
+    L.kb_cursor_force_nccl.restype = C.c_int
+    L.kb_cursor_force_nccl.argtypes = [vp, C.c_int]
     L.kb_prof_enable.restype = C.c_int
     L.kb_prof_enable.argtypes = [vp, C.c_int]
     L.kb_prof_reset.restype = C.c_int
@@ -249,9 +253,11 @@ class RangeResult:
         n = self.n_kvs
         self.elem_off = None
         if self.on_device:
-            # KB_OUT_DEVICE: the arena and the per-kv arrays stay in HBM (device pointers)
+            # KB_OUT_DEVICE: the arena and the per-kv arrays stay in HBM (device pointers, kept as integers)
             self.arena = None
             self.rec_idx = self.rev = self.key_off = self.key_len = self.val_off = self.val_len = None
+            self.dev_ptrs = {name: (C.cast(getattr(v, name), C.c_void_p).value or 0)
+                             for name in ("rec_idx", "rev", "key_off", "key_len", "val_off", "val_len", "elem_off")}
         else:
             if self.wire:
                 self.elem_off = _np(v.elem_off, n + 1, np.uint64) if n else np.zeros(1, np.uint64)
@@ -262,6 +268,14 @@ class RangeResult:
             self.val_off = _np(v.val_off, n, np.uint64)
             self.val_len = _np(v.val_len, n, np.uint32)
             self.arena = _np(v.bytes, self.n_bytes, np.uint8) if v.bytes else np.zeros(0, np.uint8)
+
+    def device_array(self, name: str, dtype) -> np.ndarray:
+        """KB_OUT_DEVICE answers: one of the per-kv arrays copied to the host (after waiting for the answer)"""
+        assert self.on_device
+        self.wait()
+        n = self.n_kvs + (1 if name == "elem_off" else 0)
+        raw = self._eng.read_device(self.dev_ptrs[name], n * np.dtype(dtype).itemsize, sync=False)
+        return np.frombuffer(raw, dtype=dtype).copy()
 
     def kvs(self, q: int = 0) -> List[Tuple[bytes, bytes, int]]:
         assert self.arena is not None, "results were left on the device"
@@ -564,6 +578,13 @@ class Engine:
         mn = C.c_uint64()
         self._check(lib().kb_cursor_allgather(self._ctx, local_rev, out.ctypes.data_as(u64p), C.byref(mn)))
         return out, mn.value
+
+    def cursor_mode(self) -> str:
+        return {0: "none", 1: "single", 2: "nccl", 3: "p2p"}[lib().kb_cursor_transport(self._ctx)]
+
+    def cursor_force_nccl(self, on: bool):
+        """collective: every rank switches before the next exchange"""
+        self._check(lib().kb_cursor_force_nccl(self._ctx, int(on)))
 
     # ---- measurement ----
     def stream(self) -> int:

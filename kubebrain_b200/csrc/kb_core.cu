@@ -817,7 +817,7 @@ k_cursor_p2p(uint64_t *const *__restrict__ peers, int me, int n, uint64_t epoch,
         volatile uint64_t *mine = peers[me] + set + (size_t)r * 2;
         const long long t0 = clock64();
         bool ok = true;
-        while (mine[1] != epoch) {
+        while (mine[1] < epoch) {  // a peer that is AHEAD (this rank skipped an exchange) also releases the wait
             if (clock64() - t0 > 8000000000ll) {  // ~4 s: a peer never joined this exchange
                 ok = false;
                 break;
@@ -830,9 +830,12 @@ k_cursor_p2p(uint64_t *const *__restrict__ peers, int me, int n, uint64_t epoch,
         else atomicExch(&failed, 1);
     }
     __syncthreads();
+    if (r < n) __threadfence_system();  // the gathered values reach the mapped host buffer before the status word
+    __syncthreads();
     if (r == 0) {
         out[n] = smin;
-        out[n + 1] = failed ? 2 : 1;  // status: 1 done, 2 timed out
+        __threadfence_system();
+        *(volatile uint64_t *)&out[n + 1] = failed ? 2 : 1;  // status: 1 done, 2 timed out
     }
 }
 
@@ -917,6 +920,23 @@ extern "C" int kb_nccl_init(kb_ctx *ctx, const uint8_t id[KB_NCCL_ID_BYTES], int
     return KB_OK;
 }
 
+extern "C" int kb_cursor_transport(kb_ctx *ctx)
+{
+    if (!ctx) return KB_EINVAL;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    if (!ctx->nccl_comm) return KB_CURSOR_NONE;
+    if (ctx->nccl_nranks == 1) return KB_CURSOR_SINGLE;
+    return ctx->p2p_ready && !ctx->cursor_force_nccl ? KB_CURSOR_P2P : KB_CURSOR_NCCL;
+}
+
+extern "C" int kb_cursor_force_nccl(kb_ctx *ctx, int on)
+{
+    if (!ctx) return KB_EINVAL;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    ctx->cursor_force_nccl = on != 0;
+    return KB_OK;
+}
+
 __global__ void k_cursor_min(const uint64_t *all, int n, uint64_t *out)
 {
     uint64_t m = ~0ull;
@@ -938,7 +958,7 @@ extern "C" int kb_cursor_allgather(kb_ctx *ctx, uint64_t local_rev, uint64_t *al
         if (min_rev) *min_rev = local_rev;
         return KB_OK;
     }
-    if (ctx->p2p_ready) {
+    if (ctx->p2p_ready && !ctx->cursor_force_nccl) {
         const uint64_t epoch = ++ctx->p2p_epoch;
         volatile uint64_t *out = ctx->h_p2p_out;
         out[n + 1] = 0;
@@ -954,7 +974,14 @@ extern "C" int kb_cursor_allgather(kb_ctx *ctx, uint64_t local_rev, uint64_t *al
             if ((spins & 0xFFFF) == 0 && std::chrono::steady_clock::now() - t0 > std::chrono::seconds(6)) break;
         }
         if (out[n + 1] == 0) KB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        if (out[n + 1] != 1) return kb_fail(ctx, KB_ENCCL, "cursor exchange: a peer did not join epoch %llu", (unsigned long long)epoch);
+        if (out[n + 1] != 1) {
+            // A peer never joined.  This rank leaves the peer-memory path for good: the late peer still finds this rank's
+            // flag for the epoch it missed, then times out on the next one and falls back too, so the ranks meet again in
+            // ncclAllGather instead of waiting 4 s on every exchange from here on.
+            ctx->p2p_ready = false;
+            return kb_fail(ctx, KB_ENCCL, "cursor exchange: a peer did not join epoch %llu (falling back to ncclAllGather)",
+                           (unsigned long long)epoch);
+        }
         if (all_revs)
             for (int r = 0; r < n; r++) all_revs[r] = out[r];
         if (min_rev) *min_rev = out[n];

@@ -211,6 +211,7 @@ struct kb_ctx {
     DBuf d_cursor;
     // peer-memory cursor exchange (set up by kb_nccl_init when every peer's slot buffer can be mapped over NVLink)
     bool p2p_ready = false;
+    bool cursor_force_nccl = false;           // kb_cursor_force_nccl: measure / use the ncclAllGather path although peers map
     uint64_t p2p_epoch = 0;
     void *p2p_mine = nullptr;                 // this rank's slot buffer: 2 epochs x nranks x {value, flag}
     std::vector<void *> p2p_peer;             // every rank's slot buffer as seen from this device (own entry = p2p_mine)

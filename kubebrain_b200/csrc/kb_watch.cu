@@ -8,19 +8,22 @@
 //
 // Brute force is W x E prefix tests (1e9 for 10k watchers x 100k events).  Here watchers are grouped by
 // distinct prefix; an event probes a device hash table once per DISTINCT PREFIX LENGTH with the FNV-1a
-// hash of its own leading bytes (verified byte-exactly), so the work is O(E * #lengths + deliveries):
-//   k_batch_pm       per collector batch: running max of Event.Revision (the "leading strip" predicate becomes
-//                    pm[i] >= min_rev) + a flag "revisions globally non-decreasing"
-//   k_match_count    per event and prefix length: matched group (kept in ematch) + warp-aggregated group counts
-//   (scan)           group segment offsets
-//   k_classify       groups by match count: small (<=32), medium (<= BIG_T), large (global bitmap)
-//   k_scatter        small/medium: warp-aggregated slot claim into the group's segment (unordered across warps);
-//                    large: the warp's ballot IS the 32-event bitmap word of the group (plain store, no atomics)
-//   k_sort_small / k_sort_medium / k_expand_large   every segment ascending (warp rank-sort / shared-memory bitmap /
-//                    ordered expansion of the global bitmap)
-//   k_expand_count   per watcher: deliveries = its group's segment filtered by min_rev
-//   (scan)           per-watcher output offsets
-//   k_expand_write   ordered event indices, one thread per delivery (suffix copy when revisions are monotone)
+// hash of its own leading bytes (verified byte-exactly), so the work is O(E * #lengths + deliveries).
+//
+// Round 2: the seven dependent launches of round 1 (each queueing again behind the scan context's persistent
+// CTAs) are ONE cooperative kernel, k_fanout, whose phases are separated by grid barriers:
+//   P1  per collector batch: running max of Event.Revision (the "leading strip" predicate becomes pm[i] >= min_rev)
+//       and a flag "revisions globally non-decreasing"; per event and prefix length: the matched group (ematch) and
+//       warp-aggregated group counts
+//   P2  per event: the group's segment is claimed lazily from a bump allocator (segments need to be disjoint, not
+//       ordered, so no prefix sum over the groups); groups are classified small (<= 32 matches), medium (<= big_t),
+//       large (global bitmap); small/medium matches are scattered with warp-aggregated slot claims, for a large group
+//       the warp's ballot IS the 32-event bitmap word
+//   P3  medium groups: shared-memory bitmap windows -> ascending segment; large groups: ordered bitmap expansion
+//   P4  warp per watcher: small groups are rank-sorted in registers here; deliveries = its group's ascending segment
+//       filtered by min_rev (a suffix found by a 32-ary search when revisions are monotone)
+//   P5  the last CTA to finish P4 computes the per-watcher output offsets and leaves the scratch clean for the next call
+// followed by k_publish_total (mapped pinned flag: the host returns here) and k_expand_write (one thread per delivery).
 #include <algorithm>
 #include <map>
 #include <unordered_map>
@@ -36,11 +39,16 @@ struct kb_events_dev {
 };
 
 struct WatchTablesDev {
-    uint32_t n_ids = 0, n_groups = 0, n_lens = 0, table_size = 0, max_len = 0;
+    uint32_t n_ids = 0, n_groups = 0, n_lens = 0, table_size = 0, max_len = 0, pstride16 = 1;
     uint64_t d_hint = 0;  // deliveries of the previous match (sizes the next output buffer)
-    DBuf gprefix, goff16, glen, ghash, gstart, gmember, wgroup, wminrev, lens, table;
+    DBuf gprefix, wgroup, wminrev, lens, table;
     // per-call scratch
-    DBuf zeros, gbase, gclass, ematch, seg, seg_sorted, bitmaps, pm, wcnt, wlo, wstart, total;
+    DBuf gstate /* gcnt | gfill | ctl */, galloc, lists, ematch, seg, seg_sorted, bitmaps, pm, wstate /* wcnt | wsrc | wn | wlo */,
+        wstart, total;
+    bool scratch_clean = false;   // the previous k_fanout left gstate / galloc / bitmaps in their initial state
+    uint32_t scratch_groups = 0, scratch_large = 0, scratch_bm_words = 0;
+    uint32_t fan_gen = 0;         // value of the grid-barrier generation word after the last launch
+    int fan_grid = 0;             // co-resident CTAs of k_fanout on this device (0: not queried yet)
 };
 
 namespace {
@@ -65,15 +73,53 @@ struct EvDev {
 };
 
 struct TabDev {
-    const uint4 *gprefix;
-    const uint32_t *goff16, *glen;
-    const uint64_t *ghash;
-    const uint32_t *gstart, *gmember, *wgroup;
+    const uint4 *gprefix;      // group g's prefix at gprefix + g * pstride16 (zero padded)
+    const uint32_t *wgroup;
     const uint64_t *wminrev;
-    const uint32_t *lens;
-    const uint32_t *table;
-    uint32_t n_ids, n_groups, n_lens, mask, max_len;
+    const uint32_t *lens;      // distinct prefix lengths, ascending
+    const uint4 *table;        // open addressing: {hash lo, hash hi, prefix length, group} ; group == NONE: empty
+    uint32_t n_ids, n_groups, n_lens, mask, max_len, pstride16;
 };
+
+// control words of one match (gstate: [gcnt G+1][gfill G+1][ctl 16])
+enum { FC_NONMONO = 0, FC_CURSOR = 1, FC_NLARGE = 2, FC_NMED = 3, FC_ARRIVE = 4, FC_GEN = 5, FC_DONE = 6, FC_WORDS = 16 };
+constexpr unsigned long long FAN_UNSET = ~0ull, FAN_BUSY = ~0ull - 1;
+constexpr uint32_t FAN_THREADS = 256;
+constexpr uint32_t BM_WORDS = 1024;  // 32768 event indices per shared-memory window (4 KiB: the CTA stays co-resident
+                                     // with the scan context's shared-memory-heavy kernels)
+
+struct FanScratch {
+    uint32_t *gcnt, *gfill, *ctl;
+    unsigned long long *galloc;      // per group (bitmap slot or NONE) << 32 | segment base; FAN_UNSET between calls
+    uint32_t *med_list, *large_list;
+    uint32_t *ematch, *seg, *sorted, *bitmaps;
+    uint64_t *pm;
+    uint32_t *wcnt, *wsrc, *wn, *wlo;
+    uint64_t *wstart, *total;
+    uint32_t big_t, max_large, bm_words, chunks_per_group, gen_base;
+};
+
+// scratch written by one CTA and read by another inside the same launch goes around the (non-coherent) L1
+__device__ __forceinline__ uint32_t ldcg32(const uint32_t *p) { return __ldcg(p); }
+__device__ __forceinline__ uint64_t ldcg64(const uint64_t *p) { return __ldcg((const unsigned long long *)p); }
+
+// grid barrier of a cooperative launch: `gen` only ever grows (the host passes the value it had before the launch)
+__device__ __forceinline__ void fan_grid_sync(uint32_t *ctl, uint32_t target)
+{
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(&ctl[FC_ARRIVE], 1u) == gridDim.x - 1) {
+            atomicExch(&ctl[FC_ARRIVE], 0u);  // nobody arrives at the next barrier before the release below
+            __threadfence();
+            atomicExch(&ctl[FC_GEN], target);
+        } else {
+            while (*(volatile uint32_t *)&ctl[FC_GEN] != target) __nanosleep(64);
+        }
+        __threadfence();
+    }
+    __syncthreads();
+}
 
 // ---- running max of the revisions inside each collector batch (filterByRevision strips only the LEADING
 //      events below min_rev, watch.go:153-159, so event i survives iff max(rev[batch start..i]) >= min_rev)
@@ -115,29 +161,29 @@ __device__ __forceinline__ void d_match_count(const EvDev &ev, const TabDev &tb,
     uint32_t pos = 0;  // bytes hashed so far
     uint4 chunk = make_uint4(0, 0, 0, 0);
     for (uint32_t li = 0; li < tb.n_lens; li++) {  // uniform trip count: the warp collectives below need all lanes
-        const uint32_t L = tb.lens[li];
+        const uint32_t L = __ldg(tb.lens + li);
         uint32_t g = KB_NONE;
         if (valid && L <= klen) {
             while (pos < L) {
-                if ((pos & 15) == 0) chunk = kp[pos >> 4];
+                if ((pos & 15) == 0) chunk = __ldg(kp + (pos >> 4));
                 h = (h ^ (uint64_t)byte_of(chunk, pos & 15)) * FNV_PRIME;
                 pos++;
             }
-            // probe (hash, length); verify the bytes so the result is exact
+            // probe (hash, length): one 16-byte entry per slot; verify the bytes so the result is exact
             uint32_t s = slot_of(h, L, tb.mask);
             for (;;) {
-                const uint32_t c = tb.table[s];
-                if (c == KB_NONE) break;
-                if (tb.ghash[c] == h && tb.glen[c] == L) {
-                    const uint4 *gp = tb.gprefix + tb.goff16[c];
+                const uint4 t = __ldg(tb.table + s);
+                if (t.w == KB_NONE) break;
+                if (t.x == (uint32_t)h && t.y == (uint32_t)(h >> 32) && t.z == L) {
+                    const uint4 *gp = tb.gprefix + (uint64_t)t.w * tb.pstride16;
                     bool eq = true;
                     for (uint32_t k = 0; k * 16 < L && eq; k++) {
-                        uint4 a = kp[k], b = gp[k];
+                        uint4 a = __ldg(kp + k), b = __ldg(gp + k);
                         int p = first_diff16(a, b);
                         if (p < 16 && k * 16 + p < L) eq = false;
                     }
                     if (eq) {
-                        g = c;
+                        g = t.w;
                         break;  // prefixes are unique per group
                     }
                 }
@@ -150,161 +196,66 @@ __device__ __forceinline__ void d_match_count(const EvDev &ev, const TabDev &tb,
     }
 }
 
-// one launch: blocks [0, pm_blocks) compute the per-batch running max, the rest match events against the groups
-__global__ void __launch_bounds__(256)
-k_match_count(EvDev ev, TabDev tb, uint32_t pm_blocks, uint64_t *__restrict__ pm, uint32_t *__restrict__ nonmono,
-              uint32_t *__restrict__ ematch, uint32_t *__restrict__ gcnt)
+// ---- P2: claim the group's segment on first touch, then scatter
+__device__ __forceinline__ unsigned long long d_group_alloc(const FanScratch &sc, uint32_t g)
 {
-    if (blockIdx.x < pm_blocks)
-        d_batch_pm(ev, pm, nonmono, blockIdx.x);
-    else if (tb.n_groups)
-        d_match_count(ev, tb, ematch, gcnt, blockIdx.x - pm_blocks);
+    unsigned long long a = __ldcg(&sc.galloc[g]);
+    if (a < FAN_BUSY) return a;
+    const unsigned long long old = atomicCAS(&sc.galloc[g], FAN_UNSET, FAN_BUSY);
+    if (old == FAN_UNSET) {
+        const uint32_t n = ldcg32(&sc.gcnt[g]);
+        uint32_t cls = KB_NONE;
+        if (n > sc.big_t) {
+            const uint32_t slot = atomicAdd(&sc.ctl[FC_NLARGE], 1u);
+            if (slot < sc.max_large) {  // cannot overflow: sum(gcnt) <= E * n_lens
+                cls = slot;
+                sc.large_list[slot] = g;
+            }
+        } else if (n > 32) {
+            sc.med_list[atomicAdd(&sc.ctl[FC_NMED], 1u)] = g;
+        }
+        const uint32_t base = atomicAdd(&sc.ctl[FC_CURSOR], n);
+        a = ((unsigned long long)cls << 32) | base;
+        __threadfence();
+        atomicExch(&sc.galloc[g], a);
+        return a;
+    }
+    if (old < FAN_BUSY) return old;
+    // another warp is allocating (it never waits for anybody): spin until it has published
+    do {
+        __nanosleep(32);
+        a = *(volatile unsigned long long *)&sc.galloc[g];
+    } while (a >= FAN_BUSY);
+    return a;
 }
 
-// single CTA: exclusive scan of the group counts (segment offsets) + classification by count.
-// lists layout: [0]=n_medium [1]=n_large [2..2+G) medium groups [2+G..2+2G) large groups
-__global__ void __launch_bounds__(1024)
-k_group_scan_classify(uint32_t n_groups, const uint32_t *__restrict__ gcnt, uint32_t big_t, uint32_t max_large,
-                      uint32_t *__restrict__ gbase, uint32_t *__restrict__ gclass, uint32_t *__restrict__ lists)
+__device__ __forceinline__ void d_scatter(const FanScratch &sc, uint32_t n_events, uint32_t n_lens, uint32_t vblock)
 {
-    __shared__ uint32_t wsum[33];
-    __shared__ uint32_t carry_s;
-    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    if (threadIdx.x == 0) carry_s = 0;
-    __syncthreads();
-    for (uint32_t c0 = 0; c0 < n_groups; c0 += 1024) {
-        const uint32_t g = c0 + threadIdx.x;
-        const uint32_t n = g < n_groups ? gcnt[g] : 0;
-        uint32_t inc = n;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            uint32_t o = __shfl_up_sync(FULL, inc, d);
-            if (lane >= (unsigned)d) inc += o;
-        }
-        if (lane == 31) wsum[wid] = inc;
-        __syncthreads();
-        if (wid == 0) {
-            uint32_t v = wsum[lane], iv = v;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                uint32_t o = __shfl_up_sync(FULL, iv, d);
-                if (lane >= (unsigned)d) iv += o;
-            }
-            wsum[lane] = iv - v;
-            if (lane == 31) wsum[32] = iv;
-        }
-        __syncthreads();
-        const uint32_t carry = carry_s;
-        if (g < n_groups) {
-            gbase[g] = carry + wsum[wid] + inc - n;
-            uint32_t cls = KB_NONE;  // NONE: small or medium (segment scatter); otherwise the bitmap slot
-            if (n > big_t) {
-                const uint32_t slot = atomicAdd(&lists[1], 1u);
-                if (slot < max_large) {  // cannot overflow: sum(gcnt) <= E * n_lens
-                    cls = slot;
-                    lists[2 + n_groups + slot] = g;
-                }
-            } else if (n > 32) {
-                lists[2 + atomicAdd(&lists[0], 1u)] = g;
-            }
-            gclass[g] = cls;
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) carry_s = carry + wsum[32];
-        __syncthreads();
-    }
-}
-
-// single CTA: exclusive scan of the per-watcher delivery counts; wstart[W] = total
-__global__ void __launch_bounds__(1024)
-k_watcher_scan(uint32_t n, const uint64_t *__restrict__ wcnt, uint64_t *__restrict__ wstart, uint64_t *__restrict__ total)
-{
-    __shared__ uint64_t wsum[33];
-    __shared__ uint64_t carry_s;
-    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    if (threadIdx.x == 0) carry_s = 0;
-    __syncthreads();
-    for (uint32_t c0 = 0; c0 < n; c0 += 1024) {
-        const uint32_t w = c0 + threadIdx.x;
-        const uint64_t v0 = w < n ? wcnt[w] : 0;
-        uint64_t inc = v0;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            uint64_t o = __shfl_up_sync(FULL, inc, d);
-            if (lane >= (unsigned)d) inc += o;
-        }
-        if (lane == 31) wsum[wid] = inc;
-        __syncthreads();
-        if (wid == 0) {
-            uint64_t v = wsum[lane], iv = v;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                uint64_t o = __shfl_up_sync(FULL, iv, d);
-                if (lane >= (unsigned)d) iv += o;
-            }
-            wsum[lane] = iv - v;
-            if (lane == 31) wsum[32] = iv;
-        }
-        __syncthreads();
-        const uint64_t carry = carry_s;
-        if (w < n) wstart[w] = carry + wsum[wid] + inc - v0;
-        __syncthreads();
-        if (threadIdx.x == 0) carry_s = carry + wsum[32];
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) {
-        wstart[n] = carry_s;
-        *total = carry_s;
-    }
-}
-
-__global__ void __launch_bounds__(256)
-k_scatter(uint32_t n_events, uint32_t n_lens, const uint32_t *__restrict__ ematch,
-          const uint32_t *__restrict__ gclass, const uint32_t *__restrict__ gbase, uint32_t *__restrict__ gfill,
-          uint32_t *__restrict__ seg, uint32_t *__restrict__ bitmaps, uint32_t bm_words)
-{
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t i = vblock * blockDim.x + threadIdx.x;
     const uint32_t lane = threadIdx.x & 31;
     const bool valid = i < n_events;
     for (uint32_t li = 0; li < n_lens; li++) {
-        const uint32_t g = valid ? ematch[(uint64_t)li * n_events + i] : KB_NONE;
+        const uint32_t g = valid ? sc.ematch[(uint64_t)li * n_events + i] : KB_NONE;  // written by this very thread in P1
         const unsigned peers = __match_any_sync(FULL, g);
         if (g == KB_NONE) continue;
         const uint32_t leader = __ffs(peers) - 1;
-        const uint32_t cls = gclass[g];
+        unsigned long long a = 0;
+        uint32_t fill = 0;
+        if (lane == leader) {
+            a = d_group_alloc(sc, g);
+            if ((uint32_t)(a >> 32) == KB_NONE) fill = atomicAdd(&sc.gfill[g], (uint32_t)__popc(peers));
+        }
+        const uint32_t base = __shfl_sync(peers, (uint32_t)a, leader);
+        const uint32_t cls = __shfl_sync(peers, (uint32_t)(a >> 32), leader);
+        fill = __shfl_sync(peers, fill, leader);
         if (cls != KB_NONE) {
             // the 32 events of this warp are exactly one bitmap word of the group
-            if (lane == leader) bitmaps[(uint64_t)cls * bm_words + (i >> 5)] = peers;
+            if (lane == leader) sc.bitmaps[(uint64_t)cls * sc.bm_words + (i >> 5)] = peers;
         } else {
-            uint32_t base = 0;
-            if (lane == leader) base = atomicAdd(&gfill[g], (uint32_t)__popc(peers));
-            base = __shfl_sync(peers, base, leader);
-            seg[gbase[g] + base + __popc(peers & ((1u << lane) - 1))] = i;
+            sc.seg[base + fill + __popc(peers & ((1u << lane) - 1))] = i;
         }
     }
 }
-
-// ---- segment sort: ascending event index per group
-__device__ __forceinline__ void d_sort_small(uint32_t n_groups, const uint32_t *__restrict__ gcnt,
-                                             const uint32_t *__restrict__ gbase, const uint32_t *__restrict__ seg,
-                                             uint32_t *__restrict__ sorted, uint32_t vblock)
-{
-    const uint32_t g = (vblock * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (g >= n_groups) return;
-    const uint32_t n = gcnt[g];
-    if (n == 0 || n > 32) return;
-    const uint32_t base = gbase[g];
-    const uint32_t v = lane < n ? seg[base + lane] : 0xFFFFFFFFu;
-    uint32_t rank = 0;
-#pragma unroll
-    for (int j = 0; j < 32; j++) {
-        const uint32_t o = __shfl_sync(FULL, v, j);
-        rank += (o < v) ? 1u : 0u;  // event indices inside one group are distinct
-    }
-    if (lane < n) sorted[base + rank] = v;
-}
-
-constexpr uint32_t BM_WORDS = 8192;  // 262144 event indices per window (32 KiB of shared memory)
 
 __device__ __forceinline__ uint32_t block_excl_scan_u32(uint32_t v, uint32_t *wsum /* 9 */, uint32_t &total)
 {
@@ -333,16 +284,13 @@ __device__ __forceinline__ uint32_t block_excl_scan_u32(uint32_t v, uint32_t *ws
     return ex;
 }
 
-// one CTA per medium group (33..big_t entries): shared-memory bitmap over [min, max] of the segment
-__device__ __forceinline__ void d_sort_medium(const uint32_t *__restrict__ lists, const uint32_t *__restrict__ gcnt,
-                                              const uint32_t *__restrict__ gbase, const uint32_t *__restrict__ seg,
-                                              uint32_t *__restrict__ sorted, uint32_t *bm, uint32_t *wsum, uint32_t *red,
-                                              uint32_t vblock, uint32_t vgrid)
+// ---- P3a: one CTA per medium group (33..big_t entries): shared-memory bitmap over windows of its [min, max]
+__device__ __forceinline__ void d_sort_medium(const FanScratch &sc, uint32_t *bm, uint32_t *wsum, uint32_t *red)
 {
-    const uint32_t nmed = lists[0];
-    for (uint32_t bi = vblock; bi < nmed; bi += vgrid) {
-        const uint32_t g = lists[2 + bi];
-        const uint32_t n = gcnt[g], base = gbase[g];
+    const uint32_t nmed = ldcg32(&sc.ctl[FC_NMED]);
+    for (uint32_t bi = blockIdx.x; bi < nmed; bi += gridDim.x) {
+        const uint32_t g = ldcg32(&sc.med_list[bi]);
+        const uint32_t n = ldcg32(&sc.gcnt[g]), base = (uint32_t)__ldcg(&sc.galloc[g]);
         if (threadIdx.x == 0) {
             red[0] = 0xFFFFFFFFu;
             red[1] = 0;
@@ -350,7 +298,7 @@ __device__ __forceinline__ void d_sort_medium(const uint32_t *__restrict__ lists
         __syncthreads();
         uint32_t mn = 0xFFFFFFFFu, mx = 0;
         for (uint32_t j = threadIdx.x; j < n; j += blockDim.x) {
-            const uint32_t v = seg[base + j];
+            const uint32_t v = ldcg32(&sc.seg[base + j]);
             mn = min(mn, v);
             mx = max(mx, v);
         }
@@ -366,7 +314,7 @@ __device__ __forceinline__ void d_sort_medium(const uint32_t *__restrict__ lists
             for (uint32_t j = threadIdx.x; j < nwords; j += blockDim.x) bm[j] = 0;
             __syncthreads();
             for (uint32_t j = threadIdx.x; j < n; j += blockDim.x) {
-                const uint64_t v = seg[base + j];
+                const uint64_t v = ldcg32(&sc.seg[base + j]);
                 if (v >= w0 && v < w0 + (uint64_t)nwords * 32) {
                     const uint32_t d = (uint32_t)(v - w0);
                     atomicOr(&bm[d >> 5], 1u << (d & 31));
@@ -385,7 +333,7 @@ __device__ __forceinline__ void d_sort_medium(const uint32_t *__restrict__ lists
                 while (bits) {
                     const uint32_t b = __ffs(bits) - 1;
                     bits &= bits - 1;
-                    sorted[base + at++] = (uint32_t)(w0 + (uint64_t)j * 32 + b);
+                    sc.sorted[base + at++] = (uint32_t)(w0 + (uint64_t)j * 32 + b);
                 }
             }
             outpos += total;
@@ -395,169 +343,247 @@ __device__ __forceinline__ void d_sort_medium(const uint32_t *__restrict__ lists
     }
 }
 
-// large groups: ordered expansion of the global bitmap; CTA = (large group, chunk of 256 words)
-__device__ __forceinline__ void d_expand_large(const uint32_t *__restrict__ lists, uint32_t n_groups,
-                                               const uint32_t *__restrict__ gbase, const uint32_t *__restrict__ bitmaps,
-                                               uint32_t bm_words, uint32_t chunks_per_group,
-                                               uint32_t *__restrict__ sorted, uint32_t *wsum, uint32_t *pre_sp,
-                                               uint32_t vblock, uint32_t vgrid)
+// ---- P3b: large groups: ordered expansion of the global bitmap; job = (large group, chunk of 256 words)
+__device__ __forceinline__ void d_expand_large(const FanScratch &sc, uint32_t *wsum, uint32_t *pre_sp)
 {
     uint32_t &pre_s = *pre_sp;
-    const uint32_t nlarge = lists[1];
-    for (uint32_t job = vblock; job < nlarge * chunks_per_group; job += vgrid) {
-        const uint32_t slot = job / chunks_per_group, chunk = job % chunks_per_group;
-        const uint32_t g = lists[2 + n_groups + slot];
-        const uint32_t *bm = bitmaps + (uint64_t)slot * bm_words;
+    const uint32_t nlarge = min(ldcg32(&sc.ctl[FC_NLARGE]), sc.max_large);
+    for (uint32_t job = blockIdx.x; job < nlarge * sc.chunks_per_group; job += gridDim.x) {
+        const uint32_t slot = job / sc.chunks_per_group, chunk = job % sc.chunks_per_group;
+        const uint32_t g = ldcg32(&sc.large_list[slot]);
+        const uint32_t *bm = sc.bitmaps + (uint64_t)slot * sc.bm_words;
         // matches in the words before this chunk
         uint32_t part = 0;
-        for (uint32_t j = threadIdx.x; j < chunk * 256; j += blockDim.x) part += __popc(bm[j]);
+        for (uint32_t j = threadIdx.x; j < chunk * 256; j += blockDim.x) part += __popc(ldcg32(&bm[j]));
         uint32_t tot;
         block_excl_scan_u32(part, wsum, tot);
         if (threadIdx.x == 0) pre_s = tot;
         __syncthreads();
         const uint32_t wi = chunk * 256 + threadIdx.x;
-        uint32_t bits = wi < bm_words ? bm[wi] : 0;
+        uint32_t bits = wi < sc.bm_words ? ldcg32(&bm[wi]) : 0;
         uint32_t total;
-        uint32_t at = gbase[g] + pre_s + block_excl_scan_u32(__popc(bits), wsum, total);
+        uint32_t at = (uint32_t)__ldcg(&sc.galloc[g]) + pre_s + block_excl_scan_u32(__popc(bits), wsum, total);
         while (bits) {
             const uint32_t b = __ffs(bits) - 1;
             bits &= bits - 1;
-            sorted[at++] = wi * 32 + b;
+            sc.sorted[at++] = wi * 32 + b;
         }
         __syncthreads();
     }
 }
 
-// one launch for the three segment-ordering paths: blocks [0,nb_small) warp rank-sort, [nb_small, nb_small+nb_med)
-// shared-memory bitmap sort of medium groups, the rest expand the large groups' global bitmaps
-__global__ void __launch_bounds__(256)
-k_sort(uint32_t n_groups, const uint32_t *__restrict__ gcnt, const uint32_t *__restrict__ gbase,
-       const uint32_t *__restrict__ seg, uint32_t *__restrict__ sorted, const uint32_t *__restrict__ lists,
-       const uint32_t *__restrict__ bitmaps, uint32_t bm_words, uint32_t chunks_per_group, uint32_t nb_small,
-       uint32_t nb_med)
+// ---- P4: warp per watcher
+__device__ __forceinline__ void d_watcher_count(const TabDev &tb, const FanScratch &sc, bool mono)
+{
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < tb.n_ids; w += warps) {
+        const uint32_t g = __ldg(tb.wgroup + w);
+        uint32_t n = 0, base = 0, lo = 0, cnt = 0;
+        unsigned long long a = FAN_UNSET;
+        if (g != KB_NONE) a = __ldcg(&sc.galloc[g]);
+        if (a < FAN_BUSY) {  // the group matched at least one event
+            n = ldcg32(&sc.gcnt[g]);
+            base = (uint32_t)a;
+            const uint64_t mr = __ldg(tb.wminrev + w);
+            if (n <= 32) {
+                // small group: rank sort in registers; every watcher of the group writes the same ascending segment
+                const uint32_t v = lane < n ? ldcg32(&sc.seg[base + lane]) : 0xFFFFFFFFu;
+                uint32_t rank = 0;
+#pragma unroll
+                for (int j = 0; j < 32; j++) {
+                    const uint32_t o = __shfl_sync(FULL, v, j);
+                    rank += (o < v) ? 1u : 0u;  // event indices inside one group are distinct
+                }
+                if (lane < n) sc.sorted[base + rank] = v;
+                const bool keep = lane < n && ldcg64(&sc.pm[v]) >= mr;
+                cnt = __popc(__ballot_sync(FULL, keep));
+                lo = mono ? n - cnt : 0;
+            } else if (mono) {
+                // survivors are a suffix of the ascending segment: 32-ary search for the first event at or above min_rev
+                const uint32_t *M = sc.sorted + base;
+                uint32_t hi = n;
+                for (;;) {
+                    const uint32_t span = hi - lo;
+                    if (span == 0) break;
+                    if (span <= 32) {
+                        const bool ge = lane < span && ldcg64(&sc.pm[ldcg32(&M[lo + lane])]) >= mr;
+                        const unsigned m = __ballot_sync(FULL, ge);
+                        lo += m ? (uint32_t)(__ffs(m) - 1) : span;
+                        break;
+                    }
+                    const uint32_t piv = lo + (uint32_t)(((uint64_t)span * (lane + 1)) / 33);
+                    const bool ge = ldcg64(&sc.pm[ldcg32(&M[piv])]) >= mr;
+                    const int k = __popc(~__ballot_sync(FULL, ge));  // pivots below min_rev: a prefix of the lanes
+                    uint32_t nlo = lo, nhi = hi;
+                    if (k > 0) nlo = __shfl_sync(FULL, piv, k - 1) + 1;
+                    if (k < 32) nhi = __shfl_sync(FULL, piv, k);
+                    lo = nlo;
+                    hi = nhi;
+                }
+                cnt = n - lo;
+            } else {
+                const uint32_t *M = sc.sorted + base;
+                for (uint32_t c = 0; c < n; c += 32) {
+                    const uint32_t j = c + lane;
+                    const bool keep = j < n && ldcg64(&sc.pm[ldcg32(&M[j])]) >= mr;
+                    cnt += __popc(__ballot_sync(FULL, keep));
+                }
+            }
+        }
+        if (lane == 0) {
+            sc.wcnt[w] = cnt;
+            sc.wsrc[w] = base;
+            sc.wn[w] = n;
+            sc.wlo[w] = lo;
+        }
+    }
+}
+
+// ---- P5 (one CTA): exclusive prefix of the per-watcher delivery counts; scratch back to its initial state
+__device__ __forceinline__ void d_finish(const TabDev &tb, const FanScratch &sc, uint64_t *ws /* 33 */)
+{
+    const uint32_t W = tb.n_ids, T = blockDim.x;
+    const uint32_t per = (W + T - 1) / T;
+    const uint32_t a = min(W, threadIdx.x * per), b = min(W, a + per);
+    uint64_t sum = 0;
+    for (uint32_t w = a; w < b; w++) sum += ldcg32(&sc.wcnt[w]);
+    // block exclusive scan of `sum`
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint64_t inc = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint64_t o = __shfl_up_sync(FULL, inc, d);
+        if (lane >= (unsigned)d) inc += o;
+    }
+    if (lane == 31) ws[wid] = inc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint64_t run = 0;
+        for (uint32_t k = 0; k < (T >> 5); k++) {
+            uint64_t x = ws[k];
+            ws[k] = run;
+            run += x;
+        }
+        ws[32] = run;
+    }
+    __syncthreads();
+    uint64_t at = ws[wid] + inc - sum;
+    for (uint32_t w = a; w < b; w++) {
+        sc.wstart[w] = at;
+        at += ldcg32(&sc.wcnt[w]);
+    }
+    if (threadIdx.x == 0) {
+        sc.wstart[W] = ws[32];
+        sc.total[0] = ws[32];
+        sc.total[1] = ldcg32(&sc.ctl[FC_NONMONO]);  // k_expand_write picks its path from this copy
+    }
+    // leave the scratch as the next call expects it (every other CTA has finished reading it)
+    const uint32_t G = tb.n_groups;
+    const uint32_t nlarge = min(ldcg32(&sc.ctl[FC_NLARGE]), sc.max_large);
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < 2 * (G + 1); i += T) sc.gcnt[i] = 0;  // gcnt | gfill are contiguous
+    for (uint32_t i = threadIdx.x; i < G; i += T) sc.galloc[i] = FAN_UNSET;
+    for (uint64_t i = threadIdx.x; i < (uint64_t)nlarge * sc.bm_words; i += T) sc.bitmaps[i] = 0;
+    if (threadIdx.x < FC_WORDS && threadIdx.x != FC_GEN) sc.ctl[threadIdx.x] = 0;
+}
+
+__global__ void __launch_bounds__(FAN_THREADS, 2)
+k_fanout(EvDev ev, TabDev tb, FanScratch sc)
 {
     __shared__ uint32_t bm[BM_WORDS];
     __shared__ uint32_t wsum[9];
     __shared__ uint32_t red[2];
-    if (blockIdx.x < nb_small)
-        d_sort_small(n_groups, gcnt, gbase, seg, sorted, blockIdx.x);
-    else if (blockIdx.x < nb_small + nb_med)
-        d_sort_medium(lists, gcnt, gbase, seg, sorted, bm, wsum, red, blockIdx.x - nb_small, nb_med);
-    else
-        d_expand_large(lists, n_groups, gbase, bitmaps, bm_words, chunks_per_group, sorted, wsum, red,
-                       blockIdx.x - nb_small - nb_med, gridDim.x - nb_small - nb_med);
-}
-
-// ---- per watcher: deliveries = its group's sorted segment filtered by pm[e] >= min_rev
-__global__ void __launch_bounds__(256)
-k_expand_count(TabDev tb, const uint32_t *__restrict__ gcnt, const uint32_t *__restrict__ gbase,
-               const uint32_t *__restrict__ sorted, const uint64_t *__restrict__ pm,
-               const uint32_t *__restrict__ nonmono, uint64_t *__restrict__ wcnt, uint32_t *__restrict__ wlo)
-{
-    if (*nonmono == 0) {
-        // revisions non-decreasing over the whole slab: the survivors are a suffix of the segment -> one thread
-        // per watcher, binary search for the first event at or above min_rev
-        const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
-        if (w >= tb.n_ids) return;
-        const uint32_t g = tb.wgroup[w];
-        uint32_t n = 0, lo = 0;
-        if (g != KB_NONE) {
-            n = gcnt[g];
-            const uint32_t *M = sorted + gbase[g];
-            const uint64_t mr = tb.wminrev[w];
-            uint32_t hi = n;
-            while (lo < hi) {
-                const uint32_t mid = (lo + hi) >> 1;
-                if (pm[M[mid]] >= mr) hi = mid; else lo = mid + 1;
-            }
-        }
-        wcnt[w] = n - lo;
-        wlo[w] = lo;
-        return;
+    __shared__ uint64_t ws64[33];
+    __shared__ uint32_t last_s;
+    // P1
+    const uint32_t pm_blocks = (ev.nb * 32 + FAN_THREADS - 1) / FAN_THREADS;
+    const uint32_t ev_blocks = tb.n_groups ? (ev.n + FAN_THREADS - 1) / FAN_THREADS : 0;
+    for (uint32_t vb = blockIdx.x; vb < pm_blocks + ev_blocks; vb += gridDim.x) {
+        if (vb < pm_blocks)
+            d_batch_pm(ev, sc.pm, &sc.ctl[FC_NONMONO], vb);
+        else
+            d_match_count(ev, tb, sc.ematch, sc.gcnt, vb - pm_blocks);
     }
-    const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (w >= tb.n_ids) return;
-    const uint32_t g = tb.wgroup[w];
-    if (g == KB_NONE) {
-        if (lane == 0) {
-            wcnt[w] = 0;
-            wlo[w] = 0;
-        }
-        return;
+    fan_grid_sync(sc.ctl, sc.gen_base + 1);
+    // P2
+    for (uint32_t vb = blockIdx.x; vb < ev_blocks; vb += gridDim.x) d_scatter(sc, ev.n, tb.n_lens, vb);
+    fan_grid_sync(sc.ctl, sc.gen_base + 2);
+    // P3
+    d_sort_medium(sc, bm, wsum, red);
+    d_expand_large(sc, wsum, red);
+    fan_grid_sync(sc.ctl, sc.gen_base + 3);
+    // P4
+    const bool mono = ldcg32(&sc.ctl[FC_NONMONO]) == 0;
+    d_watcher_count(tb, sc, mono);
+    // P5: the last CTA to get here finishes alone; the end of the kernel is the barrier for what follows
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        last_s = atomicAdd(&sc.ctl[FC_DONE], 1u) == gridDim.x - 1;
+        __threadfence();
     }
-    const uint32_t n = gcnt[g];
-    const uint32_t *M = sorted + gbase[g];
-    const uint64_t mr = tb.wminrev[w];
-    uint64_t total = 0;
-    for (uint32_t c = 0; c < n; c += 32) {
-        const uint32_t j = c + lane;
-        const bool keep = j < n && pm[M[j]] >= mr;
-        total += __popc(__ballot_sync(FULL, keep));
-    }
-    if (lane == 0) {
-        wcnt[w] = total;
-        wlo[w] = 0;
-    }
+    __syncthreads();
+    if (last_s) d_finish(tb, sc, ws64);
 }
 
 // monotone revisions: one thread per delivery (suffix copy)
-__device__ __forceinline__ void d_expand_write(const TabDev &tb, const uint32_t *__restrict__ gbase,
-                                               const uint32_t *__restrict__ sorted, const uint64_t *__restrict__ wstart,
-                                               const uint32_t *__restrict__ wlo, uint64_t n_deliveries,
+__device__ __forceinline__ void d_expand_write(uint32_t n_ids, const uint32_t *__restrict__ wsrc,
+                                               const uint32_t *__restrict__ wlo, const uint32_t *__restrict__ sorted,
+                                               const uint64_t *__restrict__ wstart, uint64_t n_deliveries,
                                                uint32_t *__restrict__ out)
 {
     for (uint64_t d = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; d < n_deliveries;
          d += (uint64_t)gridDim.x * blockDim.x) {
-    uint32_t lo = 0, hi = tb.n_ids;  // last watcher with wstart[w] <= d
-    while (hi - lo > 1) {
-        const uint32_t mid = (lo + hi) >> 1;
-        if (wstart[mid] <= d) lo = mid; else hi = mid;
-    }
-    const uint32_t w = lo;
-    const uint32_t g = tb.wgroup[w];
-    out[d] = sorted[gbase[g] + wlo[w] + (uint32_t)(d - wstart[w])];
+        uint32_t lo = 0, hi = n_ids;  // last watcher with wstart[w] <= d
+        while (hi - lo > 1) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (wstart[mid] <= d) lo = mid; else hi = mid;
+        }
+        const uint32_t w = lo;
+        out[d] = sorted[wsrc[w] + wlo[w] + (uint32_t)(d - wstart[w])];
     }
 }
 
 // non-monotone revisions (general case): warp per watcher, ordered filtered copy
-__device__ __forceinline__ void d_expand_write_general(const TabDev &tb, const uint32_t *__restrict__ gcnt,
-                                                       const uint32_t *__restrict__ gbase,
+__device__ __forceinline__ void d_expand_write_general(uint32_t n_ids, const uint64_t *__restrict__ wminrev,
+                                                       const uint32_t *__restrict__ wsrc, const uint32_t *__restrict__ wn,
                                                        const uint32_t *__restrict__ sorted,
                                                        const uint64_t *__restrict__ pm,
                                                        const uint64_t *__restrict__ wstart, uint32_t *__restrict__ out)
 {
-    const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (w >= tb.n_ids) return;
-    const uint32_t g = tb.wgroup[w];
-    if (g == KB_NONE) return;
-    const uint32_t n = gcnt[g];
-    const uint32_t *M = sorted + gbase[g];
-    const uint64_t mr = tb.wminrev[w];
-    const uint64_t o = wstart[w];
-    uint64_t total = 0;
-    for (uint32_t c = 0; c < n; c += 32) {
-        const uint32_t j = c + lane;
-        const uint32_t e = j < n ? M[j] : 0;
-        const bool keep = j < n && pm[e] >= mr;
-        const unsigned m = __ballot_sync(FULL, keep);
-        if (keep) out[o + total + __popc(m & ((1u << lane) - 1))] = e;
-        total += __popc(m);
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < n_ids; w += warps) {
+        const uint32_t n = wn[w];
+        const uint32_t *M = sorted + wsrc[w];
+        const uint64_t mr = wminrev[w];
+        const uint64_t o = wstart[w];
+        uint64_t total = 0;
+        for (uint32_t c = 0; c < n; c += 32) {
+            const uint32_t j = c + lane;
+            const uint32_t e = j < n ? M[j] : 0;
+            const bool keep = j < n && pm[e] >= mr;
+            const unsigned m = __ballot_sync(FULL, keep);
+            if (keep) out[o + total + __popc(m & ((1u << lane) - 1))] = e;
+            total += __popc(m);
+        }
     }
 }
 
 // one launch for both output paths: revisions monotone -> one thread per delivery; otherwise warp per watcher
 __global__ void __launch_bounds__(256)
-k_expand_write(TabDev tb, const uint32_t *__restrict__ gcnt, const uint32_t *__restrict__ gbase,
-               const uint32_t *__restrict__ sorted, const uint64_t *__restrict__ pm,
-               const uint32_t *__restrict__ nonmono, const uint64_t *__restrict__ wstart,
-               const uint32_t *__restrict__ wlo, uint64_t capacity, uint32_t *__restrict__ out)
+k_expand_write(uint32_t n_ids, const uint64_t *__restrict__ wminrev, const uint32_t *__restrict__ wsrc,
+               const uint32_t *__restrict__ wn, const uint32_t *__restrict__ wlo, const uint32_t *__restrict__ sorted,
+               const uint64_t *__restrict__ pm, const uint64_t *__restrict__ total /* [0] deliveries [1] non-monotone */,
+               const uint64_t *__restrict__ wstart, uint64_t capacity, uint32_t *__restrict__ out)
 {
-    const uint64_t n_deliveries = wstart[tb.n_ids];
+    const uint64_t n_deliveries = wstart[n_ids];
     if (n_deliveries > capacity) return;  // the host sees the total, grows the buffer and launches again
-    if (*nonmono == 0)
-        d_expand_write(tb, gbase, sorted, wstart, wlo, n_deliveries, out);
+    if (total[1] == 0)
+        d_expand_write(n_ids, wsrc, wlo, sorted, wstart, n_deliveries, out);
     else
-        d_expand_write_general(tb, gcnt, gbase, sorted, pm, wstart, out);
+        d_expand_write_general(n_ids, wminrev, wsrc, wn, sorted, pm, wstart, out);
 }
 
 uint64_t fnv1a(const std::string &s)
@@ -581,59 +607,55 @@ int rebuild_tables(kb_ctx *ctx)
     WatchTablesDev &T = *ctx->wt;
     const uint32_t n_ids = (uint32_t)ctx->watchers.size();
     std::map<std::string, std::vector<uint32_t>> groups;  // ordered: deterministic group ids
+    uint32_t max_len = 0;
     for (uint32_t w = 0; w < n_ids; w++)
-        if (ctx->watchers[w].live) groups[ctx->watchers[w].prefix].push_back(w);
+        if (ctx->watchers[w].live) {
+            groups[ctx->watchers[w].prefix].push_back(w);
+            max_len = std::max<uint32_t>(max_len, (uint32_t)ctx->watchers[w].prefix.size());
+        }
     const uint32_t G = (uint32_t)groups.size();
-    std::vector<uint8_t> gprefix;
-    std::vector<uint32_t> goff16(G + 1), glen(G), gstart(G + 1), gmember, wgroup(std::max(n_ids, 1u), KB_NONE), lens;
+    // every prefix zero padded to the same stride, so an entry of the hash table (hash, length, group) is all a probe reads
+    // before the byte-exact verify
+    const uint32_t pstride16 = std::max<uint32_t>(1, (max_len + 15) / 16);
+    if ((uint64_t)G * pstride16 * 16 > (1ull << 32)) return kb_fail(ctx, KB_ELIMIT, "watch prefixes exceed 4 GiB");
+    std::vector<uint8_t> gprefix((size_t)std::max(G, 1u) * pstride16 * 16, 0);
+    std::vector<uint32_t> glen(G), wgroup(std::max(n_ids, 1u), KB_NONE), lens;
     std::vector<uint64_t> ghash(std::max(G, 1u)), wminrev(std::max(n_ids, 1u), 0);
-    uint32_t gi = 0, max_len = 0;
+    uint32_t gi = 0;
     for (auto &kv : groups) {
         const std::string &p = kv.first;
-        goff16[gi] = (uint32_t)(gprefix.size() / 16);
         glen[gi] = (uint32_t)p.size();
         ghash[gi] = fnv1a(p);
-        gprefix.insert(gprefix.end(), p.begin(), p.end());
-        gprefix.resize((gprefix.size() + 15) / 16 * 16 + 16, 0);
-        gstart[gi] = (uint32_t)gmember.size();
-        for (uint32_t w : kv.second) {
-            gmember.push_back(w);
-            wgroup[w] = gi;
-        }
+        if (!p.empty()) memcpy(gprefix.data() + (size_t)gi * pstride16 * 16, p.data(), p.size());
+        for (uint32_t w : kv.second) wgroup[w] = gi;
         lens.push_back((uint32_t)p.size());
-        max_len = std::max<uint32_t>(max_len, (uint32_t)p.size());
         gi++;
     }
-    goff16[G] = (uint32_t)(gprefix.size() / 16);
-    gstart[G] = (uint32_t)gmember.size();
     for (uint32_t w = 0; w < n_ids; w++) wminrev[w] = ctx->watchers[w].min_rev;
     std::sort(lens.begin(), lens.end());
     lens.erase(std::unique(lens.begin(), lens.end()), lens.end());
     uint32_t tsize = 16;
     while (tsize < 2 * G + 2) tsize <<= 1;
-    std::vector<uint32_t> table(tsize, KB_NONE);
+    std::vector<uint4> table(tsize, make_uint4(0, 0, 0, KB_NONE));
     for (uint32_t g = 0; g < G; g++) {
         uint32_t s = slot_of(ghash[g], glen[g], tsize - 1);
-        while (table[s] != KB_NONE) s = (s + 1) & (tsize - 1);
-        table[s] = g;
+        while (table[s].w != KB_NONE) s = (s + 1) & (tsize - 1);
+        table[s] = make_uint4((uint32_t)ghash[g], (uint32_t)(ghash[g] >> 32), glen[g], g);
     }
-    if (gprefix.empty()) gprefix.resize(16, 0);
+    if (lens.empty()) lens.push_back(0);
     KB_TRY(upload(ctx, T.gprefix, gprefix.data(), gprefix.size()));
-    KB_TRY(upload(ctx, T.goff16, goff16.data(), goff16.size() * 4));
-    KB_TRY(upload(ctx, T.glen, glen.data(), glen.size() * 4));
-    KB_TRY(upload(ctx, T.ghash, ghash.data(), ghash.size() * 8));
-    KB_TRY(upload(ctx, T.gstart, gstart.data(), gstart.size() * 4));
-    KB_TRY(upload(ctx, T.gmember, gmember.data(), gmember.size() * 4));
     KB_TRY(upload(ctx, T.wgroup, wgroup.data(), wgroup.size() * 4));
     KB_TRY(upload(ctx, T.wminrev, wminrev.data(), wminrev.size() * 8));
     KB_TRY(upload(ctx, T.lens, lens.data(), lens.size() * 4));
-    KB_TRY(upload(ctx, T.table, table.data(), table.size() * 4));
+    KB_TRY(upload(ctx, T.table, table.data(), table.size() * 16));
     KB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // the host vectors die here
     T.n_ids = n_ids;
     T.n_groups = G;
-    T.n_lens = (uint32_t)lens.size();
+    T.n_lens = G ? (uint32_t)lens.size() : 0;
     T.table_size = tsize;
     T.max_len = max_len;
+    T.pstride16 = pstride16;
+    T.scratch_clean = false;  // the group count changed: the scratch is laid out again
     ctx->watch_dirty = false;
     return KB_OK;
 }
@@ -708,9 +730,8 @@ void watch_tables_free(kb_ctx *ctx)
 {
     if (!ctx->wt) return;
     WatchTablesDev &T = *ctx->wt;
-    DBuf *all[] = {&T.gprefix, &T.goff16, &T.glen, &T.ghash, &T.gstart, &T.gmember, &T.wgroup, &T.wminrev,
-                   &T.lens, &T.table, &T.zeros, &T.gbase, &T.gclass, &T.ematch, &T.seg, &T.seg_sorted, &T.bitmaps, &T.wlo, &T.pm,
-                   &T.wcnt, &T.wstart, &T.total};
+    DBuf *all[] = {&T.gprefix, &T.wgroup, &T.wminrev, &T.lens, &T.table, &T.gstate, &T.galloc, &T.lists, &T.ematch, &T.seg,
+                   &T.seg_sorted, &T.bitmaps, &T.pm, &T.wstate, &T.wstart, &T.total};
     for (DBuf *b : all)
         if (b->p) cudaFree(b->p);
     delete ctx->wt;
@@ -834,16 +855,24 @@ static int match_locked(kb_ctx *ctx, const kb_events_dev *d, int out_mode, kb_re
     const uint32_t max_large = (uint32_t)(seg_cap / big_t) + 1;
     const uint32_t bm_words = (E + 31) / 32;
     const uint32_t chunks_per_group = (bm_words + 255) / 256;
-    KB_TRY(dbuf_ensure(ctx, T.zeros, (size_t)(4 + 2 * (G + 1) + 2 * G + 8) * 4));
-    KB_TRY(dbuf_ensure(ctx, T.gbase, (size_t)(G + 1) * 4));
-    KB_TRY(dbuf_ensure(ctx, T.gclass, (size_t)(G + 1) * 4));
+    const size_t gstate_words = (size_t)2 * (G + 1) + FC_WORDS;
+    const size_t bitmap_bytes = std::max<size_t>((size_t)max_large * bm_words * 4, 16);
+    // growing a buffer frees the old one: the "clean" state of the scratch is lost with it
+    auto ensure = [&](DBuf &b, size_t bytes) -> int {
+        const void *before = b.p;
+        KB_TRY(dbuf_ensure(ctx, b, bytes));
+        if (b.p != before) T.scratch_clean = false;
+        return KB_OK;
+    };
+    KB_TRY(ensure(T.gstate, gstate_words * 4));
+    KB_TRY(ensure(T.galloc, (size_t)(G + 1) * 8));
+    KB_TRY(ensure(T.bitmaps, bitmap_bytes));
+    KB_TRY(dbuf_ensure(ctx, T.lists, (size_t)(G + max_large + 2) * 4));
     KB_TRY(dbuf_ensure(ctx, T.ematch, seg_cap * 4));
     KB_TRY(dbuf_ensure(ctx, T.seg, seg_cap * 4));
     KB_TRY(dbuf_ensure(ctx, T.seg_sorted, seg_cap * 4));
-    KB_TRY(dbuf_ensure(ctx, T.bitmaps, std::max<size_t>((size_t)max_large * bm_words * 4, 16)));
     KB_TRY(dbuf_ensure(ctx, T.pm, std::max<size_t>((size_t)E * 8, 16)));
-    KB_TRY(dbuf_ensure(ctx, T.wcnt, (size_t)(W + 1) * 8));
-    KB_TRY(dbuf_ensure(ctx, T.wlo, (size_t)(W + 1) * 4));
+    KB_TRY(dbuf_ensure(ctx, T.wstate, (size_t)(W + 1) * 16));
     KB_TRY(dbuf_ensure(ctx, T.wstart, (size_t)(W + 2) * 8));
     KB_TRY(dbuf_ensure(ctx, T.total, 16));
 
@@ -857,63 +886,71 @@ static int match_locked(kb_ctx *ctx, const kb_events_dev *d, int out_mode, kb_re
     ev.stride16 = d->stride / 16;
     TabDev tb;
     tb.gprefix = (const uint4 *)T.gprefix.p;
-    tb.goff16 = (const uint32_t *)T.goff16.p;
-    tb.glen = (const uint32_t *)T.glen.p;
-    tb.ghash = (const uint64_t *)T.ghash.p;
-    tb.gstart = (const uint32_t *)T.gstart.p;
-    tb.gmember = (const uint32_t *)T.gmember.p;
     tb.wgroup = (const uint32_t *)T.wgroup.p;
     tb.wminrev = (const uint64_t *)T.wminrev.p;
     tb.lens = (const uint32_t *)T.lens.p;
-    tb.table = (const uint32_t *)T.table.p;
+    tb.table = (const uint4 *)T.table.p;
     tb.n_ids = W;
     tb.n_groups = G;
     tb.n_lens = T.n_lens;
     tb.mask = T.table_size - 1;
     tb.max_len = T.max_len;
+    tb.pstride16 = T.pstride16;
+    FanScratch sc;
+    sc.gcnt = (uint32_t *)T.gstate.p;
+    sc.gfill = sc.gcnt + (G + 1);
+    sc.ctl = sc.gcnt + 2 * (G + 1);
+    sc.galloc = (unsigned long long *)T.galloc.p;
+    sc.med_list = (uint32_t *)T.lists.p;
+    sc.large_list = sc.med_list + G + 1;
+    sc.ematch = (uint32_t *)T.ematch.p;
+    sc.seg = (uint32_t *)T.seg.p;
+    sc.sorted = (uint32_t *)T.seg_sorted.p;
+    sc.bitmaps = (uint32_t *)T.bitmaps.p;
+    sc.pm = (uint64_t *)T.pm.p;
+    sc.wcnt = (uint32_t *)T.wstate.p;
+    sc.wsrc = sc.wcnt + (W + 1);
+    sc.wn = sc.wsrc + (W + 1);
+    sc.wlo = sc.wn + (W + 1);
+    sc.wstart = (uint64_t *)T.wstart.p;
+    sc.total = (uint64_t *)T.total.p;
+    sc.big_t = big_t;
+    sc.max_large = max_large;
+    sc.bm_words = bm_words;
+    sc.chunks_per_group = chunks_per_group;
 
-    // zeroed region: [flag x4][gcnt G+1][gfill G+1][lists 2G+4]
-    const size_t zero_bytes = (size_t)(4 + 2 * (G + 1) + 2) * 4;
-    uint32_t *zr = (uint32_t *)T.zeros.p;
-    uint32_t *gcnt = zr + 4, *gfill = zr + 4 + (G + 1), *lists = zr + 4 + 2 * (G + 1);
-    uint32_t *gbase = (uint32_t *)T.gbase.p;
-    uint32_t *gclass = (uint32_t *)T.gclass.p, *ematch = (uint32_t *)T.ematch.p;
-    uint32_t *seg = (uint32_t *)T.seg.p, *sorted = (uint32_t *)T.seg_sorted.p, *bitmaps = (uint32_t *)T.bitmaps.p;
-    uint64_t *pm = (uint64_t *)T.pm.p;
-    uint32_t *flag = zr, *wlo = (uint32_t *)T.wlo.p;
-    uint64_t *wcnt = (uint64_t *)T.wcnt.p, *wstart = (uint64_t *)T.wstart.p, *total = (uint64_t *)T.total.p;
-
-    // gcnt | gfill | lists header | flag live in one zeroed region (one memset per call)
-    KB_CUDA(ctx, cudaMemsetAsync(T.zeros.p, 0, zero_bytes, ctx->stream));
+    // The kernel leaves gcnt / gfill / ctl / galloc / the bitmaps it used in their initial state; they are only set from
+    // the host after a table rebuild, a reallocation, a failed call, or when the geometry of the bitmaps changed.
+    if (!T.scratch_clean || T.scratch_groups != G || T.scratch_large != max_large || T.scratch_bm_words != bm_words) {
+        KB_CUDA(ctx, cudaMemsetAsync(T.gstate.p, 0, gstate_words * 4, ctx->stream));
+        KB_CUDA(ctx, cudaMemsetAsync(T.galloc.p, 0xFF, (size_t)(G + 1) * 8, ctx->stream));
+        KB_CUDA(ctx, cudaMemsetAsync(T.bitmaps.p, 0, bitmap_bytes, ctx->stream));
+        T.fan_gen = 0;
+        T.scratch_groups = G;
+        T.scratch_large = max_large;
+        T.scratch_bm_words = bm_words;
+    }
+    T.scratch_clean = false;  // until this call has been enqueued completely
     const uint64_t ev_bytes = (uint64_t)E * (d->stride + 4);
-    const bool work = E && W && G;
     if (E && W) {
-        const uint32_t pm_blocks = (d->nb * 32 + 255) / 256;
-        KB_LAUNCH(ctx, "k_match_count", ev_bytes + (uint64_t)E * NL * 4 + (uint64_t)E * 16,
-                  (k_match_count<<<pm_blocks + (G ? (E + 255) / 256 : 0), 256, 0, ctx->stream>>>(ev, tb, pm_blocks, pm,
-                                                                                            flag, ematch, gcnt)));
+        if (!T.fan_grid) {
+            int per_sm = 0, sms = 0;
+            KB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fanout, (int)FAN_THREADS, 0));
+            KB_CUDA(ctx, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
+            if (per_sm < 1) return kb_fail(ctx, KB_ECUDA, "k_fanout does not fit on an SM");
+            T.fan_grid = sms * std::min(per_sm, 2);
+        }
+        sc.gen_base = T.fan_gen;
+        void *args[] = {(void *)&ev, (void *)&tb, (void *)&sc};
+        KB_LAUNCH(ctx, "k_fanout", ev_bytes + (uint64_t)E * NL * 12 + (uint64_t)E * 16 + (uint64_t)W * 44,
+                  KB_CUDA(ctx, cudaLaunchCooperativeKernel((const void *)k_fanout, dim3((unsigned)T.fan_grid), dim3(FAN_THREADS),
+                                                          args, 0, ctx->stream)));
+        T.fan_gen += 3;  // three grid barriers per launch
+    } else {
+        // no events or no watchers: every list is empty
+        KB_CUDA(ctx, cudaMemsetAsync(T.wstart.p, 0, (size_t)(W + 2) * 8, ctx->stream));
+        KB_CUDA(ctx, cudaMemsetAsync(T.total.p, 0, 16, ctx->stream));
     }
-    if (work) {
-        KB_CUDA(ctx, cudaMemsetAsync(bitmaps, 0, (size_t)max_large * bm_words * 4, ctx->stream));
-        KB_LAUNCH(ctx, "k_group_scan_classify", (uint64_t)G * 12,
-                  (k_group_scan_classify<<<1, 1024, 0, ctx->stream>>>(G, gcnt, big_t, max_large, gbase, gclass, lists)));
-        KB_LAUNCH(ctx, "k_scatter", (uint64_t)E * NL * 8,
-                  (k_scatter<<<(E + 255) / 256, 256, 0, ctx->stream>>>(E, T.n_lens, ematch, gclass, gbase, gfill, seg,
-                                                                     bitmaps, bm_words)));
-        const uint32_t nb_small = (G * 32 + 255) / 256, nb_med = 148 * 2;
-        const uint32_t nb_large = std::min<uint32_t>(148 * 4, max_large * chunks_per_group);
-        KB_LAUNCH(ctx, "k_sort", (uint64_t)E * NL * 8,
-                  (k_sort<<<nb_small + nb_med + nb_large, 256, 0, ctx->stream>>>(G, gcnt, gbase, seg, sorted, lists, bitmaps,
-                                                                               bm_words, chunks_per_group, nb_small,
-                                                                               nb_med)));
-    }
-    if (W) {
-        KB_LAUNCH(ctx, "k_expand_count", (uint64_t)W * 24,
-                  (k_expand_count<<<(W * 32 + 255) / 256, 256, 0, ctx->stream>>>(tb, gcnt, gbase, sorted, pm, flag, wcnt,
-                                                                              wlo)));
-    }
-    KB_LAUNCH(ctx, "k_watcher_scan", (uint64_t)W * 16,
-              (k_watcher_scan<<<1, 1024, 0, ctx->stream>>>(W, wcnt, wstart, total)));
     // Output [start (W+1) x u64][event_idx D x u32].  D is only known on the device; the buffer is sized from the
     // previous call's D (+25 %) and the write kernel refuses to run when it would not fit, so the steady state needs
     // no round trip before the write.
@@ -932,20 +969,20 @@ static int match_locked(kb_ctx *ctx, const kb_events_dev *d, int out_mode, kb_re
         KB_TRY(pool_get_dev(ctx, out_bytes, &d_out));
         uint64_t *o_start = (uint64_t *)d_out.p;
         uint32_t *o_idx = (uint32_t *)(o_start + W + 1);
-        cudaMemcpyAsync(o_start, wstart, (size_t)(W + 1) * 8, cudaMemcpyDeviceToDevice, ctx->stream);
+        cudaMemcpyAsync(o_start, sc.wstart, (size_t)(W + 1) * 8, cudaMemcpyDeviceToDevice, ctx->stream);
         uint64_t wepoch = 0;
         if (out_mode != KB_OUT_HOST) {
             if (!h_out.p) KB_TRY(pool_get_host(ctx, (size_t)(W + 1) * 8 + 16, &h_out));
-            cudaMemcpyAsync(h_out.p, wstart, (size_t)(W + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream);
+            cudaMemcpyAsync(h_out.p, sc.wstart, (size_t)(W + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream);
             wepoch = ++ctx->wpub_epoch;
-            k_publish_total<<<1, 32, 0, ctx->stream>>>(total, ctx->h_wpub, wepoch);
+            k_publish_total<<<1, 32, 0, ctx->stream>>>(sc.total, ctx->h_wpub, wepoch);
         }
-        if (W) {
+        if (W && E) {
             const unsigned wgrid = (unsigned)std::max<uint64_t>(std::min<uint64_t>((cap + 255) / 256, 148 * 16),
-                                                                ((uint64_t)W * 32 + 255) / 256);
+                                                                std::min<uint64_t>(((uint64_t)W * 32 + 255) / 256, 148 * 16));
             KB_LAUNCH(ctx, "k_expand_write", cap * 8,
-                      (k_expand_write<<<wgrid, 256, 0, ctx->stream>>>(tb, gcnt, gbase, sorted, pm, flag, wstart, wlo, cap,
-                                                                     o_idx)));
+                      (k_expand_write<<<wgrid, 256, 0, ctx->stream>>>(W, tb.wminrev, sc.wsrc, sc.wn, sc.wlo, sc.sorted, sc.pm,
+                                                                     sc.total, sc.wstart, cap, o_idx)));
         }
         cudaError_t e0 = cudaSuccess;
         if (out_mode != KB_OUT_HOST) {
@@ -961,7 +998,7 @@ static int match_locked(kb_ctx *ctx, const kb_events_dev *d, int out_mode, kb_re
             }
             D = ctx->h_wpub[1];
         } else {
-            KB_CUDA(ctx, cudaMemcpyAsync(ctx->h_stage2.p, total, 8, cudaMemcpyDeviceToHost, ctx->stream));
+            KB_CUDA(ctx, cudaMemcpyAsync(ctx->h_stage2.p, sc.total, 8, cudaMemcpyDeviceToHost, ctx->stream));
             kb_seg(ctx, "host:match_launch", tseg);
             e0 = cudaStreamSynchronize(ctx->stream);
             kb_seg(ctx, "host:match_sync", tseg);
@@ -977,6 +1014,7 @@ static int match_locked(kb_ctx *ctx, const kb_events_dev *d, int out_mode, kb_re
         d_out = DBuf();
         cap = D;
     }
+    T.scratch_clean = true;  // everything was enqueued: k_fanout restores the scratch before it ends
     if (out_mode == KB_OUT_HOST) {
         rc = pool_get_host(ctx, (size_t)(W + 1) * 8 + D * 4 + 16, &h_out);
         if (rc == KB_OK)
@@ -986,6 +1024,7 @@ static int match_locked(kb_ctx *ctx, const kb_events_dev *d, int out_mode, kb_re
         if (rc == KB_OK && e != cudaSuccess) rc = kb_cuda_fail(ctx, e, "watch match");
     }
     if (rc != KB_OK) {
+        T.scratch_clean = false;
         pool_put_dev(ctx, d_out);
         pool_put_host(ctx, h_out);
         return rc;

@@ -12,16 +12,31 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box via gpurun)")
 
 
-@pytest.fixture(scope="session")
-def have_gpu():
+def _gpu_count() -> int:
     try:
         import ctypes
 
         cuda = ctypes.CDLL("libcuda.so.1")
         n = ctypes.c_int(0)
         if cuda.cuInit(0) != 0:
-            return False
+            return 0
         cuda.cuDeviceGetCount(ctypes.byref(n))
-        return n.value > 0
+        return n.value
     except OSError:
-        return False
+        return 0
+
+
+def pytest_collection_modifyitems(config, items):
+    """tests marked `gpu` are skipped (not failed) on a host without a CUDA device, so a plain `pytest tests`
+    is green on a CPU-only machine; the product itself still refuses to run there (kb_open -> KB_ECUDA)."""
+    if _gpu_count() > 0:
+        return
+    skip = pytest.mark.skip(reason="no CUDA device on this host (GPU tests run on the B200 box)")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
+@pytest.fixture(scope="session")
+def have_gpu():
+    return _gpu_count() > 0

@@ -400,7 +400,7 @@ def test_config1_natural_keys(eng):
 
 def test_config2_full_size_1m(eng):
     """BASELINE config 2 at full size: 1M records, 256 B keys, 2 KB values.  The C oracle scans 1M records in well
-    under a second, so the comparison is direct; value bytes are compared through a digest of the whole arena."""
+    under a second, so the comparison is direct; ALL key / value / revision bytes of every emitted kv are compared."""
     store, meta = synth.gen_store(200000, 4, 256, 2048, 1000, config_id=2)
     st = ko.OracleStore(store)
     eng.load_sorted(store)
@@ -412,23 +412,23 @@ def test_config2_full_size_1m(eng):
         exp = ko.range_(st, s, e, rev, lim)
         assert res.rec_indices(q).astype(np.uint64).tolist() == exp.emit.tolist(), q
         assert int(res.req_examined[q]) == exp.examined
-    # every emitted kv: key/value/revision bytes equal to the store record that the oracle selected
-    koff, voff = store.keys.off, store.vals.off
-    for q in (0, 1, 5):
-        a, b = int(res.req_first[q]), int(res.req_first[q + 1])
-        idx = res.rec_idx[a:b].astype(np.int64)
-        h_got, h_exp = hashlib.sha256(), hashlib.sha256()
-        for k in range(a, b, max(1, (b - a) // 2000)):  # a strided sample of up to ~2000 kvs, all bytes of each
-            i = int(res.rec_idx[k])
-            h_got.update(res.arena[int(res.key_off[k]) : int(res.key_off[k]) + int(res.key_len[k])].tobytes())
-            h_got.update(res.arena[int(res.val_off[k]) : int(res.val_off[k]) + int(res.val_len[k])].tobytes())
-            h_exp.update(store.keys.data[int(koff[i]) + 4 : int(koff[i + 1]) - 9].tobytes())
-            h_exp.update(store.vals.data[int(voff[i]) : int(voff[i + 1])].tobytes())
-        assert h_got.digest() == h_exp.digest(), q
-        # revisions of ALL kvs
-        krev = np.array([struct.unpack(">Q", store.keys.data[int(koff[i + 1]) - 8 : int(koff[i + 1])].tobytes())[0]
-                         for i in idx[:: max(1, len(idx) // 5000)]], dtype=np.uint64)
-        assert (res.rev[a:b][:: max(1, len(idx) // 5000)] == krev).all()
+    # EVERY emitted kv of EVERY request: user-key, value and revision bytes equal to the store record the oracle
+    # selected.  The synthetic's emitted records all have Lk = 269 / Lv = 2048 (tombstones are never emitted), so the
+    # comparison is one vectorised gather per side instead of 200k Python slices.
+    koff, voff = store.keys.off.astype(np.int64), store.vals.off.astype(np.int64)
+    idx = res.rec_idx.astype(np.int64)
+    assert (res.key_len == 256).all() and (res.val_len == 2048).all()
+    assert ((koff[idx + 1] - koff[idx]) == 269).all() and ((voff[idx + 1] - voff[idx]) == 2048).all()
+    for a in range(0, len(idx), 4096):  # chunks bound the temporary index matrices to ~70 MB
+        sl = slice(a, min(a + 4096, len(idx)))
+        got_k = res.arena[res.key_off[sl].astype(np.int64)[:, None] + np.arange(256)]
+        exp_k = store.keys.data[koff[idx[sl]][:, None] + 4 + np.arange(256)]
+        assert np.array_equal(got_k, exp_k), ("user key bytes", a)
+        got_v = res.arena[res.val_off[sl].astype(np.int64)[:, None] + np.arange(2048)]
+        exp_v = store.vals.data[voff[idx[sl]][:, None] + np.arange(2048)]
+        assert np.array_equal(got_v, exp_v), ("value bytes", a)
+        exp_r = store.keys.data[koff[idx[sl]][:, None] + 261 + np.arange(8)].copy().view(">u8").reshape(-1)
+        assert np.array_equal(res.rev[sl], exp_r.astype(np.uint64)), ("revisions", a)
     # size-independent properties: emitted keys strictly ascending, one per object, none above read_rev
     a, b = int(res.req_first[0]), int(res.req_first[1])
     assert (np.diff(res.rec_idx[a:b].astype(np.int64)) > 0).all()
@@ -534,10 +534,21 @@ def test_config4_shape_10m(eng):
     res.close()
 
 
-@pytest.mark.skipif(os.environ.get("KB_FULL_SIZE") != "1", reason="set KB_FULL_SIZE=1 (needs ~40 GB of host RAM, minutes)")
+def _host_ram_gb() -> float:
+    try:
+        import psutil
+
+        return psutil.virtual_memory().available / 2**30
+    except Exception:
+        return 0.0
+
+
 def test_config4_full_size_100m():
-    """BASELINE config 4 at FULL size: 10M objects x (1 revision record + 9 versions) = 100M records.  Too large for
-    a direct list comparison in reasonable time, so: counts against the oracle + size-independent properties."""
+    """BASELINE config 4 at FULL size: 10M objects x (1 revision record + 9 versions) = 100M records, the ordered
+    victim list (80M+ delete calls with classes) compared element-wise with the oracle, plus the keep-latest
+    property.  ~40 s on the B200 box; skipped only when the host cannot hold the 16 GB synthetic twice."""
+    if _host_ram_gb() < 48:
+        pytest.skip("host has less than 48 GB of free RAM")
     store, meta = synth.gen_store(10_000_000, 9, 64, 64, 50000, config_id=4, tomb_frac=0.02)
     e = Engine(0)
     e.load_sorted(store)
