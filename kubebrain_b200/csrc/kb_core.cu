@@ -407,9 +407,10 @@ extern "C" int kb_load_sorted(kb_ctx *ctx, const uint8_t *keys, const uint64_t *
     std::vector<uint16_t> klen(n ? n : 1);
     std::vector<uint64_t> voff16(n + 1);
     std::vector<uint32_t> vlen(n ? n : 1);
-    uint64_t kacc = 0, vacc = 0, max_kv = 0;
+    uint64_t kacc = 0, vacc = 0, max_kv = 0, max_k = 0;
     for (uint64_t i = 0; i < n; i++) {
         uint64_t kl = key_off[i + 1] - key_off[i], vl = val_off[i + 1] - val_off[i];
+        max_k = std::max<uint64_t>(max_k, (kl + 15) / 16);
         if (kl > 65535) return kb_fail(ctx, KB_ELIMIT, "key %llu longer than 65535 bytes", (unsigned long long)i);
         if (vl > 0xFFFFFFFFull) return kb_fail(ctx, KB_ELIMIT, "value %llu too long", (unsigned long long)i);
         koff16[i] = (uint32_t)kacc;
@@ -426,6 +427,7 @@ extern "C" int kb_load_sorted(kb_ctx *ctx, const uint8_t *keys, const uint64_t *
     ctx->key_bytes = kacc * 16;
     ctx->val_bytes = vacc * 16;
     ctx->max_kv_chunks = (uint32_t)std::min<uint64_t>(max_kv, 0xFFFFFFFFu);
+    ctx->max_key_chunks = (uint32_t)max_k;
 
     KB_TRY(dbuf_ensure(ctx, ctx->d_kslab, kacc * 16 + 64));
     KB_TRY(dbuf_ensure(ctx, ctx->d_vslab, vacc * 16 + 16));
@@ -673,9 +675,10 @@ extern "C" int kb_restore(kb_ctx *ctx, const char *path)
     if (hd != h.sum_dir) return kb_fail(ctx, KB_EINVAL, "restore: directory checksum mismatch");
     // the directory must describe exactly the slabs that follow: monotone offsets, every record inside its slab
     if (koff16[0] != 0 || voff16[0] != 0 || koff16[n] != h.key_chunks || voff16[n] != h.val_chunks) ok = false;
-    uint64_t max_kv = 0;
+    uint64_t max_kv = 0, max_k = 0;
     for (uint64_t i = 0; ok && i < n; i++) {
         const uint64_t nk = ((uint32_t)klen[i] + 15) / 16, nv = ((uint64_t)vlen[i] + 15) / 16;
+        max_k = std::max(max_k, nk);
         if (koff16[i + 1] < koff16[i] || koff16[i + 1] - koff16[i] != nk) ok = false;
         if (voff16[i + 1] < voff16[i] || voff16[i + 1] - voff16[i] != nv) ok = false;
         max_kv = std::max(max_kv, nk + nv);
@@ -724,6 +727,7 @@ extern "C" int kb_restore(kb_ctx *ctx, const char *path)
     ctx->key_bytes = h.key_chunks * 16;
     ctx->val_bytes = h.val_chunks * 16;
     ctx->max_kv_chunks = (uint32_t)std::min<uint64_t>(max_kv, 0xFFFFFFFFu);
+    ctx->max_key_chunks = (uint32_t)max_k;
     ctx->compact_present = h.compact_present != 0;
     ctx->compact_rev = h.compact_rev;
     ctx->loaded = true;

@@ -1,19 +1,25 @@
 // kb_decode.cuh -- k_decode_lcp: the HBM-bound pass of the scan (included by kb_scan.cu).
 //
-// Streams the raw internal keys of every examined record once (one bulk-TMA copy per 32-record sub-tile into a
-// per-warp shared-memory ring, two stages deep so the next sub-tile is in flight while the current one is decoded),
-// and reduces each record to one 32-bit meta word:
+// Streams the raw internal keys of every examined record once and reduces each record to one 32-bit meta word:
 //   bits 0..15  LCP with the preceding key (common-prefix length, the input of the "same user key" test)
 //   bits 16..23 decode / visibility / tombstone / compaction-class flags (KB_M_*)
-// plus one (last PREVOK slot, min LCP after it) aggregate per 32-record sub-tile for the cross-tile carry.
 //
 // Replaces coder.Decode (pkg/backend/coder/normal.go:58-70) and the per-record front half of worker.run
 // (pkg/backend/scanner/scanner.go:430-453, 471-491, 566-591): decode, TTL expiry, revision visibility,
 // tombstone test, deleted-flag revision-record test.  Warps are persistent and fully independent (no CTA barrier).
 //
-// Per-warp software pipeline (every stage one iteration apart, so no load is waited for in the iteration that
-// issues it):   tile descriptor -> record directory (koff16/klen/vlen/voff16) -> key bytes (cp.async.bulk, completion
-// on an mbarrier) + 16-byte value probe of 9-byte values -> decode.
+// Round 2 layout of the per-warp pipeline.  Round 1 prefetched each lane's packed directory entry, the work ticket and
+// the tile descriptor ONE step ahead into registers; ncu showed every step waiting for exactly those loads
+// (long_scoreboard 43 % at their first use, 101 registers, 12 warps / SM).  Now nothing a step needs arrives through
+// a register-held global load issued less than a block (four steps) earlier:
+//   * work is handed out in BLOCKS of four steps; the ticket (one atomic) for block n+3 and the tile descriptor of block
+//     n+2 are requested when block n starts;
+//   * a step's packed directory entries (16 B per record, plus the record in front of it) are bulk-copied (TMA) into a
+//     three-slot shared-memory ring TWO steps ahead; its key bytes into a two-slot ring ONE step ahead, the copy's extent
+//     read from the directory entries that have just landed; the value probes of 9-byte values (tombstone literal /
+//     deleted-flag revision record) are issued from the same entries one step ahead;
+//   * a step covers K consecutive 32-record sub-tiles of one tile (K chosen per launch from the store's longest key so
+//     that a step always moves ~9 KB: K = 1 at Lk = 269, K = 3 at Lk = 77), each lane looping over its K records.
 #pragma once
 
 #include "kb_internal.cuh"
@@ -21,34 +27,51 @@
 namespace {
 
 constexpr uint32_t MAGIC_LE = 0x8b80fb57u;  // bytes 57 fb 80 8b (coder/normal.go:26)
-constexpr int DECODE_WARPS = 12;
-constexpr int DECODE_STAGES = 2;
+constexpr int DECODE_MAX_K = 4;             // sub-tiles (of 32 records) per step
+constexpr uint32_t DECODE_HDR_CHUNKS = 2;   // per directory slot: the step descriptor (32 bytes)
 
 __device__ __forceinline__ uint32_t bswap32(uint32_t x) { return __byte_perm(x, 0, 0x0123); }
 
-// ---- bulk (TMA) copy + mbarrier helpers: one instruction moves a whole sub-tile's key bytes into shared memory
+// ---- bulk (TMA) copy + mbarrier helpers
 __device__ __forceinline__ uint32_t dsmem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void dmbar_init(uint64_t *bar)
 {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(dsmem_u32(bar)));
 }
-__device__ __forceinline__ void dmbar_wait(uint64_t *bar, uint32_t parity)
+// Bounded wait (a bulk copy that faults never completes its barrier): gives up after ~2 s of polling and raises the
+// context's error flag instead of hanging the stream; the results of that launch are then garbage and the host fails
+// the call (kb_range_batch / kb_compact_sweep check the flag).
+__device__ __forceinline__ bool dmbar_wait(uint64_t *bar, uint32_t parity, unsigned int *err_flag)
 {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "KBD_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra KBD_DONE;\n"
-        "bra KBD_WAIT;\n"
-        "KBD_DONE:\n"
-        "}\n" ::"r"(dsmem_u32(bar)),
-        "r"(parity)
-        : "memory");
+    uint32_t done = 0;
+    for (uint32_t spins = 0; spins < (1u << 26); spins++) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(dsmem_u32(bar)), "r"(parity)
+            : "memory");
+        if (done) return true;
+    }
+    atomicExch(err_flag, 1u);
+    return false;
+}
+__device__ __forceinline__ void dbulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dsmem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(dsmem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void dmbar_expect(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(dsmem_u32(bar)), "r"(bytes) : "memory");
 }
 
 // one plain atomic by the calling lane.  Written in PTX because nvcc turns `if (lane == 0) atomicAdd(...)` into its
-// warp-aggregated form, whose result broadcast (SHFL) waits for the atomic at once and defeats issuing it a step early.
+// warp-aggregated form, whose result broadcast (SHFL) waits for the atomic at once and defeats issuing it early.
 __device__ __forceinline__ uint32_t atom_add_u32_raw(unsigned int *p, uint32_t v)
 {
     uint32_t r;
@@ -66,116 +89,13 @@ __device__ __forceinline__ bool contains_events(const uint8_t *uk, uint32_t n)  
     return false;
 }
 
-// pipeline stage 0: the tile a sub-tile belongs to
-struct TileRef {
-    uint32_t valid, sid;
-    TileDev t;
-};
-
-__device__ __forceinline__ TileRef fetch_tile(const TileDev *__restrict__ tiles, uint32_t sid, uint32_t n_sub)
-{
-    TileRef r;
-    r.valid = sid < n_sub;
-    r.sid = sid;
-    if (r.valid) {
-        const uint4 *p = (const uint4 *)(tiles + (sid >> 5));
-        const uint4 a = __ldg(p), b = __ldg(p + 1);
-        r.t.req = a.x;
-        r.t.rec0 = a.y;
-        r.t.n = a.z;
-        r.t.flat0 = a.w;
-        r.t.lo = b.x;
-        r.t.pad = b.y;
-        r.t.read_rev = ((uint64_t)b.w << 32) | b.z;
-    } else {
-        r.t.req = r.t.rec0 = r.t.n = r.t.flat0 = r.t.lo = r.t.pad = 0;
-        r.t.read_rev = 0;
-    }
-    return r;
-}
-
-// everything a warp needs to know about one 32-record sub-tile
-struct SubDesc {
-    uint32_t valid;     // sub-tile exists
-    uint32_t sid;       // flat sub-tile id (= flat slot / 32)
-    uint32_t r0, nrec;  // first record, records in the sub-tile (0 for padding sub-tiles)
-    uint32_t lo;        // first record of the request (the LCP of that record is never used)
-    uint64_t read_rev;
-    // per lane (stage 1)
-    uint32_t ko, kl, vl;  // koff16[r], klen[r], vlen[r]
-    uint64_t vo;          // voff16[r]
-    uint32_t pko, pkl;    // lane 0 only: koff16[r0-1], klen[r0-1] when r0 > lo
-    // stage 2
-    uint32_t base16, span;  // staged chunk interval [base16, base16+span)
-    uint4 v0;               // first 16 bytes of the value when it has to be inspected
-};
-
-// pipeline stage 1: the record directory of the sub-tile (all loads independent of each other)
-__device__ __forceinline__ SubDesc load_desc(const StoreDev &st, const TileRef &tr, uint32_t lane)
-{
-    SubDesc d;
-    d.valid = tr.valid;
-    d.sid = tr.sid;
-    d.r0 = d.nrec = d.lo = 0;
-    d.read_rev = 0;
-    d.ko = d.kl = d.vl = d.pko = d.pkl = 0;
-    d.vo = 0;
-    d.base16 = d.span = 0;
-    d.v0 = make_uint4(0, 0, 0, 0);
-    if (!d.valid) return d;
-    const uint32_t sub = tr.sid & 31;
-    if (sub * 32 >= tr.t.n) return d;  // padding sub-tile of the request's last tile
-    d.r0 = tr.t.rec0 + sub * 32;
-    d.nrec = min(32u, tr.t.n - sub * 32);
-    d.lo = tr.t.lo;
-    d.read_rev = tr.t.read_rev;
-    // one 16-byte packed directory entry per record (a single long-latency load per lane, see StoreDev::dir)
-    if (lane < d.nrec) {
-        const uint4 e = __ldg(st.dir + d.r0 + lane);
-        d.ko = e.x;
-        d.kl = e.y & 0xffffu;
-        d.vl = e.z;
-        d.vo = ((uint64_t)(e.y >> 16) << 32) | e.w;
-    }
-    if (lane == 0 && d.r0 > d.lo) {
-        const uint4 e = __ldg(st.dir + d.r0 - 1);
-        d.pko = e.x;
-        d.pkl = e.y & 0xffffu;
-    }
-    return d;
-}
-
-// pipeline stage 2: start the asynchronous copy of the sub-tile's key bytes (plus the record before it) into `buf`
-// and the value probe of the 9-byte values (tombstone literal / deleted-flag revision record)
-__device__ __forceinline__ void issue_stage(const StoreDev &st, const ScanMode &mode, SubDesc &d, uint4 *buf,
-                                            uint64_t *bar, uint32_t lane)
-{
-    if (!d.valid || d.nrec == 0) return;
-    const bool halo = d.r0 > d.lo;
-    d.base16 = __shfl_sync(0xffffffffu, halo ? d.pko : d.ko, 0);
-    const uint32_t end16 = __shfl_sync(0xffffffffu, d.ko + ((d.kl + 15) >> 4), d.nrec - 1);
-    d.span = end16 - d.base16;
-    if (d.span <= KB_WARP_STAGE_CHUNKS) {
-        // one bulk (TMA) copy for the whole sub-tile: [base16, base16+span) chunks -> buf.  The buffer was last read
-        // (generic proxy) two steps ago and a __syncwarp separates those reads from this point; the proxy fence orders
-        // them before the async-proxy write.
-        if (lane == 0) {
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(dsmem_u32(bar)), "r"(d.span * 16)
-                         : "memory");
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                             dsmem_u32(buf)),
-                         "l"(st.kslab + d.base16), "r"(d.span * 16), "r"(dsmem_u32(bar))
-                         : "memory");
-        }
-    }
-    // only 9-byte values are ever inspected by the range path; the TTL sweep also reads revision-record values
-    if (lane < d.nrec && d.vl >= 8 && (d.vl == 9 || mode.ttl_scan)) d.v0 = st.vslab[d.vo];
-}
-
+// One record: LCP with the preceding key + the decode / visibility flags.  kp / pp point at the key and at the key in
+// front of it (shared memory when STAGED, the slab otherwise); v = the first 12 bytes of the value when vl is 9 (or, in
+// the TTL sweep, at least 8).
 template <bool STAGED>
-__device__ __forceinline__ uint32_t decode_record(const ScanMode &mode, const SubDesc &d, const uint4 *kp,
-                                                  const uint4 *pp, uint32_t len, uint32_t plen, bool has_prev)
+__device__ __forceinline__ uint32_t decode_record(const ScanMode &mode, uint64_t read_rev, const uint4 *kp, const uint4 *pp,
+                                                  uint32_t len, uint32_t plen, bool has_prev, uint32_t vl, uint32_t vx,
+                                                  uint32_t vy, uint32_t vz)
 {
     const uint8_t *kb = (const uint8_t *)kp;
     uint32_t lcp = KB_LCP_INF;
@@ -225,9 +145,7 @@ __device__ __forceinline__ uint32_t decode_record(const ScanMode &mode, const Su
         }
         flags |= KB_M_DEC_OK;
         if (rev == 0) flags |= KB_M_REV0;
-        const uint32_t vl = d.vl;
-        const uint4 v0 = d.v0;
-        const uint64_t vrev = ((uint64_t)bswap32(v0.x) << 32) | bswap32(v0.y);
+        const uint64_t vrev = ((uint64_t)bswap32(vx) << 32) | bswap32(vy);
         bool expired = false;
         if (mode.ttl_scan && contains_events(kb + 4, len - 13)) {  // compactIfExpired scanner.go:566-591
             if (rev == 0) {
@@ -240,13 +158,13 @@ __device__ __forceinline__ uint32_t decode_record(const ScanMode &mode, const Su
                 flags |= KB_M_TTLOBJ;
             }
         }
-        if (!expired && rev <= d.read_rev) {  // scanner.go:451-453
+        if (!expired && rev <= read_rev) {  // scanner.go:451-453
             flags |= KB_M_TRIG;
-            if (vl == 9 && v0.x == 0x626d6f74u && v0.y == 0x6e6f7473u && (v0.z & 0xffu) == 0x65u)
+            if (vl == 9 && vx == 0x626d6f74u && vy == 0x6e6f7473u && (vz & 0xffu) == 0x65u)
                 flags |= KB_M_TOMB;  // "tombstone" util.go:28
             bool prevok = true;
             if (mode.compact && rev == 0 && vl == 9) {  // scanner.go:476-491
-                if (vrev > d.read_rev)
+                if (vrev > read_rev)
                     prevok = false;  // `continue` without updating prev (Q5)
                 else
                     flags |= KB_M_REVDEL;
@@ -257,117 +175,274 @@ __device__ __forceinline__ uint32_t decode_record(const ScanMode &mode, const Su
     return lcp | flags;
 }
 
-// pipeline stage 3
-__device__ __forceinline__ void process_sub(const StoreDev &st, const ScanMode &mode, const SubDesc &d,
-                                            const uint4 *buf, uint32_t lane, uint32_t *__restrict__ meta,
-                                            uint2 *__restrict__ sub_agg)
+// launch geometry (chosen by the host from the longest key of the store, see decode_geometry)
+struct DecGeom {
+    uint32_t K;          // 32-record sub-tiles per step
+    uint32_t SK;         // key chunks per key-ring slot: (32 K + 1) keys of the longest length
+    uint32_t DS;         // chunks per directory slot: 32 K + 1 entries + DECODE_HDR_CHUNKS
+    uint32_t warps;      // warps per CTA
+    uint32_t bpt;        // blocks (of four steps) per tile: ceil(ceil(32 / K) / 4)
+    uint32_t n_blocks;   // tiles * bpt
+};
+
+// step descriptor, written by lane 0 into the head of the step's directory slot
+struct StepHdr {
+    uint32_t r0, nrec, flat, halo;   // first record, records, first meta slot, 1: the entry in front of r0 is staged too
+    uint32_t rr_lo, rr_hi;           // read revision of the request
+    uint32_t base16, span;           // key chunk interval (filled when the key copy is issued); span == ~0u: last step
+};
+static_assert(sizeof(StepHdr) == DECODE_HDR_CHUNKS * 16, "StepHdr is the slot header");
+
+struct BlockTile {
+    uint32_t valid, rec0, n, flat0, first /* rec0 is the request's first record */, bj /* block inside the tile */;
+    uint32_t rr_lo, rr_hi;
+};
+
+__device__ __forceinline__ BlockTile make_block(uint32_t b, const DecGeom &g, const uint4 &ta, const uint4 &tb)
 {
-    const unsigned FULLM = 0xffffffffu;
-    if (d.nrec == 0) {
-        if (lane == 0) sub_agg[d.sid] = make_uint2(KB_NONE, KB_LCP_INF);
-        return;
-    }
-    const bool valid = lane < d.nrec;
-    const bool staged = d.span <= KB_WARP_STAGE_CHUNKS;
-    // previous record's offset / length: lane-1, or the halo record for lane 0
-    uint32_t pko = __shfl_up_sync(FULLM, d.ko, 1), pkl = __shfl_up_sync(FULLM, d.kl, 1);
-    if (lane == 0) {
-        pko = d.pko;
-        pkl = d.pkl;
-    }
-    uint32_t word = KB_LCP_INF;
-    if (valid) {
-        const uint32_t r = d.r0 + lane;
-        const bool has_prev = r > d.lo;
-        if (staged) {
-            word = decode_record<true>(mode, d, buf + (d.ko - d.base16), buf + (has_prev ? pko - d.base16 : 0), d.kl, pkl,
-                                       has_prev);
-        } else {
-            word = decode_record<false>(mode, d, st.kslab + d.ko, st.kslab + (has_prev ? pko : d.ko), d.kl, pkl,
-                                        has_prev);
-        }
-        meta[d.sid * 32 + lane] = word;
-    }
-    // sub-tile aggregate: (last PREVOK slot, min LCP of the records after it)
-    const unsigned pm = __ballot_sync(FULLM, valid && (word & KB_M_PREVOK));
-    uint32_t mval = valid ? (word & KB_M_LCP_MASK) : KB_LCP_INF;
-    uint32_t L = KB_NONE;
-    if (pm) {
-        const uint32_t top = 31 - __clz(pm);
-        if (lane <= top) mval = KB_LCP_INF;
-        L = d.sid * 32 + top;
-    }
-    mval = __reduce_min_sync(FULLM, mval);
-    if (lane == 0) sub_agg[d.sid] = make_uint2(L, mval);
+    BlockTile t;
+    t.valid = b < g.n_blocks;
+    t.rec0 = ta.y;
+    t.n = ta.z;
+    t.flat0 = ta.w;
+    t.first = ta.y == tb.x;  // TileDev.rec0 == TileDev.lo
+    t.bj = b % g.bpt;
+    t.rr_lo = tb.z;
+    t.rr_hi = tb.w;
+    return t;
 }
 
-__global__ void __launch_bounds__(DECODE_WARPS * 32, 1)
-k_decode_lcp(StoreDev st, const ReqDev *__restrict__ reqs, const TileDev *__restrict__ tiles, uint32_t n_sub,
-             ScanMode mode, uint32_t *__restrict__ meta, uint2 *__restrict__ sub_agg, unsigned int *__restrict__ work_ctr)
+template <int MAXW, int KK>
+__global__ void __launch_bounds__(MAXW * 32, 1)
+k_decode_lcp(StoreDev st, const TileDev *__restrict__ tiles, DecGeom g, ScanMode mode, uint32_t *__restrict__ meta,
+             unsigned int *__restrict__ work_ctr, unsigned int *__restrict__ err_flag)
 {
-    extern __shared__ uint4 stage[];  // DECODE_WARPS x DECODE_STAGES x KB_WARP_STAGE_CHUNKS (+ 4 chunks of slack)
+    extern __shared__ uint4 smem[];  // per warp: keys[2][SK] | dir slots[3][DS]
+    __shared__ uint64_t bars[MAXW * 5];
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint4 *buf0 = stage + (size_t)warp * DECODE_STAGES * KB_WARP_STAGE_CHUNKS;
-    // The first three sub-tiles of a warp are assigned statically (they fill the pipeline); the rest are handed out
-    // through a global counter (left at zero by k_emit, which follows every decode pass), so a CTA that starts late --
-    // its SM was still busy with another stream's kernel -- simply takes fewer.  The atomic is issued one step before
-    // its result is used: lane 0 keeps the raw value and the warp picks it up with a shuffle at the next step.
-    const uint32_t stride = gridDim.x * DECODE_WARPS;
-    const uint32_t dyn_base = 3 * stride;
-    uint32_t sid = blockIdx.x * DECODE_WARPS + warp;
-    uint32_t raw = 0;
-
-    // one mbarrier per stage buffer; the phase of buffer b flips each time it is filled
-    __shared__ uint64_t bars[DECODE_WARPS * DECODE_STAGES];
-    uint64_t *bar0 = bars + warp * DECODE_STAGES;
+    const unsigned FULLM = 0xffffffffu;
+    uint4 *kbuf = smem + (size_t)warp * (2 * g.SK + 3 * g.DS);
+    uint4 *dbuf = kbuf + 2 * g.SK;
+    uint64_t *kbar = bars + warp * 5, *dbar = kbar + 2;
     if (lane == 0) {
-        dmbar_init(bar0);
-        dmbar_init(bar0 + 1);
+        for (int i = 0; i < 5; i++) dmbar_init(kbar + i);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
 
-    // prologue: fill the pipeline
-    TileRef tA = fetch_tile(tiles, sid, n_sub);
-    sid += stride;
-    SubDesc dB = load_desc(st, tA, lane);
-    tA = fetch_tile(tiles, sid, n_sub);
-    sid += stride;
-    SubDesc dA = load_desc(st, tA, lane);
-    tA = fetch_tile(tiles, sid, n_sub);
+    // ---- block stream of this warp: the first three blocks are static (they fill the pipeline), the rest come from the
+    // global counter (left at zero by k_emit_place, which follows every decode pass), so a CTA that starts late -- its SM
+    // was still busy with another stream's kernel -- simply takes fewer.
+    const uint32_t stride = gridDim.x * g.warps;
+    const uint32_t dyn_base = 3 * stride;
+    auto tile_of = [&](uint32_t b, uint4 &ta, uint4 &tb) {
+        ta = tb = make_uint4(0, 0, 0, 0);
+        if (b < g.n_blocks) {
+            const uint4 *p = (const uint4 *)(tiles + b / g.bpt);
+            ta = __ldg(p);
+            tb = __ldg(p + 1);
+        }
+    };
+    uint32_t b0 = blockIdx.x * g.warps + warp;
+    uint4 la, lb;
+    tile_of(b0, la, lb);
+    BlockTile T = make_block(b0, g, la, lb);           // block the generator is in
+    uint32_t b1 = b0 + stride;
+    tile_of(b1, la, lb);
+    BlockTile Tn = make_block(b1, g, la, lb);          // the block after it
+    uint32_t b2 = b1 + stride;                         // block whose tile descriptor is in flight (la, lb)
+    tile_of(b2, la, lb);
+    uint32_t raw = 0;                                  // lane 0: ticket of the block after b2
     if (lane == 0) raw = atom_add_u32_raw(work_ctr, 1u);
-    issue_stage(st, mode, dB, buf0, bar0, lane);
-    uint32_t fills0 = 0, fills1 = 0;  // completed-phase counters of the two buffers (parity = count & 1)
-    // The body is unrolled six times (lcm of the 3 descriptor roles and the 2 stage buffers) so that the role
-    // rotation dC <- dB <- dA is pure register renaming inside the body; moves remain only on the back edge.
-    bool more = dB.valid != 0;
-    while (more) {
-#pragma unroll
-        for (int u = 0; u < 6; u++) {
-            if (more) {
-                const SubDesc dC = dB;  // key bytes + value probe in flight since the previous step
-                dB = dA;                // directory loaded one step ago
-                dA = load_desc(st, tA, lane);
-                sid = dyn_base + __shfl_sync(0xffffffffu, raw, 0);
-                tA = fetch_tile(tiles, sid, n_sub);
-                if (lane == 0) raw = atom_add_u32_raw(work_ctr, 1u);
-                issue_stage(st, mode, dB, buf0 + ((u + 1) & 1) * KB_WARP_STAGE_CHUNKS, bar0 + ((u + 1) & 1), lane);
-                // wait for dC's bytes (only if a copy was issued for it: real, staged sub-tile)
-                if (dC.nrec != 0 && dC.span <= KB_WARP_STAGE_CHUNKS) {
-                    if ((u & 1) == 0) {
-                        dmbar_wait(bar0, fills0 & 1);
-                        fills0++;
-                    } else {
-                        dmbar_wait(bar0 + 1, fills1 & 1);
-                        fills1++;
-                    }
-                }
-                process_sub(st, mode, dC, buf0 + (u & 1) * KB_WARP_STAGE_CHUNKS, lane, meta, sub_agg);
-                __syncwarp();
-                more = dB.valid != 0;
+    uint32_t gj = 0;                                   // generator: step inside its block (0..3)
+
+    // generator: describe the next step of the stream in directory slot `slot` and start the copy of its entries
+    auto generate = [&](uint32_t slot) {
+        uint4 *ds = dbuf + (size_t)slot * g.DS;
+        StepHdr *h = (StepHdr *)ds;
+        uint32_t nrec = 0, r0 = 0, flat = 0, halo = 0;
+        const bool live = T.valid != 0;
+        if (live) {
+            const uint32_t sub0 = (T.bj * 4 + gj) * KK;
+            if (sub0 * 32 < T.n) {
+                nrec = min((uint32_t)KK * 32, T.n - sub0 * 32);
+                r0 = T.rec0 + sub0 * 32;
+                flat = T.flat0 + sub0 * 32;
+                halo = (T.first && sub0 == 0) ? 0u : 1u;
             }
         }
+        if (lane == 0) {
+            h->r0 = r0;
+            h->nrec = nrec;
+            h->flat = flat;
+            h->halo = halo;
+            h->rr_lo = T.rr_lo;
+            h->rr_hi = T.rr_hi;
+            h->base16 = 0;
+            h->span = live ? 0u : ~0u;
+            if (nrec) {
+                // the slot was last read (generic proxy) three steps ago; the __syncwarp that ended that step orders
+                // those reads before this point, the proxy fence orders them before the async-proxy write
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                const uint32_t bytes = (nrec + halo) * 16;
+                dmbar_expect(dbar + slot, bytes);
+                dbulk_g2s(ds + DECODE_HDR_CHUNKS, st.dir + (r0 - halo), bytes, dbar + slot);
+            }
+        }
+        if (live && ++gj == 4) {  // enter the next block: everything it needs was requested a block ago
+            gj = 0;
+            T = Tn;
+            Tn = make_block(b2, g, la, lb);
+            b2 = dyn_base + __shfl_sync(FULLM, raw, 0);
+            tile_of(b2, la, lb);
+            if (lane == 0) raw = atom_add_u32_raw(work_ctr, 1u);
+        }
+    };
+
+    uint32_t vx[KK], vy[KK], vz[KK];    // value probes of the step being processed
+    uint32_t nx[KK], ny[KK], nz[KK];    // ... of the step whose keys are in flight
+#pragma unroll
+    for (int k = 0; k < KK; k++) vx[k] = vy[k] = vz[k] = nx[k] = ny[k] = nz[k] = 0;
+    uint32_t phase = 0;  // bit i: parity the next completion of barrier i will have been waited with (kbar 0,1, dbar 2,3,4)
+
+    // keys + value probes of the step described in directory slot `slot`, into key slot `ks`
+    auto stage_keys = [&](uint32_t slot, uint32_t ks) {
+        uint4 *ds = dbuf + (size_t)slot * g.DS;
+        StepHdr *h = (StepHdr *)ds;
+        const uint32_t nrec = h->nrec, halo = h->halo;
+        if (nrec == 0) return;
+        dmbar_wait(dbar + slot, (phase >> (2 + slot)) & 1, err_flag);
+        phase ^= 1u << (2 + slot);
+        const uint4 *ent = ds + DECODE_HDR_CHUNKS;
+        const uint32_t cnt = nrec + halo;
+        const uint4 e0 = ent[0], e1 = ent[cnt - 1];
+        const uint32_t base16 = e0.x, span = e1.x + (((e1.y & 0xffffu) + 15) >> 4) - e0.x;
+        if (lane == 0) {
+            h->base16 = base16;
+            h->span = span;
+            if (span <= g.SK) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                dmbar_expect(kbar + ks, span * 16);
+                dbulk_g2s(kbuf + (size_t)ks * g.SK, st.kslab + base16, span * 16, kbar + ks);
+            }
+        }
+        // only 9-byte values are ever inspected by the range path; the TTL sweep also reads revision-record values
+#pragma unroll
+        for (int k = 0; k < KK; k++) {
+            nx[k] = ny[k] = nz[k] = 0;
+            const uint32_t r = k * 32 + lane;
+            if (r < nrec) {
+                const uint4 e = ent[halo + r];
+                const uint32_t vl = e.z;
+                if (vl >= 8 && (vl == 9 || mode.ttl_scan)) {
+                    const uint4 v = __ldg(st.vslab + (((uint64_t)(e.y >> 16) << 32) | e.w));
+                    nx[k] = v.x;
+                    ny[k] = v.y;
+                    nz[k] = v.z;
+                }
+            }
+        }
+    };
+
+    // decode the step in directory slot `slot` whose keys were staged into key slot `ks`; false: end of the stream
+    auto process = [&](uint32_t slot, uint32_t ks) -> bool {
+        const uint4 *ds = dbuf + (size_t)slot * g.DS;
+        const StepHdr *h = (const StepHdr *)ds;
+        const uint32_t nrec = h->nrec;
+        if (nrec == 0) return h->span != ~0u;
+        const uint32_t halo = h->halo, base16 = h->base16, span = h->span;
+        const uint64_t read_rev = ((uint64_t)h->rr_hi << 32) | h->rr_lo;
+        const bool staged = span <= g.SK;
+        if (staged) {
+            dmbar_wait(kbar + ks, (phase >> ks) & 1, err_flag);
+            phase ^= 1u << ks;
+        }
+        const uint4 *ent = ds + DECODE_HDR_CHUNKS + halo;  // ent[r] = record r0 + r; ent[-1] = the record in front (halo)
+        const uint4 *buf = kbuf + (size_t)ks * g.SK;
+#pragma unroll
+        for (int k = 0; k < KK; k++) {
+            const uint32_t r = k * 32 + lane;
+            if (r < nrec) {
+                const uint4 e = ent[r];
+                const bool has_prev = halo != 0 || r > 0;
+                uint4 pe = e;
+                if (has_prev) pe = ent[(int)r - 1];
+                const uint32_t kl = e.y & 0xffffu, pkl = pe.y & 0xffffu;
+                uint32_t word;
+                if (staged)
+                    word = decode_record<true>(mode, read_rev, buf + (e.x - base16), buf + (pe.x - base16), kl, pkl, has_prev,
+                                               e.z, vx[k], vy[k], vz[k]);
+                else
+                    word = decode_record<false>(mode, read_rev, st.kslab + e.x, st.kslab + pe.x, kl, pkl, has_prev, e.z,
+                                                vx[k], vy[k], vz[k]);
+                meta[h->flat + r] = word;
+            }
+        }
+        return true;
+    };
+
+    // prologue: steps 0 and 1 described, keys of step 0 in flight
+    generate(0);
+    __syncwarp();
+    generate(1);
+    __syncwarp();
+    stage_keys(0, 0);
+#pragma unroll
+    for (int k = 0; k < KK; k++) {
+        vx[k] = nx[k];
+        vy[k] = ny[k];
+        vz[k] = nz[k];
     }
+    __syncwarp();
+    // steady state, iteration i: describe step i+2, stage the keys of step i+1, decode step i
+    uint32_t s0 = 0, k0 = 0;  // directory / key slot of the step being decoded
+    for (;;) {
+        const uint32_t s1 = s0 == 2 ? 0 : s0 + 1, s2 = s1 == 2 ? 0 : s1 + 1;
+        generate(s2);
+        __syncwarp();
+        stage_keys(s1, k0 ^ 1);
+        const bool more = process(s0, k0);
+#pragma unroll
+        for (int k = 0; k < KK; k++) {
+            vx[k] = nx[k];
+            vy[k] = ny[k];
+            vz[k] = nz[k];
+        }
+        __syncwarp();
+        if (!more) break;
+        s0 = s1;
+        k0 ^= 1;
+    }
+}
+
+// geometry for a store whose longest key has `max_key_chunks` 16-byte chunks; K and the warp count can be forced for
+// experiments (KB_DECODE_K, KB_DECODE_WARPS)
+static inline DecGeom decode_geometry(uint32_t max_key_chunks, uint32_t ntiles, uint32_t force_k, uint32_t force_warps,
+                                      size_t *smem_bytes)
+{
+    const uint32_t c = std::max<uint32_t>(max_key_chunks, 1);
+    const size_t budget = 227 * 1024 - 2048;
+    DecGeom g;
+    uint32_t K = force_k ? force_k : (c >= 9 ? 1u : c >= 5 ? 2u : 4u);
+    K = std::min<uint32_t>(std::max<uint32_t>(K, 1), DECODE_MAX_K);
+    auto per_warp = [&](uint32_t k) { return (size_t)(2 * (32 * k + 1) * c + 3 * (32 * k + 1 + DECODE_HDR_CHUNKS)) * 16; };
+    while (K > 1 && per_warp(K) * 4 > budget) K--;  // very long keys: fewer records per step rather than fewer than 4 warps
+    g.K = K;
+    g.SK = (32 * K + 1) * c;
+    // keys longer than ~1.7 KB: the ring would not hold a sub-tile even with four warps; cap the slot, such steps take
+    // the unstaged path (direct loads from the slab)
+    const uint32_t max_sk = (uint32_t)((budget / 4 / 16 - 3 * (32 * K + 1 + DECODE_HDR_CHUNKS)) / 2);
+    g.SK = std::min(g.SK, max_sk);
+    g.DS = 32 * K + 1 + DECODE_HDR_CHUNKS;
+    const size_t pw = (size_t)(2 * g.SK + 3 * g.DS) * 16;
+    uint32_t warps = (uint32_t)std::min<size_t>(budget / pw, 24);
+    if (force_warps) warps = std::min(warps, force_warps);
+    g.warps = std::max<uint32_t>(warps, 1);
+    const uint32_t spt = (32 + K - 1) / K;
+    g.bpt = (spt + 3) / 4;
+    g.n_blocks = ntiles * g.bpt;
+    *smem_bytes = pw * g.warps;
+    return g;
 }
 
 }  // namespace

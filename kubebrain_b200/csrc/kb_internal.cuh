@@ -74,7 +74,6 @@ enum { KB_WIRE_NONE_I = 0, KB_WIRE_KVS_I = 1, KB_WIRE_EVENTS_I = 2 };
 #define KB_NONE       0xFFFFFFFFu
 
 #define KB_TILE       1024          // records per tile (256 threads x 4)
-#define KB_WARP_STAGE_CHUNKS 576    // 16-byte chunks of shared memory per warp and stage (9 KiB: 33 keys of 272 B)
 
 // ------------------------------------------------------------------------------------------------
 // device helpers
@@ -180,6 +179,7 @@ struct kb_ctx {
     DBuf d_kslab, d_koff16, d_klen, d_vslab, d_voff16, d_vlen, d_dir;
     uint64_t key_bytes = 0, val_bytes = 0;
     uint32_t max_kv_chunks = 0;  // largest padded [key][value] pair, in 16-byte chunks: sizes the gather's ring buffers
+    uint32_t max_key_chunks = 0; // longest key, in 16-byte chunks: sizes the decode pass's key ring
     std::vector<uint32_t> h_koff16;  // host copies of the slab offsets: byte accounting and response-arena bounds
     std::vector<uint64_t> h_voff16;
     std::vector<uint16_t> h_klen;   // host copy of the whole record directory: kb_apply_batch rebuilds it on the host
@@ -188,7 +188,7 @@ struct kb_ctx {
     uint64_t compact_rev = 0;
 
     // scratch (grow only)
-    DBuf d_bounds, d_bres, d_reqs, d_tiles /* alias into d_reqs */, d_meta, d_tgt, d_agg, d_tcnt, d_tscan, d_reqout,
+    DBuf d_bounds, d_bres, d_reqs, d_tiles /* alias into d_reqs */, d_meta, d_tgt, d_agg, d_tcnt /* look-back states */, d_tscan, d_reqout,
         d_sel, d_slot, d_jobs, d_gjobs, d_jobs2, d_gjobs2 /* second job-buffer set */, d_flags,
         d_ctrs /* work-queue counters, kept at zero between kernels */;
     HBuf h_stage, h_stage2;
@@ -242,7 +242,7 @@ struct kb_result {
     int wire = 0;                          // KB_WIRE_*_I
     const uint64_t *elem_off = nullptr;    // wire modes: n_kvs + 1 element offsets into the arena
     // compact
-    uint64_t n_victims = 0, count = 0, examined = 0;
+    uint64_t n_victims = 0, count = 0, examined = 0, vic_cap = 0;
     HBuf h_vic;
     DBuf d_vic;
     // get

@@ -3,8 +3,8 @@
 // Replaces (reference file:line):
 //   storage.Iter over badger            pkg/storage/badger/iter.go:27-98        -> HBM slab + k_search
 //   coder.Decode                        pkg/backend/coder/normal.go:58-70       -> k_decode_lcp
-//   worker.run (range + compact)        pkg/backend/scanner/scanner.go:389-516  -> k_decode_lcp, k_emit, k_place
-//   commonResultReceiver (limit)        pkg/backend/scanner/receiver.go:62-103  -> k_tile_scan, k_place, k_gather
+//   worker.run (range + compact)        pkg/backend/scanner/scanner.go:389-516  -> k_decode_lcp, k_emit_place
+//   commonResultReceiver (limit)        pkg/backend/scanner/receiver.go:62-103  -> k_emit_place, k_gather
 //
 // Kernel pipeline for one batch of requests (streams: S2 = bound search, S = main, SG = copy stream):
 //   k_search      [S2] lower_bound of every [start,end) bound in the sorted slab (warp per bound, 32-ary); the only
@@ -12,15 +12,15 @@
 //   k_decode_lcp  [S] HBM-bound pass: stream the raw internal keys (one bulk-TMA copy per 32-record sub-tile into a
 //                 per-warp shared-memory ring), decode magic/split/revision, visibility, tombstone probe, and the
 //                 common-prefix length with the preceding key -> one 32-bit meta word per record + sub-tile aggregates
-//   k_emit        [S] per tile: segmented "last visible version" scan over the meta words (prev pointer +
-//                 running min-LCP), decides which record every key change emits / supersedes
-//   k_tile_scan   [S] prefix sums of per-tile counts/bytes, per-request totals
-//   k_place       [S] ordered placement of the selection (limit applied) / ordered victim list
+//   k_emit_place  [S] per tile, one pass: segmented "last visible version" scan over the meta words (prev pointer +
+//                 running min-LCP) decides which record every key change emits / supersedes; cross-tile carry and the
+//                 output positions come from decoupled look-back; writes the ordered selection (limit applied) or the
+//                 ordered victim list and the per-request totals
 //   k_req_finalize [S] per-request prefix sums; publishes the per-request rows to mapped pinned memory (the host
 //                 returns device-resident answers on that flag)
 //   k_gather_jobs / k_wire_jobs [S] one copy job per emitted kv + the per-kv view arrays
 //   k_gather / k_wire_copy [SG] bulk-TMA copy of the winners' key+value into the response arena (padded pairs, or
-//                 etcd protobuf elements); overlaps the next batch's k_decode_lcp .. k_place
+//                 etcd protobuf elements); overlaps the next batch's k_decode_lcp .. k_emit_place
 #include <algorithm>
 
 #include "kb_internal.cuh"
@@ -181,43 +181,143 @@ __device__ __forceinline__ void block_excl_scan2(uint64_t a, uint64_t b, uint64_
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_emit: the worker.run state machine, data-parallel.
+// k_emit_place: the worker.run state machine, data-parallel, in ONE pass over the meta words.
 // For every TRIG record i with prev p = last PREVOK record before it (inside the request):
 //   same key  <=> klen[i] == klen[p] && min LCP over (p, i] >= klen[i] - 9
 //   range  : key change && rev[p] > 0 && value[p] != tombstone  -> emit p         (scanner.go:457-462)
 //   compact: same key && rev[p] > 0                             -> p superseded   (scanner.go:463-469)
 // After the last record of a request the trailing prev is emitted (scanner.go:503-507).
-// tgt[i] = flat slot of the emitted (range) / superseded (compact) record, or NONE.
-// tcnt[2t] = emissions (range) or delete calls (compact) of tile t; tcnt[2t+1] = response bytes (range) or
-// object count (compact).
+//
+// Round 1 ran this as k_emit (decide + per-tile counts; the cross-tile carry was a serial walk over sub-tile
+// aggregates by one thread) -> k_tile_scan (one CTA) -> k_place / k_place_victims (second pass over the records).
+// Here a tile (1024 records, taken in ticket order) resolves both cross-tile dependencies by DECOUPLED LOOK-BACK:
+//   1. (last PREVOK slot, min LCP since) carry: the tile publishes its own aggregate at once, then warp 0 reads the
+//      states of up to 32 preceding tiles of the request per step until it meets an inclusive prefix or a tile that
+//      holds a PREVOK record (nothing before such a tile can matter).  A request whose records are all invisible --
+//      the round-1 worst case, O(tiles) dependent loads per tile -- costs one step per tile.
+//   2. emission count / response bytes (or delete calls / object count): the classic single-pass prefix sum.
+// The tile then writes its slice of the ordered selection (limit applied, receiver.go:82-87) or of the ordered
+// delete-call list directly; the request's last tile writes the request totals.
 // ------------------------------------------------------------------------------------------------
+struct ReqOut {
+    uint64_t total;        // emissions (range) / delete calls (compact)
+    uint64_t total_aux;    // response bytes (range) / object count (compact)
+    uint64_t capped_aux;   // response bytes of the first `limit` emissions (valid with KB_RO_CAPPED)
+    uint32_t examined;     // records pulled from the iterator (valid with KB_RO_LIMIT_STOP, else hi - lo)
+    uint32_t flags;
+};
+enum { KB_RO_LIMIT_STOP = 1u, KB_RO_CAPPED = 2u };
+
+struct __align__(16) TileState {  // 64 bytes; zeroed by one memset per batch
+    unsigned long long lm_agg, lm_pre;  // (last PREVOK slot | min LCP << 32): the tile alone / request start .. this tile
+    unsigned long long cnt_agg, aux_agg, cnt_pre, aux_pre;
+    uint32_t st_lm, st_cnt;  // 0 empty, 1 aggregate valid, 2 inclusive prefix valid
+    uint32_t pad[2];
+};
+enum { TS_EMPTY = 0, TS_AGG = 1, TS_PREFIX = 2 };
+
+__device__ __forceinline__ unsigned long long lm_pack(LM v) { return ((unsigned long long)v.m << 32) | v.L; }
+__device__ __forceinline__ LM lm_unpack(unsigned long long w)
+{
+    LM r;
+    r.L = (uint32_t)w;
+    r.m = (uint32_t)(w >> 32);
+    return r;
+}
+__device__ __forceinline__ void ts_publish(uint32_t *status, uint32_t v)
+{
+    __threadfence();
+    *(volatile uint32_t *)status = v;
+}
+
+// warp 0: exclusive (L, m) carry of tile t inside its request (tiles [t0, t))
+__device__ __forceinline__ LM lookback_lm(TileState *ts, uint32_t t, uint32_t t0, uint32_t lane)
+{
+    LM acc;
+    acc.L = KB_NONE;
+    acc.m = KB_LCP_INF;
+    for (uint32_t hi = t; hi > t0;) {  // this step looks at tiles hi-1, hi-2, .. (lane 0 = nearest)
+        const bool in = lane < hi - t0;
+        TileState *p = ts + (hi - 1 - (in ? lane : 0));
+        uint32_t st;
+        do {
+            st = in ? *(volatile uint32_t *)&p->st_lm : (uint32_t)TS_PREFIX;
+        } while (!__all_sync(FULL, st != TS_EMPTY));
+        __threadfence();
+        LM v;
+        v.L = KB_NONE;
+        v.m = KB_LCP_INF;
+        if (in) v = lm_unpack(*(volatile unsigned long long *)(st == TS_PREFIX ? &p->lm_pre : &p->lm_agg));
+        const unsigned term = __ballot_sync(FULL, in && (st == TS_PREFIX || v.L != KB_NONE));
+        const uint32_t k = term ? (uint32_t)(__ffs(term) - 1) : 31u;  // farthest lane that still matters
+        const uint32_t mm = __reduce_min_sync(FULL, (in && lane <= k) ? v.m : KB_LCP_INF);
+        const uint32_t Lk = __shfl_sync(FULL, v.L, k);
+        // combine(farther, nearer): nearer tiles (already in acc) hold no PREVOK, so only the minimum accumulates
+        acc.m = min(acc.m, mm);
+        if (term) {
+            acc.L = Lk;
+            break;
+        }
+        hi -= min(32u, hi - t0);
+    }
+    return acc;
+}
+
+// warp 0: exclusive sums (count, aux) of tile t inside its request
+__device__ __forceinline__ void lookback_sum(TileState *ts, uint32_t t, uint32_t t0, uint32_t lane, uint64_t &cnt,
+                                             uint64_t &aux)
+{
+    cnt = aux = 0;
+    for (uint32_t hi = t; hi > t0;) {
+        const bool in = lane < hi - t0;
+        TileState *p = ts + (hi - 1 - (in ? lane : 0));
+        uint32_t st;
+        do {
+            st = in ? *(volatile uint32_t *)&p->st_cnt : (uint32_t)TS_PREFIX;
+        } while (!__all_sync(FULL, st != TS_EMPTY));
+        __threadfence();
+        uint64_t c = 0, a = 0;
+        if (in) {
+            c = *(volatile unsigned long long *)(st == TS_PREFIX ? &p->cnt_pre : &p->cnt_agg);
+            a = *(volatile unsigned long long *)(st == TS_PREFIX ? &p->aux_pre : &p->aux_agg);
+        }
+        const unsigned term = __ballot_sync(FULL, in && st == TS_PREFIX);
+        const uint32_t k = term ? (uint32_t)(__ffs(term) - 1) : 31u;
+        if (!(in && lane <= k)) c = a = 0;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            c += __shfl_xor_sync(FULL, c, d);
+            a += __shfl_xor_sync(FULL, a, d);
+        }
+        cnt += c;
+        aux += a;
+        if (term) break;
+        hi -= min(32u, hi - t0);
+    }
+}
+
 template <bool COMPACT>
 __global__ void __launch_bounds__(256)
-k_emit(StoreDev st, const ReqDev *__restrict__ reqs, const TileDev *__restrict__ tiles,
-       const uint2 *__restrict__ sub_agg, const uint32_t *__restrict__ meta, uint32_t *__restrict__ tgt,
-       uint32_t *__restrict__ tail_tgt, uint64_t *__restrict__ tcnt, int wire, unsigned int *__restrict__ decode_ctr)
+k_emit_place(StoreDev st, const ReqDev *__restrict__ reqs, const TileDev *__restrict__ tiles,
+             const uint32_t *__restrict__ meta, TileState *__restrict__ ts, unsigned int *__restrict__ ticket,
+             uint32_t *__restrict__ sel, uint64_t *__restrict__ slot, uint32_t *__restrict__ vidx,
+             uint8_t *__restrict__ vcls, ReqOut *__restrict__ rout, int wire, int with_place,
+             unsigned int *__restrict__ decode_ctr)
 {
-    if (blockIdx.x == 0 && threadIdx.x == 0) *decode_ctr = 0;  // leave k_decode_lcp's work counter at zero
     __shared__ LM warp_tot[8];
-    __shared__ LM carry_s;
+    __shared__ LM carry_s, agg_s;
     __shared__ uint64_t ws2[18];
-    const TileDev tile = tiles[blockIdx.x];
+    __shared__ uint64_t pre_s[2];
+    __shared__ uint32_t tile_s;
+    if (threadIdx.x == 0) tile_s = atomicAdd(ticket, 1u);  // ticket order: every preceding tile has started
+    if (blockIdx.x == 0 && threadIdx.x == 0) *decode_ctr = 0;  // leave k_decode_lcp's work counter at zero
+    __syncthreads();
+    const uint32_t tix = tile_s;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const TileDev tile = tiles[tix];
     const ReqDev req = reqs[tile.req];
-    if (threadIdx.x == 0) {
-        LM c;
-        c.L = KB_NONE;
-        c.m = KB_LCP_INF;
-        // carry-in: walk the 32-record sub-tile aggregates of this request backwards until one holds a PREVOK
-        for (uint32_t t = tile.flat0 >> 5; t-- > (req.flat0 >> 5);) {
-            uint2 a = sub_agg[t];
-            c.m = min(c.m, a.y);
-            if (a.x != KB_NONE) {
-                c.L = a.x;
-                break;
-            }
-        }
-        carry_s = c;
-    }
+    const bool first_tile = tix == req.tile0, last_tile = tix == req.tile0 + req.ntiles - 1;
+    TileState *my = ts + tix;
     const uint32_t base = threadIdx.x * 4;
     const uint32_t flat = tile.flat0 + base;
     uint32_t w[4];
@@ -241,17 +341,49 @@ k_emit(StoreDev st, const ReqDev *__restrict__ reqs, const TileDev *__restrict__
             mine.m = min(mine.m, w[k] & KB_M_LCP_MASK);
         }
     }
-    LM ex = block_excl_scan_lm(mine, warp_tot);  // contains a __syncthreads: carry_s is visible after it
+    const LM ex = block_excl_scan_lm(mine, warp_tot);
+    if (threadIdx.x == 255) agg_s = lm_combine(ex, mine);
+    __syncthreads();
+    if (warp == 0) {
+        const LM agg = agg_s;
+        LM carry;
+        carry.L = KB_NONE;
+        carry.m = KB_LCP_INF;
+        if (first_tile) {
+            if (lane == 0) {
+                my->lm_pre = lm_pack(agg);
+                ts_publish(&my->st_lm, TS_PREFIX);
+            }
+        } else {
+            if (lane == 0) {
+                my->lm_agg = lm_pack(agg);
+                ts_publish(&my->st_lm, TS_AGG);
+            }
+            carry = lookback_lm(ts, tix, req.tile0, lane);
+            if (lane == 0) {
+                my->lm_pre = lm_pack(lm_combine(carry, agg));
+                ts_publish(&my->st_lm, TS_PREFIX);
+            }
+        }
+        if (lane == 0) carry_s = carry;
+    }
+    __syncthreads();
     LM x = lm_combine(carry_s, ex);
 
+    // decisions of this thread's four records (+ the request's trailing prev): t[k] = flat slot of the emitted (range) /
+    // superseded (compact) record, cnt = emissions / delete calls, aux = response bytes / object count
+    uint32_t t[5], sz[5];
+#pragma unroll
+    for (int k = 0; k < 5; k++) {
+        t[k] = KB_NONE;
+        sz[k] = 0;
+    }
     uint64_t cnt = 0, aux = 0;
-    const bool last_tile = (blockIdx.x == req.tile0 + req.ntiles - 1);
 #pragma unroll
     for (int k = 0; k < 4; k++) {
         if (base + k >= tile.n) break;
         const uint32_t i = flat + k;
         const uint32_t word = w[k];
-        uint32_t t = KB_NONE;
         if (word & KB_M_TRIG) {
             if (x.L != KB_NONE) {
                 const uint32_t mm = min(x.m, word & KB_M_LCP_MASK);
@@ -264,13 +396,14 @@ k_emit(StoreDev st, const ReqDev *__restrict__ reqs, const TileDev *__restrict__
                         if (COMPACT) {
                             aux++;  // count++ only
                         } else {
-                            t = x.L;
+                            t[k] = x.L;
+                            sz[k] = (uint32_t)kv_resp_bytes(st, prec, wire);
                             cnt++;
-                            aux += kv_resp_bytes(st, prec, wire);
+                            aux += sz[k];
                         }
                     }
                 } else if (COMPACT && !(pw & KB_M_REV0)) {
-                    t = x.L;  // superseded version
+                    t[k] = x.L;  // superseded version
                     cnt++;
                 }
             }
@@ -286,10 +419,8 @@ k_emit(StoreDev st, const ReqDev *__restrict__ reqs, const TileDev *__restrict__
         } else {
             x.m = min(x.m, word & KB_M_LCP_MASK);
         }
-        tgt[i] = t;
         if (last_tile && base + k == tile.n - 1) {
             // end of the request's iterator: the trailing prev (scanner.go:503-507)
-            uint32_t tt = KB_NONE;
             if (x.L != KB_NONE) {
                 const uint32_t pw = meta[x.L];
                 if (!(pw & KB_M_REV0) && !(pw & KB_M_TOMB)) {
@@ -297,197 +428,102 @@ k_emit(StoreDev st, const ReqDev *__restrict__ reqs, const TileDev *__restrict__
                         aux++;
                     } else {
                         const uint32_t prec = req.lo + (x.L - req.flat0);
-                        tt = x.L;
+                        t[4] = x.L;
+                        sz[4] = (uint32_t)kv_resp_bytes(st, prec, wire);
                         cnt++;
-                        aux += kv_resp_bytes(st, prec, wire);
+                        aux += sz[4];
                     }
                 }
             }
-            tail_tgt[tile.req] = tt;
         }
     }
     uint64_t ea, eb, ta, tb;
     block_excl_scan2(cnt, aux, ea, eb, ta, tb, ws2);
-    if (threadIdx.x == 0) {
-        tcnt[2 * blockIdx.x] = ta;
-        tcnt[2 * blockIdx.x + 1] = tb;
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// k_tile_scan: one CTA; exclusive prefix of the per-tile pairs + per-request totals
-// ------------------------------------------------------------------------------------------------
-struct ReqOut {
-    uint64_t total;        // emissions (range) / delete calls (compact)
-    uint64_t total_aux;    // response bytes (range) / object count (compact)
-    uint64_t capped_aux;   // response bytes of the first `limit` emissions
-    uint32_t examined;
-    uint32_t limit_stop;
-};
-
-__global__ void __launch_bounds__(256)
-k_tile_scan(const ReqDev *__restrict__ reqs, uint32_t nreq, const uint64_t *__restrict__ tcnt,
-            uint64_t *__restrict__ tscan /* 2*(T+1) */, uint32_t ntiles, ReqOut *__restrict__ rout)
-{
-    __shared__ uint64_t ws2[18];
-    __shared__ uint64_t carry[2];
-    if (threadIdx.x == 0) carry[0] = carry[1] = 0;
-    __syncthreads();
-    for (uint32_t c0 = 0; c0 < ntiles; c0 += 256) {
-        uint32_t t = c0 + threadIdx.x;
-        uint64_t a = t < ntiles ? tcnt[2 * t] : 0, b = t < ntiles ? tcnt[2 * t + 1] : 0;
-        uint64_t ea, eb, ta, tb;
-        block_excl_scan2(a, b, ea, eb, ta, tb, ws2);
-        uint64_t ca = carry[0], cb = carry[1];
-        if (t < ntiles) {
-            tscan[2 * t] = ca + ea;
-            tscan[2 * t + 1] = cb + eb;
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            carry[0] = ca + ta;
-            carry[1] = cb + tb;
-        }
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) {
-        tscan[2 * ntiles] = carry[0];
-        tscan[2 * ntiles + 1] = carry[1];
-    }
-    __syncthreads();
-    for (uint32_t q = threadIdx.x; q < nreq; q += 256) {
-        ReqDev r = reqs[q];
-        ReqOut o;
-        o.total = o.total_aux = 0;
-        if (r.ntiles) {
-            o.total = tscan[2 * (r.tile0 + r.ntiles)] - tscan[2 * r.tile0];
-            o.total_aux = tscan[2 * (r.tile0 + r.ntiles) + 1] - tscan[2 * r.tile0 + 1];
-        }
-        o.capped_aux = o.total_aux;
-        o.examined = r.hi - r.lo;
-        o.limit_stop = 0;
-        rout[q] = o;
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// k_place: ordered selection (range) -- position = emissions before it in the request; the first `limit`
-// positions are kept (commonResultReceiver.needMore, receiver.go:82-87).
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-k_place(StoreDev st, const ReqDev *__restrict__ reqs, const TileDev *__restrict__ tiles,
-        const uint32_t *__restrict__ tgt, const uint32_t *__restrict__ tail_tgt,
-        const uint64_t *__restrict__ tscan, uint32_t *__restrict__ sel, uint64_t *__restrict__ slot,
-        ReqOut *__restrict__ rout, int wire)
-{
-    __shared__ uint64_t ws2[18];
-    const TileDev tile = tiles[blockIdx.x];
-    const ReqDev req = reqs[tile.req];
-    const uint32_t base = threadIdx.x * 4;
-    const uint32_t flat = tile.flat0 + base;
-    const bool last_tile = (blockIdx.x == req.tile0 + req.ntiles - 1);
-    uint32_t t[5];
-    uint32_t sz[5];
-    uint64_t cnt = 0, bytes = 0;
-#pragma unroll
-    for (int k = 0; k < 5; k++) {
-        t[k] = KB_NONE;
-        sz[k] = 0;
-    }
-    if (base < tile.n) {
-        uint4 tw = *(const uint4 *)(tgt + flat);
-        t[0] = tw.x;
-        t[1] = base + 1 < tile.n ? tw.y : KB_NONE;
-        t[2] = base + 2 < tile.n ? tw.z : KB_NONE;
-        t[3] = base + 3 < tile.n ? tw.w : KB_NONE;
-        if (last_tile && tile.n - 1 >= base && tile.n - 1 < base + 4) t[4] = tail_tgt[tile.req];
-    }
-#pragma unroll
-    for (int k = 0; k < 5; k++) {
-        if (t[k] != KB_NONE) {
-            const uint32_t prec = req.lo + (t[k] - req.flat0);
-            sz[k] = (uint32_t)kv_resp_bytes(st, prec, wire);
-            cnt++;
-            bytes += sz[k];
-        }
-    }
-    uint64_t ea, eb, ta, tb;
-    block_excl_scan2(cnt, bytes, ea, eb, ta, tb, ws2);
-    uint64_t pos = tscan[2 * blockIdx.x] - tscan[2 * req.tile0] + ea;
-    uint64_t off = tscan[2 * blockIdx.x + 1] - tscan[2 * req.tile0 + 1] + eb;
-    const bool limited = req.limit > 0;
-#pragma unroll
-    for (int k = 0; k < 5; k++) {
-        if (t[k] == KB_NONE) continue;
-        if (!limited || pos < (uint64_t)req.limit) {
-            sel[req.sel_base + pos] = req.lo + (t[k] - req.flat0);
-            slot[req.sel_base + pos] = off;
-            if (limited && pos == (uint64_t)req.limit - 1) {
-                rout[tile.req].capped_aux = off + sz[k];
-                if (k < 4) {
-                    // the limit-th append happened inside the loop: the iterator stops here (Q4)
-                    rout[tile.req].examined = (flat + k) - req.flat0 + 1;
-                    rout[tile.req].limit_stop = 1;
-                }
+    if (warp == 0) {
+        uint64_t pc = 0, pa = 0;
+        if (first_tile) {
+            if (lane == 0) {
+                my->cnt_pre = ta;
+                my->aux_pre = tb;
+                ts_publish(&my->st_cnt, TS_PREFIX);
+            }
+        } else {
+            if (lane == 0) {
+                my->cnt_agg = ta;
+                my->aux_agg = tb;
+                ts_publish(&my->st_cnt, TS_AGG);
+            }
+            lookback_sum(ts, tix, req.tile0, lane, pc, pa);
+            if (lane == 0) {
+                my->cnt_pre = pc + ta;
+                my->aux_pre = pa + tb;
+                ts_publish(&my->st_cnt, TS_PREFIX);
             }
         }
-        pos++;
-        off += sz[k];
-    }
-}
-
-// ordered delete calls (compact): per record [superseded prev] [tombstone] [revision record] | [ttl]
-__global__ void __launch_bounds__(256)
-k_place_victims(const ReqDev *__restrict__ reqs, const TileDev *__restrict__ tiles,
-                const uint32_t *__restrict__ meta, const uint32_t *__restrict__ tgt,
-                const uint64_t *__restrict__ tscan, uint32_t *__restrict__ vidx, uint8_t *__restrict__ vcls)
-{
-    __shared__ uint64_t ws2[18];
-    const TileDev tile = tiles[blockIdx.x];
-    const ReqDev req = reqs[tile.req];
-    const uint32_t base = threadIdx.x * 4;
-    const uint32_t flat = tile.flat0 + base;
-    uint32_t t[4], w[4];
-    uint64_t cnt = 0;
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-        t[k] = KB_NONE;
-        w[k] = 0;
-        if (base + k < tile.n) {
-            t[k] = tgt[flat + k];
-            w[k] = meta[flat + k];
-            if (t[k] != KB_NONE) cnt++;
-            if ((w[k] & KB_M_TRIG) && (w[k] & KB_M_TOMB)) cnt++;
-            if (w[k] & KB_M_REVDEL) cnt++;
-            if (w[k] & (KB_M_TTLREV | KB_M_TTLOBJ)) cnt++;
+        if (lane == 0) {
+            pre_s[0] = pc;
+            pre_s[1] = pa;
+            if (last_tile) {  // inclusive prefix of the request's last tile = the request's totals
+                rout[tile.req].total = pc + ta;
+                rout[tile.req].total_aux = pa + tb;
+            }
         }
     }
-    uint64_t ea, eb, ta, tb;
-    block_excl_scan2(cnt, 0, ea, eb, ta, tb, ws2);
-    uint64_t pos = req.sel_base + tscan[2 * blockIdx.x] - tscan[2 * req.tile0] + ea;
+    __syncthreads();
+    if (!with_place) return;
+    uint64_t pos = pre_s[0] + ea;
+    if (COMPACT) {
+        // ordered delete calls: per record [superseded prev] [tombstone] [revision record] | [ttl]
+        pos += req.sel_base;
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
-        if (base + k >= tile.n) break;
-        const uint32_t irec = req.lo + (flat + k - req.flat0);
-        if (t[k] != KB_NONE) {
-            vidx[pos] = req.lo + (t[k] - req.flat0);
-            vcls[pos++] = KB_V_SUPERSEDED;
+        for (int k = 0; k < 4; k++) {
+            if (base + k >= tile.n) break;
+            const uint32_t irec = req.lo + (flat + k - req.flat0);
+            if (t[k] != KB_NONE) {
+                vidx[pos] = req.lo + (t[k] - req.flat0);
+                vcls[pos++] = KB_V_SUPERSEDED;
+            }
+            if ((w[k] & KB_M_TRIG) && (w[k] & KB_M_TOMB)) {
+                vidx[pos] = irec;
+                vcls[pos++] = KB_V_TOMBSTONE;
+            }
+            if (w[k] & KB_M_REVDEL) {
+                vidx[pos] = irec;
+                vcls[pos++] = KB_V_REVRECORD;
+            }
+            if (w[k] & KB_M_TTLREV) {
+                vidx[pos] = irec;
+                vcls[pos++] = KB_V_TTL_REVREC;
+            }
+            if (w[k] & KB_M_TTLOBJ) {
+                vidx[pos] = irec;
+                vcls[pos++] = KB_V_TTL_OBJECT;
+            }
         }
-        if ((w[k] & KB_M_TRIG) && (w[k] & KB_M_TOMB)) {
-            vidx[pos] = irec;
-            vcls[pos++] = KB_V_TOMBSTONE;
-        }
-        if (w[k] & KB_M_REVDEL) {
-            vidx[pos] = irec;
-            vcls[pos++] = KB_V_REVRECORD;
-        }
-        if (w[k] & KB_M_TTLREV) {
-            vidx[pos] = irec;
-            vcls[pos++] = KB_V_TTL_REVREC;
-        }
-        if (w[k] & KB_M_TTLOBJ) {
-            vidx[pos] = irec;
-            vcls[pos++] = KB_V_TTL_OBJECT;
+    } else {
+        // ordered selection: position = emissions before it in the request; the first `limit` positions are kept
+        // (commonResultReceiver.needMore, receiver.go:82-87)
+        uint64_t off = pre_s[1] + eb;
+        const bool limited = req.limit > 0;
+#pragma unroll
+        for (int k = 0; k < 5; k++) {
+            if (t[k] == KB_NONE) continue;
+            if (!limited || pos < (uint64_t)req.limit) {
+                sel[req.sel_base + pos] = req.lo + (t[k] - req.flat0);
+                slot[req.sel_base + pos] = off;
+                if (limited && pos == (uint64_t)req.limit - 1) {
+                    rout[tile.req].capped_aux = off + sz[k];
+                    uint32_t fl = KB_RO_CAPPED;
+                    if (k < 4) {
+                        // the limit-th append happened inside the loop: the iterator stops here (Q4)
+                        rout[tile.req].examined = (flat + k) - req.flat0 + 1;
+                        fl |= KB_RO_LIMIT_STOP;
+                    }
+                    rout[tile.req].flags = fl;
+                }
+            }
+            pos++;
+            off += sz[k];
         }
     }
 }
@@ -560,19 +596,11 @@ constexpr uint32_t GATHER_WARP_CHUNKS = 880;     // shared memory per warp (13.7
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-__device__ __forceinline__ void mbar_wait_parity(uint64_t *bar, uint32_t parity)
+// bounded like dmbar_wait (kb_decode.cuh): a bulk copy that faults never completes its barrier; give up after ~2 s of
+// polling and raise the context's error flag instead of hanging the stream
+__device__ __forceinline__ void mbar_wait_parity(uint64_t *bar, uint32_t parity, unsigned int *err_flag)
 {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "KB_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra KB_DONE;\n"
-        "bra KB_WAIT;\n"
-        "KB_DONE:\n"
-        "}\n" ::"r"(smem_u32(bar)),
-        "r"(parity)
-        : "memory");
+    dmbar_wait(bar, parity, err_flag);
 }
 
 // `piece` (chunks per ring buffer) and `stages` (buffers per warp) are chosen by the host from the store's largest
@@ -581,7 +609,8 @@ __device__ __forceinline__ void mbar_wait_parity(uint64_t *bar, uint32_t parity)
 // still busy with another stream's kernel -- simply takes fewer blocks.
 __global__ void __launch_bounds__(GATHER_WARPS * 32, 2)
 k_gather(StoreDev st, const GatherJob *__restrict__ jobs, const uint64_t *__restrict__ n_kvs_dev,
-         uint4 *__restrict__ arena, uint32_t piece, uint32_t stages, unsigned long long *__restrict__ work_ctr)
+         uint4 *__restrict__ arena, uint32_t piece, uint32_t stages, unsigned long long *__restrict__ work_ctr,
+         unsigned int *__restrict__ err_flag)
 {
     extern __shared__ __align__(128) uint4 gbuf[];  // GATHER_WARPS x stages x piece
     __shared__ uint64_t bars[GATHER_WARPS * GATHER_MAX_STAGES];
@@ -608,7 +637,7 @@ k_gather(StoreDev st, const GatherJob *__restrict__ jobs, const uint64_t *__rest
 
     // wait for the oldest in-flight piece and send it to the arena
     auto retire = [&]() {
-        mbar_wait_parity(bar + ss, ph);
+        mbar_wait_parity(bar + ss, ph, err_flag);
         asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(arena + rdst[ss]),
                      "r"(smem_u32(buf + ss * piece)), "r"(rlen[ss] * 16)
                      : "memory");
@@ -814,11 +843,13 @@ k_seg_copy(const uint4 *__restrict__ srcA, const uint4 *__restrict__ srcB, const
 // The per-request rows are the only thing the host needs before it can return a device-resident answer: the device
 // stores them into mapped pinned memory and then raises the epoch flag, the host polls the flag -- no copy, no stream
 // synchronisation, and the gather that follows keeps running after the call has returned.
-__device__ __forceinline__ void publish_rout(const ReqOut *__restrict__ rout, uint32_t nreq, uint8_t *host, uint64_t epoch)
+__device__ __forceinline__ void publish_rout(const ReqOut *__restrict__ rout, uint32_t nreq, uint8_t *host, uint64_t epoch,
+                                             const unsigned int *err_flag)
 {
     const uint4 *src = (const uint4 *)rout;
     uint4 *dst = (uint4 *)(host + 64);
     for (uint32_t i = threadIdx.x; i < nreq * 2; i += blockDim.x) dst[i] = src[i];
+    if (threadIdx.x == 0) *(volatile uint64_t *)(host + 8) = *err_flag;  // a bulk copy of this batch never completed
     __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -828,9 +859,9 @@ __device__ __forceinline__ void publish_rout(const ReqOut *__restrict__ rout, ui
 }
 
 __global__ void __launch_bounds__(256) k_publish_rout(const ReqOut *__restrict__ rout, uint32_t nreq, uint8_t *host,
-                                                      uint64_t epoch)
+                                                      uint64_t epoch, const unsigned int *err_flag)
 {
-    publish_rout(rout, nreq, host, epoch);
+    publish_rout(rout, nreq, host, epoch, err_flag);
 }
 
 // single CTA: per-request emitted count / response bytes (limit applied) and their exclusive prefixes over the
@@ -838,7 +869,8 @@ __global__ void __launch_bounds__(256) k_publish_rout(const ReqOut *__restrict__
 __global__ void __launch_bounds__(256)
 k_req_finalize(const ReqDev *__restrict__ reqs, uint32_t nreq, const ReqOut *__restrict__ rout,
                uint64_t *__restrict__ job_first, uint64_t *__restrict__ arena_base,
-               unsigned long long *__restrict__ work_ctr, uint8_t *host_rout, uint64_t epoch)
+               unsigned long long *__restrict__ work_ctr, uint8_t *host_rout, uint64_t epoch,
+               const unsigned int *__restrict__ err_flag)
 {
     if (threadIdx.x == 0) *work_ctr = 0;  // the gather's block counter
     __shared__ uint64_t ws2[18];
@@ -852,7 +884,7 @@ k_req_finalize(const ReqDev *__restrict__ reqs, uint32_t nreq, const ReqOut *__r
             const ReqOut o = rout[q];
             const int64_t lim = reqs[q].limit;
             ne = (lim > 0 && o.total > (uint64_t)lim) ? (uint64_t)lim : o.total;
-            nb = lim > 0 ? o.capped_aux : o.total_aux;
+            nb = (lim > 0 && (o.flags & KB_RO_CAPPED)) ? o.capped_aux : o.total_aux;
         }
         uint64_t ea, eb, ta, tb;
         block_excl_scan2(ne, nb, ea, eb, ta, tb, ws2);
@@ -872,7 +904,7 @@ k_req_finalize(const ReqDev *__restrict__ reqs, uint32_t nreq, const ReqOut *__r
         job_first[nreq] = carry[0];
         arena_base[nreq] = carry[1];
     }
-    publish_rout(rout, nreq, host_rout, epoch);
+    publish_rout(rout, nreq, host_rout, epoch, err_flag);
 }
 
 }  // namespace
@@ -1032,10 +1064,8 @@ int upload_layout(kb_ctx *ctx, const Resolved &R)
     ctx->d_tiles.p = (uint8_t *)ctx->d_reqs.p + req_bytes;  // alias into d_reqs (never freed on its own)
     ctx->d_tiles.cap = 0;
     KB_TRY(dbuf_ensure(ctx, ctx->d_meta, std::max<uint64_t>(R.total_flat, 4) * 4));
-    KB_TRY(dbuf_ensure(ctx, ctx->d_tgt, std::max<uint64_t>(R.total_flat, 4) * 4 + nreq * 4 + 16));
-    KB_TRY(dbuf_ensure(ctx, ctx->d_agg, std::max<size_t>(nt, 1) * 32 * 8));  // one aggregate per 32-record sub-tile
-    KB_TRY(dbuf_ensure(ctx, ctx->d_tcnt, std::max<size_t>(nt, 1) * 16));
-    KB_TRY(dbuf_ensure(ctx, ctx->d_tscan, (nt + 1) * 16));
+    // look-back states of k_emit_place: [ticket, padded to 64 bytes][one TileState per tile]
+    KB_TRY(dbuf_ensure(ctx, ctx->d_tcnt, 64 + std::max<size_t>(nt, 1) * sizeof(TileState)));
     KB_TRY(dbuf_ensure(ctx, ctx->d_reqout, std::max<size_t>(nreq, 1) * sizeof(ReqOut)));
     // pinned staging so the async copies really are asynchronous
     const size_t bytes = req_bytes + nt * sizeof(TileDev);
@@ -1052,25 +1082,43 @@ int upload_layout(kb_ctx *ctx, const Resolved &R)
 // host copy of the slab offsets, kept for algorithmic-byte accounting only
 static inline std::vector<uint32_t> &host_koff16(kb_ctx *ctx) { return ctx->h_koff16; }
 
-// persistent decode pass: one CTA per SM, DECODE_WARPS independent warps each
-static int launch_decode(kb_ctx *ctx, uint32_t ntiles, uint64_t alg_bytes, const ScanMode &mode, const ReqDev *d_reqs,
-                         const TileDev *d_tiles, uint32_t *d_meta, uint2 *d_agg)
+// persistent decode pass: one CTA per SM, independent warps; geometry from the store's longest key (kb_decode.cuh)
+template <int MAXW, int KK>
+static int launch_decode_t(kb_ctx *ctx, const DecGeom &g, size_t smem, uint64_t alg_bytes, const ScanMode &mode,
+                           const TileDev *d_tiles, uint32_t *d_meta)
 {
-    const size_t smem = ((size_t)DECODE_WARPS * DECODE_STAGES * KB_WARP_STAGE_CHUNKS + 4) * 16;
-    if (!ctx->decode_attr_set) {
-        KB_CUDA(ctx, cudaFuncSetAttribute(k_decode_lcp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        ctx->decode_attr_set = true;
+    static thread_local int attr_dev = -1;
+    static thread_local size_t attr_smem = 0;
+    if (attr_dev != ctx->device || attr_smem < smem) {
+        KB_CUDA(ctx, cudaFuncSetAttribute(k_decode_lcp<MAXW, KK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024 - 2048)));
+        attr_dev = ctx->device;
+        attr_smem = 227 * 1024 - 2048;
     }
-    if (!ctx->d_ctrs.p) {  // work counters: zero once, every consumer leaves them at zero
-        KB_TRY(dbuf_ensure(ctx, ctx->d_ctrs, 256));
-        KB_CUDA(ctx, cudaMemsetAsync(ctx->d_ctrs.p, 0, 256, ctx->stream));
-    }
-    const uint32_t n_sub = ntiles * 32;
-    const uint32_t grid = std::min<uint32_t>((n_sub + DECODE_WARPS - 1) / DECODE_WARPS, 148);
+    const uint32_t grid = std::min<uint32_t>((g.n_blocks + g.warps - 1) / g.warps, 148);
+    unsigned int *ctrs = (unsigned int *)ctx->d_ctrs.p;
     KB_LAUNCH(ctx, "k_decode_lcp", alg_bytes,
-              (k_decode_lcp<<<grid, DECODE_WARPS * 32, smem, ctx->stream>>>(ctx->st, d_reqs, d_tiles, n_sub, mode, d_meta,
-                                                                          d_agg, (unsigned int *)ctx->d_ctrs.p)));
+              (k_decode_lcp<MAXW, KK><<<grid, g.warps * 32, smem, ctx->stream>>>(ctx->st, d_tiles, g, mode, d_meta, ctrs, ctrs + 8)));
     return KB_OK;
+}
+
+static int launch_decode(kb_ctx *ctx, uint32_t ntiles, uint64_t alg_bytes, const ScanMode &mode, const TileDev *d_tiles,
+                         uint32_t *d_meta)
+{
+    static const uint32_t force_k = getenv("KB_DECODE_K") ? (uint32_t)atoi(getenv("KB_DECODE_K")) : 0;
+    static const uint32_t force_w = getenv("KB_DECODE_WARPS") ? (uint32_t)atoi(getenv("KB_DECODE_WARPS")) : 0;
+    size_t smem = 0;
+    const DecGeom g = decode_geometry(ctx->max_key_chunks, ntiles, force_k, force_w, &smem);
+#define KB_DEC_K(W)                                                                                     \
+    switch (g.K) {                                                                                      \
+    case 1: return launch_decode_t<W, 1>(ctx, g, smem, alg_bytes, mode, d_tiles, d_meta);               \
+    case 2: return launch_decode_t<W, 2>(ctx, g, smem, alg_bytes, mode, d_tiles, d_meta);               \
+    case 3: return launch_decode_t<W, 3>(ctx, g, smem, alg_bytes, mode, d_tiles, d_meta);               \
+    default: return launch_decode_t<W, 4>(ctx, g, smem, alg_bytes, mode, d_tiles, d_meta);              \
+    }
+    if (g.warps <= 12) { KB_DEC_K(12) }
+    if (g.warps <= 16) { KB_DEC_K(16) }
+    KB_DEC_K(24)
+#undef KB_DEC_K
 }
 
 // bulk-TMA gather of `n_jobs` (upper bound) copy jobs into `arena`
@@ -1088,47 +1136,49 @@ static int launch_gather(kb_ctx *ctx, cudaStream_t strm, const GatherJob *d_jobs
     const unsigned ggrid =
         (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((n_jobs + GATHER_WARPS * 32 - 1) / (GATHER_WARPS * 32), 2 * 148));
     KB_LAUNCH_S(ctx, strm, "k_gather", alg_bytes,
-                (k_gather<<<ggrid, GATHER_WARPS * 32, gsmem, strm>>>(ctx->st, d_jobs, d_njobs, arena, piece, stages, d_ctr)));
+                (k_gather<<<ggrid, GATHER_WARPS * 32, gsmem, strm>>>(ctx->st, d_jobs, d_njobs, arena, piece, stages, d_ctr,
+                                                                     (unsigned int *)ctx->d_ctrs.p + 8)));
     return KB_OK;
 }
 
-// decode -> emit -> tile scan -> (place) for an uploaded layout; everything stays enqueued on ctx->stream
-static int launch_scan_core(kb_ctx *ctx, const Resolved &R, const ScanMode &mode, bool with_place)
+// decode -> emit/place for an uploaded layout; everything stays enqueued on ctx->stream.  Range: the selection goes to
+// ctx->d_sel / d_slot; compact: the delete calls go to vidx / vcls (capacity 2 per examined record).
+static int launch_scan_core(kb_ctx *ctx, const Resolved &R, const ScanMode &mode, bool with_place,
+                            uint32_t *vidx = nullptr, uint8_t *vcls = nullptr)
 {
     const uint32_t nt = (uint32_t)R.tiles.size();
     const uint32_t nreq = (uint32_t)R.reqs.size();
     const ReqDev *d_reqs = (const ReqDev *)ctx->d_reqs.p;
     const TileDev *d_tiles = (const TileDev *)ctx->d_tiles.p;
     uint32_t *d_meta = (uint32_t *)ctx->d_meta.p;
-    uint32_t *d_tgt = (uint32_t *)ctx->d_tgt.p;
-    uint32_t *d_tail = d_tgt + std::max<uint64_t>(R.total_flat, 4);
-    uint2 *d_agg = (uint2 *)ctx->d_agg.p;
-    uint64_t *d_tcnt = (uint64_t *)ctx->d_tcnt.p;
-    uint64_t *d_tscan = (uint64_t *)ctx->d_tscan.p;
+    unsigned int *d_ticket = (unsigned int *)ctx->d_tcnt.p;
+    TileState *d_ts = (TileState *)((uint8_t *)ctx->d_tcnt.p + 64);
     ReqOut *d_rout = (ReqOut *)ctx->d_reqout.p;
     // algorithmic bytes of the decode pass: key bytes of the examined records + 10 B of offsets/lengths each
     uint64_t kbytes = 0;
     for (auto &r : R.reqs)
         kbytes += (uint64_t)(ctx->h_koff16[r.hi] - ctx->h_koff16[r.lo]) * 16 + (uint64_t)(r.hi - r.lo) * 10;
-    if (nt) {
-        KB_TRY(launch_decode(ctx, nt, kbytes, mode, d_reqs, d_tiles, d_meta, d_agg));
-        if (mode.compact) {
-            KB_LAUNCH(ctx, "k_emit_compact", R.n_records * 8,
-                      (k_emit<true><<<nt, 256, 0, ctx->stream>>>(ctx->st, d_reqs, d_tiles, d_agg, d_meta, d_tgt, d_tail,
-                                                                d_tcnt, 0, (unsigned int *)ctx->d_ctrs.p)));
-        } else {
-            KB_LAUNCH(ctx, "k_emit", R.n_records * 8,
-                      (k_emit<false><<<nt, 256, 0, ctx->stream>>>(ctx->st, d_reqs, d_tiles, d_agg, d_meta, d_tgt, d_tail,
-                                                                 d_tcnt, mode.wire, (unsigned int *)ctx->d_ctrs.p)));
-        }
+    if (!ctx->d_ctrs.p) {  // work counters [0..7] + error flag [8]: zero once, every consumer leaves the counters at zero
+        KB_TRY(dbuf_ensure(ctx, ctx->d_ctrs, 256));
+        KB_CUDA(ctx, cudaMemsetAsync(ctx->d_ctrs.p, 0, 256, ctx->stream));
     }
-    KB_LAUNCH(ctx, "k_tile_scan", (uint64_t)nt * 32,
-              (k_tile_scan<<<1, 256, 0, ctx->stream>>>(d_reqs, nreq, d_tcnt, d_tscan, nt, d_rout)));
-    if (nt && with_place) {
-        KB_LAUNCH(ctx, "k_place", R.n_records * 4,
-                  (k_place<<<nt, 256, 0, ctx->stream>>>(ctx->st, d_reqs, d_tiles, d_tgt, d_tail, d_tscan,
-                                                        (uint32_t *)ctx->d_sel.p, (uint64_t *)ctx->d_slot.p, d_rout,
-                                                        mode.wire)));
+    // request rows start at zero (empty requests are never written); look-back states and the ticket start empty
+    KB_CUDA(ctx, cudaMemsetAsync(d_rout, 0, std::max<size_t>(nreq, 1) * sizeof(ReqOut), ctx->stream));
+    if (nt) {
+        KB_CUDA(ctx, cudaMemsetAsync(ctx->d_tcnt.p, 0, 64 + (size_t)nt * sizeof(TileState), ctx->stream));
+        KB_TRY(launch_decode(ctx, nt, kbytes, mode, d_tiles, d_meta));
+        if (mode.compact) {
+            KB_LAUNCH(ctx, "k_emit_place_compact", R.n_records * 6,
+                      (k_emit_place<true><<<nt, 256, 0, ctx->stream>>>(ctx->st, d_reqs, d_tiles, d_meta, d_ts, d_ticket, nullptr,
+                                                                      nullptr, vidx, vcls, d_rout, 0, with_place ? 1 : 0,
+                                                                      (unsigned int *)ctx->d_ctrs.p)));
+        } else {
+            KB_LAUNCH(ctx, "k_emit_place", R.n_records * 6,
+                      (k_emit_place<false><<<nt, 256, 0, ctx->stream>>>(ctx->st, d_reqs, d_tiles, d_meta, d_ts, d_ticket,
+                                                                       (uint32_t *)ctx->d_sel.p, (uint64_t *)ctx->d_slot.p,
+                                                                       nullptr, nullptr, d_rout, mode.wire, with_place ? 1 : 0,
+                                                                       (unsigned int *)ctx->d_ctrs.p)));
+        }
     }
     KB_CUDA(ctx, cudaGetLastError());
     return KB_OK;
@@ -1180,7 +1230,7 @@ static int probe_limit_windows(kb_ctx *ctx, Resolved &R)
         std::vector<Todo> next;
         for (size_t i = 0; i < todo.size(); i++) {
             ReqDev &r = R.reqs[todo[i].q];
-            if (ro[i].limit_stop)
+            if (ro[i].flags & KB_RO_LIMIT_STOP)
                 r.hi = r.lo + ro[i].examined;  // exactly the records the reference's loop pulled
             else if (P.reqs[i].hi != todo[i].true_hi)
                 next.push_back(Todo{todo[i].q, todo[i].true_hi, todo[i].w * 8});
@@ -1325,7 +1375,8 @@ extern "C" int kb_range_batch(kb_ctx *ctx, const kb_range_req *reqs, uint64_t nr
         KB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_gather[set], 0));
         KB_LAUNCH(ctx, "k_req_finalize", nreq * 64,
                   (k_req_finalize<<<1, 256, 0, ctx->stream>>>(d_reqs, (uint32_t)nreq, d_rout, d_jobfirst, d_arenabase,
-                                                              d_workctr, ctx->h_rout, epoch)));
+                                                              d_workctr, ctx->h_rout, epoch,
+                                                              (const unsigned int *)ctx->d_ctrs.p + 8)));
         const unsigned jgrid = (unsigned)std::min<uint64_t>((cap_kvs + 255) / 256, 148 * 8);
         if (wire) {
             WireOut wo;
@@ -1355,7 +1406,8 @@ extern "C" int kb_range_batch(kb_ctx *ctx, const kb_range_req *reqs, uint64_t nr
                 (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((cap_kvs + WIRE_WARPS - 1) / WIRE_WARPS, 2 * 148));
             KB_LAUNCH_S(ctx, sg, "k_wire_copy", 0,
                         (k_wire_copy<<<wgrid, WIRE_WARPS * 32, wsmem, sg>>>(ctx->st, d_wj, d_jobfirst + nreq,
-                                                                          (uint8_t *)res->d_bytes.p, slot_chunks, wstages)));
+                                                                          (uint8_t *)res->d_bytes.p, slot_chunks, wstages,
+                                                                          (unsigned int *)ctx->d_ctrs.p + 8)));
         } else {
             GatherJob *d_gj = (GatherJob *)gb.p;
             KB_LAUNCH(ctx, "k_gather_jobs", cap_kvs * 20,
@@ -1380,12 +1432,15 @@ extern "C" int kb_range_batch(kb_ctx *ctx, const kb_range_req *reqs, uint64_t nr
     std::vector<ReqOut> rout(std::max<uint64_t>(nreq, 1));
     if (!want_kvs && nreq) {  // count-only / empty answers: nothing ran k_req_finalize, publish the rows directly
         KB_LAUNCH(ctx, "k_publish_rout", nreq * 32,
-                  (k_publish_rout<<<1, 256, 0, ctx->stream>>>(d_rout, (uint32_t)nreq, ctx->h_rout, epoch)));
+                  (k_publish_rout<<<1, 256, 0, ctx->stream>>>(d_rout, (uint32_t)nreq, ctx->h_rout, epoch,
+                                                              (const unsigned int *)ctx->d_ctrs.p + 8)));
     }
     kb_seg(ctx, "host:range_launch", tseg);
     if (nreq) {
         KB_TRY(rout_wait(ctx, epoch));
         memcpy(rout.data(), ctx->h_rout + 64, nreq * sizeof(ReqOut));
+        if (*(volatile uint64_t *)(ctx->h_rout + 8) != 0)
+            return kb_fail(ctx, KB_ECUDA, "range scan: a bulk copy of the decode pass never completed");
     }
     kb_seg(ctx, "host:range_sync", tseg);
 
@@ -1402,10 +1457,11 @@ extern "C" int kb_range_batch(kb_ctx *ctx, const kb_range_req *reqs, uint64_t nr
             res->req_count[q] = rout[q].total;  // emptyResultReceiver never stops the loop
             res->req_examined[q] = R.reqs[q].hi - R.reqs[q].lo;
         } else {
-            res->req_count[q] = rout[q].limit_stop ? 0 : ne;  // (0, nil) when the limit stopped the loop (Q4)
-            res->req_examined[q] = rout[q].examined;
+            const bool stop = rout[q].flags & KB_RO_LIMIT_STOP;
+            res->req_count[q] = stop ? 0 : ne;  // (0, nil) when the limit stopped the loop (Q4)
+            res->req_examined[q] = stop ? rout[q].examined : R.reqs[q].hi - R.reqs[q].lo;
             nk += ne;
-            nbytes += R.reqs[q].limit > 0 ? rout[q].capped_aux : rout[q].total_aux;
+            nbytes += (R.reqs[q].limit > 0 && (rout[q].flags & KB_RO_CAPPED)) ? rout[q].capped_aux : rout[q].total_aux;
         }
     }
     res->req_first[nreq] = nk;
@@ -1764,37 +1820,40 @@ extern "C" int kb_compact_sweep(kb_ctx *ctx, const uint8_t *start, uint64_t star
     Resolved R;
     KB_TRY(resolve_requests(ctx, &rq, 1, false, R));
     KB_TRY(upload_layout(ctx, R));
-    const uint32_t nt = (uint32_t)R.tiles.size();
-    const ReqDev *d_reqs = (const ReqDev *)ctx->d_reqs.p;
-    const TileDev *d_tiles = (const TileDev *)ctx->d_tiles.p;
-    uint32_t *d_meta = (uint32_t *)ctx->d_meta.p;
-    uint32_t *d_tgt = (uint32_t *)ctx->d_tgt.p;
-    uint32_t *d_tail = d_tgt + std::max<uint64_t>(R.total_flat, 4);
-    uint2 *d_agg = (uint2 *)ctx->d_agg.p;
-    uint64_t *d_tcnt = (uint64_t *)ctx->d_tcnt.p;
-    uint64_t *d_tscan = (uint64_t *)ctx->d_tscan.p;
     ReqOut *d_rout = (ReqOut *)ctx->d_reqout.p;
     ScanMode mode;
     mode.compact = 1;
     mode.ttl_scan = (!support_ttl && timeout_rev != 0) ? 1 : 0;
     mode.timeout_rev = timeout_rev;
     mode.wire = 0;
-    uint64_t kbytes = 0;
-    {
-        std::vector<uint32_t> &ko = host_koff16(ctx);
-        for (auto &r : R.reqs) kbytes += (uint64_t)(ko[r.hi] - ko[r.lo]) * 16 + (uint64_t)(r.hi - r.lo) * 10;
+    // One pass writes the ordered delete calls, so their buffer is sized before the count is known: a record is the
+    // target of at most two calls (superseded as somebody's prev + tombstone / deleted revision record at its own turn,
+    // or one TTL call).  The buffer is pooled; the host copy is cut to the real count.
+    kb_result *res = kb_result_new(2, out_mode);
+    const uint64_t nrec = R.n_records, cap_v = 2 * nrec;
+    uint32_t *vidx = nullptr;
+    uint8_t *vcls = nullptr;
+    if (out_mode != KB_OUT_COUNT && nrec) {
+        int rc = pool_get_dev(ctx, cap_v * 5 + 64, &res->d_vic);
+        if (rc != KB_OK) {
+            result_release_locked(ctx, res);
+            return rc;
+        }
+        vidx = (uint32_t *)res->d_vic.p;
+        vcls = (uint8_t *)(vidx + cap_v);
     }
-    if (nt) {
-        KB_TRY(launch_decode(ctx, nt, kbytes, mode, d_reqs, d_tiles, d_meta, d_agg));
-        KB_LAUNCH(ctx, "k_emit_compact", R.n_records * 8,
-                  (k_emit<true><<<nt, 256, 0, ctx->stream>>>(ctx->st, d_reqs, d_tiles, d_agg, d_meta, d_tgt, d_tail,
-                                                            d_tcnt, 0, (unsigned int *)ctx->d_ctrs.p)));
+    int rc = launch_scan_core(ctx, R, mode, vidx != nullptr, vidx, vcls);
+    if (rc == KB_OK) rc = hbuf_ensure(ctx, ctx->h_stage, sizeof(ReqOut) + 64);
+    if (rc == KB_OK && cudaMemcpyAsync(ctx->h_stage.p, d_rout, sizeof(ReqOut), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess)
+        rc = kb_fail(ctx, KB_ECUDA, "compact sweep: D2H");
+    if (rc == KB_OK) {
+        cudaError_t e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) rc = kb_cuda_fail(ctx, e, "compact sweep");
     }
-    KB_LAUNCH(ctx, "k_tile_scan", (uint64_t)nt * 32,
-              (k_tile_scan<<<1, 256, 0, ctx->stream>>>(d_reqs, 1u, d_tcnt, d_tscan, nt, d_rout)));
-    KB_TRY(hbuf_ensure(ctx, ctx->h_stage, sizeof(ReqOut) + 64));
-    KB_CUDA(ctx, cudaMemcpyAsync(ctx->h_stage.p, d_rout, sizeof(ReqOut), cudaMemcpyDeviceToHost, ctx->stream));
-    KB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (rc != KB_OK) {
+        result_release_locked(ctx, res);
+        return rc;
+    }
     ReqOut ro;
     memcpy(&ro, ctx->h_stage.p, sizeof(ro));
 
@@ -1802,36 +1861,27 @@ extern "C" int kb_compact_sweep(kb_ctx *ctx, const uint8_t *start, uint64_t star
     ctx->compact_present = true;
     ctx->compact_rev = rev;
 
-    kb_result *res = kb_result_new(2, out_mode);
     res->n_victims = ro.total;
     res->count = ro.total_aux;
     res->examined = R.reqs[0].hi - R.reqs[0].lo;
-    if (out_mode != KB_OUT_COUNT && ro.total > 0) {
+    res->vic_cap = cap_v;
+    if (out_mode == KB_OUT_HOST && ro.total > 0) {
         const uint64_t nv = ro.total;
-        int rc = pool_get_dev(ctx, nv * 5 + 64, &res->d_vic);
+        rc = pool_get_host(ctx, nv * 5 + 64, &res->h_vic);
+        if (rc == KB_OK) {
+            cudaMemcpyAsync(res->h_vic.p, vidx, nv * 4, cudaMemcpyDeviceToHost, ctx->stream);
+            cudaMemcpyAsync((uint8_t *)res->h_vic.p + nv * 4, vcls, nv, cudaMemcpyDeviceToHost, ctx->stream);
+            cudaError_t e = cudaStreamSynchronize(ctx->stream);
+            if (e != cudaSuccess) rc = kb_cuda_fail(ctx, e, "compact sweep: victims D2H");
+        }
         if (rc != KB_OK) {
             result_release_locked(ctx, res);
             return rc;
         }
-        uint32_t *vidx = (uint32_t *)res->d_vic.p;
-        uint8_t *vcls = (uint8_t *)(vidx + nv);
-        // sel_base of the single request is 0
-        KB_LAUNCH(ctx, "k_place_victims", R.n_records * 8 + nv * 5,
-                  (k_place_victims<<<nt, 256, 0, ctx->stream>>>(d_reqs, d_tiles, d_meta, d_tgt, d_tscan, vidx, vcls)));
-        if (out_mode == KB_OUT_HOST) {
-            rc = pool_get_host(ctx, nv * 5 + 64, &res->h_vic);
-            if (rc == KB_OK) cudaMemcpyAsync(res->h_vic.p, res->d_vic.p, nv * 5, cudaMemcpyDeviceToHost, ctx->stream);
-        }
-        cudaError_t e = cudaStreamSynchronize(ctx->stream);
-        if (rc == KB_OK && e != cudaSuccess) rc = kb_cuda_fail(ctx, e, "compact sweep");
-        if (rc != KB_OK) {
-            result_release_locked(ctx, res);
-            return rc;
-        }
-        if (out_mode == KB_OUT_HOST) {
-            pool_put_dev(ctx, res->d_vic);
-            res->d_vic = DBuf();
-        }
+    }
+    if (out_mode != KB_OUT_DEVICE && res->d_vic.p) {
+        pool_put_dev(ctx, res->d_vic);
+        res->d_vic = DBuf();
     }
     *out = res;
     return KB_OK;
@@ -1848,7 +1898,8 @@ extern "C" int kb_compact_view_get(const kb_result *res, kb_compact_view *v)
     const uint8_t *base = v->on_device ? (const uint8_t *)res->d_vic.p : (const uint8_t *)res->h_vic.p;
     if (base && res->out_mode != KB_OUT_COUNT) {
         v->victim_idx = (const uint32_t *)base;
-        v->victim_class = base + res->n_victims * 4;
+        // device-resident answers keep the capacity-sized layout the sweep wrote into; the host copy is compact
+        v->victim_class = base + (v->on_device ? res->vic_cap : res->n_victims) * 4;
     }
     return KB_OK;
 }
@@ -2002,6 +2053,7 @@ extern "C" int kb_apply_batch(kb_ctx *ctx, const kb_write_op *ops, uint64_t n_op
             push_pieces(kp, op_k16[i], kacc, nk, 1);
             push_pieces(vp, op_v16[i], vacc, nv, 1);
             ctx->max_kv_chunks = std::max<uint32_t>(ctx->max_kv_chunks, (uint32_t)std::min<uint64_t>(nk + nv, 0xFFFFFFFFu));
+            ctx->max_key_chunks = std::max<uint32_t>(ctx->max_key_chunks, (uint32_t)nk);
             koff2[w] = (uint32_t)kacc;
             voff2[w] = vacc;
             klen2[w] = (uint16_t)m[i].key.size();

@@ -335,19 +335,9 @@ __device__ __forceinline__ void wire_emit_element(const uint4 &loc, const uint4 
 
 __device__ __forceinline__ uint32_t wsmem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-__device__ __forceinline__ void wmbar_wait(uint64_t *bar, uint32_t parity)
+__device__ __forceinline__ void wmbar_wait(uint64_t *bar, uint32_t parity, unsigned int *err_flag)
 {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "KBW_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra KBW_DONE;\n"
-        "bra KBW_WAIT;\n"
-        "KBW_DONE:\n"
-        "}\n" ::"r"(wsmem_u32(bar)),
-        "r"(parity)
-        : "memory");
+    dmbar_wait(bar, parity, err_flag);  // bounded: see kb_decode.cuh
 }
 
 constexpr int WIRE_MAX_STAGES = 8;
@@ -362,7 +352,7 @@ constexpr uint32_t WIRE_WARP_CHUNKS = 880;                  // shared memory per
 // too large for a slot is copied straight from the slab (wire_emit_element<false>).
 __global__ void __launch_bounds__(WIRE_WARPS * 32, 2)
 k_wire_copy(StoreDev st, const WireJob *__restrict__ jobs, const uint64_t *__restrict__ n_kvs_dev,
-            uint8_t *__restrict__ arena, uint32_t slot_chunks, uint32_t stages)
+            uint8_t *__restrict__ arena, uint32_t slot_chunks, uint32_t stages, unsigned int *__restrict__ err_flag)
 {
     extern __shared__ __align__(128) uint4 wbuf[];  // WIRE_WARPS x stages x slot_chunks
     __shared__ uint64_t wbars[WIRE_WARPS * WIRE_MAX_STAGES];
@@ -425,7 +415,7 @@ k_wire_copy(StoreDev st, const WireJob *__restrict__ jobs, const uint64_t *__res
             if (++s_issue == stages) s_issue = 0;
             k_issue += kstride;
         }
-        wmbar_wait(bar + s_proc, ph);
+        wmbar_wait(bar + s_proc, ph, err_flag);
         const uint4 *sl = ring + (size_t)s_proc * slot_chunks;
         const uint4 loc = sl[0], len = sl[1], h1a = sl[2], h1b = sl[3], h2a = sl[4], h2b = sl[5];
         const uint32_t nkc = (4 + len.y + 15) >> 4, nvc = (len.z + 15) >> 4;
