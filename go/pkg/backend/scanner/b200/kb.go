@@ -22,6 +22,7 @@ import (
 	"fmt"
 	"runtime"
 	"sync"
+	"time"
 	"unsafe"
 
 	proto "github.com/kubewharf/kubebrain-client/api/v2rpc"
@@ -53,11 +54,55 @@ func (e *Engine) err(rc C.int) error {
 	return fmt.Errorf("kb_b200 %d: %s", int(rc), C.GoString(C.kb_last_error(e.ctx)))
 }
 
-// LoadSorted ingests a snapshot pulled from storage.Iter (ascending unique internal keys).
+// ptr8 / ptr64: the address of a slice's first element, or nil for an empty slice (&x[0] panics on those)
+func ptr8(b []byte) *C.uint8_t {
+	if len(b) == 0 {
+		return nil
+	}
+	return (*C.uint8_t)(unsafe.Pointer(&b[0]))
+}
+
+func ptr64(b []uint64) *C.uint64_t {
+	if len(b) == 0 {
+		return nil
+	}
+	return (*C.uint64_t)(unsafe.Pointer(&b[0]))
+}
+
+// Close releases the context; the Engine must not be used afterwards.
+func (e *Engine) Close() {
+	e.mu.Lock()
+	defer e.mu.Unlock()
+	if e.ctx != nil {
+		C.kb_close(e.ctx)
+		e.ctx = nil
+		runtime.SetFinalizer(e, nil)
+	}
+}
+
+// LoadSorted ingests a snapshot pulled from storage.Iter (ascending unique internal keys).  An empty engine
+// (len(keyOff) <= 1) loads an empty snapshot.
 func (e *Engine) LoadSorted(keys []byte, keyOff []uint64, vals []byte, valOff []uint64) error {
-	n := len(keyOff) - 1
-	return e.err(C.kb_load_sorted(e.ctx, (*C.uint8_t)(unsafe.Pointer(&keys[0])), (*C.uint64_t)(unsafe.Pointer(&keyOff[0])),
-		(*C.uint8_t)(unsafe.Pointer(&vals[0])), (*C.uint64_t)(unsafe.Pointer(&valOff[0])), C.uint64_t(n)))
+	n := 0
+	if len(keyOff) > 1 {
+		n = len(keyOff) - 1
+	}
+	zero := []uint64{0}
+	if n == 0 {
+		keyOff, valOff = zero, zero
+	}
+	e.mu.Lock()
+	defer e.mu.Unlock()
+	return e.err(C.kb_load_sorted(e.ctx, ptr8(keys), ptr64(keyOff), ptr8(vals), ptr64(valOff), C.uint64_t(n)))
+}
+
+// Expire drops every TTL'd record whose time has come from the mirror (kb_expire); returns how many.
+func (e *Engine) Expire(nowUnix uint64) (uint64, error) {
+	var n C.uint64_t
+	e.mu.Lock()
+	defer e.mu.Unlock()
+	rc := C.kb_expire(e.ctx, C.uint64_t(nowUnix), &n)
+	return uint64(n), e.err(rc)
 }
 
 // Dump / Restore persist the HBM snapshot (device layout, checksummed) so a restart need not re-iterate the engine.
@@ -75,8 +120,9 @@ func (e *Engine) Restore(path string) error {
 
 // WriteOp mirrors one Put/Del of a committed storage.BatchWrite (pkg/storage/interface.go:62-84).
 type WriteOp struct {
-	Del      bool
-	Key, Val []byte
+	Del        bool
+	Key, Val   []byte
+	ExpireUnix uint64 // puts with a ttl: wall-clock second at which the engine stops returning the key (0: never)
 }
 
 // ApplyBatch merges a committed batch into the HBM snapshot; the storage adaptor calls it after Commit succeeds.
@@ -103,16 +149,43 @@ func (e *Engine) ApplyBatch(ops []WriteOp) error {
 			raw[i].val = (*C.uint8_t)(unsafe.Pointer(&ops[i].Val[0]))
 		}
 		raw[i].val_len = C.uint64_t(len(ops[i].Val))
+		raw[i].expire_unix = C.uint64_t(ops[i].ExpireUnix)
 	}
+	e.mu.Lock()
+	defer e.mu.Unlock()
 	return e.err(C.kb_apply_batch(e.ctx, &raw[0], C.uint64_t(len(raw))))
 }
 
+// Metrics is the subset of pkg/metrics.Metrics the hot path emits (scanner.go:512-514, watcherhub.go:87).
+type Metrics interface {
+	EmitHistogram(name string, value interface{}, tags ...string) error
+	EmitCounter(name string, value interface{}, tags ...string) error
+}
+
 type b200Scanner struct {
-	e *Engine
+	e          *Engine
+	SupportTTL bool          // storage.KvStorage.SupportTTL() of the wrapped engine
+	TTL        time.Duration // scanner.Config.TTL (scanner.go:78-79)
+	metricCli  Metrics
+
+	histMu           sync.Mutex
+	compactHistories []compactRecord
 }
 
 // NewScanner replaces scanner.NewScanner at pkg/backend/backend.go:155.
-func NewScanner(e *Engine) scanner.Scanner { return &b200Scanner{e: e} }
+func NewScanner(e *Engine, supportTTL bool, ttl time.Duration, m Metrics) scanner.Scanner {
+	return &b200Scanner{e: e, SupportTTL: supportTTL, TTL: ttl, metricCli: m}
+}
+
+// emitScanMetrics: the three histograms worker.run emits when it finishes (scanner.go:512-514)
+func (s *b200Scanner) emitScanMetrics(latency time.Duration, valSize int, count int) {
+	if s.metricCli == nil {
+		return
+	}
+	_ = s.metricCli.EmitHistogram("storage.scan_worker.latency", latency.Seconds())
+	_ = s.metricCli.EmitHistogram("storage.scan_worker.size", valSize)
+	_ = s.metricCli.EmitHistogram("storage.scan_worker.count", count)
+}
 
 func (s *b200Scanner) rangeOnce(start, end []byte, revision uint64, limit int64, mode C.int) (*C.kb_result, C.kb_range_view, error) {
 	var req C.kb_range_req
@@ -166,34 +239,53 @@ func copyKvs(view C.kb_range_view) []*proto.KeyValue {
 }
 
 func (s *b200Scanner) Range(ctx context.Context, start, end []byte, revision uint64, limit int64) ([]*proto.KeyValue, error) {
+	t0 := time.Now()
 	res, view, err := s.rangeOnce(start, end, revision, limit, C.KB_OUT_HOST)
 	if err != nil {
 		return nil, err
 	}
 	defer C.kb_result_free(s.e.ctx, res)
-	return copyKvs(view), nil
+	kvs := copyKvs(view)
+	valSize := 0
+	for _, kv := range kvs {
+		valSize += len(kv.Value)
+	}
+	s.emitScanMetrics(time.Since(t0), valSize, int(*view.req_count))
+	return kvs, nil
 }
 
-// RangeResponseWire returns the serialised etcdserverpb.RangeResponse of a List (what backendShim.List builds per kv on
-// the CPU, pkg/server/etcd/backendshim.go:269-282): the kv elements are written by the device, head and tail added here.
-// The etcd gRPC handler sends it through a pass-through codec (grpc.PreparedMsg / encoding.Codec on []byte).
-func (s *b200Scanner) RangeResponseWire(start, end []byte, revision uint64, limit int64, headerRev uint64, more bool) ([]byte, error) {
-	res, view, err := s.rangeOnce(start, end, revision, limit, C.KB_OUT_HOST|C.KB_WIRE_ETCD_KVS)
+// RangeResponseWire returns the serialised etcdserverpb.RangeResponse of a List with the USER's limit (what
+// backendShim.List builds per kv on the CPU, pkg/server/etcd/backendshim.go:269-282).  Like backend.List it scans
+// limit+1 (pkg/backend/range.go:150-170), keeps the first `limit` kvs -- the arena is cut at elem_off[limit] -- and derives
+// More and Count from what it saw (count = len(kvs) + 1 when there is more, backendshim.go:269-277).  The kv elements are
+// written by the device, head and tail are added here.  The etcd gRPC handler sends it through a pass-through codec.
+func (s *b200Scanner) RangeResponseWire(start, end []byte, revision uint64, limit int64, headerRev uint64) ([]byte, error) {
+	ask := limit
+	if limit > 0 {
+		ask = limit + 1
+	}
+	res, view, err := s.rangeOnce(start, end, revision, ask, C.KB_OUT_HOST|C.KB_WIRE_ETCD_KVS)
 	if err != nil {
 		return nil, err
 	}
 	defer C.kb_result_free(s.e.ctx, res)
+	n, nbytes := int64(view.n_kvs), uint64(view.n_bytes)
+	more := limit > 0 && n > limit
+	if more {
+		n = limit
+		nbytes = unsafe.Slice((*uint64)(unsafe.Pointer(view.elem_off)), int(view.n_kvs)+1)[limit]
+	}
 	var head, tail [32]C.uint8_t
 	nh := C.kb_wire_range_head(C.uint64_t(headerRev), &head[0])
-	m, count := C.int(0), C.int64_t(view.n_kvs)
+	m, count := C.int(0), C.int64_t(n)
 	if more {
 		m, count = 1, count+1
 	}
 	nt := C.kb_wire_range_tail(m, count, &tail[0])
-	out := make([]byte, 0, int(nh)+int(view.n_bytes)+int(nt))
+	out := make([]byte, 0, int(nh)+int(nbytes)+int(nt))
 	out = append(out, C.GoBytes(unsafe.Pointer(&head[0]), C.int(nh))...)
-	if view.n_bytes > 0 {
-		out = append(out, unsafe.Slice((*byte)(unsafe.Pointer(view.bytes)), int(view.n_bytes))...)
+	if nbytes > 0 {
+		out = append(out, unsafe.Slice((*byte)(unsafe.Pointer(view.bytes)), int(nbytes))...)
 	}
 	out = append(out, C.GoBytes(unsafe.Pointer(&tail[0]), C.int(nt))...)
 	return out, nil
@@ -245,9 +337,8 @@ func (s *b200Scanner) Sweep(start, end []byte, revision, timeoutRevision uint64,
 		ttl = 1
 	}
 	s.e.mu.Lock()
-	rc := C.kb_compact_sweep(s.e.ctx, (*C.uint8_t)(unsafe.Pointer(&start[0])), C.uint64_t(len(start)),
-		(*C.uint8_t)(unsafe.Pointer(&end[0])), C.uint64_t(len(end)), C.uint64_t(revision), C.uint64_t(timeoutRevision),
-		ttl, C.KB_OUT_HOST, &res)
+	rc := C.kb_compact_sweep(s.e.ctx, ptr8(start), C.uint64_t(len(start)), ptr8(end), C.uint64_t(len(end)),
+		C.uint64_t(revision), C.uint64_t(timeoutRevision), ttl, C.KB_OUT_HOST, &res)
 	s.e.mu.Unlock()
 	if rc != 0 {
 		return nil, 0, s.e.err(rc)
@@ -267,12 +358,46 @@ func (s *b200Scanner) Sweep(start, end []byte, revision, timeoutRevision uint64,
 	return out, int(v.count), nil
 }
 
-// Apply is supplied by the storage adaptor: it deletes the victims in bulk (one engine batch instead of the
+// Apply is supplied by the storage adaptor: it deletes the victims in bulk (one engine batch per chunk instead of the
 // reference's one transaction per victim, scanner.go:538-564).
 var Apply func(ctx context.Context, victims []Victim) error
 
+// compactRecord / logCompactHistory / getTimeoutRevision: pkg/backend/scanner/compact.go:22-52, scanner.go:147-177.
+// Engines without TTL support (TiKV) expire /events/ keys through the compaction sweep: a key written before the compact
+// revision that is now older than cfg.TTL goes (scanner.go:566-591); engines with TTL never see a timeout revision.
+type compactRecord struct {
+	revision uint64
+	time     time.Time
+}
+
+func (s *b200Scanner) logCompactHistory(revision uint64) {
+	s.histMu.Lock()
+	s.compactHistories = append(s.compactHistories, compactRecord{revision, time.Now()})
+	s.histMu.Unlock()
+}
+
+func (s *b200Scanner) getTimeoutRevision() uint64 {
+	if s.SupportTTL {
+		return 0
+	}
+	s.histMu.Lock()
+	defer s.histMu.Unlock()
+	prev := uint64(0)
+	for len(s.compactHistories) > 0 && time.Since(s.compactHistories[0].time) >= s.TTL {
+		prev = s.compactHistories[0].revision
+		s.compactHistories = s.compactHistories[1:]
+	}
+	return prev
+}
+
 func (s *b200Scanner) Compact(ctx context.Context, start, end []byte, revision uint64) {
-	victims, _, err := s.Sweep(start, end, revision, 0, true)
+	s.logCompactHistory(revision)
+	if s.SupportTTL {
+		_, _ = s.e.Expire(uint64(time.Now().Unix())) // what the engine no longer returns must not be classified
+	}
+	t0 := time.Now()
+	victims, count, err := s.Sweep(start, end, revision, s.getTimeoutRevision(), s.SupportTTL)
+	s.emitScanMetrics(time.Since(t0), 0, count)
 	if err == nil && Apply != nil {
 		_ = Apply(ctx, victims)
 	}
@@ -283,10 +408,16 @@ var errNoWatchers = errors.New("no watchers")
 // Match replaces WatcherHub.Stream + processEvents for one collector batch run: it returns, per watcher id, the
 // indices of the events to deliver, in order (pkg/backend/watcherhub.go:78-92, watch.go:119-159).
 func (e *Engine) Match(keys []byte, keyOff, rev, batchOff []uint64) (start []uint64, eventIdx []uint32, err error) {
+	if len(rev) == 0 {
+		return nil, nil, nil // nothing to deliver
+	}
+	nb := 0
+	if len(batchOff) > 1 {
+		nb = len(batchOff) - 1
+	}
 	ev := C.kb_events{
-		keys: (*C.uint8_t)(unsafe.Pointer(&keys[0])), key_off: (*C.uint64_t)(unsafe.Pointer(&keyOff[0])),
-		rev: (*C.uint64_t)(unsafe.Pointer(&rev[0])), n: C.uint64_t(len(rev)),
-		batch_off: (*C.uint64_t)(unsafe.Pointer(&batchOff[0])), n_batches: C.uint64_t(len(batchOff) - 1),
+		keys: ptr8(keys), key_off: ptr64(keyOff), rev: ptr64(rev), n: C.uint64_t(len(rev)),
+		batch_off: ptr64(batchOff), n_batches: C.uint64_t(nb),
 	}
 	var res *C.kb_result
 	e.mu.Lock()
@@ -313,7 +444,8 @@ func (e *Engine) WatchAdd(prefix []byte, minRev uint64) (uint32, error) {
 	}
 	e.mu.Lock()
 	defer e.mu.Unlock()
-	return uint32(id), e.err(C.kb_watch_add(e.ctx, p, C.uint64_t(len(prefix)), C.uint64_t(minRev), &id))
+	rc := C.kb_watch_add(e.ctx, p, C.uint64_t(len(prefix)), C.uint64_t(minRev), &id) // call first: `id` is written by it
+	return uint32(id), e.err(rc)
 }
 
 func (e *Engine) WatchDel(id uint32) error {

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define KB_ABI_VERSION 1
+#define KB_ABI_VERSION 2  /* 2: kb_write_op.expire_unix, kb_expire, kb_cursor_transport / kb_cursor_force_nccl */
 
 typedef enum kb_status {
     KB_OK = 0,
@@ -86,8 +86,16 @@ typedef struct kb_write_op {
     uint32_t type;                              /* KB_OP_PUT / KB_OP_DEL */
     const uint8_t *key;  uint64_t key_len;
     const uint8_t *val;  uint64_t val_len;      /* ignored for KB_OP_DEL */
+    uint64_t expire_unix;                       /* KB_OP_PUT: 0 = never; else the wall-clock second at which the engine
+                                                   stops returning the key (the backend writes /events/ keys with a ttl,
+                                                   storage.BatchWrite.Put(key, val, ttl), badger WithTTL batch.go:47-93) */
 } kb_write_op;
 int kb_apply_batch(kb_ctx *ctx, const kb_write_op *ops, uint64_t n);
+/* TTL: engines with SupportTTL() (badger) never delete expired keys explicitly -- they just stop returning them.  The
+ * mirror keeps (expire_unix, key) of every TTL put and kb_expire removes from the snapshot every record whose time has
+ * come (one kb_apply_batch-style merge).  The storage adaptor calls it from a ticker and in front of every compaction, so
+ * the mirror lags the engine by at most one tick.  *n_dropped (optional) = records removed. */
+int kb_expire(kb_ctx *ctx, uint64_t now_unix, uint64_t *n_dropped);
 /* compact_key record used by checkCompactRace (scanner.go:594-626); present=0 clears it */
 int kb_set_compact_revision(kb_ctx *ctx, int present, uint64_t rev);
 

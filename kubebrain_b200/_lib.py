@@ -32,7 +32,7 @@ KB_OP_PUT, KB_OP_DEL = 0, 1
 
 ABI_SYMBOLS = [
     "kb_abi_version", "kb_open", "kb_close", "kb_last_error", "kb_stream", "kb_sync",
-    "kb_load_sorted", "kb_store_info", "kb_dump", "kb_restore", "kb_apply_batch", "kb_set_compact_revision",
+    "kb_load_sorted", "kb_store_info", "kb_dump", "kb_restore", "kb_apply_batch", "kb_expire", "kb_set_compact_revision",
     "kb_range_batch", "kb_range_view_get", "kb_result_wait", "kb_wire_range_head", "kb_wire_range_tail", "kb_wire_watch_head",
     "kb_get_batch", "kb_get_view_get",
     "kb_compact_sweep", "kb_compact_view_get",
@@ -70,7 +70,7 @@ class KbRangeView(C.Structure):
 
 class KbWriteOp(C.Structure):
     _fields_ = [("type", C.c_uint32), ("key", C.c_char_p), ("key_len", C.c_uint64), ("val", C.c_char_p),
-                ("val_len", C.c_uint64)]
+                ("val_len", C.c_uint64), ("expire_unix", C.c_uint64)]
 
 
 class KbGetReq(C.Structure):
@@ -157,6 +157,8 @@ def lib():
     L.kb_restore.argtypes = [vp, C.c_char_p]
     L.kb_apply_batch.argtypes = [vp, C.POINTER(KbWriteOp), C.c_uint64]
     L.kb_apply_batch.restype = C.c_int
+    L.kb_expire.restype = C.c_int
+    L.kb_expire.argtypes = [vp, C.c_uint64, u64p]
     L.kb_set_compact_revision.argtypes = [vp, C.c_int, C.c_uint64]
     L.kb_range_batch.restype = C.c_int
     L.kb_range_batch.argtypes = [vp, C.POINTER(KbRangeReq), C.c_uint64, C.c_int, C.POINTER(vp)]
@@ -458,16 +460,25 @@ class Engine:
         vd, vo, vp, vop = _slab_ptrs(store.vals)
         self._check(lib().kb_load_sorted(self._ctx, kp, kop, vp, vop, store.n))
 
-    def apply_batch(self, ops: Sequence[Tuple[bytes, Optional[bytes]]]):
+    def apply_batch(self, ops: Sequence[tuple]):
         """One committed BatchWrite (pkg/storage/interface.go:62-84): (internal_key, value) puts, (internal_key, None)
-        deletes, applied in order (the last op on a key wins)."""
+        deletes, applied in order (the last op on a key wins).  A put may carry a third element: the wall-clock second at
+        which the key expires (BatchWrite.Put(key, val, ttl) of a TTL engine)."""
         arr = (KbWriteOp * max(len(ops), 1))()
-        for i, (k, v) in enumerate(ops):
+        for i, op in enumerate(ops):
+            k, v = op[0], op[1]
             arr[i].type = KB_OP_DEL if v is None else KB_OP_PUT
             arr[i].key, arr[i].key_len = k, len(k)
             if v is not None:
                 arr[i].val, arr[i].val_len = v, len(v)
+                arr[i].expire_unix = int(op[2]) if len(op) > 2 and op[2] else 0
         self._check(lib().kb_apply_batch(self._ctx, arr, len(ops)))
+
+    def expire(self, now_unix: int) -> int:
+        """drop every TTL record whose time has come (kb_expire); returns the number of records removed"""
+        n = C.c_uint64()
+        self._check(lib().kb_expire(self._ctx, int(now_unix), C.byref(n)))
+        return n.value
 
     def dump(self, path: str):
         """write the snapshot (directory, slabs, compact revision) to `path` (atomically: tmp file + rename)"""

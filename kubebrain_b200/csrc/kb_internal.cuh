@@ -7,8 +7,10 @@
 #include <string.h>
 
 #include <chrono>
+#include <map>
 #include <mutex>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/kb_b200.h"
@@ -186,6 +188,10 @@ struct kb_ctx {
     std::vector<uint32_t> h_vlen;
     bool compact_present = false;
     uint64_t compact_rev = 0;
+    // TTL puts: (expire_unix, internal key), ordered by time; ttl_of[key] = the expiry the key currently has (a later put
+    // of the same key replaces or cancels it, a delete cancels it)
+    std::multimap<uint64_t, std::string> ttl_queue;
+    std::unordered_map<std::string, uint64_t> ttl_of;
 
     // scratch (grow only)
     DBuf d_bounds, d_bres, d_reqs, d_tiles /* alias into d_reqs */, d_meta, d_tgt, d_agg, d_tcnt /* look-back states */, d_tscan, d_reqout,

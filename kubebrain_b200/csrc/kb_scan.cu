@@ -1928,10 +1928,58 @@ void push_pieces(std::vector<CopyPiece> &out, uint64_t src16, uint64_t dst16, ui
 }
 }  // namespace
 
+static int apply_batch_locked(kb_ctx *ctx, const kb_write_op *ops, uint64_t n_ops);
+
 extern "C" int kb_apply_batch(kb_ctx *ctx, const kb_write_op *ops, uint64_t n_ops)
 {
     if (!ctx || (n_ops && !ops)) return KB_EINVAL;
     std::lock_guard<std::mutex> g(ctx->mu);
+    KB_TRY(apply_batch_locked(ctx, ops, n_ops));
+    // TTL bookkeeping, in op order: the last op on a key decides whether (and when) it expires
+    for (uint64_t i = 0; i < n_ops; i++) {
+        std::string k((const char *)ops[i].key, ops[i].key_len);
+        if (ops[i].type == KB_OP_PUT && ops[i].expire_unix) {
+            ctx->ttl_of[k] = ops[i].expire_unix;
+            ctx->ttl_queue.emplace(ops[i].expire_unix, std::move(k));
+        } else if (!ctx->ttl_of.empty()) {
+            ctx->ttl_of.erase(k);  // deleted, or rewritten without a ttl: stale queue entries are skipped by kb_expire
+        }
+    }
+    return KB_OK;
+}
+
+extern "C" int kb_expire(kb_ctx *ctx, uint64_t now_unix, uint64_t *n_dropped)
+{
+    if (!ctx) return KB_EINVAL;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    if (n_dropped) *n_dropped = 0;
+    if (!ctx->loaded) return kb_fail(ctx, KB_ESTATE, "no store loaded");
+    std::vector<std::string> due;
+    auto end = ctx->ttl_queue.upper_bound(now_unix);
+    for (auto it = ctx->ttl_queue.begin(); it != end; ++it) {
+        auto cur = ctx->ttl_of.find(it->second);
+        if (cur != ctx->ttl_of.end() && cur->second == it->first) {  // still the expiry the key has
+            due.push_back(it->second);
+            ctx->ttl_of.erase(cur);
+        }
+    }
+    ctx->ttl_queue.erase(ctx->ttl_queue.begin(), end);
+    if (due.empty()) return KB_OK;
+    std::vector<kb_write_op> ops(due.size());
+    for (size_t i = 0; i < due.size(); i++) {
+        memset(&ops[i], 0, sizeof(kb_write_op));
+        ops[i].type = KB_OP_DEL;
+        ops[i].key = (const uint8_t *)due[i].data();
+        ops[i].key_len = due[i].size();
+    }
+    const uint64_t before = ctx->st.n;
+    KB_TRY(apply_batch_locked(ctx, ops.data(), ops.size()));
+    if (n_dropped) *n_dropped = before - ctx->st.n;
+    return KB_OK;
+}
+
+static int apply_batch_locked(kb_ctx *ctx, const kb_write_op *ops, uint64_t n_ops)
+{
     if (!ctx->loaded) return kb_fail(ctx, KB_ESTATE, "no store loaded");
     cudaSetDevice(ctx->device);
     KB_TRY(ctx_quiesce(ctx));

@@ -41,6 +41,25 @@ def range_response(res: RangeResult, q: int, header_rev: int, more: bool) -> byt
     return range_head(header_rev) + bytes(res.elements(q)) + range_tail(more, n + (1 if more else 0))
 
 
+def list_response(eng, start: bytes, end: bytes, revision: int, limit: int, header_rev: int) -> bytes:
+    """The serialized etcdserverpb.RangeResponse of a List with the USER's limit, as backend.List + backendShim.List build
+    it: the scanner is asked for limit + 1 (pkg/backend/range.go:150-170), the first `limit` kvs are kept (the arena is cut
+    at elem_off[limit]), More says whether one was dropped and Count = len(kvs) + (1 if More) (backendshim.go:269-277).
+    start / end are internal keys."""
+    from ._lib import KB_OUT_HOST, KB_WIRE_ETCD_KVS
+
+    res = eng.range_batch([(start, end, revision, limit + 1 if limit > 0 else 0)], KB_OUT_HOST | KB_WIRE_ETCD_KVS)
+    try:
+        n = res.n_kvs
+        more = limit > 0 and n > limit
+        if more:
+            n = limit
+        body = bytes(res.elements(0, 0, n))
+        return range_head(header_rev) + body + range_tail(more, n + (1 if more else 0))
+    finally:
+        res.close()
+
+
 def stream_messages(res: RangeResult, q: int, revision: int, err: Optional[str] = None) -> Iterator[bytes]:
     """the serialized etcdserverpb.WatchResponse sequence of one range stream: batches of 300 events whose header
     revision is 0 (forked receivers never get readRev, receiver.go:162-166), then the cancel message carrying the read

@@ -31,7 +31,7 @@ def test_library_exports_every_symbol():
     L = ctypes.CDLL(_lib.LIB_PATH)
     for name in _declared():
         assert hasattr(L, name), f"libkbb200.so does not export {name}"
-    assert L.kb_abi_version() == 1
+    assert L.kb_abi_version() == 2
 
 
 def test_no_cpu_fallback(have_gpu):

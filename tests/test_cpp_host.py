@@ -27,6 +27,16 @@ def test_cpp_host_mirror_cpu():
 
 
 @pytest.mark.gpu
+def test_go_shim_call_sequences_replayed():
+    """tests/cpp/shim_replay_test.cpp: every method of the Go shim (storage adaptor, scanner, event slab) as the exact C
+    call sequence it issues, against the oracle"""
+    _build()
+    exe = os.path.join(ROOT, "tests", "cpp", "shim_replay_test")
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "shim replay ok" in out.stdout, out.stdout + out.stderr
+
+
+@pytest.mark.gpu
 def test_cpp_host_mirror_gpu():
     _build()
     out = subprocess.run([EXE, "gpu"], capture_output=True, text=True, timeout=300)
