@@ -286,7 +286,7 @@ extern "C" void kb_close(kb_ctx *ctx)
                    &ctx->d_bounds, &ctx->d_bres, &ctx->d_reqs,
                    &ctx->d_meta, &ctx->d_tgt, &ctx->d_agg, &ctx->d_tcnt, &ctx->d_tscan, &ctx->d_reqout,
                    &ctx->d_sel, &ctx->d_slot, &ctx->d_jobs, &ctx->d_gjobs, &ctx->d_jobs2, &ctx->d_gjobs2, &ctx->d_flags, &ctx->d_cursor,
-                   &ctx->d_ctrs};
+                   &ctx->d_ctrs, &ctx->s_koff16, &ctx->s_klen, &ctx->s_voff16, &ctx->s_vlen, &ctx->s_dir};
     for (DBuf *b : all) dfree(*b);
     for (auto &b : ctx->free_dev) cudaFree(b.p);
     for (auto &b : ctx->free_host) cudaFreeHost(b.p);
@@ -504,10 +504,11 @@ extern "C" int kb_load_sorted(kb_ctx *ctx, const uint8_t *keys, const uint64_t *
     ctx->st.vlen = (const uint32_t *)ctx->d_vlen.p;
     ctx->st.n = (uint32_t)n;
     KB_TRY(store_pack_dir(ctx));
-    ctx->h_koff16 = koff16;
-    ctx->h_voff16 = voff16;
-    ctx->h_klen = klen;
-    ctx->h_vlen = vlen;
+    ctx->kused16 = kacc;
+    ctx->vused16 = vacc;
+    ctx->garbage_k16 = ctx->garbage_v16 = ctx->displaced = 0;
+    ctx->ttl_queue.clear();
+    ctx->ttl_of.clear();
 
     // the iterator contract: strictly ascending unique keys
     if (n > 1) {
@@ -598,7 +599,22 @@ extern "C" int kb_dump(kb_ctx *ctx, const char *path)
     if (!ctx->loaded) return kb_fail(ctx, KB_ESTATE, "no store loaded");
     cudaSetDevice(ctx->device);
     KB_TRY(ctx_quiesce(ctx));
+    KB_TRY(store_compact_layout(ctx));  // the file holds the contiguous, key-ordered layout
     KB_TRY(hbuf_ensure(ctx, ctx->h_stage, DUMP_STAGE));
+    // the record directory lives on the device only: fetch it for the directory section
+    std::vector<uint32_t> h_koff16(ctx->st.n + 1), h_vlen(std::max<uint32_t>(ctx->st.n, 1));
+    std::vector<uint16_t> h_klen(std::max<uint32_t>(ctx->st.n, 1));
+    std::vector<uint64_t> h_voff16(ctx->st.n + 1);
+    if (ctx->st.n) {
+        const uint64_t nn = ctx->st.n;
+        KB_CUDA(ctx, cudaMemcpyAsync(h_koff16.data(), ctx->st.koff16, nn * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        KB_CUDA(ctx, cudaMemcpyAsync(h_klen.data(), ctx->st.klen, nn * 2, cudaMemcpyDeviceToHost, ctx->stream));
+        KB_CUDA(ctx, cudaMemcpyAsync(h_voff16.data(), ctx->st.voff16, nn * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        KB_CUDA(ctx, cudaMemcpyAsync(h_vlen.data(), ctx->st.vlen, nn * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        KB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    h_koff16[ctx->st.n] = (uint32_t)ctx->kused16;
+    h_voff16[ctx->st.n] = ctx->vused16;
     const std::string tmp = std::string(path) + ".tmp";
     FILE *f = fopen(tmp.c_str(), "wb");
     if (!f) return kb_fail(ctx, KB_EIO, "dump: cannot create %s", tmp.c_str());
@@ -623,10 +639,10 @@ extern "C" int kb_dump(kb_ctx *ctx, const char *path)
         hd = fnv1a64_update(hd, (const uint8_t *)p, bytes);
         if (bytes && fwrite(p, 1, bytes, f) != bytes) rc = kb_fail(ctx, KB_EIO, "dump: short write");
     };
-    put(ctx->h_koff16.data(), (n + 1) * 4);
-    put(ctx->h_klen.data(), n * 2);
-    put(ctx->h_voff16.data(), (n + 1) * 8);
-    put(ctx->h_vlen.data(), n * 4);
+    put(h_koff16.data(), (n + 1) * 4);
+    put(h_klen.data(), n * 2);
+    put(h_voff16.data(), (n + 1) * 8);
+    put(h_vlen.data(), n * 4);
     h.sum_dir = hd;
     if (rc == KB_OK) rc = dump_section(ctx, f, ctx->d_kslab.p, ctx->key_bytes, &h.sum_keys);
     if (rc == KB_OK) rc = dump_section(ctx, f, ctx->d_vslab.p, ctx->val_bytes, &h.sum_vals);
@@ -720,10 +736,11 @@ extern "C" int kb_restore(kb_ctx *ctx, const char *path)
     } else {
         KB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     }
-    ctx->h_koff16.swap(koff16);
-    ctx->h_voff16.swap(voff16);
-    ctx->h_klen.swap(klen);
-    ctx->h_vlen.swap(vlen);
+    ctx->kused16 = h.key_chunks;
+    ctx->vused16 = h.val_chunks;
+    ctx->garbage_k16 = ctx->garbage_v16 = ctx->displaced = 0;
+    ctx->ttl_queue.clear();
+    ctx->ttl_of.clear();
     ctx->key_bytes = h.key_chunks * 16;
     ctx->val_bytes = h.val_chunks * 16;
     ctx->max_kv_chunks = (uint32_t)std::min<uint64_t>(max_kv, 0xFFFFFFFFu);

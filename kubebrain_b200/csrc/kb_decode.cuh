@@ -29,6 +29,8 @@ namespace {
 constexpr uint32_t MAGIC_LE = 0x8b80fb57u;  // bytes 57 fb 80 8b (coder/normal.go:26)
 constexpr int DECODE_MAX_K = 4;             // sub-tiles (of 32 records) per step
 constexpr uint32_t DECODE_HDR_CHUNKS = 2;   // per directory slot: the step descriptor (32 bytes)
+constexpr int DECODE_MAX_KS = 4;            // key slots per warp (ring depth)
+constexpr int DECODE_MAX_BARS = 2 * DECODE_MAX_KS + 1;  // one mbarrier per key slot and per directory slot
 
 __device__ __forceinline__ uint32_t bswap32(uint32_t x) { return __byte_perm(x, 0, 0x0123); }
 
@@ -180,6 +182,7 @@ struct DecGeom {
     uint32_t K;          // 32-record sub-tiles per step
     uint32_t SK;         // key chunks per key-ring slot: (32 K + 1) keys of the longest length
     uint32_t DS;         // chunks per directory slot: 32 K + 1 entries + DECODE_HDR_CHUNKS
+    uint32_t NKS;        // key slots per warp (keys in flight NKS - 1 steps ahead); NKS + 1 directory slots
     uint32_t warps;      // warps per CTA
     uint32_t bpt;        // blocks (of four steps) per tile: ceil(ceil(32 / K) / 4)
     uint32_t n_blocks;   // tiles * bpt
@@ -217,15 +220,16 @@ __global__ void __launch_bounds__(MAXW * 32, 1)
 k_decode_lcp(StoreDev st, const TileDev *__restrict__ tiles, DecGeom g, ScanMode mode, uint32_t *__restrict__ meta,
              unsigned int *__restrict__ work_ctr, unsigned int *__restrict__ err_flag)
 {
-    extern __shared__ uint4 smem[];  // per warp: keys[2][SK] | dir slots[3][DS]
-    __shared__ uint64_t bars[MAXW * 5];
+    extern __shared__ uint4 smem[];  // per warp: key slots[NKS][SK] | directory slots[NKS + 1][DS]
+    __shared__ uint64_t bars[MAXW * DECODE_MAX_BARS];
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const unsigned FULLM = 0xffffffffu;
-    uint4 *kbuf = smem + (size_t)warp * (2 * g.SK + 3 * g.DS);
-    uint4 *dbuf = kbuf + 2 * g.SK;
-    uint64_t *kbar = bars + warp * 5, *dbar = kbar + 2;
+    const uint32_t NKS = g.NKS, NDS = g.NKS + 1;  // a step's keys are in flight NKS - 1 steps, its directory entries NKS
+    uint4 *kbuf = smem + (size_t)warp * (NKS * g.SK + NDS * g.DS);
+    uint4 *dbuf = kbuf + NKS * g.SK;
+    uint64_t *kbar = bars + warp * DECODE_MAX_BARS, *dbar = kbar + DECODE_MAX_KS;
     if (lane == 0) {
-        for (int i = 0; i < 5; i++) dmbar_init(kbar + i);
+        for (int i = 0; i < DECODE_MAX_BARS; i++) dmbar_init(kbar + i);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
@@ -303,7 +307,7 @@ k_decode_lcp(StoreDev st, const TileDev *__restrict__ tiles, DecGeom g, ScanMode
     uint32_t nx[KK], ny[KK], nz[KK];    // ... of the step whose keys are in flight
 #pragma unroll
     for (int k = 0; k < KK; k++) vx[k] = vy[k] = vz[k] = nx[k] = ny[k] = nz[k] = 0;
-    uint32_t phase = 0;  // bit i: parity the next completion of barrier i will have been waited with (kbar 0,1, dbar 2,3,4)
+    uint32_t phase = 0;  // bit i: parity of the next completion of barrier i (key slots 0 .., directory slots DECODE_MAX_KS ..)
 
     // keys + value probes of the step described in directory slot `slot`, into key slot `ks`
     auto stage_keys = [&](uint32_t slot, uint32_t ks) {
@@ -311,12 +315,26 @@ k_decode_lcp(StoreDev st, const TileDev *__restrict__ tiles, DecGeom g, ScanMode
         StepHdr *h = (StepHdr *)ds;
         const uint32_t nrec = h->nrec, halo = h->halo;
         if (nrec == 0) return;
-        dmbar_wait(dbar + slot, (phase >> (2 + slot)) & 1, err_flag);
-        phase ^= 1u << (2 + slot);
+        dmbar_wait(dbar + slot, (phase >> (DECODE_MAX_KS + slot)) & 1, err_flag);
+        phase ^= 1u << (DECODE_MAX_KS + slot);
         const uint4 *ent = ds + DECODE_HDR_CHUNKS;
         const uint32_t cnt = nrec + halo;
-        const uint4 e0 = ent[0], e1 = ent[cnt - 1];
-        const uint32_t base16 = e0.x, span = e1.x + (((e1.y & 0xffffu) + 15) >> 4) - e0.x;
+        // Chunk interval covering every key of the step (and the one in front of it).  In a freshly loaded or compacted
+        // store the keys of consecutive records are contiguous and this is exactly first .. last; records appended by
+        // kb_apply_batch since then live at the slab tail, the interval then exceeds the ring slot and the step reads its
+        // keys in place (unstaged path).
+        uint32_t lo16 = 0xFFFFFFFFu, hi16 = 0;
+#pragma unroll
+        for (int k = 0; k <= KK; k++) {
+            const uint32_t r = k * 32 + lane;
+            if (r < cnt) {
+                const uint4 e = ent[r];
+                lo16 = min(lo16, e.x);
+                hi16 = max(hi16, e.x + (((e.y & 0xffffu) + 15) >> 4));
+            }
+        }
+        const uint32_t base16 = __reduce_min_sync(FULLM, lo16);
+        const uint32_t span = __reduce_max_sync(FULLM, hi16) - base16;
         if (lane == 0) {
             h->base16 = base16;
             h->span = span;
@@ -326,7 +344,16 @@ k_decode_lcp(StoreDev st, const TileDev *__restrict__ tiles, DecGeom g, ScanMode
                 dbulk_g2s(kbuf + (size_t)ks * g.SK, st.kslab + base16, span * 16, kbar + ks);
             }
         }
-        // only 9-byte values are ever inspected by the range path; the TTL sweep also reads revision-record values
+    };
+
+    // value probes of the step described in directory slot `slot` (its entries landed when its keys were staged): issued one
+    // step before the step is decoded.  Only 9-byte values are ever inspected by the range path; the TTL sweep also reads
+    // revision-record values.
+    auto probe_values = [&](uint32_t slot) {
+        const uint4 *ds = dbuf + (size_t)slot * g.DS;
+        const StepHdr *h = (const StepHdr *)ds;
+        const uint32_t nrec = h->nrec, halo = h->halo;
+        const uint4 *ent = ds + DECODE_HDR_CHUNKS;
 #pragma unroll
         for (int k = 0; k < KK; k++) {
             nx[k] = ny[k] = nz[k] = 0;
@@ -381,12 +408,13 @@ k_decode_lcp(StoreDev st, const TileDev *__restrict__ tiles, DecGeom g, ScanMode
         return true;
     };
 
-    // prologue: steps 0 and 1 described, keys of step 0 in flight
-    generate(0);
-    __syncwarp();
-    generate(1);
-    __syncwarp();
-    stage_keys(0, 0);
+    // prologue: steps 0 .. NKS-1 described, keys of steps 0 .. NKS-2 in flight, probes of step 0 issued
+    for (uint32_t i = 0; i < NKS; i++) {
+        generate(i);
+        __syncwarp();
+    }
+    for (uint32_t i = 0; i + 1 < NKS; i++) stage_keys(i, i);
+    probe_values(0);
 #pragma unroll
     for (int k = 0; k < KK; k++) {
         vx[k] = nx[k];
@@ -394,14 +422,19 @@ k_decode_lcp(StoreDev st, const TileDev *__restrict__ tiles, DecGeom g, ScanMode
         vz[k] = nz[k];
     }
     __syncwarp();
-    // steady state, iteration i: describe step i+2, stage the keys of step i+1, decode step i
-    uint32_t s0 = 0, k0 = 0;  // directory / key slot of the step being decoded
+    // steady state, iteration i: describe step i+NKS, stage the keys of step i+NKS-1, probe the values of step i+1, decode
+    // step i.  d0 / k0: directory / key slot of the step being decoded.
+    uint32_t d0 = 0, k0 = 0;
     for (;;) {
-        const uint32_t s1 = s0 == 2 ? 0 : s0 + 1, s2 = s1 == 2 ? 0 : s1 + 1;
-        generate(s2);
+        const uint32_t dg = d0 + NKS >= NDS ? d0 + NKS - NDS : d0 + NKS;       // (d0 + NKS) mod NDS
+        const uint32_t dk = d0 + NKS - 1 >= NDS ? d0 - 2 : d0 + NKS - 1;        // (d0 + NKS - 1) mod NDS
+        const uint32_t kk = k0 == 0 ? NKS - 1 : k0 - 1;                         // (k0 + NKS - 1) mod NKS
+        const uint32_t d1 = d0 + 1 == NDS ? 0 : d0 + 1;
+        generate(dg);
         __syncwarp();
-        stage_keys(s1, k0 ^ 1);
-        const bool more = process(s0, k0);
+        stage_keys(dk, kk);
+        probe_values(d1);
+        const bool more = process(d0, k0);
 #pragma unroll
         for (int k = 0; k < KK; k++) {
             vx[k] = nx[k];
@@ -410,31 +443,38 @@ k_decode_lcp(StoreDev st, const TileDev *__restrict__ tiles, DecGeom g, ScanMode
         }
         __syncwarp();
         if (!more) break;
-        s0 = s1;
-        k0 ^= 1;
+        d0 = d1;
+        k0 = k0 + 1 == NKS ? 0 : k0 + 1;
     }
 }
 
-// geometry for a store whose longest key has `max_key_chunks` 16-byte chunks; K and the warp count can be forced for
-// experiments (KB_DECODE_K, KB_DECODE_WARPS)
-static inline DecGeom decode_geometry(uint32_t max_key_chunks, uint32_t ntiles, uint32_t force_k, uint32_t force_warps,
-                                      size_t *smem_bytes)
+// geometry for a store whose longest key has `max_key_chunks` 16-byte chunks; K, the ring depth and the warp count can
+// be forced for experiments (KB_DECODE_K, KB_DECODE_NKS, KB_DECODE_WARPS)
+static inline DecGeom decode_geometry(uint32_t max_key_chunks, uint32_t ntiles, uint32_t force_k, uint32_t force_nks,
+                                      uint32_t force_warps, size_t *smem_bytes)
 {
     const uint32_t c = std::max<uint32_t>(max_key_chunks, 1);
     const size_t budget = 227 * 1024 - 2048;
     DecGeom g;
     uint32_t K = force_k ? force_k : (c >= 9 ? 1u : c >= 5 ? 2u : 4u);
     K = std::min<uint32_t>(std::max<uint32_t>(K, 1), DECODE_MAX_K);
-    auto per_warp = [&](uint32_t k) { return (size_t)(2 * (32 * k + 1) * c + 3 * (32 * k + 1 + DECODE_HDR_CHUNKS)) * 16; };
-    while (K > 1 && per_warp(K) * 4 > budget) K--;  // very long keys: fewer records per step rather than fewer than 4 warps
+    // Ring depth: the pass is bound by the bytes it keeps in flight (measured: 4.7 TB/s with one key copy in flight per
+    // warp at ~100 KB per SM), so prefer fewer warps with more copies in flight each.
+    uint32_t NKS = force_nks ? std::min<uint32_t>(std::max<uint32_t>(force_nks, 2), DECODE_MAX_KS) : 3;
+    auto per_warp = [&](uint32_t k, uint32_t nks) {
+        return (size_t)(nks * (32 * k + 1) * c + (nks + 1) * (32 * k + 1 + DECODE_HDR_CHUNKS)) * 16;
+    };
+    while (per_warp(K, NKS) * 4 > budget && NKS > 2) NKS--;
+    while (per_warp(K, NKS) * 4 > budget && K > 1) K--;  // very long keys: fewer records per step rather than < 4 warps
     g.K = K;
+    g.NKS = NKS;
+    g.DS = 32 * K + 1 + DECODE_HDR_CHUNKS;
     g.SK = (32 * K + 1) * c;
     // keys longer than ~1.7 KB: the ring would not hold a sub-tile even with four warps; cap the slot, such steps take
     // the unstaged path (direct loads from the slab)
-    const uint32_t max_sk = (uint32_t)((budget / 4 / 16 - 3 * (32 * K + 1 + DECODE_HDR_CHUNKS)) / 2);
+    const uint32_t max_sk = (uint32_t)((budget / 4 / 16 - (NKS + 1) * g.DS) / NKS);
     g.SK = std::min(g.SK, max_sk);
-    g.DS = 32 * K + 1 + DECODE_HDR_CHUNKS;
-    const size_t pw = (size_t)(2 * g.SK + 3 * g.DS) * 16;
+    const size_t pw = (size_t)(NKS * g.SK + (NKS + 1) * g.DS) * 16;
     uint32_t warps = (uint32_t)std::min<size_t>(budget / pw, 24);
     if (force_warps) warps = std::min(warps, force_warps);
     g.warps = std::max<uint32_t>(warps, 1);

@@ -32,6 +32,8 @@ struct StoreDev {
 
 // fills StoreDev::dir from the four directory arrays (kb_core.cu); enqueued on ctx->stream
 int store_pack_dir(struct kb_ctx *ctx);
+// rewrites both slabs contiguously in key order when records are out of place or garbage exists (kb_scan.cu)
+int store_compact_layout(struct kb_ctx *ctx);
 
 // one scanner.Range / Count / Compact request, resolved to record indices
 struct ReqDev {
@@ -182,10 +184,10 @@ struct kb_ctx {
     uint64_t key_bytes = 0, val_bytes = 0;
     uint32_t max_kv_chunks = 0;  // largest padded [key][value] pair, in 16-byte chunks: sizes the gather's ring buffers
     uint32_t max_key_chunks = 0; // longest key, in 16-byte chunks: sizes the decode pass's key ring
-    std::vector<uint32_t> h_koff16;  // host copies of the slab offsets: byte accounting and response-arena bounds
-    std::vector<uint64_t> h_voff16;
-    std::vector<uint16_t> h_klen;   // host copy of the whole record directory: kb_apply_batch rebuilds it on the host
-    std::vector<uint32_t> h_vlen;
+    // heap + sorted directory (kb_apply_batch): chunks in use at the slab tails, chunks no live record points at, records
+    // appended out of key order since the last layout compaction; s_* = the spare directory set the next merge writes
+    uint64_t kused16 = 0, vused16 = 0, garbage_k16 = 0, garbage_v16 = 0, displaced = 0, layout_compactions = 0;
+    DBuf s_koff16, s_klen, s_voff16, s_vlen, s_dir;
     bool compact_present = false;
     uint64_t compact_rev = 0;
     // TTL puts: (expire_unix, internal key), ordered by time; ttl_of[key] = the expiry the key currently has (a later put

@@ -230,15 +230,22 @@ __device__ __forceinline__ void ts_publish(uint32_t *status, uint32_t v)
     *(volatile uint32_t *)status = v;
 }
 
-// warp 0: exclusive (L, m) carry of tile t inside its request (tiles [t0, t))
-__device__ __forceinline__ LM lookback_lm(TileState *ts, uint32_t t, uint32_t t0, uint32_t lane)
+// Look-back window: all eight warps of the CTA read the states of up to 256 preceding tiles per step (warp w looks at
+// tiles hi-1-32w .. hi-32-32w).  With one warp (32 tiles per step) the frontier of resolved prefixes advanced 32 tiles per
+// memory round trip and a 100M-record sweep (97 656 tiles, ~1 200 in flight) spent 2 ms waiting for it.
+constexpr uint32_t LB_WINDOW = 256;
+
+// exclusive (L, m) carry of tile t inside its request (tiles [t0, t)); every thread of the CTA calls it, all return the carry
+__device__ __forceinline__ LM lookback_lm(TileState *ts, uint32_t t, uint32_t t0, uint32_t *sh /* 8 x {term, L, m} + 1 */)
 {
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     LM acc;
     acc.L = KB_NONE;
     acc.m = KB_LCP_INF;
-    for (uint32_t hi = t; hi > t0;) {  // this step looks at tiles hi-1, hi-2, .. (lane 0 = nearest)
-        const bool in = lane < hi - t0;
-        TileState *p = ts + (hi - 1 - (in ? lane : 0));
+    for (uint32_t hi = t; hi > t0;) {  // this step looks at tiles hi-1, hi-2, .. (thread 0 = nearest)
+        const uint32_t back = threadIdx.x;
+        const bool in = back < hi - t0;
+        TileState *p = ts + (hi - 1 - (in ? back : 0));
         uint32_t st;
         do {
             st = in ? *(volatile uint32_t *)&p->st_lm : (uint32_t)TS_PREFIX;
@@ -249,28 +256,41 @@ __device__ __forceinline__ LM lookback_lm(TileState *ts, uint32_t t, uint32_t t0
         v.m = KB_LCP_INF;
         if (in) v = lm_unpack(*(volatile unsigned long long *)(st == TS_PREFIX ? &p->lm_pre : &p->lm_agg));
         const unsigned term = __ballot_sync(FULL, in && (st == TS_PREFIX || v.L != KB_NONE));
-        const uint32_t k = term ? (uint32_t)(__ffs(term) - 1) : 31u;  // farthest lane that still matters
+        const uint32_t k = term ? (uint32_t)(__ffs(term) - 1) : 31u;  // farthest lane of this warp that still matters
         const uint32_t mm = __reduce_min_sync(FULL, (in && lane <= k) ? v.m : KB_LCP_INF);
         const uint32_t Lk = __shfl_sync(FULL, v.L, k);
-        // combine(farther, nearer): nearer tiles (already in acc) hold no PREVOK, so only the minimum accumulates
-        acc.m = min(acc.m, mm);
-        if (term) {
-            acc.L = Lk;
-            break;
+        if (lane == 0) {
+            sh[warp * 3 + 0] = term ? 1u : 0u;
+            sh[warp * 3 + 1] = Lk;
+            sh[warp * 3 + 2] = mm;
         }
-        hi -= min(32u, hi - t0);
+        __syncthreads();
+        // combine(farther, nearer): nearer tiles (already in acc) hold no PREVOK, so only the minimum accumulates
+        bool done = false;
+        for (uint32_t w = 0; w < 8 && !done; w++) {
+            acc.m = min(acc.m, sh[w * 3 + 2]);
+            if (sh[w * 3 + 0]) {
+                acc.L = sh[w * 3 + 1];
+                done = true;
+            }
+        }
+        __syncthreads();
+        if (done) break;
+        hi -= min(LB_WINDOW, hi - t0);
     }
     return acc;
 }
 
-// warp 0: exclusive sums (count, aux) of tile t inside its request
-__device__ __forceinline__ void lookback_sum(TileState *ts, uint32_t t, uint32_t t0, uint32_t lane, uint64_t &cnt,
-                                             uint64_t &aux)
+// exclusive sums (count, aux) of tile t inside its request; every thread of the CTA calls it
+__device__ __forceinline__ void lookback_sum(TileState *ts, uint32_t t, uint32_t t0, uint64_t *sh /* 8 x {term, c, a} */,
+                                             uint64_t &cnt, uint64_t &aux)
 {
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     cnt = aux = 0;
     for (uint32_t hi = t; hi > t0;) {
-        const bool in = lane < hi - t0;
-        TileState *p = ts + (hi - 1 - (in ? lane : 0));
+        const uint32_t back = threadIdx.x;
+        const bool in = back < hi - t0;
+        TileState *p = ts + (hi - 1 - (in ? back : 0));
         uint32_t st;
         do {
             st = in ? *(volatile uint32_t *)&p->st_cnt : (uint32_t)TS_PREFIX;
@@ -289,10 +309,21 @@ __device__ __forceinline__ void lookback_sum(TileState *ts, uint32_t t, uint32_t
             c += __shfl_xor_sync(FULL, c, d);
             a += __shfl_xor_sync(FULL, a, d);
         }
-        cnt += c;
-        aux += a;
-        if (term) break;
-        hi -= min(32u, hi - t0);
+        if (lane == 0) {
+            sh[warp * 3 + 0] = term ? 1u : 0u;
+            sh[warp * 3 + 1] = c;
+            sh[warp * 3 + 2] = a;
+        }
+        __syncthreads();
+        bool done = false;
+        for (uint32_t w = 0; w < 8 && !done; w++) {
+            cnt += sh[w * 3 + 1];
+            aux += sh[w * 3 + 2];
+            done = sh[w * 3 + 0] != 0;
+        }
+        __syncthreads();
+        if (done) break;
+        hi -= min(LB_WINDOW, hi - t0);
     }
 }
 
@@ -308,12 +339,13 @@ k_emit_place(StoreDev st, const ReqDev *__restrict__ reqs, const TileDev *__rest
     __shared__ LM carry_s, agg_s;
     __shared__ uint64_t ws2[18];
     __shared__ uint64_t pre_s[2];
+    __shared__ uint64_t lb64[24];
+    __shared__ uint32_t lb32[24];
     __shared__ uint32_t tile_s;
     if (threadIdx.x == 0) tile_s = atomicAdd(ticket, 1u);  // ticket order: every preceding tile has started
     if (blockIdx.x == 0 && threadIdx.x == 0) *decode_ctr = 0;  // leave k_decode_lcp's work counter at zero
     __syncthreads();
     const uint32_t tix = tile_s;
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const TileDev tile = tiles[tix];
     const ReqDev req = reqs[tile.req];
     const bool first_tile = tix == req.tile0, last_tile = tix == req.tile0 + req.ntiles - 1;
@@ -344,28 +376,28 @@ k_emit_place(StoreDev st, const ReqDev *__restrict__ reqs, const TileDev *__rest
     const LM ex = block_excl_scan_lm(mine, warp_tot);
     if (threadIdx.x == 255) agg_s = lm_combine(ex, mine);
     __syncthreads();
-    if (warp == 0) {
+    {
         const LM agg = agg_s;
         LM carry;
         carry.L = KB_NONE;
         carry.m = KB_LCP_INF;
         if (first_tile) {
-            if (lane == 0) {
+            if (threadIdx.x == 0) {
                 my->lm_pre = lm_pack(agg);
                 ts_publish(&my->st_lm, TS_PREFIX);
             }
         } else {
-            if (lane == 0) {
+            if (threadIdx.x == 0) {
                 my->lm_agg = lm_pack(agg);
                 ts_publish(&my->st_lm, TS_AGG);
             }
-            carry = lookback_lm(ts, tix, req.tile0, lane);
-            if (lane == 0) {
+            carry = lookback_lm(ts, tix, req.tile0, lb32);
+            if (threadIdx.x == 0) {
                 my->lm_pre = lm_pack(lm_combine(carry, agg));
                 ts_publish(&my->st_lm, TS_PREFIX);
             }
         }
-        if (lane == 0) carry_s = carry;
+        if (threadIdx.x == 0) carry_s = carry;
     }
     __syncthreads();
     LM x = lm_combine(carry_s, ex);
@@ -439,28 +471,28 @@ k_emit_place(StoreDev st, const ReqDev *__restrict__ reqs, const TileDev *__rest
     }
     uint64_t ea, eb, ta, tb;
     block_excl_scan2(cnt, aux, ea, eb, ta, tb, ws2);
-    if (warp == 0) {
+    {
         uint64_t pc = 0, pa = 0;
         if (first_tile) {
-            if (lane == 0) {
+            if (threadIdx.x == 0) {
                 my->cnt_pre = ta;
                 my->aux_pre = tb;
                 ts_publish(&my->st_cnt, TS_PREFIX);
             }
         } else {
-            if (lane == 0) {
+            if (threadIdx.x == 0) {
                 my->cnt_agg = ta;
                 my->aux_agg = tb;
                 ts_publish(&my->st_cnt, TS_AGG);
             }
-            lookback_sum(ts, tix, req.tile0, lane, pc, pa);
-            if (lane == 0) {
+            lookback_sum(ts, tix, req.tile0, lb64, pc, pa);
+            if (threadIdx.x == 0) {
                 my->cnt_pre = pc + ta;
                 my->aux_pre = pa + tb;
                 ts_publish(&my->st_cnt, TS_PREFIX);
             }
         }
-        if (lane == 0) {
+        if (threadIdx.x == 0) {
             pre_s[0] = pc;
             pre_s[1] = pa;
             if (last_tile) {  // inclusive prefix of the request's last tile = the request's totals
@@ -738,6 +770,7 @@ static inline void gather_geometry(uint32_t max_kv_chunks, uint32_t *piece, uint
 struct GetOut {
     uint8_t *status;
     uint64_t *mod_rev;
+    uint64_t *voff16;  // value slab chunk of the answering record (the host builds the copy jobs from it)
     uint32_t *rec;
     uint32_t *vlen;
 };
@@ -750,7 +783,7 @@ k_get_resolve(StoreDev st, const uint4 *__restrict__ bounds, const uint32_t *__r
     if (g >= n) return;
     const uint32_t idx = ub[g];
     uint32_t status = KB_GET_NOT_FOUND, rec = 0, vl = 0;
-    uint64_t mrev = 0;
+    uint64_t mrev = 0, vo = 0;
     if (idx > 0) {
         rec = idx - 1;
         const uint32_t bl = blen[g];           // magic + key + '$' + rev(8) + one 0x00 byte
@@ -770,9 +803,10 @@ k_get_resolve(StoreDev st, const uint4 *__restrict__ bounds, const uint32_t *__r
                 mrev = be64_bytes((const uint8_t *)a + kl - 8);
                 if (mrev != 0) {
                     vl = st.vlen[rec];
+                    vo = st.voff16[rec];
                     status = KB_GET_FOUND;
                     if (vl == 9) {
-                        const uint4 v0 = st.vslab[st.voff16[rec]];
+                        const uint4 v0 = st.vslab[vo];
                         if (v0.x == 0x626d6f74u && v0.y == 0x6e6f7473u && (v0.z & 0xffu) == 0x65u) status = KB_GET_TOMBSTONE;
                     }
                 }
@@ -782,16 +816,19 @@ k_get_resolve(StoreDev st, const uint4 *__restrict__ bounds, const uint32_t *__r
     if (lane == 0) {
         out.status[g] = (uint8_t)status;
         out.mod_rev[g] = status == KB_GET_NOT_FOUND ? 0 : mrev;
+        out.voff16[g] = vo;
         out.rec[g] = rec;
         out.vlen[g] = vl;
     }
 }
 
 // ---- kb_apply_batch helpers ------------------------------------------------------------------------------
-// exists[i] = 1 iff the record at pos[i] (lower_bound of op key i) carries exactly that key
+// exists[i] = 1 iff the record at pos[i] (lower_bound of op key i) carries exactly that key; old_vchunks[i] = its value's
+// 16-byte chunks (they become garbage when the op replaces or deletes the record)
 __global__ void __launch_bounds__(128)
 k_key_exists(StoreDev st, const uint4 *__restrict__ bounds, const uint32_t *__restrict__ boff16,
-             const uint32_t *__restrict__ blen, const uint32_t *__restrict__ pos, uint32_t n, uint8_t *__restrict__ exists)
+             const uint32_t *__restrict__ blen, const uint32_t *__restrict__ pos, uint32_t n, uint8_t *__restrict__ exists,
+             uint32_t *__restrict__ old_vchunks)
 {
     const uint32_t g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (g >= n) return;
@@ -811,32 +848,83 @@ k_key_exists(StoreDev st, const uint4 *__restrict__ bounds, const uint32_t *__re
         }
         eq = __all_sync(0xffffffffu, eq);
     }
-    if (lane == 0) exists[g] = eq ? 1 : 0;
+    if (lane == 0) {
+        exists[g] = eq ? 1 : 0;
+        old_vchunks[g] = eq ? (st.vlen[r] + 15) >> 4 : 0;
+    }
 }
 
-// one CTA per piece: copy n16 chunks from (sel ? srcB : srcA) + src16 to dst + dst16
-struct CopyPiece {
-    uint64_t src16, dst16;
-    uint32_t n16, sel;
+// The store is a HEAP of key / value bytes plus a directory sorted by key.  A committed batch appends the bytes of its
+// puts at the slab tails and rebuilds only the directory: every surviving record moves by (#inserts at or before it) -
+// (#deletes before it), every insert lands at (its lower bound) + (#inserts before it) - (#deletes before it).
+// ins_pos / del_pos / rep_pos are ascending; entries are packed like StoreDev::dir.
+struct DirArrays {
+    uint32_t *koff16;
+    uint16_t *klen;
+    uint64_t *voff16;
+    uint32_t *vlen;
+    uint4 *dir;
 };
 
-__global__ void __launch_bounds__(256)
-k_seg_copy(const uint4 *__restrict__ srcA, const uint4 *__restrict__ srcB, const CopyPiece *__restrict__ pieces,
-           uint32_t npieces, uint4 *__restrict__ dst)
+__device__ __forceinline__ uint32_t lower_bound_u32(const uint32_t *a, uint32_t n, uint32_t v)
 {
-    for (uint32_t p = blockIdx.x; p < npieces; p += gridDim.x) {
-        const CopyPiece pc = pieces[p];
-        const uint4 *s = (pc.sel ? srcB : srcA) + pc.src16;
-        uint4 *d = dst + pc.dst16;
-        for (uint32_t c = threadIdx.x; c < pc.n16; c += blockDim.x * 4) {
-            uint4 v[4];
-#pragma unroll
-            for (int j = 0; j < 4; j++)
-                if (c + j * blockDim.x < pc.n16) v[j] = ldg_stream(s + c + j * blockDim.x);
-#pragma unroll
-            for (int j = 0; j < 4; j++)
-                if (c + j * blockDim.x < pc.n16) stg_stream(d + c + j * blockDim.x, v[j]);
+    uint32_t lo = 0, hi = n;
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (a[mid] < v) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+__device__ __forceinline__ void dir_store(const DirArrays &d, uint32_t at, const uint4 &e)
+{
+    d.koff16[at] = e.x;
+    d.klen[at] = (uint16_t)(e.y & 0xffffu);
+    d.voff16[at] = ((uint64_t)(e.y >> 16) << 32) | e.w;
+    d.vlen[at] = e.z;
+    d.dir[at] = e;
+}
+
+__global__ void __launch_bounds__(256)
+k_dir_merge(StoreDev old, const uint32_t *__restrict__ ins_pos, const uint4 *__restrict__ ins_ent, uint32_t n_ins,
+            const uint32_t *__restrict__ del_pos, uint32_t n_del, const uint32_t *__restrict__ rep_pos,
+            const uint4 *__restrict__ rep_ent, uint32_t n_rep, DirArrays out)
+{
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < old.n) {
+        const uint32_t i = (uint32_t)t;
+        const uint32_t db = lower_bound_u32(del_pos, n_del, i);
+        if (db < n_del && del_pos[db] == i) return;  // deleted
+        const uint32_t ib = lower_bound_u32(ins_pos, n_ins, i + 1);  // inserts with pos <= i sort in front of record i
+        uint4 e = old.dir[i];
+        const uint32_t rb = lower_bound_u32(rep_pos, n_rep, i);
+        if (rb < n_rep && rep_pos[rb] == i) {  // same key, new value
+            const uint4 r = rep_ent[rb];
+            e.y = (e.y & 0xffffu) | (r.y & 0xffff0000u);
+            e.z = r.z;
+            e.w = r.w;
         }
+        dir_store(out, i + ib - db, e);
+    } else if (t < (uint64_t)old.n + n_ins) {
+        const uint32_t k = (uint32_t)(t - old.n);
+        const uint32_t p = ins_pos[k];
+        dir_store(out, p + k - lower_bound_u32(del_pos, n_del, p), ins_ent[k]);
+    }
+}
+
+// layout compaction: every record's key and value copied to its place in fresh, contiguous, sorted slabs (warp per record)
+__global__ void __launch_bounds__(256)
+k_relocate(StoreDev old, const uint32_t *__restrict__ nkoff16, const uint64_t *__restrict__ nvoff16, uint4 *__restrict__ nk,
+           uint4 *__restrict__ nv)
+{
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t r = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < old.n; r += warps) {
+        const uint32_t kc = ((uint32_t)old.klen[r] + 15) >> 4, vc = (old.vlen[r] + 15) >> 4;
+        const uint4 *ks = old.kslab + old.koff16[r], *vs = old.vslab + old.voff16[r];
+        uint4 *kd = nk + nkoff16[r], *vd = nv + nvoff16[r];
+        for (uint32_t c = lane; c < kc; c += 32) kd[c] = ldg_stream(ks + c);
+        for (uint32_t c = lane; c < vc; c += 32) stg_stream(vd + c, ldg_stream(vs + c));
     }
 }
 
@@ -1079,8 +1167,13 @@ int upload_layout(kb_ctx *ctx, const Resolved &R)
 
 }  // namespace
 
-// host copy of the slab offsets, kept for algorithmic-byte accounting only
-static inline std::vector<uint32_t> &host_koff16(kb_ctx *ctx) { return ctx->h_koff16; }
+// algorithmic key bytes of `n_rec` examined records: the store's average padded key + 10 B of directory fields each
+static inline uint64_t scan_alg_bytes(kb_ctx *ctx, uint64_t n_rec)
+{
+    const uint64_t n = std::max<uint64_t>(ctx->st.n, 1);
+    const uint64_t live16 = ctx->kused16 > ctx->garbage_k16 ? ctx->kused16 - ctx->garbage_k16 : 0;
+    return n_rec * 10 + (uint64_t)((double)live16 * 16.0 / (double)n * (double)n_rec);
+}
 
 // persistent decode pass: one CTA per SM, independent warps; geometry from the store's longest key (kb_decode.cuh)
 template <int MAXW, int KK>
@@ -1106,8 +1199,9 @@ static int launch_decode(kb_ctx *ctx, uint32_t ntiles, uint64_t alg_bytes, const
 {
     static const uint32_t force_k = getenv("KB_DECODE_K") ? (uint32_t)atoi(getenv("KB_DECODE_K")) : 0;
     static const uint32_t force_w = getenv("KB_DECODE_WARPS") ? (uint32_t)atoi(getenv("KB_DECODE_WARPS")) : 0;
+    static const uint32_t force_nks = getenv("KB_DECODE_NKS") ? (uint32_t)atoi(getenv("KB_DECODE_NKS")) : 0;
     size_t smem = 0;
-    const DecGeom g = decode_geometry(ctx->max_key_chunks, ntiles, force_k, force_w, &smem);
+    const DecGeom g = decode_geometry(ctx->max_key_chunks, ntiles, force_k, force_nks, force_w, &smem);
 #define KB_DEC_K(W)                                                                                     \
     switch (g.K) {                                                                                      \
     case 1: return launch_decode_t<W, 1>(ctx, g, smem, alg_bytes, mode, d_tiles, d_meta);               \
@@ -1155,9 +1249,7 @@ static int launch_scan_core(kb_ctx *ctx, const Resolved &R, const ScanMode &mode
     TileState *d_ts = (TileState *)((uint8_t *)ctx->d_tcnt.p + 64);
     ReqOut *d_rout = (ReqOut *)ctx->d_reqout.p;
     // algorithmic bytes of the decode pass: key bytes of the examined records + 10 B of offsets/lengths each
-    uint64_t kbytes = 0;
-    for (auto &r : R.reqs)
-        kbytes += (uint64_t)(ctx->h_koff16[r.hi] - ctx->h_koff16[r.lo]) * 16 + (uint64_t)(r.hi - r.lo) * 10;
+    const uint64_t kbytes = scan_alg_bytes(ctx, R.n_records);
     if (!ctx->d_ctrs.p) {  // work counters [0..7] + error flag [8]: zero once, every consumer leaves the counters at zero
         KB_TRY(dbuf_ensure(ctx, ctx->d_ctrs, 256));
         KB_CUDA(ctx, cudaMemsetAsync(ctx->d_ctrs.p, 0, 256, ctx->stream));
@@ -1321,9 +1413,14 @@ extern "C" int kb_range_batch(kb_ctx *ctx, const kb_range_req *reqs, uint64_t nr
     // record intervals), so the gather is enqueued right behind the placement and the only synchronisation left is
     // the final one (the arena is pooled, so steady-state calls reuse it).
     const bool want_kvs = out_mode != KB_OUT_COUNT && R.total_sel > 0;
+    // (a heap has no "bytes of an interval": every examined record could be emitted with the store's largest pair, and
+    // no answer can exceed one copy of everything per request that could return it all)
     uint64_t ub_bytes = 0;
-    for (auto &r : R.reqs)
-        ub_bytes += ((uint64_t)(ctx->h_koff16[r.hi] - ctx->h_koff16[r.lo]) + (ctx->h_voff16[r.hi] - ctx->h_voff16[r.lo])) * 16;
+    for (auto &r : R.reqs) {
+        uint64_t cap = (uint64_t)(r.hi - r.lo);
+        if (r.limit > 0) cap = std::min<uint64_t>(cap, (uint64_t)r.limit);
+        ub_bytes += std::min<uint64_t>(cap * ctx->max_kv_chunks, ctx->kused16 + ctx->vused16) * 16;
+    }
     // a wire element is at most 48 bytes of tags / varints longer than its key + value (and the key loses 13)
     if (wire) ub_bytes += (uint64_t)R.total_sel * 48;
     kb_result *res = kb_result_new(1, out_mode);
@@ -1673,13 +1770,14 @@ extern "C" int kb_get_batch(kb_ctx *ctx, const kb_get_req *reqs, uint64_t n, int
     }
     KB_TRY(dbuf_ensure(ctx, ctx->d_bounds, chunks * 16 + n * 8 + 64));
     KB_TRY(dbuf_ensure(ctx, ctx->d_bres, std::max<uint64_t>(n, 1) * 4));
-    // per-read outputs on the device: [mod_rev u64][rec u32][vlen u32][status u8]
-    KB_TRY(dbuf_ensure(ctx, ctx->d_reqout, std::max<uint64_t>(n, 1) * 17 + 64));
+    // per-read outputs on the device: [mod_rev u64][voff16 u64][rec u32][vlen u32][status u8]
+    KB_TRY(dbuf_ensure(ctx, ctx->d_reqout, std::max<uint64_t>(n, 1) * 25 + 64));
     KB_CUDA(ctx, cudaMemcpyAsync(ctx->d_bounds.p, hs, chunks * 16 + n * 8, cudaMemcpyHostToDevice, ctx->stream));
     const uint32_t *d_boff = (const uint32_t *)((const uint8_t *)ctx->d_bounds.p + chunks * 16);
     GetOut go;
     go.mod_rev = (uint64_t *)ctx->d_reqout.p;
-    go.rec = (uint32_t *)(go.mod_rev + n);
+    go.voff16 = go.mod_rev + n;
+    go.rec = (uint32_t *)(go.voff16 + n);
     go.vlen = go.rec + n;
     go.status = (uint8_t *)(go.vlen + n);
     if (n) {
@@ -1705,6 +1803,7 @@ extern "C" int kb_get_batch(kb_ctx *ctx, const kb_get_req *reqs, uint64_t n, int
     uint64_t *h_mrev = (uint64_t *)(hg + st_off), *h_voff = h_mrev + n;
     uint32_t *h_rec = (uint32_t *)(h_voff + n), *h_vlen = h_rec + n;
     if (n) {
+        cudaMemcpyAsync(h_voff, go.voff16, n * 8, cudaMemcpyDeviceToHost, ctx->stream);  // slab chunk; rewritten below
         cudaMemcpyAsync(h_mrev, go.mod_rev, n * 8, cudaMemcpyDeviceToHost, ctx->stream);
         cudaMemcpyAsync(h_rec, go.rec, n * 4, cudaMemcpyDeviceToHost, ctx->stream);
         cudaMemcpyAsync(h_vlen, go.vlen, n * 4, cudaMemcpyDeviceToHost, ctx->stream);
@@ -1719,6 +1818,7 @@ extern "C" int kb_get_batch(kb_ctx *ctx, const kb_get_req *reqs, uint64_t n, int
     std::vector<GatherJob> jobs;
     uint64_t nbytes = 0;
     for (uint64_t i = 0; i < n; i++) {
+        const uint64_t src16 = h_voff[i];
         h_voff[i] = 0;
         if (h_status[i] != KB_GET_FOUND) {
             if (h_status[i] == KB_GET_NOT_FOUND) h_vlen[i] = 0;
@@ -1726,7 +1826,7 @@ extern "C" int kb_get_batch(kb_ctx *ctx, const kb_get_req *reqs, uint64_t n, int
         }
         GatherJob j;
         j.dst16 = nbytes / 16;
-        j.vsrc16 = ctx->h_voff16[h_rec[i]];
+        j.vsrc16 = src16;
         j.ksrc16 = 0;
         j.nk = 0;
         j.nv = (h_vlen[i] + 15) / 16;
@@ -1906,7 +2006,15 @@ extern "C" int kb_compact_view_get(const kb_result *res, kb_compact_view *v)
 
 
 // ------------------------------------------------------------------------------------------------
-// kb_apply_batch: one committed BatchWrite merged into the HBM snapshot
+// kb_apply_batch: one committed BatchWrite merged into the HBM snapshot.
+//
+// Round 1 rebuilt both slabs and merged the whole directory on the host for every batch (O(store bytes)).  Now the
+// store is a heap + a sorted directory: the bytes of the batch's puts are appended at the slab tails (a value that
+// replaces an existing key leaves the old bytes behind as garbage; the key bytes are reused), and only the directory
+// (34 bytes per record) is rebuilt, on the device, by k_dir_merge.  The decode pass stages a step's keys with one bulk
+// copy when they lie within one ring slot of each other and reads them in place otherwise, so records appended out of
+// key order cost a slower step, not a wrong one.  When more than 1/32 of the records are out of place, or a quarter of a
+// slab is garbage, store_compact_layout rewrites the slabs contiguously in key order (O(store), amortised O(1) per op).
 // ------------------------------------------------------------------------------------------------
 namespace {
 struct ApplyOp {
@@ -1915,18 +2023,118 @@ struct ApplyOp {
     uint64_t order;
 };
 
-// append `n16` chunks starting at src16 (of source `sel`) as pieces of at most 4096 chunks
-void push_pieces(std::vector<CopyPiece> &out, uint64_t src16, uint64_t dst16, uint64_t n16, uint32_t sel)
+// grow a slab to hold `need16` chunks (+ slack), keeping its first `used16` chunks
+int slab_reserve(kb_ctx *ctx, DBuf &slab, uint64_t used16, uint64_t need16)
 {
-    while (n16) {
-        const uint32_t k = (uint32_t)std::min<uint64_t>(n16, 4096);
-        out.push_back(CopyPiece{src16, dst16, k, sel});
-        src16 += k;
-        dst16 += k;
-        n16 -= k;
-    }
+    const size_t need = (size_t)need16 * 16 + 64;
+    if (slab.p && slab.cap >= need) return KB_OK;
+    DBuf nb;
+    KB_TRY(dbuf_ensure(ctx, nb, need + need / 2));
+    if (slab.p && used16)
+        KB_CUDA(ctx, cudaMemcpyAsync(nb.p, slab.p, (size_t)used16 * 16, cudaMemcpyDeviceToDevice, ctx->stream));
+    KB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (slab.p) cudaFree(slab.p);
+    slab = nb;
+    return KB_OK;
 }
 }  // namespace
+
+// the directory arrays that are NOT live (k_dir_merge / store_compact_layout write them, then the sets swap)
+static int dir_spare_ensure(kb_ctx *ctx, uint64_t n)
+{
+    KB_TRY(dbuf_ensure(ctx, ctx->s_koff16, (n + 1) * 4));
+    KB_TRY(dbuf_ensure(ctx, ctx->s_klen, (n + 1) * 2));
+    KB_TRY(dbuf_ensure(ctx, ctx->s_voff16, (n + 1) * 8));
+    KB_TRY(dbuf_ensure(ctx, ctx->s_vlen, (n + 1) * 4));
+    KB_TRY(dbuf_ensure(ctx, ctx->s_dir, (n + 1) * 16));
+    return KB_OK;
+}
+
+static void dir_swap(kb_ctx *ctx, uint64_t n)
+{
+    std::swap(ctx->d_koff16, ctx->s_koff16);
+    std::swap(ctx->d_klen, ctx->s_klen);
+    std::swap(ctx->d_voff16, ctx->s_voff16);
+    std::swap(ctx->d_vlen, ctx->s_vlen);
+    std::swap(ctx->d_dir, ctx->s_dir);
+    ctx->st.koff16 = (const uint32_t *)ctx->d_koff16.p;
+    ctx->st.klen = (const uint16_t *)ctx->d_klen.p;
+    ctx->st.voff16 = (const uint64_t *)ctx->d_voff16.p;
+    ctx->st.vlen = (const uint32_t *)ctx->d_vlen.p;
+    ctx->st.dir = (const uint4 *)ctx->d_dir.p;
+    ctx->st.kslab = (const uint4 *)ctx->d_kslab.p;
+    ctx->st.vslab = (const uint4 *)ctx->d_vslab.p;
+    ctx->st.n = (uint32_t)n;
+}
+
+// rewrite both slabs contiguously in key order (also what kb_dump writes); the caller holds ctx->mu
+int store_compact_layout(kb_ctx *ctx)
+{
+    const uint64_t n = ctx->st.n;
+    if (ctx->displaced == 0 && ctx->garbage_k16 == 0 && ctx->garbage_v16 == 0) return KB_OK;
+    std::vector<uint16_t> klen(std::max<uint64_t>(n, 1));
+    std::vector<uint32_t> vlen(std::max<uint64_t>(n, 1)), nko(n + 1);
+    std::vector<uint64_t> nvo(n + 1);
+    if (n) {
+        KB_CUDA(ctx, cudaMemcpyAsync(klen.data(), ctx->st.klen, n * 2, cudaMemcpyDeviceToHost, ctx->stream));
+        KB_CUDA(ctx, cudaMemcpyAsync(vlen.data(), ctx->st.vlen, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        KB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    uint64_t kacc = 0, vacc = 0;
+    for (uint64_t i = 0; i < n; i++) {
+        nko[i] = (uint32_t)kacc;
+        nvo[i] = vacc;
+        kacc += ((uint32_t)klen[i] + 15) / 16;
+        vacc += ((uint64_t)vlen[i] + 15) / 16;
+    }
+    nko[n] = (uint32_t)kacc;
+    nvo[n] = vacc;
+    DBuf nk, nv;
+    KB_TRY(dbuf_ensure(ctx, nk, kacc * 16 + 64));
+    int rc = dbuf_ensure(ctx, nv, vacc * 16 + 64);
+    if (rc == KB_OK) rc = dir_spare_ensure(ctx, n);
+    if (rc != KB_OK) {
+        cudaFree(nk.p);
+        if (nv.p) cudaFree(nv.p);
+        return rc;
+    }
+    cudaMemsetAsync((uint8_t *)nk.p + kacc * 16, 0, 64, ctx->stream);
+    cudaMemsetAsync((uint8_t *)nv.p + vacc * 16, 0, 64, ctx->stream);
+    cudaMemcpyAsync(ctx->s_koff16.p, nko.data(), (n + 1) * 4, cudaMemcpyHostToDevice, ctx->stream);
+    cudaMemcpyAsync(ctx->s_voff16.p, nvo.data(), (n + 1) * 8, cudaMemcpyHostToDevice, ctx->stream);
+    if (n) {
+        KB_LAUNCH(ctx, "k_relocate", 2 * (kacc + vacc) * 16,
+                  (k_relocate<<<148 * 8, 256, 0, ctx->stream>>>(ctx->st, (const uint32_t *)ctx->s_koff16.p,
+                                                               (const uint64_t *)ctx->s_voff16.p, (uint4 *)nk.p, (uint4 *)nv.p)));
+        cudaMemcpyAsync(ctx->s_klen.p, ctx->st.klen, n * 2, cudaMemcpyDeviceToDevice, ctx->stream);
+        cudaMemcpyAsync(ctx->s_vlen.p, ctx->st.vlen, n * 4, cudaMemcpyDeviceToDevice, ctx->stream);
+    }
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);  // the host vectors die here; the old slabs are released below
+    if (e != cudaSuccess) {
+        cudaFree(nk.p);
+        cudaFree(nv.p);
+        ctx->loaded = false;
+        return kb_cuda_fail(ctx, e, "layout compaction");
+    }
+    cudaFree(ctx->d_kslab.p);
+    cudaFree(ctx->d_vslab.p);
+    ctx->d_kslab = nk;
+    ctx->d_vslab = nv;
+    dir_swap(ctx, n);
+    rc = store_pack_dir(ctx);
+    if (rc == KB_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = KB_ECUDA;
+    if (rc != KB_OK) {
+        ctx->loaded = false;
+        return rc;
+    }
+    ctx->kused16 = kacc;
+    ctx->vused16 = vacc;
+    ctx->key_bytes = kacc * 16;
+    ctx->val_bytes = vacc * 16;
+    ctx->garbage_k16 = ctx->garbage_v16 = ctx->displaced = 0;
+    ctx->layout_compactions++;
+    return KB_OK;
+}
 
 static int apply_batch_locked(kb_ctx *ctx, const kb_write_op *ops, uint64_t n_ops);
 
@@ -2005,179 +2213,144 @@ static int apply_batch_locked(kb_ctx *ctx, const kb_write_op *ops, uint64_t n_op
         if (i + 1 == all.size() || all[i + 1].key != all[i].key) m.push_back(std::move(all[i]));
     const uint64_t M = m.size();
 
-    // 2. op keys (and PUT values) as padded slabs on the device; positions by k_search
-    uint64_t kchunks = 0, vchunks = 0;
-    for (auto &o : m) {
-        kchunks += (o.key.size() + 15) / 16 + 3;
-        if (o.type == KB_OP_PUT) vchunks += (o.val.size() + 15) / 16;
-    }
-    KB_TRY(hbuf_ensure(ctx, ctx->h_stage, kchunks * 16 + M * 8 + vchunks * 16 + 256));
+    // 2. op keys as a padded bound slab on the device; lower bound and exact-match test of every op key
+    uint64_t kchunks = 0;
+    for (auto &o : m) kchunks += (o.key.size() + 15) / 16 + 3;
+    KB_TRY(hbuf_ensure(ctx, ctx->h_stage, kchunks * 16 + M * 8 + 256));
     uint8_t *hs = (uint8_t *)ctx->h_stage.p;
     memset(hs, 0, kchunks * 16);
     uint32_t *hboff = (uint32_t *)(hs + kchunks * 16), *hblen = hboff + M;
-    uint8_t *hv = hs + kchunks * 16 + M * 8;
-    hv = (uint8_t *)(((uintptr_t)hv + 15) & ~(uintptr_t)15);
-    memset(hv, 0, vchunks * 16);
-    std::vector<uint64_t> op_k16(M), op_v16(M);
-    uint64_t kc = 0, vc = 0;
+    uint64_t kc = 0;
     for (uint64_t i = 0; i < M; i++) {
         hboff[i] = (uint32_t)kc;
         hblen[i] = (uint32_t)m[i].key.size();
         if (!m[i].key.empty()) memcpy(hs + kc * 16, m[i].key.data(), m[i].key.size());
-        op_k16[i] = kc;
         kc += (m[i].key.size() + 15) / 16 + 3;
-        op_v16[i] = vc;
-        if (m[i].type == KB_OP_PUT) {
-            if (!m[i].val.empty()) memcpy(hv + vc * 16, m[i].val.data(), m[i].val.size());
-            vc += (m[i].val.size() + 15) / 16;
-        }
     }
-    // temporaries of this call: released on every path out (the new slabs only until they are adopted)
-    struct Temps {
-        DBuf opv, nk_slab, nv_slab, pieces;
-        ~Temps()
-        {
-            for (DBuf *b : {&opv, &nk_slab, &nv_slab, &pieces})
-                if (b->p) cudaFree(b->p);
-        }
-    } T;
-    DBuf &d_opv = T.opv;
     KB_TRY(dbuf_ensure(ctx, ctx->d_bounds, kchunks * 16 + M * 8 + 64));
-    KB_TRY(dbuf_ensure(ctx, ctx->d_bres, M * 4 + M + 64));
-    KB_TRY(dbuf_ensure(ctx, d_opv, vchunks * 16 + 64));
+    KB_TRY(dbuf_ensure(ctx, ctx->d_bres, M * 9 + 64));
     KB_CUDA(ctx, cudaMemcpyAsync(ctx->d_bounds.p, hs, kchunks * 16 + M * 8, cudaMemcpyHostToDevice, ctx->stream));
-    if (vchunks) KB_CUDA(ctx, cudaMemcpyAsync(d_opv.p, hv, vchunks * 16, cudaMemcpyHostToDevice, ctx->stream));
     const uint32_t *d_boff = (const uint32_t *)((const uint8_t *)ctx->d_bounds.p + kchunks * 16);
-    uint32_t *d_pos = (uint32_t *)ctx->d_bres.p;
-    uint8_t *d_exists = (uint8_t *)(d_pos + M);
+    uint32_t *d_pos = (uint32_t *)ctx->d_bres.p, *d_oldv = d_pos + M;
+    uint8_t *d_exists = (uint8_t *)(d_oldv + M);
     const unsigned sg = (unsigned)((M * 32 + 127) / 128);
     KB_LAUNCH(ctx, "k_search", M * 64,
               (k_search<<<sg, 128, 0, ctx->stream>>>(ctx->st, (const uint4 *)ctx->d_bounds.p, d_boff, d_boff + M, (uint32_t)M,
                                                      d_pos)));
     KB_LAUNCH(ctx, "k_key_exists", M * 320,
               (k_key_exists<<<sg, 128, 0, ctx->stream>>>(ctx->st, (const uint4 *)ctx->d_bounds.p, d_boff, d_boff + M, d_pos,
-                                                         (uint32_t)M, d_exists)));
-    std::vector<uint32_t> pos(M);
+                                                         (uint32_t)M, d_exists, d_oldv)));
+    std::vector<uint32_t> pos(M), oldv(M);
     std::vector<uint8_t> exists(M);
     KB_CUDA(ctx, cudaMemcpyAsync(pos.data(), d_pos, M * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    KB_CUDA(ctx, cudaMemcpyAsync(oldv.data(), d_oldv, M * 4, cudaMemcpyDeviceToHost, ctx->stream));
     KB_CUDA(ctx, cudaMemcpyAsync(exists.data(), d_exists, M, cudaMemcpyDeviceToHost, ctx->stream));
     cudaError_t e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) return kb_cuda_fail(ctx, e, "apply: search");
 
-    // 3. merge the record directory on the host; emit the slab copies as pieces
+    // 3. classify; lay the appended bytes out behind the slab tails
     const uint64_t N = ctx->st.n;
-    uint64_t n_ins = 0, n_del = 0;
+    std::vector<uint32_t> ins_pos, del_pos, rep_pos;
+    std::vector<uint4> ins_ent, rep_ent;
+    std::vector<uint8_t> kimg, vimg;  // images of the appended key / value chunks
+    uint64_t ktail = ctx->kused16, vtail = ctx->vused16, garbage_k = 0, garbage_v = 0;
+    uint32_t max_k = ctx->max_key_chunks, max_kv = ctx->max_kv_chunks;
+    auto append = [](std::vector<uint8_t> &img, const std::string &b) {
+        const size_t at = img.size(), n16 = (b.size() + 15) / 16;
+        img.resize(at + n16 * 16, 0);
+        if (!b.empty()) memcpy(img.data() + at, b.data(), b.size());
+        return (uint64_t)n16;
+    };
+    auto entry = [](uint64_t ko, size_t kl, uint64_t vo, size_t vl) {
+        return make_uint4((uint32_t)ko, (uint32_t)kl | ((uint32_t)(vo >> 32) << 16), (uint32_t)vl, (uint32_t)vo);
+    };
     for (uint64_t i = 0; i < M; i++) {
-        n_ins += m[i].type == KB_OP_PUT;
-        n_del += exists[i];
+        if (m[i].type == KB_OP_PUT) {
+            const uint64_t vo = vtail;
+            const uint64_t nv = append(vimg, m[i].val);
+            vtail += nv;
+            const uint64_t nk = (m[i].key.size() + 15) / 16;
+            if (exists[i]) {  // same key: the key bytes stay where they are, the old value becomes garbage
+                rep_pos.push_back(pos[i]);
+                rep_ent.push_back(entry(0, 0, vo, m[i].val.size()));
+                garbage_v += oldv[i];
+            } else {
+                ins_pos.push_back(pos[i]);
+                ins_ent.push_back(entry(ktail, m[i].key.size(), vo, m[i].val.size()));
+                ktail += append(kimg, m[i].key);
+            }
+            max_k = std::max<uint32_t>(max_k, (uint32_t)nk);
+            max_kv = std::max<uint32_t>(max_kv, (uint32_t)std::min<uint64_t>(nk + nv, 0xFFFFFFFFu));
+        } else if (exists[i]) {
+            del_pos.push_back(pos[i]);
+            garbage_k += (m[i].key.size() + 15) / 16;
+            garbage_v += oldv[i];
+        }
     }
+    const uint64_t n_ins = ins_pos.size(), n_del = del_pos.size(), n_rep = rep_pos.size();
     const uint64_t N2 = N + n_ins - n_del;
     if (N2 >= 0xFFFFFFFEull) return kb_fail(ctx, KB_ELIMIT, "too many records");
-    std::vector<uint32_t> koff2(N2 + 1), vlen2(std::max<uint64_t>(N2, 1));
-    std::vector<uint16_t> klen2(std::max<uint64_t>(N2, 1));
-    std::vector<uint64_t> voff2(N2 + 1);
-    std::vector<CopyPiece> kp, vp;
-    uint64_t kacc = 0, vacc = 0, w = 0;
-    auto copy_base = [&](uint64_t a, uint64_t b) {  // surviving base records [a, b)
-        if (a >= b) return;
-        const uint64_t k0 = ctx->h_koff16[a], k1 = ctx->h_koff16[b], v0 = ctx->h_voff16[a], v1 = ctx->h_voff16[b];
-        push_pieces(kp, k0, kacc, k1 - k0, 0);
-        push_pieces(vp, v0, vacc, v1 - v0, 0);
-        for (uint64_t r = a; r < b; r++, w++) {
-            koff2[w] = (uint32_t)(kacc + (ctx->h_koff16[r] - k0));
-            voff2[w] = vacc + (ctx->h_voff16[r] - v0);
-            klen2[w] = ctx->h_klen[r];
-            vlen2[w] = ctx->h_vlen[r];
-        }
-        kacc += k1 - k0;
-        vacc += v1 - v0;
-    };
-    uint64_t next_base = 0;
-    for (uint64_t i = 0; i < M; i++) {
-        copy_base(next_base, pos[i]);
-        next_base = pos[i] + (exists[i] ? 1 : 0);  // the matched base record is replaced or dropped
-        if (m[i].type == KB_OP_PUT) {
-            const uint64_t nk = (m[i].key.size() + 15) / 16, nv = (m[i].val.size() + 15) / 16;
-            push_pieces(kp, op_k16[i], kacc, nk, 1);
-            push_pieces(vp, op_v16[i], vacc, nv, 1);
-            ctx->max_kv_chunks = std::max<uint32_t>(ctx->max_kv_chunks, (uint32_t)std::min<uint64_t>(nk + nv, 0xFFFFFFFFu));
-            ctx->max_key_chunks = std::max<uint32_t>(ctx->max_key_chunks, (uint32_t)nk);
-            koff2[w] = (uint32_t)kacc;
-            voff2[w] = vacc;
-            klen2[w] = (uint16_t)m[i].key.size();
-            vlen2[w] = (uint32_t)m[i].val.size();
-            w++;
-            kacc += nk;
-            vacc += nv;
-            if (kacc > 0xFFFFFFF0ull) return kb_fail(ctx, KB_ELIMIT, "key slab exceeds 64 GiB");
-        }
-    }
-    copy_base(next_base, N);
-    koff2[N2] = (uint32_t)kacc;
-    voff2[N2] = vacc;
+    if (ktail > 0xFFFFFFF0ull) return kb_fail(ctx, KB_ELIMIT, "key slab exceeds 64 GiB");
+    if (n_ins + n_del + n_rep == 0) return KB_OK;  // only deletes of absent keys
 
-    // 4. new slabs on the device: segmented copy from the old slab (sel 0) and the op slabs (sel 1)
-    DBuf &nk_slab = T.nk_slab, &nv_slab = T.nv_slab, &d_pieces = T.pieces;
-    int rc = dbuf_ensure(ctx, nk_slab, kacc * 16 + 64);
-    if (rc == KB_OK) rc = dbuf_ensure(ctx, nv_slab, vacc * 16 + 64);
-    if (rc == KB_OK) rc = dbuf_ensure(ctx, d_pieces, (kp.size() + vp.size() + 1) * sizeof(CopyPiece));
-    if (rc != KB_OK) return rc;  // nothing of the live store has been touched yet
-    // the directory arrays grow in place (their old contents are about to be overwritten anyway)
-    rc = dbuf_ensure(ctx, ctx->d_koff16, (N2 + 1) * 4);
-    if (rc == KB_OK) rc = dbuf_ensure(ctx, ctx->d_klen, (N2 + 1) * 2);
-    if (rc == KB_OK) rc = dbuf_ensure(ctx, ctx->d_voff16, (N2 + 1) * 8);
-    if (rc == KB_OK) rc = dbuf_ensure(ctx, ctx->d_vlen, (N2 + 1) * 4);
-    if (rc != KB_OK) {
-        ctx->loaded = false;  // a directory array may have been released: the caller reloads
-        return rc;
-    }
-    cudaMemsetAsync((uint8_t *)nk_slab.p + kacc * 16, 0, 64, ctx->stream);
-    cudaMemsetAsync((uint8_t *)nv_slab.p + vacc * 16, 0, 64, ctx->stream);
-    CopyPiece *dp = (CopyPiece *)d_pieces.p;
-    cudaMemcpyAsync(dp, kp.data(), kp.size() * sizeof(CopyPiece), cudaMemcpyHostToDevice, ctx->stream);
-    cudaMemcpyAsync(dp + kp.size(), vp.data(), vp.size() * sizeof(CopyPiece), cudaMemcpyHostToDevice, ctx->stream);
-    if (!kp.empty()) {
-        KB_LAUNCH(ctx, "k_seg_copy", 2 * kacc * 16,
-                  (k_seg_copy<<<(unsigned)std::min<size_t>(kp.size(), 148 * 16), 256, 0, ctx->stream>>>(
-                      ctx->st.kslab, (const uint4 *)ctx->d_bounds.p, dp, (uint32_t)kp.size(), (uint4 *)nk_slab.p)));
-    }
-    if (!vp.empty()) {
-        KB_LAUNCH(ctx, "k_seg_copy", 2 * vacc * 16,
-                  (k_seg_copy<<<(unsigned)std::min<size_t>(vp.size(), 148 * 16), 256, 0, ctx->stream>>>(
-                      ctx->st.vslab, (const uint4 *)d_opv.p, dp + kp.size(), (uint32_t)vp.size(), (uint4 *)nv_slab.p)));
-    }
-    cudaMemcpyAsync(ctx->d_koff16.p, koff2.data(), (N2 + 1) * 4, cudaMemcpyHostToDevice, ctx->stream);
-    cudaMemcpyAsync(ctx->d_klen.p, klen2.data(), N2 * 2, cudaMemcpyHostToDevice, ctx->stream);
-    cudaMemcpyAsync(ctx->d_voff16.p, voff2.data(), (N2 + 1) * 8, cudaMemcpyHostToDevice, ctx->stream);
-    cudaMemcpyAsync(ctx->d_vlen.p, vlen2.data(), N2 * 4, cudaMemcpyHostToDevice, ctx->stream);
-    e = cudaStreamSynchronize(ctx->stream);
-    if (e != cudaSuccess) {
-        ctx->loaded = false;  // the directory on the device may be half written
-        return kb_cuda_fail(ctx, e, "apply: merge");
-    }
-    // 5. swap: the context adopts the new slabs, the old ones become the temporaries that are released on return
-    std::swap(ctx->d_kslab, nk_slab);
-    std::swap(ctx->d_vslab, nv_slab);
+    // 4. bytes to the slab tails (growing a slab copies its used part once; the live store is untouched until step 6)
+    KB_TRY(slab_reserve(ctx, ctx->d_kslab, ctx->kused16, ktail));
+    KB_TRY(slab_reserve(ctx, ctx->d_vslab, ctx->vused16, vtail));
     ctx->st.kslab = (const uint4 *)ctx->d_kslab.p;
     ctx->st.vslab = (const uint4 *)ctx->d_vslab.p;
-    ctx->st.koff16 = (const uint32_t *)ctx->d_koff16.p;
-    ctx->st.klen = (const uint16_t *)ctx->d_klen.p;
-    ctx->st.voff16 = (const uint64_t *)ctx->d_voff16.p;
-    ctx->st.vlen = (const uint32_t *)ctx->d_vlen.p;
-    ctx->st.n = (uint32_t)N2;
-    {
-        int prc = store_pack_dir(ctx);
-        if (prc == KB_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) prc = KB_ECUDA;
-        if (prc != KB_OK) {
-            ctx->loaded = false;
-            return prc;
-        }
+    const size_t tab_bytes = (n_ins + n_del + n_rep) * 4 + (n_ins + n_rep) * 16 + 64;
+    KB_TRY(hbuf_ensure(ctx, ctx->h_stage2, kimg.size() + vimg.size() + tab_bytes + 256));
+    uint8_t *h2 = (uint8_t *)ctx->h_stage2.p;
+    if (!kimg.empty()) memcpy(h2, kimg.data(), kimg.size());
+    if (!vimg.empty()) memcpy(h2 + kimg.size(), vimg.data(), vimg.size());
+    uint8_t *ht = h2 + ((kimg.size() + vimg.size() + 15) & ~(size_t)15);
+    uint4 *t_ins_ent = (uint4 *)ht, *t_rep_ent = t_ins_ent + n_ins;
+    uint32_t *t_ins_pos = (uint32_t *)(t_rep_ent + n_rep), *t_del_pos = t_ins_pos + n_ins, *t_rep_pos = t_del_pos + n_del;
+    if (n_ins) memcpy(t_ins_ent, ins_ent.data(), n_ins * 16), memcpy(t_ins_pos, ins_pos.data(), n_ins * 4);
+    if (n_rep) memcpy(t_rep_ent, rep_ent.data(), n_rep * 16), memcpy(t_rep_pos, rep_pos.data(), n_rep * 4);
+    if (n_del) memcpy(t_del_pos, del_pos.data(), n_del * 4);
+    KB_TRY(dbuf_ensure(ctx, ctx->d_bounds, tab_bytes + 64));  // the bound slab is no longer needed: reuse it for the tables
+    KB_TRY(dir_spare_ensure(ctx, N2));
+    if (!kimg.empty())
+        KB_CUDA(ctx, cudaMemcpyAsync((uint8_t *)ctx->d_kslab.p + ctx->kused16 * 16, h2, kimg.size(), cudaMemcpyHostToDevice, ctx->stream));
+    if (!vimg.empty())
+        KB_CUDA(ctx, cudaMemcpyAsync((uint8_t *)ctx->d_vslab.p + ctx->vused16 * 16, h2 + kimg.size(), vimg.size(),
+                                     cudaMemcpyHostToDevice, ctx->stream));
+    // key_less / decode read up to three chunks past a key: keep the slack behind the tails zero
+    KB_CUDA(ctx, cudaMemsetAsync((uint8_t *)ctx->d_kslab.p + ktail * 16, 0, 64, ctx->stream));
+    KB_CUDA(ctx, cudaMemsetAsync((uint8_t *)ctx->d_vslab.p + vtail * 16, 0, 64, ctx->stream));
+    KB_CUDA(ctx, cudaMemcpyAsync(ctx->d_bounds.p, ht, tab_bytes - 64, cudaMemcpyHostToDevice, ctx->stream));
+    // 5. the directory, rebuilt on the device into the spare set
+    const uint4 *d_ins_ent = (const uint4 *)ctx->d_bounds.p, *d_rep_ent = d_ins_ent + n_ins;
+    const uint32_t *d_ins_pos = (const uint32_t *)(d_rep_ent + n_rep), *d_del_pos = d_ins_pos + n_ins, *d_rep_pos = d_del_pos + n_del;
+    DirArrays out;
+    out.koff16 = (uint32_t *)ctx->s_koff16.p;
+    out.klen = (uint16_t *)ctx->s_klen.p;
+    out.voff16 = (uint64_t *)ctx->s_voff16.p;
+    out.vlen = (uint32_t *)ctx->s_vlen.p;
+    out.dir = (uint4 *)ctx->s_dir.p;
+    const uint64_t threads = N + n_ins;
+    KB_LAUNCH(ctx, "k_dir_merge", (N + N2) * 34,
+              (k_dir_merge<<<(unsigned)((threads + 255) / 256), 256, 0, ctx->stream>>>(ctx->st, d_ins_pos, d_ins_ent, (uint32_t)n_ins,
+                                                                                       d_del_pos, (uint32_t)n_del, d_rep_pos,
+                                                                                       d_rep_ent, (uint32_t)n_rep, out)));
+    e = cudaStreamSynchronize(ctx->stream);  // the staging buffers are reused by the next call
+    if (e != cudaSuccess) {
+        ctx->loaded = false;
+        return kb_cuda_fail(ctx, e, "apply: directory merge");
     }
-    ctx->h_koff16.swap(koff2);
-    ctx->h_voff16.swap(voff2);
-    ctx->h_klen.swap(klen2);
-    ctx->h_vlen.swap(vlen2);
-    ctx->key_bytes = kacc * 16;
-    ctx->val_bytes = vacc * 16;
+    // 6. the new snapshot becomes visible
+    dir_swap(ctx, N2);
+    ctx->kused16 = ktail;
+    ctx->vused16 = vtail;
+    ctx->key_bytes = ktail * 16;
+    ctx->val_bytes = vtail * 16;
+    ctx->garbage_k16 += garbage_k;
+    ctx->garbage_v16 += garbage_v;
+    ctx->displaced += n_ins;
+    ctx->max_key_chunks = max_k;
+    ctx->max_kv_chunks = max_kv;
+    if (ctx->displaced > std::max<uint64_t>(4096, N2 / 32) || ctx->garbage_k16 * 4 > ktail || ctx->garbage_v16 * 4 > vtail)
+        KB_TRY(store_compact_layout(ctx));
     return KB_OK;
 }

@@ -82,9 +82,9 @@ struct TabDev {
 };
 
 // control words of one match (gstate: [gcnt G+1][gfill G+1][ctl 16])
-enum { FC_NONMONO = 0, FC_CURSOR = 1, FC_NLARGE = 2, FC_NMED = 3, FC_ARRIVE = 4, FC_GEN = 5, FC_DONE = 6, FC_WORDS = 16 };
+enum { FC_NONMONO = 0, FC_CURSOR = 1, FC_NLARGE = 2, FC_NMED = 3, FC_ARRIVE = 4, FC_GEN = 5, FC_DONE = 6, FC_ABORT = 7, FC_WORDS = 16 };
 constexpr unsigned long long FAN_UNSET = ~0ull, FAN_BUSY = ~0ull - 1;
-constexpr uint32_t FAN_THREADS = 256;
+constexpr uint32_t FAN_THREADS = 512;  // one CTA per SM: fits beside the scan context's decode CTA or its two gather CTAs
 constexpr uint32_t BM_WORDS = 1024;  // 32768 event indices per shared-memory window (4 KiB: the CTA stays co-resident
                                      // with the scan context's shared-memory-heavy kernels)
 
@@ -103,7 +103,13 @@ struct FanScratch {
 __device__ __forceinline__ uint32_t ldcg32(const uint32_t *p) { return __ldcg(p); }
 __device__ __forceinline__ uint64_t ldcg64(const uint64_t *p) { return __ldcg((const unsigned long long *)p); }
 
-// grid barrier of a cooperative launch: `gen` only ever grows (the host passes the value it had before the launch)
+// Grid barrier.  The kernel is launched with ONE CTA per SM of modest size (512 threads, < 30 k registers, 4.5 KiB of
+// shared memory), which fits beside whatever the scan context has resident, so every CTA gets an SM while the others
+// spin; nothing this kernel waits for depends on work queued behind it.  (A cooperative launch would guarantee the same
+// but is gang-scheduled: measured, it waited for the scan context's persistent kernels to drain -- 247 us in a step
+// against 90 us alone -- and held k_search behind it.)  `gen` only ever grows; the host passes its value before the launch.
+// A barrier that does not complete within ~2 s raises FC_ABORT: every CTA then falls through to the end of the kernel
+// and the host fails the call instead of hanging.
 __device__ __forceinline__ void fan_grid_sync(uint32_t *ctl, uint32_t target)
 {
     __syncthreads();
@@ -114,7 +120,15 @@ __device__ __forceinline__ void fan_grid_sync(uint32_t *ctl, uint32_t target)
             __threadfence();
             atomicExch(&ctl[FC_GEN], target);
         } else {
-            while (*(volatile uint32_t *)&ctl[FC_GEN] != target) __nanosleep(64);
+            const long long t0 = clock64();
+            while (*(volatile uint32_t *)&ctl[FC_GEN] != target) {
+                __nanosleep(64);
+                if (clock64() - t0 > 4000000000ll) {
+                    atomicExch(&ctl[FC_ABORT], 1u);
+                    break;
+                }
+                if (*(volatile uint32_t *)&ctl[FC_ABORT]) break;
+            }
         }
         __threadfence();
     }
@@ -257,9 +271,9 @@ __device__ __forceinline__ void d_scatter(const FanScratch &sc, uint32_t n_event
     }
 }
 
-__device__ __forceinline__ uint32_t block_excl_scan_u32(uint32_t v, uint32_t *wsum /* 9 */, uint32_t &total)
+__device__ __forceinline__ uint32_t block_excl_scan_u32(uint32_t v, uint32_t *wsum /* 33 */, uint32_t &total)
 {
-    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
     uint32_t inc = v;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -270,16 +284,16 @@ __device__ __forceinline__ uint32_t block_excl_scan_u32(uint32_t v, uint32_t *ws
     __syncthreads();
     if (threadIdx.x == 0) {
         uint32_t run = 0;
-        for (int k = 0; k < 8; k++) {
+        for (uint32_t k = 0; k < nw; k++) {
             uint32_t x = wsum[k];
             wsum[k] = run;
             run += x;
         }
-        wsum[8] = run;
+        wsum[32] = run;
     }
     __syncthreads();
     const uint32_t ex = wsum[wid] + inc - v;
-    total = wsum[8];
+    total = wsum[32];
     __syncthreads();
     return ex;
 }
@@ -343,7 +357,7 @@ __device__ __forceinline__ void d_sort_medium(const FanScratch &sc, uint32_t *bm
     }
 }
 
-// ---- P3b: large groups: ordered expansion of the global bitmap; job = (large group, chunk of 256 words)
+// ---- P3b: large groups: ordered expansion of the global bitmap; job = (large group, chunk of FAN_THREADS words)
 __device__ __forceinline__ void d_expand_large(const FanScratch &sc, uint32_t *wsum, uint32_t *pre_sp)
 {
     uint32_t &pre_s = *pre_sp;
@@ -354,12 +368,12 @@ __device__ __forceinline__ void d_expand_large(const FanScratch &sc, uint32_t *w
         const uint32_t *bm = sc.bitmaps + (uint64_t)slot * sc.bm_words;
         // matches in the words before this chunk
         uint32_t part = 0;
-        for (uint32_t j = threadIdx.x; j < chunk * 256; j += blockDim.x) part += __popc(ldcg32(&bm[j]));
+        for (uint32_t j = threadIdx.x; j < chunk * FAN_THREADS; j += blockDim.x) part += __popc(ldcg32(&bm[j]));
         uint32_t tot;
         block_excl_scan_u32(part, wsum, tot);
         if (threadIdx.x == 0) pre_s = tot;
         __syncthreads();
-        const uint32_t wi = chunk * 256 + threadIdx.x;
+        const uint32_t wi = chunk * FAN_THREADS + threadIdx.x;
         uint32_t bits = wi < sc.bm_words ? ldcg32(&bm[wi]) : 0;
         uint32_t total;
         uint32_t at = (uint32_t)__ldcg(&sc.galloc[g]) + pre_s + block_excl_scan_u32(__popc(bits), wsum, total);
@@ -476,7 +490,8 @@ __device__ __forceinline__ void d_finish(const TabDev &tb, const FanScratch &sc,
     if (threadIdx.x == 0) {
         sc.wstart[W] = ws[32];
         sc.total[0] = ws[32];
-        sc.total[1] = ldcg32(&sc.ctl[FC_NONMONO]);  // k_expand_write picks its path from this copy
+        // k_expand_write picks its path from this copy; bit 32 = a grid barrier timed out (the answer is void)
+        sc.total[1] = (uint64_t)ldcg32(&sc.ctl[FC_NONMONO]) | ((uint64_t)ldcg32(&sc.ctl[FC_ABORT]) << 32);
     }
     // leave the scratch as the next call expects it (every other CTA has finished reading it)
     const uint32_t G = tb.n_groups;
@@ -488,11 +503,11 @@ __device__ __forceinline__ void d_finish(const TabDev &tb, const FanScratch &sc,
     if (threadIdx.x < FC_WORDS && threadIdx.x != FC_GEN) sc.ctl[threadIdx.x] = 0;
 }
 
-__global__ void __launch_bounds__(FAN_THREADS, 2)
+__global__ void __launch_bounds__(FAN_THREADS, 1)
 k_fanout(EvDev ev, TabDev tb, FanScratch sc)
 {
     __shared__ uint32_t bm[BM_WORDS];
-    __shared__ uint32_t wsum[9];
+    __shared__ uint32_t wsum[33];
     __shared__ uint32_t red[2];
     __shared__ uint64_t ws64[33];
     __shared__ uint32_t last_s;
@@ -580,7 +595,8 @@ k_expand_write(uint32_t n_ids, const uint64_t *__restrict__ wminrev, const uint3
 {
     const uint64_t n_deliveries = wstart[n_ids];
     if (n_deliveries > capacity) return;  // the host sees the total, grows the buffer and launches again
-    if (total[1] == 0)
+    if ((total[1] >> 32) != 0) return;  // aborted match
+    if ((uint32_t)total[1] == 0)
         d_expand_write(n_ids, wsrc, wlo, sorted, wstart, n_deliveries, out);
     else
         d_expand_write_general(n_ids, wminrev, wsrc, wn, sorted, pm, wstart, out);
@@ -819,7 +835,8 @@ extern "C" void kb_events_free(kb_ctx *ctx, kb_events_dev *ev)
 __global__ void k_publish_total(const uint64_t *__restrict__ total, uint64_t *host, uint64_t epoch)
 {
     if (threadIdx.x == 0) {
-        host[1] = *total;
+        host[1] = total[0];
+        host[2] = total[1] >> 32;  // 1: a grid barrier of k_fanout timed out
         __threadfence_system();
         *(volatile uint64_t *)host = epoch;
     }
@@ -854,7 +871,7 @@ static int match_locked(kb_ctx *ctx, const kb_events_dev *d, int out_mode, kb_re
     const uint32_t big_t = std::max<uint32_t>(1024, E / 64);
     const uint32_t max_large = (uint32_t)(seg_cap / big_t) + 1;
     const uint32_t bm_words = (E + 31) / 32;
-    const uint32_t chunks_per_group = (bm_words + 255) / 256;
+    const uint32_t chunks_per_group = (bm_words + FAN_THREADS - 1) / FAN_THREADS;
     const size_t gstate_words = (size_t)2 * (G + 1) + FC_WORDS;
     const size_t bitmap_bytes = std::max<size_t>((size_t)max_large * bm_words * 4, 16);
     // growing a buffer frees the old one: the "clean" state of the scratch is lost with it
@@ -938,13 +955,11 @@ static int match_locked(kb_ctx *ctx, const kb_events_dev *d, int out_mode, kb_re
             KB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fanout, (int)FAN_THREADS, 0));
             KB_CUDA(ctx, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
             if (per_sm < 1) return kb_fail(ctx, KB_ECUDA, "k_fanout does not fit on an SM");
-            T.fan_grid = sms * std::min(per_sm, 2);
+            T.fan_grid = sms;  // one CTA per SM: all of them are resident together (see fan_grid_sync)
         }
         sc.gen_base = T.fan_gen;
-        void *args[] = {(void *)&ev, (void *)&tb, (void *)&sc};
         KB_LAUNCH(ctx, "k_fanout", ev_bytes + (uint64_t)E * NL * 12 + (uint64_t)E * 16 + (uint64_t)W * 44,
-                  KB_CUDA(ctx, cudaLaunchCooperativeKernel((const void *)k_fanout, dim3((unsigned)T.fan_grid), dim3(FAN_THREADS),
-                                                          args, 0, ctx->stream)));
+                  (k_fanout<<<(unsigned)T.fan_grid, FAN_THREADS, 0, ctx->stream>>>(ev, tb, sc)));
         T.fan_gen += 3;  // three grid barriers per launch
     } else {
         // no events or no watchers: every list is empty
@@ -997,8 +1012,14 @@ static int match_locked(kb_ctx *ctx, const kb_events_dev *d, int out_mode, kb_re
                 return rc;
             }
             D = ctx->h_wpub[1];
+            if (ctx->h_wpub[2]) rc = kb_fail(ctx, KB_ECUDA, "watch match: a grid barrier timed out");
+            if (rc != KB_OK) {
+                pool_put_dev(ctx, d_out);
+                pool_put_host(ctx, h_out);
+                return rc;
+            }
         } else {
-            KB_CUDA(ctx, cudaMemcpyAsync(ctx->h_stage2.p, sc.total, 8, cudaMemcpyDeviceToHost, ctx->stream));
+            KB_CUDA(ctx, cudaMemcpyAsync(ctx->h_stage2.p, sc.total, 16, cudaMemcpyDeviceToHost, ctx->stream));
             kb_seg(ctx, "host:match_launch", tseg);
             e0 = cudaStreamSynchronize(ctx->stream);
             kb_seg(ctx, "host:match_sync", tseg);
@@ -1007,6 +1028,10 @@ static int match_locked(kb_ctx *ctx, const kb_events_dev *d, int out_mode, kb_re
                 return kb_cuda_fail(ctx, e0, "watch match");
             }
             D = *(uint64_t *)ctx->h_stage2.p;
+            if (((uint64_t *)ctx->h_stage2.p)[1] >> 32) {
+                pool_put_dev(ctx, d_out);
+                return kb_fail(ctx, KB_ECUDA, "watch match: a grid barrier timed out");
+            }
         }
         T.d_hint = D;
         if (D <= cap) break;
