@@ -356,7 +356,10 @@ def run_b200(args, rank: int, local_rank: int, world: int):
         t = torch.tensor(list(uid), dtype=torch.uint8, device="cuda")
         dist.broadcast(t, 0)
         uid = bytes(t.cpu().tolist())
-    eng.nccl_init(uid, rank, world)
+    # the cursor exchange runs on the fan-out context: it is off the scan call's critical path (round 1: 12 -> 51 us in front
+    # of every range batch at N = 1 -> 8) and the scan of step n reads at the revision the exchange of step n-1 agreed on
+    ceng = weng
+    ceng.nccl_init(uid, rank, world)
     evh = weng.events_upload(wl["events"])
     stream = torch.cuda.ExternalStream(eng.stream())
     wstream = torch.cuda.ExternalStream(weng.stream())
@@ -387,8 +390,12 @@ def run_b200(args, rank: int, local_rank: int, world: int):
         wthread = threading.Thread(target=worker, daemon=True)
         wthread.start()
 
+    readable = {"rev": 0}
+
     def fan_device():
         t0 = time.perf_counter()
+        _, readable["rev"] = ceng.cursor_allgather(local_rev)
+        pyt["cursor"] += time.perf_counter() - t0
         m = weng.watch_match_dev(evh, KB_OUT_DEVICE)
         d = m.n_deliveries
         m.close()
@@ -396,6 +403,7 @@ def run_b200(args, rank: int, local_rank: int, world: int):
         return d
 
     def fan_e2e():
+        _, readable["rev"] = ceng.cursor_allgather(local_rev)
         m = weng.watch_match(wl["events"], KB_OUT_HOST)
         d = m.n_deliveries
         dbytes = d * 4 + (m.n_watchers + 1) * 8
@@ -414,8 +422,6 @@ def run_b200(args, rank: int, local_rank: int, world: int):
         return a, b
 
     def scan_device():
-        t0 = time.perf_counter()
-        _, readable = eng.cursor_allgather(local_rev)
         t1 = time.perf_counter()
         r = eng.range_batch(reqs, KB_OUT_DEVICE)
         t2 = time.perf_counter()
@@ -423,14 +429,12 @@ def run_b200(args, rank: int, local_rank: int, world: int):
         nk = r.n_kvs
         r.close()
         t3 = time.perf_counter()
-        pyt["cursor"] += t1 - t0
         pyt["range_call"] += t2 - t1
         pyt["range_result"] += t3 - t2
         pyt["n"] += 1
         return ex, nk
 
     def scan_e2e():
-        _, readable = eng.cursor_allgather(local_rev)
         r = eng.range_batch(reqs, KB_OUT_HOST)
         ex = int(r.req_examined.sum())
         nbytes = r.n_bytes + r.n_kvs * 36
@@ -515,18 +519,18 @@ def run_b200(args, rank: int, local_rank: int, world: int):
     # the cursor exchange on its own, both transports (the timed loop uses the peer-memory kernel when peers map)
     cursor_us = {}
     if world > 1:
-        for name, force_nccl in (("p2p" if eng.cursor_mode() == "p2p" else "nccl", False), ("nccl", True)):
+        for name, force_nccl in (("p2p" if ceng.cursor_mode() == "p2p" else "nccl", False), ("nccl", True)):
             if name in cursor_us:
                 continue
-            eng.cursor_force_nccl(force_nccl)
+            ceng.cursor_force_nccl(force_nccl)
             for _ in range(5):
-                eng.cursor_allgather(local_rev)
+                ceng.cursor_allgather(local_rev)
             barrier()
             t0 = time.perf_counter()
             for _ in range(50):
-                eng.cursor_allgather(local_rev)
+                ceng.cursor_allgather(local_rev)
             cursor_us[name] = (time.perf_counter() - t0) / 50 * 1e6
-        eng.cursor_force_nccl(False)
+        ceng.cursor_force_nccl(False)
         t = torch.tensor([cursor_us.get("p2p", 0.0), cursor_us.get("nccl", 0.0)], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         cursor_us = {k: float(v) for k, v in zip(("p2p", "nccl"), t.tolist()) if v > 0}
@@ -597,7 +601,7 @@ def run_b200(args, rank: int, local_rank: int, world: int):
             line["cpu_baseline"] = cpu_baseline(wl)
         if world == 1 and not args.no_extras:
             line["extra"] = {"compaction": compaction_extra(local_rank, peak, full=not args.small_compaction),
-                             "wire": wire_extra(eng, wl)}
+                             "wire": wire_extra(eng, wl), "write_path": write_rate_extra(eng, wl)}
         print(json.dumps(line), flush=True)
     if wthread is not None:
         jobs_q.put(None)
@@ -810,6 +814,48 @@ def fanout_alone(weng, evh, wl, peak: float, reps: int = 30):
             "roofline": {"bound": "hbm", "achieved": alg / 1e9 / (ms / 1e3), "peak": peak, "unit": "GB/s",
                          "frac": alg / 1e9 / (ms / 1e3) / peak, "alg_bytes": alg,
                          "note": "latency bound: 41 MB of algorithmic traffic per burst"}}
+
+
+def write_rate_extra(eng, wl):
+    """extra, run last (it changes the snapshot): the write path behind the collector's <= 300-event batches on the bench
+    store -- 150 updates per batch, each a CAS of the revision record + a Put of the new 2 KB version
+    (pkg/backend/txn.go:249-265) -- through kb_apply_batch (heap + sorted directory: the cost of a batch does not grow with
+    the bytes of the store)"""
+    import random
+    import struct
+
+    keys = wl["store"].keys
+    rng = random.Random(5)
+    rev = int(wl["meta"].last_rev)
+    n0 = eng.store_info()[0]
+    batches, n_ops = 40, 0
+    val = b"w" * LV
+    plan = []
+    for _ in range(batches):
+        ops = []
+        for i in rng.sample(range(keys.n), 150):
+            uk = keys[i][4:-9]
+            rev += 1
+            ops.append((CODER.encode_object_key(uk, 0), struct.pack(">Q", rev)))
+            ops.append((CODER.encode_object_key(uk, rev), val))
+        plan.append(ops)
+    eng.apply_batch(plan[0])
+    t0 = time.perf_counter()
+    for ops in plan[1:]:
+        eng.apply_batch(ops)
+        n_ops += len(ops)
+    dt = time.perf_counter() - t0
+    assert eng.store_info()[0] == n0 + batches * 150
+    # the snapshot still answers: a count over everything at the new revision
+    lo, hi = CODER.encode_object_key(b"/registry/", 0), CODER.encode_object_key(b"/registry0", 0)
+    from kubebrain_b200._lib import KB_OUT_COUNT
+
+    r = eng.range_batch([(lo, hi, rev, 0)], KB_OUT_COUNT)
+    objects = int(r.req_count[0])
+    r.close()
+    return {"workload": f"{batches - 1} batches of 300 ops (150 updates) on the {n0}-record store",
+            "ops_per_s": n_ops / dt, "ms_per_batch": dt / (batches - 1) * 1e3, "records_after": int(eng.store_info()[0]),
+            "objects_visible_after": objects}
 
 
 def wire_extra(eng, wl):

@@ -458,9 +458,10 @@ static inline DecGeom decode_geometry(uint32_t max_key_chunks, uint32_t ntiles, 
     DecGeom g;
     uint32_t K = force_k ? force_k : (c >= 9 ? 1u : c >= 5 ? 2u : 4u);
     K = std::min<uint32_t>(std::max<uint32_t>(K, 1), DECODE_MAX_K);
-    // Ring depth: the pass is bound by the bytes it keeps in flight (measured: 4.7 TB/s with one key copy in flight per
-    // warp at ~100 KB per SM), so prefer fewer warps with more copies in flight each.
-    uint32_t NKS = force_nks ? std::min<uint32_t>(std::max<uint32_t>(force_nks, 2), DECODE_MAX_KS) : 3;
+    // Ring depth.  Measured (profiles/r02_run2_decode_sweep.txt, 1M records of 269 B): 2 key slots x 11 warps 59 us, 3 x 7
+    // 77 us, 4 x 5 98 us -- the pass is bound by how many warps decode, not by the bytes in flight, so the shallowest ring
+    // (most warps) is the default.
+    uint32_t NKS = force_nks ? std::min<uint32_t>(std::max<uint32_t>(force_nks, 2), DECODE_MAX_KS) : 2;
     auto per_warp = [&](uint32_t k, uint32_t nks) {
         return (size_t)(nks * (32 * k + 1) * c + (nks + 1) * (32 * k + 1 + DECODE_HDR_CHUNKS)) * 16;
     };

@@ -3,8 +3,8 @@
 // Replaces (reference file:line):
 //   storage.Iter over badger            pkg/storage/badger/iter.go:27-98        -> HBM slab + k_search
 //   coder.Decode                        pkg/backend/coder/normal.go:58-70       -> k_decode_lcp
-//   worker.run (range + compact)        pkg/backend/scanner/scanner.go:389-516  -> k_decode_lcp, k_emit_place
-//   commonResultReceiver (limit)        pkg/backend/scanner/receiver.go:62-103  -> k_emit_place, k_gather
+//   worker.run (range + compact)        pkg/backend/scanner/scanner.go:389-516  -> k_decode_lcp, k_emit, k_place
+//   commonResultReceiver (limit)        pkg/backend/scanner/receiver.go:62-103  -> k_tile_scan, k_place, k_gather
 //
 // Kernel pipeline for one batch of requests (streams: S2 = bound search, S = main, SG = copy stream):
 //   k_search      [S2] lower_bound of every [start,end) bound in the sorted slab (warp per bound, 32-ary); the only
@@ -12,15 +12,16 @@
 //   k_decode_lcp  [S] HBM-bound pass: stream the raw internal keys (one bulk-TMA copy per 32-record sub-tile into a
 //                 per-warp shared-memory ring), decode magic/split/revision, visibility, tombstone probe, and the
 //                 common-prefix length with the preceding key -> one 32-bit meta word per record + sub-tile aggregates
-//   k_emit_place  [S] per tile, one pass: segmented "last visible version" scan over the meta words (prev pointer +
-//                 running min-LCP) decides which record every key change emits / supersedes; cross-tile carry and the
-//                 output positions come from decoupled look-back; writes the ordered selection (limit applied) or the
-//                 ordered victim list and the per-request totals
+//   k_emit        [S] per tile: segmented "last visible version" scan over the meta words (prev pointer + running
+//                 min-LCP; the cross-tile carry by decoupled look-back) decides which record every key change emits /
+//                 supersedes
+//   k_tile_scan   [S] prefix sums of the per-tile counts / bytes (one CTA per 1024 tiles); k_req_totals: per-request rows
+//   k_place       [S] ordered placement of the selection (limit applied) / ordered victim list
 //   k_req_finalize [S] per-request prefix sums; publishes the per-request rows to mapped pinned memory (the host
 //                 returns device-resident answers on that flag)
 //   k_gather_jobs / k_wire_jobs [S] one copy job per emitted kv + the per-kv view arrays
 //   k_gather / k_wire_copy [SG] bulk-TMA copy of the winners' key+value into the response arena (padded pairs, or
-//                 etcd protobuf elements); overlaps the next batch's k_decode_lcp .. k_emit_place
+//                 etcd protobuf elements); overlaps the next batch's k_decode_lcp .. k_place
 #include <algorithm>
 
 #include "kb_internal.cuh"
@@ -181,23 +182,25 @@ __device__ __forceinline__ void block_excl_scan2(uint64_t a, uint64_t b, uint64_
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_emit_place: the worker.run state machine, data-parallel, in ONE pass over the meta words.
+// k_emit: the worker.run state machine, data-parallel.
 // For every TRIG record i with prev p = last PREVOK record before it (inside the request):
 //   same key  <=> klen[i] == klen[p] && min LCP over (p, i] >= klen[i] - 9
 //   range  : key change && rev[p] > 0 && value[p] != tombstone  -> emit p         (scanner.go:457-462)
 //   compact: same key && rev[p] > 0                             -> p superseded   (scanner.go:463-469)
 // After the last record of a request the trailing prev is emitted (scanner.go:503-507).
+// tgt[i] = flat slot of the emitted (range) / superseded (compact) record, or NONE.
+// tcnt[2t] = emissions (range) or delete calls (compact) of tile t; tcnt[2t+1] = response bytes (range) or object
+// count (compact).
 //
-// Round 1 ran this as k_emit (decide + per-tile counts; the cross-tile carry was a serial walk over sub-tile
-// aggregates by one thread) -> k_tile_scan (one CTA) -> k_place / k_place_victims (second pass over the records).
-// Here a tile (1024 records, taken in ticket order) resolves both cross-tile dependencies by DECOUPLED LOOK-BACK:
-//   1. (last PREVOK slot, min LCP since) carry: the tile publishes its own aggregate at once, then warp 0 reads the
-//      states of up to 32 preceding tiles of the request per step until it meets an inclusive prefix or a tile that
-//      holds a PREVOK record (nothing before such a tile can matter).  A request whose records are all invisible --
-//      the round-1 worst case, O(tiles) dependent loads per tile -- costs one step per tile.
-//   2. emission count / response bytes (or delete calls / object count): the classic single-pass prefix sum.
-// The tile then writes its slice of the ordered selection (limit applied, receiver.go:82-87) or of the ordered
-// delete-call list directly; the request's last tile writes the request totals.
+// The (last PREVOK slot, min LCP since) carry into a tile comes from DECOUPLED LOOK-BACK over per-tile states: a tile
+// (taken in ticket order) publishes its own aggregate at once, then warp 0 reads the states of up to 32 preceding tiles
+// of the request per step until it meets an inclusive prefix or a tile that holds a PREVOK record (nothing before such a
+// tile can matter).  Round 1 walked the sub-tile aggregates backwards with one thread until it met a visible record: a
+// scan whose records are mostly invisible (read revision below the versions, compact at an old revision) cost O(tiles)
+// dependent loads per tile; now it costs one step per tile.
+// (Round 2 also tried resolving the output positions by look-back in the same pass -- one kernel instead of three: with
+// ~1 200 tiles of 1 024 records in flight every tile walked ~5 windows back to the frontier of resolved prefixes, 2.5 ms
+// per 100M records against 1.1 ms for emit + scan + place; profiles/r02_run2_decode_sweep.txt.)
 // ------------------------------------------------------------------------------------------------
 struct ReqOut {
     uint64_t total;        // emissions (range) / delete calls (compact)
@@ -208,11 +211,10 @@ struct ReqOut {
 };
 enum { KB_RO_LIMIT_STOP = 1u, KB_RO_CAPPED = 2u };
 
-struct __align__(16) TileState {  // 64 bytes; zeroed by one memset per batch
+struct __align__(16) TileState {  // 32 bytes; zeroed by one memset per batch
     unsigned long long lm_agg, lm_pre;  // (last PREVOK slot | min LCP << 32): the tile alone / request start .. this tile
-    unsigned long long cnt_agg, aux_agg, cnt_pre, aux_pre;
-    uint32_t st_lm, st_cnt;  // 0 empty, 1 aggregate valid, 2 inclusive prefix valid
-    uint32_t pad[2];
+    uint32_t st_lm;                     // 0 empty, 1 aggregate valid, 2 inclusive prefix valid
+    uint32_t pad[3];
 };
 enum { TS_EMPTY = 0, TS_AGG = 1, TS_PREFIX = 2 };
 
@@ -230,22 +232,15 @@ __device__ __forceinline__ void ts_publish(uint32_t *status, uint32_t v)
     *(volatile uint32_t *)status = v;
 }
 
-// Look-back window: all eight warps of the CTA read the states of up to 256 preceding tiles per step (warp w looks at
-// tiles hi-1-32w .. hi-32-32w).  With one warp (32 tiles per step) the frontier of resolved prefixes advanced 32 tiles per
-// memory round trip and a 100M-record sweep (97 656 tiles, ~1 200 in flight) spent 2 ms waiting for it.
-constexpr uint32_t LB_WINDOW = 256;
-
-// exclusive (L, m) carry of tile t inside its request (tiles [t0, t)); every thread of the CTA calls it, all return the carry
-__device__ __forceinline__ LM lookback_lm(TileState *ts, uint32_t t, uint32_t t0, uint32_t *sh /* 8 x {term, L, m} + 1 */)
+// warp 0: exclusive (L, m) carry of tile t inside its request (tiles [t0, t))
+__device__ __forceinline__ LM lookback_lm(TileState *ts, uint32_t t, uint32_t t0, uint32_t lane)
 {
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     LM acc;
     acc.L = KB_NONE;
     acc.m = KB_LCP_INF;
-    for (uint32_t hi = t; hi > t0;) {  // this step looks at tiles hi-1, hi-2, .. (thread 0 = nearest)
-        const uint32_t back = threadIdx.x;
-        const bool in = back < hi - t0;
-        TileState *p = ts + (hi - 1 - (in ? back : 0));
+    for (uint32_t hi = t; hi > t0;) {  // this step looks at tiles hi-1, hi-2, .. (lane 0 = nearest)
+        const bool in = lane < hi - t0;
+        TileState *p = ts + (hi - 1 - (in ? lane : 0));
         uint32_t st;
         do {
             st = in ? *(volatile uint32_t *)&p->st_lm : (uint32_t)TS_PREFIX;
@@ -256,96 +251,35 @@ __device__ __forceinline__ LM lookback_lm(TileState *ts, uint32_t t, uint32_t t0
         v.m = KB_LCP_INF;
         if (in) v = lm_unpack(*(volatile unsigned long long *)(st == TS_PREFIX ? &p->lm_pre : &p->lm_agg));
         const unsigned term = __ballot_sync(FULL, in && (st == TS_PREFIX || v.L != KB_NONE));
-        const uint32_t k = term ? (uint32_t)(__ffs(term) - 1) : 31u;  // farthest lane of this warp that still matters
+        const uint32_t k = term ? (uint32_t)(__ffs(term) - 1) : 31u;  // farthest lane that still matters
         const uint32_t mm = __reduce_min_sync(FULL, (in && lane <= k) ? v.m : KB_LCP_INF);
         const uint32_t Lk = __shfl_sync(FULL, v.L, k);
-        if (lane == 0) {
-            sh[warp * 3 + 0] = term ? 1u : 0u;
-            sh[warp * 3 + 1] = Lk;
-            sh[warp * 3 + 2] = mm;
-        }
-        __syncthreads();
         // combine(farther, nearer): nearer tiles (already in acc) hold no PREVOK, so only the minimum accumulates
-        bool done = false;
-        for (uint32_t w = 0; w < 8 && !done; w++) {
-            acc.m = min(acc.m, sh[w * 3 + 2]);
-            if (sh[w * 3 + 0]) {
-                acc.L = sh[w * 3 + 1];
-                done = true;
-            }
+        acc.m = min(acc.m, mm);
+        if (term) {
+            acc.L = Lk;
+            break;
         }
-        __syncthreads();
-        if (done) break;
-        hi -= min(LB_WINDOW, hi - t0);
+        hi -= min(32u, hi - t0);
     }
     return acc;
 }
 
-// exclusive sums (count, aux) of tile t inside its request; every thread of the CTA calls it
-__device__ __forceinline__ void lookback_sum(TileState *ts, uint32_t t, uint32_t t0, uint64_t *sh /* 8 x {term, c, a} */,
-                                             uint64_t &cnt, uint64_t &aux)
-{
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    cnt = aux = 0;
-    for (uint32_t hi = t; hi > t0;) {
-        const uint32_t back = threadIdx.x;
-        const bool in = back < hi - t0;
-        TileState *p = ts + (hi - 1 - (in ? back : 0));
-        uint32_t st;
-        do {
-            st = in ? *(volatile uint32_t *)&p->st_cnt : (uint32_t)TS_PREFIX;
-        } while (!__all_sync(FULL, st != TS_EMPTY));
-        __threadfence();
-        uint64_t c = 0, a = 0;
-        if (in) {
-            c = *(volatile unsigned long long *)(st == TS_PREFIX ? &p->cnt_pre : &p->cnt_agg);
-            a = *(volatile unsigned long long *)(st == TS_PREFIX ? &p->aux_pre : &p->aux_agg);
-        }
-        const unsigned term = __ballot_sync(FULL, in && st == TS_PREFIX);
-        const uint32_t k = term ? (uint32_t)(__ffs(term) - 1) : 31u;
-        if (!(in && lane <= k)) c = a = 0;
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) {
-            c += __shfl_xor_sync(FULL, c, d);
-            a += __shfl_xor_sync(FULL, a, d);
-        }
-        if (lane == 0) {
-            sh[warp * 3 + 0] = term ? 1u : 0u;
-            sh[warp * 3 + 1] = c;
-            sh[warp * 3 + 2] = a;
-        }
-        __syncthreads();
-        bool done = false;
-        for (uint32_t w = 0; w < 8 && !done; w++) {
-            cnt += sh[w * 3 + 1];
-            aux += sh[w * 3 + 2];
-            done = sh[w * 3 + 0] != 0;
-        }
-        __syncthreads();
-        if (done) break;
-        hi -= min(LB_WINDOW, hi - t0);
-    }
-}
-
 template <bool COMPACT>
 __global__ void __launch_bounds__(256)
-k_emit_place(StoreDev st, const ReqDev *__restrict__ reqs, const TileDev *__restrict__ tiles,
-             const uint32_t *__restrict__ meta, TileState *__restrict__ ts, unsigned int *__restrict__ ticket,
-             uint32_t *__restrict__ sel, uint64_t *__restrict__ slot, uint32_t *__restrict__ vidx,
-             uint8_t *__restrict__ vcls, ReqOut *__restrict__ rout, int wire, int with_place,
-             unsigned int *__restrict__ decode_ctr)
+k_emit(StoreDev st, const ReqDev *__restrict__ reqs, const TileDev *__restrict__ tiles, const uint32_t *__restrict__ meta,
+       TileState *__restrict__ ts, unsigned int *__restrict__ ticket, uint32_t *__restrict__ tgt,
+       uint32_t *__restrict__ tail_tgt, uint64_t *__restrict__ tcnt, int wire, unsigned int *__restrict__ decode_ctr)
 {
     __shared__ LM warp_tot[8];
     __shared__ LM carry_s, agg_s;
     __shared__ uint64_t ws2[18];
-    __shared__ uint64_t pre_s[2];
-    __shared__ uint64_t lb64[24];
-    __shared__ uint32_t lb32[24];
     __shared__ uint32_t tile_s;
     if (threadIdx.x == 0) tile_s = atomicAdd(ticket, 1u);  // ticket order: every preceding tile has started
     if (blockIdx.x == 0 && threadIdx.x == 0) *decode_ctr = 0;  // leave k_decode_lcp's work counter at zero
     __syncthreads();
     const uint32_t tix = tile_s;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const TileDev tile = tiles[tix];
     const ReqDev req = reqs[tile.req];
     const bool first_tile = tix == req.tile0, last_tile = tix == req.tile0 + req.ntiles - 1;
@@ -376,46 +310,39 @@ k_emit_place(StoreDev st, const ReqDev *__restrict__ reqs, const TileDev *__rest
     const LM ex = block_excl_scan_lm(mine, warp_tot);
     if (threadIdx.x == 255) agg_s = lm_combine(ex, mine);
     __syncthreads();
-    {
+    if (warp == 0) {
         const LM agg = agg_s;
         LM carry;
         carry.L = KB_NONE;
         carry.m = KB_LCP_INF;
         if (first_tile) {
-            if (threadIdx.x == 0) {
+            if (lane == 0) {
                 my->lm_pre = lm_pack(agg);
                 ts_publish(&my->st_lm, TS_PREFIX);
             }
         } else {
-            if (threadIdx.x == 0) {
+            if (lane == 0) {
                 my->lm_agg = lm_pack(agg);
                 ts_publish(&my->st_lm, TS_AGG);
             }
-            carry = lookback_lm(ts, tix, req.tile0, lb32);
-            if (threadIdx.x == 0) {
+            carry = lookback_lm(ts, tix, req.tile0, lane);
+            if (lane == 0) {
                 my->lm_pre = lm_pack(lm_combine(carry, agg));
                 ts_publish(&my->st_lm, TS_PREFIX);
             }
         }
-        if (threadIdx.x == 0) carry_s = carry;
+        if (lane == 0) carry_s = carry;
     }
     __syncthreads();
     LM x = lm_combine(carry_s, ex);
 
-    // decisions of this thread's four records (+ the request's trailing prev): t[k] = flat slot of the emitted (range) /
-    // superseded (compact) record, cnt = emissions / delete calls, aux = response bytes / object count
-    uint32_t t[5], sz[5];
-#pragma unroll
-    for (int k = 0; k < 5; k++) {
-        t[k] = KB_NONE;
-        sz[k] = 0;
-    }
     uint64_t cnt = 0, aux = 0;
 #pragma unroll
     for (int k = 0; k < 4; k++) {
         if (base + k >= tile.n) break;
         const uint32_t i = flat + k;
         const uint32_t word = w[k];
+        uint32_t t = KB_NONE;
         if (word & KB_M_TRIG) {
             if (x.L != KB_NONE) {
                 const uint32_t mm = min(x.m, word & KB_M_LCP_MASK);
@@ -428,14 +355,13 @@ k_emit_place(StoreDev st, const ReqDev *__restrict__ reqs, const TileDev *__rest
                         if (COMPACT) {
                             aux++;  // count++ only
                         } else {
-                            t[k] = x.L;
-                            sz[k] = (uint32_t)kv_resp_bytes(st, prec, wire);
+                            t = x.L;
                             cnt++;
-                            aux += sz[k];
+                            aux += kv_resp_bytes(st, prec, wire);
                         }
                     }
                 } else if (COMPACT && !(pw & KB_M_REV0)) {
-                    t[k] = x.L;  // superseded version
+                    t = x.L;  // superseded version
                     cnt++;
                 }
             }
@@ -451,8 +377,10 @@ k_emit_place(StoreDev st, const ReqDev *__restrict__ reqs, const TileDev *__rest
         } else {
             x.m = min(x.m, word & KB_M_LCP_MASK);
         }
+        tgt[i] = t;
         if (last_tile && base + k == tile.n - 1) {
             // end of the request's iterator: the trailing prev (scanner.go:503-507)
+            uint32_t tt = KB_NONE;
             if (x.L != KB_NONE) {
                 const uint32_t pw = meta[x.L];
                 if (!(pw & KB_M_REV0) && !(pw & KB_M_TOMB)) {
@@ -460,102 +388,240 @@ k_emit_place(StoreDev st, const ReqDev *__restrict__ reqs, const TileDev *__rest
                         aux++;
                     } else {
                         const uint32_t prec = req.lo + (x.L - req.flat0);
-                        t[4] = x.L;
-                        sz[4] = (uint32_t)kv_resp_bytes(st, prec, wire);
+                        tt = x.L;
                         cnt++;
-                        aux += sz[4];
+                        aux += kv_resp_bytes(st, prec, wire);
                     }
                 }
             }
+            tail_tgt[tile.req] = tt;
         }
     }
     uint64_t ea, eb, ta, tb;
     block_excl_scan2(cnt, aux, ea, eb, ta, tb, ws2);
-    {
-        uint64_t pc = 0, pa = 0;
-        if (first_tile) {
-            if (threadIdx.x == 0) {
-                my->cnt_pre = ta;
-                my->aux_pre = tb;
-                ts_publish(&my->st_cnt, TS_PREFIX);
-            }
-        } else {
-            if (threadIdx.x == 0) {
-                my->cnt_agg = ta;
-                my->aux_agg = tb;
-                ts_publish(&my->st_cnt, TS_AGG);
-            }
-            lookback_sum(ts, tix, req.tile0, lb64, pc, pa);
-            if (threadIdx.x == 0) {
-                my->cnt_pre = pc + ta;
-                my->aux_pre = pa + tb;
-                ts_publish(&my->st_cnt, TS_PREFIX);
+    if (threadIdx.x == 0) {
+        tcnt[2 * tix] = ta;
+        tcnt[2 * tix + 1] = tb;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_tile_scan: exclusive prefix of the per-tile (count, aux) pairs over ALL tiles of the batch, tscan[2 * (T + 1)].
+// One CTA per chunk of 1024 tiles (round 1: one CTA for everything, 35 us per 10M records): a chunk scans its tiles,
+// publishes its total, and adds the totals of the chunks in front of it (at most a few hundred: plain look-back).
+// ------------------------------------------------------------------------------------------------
+struct __align__(16) ChunkState {
+    unsigned long long cnt, aux;
+    uint32_t ready;
+    uint32_t pad[3];
+};
+
+__global__ void __launch_bounds__(256)
+k_tile_scan(const uint64_t *__restrict__ tcnt, uint64_t *__restrict__ tscan, uint32_t ntiles, ChunkState *__restrict__ cs)
+{
+    __shared__ uint64_t ws2[18];
+    __shared__ uint64_t base_s[2];
+    const uint32_t c = blockIdx.x, t0 = c * 1024 + threadIdx.x * 4;
+    uint64_t a[4], b[4], sa = 0, sb = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        a[k] = t0 + k < ntiles ? tcnt[2 * (t0 + k)] : 0;
+        b[k] = t0 + k < ntiles ? tcnt[2 * (t0 + k) + 1] : 0;
+        sa += a[k];
+        sb += b[k];
+    }
+    uint64_t ea, eb, ta, tb;
+    block_excl_scan2(sa, sb, ea, eb, ta, tb, ws2);
+    if (threadIdx.x == 0) {
+        cs[c].cnt = ta;
+        cs[c].aux = tb;
+        ts_publish(&cs[c].ready, 1u);
+    }
+    if (threadIdx.x < 32) {
+        // totals of the chunks in front, 32 at a time (each is ready as soon as its own 1024 counts are summed)
+        const uint32_t lane = threadIdx.x;
+        uint64_t pa = 0, pb = 0;
+        for (uint32_t p0 = 0; p0 < c; p0 += 32) {
+            const uint32_t p = p0 + lane;
+            if (p < c) {
+                while (*(volatile uint32_t *)&cs[p].ready == 0) {}
+                __threadfence();
+                pa += *(volatile unsigned long long *)&cs[p].cnt;
+                pb += *(volatile unsigned long long *)&cs[p].aux;
             }
         }
-        if (threadIdx.x == 0) {
-            pre_s[0] = pc;
-            pre_s[1] = pa;
-            if (last_tile) {  // inclusive prefix of the request's last tile = the request's totals
-                rout[tile.req].total = pc + ta;
-                rout[tile.req].total_aux = pa + tb;
-            }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            pa += __shfl_xor_sync(FULL, pa, d);
+            pb += __shfl_xor_sync(FULL, pb, d);
+        }
+        if (lane == 0) {
+            base_s[0] = pa;
+            base_s[1] = pb;
         }
     }
     __syncthreads();
-    if (!with_place) return;
-    uint64_t pos = pre_s[0] + ea;
-    if (COMPACT) {
-        // ordered delete calls: per record [superseded prev] [tombstone] [revision record] | [ttl]
-        pos += req.sel_base;
+    uint64_t ra = base_s[0] + ea, rb = base_s[1] + eb;
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-            if (base + k >= tile.n) break;
-            const uint32_t irec = req.lo + (flat + k - req.flat0);
-            if (t[k] != KB_NONE) {
-                vidx[pos] = req.lo + (t[k] - req.flat0);
-                vcls[pos++] = KB_V_SUPERSEDED;
-            }
-            if ((w[k] & KB_M_TRIG) && (w[k] & KB_M_TOMB)) {
-                vidx[pos] = irec;
-                vcls[pos++] = KB_V_TOMBSTONE;
-            }
-            if (w[k] & KB_M_REVDEL) {
-                vidx[pos] = irec;
-                vcls[pos++] = KB_V_REVRECORD;
-            }
-            if (w[k] & KB_M_TTLREV) {
-                vidx[pos] = irec;
-                vcls[pos++] = KB_V_TTL_REVREC;
-            }
-            if (w[k] & KB_M_TTLOBJ) {
-                vidx[pos] = irec;
-                vcls[pos++] = KB_V_TTL_OBJECT;
+    for (int k = 0; k < 4; k++) {
+        if (t0 + k < ntiles) {
+            tscan[2 * (t0 + k)] = ra;
+            tscan[2 * (t0 + k) + 1] = rb;
+        }
+        ra += a[k];
+        rb += b[k];
+        if (t0 + k == ntiles - 1) {
+            tscan[2 * ntiles] = ra;
+            tscan[2 * ntiles + 1] = rb;
+        }
+    }
+}
+
+// per-request totals from the tile prefix sums; every field of the row is written (no memset needed)
+__global__ void __launch_bounds__(256)
+k_req_totals(const ReqDev *__restrict__ reqs, uint32_t nreq, const uint64_t *__restrict__ tscan, ReqOut *__restrict__ rout)
+{
+    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nreq) return;
+    const ReqDev r = reqs[q];
+    ReqOut o;
+    o.total = o.total_aux = 0;
+    if (r.ntiles) {
+        o.total = tscan[2 * (r.tile0 + r.ntiles)] - tscan[2 * r.tile0];
+        o.total_aux = tscan[2 * (r.tile0 + r.ntiles) + 1] - tscan[2 * r.tile0 + 1];
+    }
+    o.capped_aux = 0;
+    o.examined = 0;
+    o.flags = 0;
+    rout[q] = o;
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_place: ordered selection (range) -- position = emissions before it in the request; the first `limit`
+// positions are kept (commonResultReceiver.needMore, receiver.go:82-87).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_place(StoreDev st, const ReqDev *__restrict__ reqs, const TileDev *__restrict__ tiles,
+        const uint32_t *__restrict__ tgt, const uint32_t *__restrict__ tail_tgt,
+        const uint64_t *__restrict__ tscan, uint32_t *__restrict__ sel, uint64_t *__restrict__ slot,
+        ReqOut *__restrict__ rout, int wire)
+{
+    __shared__ uint64_t ws2[18];
+    const TileDev tile = tiles[blockIdx.x];
+    const ReqDev req = reqs[tile.req];
+    const uint32_t base = threadIdx.x * 4;
+    const uint32_t flat = tile.flat0 + base;
+    const bool last_tile = (blockIdx.x == req.tile0 + req.ntiles - 1);
+    uint32_t t[5];
+    uint32_t sz[5];
+    uint64_t cnt = 0, bytes = 0;
+#pragma unroll
+    for (int k = 0; k < 5; k++) {
+        t[k] = KB_NONE;
+        sz[k] = 0;
+    }
+    if (base < tile.n) {
+        uint4 tw = *(const uint4 *)(tgt + flat);
+        t[0] = tw.x;
+        t[1] = base + 1 < tile.n ? tw.y : KB_NONE;
+        t[2] = base + 2 < tile.n ? tw.z : KB_NONE;
+        t[3] = base + 3 < tile.n ? tw.w : KB_NONE;
+        if (last_tile && tile.n - 1 >= base && tile.n - 1 < base + 4) t[4] = tail_tgt[tile.req];
+    }
+#pragma unroll
+    for (int k = 0; k < 5; k++) {
+        if (t[k] != KB_NONE) {
+            const uint32_t prec = req.lo + (t[k] - req.flat0);
+            sz[k] = (uint32_t)kv_resp_bytes(st, prec, wire);
+            cnt++;
+            bytes += sz[k];
+        }
+    }
+    uint64_t ea, eb, ta, tb;
+    block_excl_scan2(cnt, bytes, ea, eb, ta, tb, ws2);
+    uint64_t pos = tscan[2 * blockIdx.x] - tscan[2 * req.tile0] + ea;
+    uint64_t off = tscan[2 * blockIdx.x + 1] - tscan[2 * req.tile0 + 1] + eb;
+    const bool limited = req.limit > 0;
+#pragma unroll
+    for (int k = 0; k < 5; k++) {
+        if (t[k] == KB_NONE) continue;
+        if (!limited || pos < (uint64_t)req.limit) {
+            sel[req.sel_base + pos] = req.lo + (t[k] - req.flat0);
+            slot[req.sel_base + pos] = off;
+            if (limited && pos == (uint64_t)req.limit - 1) {
+                rout[tile.req].capped_aux = off + sz[k];
+                uint32_t fl = KB_RO_CAPPED;
+                if (k < 4) {
+                    // the limit-th append happened inside the loop: the iterator stops here (Q4)
+                    rout[tile.req].examined = (flat + k) - req.flat0 + 1;
+                    fl |= KB_RO_LIMIT_STOP;
+                }
+                rout[tile.req].flags = fl;
             }
         }
-    } else {
-        // ordered selection: position = emissions before it in the request; the first `limit` positions are kept
-        // (commonResultReceiver.needMore, receiver.go:82-87)
-        uint64_t off = pre_s[1] + eb;
-        const bool limited = req.limit > 0;
+        pos++;
+        off += sz[k];
+    }
+}
+
+// ordered delete calls (compact): per record [superseded prev] [tombstone] [revision record] | [ttl]
+__global__ void __launch_bounds__(256)
+k_place_victims(const ReqDev *__restrict__ reqs, const TileDev *__restrict__ tiles,
+                const uint32_t *__restrict__ meta, const uint32_t *__restrict__ tgt,
+                const uint64_t *__restrict__ tscan, uint32_t *__restrict__ vidx, uint8_t *__restrict__ vcls)
+{
+    __shared__ uint64_t ws2[18];
+    const TileDev tile = tiles[blockIdx.x];
+    const ReqDev req = reqs[tile.req];
+    const uint32_t base = threadIdx.x * 4;
+    const uint32_t flat = tile.flat0 + base;
+    uint32_t t[4], w[4];
+    uint64_t cnt = 0;
 #pragma unroll
-        for (int k = 0; k < 5; k++) {
-            if (t[k] == KB_NONE) continue;
-            if (!limited || pos < (uint64_t)req.limit) {
-                sel[req.sel_base + pos] = req.lo + (t[k] - req.flat0);
-                slot[req.sel_base + pos] = off;
-                if (limited && pos == (uint64_t)req.limit - 1) {
-                    rout[tile.req].capped_aux = off + sz[k];
-                    uint32_t fl = KB_RO_CAPPED;
-                    if (k < 4) {
-                        // the limit-th append happened inside the loop: the iterator stops here (Q4)
-                        rout[tile.req].examined = (flat + k) - req.flat0 + 1;
-                        fl |= KB_RO_LIMIT_STOP;
-                    }
-                    rout[tile.req].flags = fl;
-                }
-            }
-            pos++;
-            off += sz[k];
+    for (int k = 0; k < 4; k++) {
+        t[k] = KB_NONE;
+        w[k] = 0;
+    }
+    if (base < tile.n) {
+        const uint4 tw = *(const uint4 *)(tgt + flat), mw = *(const uint4 *)(meta + flat);
+        t[0] = tw.x, w[0] = mw.x;
+        if (base + 1 < tile.n) t[1] = tw.y, w[1] = mw.y;
+        if (base + 2 < tile.n) t[2] = tw.z, w[2] = mw.z;
+        if (base + 3 < tile.n) t[3] = tw.w, w[3] = mw.w;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        if (t[k] != KB_NONE) cnt++;
+        if ((w[k] & KB_M_TRIG) && (w[k] & KB_M_TOMB)) cnt++;
+        if (w[k] & KB_M_REVDEL) cnt++;
+        if (w[k] & (KB_M_TTLREV | KB_M_TTLOBJ)) cnt++;
+    }
+    uint64_t ea, eb, ta, tb;
+    block_excl_scan2(cnt, 0, ea, eb, ta, tb, ws2);
+    uint64_t pos = req.sel_base + tscan[2 * blockIdx.x] - tscan[2 * req.tile0] + ea;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        if (base + k >= tile.n) break;
+        const uint32_t irec = req.lo + (flat + k - req.flat0);
+        if (t[k] != KB_NONE) {
+            vidx[pos] = req.lo + (t[k] - req.flat0);
+            vcls[pos++] = KB_V_SUPERSEDED;
+        }
+        if ((w[k] & KB_M_TRIG) && (w[k] & KB_M_TOMB)) {
+            vidx[pos] = irec;
+            vcls[pos++] = KB_V_TOMBSTONE;
+        }
+        if (w[k] & KB_M_REVDEL) {
+            vidx[pos] = irec;
+            vcls[pos++] = KB_V_REVRECORD;
+        }
+        if (w[k] & KB_M_TTLREV) {
+            vidx[pos] = irec;
+            vcls[pos++] = KB_V_TTL_REVREC;
+        }
+        if (w[k] & KB_M_TTLOBJ) {
+            vidx[pos] = irec;
+            vcls[pos++] = KB_V_TTL_OBJECT;
         }
     }
 }
@@ -1152,8 +1218,11 @@ int upload_layout(kb_ctx *ctx, const Resolved &R)
     ctx->d_tiles.p = (uint8_t *)ctx->d_reqs.p + req_bytes;  // alias into d_reqs (never freed on its own)
     ctx->d_tiles.cap = 0;
     KB_TRY(dbuf_ensure(ctx, ctx->d_meta, std::max<uint64_t>(R.total_flat, 4) * 4));
-    // look-back states of k_emit_place: [ticket, padded to 64 bytes][one TileState per tile]
-    KB_TRY(dbuf_ensure(ctx, ctx->d_tcnt, 64 + std::max<size_t>(nt, 1) * sizeof(TileState)));
+    KB_TRY(dbuf_ensure(ctx, ctx->d_tgt, std::max<uint64_t>(R.total_flat, 4) * 4 + nreq * 4 + 16));
+    // one zeroed region per batch: [ticket, padded to 64 bytes][one ChunkState per 1024 tiles][one TileState per tile]
+    KB_TRY(dbuf_ensure(ctx, ctx->d_tscan, 64 + (std::max<size_t>(nt, 1) / 1024 + 1) * sizeof(ChunkState) +
+                                              std::max<size_t>(nt, 1) * sizeof(TileState)));
+    KB_TRY(dbuf_ensure(ctx, ctx->d_tcnt, (std::max<size_t>(nt, 1) * 2 + (nt + 1) * 2) * 8));  // tcnt | tscan
     KB_TRY(dbuf_ensure(ctx, ctx->d_reqout, std::max<size_t>(nreq, 1) * sizeof(ReqOut)));
     // pinned staging so the async copies really are asynchronous
     const size_t bytes = req_bytes + nt * sizeof(TileDev);
@@ -1235,8 +1304,8 @@ static int launch_gather(kb_ctx *ctx, cudaStream_t strm, const GatherJob *d_jobs
     return KB_OK;
 }
 
-// decode -> emit/place for an uploaded layout; everything stays enqueued on ctx->stream.  Range: the selection goes to
-// ctx->d_sel / d_slot; compact: the delete calls go to vidx / vcls (capacity 2 per examined record).
+// decode -> emit -> tile scan -> request totals -> (place) for an uploaded layout; everything stays enqueued on
+// ctx->stream.  Range: the selection goes to ctx->d_sel / d_slot; compact: the delete calls go to vidx / vcls.
 static int launch_scan_core(kb_ctx *ctx, const Resolved &R, const ScanMode &mode, bool with_place,
                             uint32_t *vidx = nullptr, uint8_t *vcls = nullptr)
 {
@@ -1245,31 +1314,48 @@ static int launch_scan_core(kb_ctx *ctx, const Resolved &R, const ScanMode &mode
     const ReqDev *d_reqs = (const ReqDev *)ctx->d_reqs.p;
     const TileDev *d_tiles = (const TileDev *)ctx->d_tiles.p;
     uint32_t *d_meta = (uint32_t *)ctx->d_meta.p;
-    unsigned int *d_ticket = (unsigned int *)ctx->d_tcnt.p;
-    TileState *d_ts = (TileState *)((uint8_t *)ctx->d_tcnt.p + 64);
+    uint32_t *d_tgt = (uint32_t *)ctx->d_tgt.p;
+    uint32_t *d_tail = d_tgt + std::max<uint64_t>(R.total_flat, 4);
+    const uint32_t nchunks = nt / 1024 + 1;
+    unsigned int *d_ticket = (unsigned int *)ctx->d_tscan.p;
+    ChunkState *d_cs = (ChunkState *)((uint8_t *)ctx->d_tscan.p + 64);
+    TileState *d_ts = (TileState *)(d_cs + nchunks);
+    uint64_t *d_tcnt = (uint64_t *)ctx->d_tcnt.p, *d_tscan = d_tcnt + (size_t)std::max<uint32_t>(nt, 1) * 2;
     ReqOut *d_rout = (ReqOut *)ctx->d_reqout.p;
-    // algorithmic bytes of the decode pass: key bytes of the examined records + 10 B of offsets/lengths each
     const uint64_t kbytes = scan_alg_bytes(ctx, R.n_records);
     if (!ctx->d_ctrs.p) {  // work counters [0..7] + error flag [8]: zero once, every consumer leaves the counters at zero
         KB_TRY(dbuf_ensure(ctx, ctx->d_ctrs, 256));
         KB_CUDA(ctx, cudaMemsetAsync(ctx->d_ctrs.p, 0, 256, ctx->stream));
     }
-    // request rows start at zero (empty requests are never written); look-back states and the ticket start empty
-    KB_CUDA(ctx, cudaMemsetAsync(d_rout, 0, std::max<size_t>(nreq, 1) * sizeof(ReqOut), ctx->stream));
     if (nt) {
-        KB_CUDA(ctx, cudaMemsetAsync(ctx->d_tcnt.p, 0, 64 + (size_t)nt * sizeof(TileState), ctx->stream));
+        // the ticket and the look-back states start empty
+        KB_CUDA(ctx, cudaMemsetAsync(ctx->d_tscan.p, 0, 64 + (size_t)nchunks * sizeof(ChunkState) + (size_t)nt * sizeof(TileState),
+                                     ctx->stream));
         KB_TRY(launch_decode(ctx, nt, kbytes, mode, d_tiles, d_meta));
         if (mode.compact) {
-            KB_LAUNCH(ctx, "k_emit_place_compact", R.n_records * 6,
-                      (k_emit_place<true><<<nt, 256, 0, ctx->stream>>>(ctx->st, d_reqs, d_tiles, d_meta, d_ts, d_ticket, nullptr,
-                                                                      nullptr, vidx, vcls, d_rout, 0, with_place ? 1 : 0,
-                                                                      (unsigned int *)ctx->d_ctrs.p)));
+            KB_LAUNCH(ctx, "k_emit_compact", R.n_records * 8,
+                      (k_emit<true><<<nt, 256, 0, ctx->stream>>>(ctx->st, d_reqs, d_tiles, d_meta, d_ts, d_ticket, d_tgt, d_tail,
+                                                                d_tcnt, 0, (unsigned int *)ctx->d_ctrs.p)));
         } else {
-            KB_LAUNCH(ctx, "k_emit_place", R.n_records * 6,
-                      (k_emit_place<false><<<nt, 256, 0, ctx->stream>>>(ctx->st, d_reqs, d_tiles, d_meta, d_ts, d_ticket,
-                                                                       (uint32_t *)ctx->d_sel.p, (uint64_t *)ctx->d_slot.p,
-                                                                       nullptr, nullptr, d_rout, mode.wire, with_place ? 1 : 0,
-                                                                       (unsigned int *)ctx->d_ctrs.p)));
+            KB_LAUNCH(ctx, "k_emit", R.n_records * 8,
+                      (k_emit<false><<<nt, 256, 0, ctx->stream>>>(ctx->st, d_reqs, d_tiles, d_meta, d_ts, d_ticket, d_tgt, d_tail,
+                                                                 d_tcnt, mode.wire, (unsigned int *)ctx->d_ctrs.p)));
+        }
+        KB_LAUNCH(ctx, "k_tile_scan", (uint64_t)nt * 32,
+                  (k_tile_scan<<<nchunks, 256, 0, ctx->stream>>>(d_tcnt, d_tscan, nt, d_cs)));
+    }
+    if (nreq)
+        KB_LAUNCH(ctx, "k_req_totals", (uint64_t)nreq * 64,
+                  (k_req_totals<<<(nreq + 255) / 256, 256, 0, ctx->stream>>>(d_reqs, nreq, d_tscan, d_rout)));
+    if (nt && with_place) {
+        if (mode.compact) {
+            KB_LAUNCH(ctx, "k_place_victims", R.n_records * 8,
+                      (k_place_victims<<<nt, 256, 0, ctx->stream>>>(d_reqs, d_tiles, d_meta, d_tgt, d_tscan, vidx, vcls)));
+        } else {
+            KB_LAUNCH(ctx, "k_place", R.n_records * 4,
+                      (k_place<<<nt, 256, 0, ctx->stream>>>(ctx->st, d_reqs, d_tiles, d_tgt, d_tail, d_tscan,
+                                                            (uint32_t *)ctx->d_sel.p, (uint64_t *)ctx->d_slot.p, d_rout,
+                                                            mode.wire)));
         }
     }
     KB_CUDA(ctx, cudaGetLastError());
@@ -1282,8 +1368,11 @@ static int launch_scan_core(kb_ctx *ctx, const Resolved &R, const ScanMode &mode
 // sees what the reference saw, with work proportional to the answer instead of to the interval.
 constexpr uint32_t KB_LIMIT_WINDOW_MIN = 8192;
 
-static int probe_limit_windows(kb_ctx *ctx, Resolved &R)
+// *reused: the probe pass WAS the final pass (every request of the batch was probed, all of them were settled by the first
+// window, padded-arena sizes): its selection and request rows are already on the device, the caller skips its own scan
+static int probe_limit_windows(kb_ctx *ctx, Resolved &R, int wire, bool *reused)
 {
+    *reused = false;
     struct Todo {
         uint32_t q, true_hi;
         uint64_t w;
@@ -1302,7 +1391,7 @@ static int probe_limit_windows(kb_ctx *ctx, Resolved &R)
     mode.ttl_scan = 0;
     mode.timeout_rev = 0;
     mode.wire = 0;
-    while (!todo.empty()) {
+    for (int round = 0; !todo.empty(); round++) {
         Resolved P;
         P.reqs.resize(todo.size());
         for (size_t i = 0; i < todo.size(); i++) {
@@ -1327,6 +1416,14 @@ static int probe_limit_windows(kb_ctx *ctx, Resolved &R)
             else if (P.reqs[i].hi != todo[i].true_hi)
                 next.push_back(Todo{todo[i].q, todo[i].true_hi, todo[i].w * 8});
             // else: the whole interval was examined and the limit was not reached inside the loop
+        }
+        if (round == 0 && next.empty() && wire == 0 && todo.size() == R.reqs.size()) {
+            // every request of the batch sits in P in the same order; for a request the limit stopped, the window holds
+            // more records than the reference's loop pulled, but the first `limit` emissions, the bytes of those and the
+            // examined count (all in its request row) are the ones the clipped scan would produce
+            R = P;
+            *reused = true;
+            return KB_OK;
         }
         todo.swap(next);
     }
@@ -1391,13 +1488,16 @@ extern "C" int kb_range_batch(kb_ctx *ctx, const kb_range_req *reqs, uint64_t nr
     Resolved R;
     KB_TRY(resolve_requests(ctx, reqs, nreq, true, R, &tseg));
     kb_seg(ctx, "host:range_layout", tseg);
+    bool probe_is_final = false;
     if (out_mode != KB_OUT_COUNT) {
-        KB_TRY(probe_limit_windows(ctx, R));
+        KB_TRY(probe_limit_windows(ctx, R, wire, &probe_is_final));
         kb_seg(ctx, "host:range_limit_probe", tseg);
     }
-    KB_TRY(upload_layout(ctx, R));
-    KB_TRY(dbuf_ensure(ctx, ctx->d_sel, std::max<uint64_t>(R.total_sel, 1) * 4));
-    KB_TRY(dbuf_ensure(ctx, ctx->d_slot, std::max<uint64_t>(R.total_sel, 1) * 8));
+    if (!probe_is_final) {
+        KB_TRY(upload_layout(ctx, R));
+        KB_TRY(dbuf_ensure(ctx, ctx->d_sel, std::max<uint64_t>(R.total_sel, 1) * 4));
+        KB_TRY(dbuf_ensure(ctx, ctx->d_slot, std::max<uint64_t>(R.total_sel, 1) * 8));
+    }
     const ReqDev *d_reqs = (const ReqDev *)ctx->d_reqs.p;
     ReqOut *d_rout = (ReqOut *)ctx->d_reqout.p;
     ScanMode mode;
@@ -1405,7 +1505,7 @@ extern "C" int kb_range_batch(kb_ctx *ctx, const kb_range_req *reqs, uint64_t nr
     mode.ttl_scan = 0;
     mode.timeout_rev = 0;
     mode.wire = wire;
-    KB_TRY(launch_scan_core(ctx, R, mode, out_mode != KB_OUT_COUNT));
+    if (!probe_is_final) KB_TRY(launch_scan_core(ctx, R, mode, out_mode != KB_OUT_COUNT));
     KB_TRY(rout_map_ensure(ctx, nreq));
     const uint64_t epoch = ++ctx->rout_epoch;
 

@@ -84,9 +84,12 @@ struct TabDev {
 // control words of one match (gstate: [gcnt G+1][gfill G+1][ctl 16])
 enum { FC_NONMONO = 0, FC_CURSOR = 1, FC_NLARGE = 2, FC_NMED = 3, FC_ARRIVE = 4, FC_GEN = 5, FC_DONE = 6, FC_ABORT = 7, FC_WORDS = 16 };
 constexpr unsigned long long FAN_UNSET = ~0ull, FAN_BUSY = ~0ull - 1;
-constexpr uint32_t FAN_THREADS = 512;  // one CTA per SM: fits beside the scan context's decode CTA or its two gather CTAs
-constexpr uint32_t BM_WORDS = 1024;  // 32768 event indices per shared-memory window (4 KiB: the CTA stays co-resident
-                                     // with the scan context's shared-memory-heavy kernels)
+constexpr uint32_t FAN_THREADS = 256;  // one CTA per SM, < 15 k registers, < 2 KiB of shared memory (see fan_grid_sync)
+constexpr uint32_t BM_WORDS = 256;   // 8192 event indices per shared-memory window (1 KiB).  The scan context's two gather
+                                     // CTAs leave ~6 KiB of an SM's shared memory (every resident CTA also costs 1 KiB of
+                                     // reserve): with a 4 KiB window here NOTHING else of the scan context -- not even the
+                                     // shared-memory-free k_search -- fitted beside them for the whole fan-out (measured:
+                                     // k_search 10 us alone, 140 us in a step)
 
 struct FanScratch {
     uint32_t *gcnt, *gfill, *ctl;
@@ -103,7 +106,7 @@ struct FanScratch {
 __device__ __forceinline__ uint32_t ldcg32(const uint32_t *p) { return __ldcg(p); }
 __device__ __forceinline__ uint64_t ldcg64(const uint64_t *p) { return __ldcg((const unsigned long long *)p); }
 
-// Grid barrier.  The kernel is launched with ONE CTA per SM of modest size (512 threads, < 30 k registers, 4.5 KiB of
+// Grid barrier.  The kernel is launched with ONE CTA per SM of modest size (256 threads, < 15 k registers, < 2 KiB of
 // shared memory), which fits beside whatever the scan context has resident, so every CTA gets an SM while the others
 // spin; nothing this kernel waits for depends on work queued behind it.  (A cooperative launch would guarantee the same
 // but is gang-scheduled: measured, it waited for the scan context's persistent kernels to drain -- 247 us in a step

@@ -56,8 +56,11 @@ def main():
     if len(sys.argv) > 1:
         child(sys.argv[1])
         return
-    geoms = {"long": [(1, 2, 0), (1, 3, 0), (1, 4, 0), (1, 3, 6), (1, 2, 8)],
-             "short": [(2, 2, 0), (2, 3, 0), (2, 4, 0), (3, 3, 0), (4, 3, 0), (4, 2, 0), (1, 3, 0), (1, 4, 0)]}
+    geoms = {"long": [(1, 2, 0)],
+             "short": [(2, 2, 0), (1, 2, 0), (1, 2, 16), (2, 2, 12), (3, 2, 0)]}
+    if os.environ.get("KB_SWEEP_FULL"):
+        geoms = {"long": [(1, 2, 0), (1, 3, 0), (1, 4, 0), (1, 3, 6), (1, 2, 8)],
+                 "short": [(2, 2, 0), (2, 3, 0), (2, 4, 0), (3, 3, 0), (4, 3, 0), (4, 2, 0), (1, 3, 0), (1, 4, 0)]}
     for which, gl in geoms.items():
         for k, nks, w in gl:
             env = dict(os.environ, KB_DECODE_K=str(k), KB_DECODE_NKS=str(nks), KB_DECODE_WARPS=str(w))
