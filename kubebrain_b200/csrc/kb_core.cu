@@ -255,8 +255,10 @@ extern "C" int kb_open(int device_ordinal, const kb_config *cfg, kb_ctx **out)
     if (cudaSetDevice(device_ordinal) != cudaSuccess ||
         cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi) != cudaSuccess ||
         cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, high ? prio_hi : prio_lo) != cudaSuccess ||
-        cudaStreamCreateWithPriority(&ctx->stream2, cudaStreamNonBlocking, high ? prio_hi : prio_lo) != cudaSuccess ||
-        cudaStreamCreateWithPriority(&ctx->stream_g, cudaStreamNonBlocking, high ? prio_hi : prio_lo) != cudaSuccess ||
+        // the bound search is tiny and the host waits for it: always ahead of everything; the copy stream (gather / wire
+        // copy) is throughput work that the next batch's short kernels should not queue behind: always behind
+        cudaStreamCreateWithPriority(&ctx->stream2, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
+        cudaStreamCreateWithPriority(&ctx->stream_g, cudaStreamNonBlocking, prio_lo) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_jobs, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_gather[0], cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_gather[1], cudaEventDisableTiming) != cudaSuccess) {
