@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define KB_ABI_VERSION 2  /* 2: kb_write_op.expire_unix, kb_expire, kb_cursor_transport / kb_cursor_force_nccl */
+#define KB_ABI_VERSION 2  /* 2: kb_write_op.expire_unix, kb_expire, kb_range_prefetch, kb_cursor_transport / _force_nccl */
 
 typedef enum kb_status {
     KB_OK = 0,
@@ -152,6 +152,10 @@ typedef struct kb_range_view {
 
 /* One call = one batch of independent scanner.Range requests answered on one snapshot. */
 int kb_range_batch(kb_ctx *ctx, const kb_range_req *reqs, uint64_t n_req, int out_mode, kb_result **out);
+/* Optional: start the bound search of a batch ahead of the kb_range_batch call that will ask for it (identical bounds, same
+ * snapshot; anything else is ignored).  A caller with a queue of pending requests submits batch n+1 before it waits for
+ * batch n; the one host round trip of a range call then overlaps the previous batch's kernels. */
+int kb_range_prefetch(kb_ctx *ctx, const kb_range_req *reqs, uint64_t n_req);
 int kb_range_view_get(const kb_result *res, kb_range_view *view);
 /* Completion of a KB_OUT_DEVICE range answer: cuda_stream (a cudaStream_t) is made to wait for it on the device;
  * with cuda_stream == NULL the calling host thread blocks until it is complete.  No-op for host-resident results. */

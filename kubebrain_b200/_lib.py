@@ -33,7 +33,7 @@ KB_OP_PUT, KB_OP_DEL = 0, 1
 ABI_SYMBOLS = [
     "kb_abi_version", "kb_open", "kb_close", "kb_last_error", "kb_stream", "kb_sync",
     "kb_load_sorted", "kb_store_info", "kb_dump", "kb_restore", "kb_apply_batch", "kb_expire", "kb_set_compact_revision",
-    "kb_range_batch", "kb_range_view_get", "kb_result_wait", "kb_wire_range_head", "kb_wire_range_tail", "kb_wire_watch_head",
+    "kb_range_batch", "kb_range_prefetch", "kb_range_view_get", "kb_result_wait", "kb_wire_range_head", "kb_wire_range_tail", "kb_wire_watch_head",
     "kb_get_batch", "kb_get_view_get",
     "kb_compact_sweep", "kb_compact_view_get",
     "kb_watch_add", "kb_watch_del", "kb_watch_count", "kb_watch_match", "kb_events_upload", "kb_events_free",
@@ -162,6 +162,8 @@ def lib():
     L.kb_set_compact_revision.argtypes = [vp, C.c_int, C.c_uint64]
     L.kb_range_batch.restype = C.c_int
     L.kb_range_batch.argtypes = [vp, C.POINTER(KbRangeReq), C.c_uint64, C.c_int, C.POINTER(vp)]
+    L.kb_range_prefetch.restype = C.c_int
+    L.kb_range_prefetch.argtypes = [vp, C.POINTER(KbRangeReq), C.c_uint64]
     L.kb_range_view_get.restype = C.c_int
     L.kb_range_view_get.argtypes = [vp, C.POINTER(KbRangeView)]
     L.kb_result_wait.restype = C.c_int
@@ -508,6 +510,11 @@ class Engine:
         h = C.c_void_p()
         self._check(lib().kb_range_batch(self._ctx, pk.arr, pk.n, out_mode, C.byref(h)))
         return RangeResult(self, h)
+
+    def range_prefetch(self, reqs):
+        """start the bound search of a batch that a later range_batch(reqs) will ask for (kb_range_prefetch)"""
+        pk = reqs if isinstance(reqs, PackedRangeReqs) else PackedRangeReqs(reqs)
+        self._check(lib().kb_range_prefetch(self._ctx, pk.arr, pk.n))
 
     def get_batch(self, reqs: Sequence[Tuple[bytes, int]], out_mode: int = KB_OUT_HOST) -> GetResult:
         """reqs: (user_key, revision) -- revision 0 means latest"""

@@ -117,6 +117,7 @@ void pool_put_arena(kb_ctx *ctx, DBuf b)
 int ctx_quiesce(kb_ctx *ctx)
 {
     if (ctx->stream_g) KB_CUDA(ctx, cudaStreamSynchronize(ctx->stream_g));
+    if (ctx->stream2) KB_CUDA(ctx, cudaStreamSynchronize(ctx->stream2));  // a prefetched bound search may still read the slabs
     return KB_OK;
 }
 
@@ -315,6 +316,12 @@ extern "C" void kb_close(kb_ctx *ctx)
     if (ctx->h_rout) cudaFreeHost(ctx->h_rout);
     if (ctx->h_wpub) cudaFreeHost(ctx->h_wpub);
     for (auto &b : ctx->free_arena) cudaFree(b.p);
+    for (auto &sl : ctx->prefetch) {
+        if (sl.stage.p) cudaFreeHost(sl.stage.p);
+        if (sl.d_bounds.p) cudaFree(sl.d_bounds.p);
+        if (sl.d_bres.p) cudaFree(sl.d_bres.p);
+        if (sl.done) cudaEventDestroy(sl.done);
+    }
     if (ctx->ev_jobs) cudaEventDestroy(ctx->ev_jobs);
     for (int i = 0; i < 2; i++)
         if (ctx->ev_gather[i]) cudaEventDestroy(ctx->ev_gather[i]);
@@ -508,6 +515,7 @@ extern "C" int kb_load_sorted(kb_ctx *ctx, const uint8_t *keys, const uint64_t *
     KB_TRY(store_pack_dir(ctx));
     ctx->kused16 = kacc;
     ctx->vused16 = vacc;
+    ctx->store_gen++;
     ctx->garbage_k16 = ctx->garbage_v16 = ctx->displaced = 0;
     ctx->ttl_queue.clear();
     ctx->ttl_of.clear();
@@ -740,6 +748,7 @@ extern "C" int kb_restore(kb_ctx *ctx, const char *path)
     }
     ctx->kused16 = h.key_chunks;
     ctx->vused16 = h.val_chunks;
+    ctx->store_gen++;
     ctx->garbage_k16 = ctx->garbage_v16 = ctx->displaced = 0;
     ctx->ttl_queue.clear();
     ctx->ttl_of.clear();

@@ -201,6 +201,18 @@ struct kb_ctx {
         d_ctrs /* work-queue counters, kept at zero between kernels */;
     HBuf h_stage, h_stage2;
 
+    // kb_range_prefetch: bound searches started ahead of the kb_range_batch that will use them (two in flight at most)
+    struct SearchSlot {
+        HBuf stage;
+        DBuf d_bounds, d_bres;
+        cudaEvent_t done = nullptr;
+        size_t ident_bytes = 0;
+        uint64_t store_gen = 0, seq = 0;
+        bool valid = false;
+    } prefetch[2];
+    uint32_t prefetch_next = 0;
+    uint64_t store_gen = 0;  // bumped whenever the snapshot changes
+
     // buffer pools for results
     std::vector<DBuf> free_dev;
     std::vector<DBuf> free_arena;  // response arenas: only ever written by the gather stream (or after ctx_quiesce)

@@ -1184,10 +1184,10 @@ int layout_requests(kb_ctx *ctx, bool cap_by_limit, Resolved &R)
 }
 
 // upload the bound keys, run k_search, and lay the requests out as tiles
-int resolve_requests(kb_ctx *ctx, const kb_range_req *reqs, uint64_t nreq, bool cap_by_limit, Resolved &R,
-                     kb_tp *tseg = nullptr)
+// pack the bounds of a batch the way k_search reads them: [keys, each padded to 16 bytes + 3 chunks of slack | offsets |
+// lengths]; returns the bytes to upload (the search results land behind them)
+int pack_bounds(kb_ctx *ctx, const kb_range_req *reqs, uint64_t nreq, HBuf &stage, uint64_t *chunks_out)
 {
-    // bound slab: 2 keys per request, each padded to 16 bytes
     uint64_t chunks = 0;
     for (uint64_t q = 0; q < nreq; q++) {
         if ((!reqs[q].start && reqs[q].start_len) || (!reqs[q].end && reqs[q].end_len)) return KB_EINVAL;
@@ -1195,13 +1195,10 @@ int resolve_requests(kb_ctx *ctx, const kb_range_req *reqs, uint64_t nreq, bool 
         chunks += (reqs[q].start_len + 15) / 16 + (reqs[q].end_len + 15) / 16 + 6;
     }
     const uint64_t nb = 2 * nreq;
-    size_t stage_bytes = chunks * 16 + nb * 8 + 64;
-    KB_TRY(hbuf_ensure(ctx, ctx->h_stage, stage_bytes + nb * 4));
-    uint8_t *hs = (uint8_t *)ctx->h_stage.p;
+    KB_TRY(hbuf_ensure(ctx, stage, chunks * 16 + nb * 12 + 128));
+    uint8_t *hs = (uint8_t *)stage.p;
     memset(hs, 0, chunks * 16);
-    uint32_t *hboff = (uint32_t *)(hs + chunks * 16);
-    uint32_t *hblen = hboff + nb;
-    uint32_t *hres = hblen + nb;  // D2H target
+    uint32_t *hboff = (uint32_t *)(hs + chunks * 16), *hblen = hboff + nb;
     uint64_t c = 0;
     for (uint64_t q = 0; q < nreq; q++) {
         const uint8_t *keys[2] = {reqs[q].start, reqs[q].end};
@@ -1213,23 +1210,61 @@ int resolve_requests(kb_ctx *ctx, const kb_range_req *reqs, uint64_t nreq, bool 
             c += (lens[j] + 15) / 16 + 3;
         }
     }
-    // one upload: [bound keys | offsets | lengths] are contiguous in the pinned staging buffer
-    KB_TRY(dbuf_ensure(ctx, ctx->d_bounds, chunks * 16 + nb * 8 + 64));
-    KB_TRY(dbuf_ensure(ctx, ctx->d_bres, nb * 4));
-    // The search only reads the snapshot and its own bound slab, so it runs on the second stream: while the previous
-    // batch's gather is still draining on the main stream the host already learns the record intervals of this one.
-    // (With every kernel bracketed by profiling events -- level 1 -- it stays on the main stream.)
-    cudaStream_t ss = ctx->prof_on == 1 ? ctx->stream : ctx->stream2;
-    KB_CUDA(ctx, cudaMemcpyAsync(ctx->d_bounds.p, hs, chunks * 16 + nb * 8, cudaMemcpyHostToDevice, ss));
-    const uint32_t *d_boff = (const uint32_t *)((const uint8_t *)ctx->d_bounds.p + chunks * 16);
+    *chunks_out = chunks;
+    return KB_OK;
+}
+
+// upload + k_search + download of the results, all asynchronous on `ss`
+int enqueue_search(kb_ctx *ctx, HBuf &stage, DBuf &d_bounds, DBuf &d_bres, uint64_t chunks, uint64_t nb, cudaStream_t ss)
+{
+    uint8_t *hs = (uint8_t *)stage.p;
+    uint32_t *hres = (uint32_t *)(hs + chunks * 16) + 2 * nb;  // D2H target, behind offsets and lengths
+    KB_TRY(dbuf_ensure(ctx, d_bounds, chunks * 16 + nb * 8 + 64));
+    KB_TRY(dbuf_ensure(ctx, d_bres, nb * 4 + 16));
+    KB_CUDA(ctx, cudaMemcpyAsync(d_bounds.p, hs, chunks * 16 + nb * 8, cudaMemcpyHostToDevice, ss));
+    const uint32_t *d_boff = (const uint32_t *)((const uint8_t *)d_bounds.p + chunks * 16);
     const unsigned sgrid = (unsigned)((nb * 32 + 127) / 128);
-    KB_LAUNCH(ctx, "k_search", nb * 64,
-              (k_search<<<sgrid, 128, 0, ss>>>(ctx->st, (const uint4 *)ctx->d_bounds.p, d_boff, d_boff + nb, (uint32_t)nb,
-                                               (uint32_t *)ctx->d_bres.p)));
-    KB_CUDA(ctx, cudaMemcpyAsync(hres, ctx->d_bres.p, nb * 4, cudaMemcpyDeviceToHost, ss));
-    if (tseg) kb_seg(ctx, "host:range_search_enqueue", *tseg);
-    KB_CUDA(ctx, cudaStreamSynchronize(ss));
-    if (tseg) kb_seg(ctx, "host:range_search_sync", *tseg);
+    if (nb)
+        KB_LAUNCH(ctx, "k_search", nb * 64,
+                  (k_search<<<sgrid, 128, 0, ss>>>(ctx->st, (const uint4 *)d_bounds.p, d_boff, d_boff + nb, (uint32_t)nb,
+                                                   (uint32_t *)d_bres.p)));
+    if (nb) KB_CUDA(ctx, cudaMemcpyAsync(hres, d_bres.p, nb * 4, cudaMemcpyDeviceToHost, ss));
+    return KB_OK;
+}
+
+// upload the bound keys, run k_search (or pick up the search kb_range_prefetch started for exactly these bounds), and lay
+// the requests out as tiles
+int resolve_requests(kb_ctx *ctx, const kb_range_req *reqs, uint64_t nreq, bool cap_by_limit, Resolved &R,
+                     kb_tp *tseg = nullptr)
+{
+    uint64_t chunks = 0;
+    KB_TRY(pack_bounds(ctx, reqs, nreq, ctx->h_stage, &chunks));
+    const uint64_t nb = 2 * nreq;
+    uint8_t *hs = (uint8_t *)ctx->h_stage.p;
+    const uint32_t *hres = (const uint32_t *)(hs + chunks * 16) + 2 * nb;
+    const size_t ident_bytes = chunks * 16 + nb * 8;
+    // a prefetched search for the same bounds on the same snapshot?
+    kb_ctx::SearchSlot *hit = nullptr;
+    for (auto &sl : ctx->prefetch)  // the OLDEST matching one: a caller may already have submitted the batch after this one
+        if (sl.valid && sl.ident_bytes == ident_bytes && sl.store_gen == ctx->store_gen &&
+            memcmp(sl.stage.p, hs, ident_bytes) == 0 && (!hit || sl.seq < hit->seq))
+            hit = &sl;
+    if (hit && ctx->prof_on != 1) {
+        if (tseg) kb_seg(ctx, "host:range_search_enqueue", *tseg);
+        KB_CUDA(ctx, cudaEventSynchronize(hit->done));
+        hres = (const uint32_t *)((const uint8_t *)hit->stage.p + chunks * 16) + 2 * nb;
+        hit->valid = false;  // consumed
+        if (tseg) kb_seg(ctx, "host:range_search_sync", *tseg);
+    } else {
+        // The search only reads the snapshot and its own bound slab, so it runs on the second stream: while the previous
+        // batch's gather is still draining the host already learns the record intervals of this one.
+        // (With every kernel bracketed by profiling events -- level 1 -- it stays on the main stream.)
+        cudaStream_t ss = ctx->prof_on == 1 ? ctx->stream : ctx->stream2;
+        KB_TRY(enqueue_search(ctx, ctx->h_stage, ctx->d_bounds, ctx->d_bres, chunks, nb, ss));
+        if (tseg) kb_seg(ctx, "host:range_search_enqueue", *tseg);
+        KB_CUDA(ctx, cudaStreamSynchronize(ss));
+        if (tseg) kb_seg(ctx, "host:range_search_sync", *tseg);
+    }
 
     R.reqs.resize(nreq);
     for (uint64_t q = 0; q < nreq; q++) {
@@ -1764,6 +1799,30 @@ extern "C" int kb_range_batch(kb_ctx *ctx, const kb_range_req *reqs, uint64_t nr
     return KB_OK;
 }
 
+// Start the bound search of a batch that a later kb_range_batch will ask for (same bounds, same snapshot): a caller with a
+// queue of pending requests submits batch n+1 before it waits for batch n, so the search's host round trip (the one
+// synchronisation a range call needs before it can lay its requests out) overlaps the previous batch's kernels.
+extern "C" int kb_range_prefetch(kb_ctx *ctx, const kb_range_req *reqs, uint64_t nreq)
+{
+    if (!ctx || (nreq && !reqs)) return KB_EINVAL;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    if (!ctx->loaded) return kb_fail(ctx, KB_ESTATE, "no store loaded");
+    cudaSetDevice(ctx->device);
+    kb_ctx::SearchSlot &sl = ctx->prefetch[ctx->prefetch_next++ & 1];
+    if (!sl.done) KB_CUDA(ctx, cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
+    else KB_CUDA(ctx, cudaEventSynchronize(sl.done));  // an unconsumed older prefetch still owns the slot's buffers
+    sl.valid = false;
+    uint64_t chunks = 0;
+    KB_TRY(pack_bounds(ctx, reqs, nreq, sl.stage, &chunks));
+    KB_TRY(enqueue_search(ctx, sl.stage, sl.d_bounds, sl.d_bres, chunks, 2 * nreq, ctx->stream2));
+    KB_CUDA(ctx, cudaEventRecord(sl.done, ctx->stream2));
+    sl.ident_bytes = chunks * 16 + 2 * nreq * 8;
+    sl.store_gen = ctx->store_gen;
+    sl.seq = ctx->prefetch_next;
+    sl.valid = true;
+    return KB_OK;
+}
+
 extern "C" int kb_result_wait(kb_ctx *ctx, const kb_result *res, void *cuda_stream)
 {
     if (!ctx || !res) return KB_EINVAL;
@@ -2202,6 +2261,7 @@ static void dir_swap(kb_ctx *ctx, uint64_t n)
     ctx->st.kslab = (const uint4 *)ctx->d_kslab.p;
     ctx->st.vslab = (const uint4 *)ctx->d_vslab.p;
     ctx->st.n = (uint32_t)n;
+    ctx->store_gen++;  // prefetched bound searches of the old snapshot are void
 }
 
 // rewrite both slabs contiguously in key order (also what kb_dump writes); the caller holds ctx->mu

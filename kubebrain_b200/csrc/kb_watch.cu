@@ -166,50 +166,78 @@ __device__ __forceinline__ void d_batch_pm(const EvDev &ev, uint64_t *__restrict
 
 // ---- per event and distinct prefix length: the group whose prefix the key starts with (or NONE).
 //      ematch[li * E + i]; group counts are aggregated inside the warp before touching memory.
+//      A thread owns EPT events (i, i + blockDim, ..): the hash / probe / verify chains of its events are independent and
+//      are written interleaved so that their loads are in flight together (the phase is a chain of ~4 dependent loads per
+//      prefix length; one CTA per SM has 256 threads for ~680 events).
+constexpr int FAN_EPT = 3;
+
 __device__ __forceinline__ void d_match_count(const EvDev &ev, const TabDev &tb, uint32_t *__restrict__ ematch,
                                               uint32_t *__restrict__ gcnt, uint32_t vblock)
 {
-    const uint32_t i = vblock * blockDim.x + threadIdx.x;
     const uint32_t lane = threadIdx.x & 31;
-    const bool valid = i < ev.n;
-    const uint32_t klen = valid ? ev.klen[i] : 0;
-    const uint4 *kp = ev.keys + (uint64_t)(valid ? i : 0) * ev.stride16;
-    uint64_t h = FNV_OFFSET;
-    uint32_t pos = 0;  // bytes hashed so far
-    uint4 chunk = make_uint4(0, 0, 0, 0);
+    uint32_t i[FAN_EPT], klen[FAN_EPT];
+    const uint4 *kp[FAN_EPT];
+    uint64_t h[FAN_EPT];
+    uint4 chunk[FAN_EPT];
+    bool valid[FAN_EPT];
+#pragma unroll
+    for (int e = 0; e < FAN_EPT; e++) {
+        i[e] = (vblock * FAN_EPT + e) * blockDim.x + threadIdx.x;
+        valid[e] = i[e] < ev.n;
+        klen[e] = valid[e] ? ev.klen[i[e]] : 0;
+        kp[e] = ev.keys + (uint64_t)(valid[e] ? i[e] : 0) * ev.stride16;
+        h[e] = FNV_OFFSET;
+        chunk[e] = make_uint4(0, 0, 0, 0);
+    }
+    uint32_t pos = 0;  // bytes hashed so far (the same for every event: lengths are visited in ascending order)
     for (uint32_t li = 0; li < tb.n_lens; li++) {  // uniform trip count: the warp collectives below need all lanes
         const uint32_t L = __ldg(tb.lens + li);
-        uint32_t g = KB_NONE;
-        if (valid && L <= klen) {
-            while (pos < L) {
-                if ((pos & 15) == 0) chunk = __ldg(kp + (pos >> 4));
-                h = (h ^ (uint64_t)byte_of(chunk, pos & 15)) * FNV_PRIME;
-                pos++;
+        for (; pos < L; pos++) {
+            if ((pos & 15) == 0) {
+#pragma unroll
+                for (int e = 0; e < FAN_EPT; e++) chunk[e] = __ldg(kp[e] + (pos >> 4));  // in bounds: L <= stride
             }
-            // probe (hash, length): one 16-byte entry per slot; verify the bytes so the result is exact
-            uint32_t s = slot_of(h, L, tb.mask);
+#pragma unroll
+            for (int e = 0; e < FAN_EPT; e++) h[e] = (h[e] ^ (uint64_t)byte_of(chunk[e], pos & 15)) * FNV_PRIME;
+        }
+        // probe (hash, length): one 16-byte entry per slot; the first probes of all events go out together
+        uint32_t s[FAN_EPT], g[FAN_EPT];
+        uint4 t[FAN_EPT];
+#pragma unroll
+        for (int e = 0; e < FAN_EPT; e++) {
+            s[e] = slot_of(h[e], L, tb.mask);
+            t[e] = __ldg(tb.table + s[e]);
+            g[e] = KB_NONE;
+        }
+#pragma unroll
+        for (int e = 0; e < FAN_EPT; e++) {
+            if (!(valid[e] && L <= klen[e])) continue;
             for (;;) {
-                const uint4 t = __ldg(tb.table + s);
-                if (t.w == KB_NONE) break;
-                if (t.x == (uint32_t)h && t.y == (uint32_t)(h >> 32) && t.z == L) {
-                    const uint4 *gp = tb.gprefix + (uint64_t)t.w * tb.pstride16;
+                if (t[e].w == KB_NONE) break;
+                if (t[e].x == (uint32_t)h[e] && t[e].y == (uint32_t)(h[e] >> 32) && t[e].z == L) {
+                    // verify the bytes so the result is exact
+                    const uint4 *gp = tb.gprefix + (uint64_t)t[e].w * tb.pstride16;
                     bool eq = true;
                     for (uint32_t k = 0; k * 16 < L && eq; k++) {
-                        uint4 a = __ldg(kp + k), b = __ldg(gp + k);
+                        uint4 a = __ldg(kp[e] + k), b = __ldg(gp + k);
                         int p = first_diff16(a, b);
                         if (p < 16 && k * 16 + p < L) eq = false;
                     }
                     if (eq) {
-                        g = t.w;
+                        g[e] = t[e].w;
                         break;  // prefixes are unique per group
                     }
                 }
-                s = (s + 1) & tb.mask;
+                s[e] = (s[e] + 1) & tb.mask;
+                t[e] = __ldg(tb.table + s[e]);
             }
         }
-        if (valid) ematch[(uint64_t)li * ev.n + i] = g;
-        const unsigned peers = __match_any_sync(FULL, g);
-        if (g != KB_NONE && lane == (unsigned)(__ffs(peers) - 1)) atomicAdd(&gcnt[g], (uint32_t)__popc(peers));
+#pragma unroll
+        for (int e = 0; e < FAN_EPT; e++) {
+            if (valid[e]) ematch[(uint64_t)li * ev.n + i[e]] = g[e];
+            const unsigned peers = __match_any_sync(FULL, g[e]);
+            if (g[e] != KB_NONE && lane == (unsigned)(__ffs(peers) - 1)) atomicAdd(&gcnt[g[e]], (uint32_t)__popc(peers));
+        }
     }
 }
 
@@ -252,7 +280,7 @@ __device__ __forceinline__ void d_scatter(const FanScratch &sc, uint32_t n_event
     const uint32_t lane = threadIdx.x & 31;
     const bool valid = i < n_events;
     for (uint32_t li = 0; li < n_lens; li++) {
-        const uint32_t g = valid ? sc.ematch[(uint64_t)li * n_events + i] : KB_NONE;  // written by this very thread in P1
+        const uint32_t g = valid ? ldcg32(&sc.ematch[(uint64_t)li * n_events + i]) : KB_NONE;  // written by another CTA in P1
         const unsigned peers = __match_any_sync(FULL, g);
         if (g == KB_NONE) continue;
         const uint32_t leader = __ffs(peers) - 1;
@@ -389,71 +417,108 @@ __device__ __forceinline__ void d_expand_large(const FanScratch &sc, uint32_t *w
     }
 }
 
-// ---- P4: warp per watcher
+// ---- P4: deliveries per watcher.  A warp takes TWO watchers at a time, one per 16-lane half: a namespace watcher's
+// group holds a handful of events (<= 16 in 99 % of the cases), which a half-warp rank-sorts in registers; a watcher whose
+// group is larger (or medium / large: already sorted by P3) is then handled by the whole warp.
+__device__ __forceinline__ void d_watcher_big(const TabDev &tb, const FanScratch &sc, bool mono, uint32_t w, uint32_t n,
+                                              uint32_t base, uint32_t lane)
+{
+    const uint64_t mr = __ldg(tb.wminrev + w);
+    uint32_t lo = 0, cnt = 0;
+    if (n <= 32) {
+        // small group: rank sort in registers; every watcher of the group writes the same ascending segment
+        const uint32_t v = lane < n ? ldcg32(&sc.seg[base + lane]) : 0xFFFFFFFFu;
+        uint32_t rank = 0;
+#pragma unroll
+        for (int j = 0; j < 32; j++) {
+            const uint32_t o = __shfl_sync(FULL, v, j);
+            rank += (o < v) ? 1u : 0u;  // event indices inside one group are distinct
+        }
+        if (lane < n) sc.sorted[base + rank] = v;
+        const bool keep = lane < n && ldcg64(&sc.pm[v]) >= mr;
+        cnt = __popc(__ballot_sync(FULL, keep));
+        lo = mono ? n - cnt : 0;
+    } else if (mono) {
+        // survivors are a suffix of the ascending segment: 32-ary search for the first event at or above min_rev
+        const uint32_t *M = sc.sorted + base;
+        uint32_t hi = n;
+        for (;;) {
+            const uint32_t span = hi - lo;
+            if (span == 0) break;
+            if (span <= 32) {
+                const bool ge = lane < span && ldcg64(&sc.pm[ldcg32(&M[lo + lane])]) >= mr;
+                const unsigned m = __ballot_sync(FULL, ge);
+                lo += m ? (uint32_t)(__ffs(m) - 1) : span;
+                break;
+            }
+            const uint32_t piv = lo + (uint32_t)(((uint64_t)span * (lane + 1)) / 33);
+            const bool ge = ldcg64(&sc.pm[ldcg32(&M[piv])]) >= mr;
+            const int k = __popc(~__ballot_sync(FULL, ge));  // pivots below min_rev: a prefix of the lanes
+            uint32_t nlo = lo, nhi = hi;
+            if (k > 0) nlo = __shfl_sync(FULL, piv, k - 1) + 1;
+            if (k < 32) nhi = __shfl_sync(FULL, piv, k);
+            lo = nlo;
+            hi = nhi;
+        }
+        cnt = n - lo;
+    } else {
+        const uint32_t *M = sc.sorted + base;
+        for (uint32_t c = 0; c < n; c += 32) {
+            const uint32_t j = c + lane;
+            const bool keep = j < n && ldcg64(&sc.pm[ldcg32(&M[j])]) >= mr;
+            cnt += __popc(__ballot_sync(FULL, keep));
+        }
+    }
+    if (lane == 0) {
+        sc.wcnt[w] = cnt;
+        sc.wsrc[w] = base;
+        sc.wn[w] = n;
+        sc.wlo[w] = lo;
+    }
+}
+
 __device__ __forceinline__ void d_watcher_count(const TabDev &tb, const FanScratch &sc, bool mono)
 {
-    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t lane = threadIdx.x & 31, half = lane >> 4, sub = lane & 15;
     const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
-    for (uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < tb.n_ids; w += warps) {
-        const uint32_t g = __ldg(tb.wgroup + w);
-        uint32_t n = 0, base = 0, lo = 0, cnt = 0;
+    for (uint32_t w0 = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 2; w0 < tb.n_ids; w0 += warps * 2) {
+        const uint32_t w = w0 + half;
+        const bool have = w < tb.n_ids;
+        const uint32_t g = have ? __ldg(tb.wgroup + w) : KB_NONE;
+        uint32_t n = 0, base = 0;
         unsigned long long a = FAN_UNSET;
         if (g != KB_NONE) a = __ldcg(&sc.galloc[g]);
         if (a < FAN_BUSY) {  // the group matched at least one event
             n = ldcg32(&sc.gcnt[g]);
             base = (uint32_t)a;
-            const uint64_t mr = __ldg(tb.wminrev + w);
-            if (n <= 32) {
-                // small group: rank sort in registers; every watcher of the group writes the same ascending segment
-                const uint32_t v = lane < n ? ldcg32(&sc.seg[base + lane]) : 0xFFFFFFFFu;
-                uint32_t rank = 0;
+        }
+        const unsigned hmask = half ? 0xFFFF0000u : 0x0000FFFFu;  // the halves may diverge: they only sync among themselves
+        if (n <= 16) {
+            // this half-warp's watcher: rank sort of <= 16 entries with 16-lane shuffles
+            const uint64_t mr = have ? __ldg(tb.wminrev + w) : 0;
+            const uint32_t v = sub < n ? ldcg32(&sc.seg[base + sub]) : 0xFFFFFFFFu;
+            uint32_t rank = 0;
 #pragma unroll
-                for (int j = 0; j < 32; j++) {
-                    const uint32_t o = __shfl_sync(FULL, v, j);
-                    rank += (o < v) ? 1u : 0u;  // event indices inside one group are distinct
-                }
-                if (lane < n) sc.sorted[base + rank] = v;
-                const bool keep = lane < n && ldcg64(&sc.pm[v]) >= mr;
-                cnt = __popc(__ballot_sync(FULL, keep));
-                lo = mono ? n - cnt : 0;
-            } else if (mono) {
-                // survivors are a suffix of the ascending segment: 32-ary search for the first event at or above min_rev
-                const uint32_t *M = sc.sorted + base;
-                uint32_t hi = n;
-                for (;;) {
-                    const uint32_t span = hi - lo;
-                    if (span == 0) break;
-                    if (span <= 32) {
-                        const bool ge = lane < span && ldcg64(&sc.pm[ldcg32(&M[lo + lane])]) >= mr;
-                        const unsigned m = __ballot_sync(FULL, ge);
-                        lo += m ? (uint32_t)(__ffs(m) - 1) : span;
-                        break;
-                    }
-                    const uint32_t piv = lo + (uint32_t)(((uint64_t)span * (lane + 1)) / 33);
-                    const bool ge = ldcg64(&sc.pm[ldcg32(&M[piv])]) >= mr;
-                    const int k = __popc(~__ballot_sync(FULL, ge));  // pivots below min_rev: a prefix of the lanes
-                    uint32_t nlo = lo, nhi = hi;
-                    if (k > 0) nlo = __shfl_sync(FULL, piv, k - 1) + 1;
-                    if (k < 32) nhi = __shfl_sync(FULL, piv, k);
-                    lo = nlo;
-                    hi = nhi;
-                }
-                cnt = n - lo;
-            } else {
-                const uint32_t *M = sc.sorted + base;
-                for (uint32_t c = 0; c < n; c += 32) {
-                    const uint32_t j = c + lane;
-                    const bool keep = j < n && ldcg64(&sc.pm[ldcg32(&M[j])]) >= mr;
-                    cnt += __popc(__ballot_sync(FULL, keep));
-                }
+            for (int j = 0; j < 16; j++) {
+                const uint32_t o = __shfl_sync(hmask, v, j, 16);
+                rank += (o < v) ? 1u : 0u;
+            }
+            if (sub < n) sc.sorted[base + rank] = v;
+            const bool keep = sub < n && ldcg64(&sc.pm[v]) >= mr;
+            const uint32_t cnt = __popc(__ballot_sync(hmask, keep));
+            if (sub == 0 && have) {
+                sc.wcnt[w] = cnt;
+                sc.wsrc[w] = base;
+                sc.wn[w] = n;
+                sc.wlo[w] = mono ? n - cnt : 0;
             }
         }
-        if (lane == 0) {
-            sc.wcnt[w] = cnt;
-            sc.wsrc[w] = base;
-            sc.wn[w] = n;
-            sc.wlo[w] = lo;
-        }
+        __syncwarp();
+        // watchers with a bigger group: the whole warp, one after the other
+        const uint32_t n0 = __shfl_sync(FULL, n, 0), n1 = __shfl_sync(FULL, n, 16);
+        const uint32_t b0 = __shfl_sync(FULL, base, 0), b1 = __shfl_sync(FULL, base, 16);
+        if (n0 > 16) d_watcher_big(tb, sc, mono, w0, n0, b0, lane);
+        if (n1 > 16 && w0 + 1 < tb.n_ids) d_watcher_big(tb, sc, mono, w0 + 1, n1, b1, lane);
     }
 }
 
@@ -517,7 +582,8 @@ k_fanout(EvDev ev, TabDev tb, FanScratch sc)
     // P1
     const uint32_t pm_blocks = (ev.nb * 32 + FAN_THREADS - 1) / FAN_THREADS;
     const uint32_t ev_blocks = tb.n_groups ? (ev.n + FAN_THREADS - 1) / FAN_THREADS : 0;
-    for (uint32_t vb = blockIdx.x; vb < pm_blocks + ev_blocks; vb += gridDim.x) {
+    const uint32_t ev_blocks3 = (ev_blocks + FAN_EPT - 1) / FAN_EPT;  // P1: a virtual block covers FAN_EPT x 256 events
+    for (uint32_t vb = blockIdx.x; vb < pm_blocks + ev_blocks3; vb += gridDim.x) {
         if (vb < pm_blocks)
             d_batch_pm(ev, sc.pm, &sc.ctl[FC_NONMONO], vb);
         else

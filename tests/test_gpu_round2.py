@@ -79,6 +79,31 @@ def test_ttl_expire(eng):
     assert not expire
 
 
+def test_range_prefetch(eng):
+    """kb_range_prefetch: the bound search of a batch started ahead is picked up by the identical batch on the same
+    snapshot and ignored otherwise (other bounds, snapshot changed in between); two submissions may be outstanding"""
+    store, meta = synth.gen_store(3000, 3, 64, 80, 9, config_id=2, tomb_frac=0.1)
+    st = ko.OracleStore(store)
+    eng.load_sorted(store)
+    p = b"/registry/pods/ns-00003/"
+    a = [(LO, HI, meta.read_rev, 0), (CODER.encode_object_key(p, 0), CODER.encode_object_key(prefix_end(p), 0), meta.last_rev, 5)]
+    b = [(LO, HI, meta.last_rev, 7)]
+    eng.range_prefetch(a)
+    eng.range_prefetch(a)  # the batch after the next one, submitted before the first is consumed
+    check_ranges(eng, store, st, a)
+    check_ranges(eng, store, st, a)
+    eng.range_prefetch(a)
+    check_ranges(eng, store, st, b)  # different bounds: own search
+    check_ranges(eng, store, st, a)  # the submission from before is still there
+    eng.range_prefetch(a)
+    k = store.keys[10]
+    eng.apply_batch([(k, None)])  # the snapshot changes: the submitted search is void
+    items = dict(zip(store.keys.tolist(), store.vals.tolist()))
+    items.pop(k)
+    cur = PackedStore.from_items(list(items.items()))
+    check_ranges(eng, cur, ko.OracleStore(cur), a)
+
+
 def test_list_response_wire(eng):
     """wire.list_response: user limit -> scan limit + 1 -> cut at elem_off[limit] -> More / Count
     (pkg/backend/range.go:150-170, pkg/server/etcd/backendshim.go:269-277)"""
