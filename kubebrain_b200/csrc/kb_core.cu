@@ -320,8 +320,9 @@ extern "C" void kb_close(kb_ctx *ctx)
         if (sl.stage.p) cudaFreeHost(sl.stage.p);
         if (sl.d_bounds.p) cudaFree(sl.d_bounds.p);
         if (sl.d_bres.p) cudaFree(sl.d_bres.p);
-        if (sl.done) cudaEventDestroy(sl.done);
+        if (sl.pub.host) cudaFreeHost(sl.pub.host);
     }
+    if (ctx->search_pub.host) cudaFreeHost(ctx->search_pub.host);
     if (ctx->ev_jobs) cudaEventDestroy(ctx->ev_jobs);
     for (int i = 0; i < 2; i++)
         if (ctx->ev_gather[i]) cudaEventDestroy(ctx->ev_gather[i]);

@@ -67,6 +67,22 @@ __device__ __forceinline__ void dbulk_g2s(void *dst, const void *src, uint32_t b
                  "l"(src), "r"(bytes), "r"(dsmem_u32(bar))
                  : "memory");
 }
+// Streaming variant: the bytes are read once per scan, so they are the first to leave L2 (evict_first) -- the 126 MB L2 then
+// keeps what the latency-bound kernels running beside the scan re-read (directory arrays, meta words, the fan-out's
+// tables and scratch) instead of cycling 1.2 GB of keys and values through it every step.
+__device__ __forceinline__ uint64_t l2_evict_first_policy()
+{
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void dbulk_g2s_stream(void *dst, const void *src, uint32_t bytes, uint64_t *bar, uint64_t pol)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                     dsmem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(dsmem_u32(bar)), "l"(pol)
+                 : "memory");
+}
 __device__ __forceinline__ void dmbar_expect(uint64_t *bar, uint32_t bytes)
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(dsmem_u32(bar)), "r"(bytes) : "memory");
@@ -225,6 +241,7 @@ k_decode_lcp(StoreDev st, const TileDev *__restrict__ tiles, DecGeom g, ScanMode
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const unsigned FULLM = 0xffffffffu;
     const uint32_t NKS = g.NKS, NDS = g.NKS + 1;  // a step's keys are in flight NKS - 1 steps, its directory entries NKS
+    const uint64_t l2pol = l2_evict_first_policy();
     uint4 *kbuf = smem + (size_t)warp * (NKS * g.SK + NDS * g.DS);
     uint4 *dbuf = kbuf + NKS * g.SK;
     uint64_t *kbar = bars + warp * DECODE_MAX_BARS, *dbar = kbar + DECODE_MAX_KS;
@@ -341,7 +358,7 @@ k_decode_lcp(StoreDev st, const TileDev *__restrict__ tiles, DecGeom g, ScanMode
             if (span <= g.SK) {
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 dmbar_expect(kbar + ks, span * 16);
-                dbulk_g2s(kbuf + (size_t)ks * g.SK, st.kslab + base16, span * 16, kbar + ks);
+                dbulk_g2s_stream(kbuf + (size_t)ks * g.SK, st.kslab + base16, span * 16, kbar + ks, l2pol);
             }
         }
     };

@@ -202,10 +202,16 @@ struct kb_ctx {
     HBuf h_stage, h_stage2;
 
     // kb_range_prefetch: bound searches started ahead of the kb_range_batch that will use them (two in flight at most)
+    struct SearchPubBuf {  // mapped pinned: [flag u64 | pad to 64 bytes | results u32 x nb], written by k_search
+        uint8_t *host = nullptr;
+        size_t cap = 0;
+        uint64_t epoch = 0;
+    };
+    SearchPubBuf search_pub;  // of the search a range call runs itself
     struct SearchSlot {
         HBuf stage;
         DBuf d_bounds, d_bres;
-        cudaEvent_t done = nullptr;
+        SearchPubBuf pub;
         size_t ident_bytes = 0;
         uint64_t store_gen = 0, seq = 0;
         bool valid = false;

@@ -62,10 +62,19 @@ __device__ __forceinline__ bool key_less(const StoreDev &st, uint32_t rec, const
 }
 
 // out[w] = index of the first record whose key >= bound w (bytes.Compare order)
+// pub (optional): mapped pinned memory [flag u64 | pad to 64 bytes | results u32 x nb].  Every warp stores its result there
+// too; the warp that completes the count raises the flag to `epoch` -- the host polls it instead of paying a stream /
+// event synchronisation (measured 70 us for an already finished search while another host thread was busy in the driver).
+struct SearchPub {
+    uint8_t *host;          // nullptr: results only in `out`
+    unsigned int *done;     // device counter, zero between searches
+    uint64_t epoch;
+};
+
 __global__ void __launch_bounds__(128) k_search(StoreDev st, const uint4 *__restrict__ bounds,
                                                 const uint32_t *__restrict__ boff16,
                                                 const uint32_t *__restrict__ blen, uint32_t nb,
-                                                uint32_t *__restrict__ out)
+                                                uint32_t *__restrict__ out, SearchPub pub)
 {
     uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     uint32_t lane = threadIdx.x & 31;
@@ -90,7 +99,18 @@ __global__ void __launch_bounds__(128) k_search(StoreDev st, const uint4 *__rest
         lo = nlo;
         hi = nhi;
     }
-    if (lane == 0) out[w] = lo;
+    if (lane == 0) {
+        out[w] = lo;
+        if (pub.host) {
+            ((volatile uint32_t *)(pub.host + 64))[w] = lo;
+            __threadfence_system();
+            if (atomicAdd(pub.done, 1u) == nb - 1) {
+                *pub.done = 0;
+                __threadfence_system();
+                *(volatile uint64_t *)pub.host = pub.epoch;
+            }
+        }
+    }
 }
 
 
@@ -772,6 +792,7 @@ k_gather(StoreDev st, const GatherJob *__restrict__ jobs, const uint64_t *__rest
     __syncwarp();
 
     const uint64_t n_kvs = *n_kvs_dev;
+    const uint64_t l2pol = l2_evict_first_policy();  // both directions stream: the copy must not flush L2 for its neighbours
     const uint32_t dist = stages - 2;   // pieces in flight per warp
     uint32_t in_flight = 0;             // pieces issued and not yet stored (lane 0 only)
     uint32_t si = 0, ss = 0, ph = 0;    // issue slot, store slot, parity of the store slot's current fill
@@ -779,8 +800,8 @@ k_gather(StoreDev st, const GatherJob *__restrict__ jobs, const uint64_t *__rest
     // wait for the oldest in-flight piece and send it to the arena
     auto retire = [&]() {
         mbar_wait_parity(bar + ss, ph, err_flag);
-        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(arena + rdst[ss]),
-                     "r"(smem_u32(buf + ss * piece)), "r"(rlen[ss] * 16)
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(arena + rdst[ss]),
+                     "r"(smem_u32(buf + ss * piece)), "r"(rlen[ss] * 16), "l"(l2pol)
                      : "memory");
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         if (++ss == stages) {
@@ -837,16 +858,16 @@ k_gather(StoreDev st, const GatherJob *__restrict__ jobs, const uint64_t *__rest
                     const uint32_t kpart = c0 < nk ? min(nk - c0, len) : 0;  // chunks of this piece from the key
                     if (kpart)
                         asm volatile(
-                            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
                                 smem_u32(dstbuf)),
-                            "l"(st.kslab + ksrc16 + c0), "r"(kpart * 16), "r"(smem_u32(bar + si))
+                            "l"(st.kslab + ksrc16 + c0), "r"(kpart * 16), "r"(smem_u32(bar + si)), "l"(l2pol)
                             : "memory");
                     if (len > kpart) {
                         const uint32_t v0c = (c0 + kpart) - nk;  // first value chunk of this piece
                         asm volatile(
-                            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
                                 smem_u32(dstbuf + kpart)),
-                            "l"(st.vslab + vsrc16 + v0c), "r"((len - kpart) * 16), "r"(smem_u32(bar + si))
+                            "l"(st.vslab + vsrc16 + v0c), "r"((len - kpart) * 16), "r"(smem_u32(bar + si)), "l"(l2pol)
                             : "memory");
                     }
                     rdst[si] = dst16 + c0;
@@ -1214,22 +1235,57 @@ int pack_bounds(kb_ctx *ctx, const kb_range_req *reqs, uint64_t nreq, HBuf &stag
     return KB_OK;
 }
 
-// upload + k_search + download of the results, all asynchronous on `ss`
-int enqueue_search(kb_ctx *ctx, HBuf &stage, DBuf &d_bounds, DBuf &d_bres, uint64_t chunks, uint64_t nb, cudaStream_t ss)
+// upload + k_search, asynchronous on `ss`; the results are published into `pub` (mapped pinned: [flag | pad | u32 x nb])
+int enqueue_search(kb_ctx *ctx, HBuf &stage, DBuf &d_bounds, DBuf &d_bres, uint64_t chunks, uint64_t nb, cudaStream_t ss,
+                   kb_ctx::SearchPubBuf &pb, int slot)
 {
     uint8_t *hs = (uint8_t *)stage.p;
-    uint32_t *hres = (uint32_t *)(hs + chunks * 16) + 2 * nb;  // D2H target, behind offsets and lengths
     KB_TRY(dbuf_ensure(ctx, d_bounds, chunks * 16 + nb * 8 + 64));
     KB_TRY(dbuf_ensure(ctx, d_bres, nb * 4 + 16));
+    const size_t need = 64 + nb * 4 + 64;
+    if (!pb.host || pb.cap < need) {
+        if (pb.host) {
+            KB_CUDA(ctx, cudaStreamSynchronize(ss));
+            cudaFreeHost(pb.host);
+            pb.host = nullptr;
+        }
+        KB_CUDA(ctx, cudaHostAlloc((void **)&pb.host, need * 2, cudaHostAllocMapped));
+        memset(pb.host, 0, need * 2);
+        pb.cap = need * 2;
+        pb.epoch = 0;
+    }
+    if (!ctx->d_ctrs.p) {
+        KB_TRY(dbuf_ensure(ctx, ctx->d_ctrs, 256));
+        KB_CUDA(ctx, cudaMemsetAsync(ctx->d_ctrs.p, 0, 256, ss));
+    }
     KB_CUDA(ctx, cudaMemcpyAsync(d_bounds.p, hs, chunks * 16 + nb * 8, cudaMemcpyHostToDevice, ss));
     const uint32_t *d_boff = (const uint32_t *)((const uint8_t *)d_bounds.p + chunks * 16);
     const unsigned sgrid = (unsigned)((nb * 32 + 127) / 128);
-    if (nb)
-        KB_LAUNCH(ctx, "k_search", nb * 64,
-                  (k_search<<<sgrid, 128, 0, ss>>>(ctx->st, (const uint4 *)d_bounds.p, d_boff, d_boff + nb, (uint32_t)nb,
-                                                   (uint32_t *)d_bres.p)));
-    if (nb) KB_CUDA(ctx, cudaMemcpyAsync(hres, d_bres.p, nb * 4, cudaMemcpyDeviceToHost, ss));
+    pb.epoch++;
+    if (nb == 0) {
+        *(volatile uint64_t *)pb.host = pb.epoch;  // nothing to search: already "published"
+        return KB_OK;
+    }
+    SearchPub pub{pb.host, (unsigned int *)ctx->d_ctrs.p + 16 + slot, pb.epoch};
+    KB_LAUNCH(ctx, "k_search", nb * 64,
+              (k_search<<<sgrid, 128, 0, ss>>>(ctx->st, (const uint4 *)d_bounds.p, d_boff, d_boff + nb, (uint32_t)nb,
+                                               (uint32_t *)d_bres.p, pub)));
     return KB_OK;
+}
+
+// wait for a published search; the stream is consulted now and then so that a failed launch is noticed
+int search_wait(kb_ctx *ctx, kb_ctx::SearchPubBuf &pb, cudaStream_t ss)
+{
+    volatile uint64_t *flag = (volatile uint64_t *)pb.host;
+    for (uint64_t spins = 1;; spins++) {
+        if (*flag == pb.epoch) return KB_OK;
+        kb_cpu_relax();
+        if ((spins & 0xFFFF) == 0) {
+            const cudaError_t q = cudaStreamQuery(ss);
+            if (q == cudaSuccess) return *flag == pb.epoch ? KB_OK : kb_fail(ctx, KB_ECUDA, "bound search: results were not published");
+            if (q != cudaErrorNotReady) return kb_cuda_fail(ctx, q, "bound search");
+        }
+    }
 }
 
 // upload the bound keys, run k_search (or pick up the search kb_range_prefetch started for exactly these bounds), and lay
@@ -1241,7 +1297,7 @@ int resolve_requests(kb_ctx *ctx, const kb_range_req *reqs, uint64_t nreq, bool 
     KB_TRY(pack_bounds(ctx, reqs, nreq, ctx->h_stage, &chunks));
     const uint64_t nb = 2 * nreq;
     uint8_t *hs = (uint8_t *)ctx->h_stage.p;
-    const uint32_t *hres = (const uint32_t *)(hs + chunks * 16) + 2 * nb;
+    const uint32_t *hres = nullptr;
     const size_t ident_bytes = chunks * 16 + nb * 8;
     // a prefetched search for the same bounds on the same snapshot?
     kb_ctx::SearchSlot *hit = nullptr;
@@ -1251,8 +1307,8 @@ int resolve_requests(kb_ctx *ctx, const kb_range_req *reqs, uint64_t nreq, bool 
             hit = &sl;
     if (hit && ctx->prof_on != 1) {
         if (tseg) kb_seg(ctx, "host:range_search_enqueue", *tseg);
-        KB_CUDA(ctx, cudaEventSynchronize(hit->done));
-        hres = (const uint32_t *)((const uint8_t *)hit->stage.p + chunks * 16) + 2 * nb;
+        KB_TRY(search_wait(ctx, hit->pub, ctx->stream2));
+        hres = (const uint32_t *)(hit->pub.host + 64);
         hit->valid = false;  // consumed
         if (tseg) kb_seg(ctx, "host:range_search_sync", *tseg);
     } else {
@@ -1260,9 +1316,10 @@ int resolve_requests(kb_ctx *ctx, const kb_range_req *reqs, uint64_t nreq, bool 
         // batch's gather is still draining the host already learns the record intervals of this one.
         // (With every kernel bracketed by profiling events -- level 1 -- it stays on the main stream.)
         cudaStream_t ss = ctx->prof_on == 1 ? ctx->stream : ctx->stream2;
-        KB_TRY(enqueue_search(ctx, ctx->h_stage, ctx->d_bounds, ctx->d_bres, chunks, nb, ss));
+        KB_TRY(enqueue_search(ctx, ctx->h_stage, ctx->d_bounds, ctx->d_bres, chunks, nb, ss, ctx->search_pub, 2));
         if (tseg) kb_seg(ctx, "host:range_search_enqueue", *tseg);
-        KB_CUDA(ctx, cudaStreamSynchronize(ss));
+        KB_TRY(search_wait(ctx, ctx->search_pub, ss));
+        hres = (const uint32_t *)(ctx->search_pub.host + 64);
         if (tseg) kb_seg(ctx, "host:range_search_sync", *tseg);
     }
 
@@ -1808,14 +1865,13 @@ extern "C" int kb_range_prefetch(kb_ctx *ctx, const kb_range_req *reqs, uint64_t
     std::lock_guard<std::mutex> g(ctx->mu);
     if (!ctx->loaded) return kb_fail(ctx, KB_ESTATE, "no store loaded");
     cudaSetDevice(ctx->device);
-    kb_ctx::SearchSlot &sl = ctx->prefetch[ctx->prefetch_next++ & 1];
-    if (!sl.done) KB_CUDA(ctx, cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
-    else KB_CUDA(ctx, cudaEventSynchronize(sl.done));  // an unconsumed older prefetch still owns the slot's buffers
+    const int slot = (int)(ctx->prefetch_next++ & 1);
+    kb_ctx::SearchSlot &sl = ctx->prefetch[slot];
+    if (sl.valid) KB_TRY(search_wait(ctx, sl.pub, ctx->stream2));  // an unconsumed older submission still owns the buffers
     sl.valid = false;
     uint64_t chunks = 0;
     KB_TRY(pack_bounds(ctx, reqs, nreq, sl.stage, &chunks));
-    KB_TRY(enqueue_search(ctx, sl.stage, sl.d_bounds, sl.d_bres, chunks, 2 * nreq, ctx->stream2));
-    KB_CUDA(ctx, cudaEventRecord(sl.done, ctx->stream2));
+    KB_TRY(enqueue_search(ctx, sl.stage, sl.d_bounds, sl.d_bres, chunks, 2 * nreq, ctx->stream2, sl.pub, slot));
     sl.ident_bytes = chunks * 16 + 2 * nreq * 8;
     sl.store_gen = ctx->store_gen;
     sl.seq = ctx->prefetch_next;
@@ -1979,7 +2035,7 @@ extern "C" int kb_get_batch(kb_ctx *ctx, const kb_get_req *reqs, uint64_t n, int
     if (n) {
         KB_LAUNCH(ctx, "k_search", n * 64,
                   (k_search<<<(unsigned)((n * 32 + 127) / 128), 128, 0, ctx->stream>>>(
-                      ctx->st, (const uint4 *)ctx->d_bounds.p, d_boff, d_boff + n, (uint32_t)n, (uint32_t *)ctx->d_bres.p)));
+                      ctx->st, (const uint4 *)ctx->d_bounds.p, d_boff, d_boff + n, (uint32_t)n, (uint32_t *)ctx->d_bres.p, SearchPub{nullptr, nullptr, 0})));
         KB_LAUNCH(ctx, "k_get_resolve", n * 320,
                   (k_get_resolve<<<(unsigned)((n * 32 + 127) / 128), 128, 0, ctx->stream>>>(
                       ctx->st, (const uint4 *)ctx->d_bounds.p, d_boff, d_boff + n, (const uint32_t *)ctx->d_bres.p,
@@ -2433,7 +2489,7 @@ static int apply_batch_locked(kb_ctx *ctx, const kb_write_op *ops, uint64_t n_op
     const unsigned sg = (unsigned)((M * 32 + 127) / 128);
     KB_LAUNCH(ctx, "k_search", M * 64,
               (k_search<<<sg, 128, 0, ctx->stream>>>(ctx->st, (const uint4 *)ctx->d_bounds.p, d_boff, d_boff + M, (uint32_t)M,
-                                                     d_pos)));
+                                                     d_pos, SearchPub{nullptr, nullptr, 0})));
     KB_LAUNCH(ctx, "k_key_exists", M * 320,
               (k_key_exists<<<sg, 128, 0, ctx->stream>>>(ctx->st, (const uint4 *)ctx->d_bounds.p, d_boff, d_boff + M, d_pos,
                                                          (uint32_t)M, d_exists, d_oldv)));
