@@ -27,6 +27,10 @@ import time
 
 import numpy as np
 
+# more hardware work queues than the default 8: the bench drives two contexts x three streams (+ torch's); streams that
+# share a queue serialise behind each other (must be set before the CUDA context exists)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
@@ -367,6 +371,10 @@ def run_b200(args, rank: int, local_rank: int, world: int):
     # the kb_range_req[] a C / cgo caller passes directly; marshalled once so the timed call is the C-ABI call itself
     reqs = Engine.pack_range_reqs(wl["reqs"])
     local_rev = int(wl["meta"].last_rev)
+    if not args.no_prefetch:
+        # pipeline depth one: the FIRST step's bound search is submitted here, every step then submits the next step's
+        # before it asks for its own answer (one submission and one consumption per step)
+        eng.range_prefetch(reqs)
 
     # the fan-out half runs on a long-lived worker thread (ctypes releases the GIL inside the C ABI calls)
     import queue

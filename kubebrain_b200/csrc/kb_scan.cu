@@ -1278,7 +1278,10 @@ int search_wait(kb_ctx *ctx, kb_ctx::SearchPubBuf &pb, cudaStream_t ss)
 {
     volatile uint64_t *flag = (volatile uint64_t *)pb.host;
     for (uint64_t spins = 1;; spins++) {
-        if (*flag == pb.epoch) return KB_OK;
+        if (*flag == pb.epoch) {
+            if (ctx->prof_on) ctx->prof[prof_index(ctx, "host:search_wait_spins")].launches += spins;
+            return KB_OK;
+        }
         kb_cpu_relax();
         if ((spins & 0xFFFF) == 0) {
             const cudaError_t q = cudaStreamQuery(ss);
@@ -1295,6 +1298,7 @@ int resolve_requests(kb_ctx *ctx, const kb_range_req *reqs, uint64_t nreq, bool 
 {
     uint64_t chunks = 0;
     KB_TRY(pack_bounds(ctx, reqs, nreq, ctx->h_stage, &chunks));
+    if (tseg) kb_seg(ctx, "host:range_pack_bounds", *tseg);
     const uint64_t nb = 2 * nreq;
     uint8_t *hs = (uint8_t *)ctx->h_stage.p;
     const uint32_t *hres = nullptr;
@@ -1867,6 +1871,13 @@ extern "C" int kb_range_prefetch(kb_ctx *ctx, const kb_range_req *reqs, uint64_t
     cudaSetDevice(ctx->device);
     const int slot = (int)(ctx->prefetch_next++ & 1);
     kb_ctx::SearchSlot &sl = ctx->prefetch[slot];
+    if (ctx->prof_on) {  // diagnostic: is the OTHER slot's (older) submission already complete when the next one is made?
+        kb_ctx::SearchSlot &other = ctx->prefetch[slot ^ 1];
+        if (other.valid && other.pub.host) {
+            const bool ready = *(volatile uint64_t *)other.pub.host == other.pub.epoch;
+            ctx->prof[prof_index(ctx, ready ? "host:prefetch_older_ready" : "host:prefetch_older_pending")].launches++;
+        }
+    }
     if (sl.valid) KB_TRY(search_wait(ctx, sl.pub, ctx->stream2));  // an unconsumed older submission still owns the buffers
     sl.valid = false;
     uint64_t chunks = 0;

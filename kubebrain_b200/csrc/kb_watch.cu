@@ -45,6 +45,11 @@ struct WatchTablesDev {
     // per-call scratch
     DBuf gstate /* gcnt | gfill | ctl */, galloc, lists, ematch, seg, seg_sorted, bitmaps, pm, wstate /* wcnt | wsrc | wn | wlo */,
         wstart, total;
+    // Everything above is carved out of ONE allocation: [tables | per-call scratch].  The context's stream carries an L2
+    // access-policy window over it (persisting): the scan context streams > 1 GB through the 126 MB L2 in every step, which
+    // would otherwise evict the tables and the scratch between two phases of k_fanout (it then runs on HBM latency).
+    DBuf arena;
+    size_t tab_end = 0, scr_bytes = 0, scr_sig = 0;
     bool scratch_clean = false;   // the previous k_fanout left gstate / galloc / bitmaps in their initial state
     uint32_t scratch_groups = 0, scratch_large = 0, scratch_bm_words = 0;
     uint32_t fan_gen = 0;         // value of the grid-barrier generation word after the last launch
@@ -678,9 +683,44 @@ uint64_t fnv1a(const std::string &s)
     return h;
 }
 
+inline size_t arena_align(size_t x) { return (x + 255) & ~(size_t)255; }
+
+// a view of `bytes` at `cursor` inside the arena (the caller made sure it fits); views are never freed on their own
+void arena_view(WatchTablesDev &T, size_t &cursor, DBuf &view, size_t bytes)
+{
+    view.p = (uint8_t *)T.arena.p + cursor;
+    view.cap = 0;
+    cursor += arena_align(std::max<size_t>(bytes, 16));
+}
+
+// (re)allocate the arena for `need` bytes and put the L2 access-policy window of the context's stream over it
+int arena_reserve(kb_ctx *ctx, WatchTablesDev &T, size_t need)
+{
+    if (T.arena.p && T.arena.cap >= need) return KB_OK;
+    KB_TRY(dbuf_ensure(ctx, T.arena, need + need / 2));
+    T.scratch_clean = false;
+    ctx->watch_dirty = true;  // the tables lived in the old allocation
+    cudaStreamAttrValue attr;
+    memset(&attr, 0, sizeof(attr));
+    int max_win = 0, persist_max = 0;
+    cudaDeviceGetAttribute(&max_win, cudaDevAttrMaxAccessPolicyWindowSize, ctx->device);
+    cudaDeviceGetAttribute(&persist_max, cudaDevAttrMaxPersistingL2CacheSize, ctx->device);
+    const size_t setaside = std::min<size_t>((size_t)persist_max, (size_t)32 << 20);
+    if (max_win > 0 && setaside > 0) {
+        cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, setaside);  // device-wide; the same value from every context
+        attr.accessPolicyWindow.base_ptr = T.arena.p;
+        attr.accessPolicyWindow.num_bytes = std::min<size_t>(T.arena.cap, (size_t)max_win);
+        attr.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)setaside / (double)attr.accessPolicyWindow.num_bytes);
+        attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &attr);
+    }
+    cudaGetLastError();  // the window is an optimisation: a part that refuses it still computes the same answers
+    return KB_OK;
+}
+
 int upload(kb_ctx *ctx, DBuf &b, const void *src, size_t bytes)
 {
-    KB_TRY(dbuf_ensure(ctx, b, std::max<size_t>(bytes, 16)));
     if (bytes) KB_CUDA(ctx, cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
     return KB_OK;
 }
@@ -728,6 +768,18 @@ int rebuild_tables(kb_ctx *ctx)
         table[s] = make_uint4((uint32_t)ghash[g], (uint32_t)(ghash[g] >> 32), glen[g], g);
     }
     if (lens.empty()) lens.push_back(0);
+    // tables at the head of the arena, the per-call scratch (sized by the last burst) behind them
+    const size_t tab_bytes = arena_align(gprefix.size()) + arena_align(wgroup.size() * 4) + arena_align(wminrev.size() * 8) +
+                             arena_align(lens.size() * 4) + arena_align(table.size() * 16);
+    KB_TRY(arena_reserve(ctx, T, tab_bytes + T.scr_bytes + 4096));
+    size_t cur = 0;
+    arena_view(T, cur, T.gprefix, gprefix.size());
+    arena_view(T, cur, T.wgroup, wgroup.size() * 4);
+    arena_view(T, cur, T.wminrev, wminrev.size() * 8);
+    arena_view(T, cur, T.lens, lens.size() * 4);
+    arena_view(T, cur, T.table, table.size() * 16);
+    if (cur != T.tab_end) T.scr_sig = 0;  // the scratch behind the tables moves
+    T.tab_end = cur;
     KB_TRY(upload(ctx, T.gprefix, gprefix.data(), gprefix.size()));
     KB_TRY(upload(ctx, T.wgroup, wgroup.data(), wgroup.size() * 4));
     KB_TRY(upload(ctx, T.wminrev, wminrev.data(), wminrev.size() * 8));
@@ -815,10 +867,7 @@ void watch_tables_free(kb_ctx *ctx)
 {
     if (!ctx->wt) return;
     WatchTablesDev &T = *ctx->wt;
-    DBuf *all[] = {&T.gprefix, &T.wgroup, &T.wminrev, &T.lens, &T.table, &T.gstate, &T.galloc, &T.lists, &T.ematch, &T.seg,
-                   &T.seg_sorted, &T.bitmaps, &T.pm, &T.wstate, &T.wstart, &T.total};
-    for (DBuf *b : all)
-        if (b->p) cudaFree(b->p);
+    if (T.arena.p) cudaFree(T.arena.p);  // every other buffer is a view into it
     delete ctx->wt;
     ctx->wt = nullptr;
     if (ctx->ev_scratch) {
@@ -943,24 +992,29 @@ static int match_locked(kb_ctx *ctx, const kb_events_dev *d, int out_mode, kb_re
     const uint32_t chunks_per_group = (bm_words + FAN_THREADS - 1) / FAN_THREADS;
     const size_t gstate_words = (size_t)2 * (G + 1) + FC_WORDS;
     const size_t bitmap_bytes = std::max<size_t>((size_t)max_large * bm_words * 4, 16);
-    // growing a buffer frees the old one: the "clean" state of the scratch is lost with it
-    auto ensure = [&](DBuf &b, size_t bytes) -> int {
-        const void *before = b.p;
-        KB_TRY(dbuf_ensure(ctx, b, bytes));
-        if (b.p != before) T.scratch_clean = false;
-        return KB_OK;
-    };
-    KB_TRY(ensure(T.gstate, gstate_words * 4));
-    KB_TRY(ensure(T.galloc, (size_t)(G + 1) * 8));
-    KB_TRY(ensure(T.bitmaps, bitmap_bytes));
-    KB_TRY(dbuf_ensure(ctx, T.lists, (size_t)(G + max_large + 2) * 4));
-    KB_TRY(dbuf_ensure(ctx, T.ematch, seg_cap * 4));
-    KB_TRY(dbuf_ensure(ctx, T.seg, seg_cap * 4));
-    KB_TRY(dbuf_ensure(ctx, T.seg_sorted, seg_cap * 4));
-    KB_TRY(dbuf_ensure(ctx, T.pm, std::max<size_t>((size_t)E * 8, 16)));
-    KB_TRY(dbuf_ensure(ctx, T.wstate, (size_t)(W + 1) * 16));
-    KB_TRY(dbuf_ensure(ctx, T.wstart, (size_t)(W + 2) * 8));
-    KB_TRY(dbuf_ensure(ctx, T.total, 16));
+    // per-call scratch behind the tables (one arena, see WatchTablesDev); a layout change voids the "clean" state
+    const size_t sizes[11] = {gstate_words * 4, (size_t)(G + 1) * 8, bitmap_bytes, (size_t)(G + max_large + 2) * 4, seg_cap * 4,
+                              seg_cap * 4, seg_cap * 4, std::max<size_t>((size_t)E * 8, 16), (size_t)(W + 1) * 16,
+                              (size_t)(W + 2) * 8, 16};
+    size_t scr = 0, sig = 1469598103934665603ull;
+    for (size_t x : sizes) {
+        scr += arena_align(std::max<size_t>(x, 16));
+        sig = (sig ^ x) * 1099511628211ull;
+    }
+    if (T.tab_end + scr > T.arena.cap) {
+        T.scr_bytes = scr;
+        KB_TRY(arena_reserve(ctx, T, T.tab_end + scr + 4096));
+        KB_TRY(rebuild_tables(ctx));  // the tables moved with the arena
+    }
+    T.scr_bytes = std::max(T.scr_bytes, scr);
+    if (sig != T.scr_sig) T.scratch_clean = false;
+    T.scr_sig = sig;
+    {
+        size_t cur = T.tab_end;
+        DBuf *views[11] = {&T.gstate, &T.galloc, &T.bitmaps, &T.lists, &T.ematch, &T.seg, &T.seg_sorted, &T.pm, &T.wstate,
+                           &T.wstart, &T.total};
+        for (int i = 0; i < 11; i++) arena_view(T, cur, *views[i], sizes[i]);
+    }
 
     EvDev ev;
     ev.keys = (const uint4 *)d->keys.p;
