@@ -706,7 +706,11 @@ int arena_reserve(kb_ctx *ctx, WatchTablesDev &T, size_t need)
     cudaDeviceGetAttribute(&max_win, cudaDevAttrMaxAccessPolicyWindowSize, ctx->device);
     cudaDeviceGetAttribute(&persist_max, cudaDevAttrMaxPersistingL2CacheSize, ctx->device);
     const size_t setaside = std::min<size_t>((size_t)persist_max, (size_t)32 << 20);
-    if (max_win > 0 && setaside > 0) {
+    // Off unless KB_L2_PERSIST=1.  Measured (profiles/r02_l2_persist_ab.txt): with a 32 MB set-aside the fan-out itself does
+    // not get faster inside a step (231 -> 290 us) and the scan context's gather loses the L2 it uses as a write buffer
+    // (185 -> 250 us): 0.327 -> 0.381 ms per step.
+    static const bool l2_persist = getenv("KB_L2_PERSIST") && atoi(getenv("KB_L2_PERSIST")) == 1;
+    if (max_win > 0 && setaside > 0 && l2_persist) {
         cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, setaside);  // device-wide; the same value from every context
         attr.accessPolicyWindow.base_ptr = T.arena.p;
         attr.accessPolicyWindow.num_bytes = std::min<size_t>(T.arena.cap, (size_t)max_win);
