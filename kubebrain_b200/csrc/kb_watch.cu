@@ -89,7 +89,7 @@ struct TabDev {
 // control words of one match (gstate: [gcnt G+1][gfill G+1][ctl 16])
 enum { FC_NONMONO = 0, FC_CURSOR = 1, FC_NLARGE = 2, FC_NMED = 3, FC_ARRIVE = 4, FC_GEN = 5, FC_DONE = 6, FC_ABORT = 7, FC_WORDS = 16 };
 constexpr unsigned long long FAN_UNSET = ~0ull, FAN_BUSY = ~0ull - 1;
-constexpr uint32_t FAN_THREADS = 256;  // one CTA per SM, < 15 k registers, < 2 KiB of shared memory (see fan_grid_sync)
+constexpr uint32_t FAN_THREADS = 384;  // one CTA per SM, < 28 k registers (fits beside the decode CTA or the two gather CTAs), < 2 KiB of shared memory (see fan_grid_sync)
 constexpr uint32_t BM_WORDS = 256;   // 8192 event indices per shared-memory window (1 KiB).  The scan context's two gather
                                      // CTAs leave ~6 KiB of an SM's shared memory (every resident CTA also costs 1 KiB of
                                      // reserve): with a 4 KiB window here NOTHING else of the scan context -- not even the
@@ -111,7 +111,7 @@ struct FanScratch {
 __device__ __forceinline__ uint32_t ldcg32(const uint32_t *p) { return __ldcg(p); }
 __device__ __forceinline__ uint64_t ldcg64(const uint64_t *p) { return __ldcg((const unsigned long long *)p); }
 
-// Grid barrier.  The kernel is launched with ONE CTA per SM of modest size (256 threads, < 15 k registers, < 2 KiB of
+// Grid barrier.  The kernel is launched with ONE CTA per SM of modest size (384 threads, < 28 k registers, < 2 KiB of
 // shared memory), which fits beside whatever the scan context has resident, so every CTA gets an SM while the others
 // spin; nothing this kernel waits for depends on work queued behind it.  (A cooperative launch would guarantee the same
 // but is gang-scheduled: measured, it waited for the scan context's persistent kernels to drain -- 247 us in a step
