@@ -105,6 +105,8 @@ struct FanScratch {
     uint32_t *wcnt, *wsrc, *wn, *wlo;
     uint64_t *wstart, *total;
     uint32_t big_t, max_large, bm_words, chunks_per_group, gen_base;
+    uint64_t *o_start, *h_start;   // the output buffer's offsets and their (pinned, device-visible) host copy
+    uint64_t *h_pub, epoch;        // mapped flag: [0] epoch, [1] total deliveries, [2] a barrier timed out
 };
 
 // scratch written by one CTA and read by another inside the same launch goes around the (non-coherent) L1
@@ -558,10 +560,14 @@ __device__ __forceinline__ void d_finish(const TabDev &tb, const FanScratch &sc,
     uint64_t at = ws[wid] + inc - sum;
     for (uint32_t w = a; w < b; w++) {
         sc.wstart[w] = at;
+        sc.o_start[w] = at;
+        sc.h_start[w] = at;
         at += ldcg32(&sc.wcnt[w]);
     }
     if (threadIdx.x == 0) {
         sc.wstart[W] = ws[32];
+        sc.o_start[W] = ws[32];
+        sc.h_start[W] = ws[32];
         sc.total[0] = ws[32];
         // k_expand_write picks its path from this copy; bit 32 = a grid barrier timed out (the answer is void)
         sc.total[1] = (uint64_t)ldcg32(&sc.ctl[FC_NONMONO]) | ((uint64_t)ldcg32(&sc.ctl[FC_ABORT]) << 32);
@@ -573,7 +579,18 @@ __device__ __forceinline__ void d_finish(const TabDev &tb, const FanScratch &sc,
     for (uint32_t i = threadIdx.x; i < 2 * (G + 1); i += T) sc.gcnt[i] = 0;  // gcnt | gfill are contiguous
     for (uint32_t i = threadIdx.x; i < G; i += T) sc.galloc[i] = FAN_UNSET;
     for (uint64_t i = threadIdx.x; i < (uint64_t)nlarge * sc.bm_words; i += T) sc.bitmaps[i] = 0;
+    const uint32_t aborted = ldcg32(&sc.ctl[FC_ABORT]);
+    __syncthreads();
     if (threadIdx.x < FC_WORDS && threadIdx.x != FC_GEN) sc.ctl[threadIdx.x] = 0;
+    // the offsets in host memory, then the flag the host polls
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        sc.h_pub[1] = sc.total[0];
+        sc.h_pub[2] = aborted;
+        __threadfence_system();
+        *(volatile uint64_t *)sc.h_pub = sc.epoch;
+    }
 }
 
 __global__ void __launch_bounds__(FAN_THREADS, 1)
@@ -1076,26 +1093,10 @@ static int match_locked(kb_ctx *ctx, const kb_events_dev *d, int out_mode, kb_re
     }
     T.scratch_clean = false;  // until this call has been enqueued completely
     const uint64_t ev_bytes = (uint64_t)E * (d->stride + 4);
-    if (E && W) {
-        if (!T.fan_grid) {
-            int per_sm = 0, sms = 0;
-            KB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fanout, (int)FAN_THREADS, 0));
-            KB_CUDA(ctx, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
-            if (per_sm < 1) return kb_fail(ctx, KB_ECUDA, "k_fanout does not fit on an SM");
-            T.fan_grid = sms;  // one CTA per SM: all of them are resident together (see fan_grid_sync)
-        }
-        sc.gen_base = T.fan_gen;
-        KB_LAUNCH(ctx, "k_fanout", ev_bytes + (uint64_t)E * NL * 12 + (uint64_t)E * 16 + (uint64_t)W * 44,
-                  (k_fanout<<<(unsigned)T.fan_grid, FAN_THREADS, 0, ctx->stream>>>(ev, tb, sc)));
-        T.fan_gen += 3;  // three grid barriers per launch
-    } else {
-        // no events or no watchers: every list is empty
-        KB_CUDA(ctx, cudaMemsetAsync(T.wstart.p, 0, (size_t)(W + 2) * 8, ctx->stream));
-        KB_CUDA(ctx, cudaMemsetAsync(T.total.p, 0, 16, ctx->stream));
-    }
     // Output [start (W+1) x u64][event_idx D x u32].  D is only known on the device; the buffer is sized from the
     // previous call's D (+25 %) and the write kernel refuses to run when it would not fit, so the steady state needs
-    // no round trip before the write.
+    // no round trip before the write.  k_fanout's last CTA writes the offsets straight into the output buffer and into
+    // the (pinned, device-visible) host copy and raises the epoch flag: the host returns on it.
     KB_TRY(hbuf_ensure(ctx, ctx->h_stage2, 64));
     if (!ctx->h_wpub) {
         KB_CUDA(ctx, cudaHostAlloc((void **)&ctx->h_wpub, 64, cudaHostAllocMapped));
@@ -1106,68 +1107,80 @@ static int match_locked(kb_ctx *ctx, const kb_events_dev *d, int out_mode, kb_re
     DBuf d_out;
     HBuf h_out;
     int rc = KB_OK;
-    for (int attempt = 0; attempt < 2; attempt++) {
-        const size_t out_bytes = (size_t)(W + 1) * 8 + cap * 4 + 16;
-        KB_TRY(pool_get_dev(ctx, out_bytes, &d_out));
-        uint64_t *o_start = (uint64_t *)d_out.p;
-        uint32_t *o_idx = (uint32_t *)(o_start + W + 1);
-        cudaMemcpyAsync(o_start, sc.wstart, (size_t)(W + 1) * 8, cudaMemcpyDeviceToDevice, ctx->stream);
-        uint64_t wepoch = 0;
-        if (out_mode != KB_OUT_HOST) {
-            if (!h_out.p) KB_TRY(pool_get_host(ctx, (size_t)(W + 1) * 8 + 16, &h_out));
-            cudaMemcpyAsync(h_out.p, sc.wstart, (size_t)(W + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream);
-            wepoch = ++ctx->wpub_epoch;
-            k_publish_total<<<1, 32, 0, ctx->stream>>>(sc.total, ctx->h_wpub, wepoch);
-        }
-        if (W && E) {
-            const unsigned wgrid = (unsigned)std::max<uint64_t>(std::min<uint64_t>((cap + 255) / 256, 148 * 16),
-                                                                std::min<uint64_t>(((uint64_t)W * 32 + 255) / 256, 148 * 16));
-            KB_LAUNCH(ctx, "k_expand_write", cap * 8,
-                      (k_expand_write<<<wgrid, 256, 0, ctx->stream>>>(W, tb.wminrev, sc.wsrc, sc.wn, sc.wlo, sc.sorted, sc.pm,
-                                                                     sc.total, sc.wstart, cap, o_idx)));
-        }
-        cudaError_t e0 = cudaSuccess;
-        if (out_mode != KB_OUT_HOST) {
-            // device-resident result: the offsets have travelled and the total is published in front of the write
-            // kernel; the host returns on the flag while the delivery lists are still being written (stream order)
-            kb_seg(ctx, "host:match_launch", tseg);
-            rc = wpub_wait(ctx, wepoch);
-            kb_seg(ctx, "host:match_sync", tseg);
-            if (rc != KB_OK) {
+    KB_TRY(pool_get_dev(ctx, (size_t)(W + 1) * 8 + cap * 4 + 16, &d_out));
+    rc = pool_get_host(ctx, (size_t)(W + 1) * 8 + 16, &h_out);
+    if (rc != KB_OK) {
+        pool_put_dev(ctx, d_out);
+        return rc;
+    }
+    const uint64_t wepoch = ++ctx->wpub_epoch;
+    sc.o_start = (uint64_t *)d_out.p;
+    sc.h_start = (uint64_t *)h_out.p;
+    sc.h_pub = ctx->h_wpub;
+    sc.epoch = wepoch;
+    const bool run = E && W;
+    if (run) {
+        if (!T.fan_grid) {
+            int per_sm = 0, sms = 0;
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fanout, (int)FAN_THREADS, 0);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+            if (per_sm < 1 || sms < 1) {
                 pool_put_dev(ctx, d_out);
                 pool_put_host(ctx, h_out);
-                return rc;
+                return kb_fail(ctx, KB_ECUDA, "k_fanout does not fit on an SM");
             }
-            D = ctx->h_wpub[1];
-            if (ctx->h_wpub[2]) rc = kb_fail(ctx, KB_ECUDA, "watch match: a grid barrier timed out");
-            if (rc != KB_OK) {
-                pool_put_dev(ctx, d_out);
-                pool_put_host(ctx, h_out);
-                return rc;
-            }
-        } else {
-            KB_CUDA(ctx, cudaMemcpyAsync(ctx->h_stage2.p, sc.total, 16, cudaMemcpyDeviceToHost, ctx->stream));
-            kb_seg(ctx, "host:match_launch", tseg);
-            e0 = cudaStreamSynchronize(ctx->stream);
-            kb_seg(ctx, "host:match_sync", tseg);
-            if (e0 != cudaSuccess) {
-                pool_put_dev(ctx, d_out);
-                return kb_cuda_fail(ctx, e0, "watch match");
-            }
-            D = *(uint64_t *)ctx->h_stage2.p;
-            if (((uint64_t *)ctx->h_stage2.p)[1] >> 32) {
-                pool_put_dev(ctx, d_out);
-                return kb_fail(ctx, KB_ECUDA, "watch match: a grid barrier timed out");
-            }
+            T.fan_grid = sms;  // one CTA per SM: all of them are resident together (see fan_grid_sync)
         }
-        T.d_hint = D;
-        if (D <= cap) break;
-        pool_put_dev(ctx, d_out);  // first call or a burst larger than the hint: grow and write again
+        sc.gen_base = T.fan_gen;
+        KB_LAUNCH(ctx, "k_fanout", ev_bytes + (uint64_t)E * NL * 12 + (uint64_t)E * 16 + (uint64_t)W * 44,
+                  (k_fanout<<<(unsigned)T.fan_grid, FAN_THREADS, 0, ctx->stream>>>(ev, tb, sc)));
+        T.fan_gen += 3;  // three grid barriers per launch
+    } else {
+        // no events or no watchers: every list is empty
+        cudaMemsetAsync(T.wstart.p, 0, (size_t)(W + 2) * 8, ctx->stream);
+        cudaMemsetAsync(T.total.p, 0, 16, ctx->stream);
+        cudaMemsetAsync(d_out.p, 0, (size_t)(W + 1) * 8, ctx->stream);
+        memset(h_out.p, 0, (size_t)(W + 1) * 8);
+        k_publish_total<<<1, 32, 0, ctx->stream>>>(sc.total, ctx->h_wpub, wepoch);
+    }
+    auto launch_write = [&](uint32_t *o_idx, uint64_t capacity) {
+        const unsigned wgrid = (unsigned)std::max<uint64_t>(std::min<uint64_t>((capacity + 255) / 256, 148 * 16),
+                                                            std::min<uint64_t>(((uint64_t)W * 32 + 255) / 256, 148 * 16));
+        KB_LAUNCH(ctx, "k_expand_write", capacity * 8,
+                  (k_expand_write<<<wgrid, 256, 0, ctx->stream>>>(W, tb.wminrev, sc.wsrc, sc.wn, sc.wlo, sc.sorted, sc.pm, sc.total,
+                                                                 sc.wstart, capacity, o_idx)));
+    };
+    if (run) launch_write((uint32_t *)((uint64_t *)d_out.p + W + 1), cap);
+    // the total (and the offsets) are published in front of the write kernel: a device-resident answer returns on the flag
+    // while the delivery lists are still being written (they are valid in stream order)
+    kb_seg(ctx, "host:match_launch", tseg);
+    rc = wpub_wait(ctx, wepoch);
+    kb_seg(ctx, "host:match_sync", tseg);
+    if (rc == KB_OK && ctx->h_wpub[2]) rc = kb_fail(ctx, KB_ECUDA, "watch match: a grid barrier timed out");
+    if (rc != KB_OK) {
+        pool_put_dev(ctx, d_out);
+        pool_put_host(ctx, h_out);
+        return rc;
+    }
+    D = ctx->h_wpub[1];
+    T.d_hint = D;
+    if (D > cap) {
+        // first call or a burst larger than the hint: a buffer that fits, the offsets again, and the write once more
+        pool_put_dev(ctx, d_out);
         d_out = DBuf();
         cap = D;
+        rc = pool_get_dev(ctx, (size_t)(W + 1) * 8 + cap * 4 + 16, &d_out);
+        if (rc != KB_OK) {
+            pool_put_host(ctx, h_out);
+            return rc;
+        }
+        cudaMemcpyAsync(d_out.p, sc.wstart, (size_t)(W + 1) * 8, cudaMemcpyDeviceToDevice, ctx->stream);
+        launch_write((uint32_t *)((uint64_t *)d_out.p + W + 1), cap);
     }
-    T.scratch_clean = true;  // everything was enqueued: k_fanout restores the scratch before it ends
+    T.scratch_clean = run;  // everything was enqueued: k_fanout restores the scratch before it ends
     if (out_mode == KB_OUT_HOST) {
+        pool_put_host(ctx, h_out);
+        h_out = HBuf();
         rc = pool_get_host(ctx, (size_t)(W + 1) * 8 + D * 4 + 16, &h_out);
         if (rc == KB_OK)
             cudaMemcpyAsync(h_out.p, d_out.p, (size_t)(W + 1) * 8 + D * 4, cudaMemcpyDeviceToHost, ctx->stream);
