@@ -825,11 +825,20 @@ def fanout_alone(weng, evh, wl, peak: float, reps: int = 30):
     b.record(ws)
     torch.cuda.synchronize()
     ms = a.elapsed_time(b) / reps
+    # where the time goes: per-kernel events and the phase spans k_fanout's first CTA stamps (a separate, untimed pass)
+    weng.prof_reset()
+    weng.prof_enable(1)
+    for _ in range(10):
+        weng.watch_match_dev(evh, KB_OUT_DEVICE).close()
+    weng.prof_enable(0)
+    parts = {p["name"]: round(1e3 * p["total_ms"] / p["launches"], 1) for p in weng.prof_read()
+             if p["launches"] and (p["name"].startswith("fan:") or p["name"] in ("k_fanout", "k_expand_write"))}
+    weng.prof_reset()
     E, W = int(wl["events"].n), int(wl["watchers"].n)
     alg = E * (LU + 12) + W * 44 + d * 8
     return {"workload": "configs[2] alone: 100k-event burst x 10k watchers, device-resident slab and answer",
             "us_per_burst": ms * 1e3, "events_per_s": E / (ms / 1e3), "deliveries_per_s": d / (ms / 1e3),
-            "launches_per_burst": (weng.launch_count() - l0) / reps,
+            "launches_per_burst": (weng.launch_count() - l0) / reps, "parts_us": parts,
             "roofline": {"bound": "hbm", "achieved": alg / 1e9 / (ms / 1e3), "peak": peak, "unit": "GB/s",
                          "frac": alg / 1e9 / (ms / 1e3) / peak, "alg_bytes": alg,
                          "note": "latency bound: 41 MB of algorithmic traffic per burst"}}

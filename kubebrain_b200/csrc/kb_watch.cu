@@ -106,7 +106,7 @@ struct FanScratch {
     uint64_t *wstart, *total;
     uint32_t big_t, max_large, bm_words, chunks_per_group, gen_base;
     uint64_t *o_start, *h_start;   // the output buffer's offsets and their (pinned, device-visible) host copy
-    uint64_t *h_pub, epoch;        // mapped flag: [0] epoch, [1] total deliveries, [2] a barrier timed out
+    uint64_t *h_pub, epoch;        // mapped flag: [0] epoch, [1] total deliveries, [2] a barrier timed out; [3..7] phase ends (ns)
 };
 
 // scratch written by one CTA and read by another inside the same launch goes around the (non-coherent) L1
@@ -593,9 +593,22 @@ __device__ __forceinline__ void d_finish(const TabDev &tb, const FanScratch &sc,
     }
 }
 
+__device__ __forceinline__ uint64_t fan_now_ns();
+
+__device__ __forceinline__ uint64_t fan_now_ns()
+{
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
 __global__ void __launch_bounds__(FAN_THREADS, 1)
 k_fanout(EvDev ev, TabDev tb, FanScratch sc)
 {
+    // phase timestamps of CTA 0 (profiling: kb_prof_read reports them as fan:P1 .. fan:finish when profiling is on)
+    const bool stamp = blockIdx.x == 0 && threadIdx.x == 0;
+    const uint64_t t_begin = stamp ? fan_now_ns() : 0;
+    uint64_t t_p[4] = {0, 0, 0, 0};
     __shared__ uint32_t bm[BM_WORDS];
     __shared__ uint32_t wsum[33];
     __shared__ uint32_t red[2];
@@ -612,16 +625,27 @@ k_fanout(EvDev ev, TabDev tb, FanScratch sc)
             d_match_count(ev, tb, sc.ematch, sc.gcnt, vb - pm_blocks);
     }
     fan_grid_sync(sc.ctl, sc.gen_base + 1);
+    if (stamp) t_p[0] = fan_now_ns();
     // P2
     for (uint32_t vb = blockIdx.x; vb < ev_blocks; vb += gridDim.x) d_scatter(sc, ev.n, tb.n_lens, vb);
     fan_grid_sync(sc.ctl, sc.gen_base + 2);
+    if (stamp) t_p[1] = fan_now_ns();
     // P3
     d_sort_medium(sc, bm, wsum, red);
     d_expand_large(sc, wsum, red);
     fan_grid_sync(sc.ctl, sc.gen_base + 3);
+    if (stamp) t_p[2] = fan_now_ns();
     // P4
     const bool mono = ldcg32(&sc.ctl[FC_NONMONO]) == 0;
     d_watcher_count(tb, sc, mono);
+    if (stamp) {
+        t_p[3] = fan_now_ns();
+        sc.h_pub[3] = t_p[0] - t_begin;   // P1 + barrier
+        sc.h_pub[4] = t_p[1] - t_p[0];    // P2 + barrier
+        sc.h_pub[5] = t_p[2] - t_p[1];    // P3 + barrier
+        sc.h_pub[6] = t_p[3] - t_p[2];    // P4 of this CTA
+        sc.h_pub[7] = t_begin;            // start: the finishing CTA turns it into the kernel's span
+    }
     // P5: the last CTA to get here finishes alone; the end of the kernel is the barrier for what follows
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -1164,6 +1188,14 @@ static int match_locked(kb_ctx *ctx, const kb_events_dev *d, int out_mode, kb_re
     }
     D = ctx->h_wpub[1];
     T.d_hint = D;
+    if (ctx->prof_on && run) {  // phase spans of CTA 0 (ns -> ms), as pseudo kernels "fan:*"
+        static const char *names[4] = {"fan:P1_match", "fan:P2_scatter", "fan:P3_sort", "fan:P4_watchers"};
+        for (int i = 0; i < 4; i++) {
+            ProfEntry &pe = ctx->prof[prof_index(ctx, names[i])];
+            pe.launches++;
+            pe.ms += (double)ctx->h_wpub[3 + i] * 1e-6;
+        }
+    }
     if (D > cap) {
         // first call or a burst larger than the hint: a buffer that fits, the offsets again, and the write once more
         pool_put_dev(ctx, d_out);
