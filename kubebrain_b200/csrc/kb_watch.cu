@@ -53,6 +53,7 @@ struct WatchTablesDev {
     bool scratch_clean = false;   // the previous k_fanout left gstate / galloc / bitmaps in their initial state
     uint32_t scratch_groups = 0, scratch_large = 0, scratch_bm_words = 0;
     uint32_t fan_gen = 0;         // value of the grid-barrier generation word after the last launch
+    uint32_t fan_set = 0;         // which of the two sets of group state the next k_fanout uses
     int fan_grid = 0;             // co-resident CTAs of k_fanout on this device (0: not queried yet)
 };
 
@@ -105,6 +106,10 @@ struct FanScratch {
     uint32_t *wcnt, *wsrc, *wn, *wlo;
     uint64_t *wstart, *total;
     uint32_t big_t, max_large, bm_words, chunks_per_group, gen_base;
+    // group state is double buffered: this call uses gcnt / gfill / galloc / bitmaps and clears the OTHER set (used by the
+    // previous call) in its first phase, fully parallel; *nlarge_w: bitmap slots this call used, *nlarge_r: the previous one
+    uint32_t *z_gcnt, *z_bitmaps, *nlarge_w, *nlarge_r;
+    unsigned long long *z_galloc;
     uint64_t *o_start, *h_start;   // the output buffer's offsets and their (pinned, device-visible) host copy
     uint64_t *h_pub, epoch;        // mapped flag: [0] epoch, [1] total deliveries, [2] a barrier timed out; [3..7] phase ends (ns)
 };
@@ -532,24 +537,23 @@ __device__ __forceinline__ void d_watcher_count(const TabDev &tb, const FanScrat
 // ---- P5 (one CTA): exclusive prefix of the per-watcher delivery counts; scratch back to its initial state
 __device__ __forceinline__ void d_finish(const TabDev &tb, const FanScratch &sc, uint64_t *ws /* 33 */)
 {
-    const uint32_t W = tb.n_ids, T = blockDim.x;
-    const uint32_t per = (W + T - 1) / T;
-    const uint32_t a = min(W, threadIdx.x * per), b = min(W, a + per);
+    // Exclusive prefix of the per-watcher counts by ONE CTA with coalesced accesses: every warp owns a contiguous chunk
+    // of watchers and walks it 32 at a time (first pass: chunk totals; second pass: warp scans with the running carry).
+    // The offsets go to the device scratch, to the output buffer and -- 256 contiguous bytes per warp store -- to the
+    // pinned host copy.  (The first version gave each thread a contiguous run: 8-byte PCIe writes 216 bytes apart; with
+    // the scratch zeroing it made this tail ~50 us of a 110 us kernel.)
+    const uint32_t W = tb.n_ids, lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const uint32_t per = ((W + nw - 1) / nw + 31) & ~31u;  // watchers per warp, a multiple of 32
+    const uint32_t a = min(W, wid * per), b = min(W, a + per);
     uint64_t sum = 0;
-    for (uint32_t w = a; w < b; w++) sum += ldcg32(&sc.wcnt[w]);
-    // block exclusive scan of `sum`
-    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    uint64_t inc = sum;
+    for (uint32_t w = a + lane; w < b; w += 32) sum += ldcg32(&sc.wcnt[w]);
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        uint64_t o = __shfl_up_sync(FULL, inc, d);
-        if (lane >= (unsigned)d) inc += o;
-    }
-    if (lane == 31) ws[wid] = inc;
+    for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(FULL, sum, d);
+    if (lane == 0) ws[wid] = sum;
     __syncthreads();
     if (threadIdx.x == 0) {
         uint64_t run = 0;
-        for (uint32_t k = 0; k < (T >> 5); k++) {
+        for (uint32_t k = 0; k < nw; k++) {
             uint64_t x = ws[k];
             ws[k] = run;
             run += x;
@@ -557,36 +561,43 @@ __device__ __forceinline__ void d_finish(const TabDev &tb, const FanScratch &sc,
         ws[32] = run;
     }
     __syncthreads();
-    uint64_t at = ws[wid] + inc - sum;
-    for (uint32_t w = a; w < b; w++) {
-        sc.wstart[w] = at;
-        sc.o_start[w] = at;
-        sc.h_start[w] = at;
-        at += ldcg32(&sc.wcnt[w]);
+    uint64_t carry = ws[wid];
+    for (uint32_t w0 = a; w0 < b; w0 += 32) {
+        const uint32_t w = w0 + lane;
+        const uint64_t c = w < b ? ldcg32(&sc.wcnt[w]) : 0;
+        uint64_t inc = c;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint64_t o = __shfl_up_sync(FULL, inc, d);
+            if (lane >= (unsigned)d) inc += o;
+        }
+        if (w < b) {
+            const uint64_t at = carry + inc - c;
+            sc.wstart[w] = at;
+            sc.o_start[w] = at;
+            sc.h_start[w] = at;
+        }
+        carry += __shfl_sync(FULL, inc, 31);
     }
+    const uint32_t aborted = ldcg32(&sc.ctl[FC_ABORT]);
     if (threadIdx.x == 0) {
         sc.wstart[W] = ws[32];
         sc.o_start[W] = ws[32];
         sc.h_start[W] = ws[32];
         sc.total[0] = ws[32];
         // k_expand_write picks its path from this copy; bit 32 = a grid barrier timed out (the answer is void)
-        sc.total[1] = (uint64_t)ldcg32(&sc.ctl[FC_NONMONO]) | ((uint64_t)ldcg32(&sc.ctl[FC_ABORT]) << 32);
+        sc.total[1] = (uint64_t)ldcg32(&sc.ctl[FC_NONMONO]) | ((uint64_t)aborted << 32);
+        *sc.nlarge_w = min(ldcg32(&sc.ctl[FC_NLARGE]), sc.max_large);  // bitmap slots the NEXT call has to clear
     }
-    // leave the scratch as the next call expects it (every other CTA has finished reading it)
-    const uint32_t G = tb.n_groups;
-    const uint32_t nlarge = min(ldcg32(&sc.ctl[FC_NLARGE]), sc.max_large);
     __syncthreads();
-    for (uint32_t i = threadIdx.x; i < 2 * (G + 1); i += T) sc.gcnt[i] = 0;  // gcnt | gfill are contiguous
-    for (uint32_t i = threadIdx.x; i < G; i += T) sc.galloc[i] = FAN_UNSET;
-    for (uint64_t i = threadIdx.x; i < (uint64_t)nlarge * sc.bm_words; i += T) sc.bitmaps[i] = 0;
-    const uint32_t aborted = ldcg32(&sc.ctl[FC_ABORT]);
-    __syncthreads();
+    // the per-call control words back to zero (the group state itself is double buffered: the next call clears this set
+    // in its first phase, see k_fanout)
     if (threadIdx.x < FC_WORDS && threadIdx.x != FC_GEN) sc.ctl[threadIdx.x] = 0;
     // the offsets in host memory, then the flag the host polls
     __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) {
-        sc.h_pub[1] = sc.total[0];
+        sc.h_pub[1] = ws[32];
         sc.h_pub[2] = aborted;
         __threadfence_system();
         *(volatile uint64_t *)sc.h_pub = sc.epoch;
@@ -618,6 +629,14 @@ k_fanout(EvDev ev, TabDev tb, FanScratch sc)
     const uint32_t pm_blocks = (ev.nb * 32 + FAN_THREADS - 1) / FAN_THREADS;
     const uint32_t ev_blocks = tb.n_groups ? (ev.n + FAN_THREADS - 1) / FAN_THREADS : 0;
     const uint32_t ev_blocks3 = (ev_blocks + FAN_EPT - 1) / FAN_EPT;  // P1: a virtual block covers FAN_EPT x 256 events
+    {   // the other set of group state (the previous call's) back to its initial state
+        const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (uint64_t)gridDim.x * blockDim.x;
+        const uint32_t G = tb.n_groups;
+        for (uint64_t i = tid; i < 2ull * (G + 1); i += nth) sc.z_gcnt[i] = 0;  // gcnt | gfill are contiguous
+        for (uint64_t i = tid; i < G; i += nth) sc.z_galloc[i] = FAN_UNSET;
+        const uint64_t zb = (uint64_t)min(ldcg32(sc.nlarge_r), sc.max_large) * sc.bm_words;
+        for (uint64_t i = tid; i < zb; i += nth) sc.z_bitmaps[i] = 0;
+    }
     for (uint32_t vb = blockIdx.x; vb < pm_blocks + ev_blocks3; vb += gridDim.x) {
         if (vb < pm_blocks)
             d_batch_pm(ev, sc.pm, &sc.ctl[FC_NONMONO], vb);
@@ -1035,10 +1054,11 @@ static int match_locked(kb_ctx *ctx, const kb_events_dev *d, int out_mode, kb_re
     const uint32_t max_large = (uint32_t)(seg_cap / big_t) + 1;
     const uint32_t bm_words = (E + 31) / 32;
     const uint32_t chunks_per_group = (bm_words + FAN_THREADS - 1) / FAN_THREADS;
-    const size_t gstate_words = (size_t)2 * (G + 1) + FC_WORDS;
+    const size_t gstate_words = (size_t)4 * (G + 1) + FC_WORDS + 4;  // two sets of gcnt | gfill, control words, nlarge[2]
     const size_t bitmap_bytes = std::max<size_t>((size_t)max_large * bm_words * 4, 16);
     // per-call scratch behind the tables (one arena, see WatchTablesDev); a layout change voids the "clean" state
-    const size_t sizes[11] = {gstate_words * 4, (size_t)(G + 1) * 8, bitmap_bytes, (size_t)(G + max_large + 2) * 4, seg_cap * 4,
+    // (group state -- gcnt | gfill, galloc, bitmaps -- twice: the sets alternate between calls)
+    const size_t sizes[11] = {gstate_words * 4, (size_t)2 * (G + 1) * 8, 2 * bitmap_bytes, (size_t)(G + max_large + 2) * 4, seg_cap * 4,
                               seg_cap * 4, seg_cap * 4, std::max<size_t>((size_t)E * 8, 16), (size_t)(W + 1) * 16,
                               (size_t)(W + 2) * 8, 16};
     size_t scr = 0, sig = 1469598103934665603ull;
@@ -1082,16 +1102,23 @@ static int match_locked(kb_ctx *ctx, const kb_events_dev *d, int out_mode, kb_re
     tb.max_len = T.max_len;
     tb.pstride16 = T.pstride16;
     FanScratch sc;
-    sc.gcnt = (uint32_t *)T.gstate.p;
+    const uint32_t set = T.fan_set & 1;
+    uint32_t *gs = (uint32_t *)T.gstate.p;
+    sc.gcnt = gs + (size_t)set * 2 * (G + 1);
     sc.gfill = sc.gcnt + (G + 1);
-    sc.ctl = sc.gcnt + 2 * (G + 1);
-    sc.galloc = (unsigned long long *)T.galloc.p;
+    sc.z_gcnt = gs + (size_t)(set ^ 1) * 2 * (G + 1);
+    sc.ctl = gs + (size_t)4 * (G + 1);
+    sc.nlarge_w = sc.ctl + FC_WORDS + set;
+    sc.nlarge_r = sc.ctl + FC_WORDS + (set ^ 1);
+    sc.galloc = (unsigned long long *)T.galloc.p + (size_t)set * (G + 1);
+    sc.z_galloc = (unsigned long long *)T.galloc.p + (size_t)(set ^ 1) * (G + 1);
     sc.med_list = (uint32_t *)T.lists.p;
     sc.large_list = sc.med_list + G + 1;
     sc.ematch = (uint32_t *)T.ematch.p;
     sc.seg = (uint32_t *)T.seg.p;
     sc.sorted = (uint32_t *)T.seg_sorted.p;
-    sc.bitmaps = (uint32_t *)T.bitmaps.p;
+    sc.bitmaps = (uint32_t *)T.bitmaps.p + (size_t)set * (bitmap_bytes / 4);
+    sc.z_bitmaps = (uint32_t *)T.bitmaps.p + (size_t)(set ^ 1) * (bitmap_bytes / 4);
     sc.pm = (uint64_t *)T.pm.p;
     sc.wcnt = (uint32_t *)T.wstate.p;
     sc.wsrc = sc.wcnt + (W + 1);
@@ -1108,8 +1135,8 @@ static int match_locked(kb_ctx *ctx, const kb_events_dev *d, int out_mode, kb_re
     // the host after a table rebuild, a reallocation, a failed call, or when the geometry of the bitmaps changed.
     if (!T.scratch_clean || T.scratch_groups != G || T.scratch_large != max_large || T.scratch_bm_words != bm_words) {
         KB_CUDA(ctx, cudaMemsetAsync(T.gstate.p, 0, gstate_words * 4, ctx->stream));
-        KB_CUDA(ctx, cudaMemsetAsync(T.galloc.p, 0xFF, (size_t)(G + 1) * 8, ctx->stream));
-        KB_CUDA(ctx, cudaMemsetAsync(T.bitmaps.p, 0, bitmap_bytes, ctx->stream));
+        KB_CUDA(ctx, cudaMemsetAsync(T.galloc.p, 0xFF, (size_t)2 * (G + 1) * 8, ctx->stream));
+        KB_CUDA(ctx, cudaMemsetAsync(T.bitmaps.p, 0, 2 * bitmap_bytes, ctx->stream));
         T.fan_gen = 0;
         T.scratch_groups = G;
         T.scratch_large = max_large;
@@ -1159,6 +1186,7 @@ static int match_locked(kb_ctx *ctx, const kb_events_dev *d, int out_mode, kb_re
         KB_LAUNCH(ctx, "k_fanout", ev_bytes + (uint64_t)E * NL * 12 + (uint64_t)E * 16 + (uint64_t)W * 44,
                   (k_fanout<<<(unsigned)T.fan_grid, FAN_THREADS, 0, ctx->stream>>>(ev, tb, sc)));
         T.fan_gen += 3;  // three grid barriers per launch
+        T.fan_set ^= 1;  // the next call uses the other set of group state and clears this one
     } else {
         // no events or no watchers: every list is empty
         cudaMemsetAsync(T.wstart.p, 0, (size_t)(W + 2) * 8, ctx->stream);
