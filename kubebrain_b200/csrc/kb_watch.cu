@@ -618,7 +618,11 @@ k_fanout(EvDev ev, TabDev tb, FanScratch sc)
 {
     // phase timestamps of CTA 0 (profiling: kb_prof_read reports them as fan:P1 .. fan:finish when profiling is on)
     const bool stamp = blockIdx.x == 0 && threadIdx.x == 0;
-    const uint64_t t_begin = stamp ? fan_now_ns() : 0;
+    uint64_t t_begin = 0;
+    if (threadIdx.x == 0) {  // when did the LAST CTA of the grid get its SM? (ctl words 8..9 as one u64, zeroed at the end)
+        t_begin = fan_now_ns();
+        atomicMax((unsigned long long *)&sc.ctl[8], (unsigned long long)t_begin);
+    }
     uint64_t t_p[4] = {0, 0, 0, 0};
     __shared__ uint32_t bm[BM_WORDS];
     __shared__ uint32_t wsum[33];
@@ -663,7 +667,7 @@ k_fanout(EvDev ev, TabDev tb, FanScratch sc)
         sc.h_pub[4] = t_p[1] - t_p[0];    // P2 + barrier
         sc.h_pub[5] = t_p[2] - t_p[1];    // P3 + barrier
         sc.h_pub[6] = t_p[3] - t_p[2];    // P4 of this CTA
-        sc.h_pub[7] = t_begin;            // start: the finishing CTA turns it into the kernel's span
+        sc.h_pub[7] = __ldcg((const unsigned long long *)&sc.ctl[8]) - t_begin;  // start of the last CTA - start of CTA 0
     }
     // P5: the last CTA to get here finishes alone; the end of the kernel is the barrier for what follows
     __syncthreads();
@@ -1217,8 +1221,8 @@ static int match_locked(kb_ctx *ctx, const kb_events_dev *d, int out_mode, kb_re
     D = ctx->h_wpub[1];
     T.d_hint = D;
     if (ctx->prof_on && run) {  // phase spans of CTA 0 (ns -> ms), as pseudo kernels "fan:*"
-        static const char *names[4] = {"fan:P1_match", "fan:P2_scatter", "fan:P3_sort", "fan:P4_watchers"};
-        for (int i = 0; i < 4; i++) {
+        static const char *names[5] = {"fan:P1_match", "fan:P2_scatter", "fan:P3_sort", "fan:P4_watchers", "fan:last_cta_start"};
+        for (int i = 0; i < 5; i++) {
             ProfEntry &pe = ctx->prof[prof_index(ctx, names[i])];
             pe.launches++;
             pe.ms += (double)ctx->h_wpub[3 + i] * 1e-6;
