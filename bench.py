@@ -323,8 +323,10 @@ def workload_config(world: int, wl):
         "events_per_gpu": int(wl["events"].n), "read_rev": int(wl["meta"].read_rev),
         "parallelism": f"hash-shard x{world}" if world > 1 else "single GPU",
         "l2": "inputs larger than L2 (>= 0.7 GB streamed from HBM per step)",
-        "overlap": "scan and fan-out run concurrently on two kb_ctx of the same GPU; device-resident answers are "
-                   "stream ordered, so a batch's copy into the arena overlaps the next batch's decode",
+        "overlap": "scan and fan-out run concurrently on two kb_ctx of the same GPU, K batches and K bursts per timed region, "
+                   "each half on its own host thread; range batches are submitted ahead (kb_range_submit / kb_range_collect, "
+                   "`pipeline.range_batches_in_flight` on the B200 line), so one batch's host round trip and first kernels "
+                   "overlap the previous batch's kernels",
         "unit_of_work": "records examined + events matched",
     }
 
@@ -381,7 +383,7 @@ def run_b200(args, rank: int, local_rank: int, world: int):
     import threading
 
     jobs_q, done_q = queue.SimpleQueue(), queue.SimpleQueue()
-    pyt = {"cursor": 0.0, "range_call": 0.0, "range_result": 0.0, "fan_call": 0.0, "n": 0}
+    pyt = {"cursor": 0.0, "range_call": 0.0, "range_submit": 0.0, "range_collect": 0.0, "range_result": 0.0, "fan_call": 0.0, "n": 0}
 
     def worker():
         torch.cuda.set_device(local_rank)
@@ -464,19 +466,68 @@ def run_b200(args, rank: int, local_rank: int, world: int):
         (ex, nbytes, checksum), dbytes = both(scan_e2e, fan_e2e)
         return ex, nbytes + dbytes, checksum
 
+    # Batches in flight (default 2): batch n+1 is submitted (bound search, layout, launches) before batch n is collected,
+    # the way the shim serves concurrent scanner.Range goroutines; every step is still one whole batch, and all K batches
+    # are submitted, answered and drained inside the timed region.  The fan-out bursts run on their own thread, K of them
+    # in the same region (the reference's watcher hub is an independent goroutine, it does not wait for scans).
+    def scan_pipelined(steps, e2e):
+        mode = KB_OUT_HOST if e2e else KB_OUT_DEVICE
+        out = None
+        pend = []
+
+        def finish(pd):
+            t2 = time.perf_counter()
+            r = pd.collect()
+            t3 = time.perf_counter()
+            ex = int(r.req_examined.sum())
+            if e2e:
+                nbytes = r.n_bytes + r.n_kvs * 36
+                checksum = int(r.arena[:: max(1, r.n_bytes // 4096)].sum()) if r.n_bytes else 0  # the host reads the result
+                o = (ex, nbytes, checksum)
+            else:
+                o = (ex, r.n_kvs)
+            r.close()
+            pyt["range_collect"] += t3 - t2
+            pyt["range_result"] += time.perf_counter() - t3
+            return o
+
+        for _ in range(steps):
+            t1 = time.perf_counter()
+            pend.append(eng.range_submit(reqs, mode))
+            pyt["range_submit"] += time.perf_counter() - t1
+            pyt["n"] += 1
+            if len(pend) >= args.in_flight:
+                out = finish(pend.pop(0))
+        while pend:
+            out = finish(pend.pop(0))
+        return out
+
+    def run_steps(steps, e2e):
+        """K steps; returns what the last step of each half returned"""
+        if args.serial or args.in_flight <= 1:
+            out = None
+            for _ in range(steps):
+                out = step_e2e() if e2e else step_device()
+            return out
+        fan = fan_e2e if e2e else fan_device
+        jobs_q.put(lambda: [fan() for _ in range(steps)][-1])
+        sc = scan_pipelined(steps, e2e)
+        f = done_q.get()
+        if isinstance(f, Exception):
+            raise f
+        return (sc[0], sc[1], f) if not e2e else (sc[0], sc[1] + f, sc[2])
+
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
+    def timed(e2e, steps):
         barrier()
         a, b, bw = (torch.cuda.Event(enable_timing=True) for _ in range(3))
         a.record(stream)
         t0 = time.perf_counter()
-        out = None
-        for _ in range(steps):
-            out = fn()
+        out = run_steps(steps, e2e)
         # device-resident answers return while their last copy is still running on the context's copy stream:
         # drain both contexts before the end events so that the timed region holds ALL the work of the K steps
         eng.sync()
@@ -498,9 +549,9 @@ def run_b200(args, rank: int, local_rank: int, world: int):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    for _ in range(max(args.warmup, 3)):
-        step_device()
-        step_e2e()
+    n_warm = max(args.warmup, 3, args.in_flight + 1)  # every lane of the range pipeline allocates its scratch on first use
+    run_steps(n_warm, False)
+    run_steps(n_warm, True)
 
     # timed region: CUDA events bracket only the two HBM-bound kernels (level 2) so the event records do not
     # perturb the step; a second, untimed pass with every kernel bracketed fills the per-kernel table
@@ -511,7 +562,7 @@ def run_b200(args, rank: int, local_rank: int, world: int):
     l0 = sum(e.launch_count() for e in engines)
     for k in list(pyt):
         pyt[k] = 0
-    dev_ms, wall_s, (examined, n_kvs, deliveries) = timed(step_device, args.steps)
+    dev_ms, wall_s, (examined, n_kvs, deliveries) = timed(False, args.steps)
     host_call_us = {k: 1e6 * v / max(pyt["n"], 1) for k, v in pyt.items() if k != "n"}
     launches = sum(e.launch_count() for e in engines) - l0
     prof_major = {}
@@ -520,7 +571,7 @@ def run_b200(args, rank: int, local_rank: int, world: int):
         prof_major.update({p["name"]: p for p in e.prof_read()})
         e.prof_reset()
         e.prof_enable(1)
-    prof_ms, _, _ = timed(step_device, args.steps)
+    prof_ms, _, _ = timed(False, args.steps)
     prof = []
     for e in engines:
         e.prof_enable(0)
@@ -528,7 +579,7 @@ def run_b200(args, rank: int, local_rank: int, world: int):
     for p in prof:  # the timed-region measurement wins for the kernels it covers
         if p["name"] in prof_major:
             p.update(prof_major[p["name"]])
-    e2e_ms, e2e_wall, (examined2, d2h_bytes, _) = timed(step_e2e, args.steps)
+    e2e_ms, e2e_wall, (examined2, d2h_bytes, _) = timed(True, args.steps)
     clocks = sampler.stop() if rank == 0 else None
     # the cursor exchange on its own, both transports (the timed loop uses the peer-memory kernel when peers map)
     cursor_us = {}
@@ -599,6 +650,8 @@ def run_b200(args, rank: int, local_rank: int, world: int):
             "metric": METRIC, "value": value, "unit": "events/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.mode,
             "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": workload_config(world, wl),
+            "pipeline": {"range_batches_in_flight": 1 if args.serial else max(1, args.in_flight),
+                         "halves": "joined at every step" if (args.serial or args.in_flight <= 1) else "independent threads, K steps each"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "events/s", "h2d_bytes_per_step": int(h2d_bytes),
                     "d2h_bytes_per_step": int(d2h_bytes), "ms_per_step": e2e_ms / args.steps},
@@ -1010,6 +1063,9 @@ def main():
     ap.add_argument("--prefetch", dest="no_prefetch", action="store_false", default=True,
                     help="submit the next step's bound search ahead (kb_range_prefetch).  Off by default: measured, it moves the "
                          "next decode under the previous gather and both HBM-bound kernels slow each other down (0.38 vs 0.33 ms)")
+    ap.add_argument("--in-flight", type=int, default=2,
+                    help="range batches in flight (kb_range_submit / kb_range_collect); 1 = one kb_range_batch per step, "
+                         "joined with the fan-out burst at every step (the round-1 loop)")
     ap.add_argument("--small-compaction", action="store_true", help="extra: config 4 at 1/10 size instead of 100M records")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -203,10 +203,23 @@ func (s *b200Scanner) rangeOnce(start, end []byte, revision uint64, limit int64,
 	req.read_rev, req.limit = C.uint64_t(revision), C.int64_t(limit)
 	var res *C.kb_result
 	var view C.kb_range_view
+	// Two critical sections instead of one kb_range_batch: between them another goroutine's Range can submit, so two
+	// scans are in flight on the device (the second one's bound search and layout overlap the first one's kernels; a
+	// third submission first reads back the first one's rows).  The bound keys are only read by the submission.
+	var pend *C.kb_pending
 	s.e.mu.Lock()
-	defer s.e.mu.Unlock()
-	if rc := C.kb_range_batch(s.e.ctx, &req, 1, mode, &res); rc != 0 {
-		return nil, view, s.e.err(rc) // KB_ECOMPACTED carries the reference's message (scanner.go:620-623)
+	rc := C.kb_range_submit(s.e.ctx, &req, 1, mode, &pend)
+	err := s.e.err(rc) // KB_ECOMPACTED carries the reference's message (scanner.go:620-623)
+	s.e.mu.Unlock()
+	if err != nil {
+		return nil, view, err
+	}
+	s.e.mu.Lock()
+	rc = C.kb_range_collect(s.e.ctx, pend, &res) // ends the pending on success and on failure
+	err = s.e.err(rc)
+	s.e.mu.Unlock()
+	if err != nil {
+		return nil, view, err
 	}
 	C.kb_range_view_get(res, &view)
 	return res, view, nil

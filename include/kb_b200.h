@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define KB_ABI_VERSION 2  /* 2: kb_write_op.expire_unix, kb_expire, kb_range_prefetch, kb_cursor_transport / _force_nccl */
+#define KB_ABI_VERSION 2  /* 2: kb_write_op.expire_unix, kb_expire, kb_range_prefetch, kb_range_submit / _collect, kb_cursor_transport / _force_nccl */
 
 typedef enum kb_status {
     KB_OK = 0,
@@ -156,6 +156,17 @@ int kb_range_batch(kb_ctx *ctx, const kb_range_req *reqs, uint64_t n_req, int ou
  * snapshot; anything else is ignored).  A caller with a queue of pending requests submits batch n+1 before it waits for
  * batch n; the one host round trip of a range call then overlaps the previous batch's kernels. */
 int kb_range_prefetch(kb_ctx *ctx, const kb_range_req *reqs, uint64_t n_req);
+/* A range call in two halves (kb_range_batch == submit + collect): kb_range_submit lays the batch out and launches its
+ * kernels, kb_range_collect waits for its rows and builds the result (host copies for KB_OUT_HOST happen here).  A caller
+ * with a queue of batches (the shim under concurrent scanner.Range goroutines) submits batch n+1 before it collects batch
+ * n: n+1's bound search, layout and first kernels then overlap n's kernels.  Two batches are in flight at most; a third
+ * submission first waits for the rows of the batch two back.  Collect in any order; every pending ends in exactly one of
+ * kb_range_collect (also on failure) or kb_pending_free.  Any other entry point may be called in between (it first
+ * reads back the rows of what is in flight). */
+typedef struct kb_pending kb_pending;
+int kb_range_submit(kb_ctx *ctx, const kb_range_req *reqs, uint64_t n_req, int out_mode, kb_pending **out);
+int kb_range_collect(kb_ctx *ctx, kb_pending *pending, kb_result **out);
+void kb_pending_free(kb_ctx *ctx, kb_pending *pending);
 int kb_range_view_get(const kb_result *res, kb_range_view *view);
 /* Completion of a KB_OUT_DEVICE range answer: cuda_stream (a cudaStream_t) is made to wait for it on the device;
  * with cuda_stream == NULL the calling host thread blocks until it is complete.  No-op for host-resident results. */

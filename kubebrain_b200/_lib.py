@@ -33,7 +33,7 @@ KB_OP_PUT, KB_OP_DEL = 0, 1
 ABI_SYMBOLS = [
     "kb_abi_version", "kb_open", "kb_close", "kb_last_error", "kb_stream", "kb_sync",
     "kb_load_sorted", "kb_store_info", "kb_dump", "kb_restore", "kb_apply_batch", "kb_expire", "kb_set_compact_revision",
-    "kb_range_batch", "kb_range_prefetch", "kb_range_view_get", "kb_result_wait", "kb_wire_range_head", "kb_wire_range_tail", "kb_wire_watch_head",
+    "kb_range_batch", "kb_range_prefetch", "kb_range_submit", "kb_range_collect", "kb_pending_free", "kb_range_view_get", "kb_result_wait", "kb_wire_range_head", "kb_wire_range_tail", "kb_wire_watch_head",
     "kb_get_batch", "kb_get_view_get",
     "kb_compact_sweep", "kb_compact_view_get",
     "kb_watch_add", "kb_watch_del", "kb_watch_count", "kb_watch_match", "kb_events_upload", "kb_events_free",
@@ -41,6 +41,32 @@ ABI_SYMBOLS = [
     "kb_nccl_unique_id", "kb_nccl_init", "kb_cursor_allgather", "kb_cursor_transport", "kb_cursor_force_nccl",
     "kb_prof_enable", "kb_prof_reset", "kb_prof_read", "kb_launch_count",
 ]
+
+
+class PendingRange:
+    """a submitted range batch (kb_pending): collect() exactly once, or close() to give it up"""
+
+    def __init__(self, eng, handle, keepalive):
+        self._eng, self._h, self._keep = eng, handle, keepalive
+
+    def collect(self) -> "RangeResult":
+        if self._h is None:
+            raise KbError(KB_ESTATE, "pending batch already collected")
+        h, self._h = self._h, None
+        r = C.c_void_p()
+        self._eng._check(lib().kb_range_collect(self._eng._ctx, h, C.byref(r)))  # the C side ends the pending either way
+        return RangeResult(self._eng, r)
+
+    def close(self):
+        if self._h is not None and self._eng._ctx:
+            lib().kb_pending_free(self._eng._ctx, self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class KbError(RuntimeError):
@@ -164,6 +190,12 @@ def lib():
     L.kb_range_batch.argtypes = [vp, C.POINTER(KbRangeReq), C.c_uint64, C.c_int, C.POINTER(vp)]
     L.kb_range_prefetch.restype = C.c_int
     L.kb_range_prefetch.argtypes = [vp, C.POINTER(KbRangeReq), C.c_uint64]
+    L.kb_range_submit.restype = C.c_int
+    L.kb_range_submit.argtypes = [vp, C.POINTER(KbRangeReq), C.c_uint64, C.c_int, C.POINTER(vp)]
+    L.kb_range_collect.restype = C.c_int
+    L.kb_range_collect.argtypes = [vp, vp, C.POINTER(vp)]
+    L.kb_pending_free.restype = None
+    L.kb_pending_free.argtypes = [vp, vp]
     L.kb_range_view_get.restype = C.c_int
     L.kb_range_view_get.argtypes = [vp, C.POINTER(KbRangeView)]
     L.kb_result_wait.restype = C.c_int
@@ -510,6 +542,14 @@ class Engine:
         h = C.c_void_p()
         self._check(lib().kb_range_batch(self._ctx, pk.arr, pk.n, out_mode, C.byref(h)))
         return RangeResult(self, h)
+
+    def range_submit(self, reqs, out_mode: int = KB_OUT_HOST) -> "PendingRange":
+        """first half of range_batch: the batch is laid out and its kernels launched; .collect() returns the RangeResult.
+        Submit batch n+1 before collecting batch n to keep two batches in flight (kb_range_submit / kb_range_collect)."""
+        pk = reqs if isinstance(reqs, PackedRangeReqs) else PackedRangeReqs(reqs)
+        h = C.c_void_p()
+        self._check(lib().kb_range_submit(self._ctx, pk.arr, pk.n, out_mode, C.byref(h)))
+        return PendingRange(self, h, pk)
 
     def range_prefetch(self, reqs):
         """start the bound search of a batch that a later range_batch(reqs) will ask for (kb_range_prefetch)"""

@@ -116,6 +116,7 @@ void pool_put_arena(kb_ctx *ctx, DBuf b)
 
 int ctx_quiesce(kb_ctx *ctx)
 {
+    KB_TRY(kb_pending_harvest_all(ctx));  // submitted range batches: their kernels are done once their rows are back
     if (ctx->stream_g) KB_CUDA(ctx, cudaStreamSynchronize(ctx->stream_g));
     if (ctx->stream2) KB_CUDA(ctx, cudaStreamSynchronize(ctx->stream2));  // a prefetched bound search may still read the slabs
     return KB_OK;
@@ -252,22 +253,78 @@ extern "C" int kb_open(int device_ordinal, const kb_config *cfg, kb_ctx **out)
     }
     kb_ctx *ctx = new kb_ctx();
     ctx->device = device_ordinal;
-    int prio_lo = 0, prio_hi = 0;
+    int prio_lo = 0, prio_hi = 0, prio_lane = 0;
     if (cudaSetDevice(device_ordinal) != cudaSuccess ||
-        cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi) != cudaSuccess ||
-        cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, high ? prio_hi : prio_lo) != cudaSuccess ||
+        cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi) != cudaSuccess)
+        prio_lo = prio_hi = 0;
+    // three levels when the device has them (numerically lower = more urgent): bound search > lane streams (short kernels of a
+    // batch) > bulk kernels (decode by launch attribute, gather / wire copy by their stream)
+    static const bool split = !(getenv("KB_PRIO_SPLIT") && atoi(getenv("KB_PRIO_SPLIT")) == 0);
+    prio_lane = (split && prio_lo - prio_hi >= 2) ? prio_lo - 1 : prio_lo;
+    ctx->prio_bulk = prio_lo;
+    ctx->prio_split = prio_lane != prio_lo;
+    if (
+        cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, high ? prio_hi : prio_lane) != cudaSuccess ||
         // the bound search is tiny and the host waits for it: always ahead of everything; the copy stream (gather / wire
         // copy) is throughput work that the next batch's short kernels should not queue behind: always behind
         cudaStreamCreateWithPriority(&ctx->stream2, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
         cudaStreamCreateWithPriority(&ctx->stream_g, cudaStreamNonBlocking, prio_lo) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_jobs, cudaEventDisableTiming) != cudaSuccess ||
+        // second lane of range batches (kb_range_submit) and the stream of the device -> host answer copies
+        cudaStreamCreateWithPriority(&ctx->stream_h, cudaStreamNonBlocking, prio_lo) != cudaSuccess ||
+        // work counters of both lanes + the error flag: zeroed once, before any stream can touch them
+        cudaMalloc(&ctx->d_ctrs.p, 1024) != cudaSuccess || cudaMemset(ctx->d_ctrs.p, 0, 1024) != cudaSuccess ||
+        cudaDeviceSynchronize() != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_gather[0], cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_gather[1], cudaEventDisableTiming) != cudaSuccess) {
         delete ctx;
         return KB_ECUDA;
     }
+    ctx->d_ctrs.cap = 1024;
+    // the other lanes of range batches (kb_range_submit): KB_LANES batches in flight at most
+    ctx->n_lanes = getenv("KB_LANES") ? std::min(std::max(atoi(getenv("KB_LANES")), 1), KB_MAX_LANES) : 3;
+    ctx->ctr_base = 64;
+    for (int l = 1; l < ctx->n_lanes; l++) {
+        ScanLane &a = ctx->parked[l - 1];
+        a.id = l;
+        a.ctr_base = 64 + 16 * l;
+        if (cudaStreamCreateWithPriority(&a.stream, cudaStreamNonBlocking, high ? prio_hi : prio_lane) != cudaSuccess ||
+            cudaEventCreateWithFlags(&a.ev_jobs, cudaEventDisableTiming) != cudaSuccess) {
+            delete ctx;
+            return KB_ECUDA;
+        }
+    }
     *out = ctx;
     return KB_OK;
+}
+
+// exchange the current lane's fields with the other lane's (the enqueued work holds raw pointers, not these fields)
+void lane_swap(kb_ctx *ctx)
+{
+    if (ctx->n_lanes < 2) return;
+    ScanLane &a = ctx->parked[ctx->park_next];
+    ctx->park_next = (ctx->park_next + 1) % (ctx->n_lanes - 1);
+    std::swap(ctx->stream, a.stream);
+    std::swap(ctx->ev_jobs, a.ev_jobs);
+    std::swap(ctx->h_rout, a.h_rout);
+    std::swap(ctx->h_rout_cap, a.h_rout_cap);
+    std::swap(ctx->rout_epoch, a.rout_epoch);
+    std::swap(ctx->d_bounds, a.d_bounds);
+    std::swap(ctx->d_bres, a.d_bres);
+    std::swap(ctx->d_reqs, a.d_reqs);
+    std::swap(ctx->d_tiles, a.d_tiles);
+    std::swap(ctx->d_meta, a.d_meta);
+    std::swap(ctx->d_tgt, a.d_tgt);
+    std::swap(ctx->d_tcnt, a.d_tcnt);
+    std::swap(ctx->d_tscan, a.d_tscan);
+    std::swap(ctx->d_reqout, a.d_reqout);
+    std::swap(ctx->d_sel, a.d_sel);
+    std::swap(ctx->d_slot, a.d_slot);
+    std::swap(ctx->h_stage, a.h_stage);
+    std::swap(ctx->h_stage2, a.h_stage2);
+    std::swap(ctx->search_pub, a.search_pub);
+    std::swap(ctx->ctr_base, a.ctr_base);
+    std::swap(ctx->lane, a.id);
 }
 
 static void dfree(DBuf &b)
@@ -281,10 +338,25 @@ extern "C" void kb_close(kb_ctx *ctx)
 {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
+    kb_pending_drop_all(ctx);
     cudaStreamSynchronize(ctx->stream);
+    for (auto &a : ctx->parked)
+        if (a.stream) cudaStreamSynchronize(a.stream);
     if (ctx->stream_g) cudaStreamSynchronize(ctx->stream_g);
     if (ctx->stream2) cudaStreamSynchronize(ctx->stream2);
+    if (ctx->stream_h) cudaStreamSynchronize(ctx->stream_h);
     watch_tables_free(ctx);
+    for (auto &a : ctx->parked) {  // (d_tiles aliases d_reqs)
+        DBuf *lane[] = {&a.d_bounds, &a.d_bres, &a.d_reqs, &a.d_meta, &a.d_tgt, &a.d_tcnt, &a.d_tscan, &a.d_reqout, &a.d_sel, &a.d_slot};
+        for (DBuf *b : lane) dfree(*b);
+        if (a.h_stage.p) cudaFreeHost(a.h_stage.p);
+        if (a.h_stage2.p) cudaFreeHost(a.h_stage2.p);
+        if (a.h_rout) cudaFreeHost(a.h_rout);
+        if (a.search_pub.host) cudaFreeHost(a.search_pub.host);
+        if (a.ev_jobs) cudaEventDestroy(a.ev_jobs);
+        if (a.stream) cudaStreamDestroy(a.stream);
+    }
+    if (ctx->stream_h) cudaStreamDestroy(ctx->stream_h);
     DBuf *all[] = {&ctx->d_kslab, &ctx->d_koff16, &ctx->d_klen, &ctx->d_vslab, &ctx->d_voff16, &ctx->d_vlen, &ctx->d_dir,
                    &ctx->d_bounds, &ctx->d_bres, &ctx->d_reqs,
                    &ctx->d_meta, &ctx->d_tgt, &ctx->d_agg, &ctx->d_tcnt, &ctx->d_tscan, &ctx->d_reqout,
@@ -340,7 +412,10 @@ extern "C" int kb_sync(kb_ctx *ctx)
     if (!ctx) return KB_EINVAL;
     std::lock_guard<std::mutex> g(ctx->mu);
     KB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (auto &a : ctx->parked)
+        if (a.stream) KB_CUDA(ctx, cudaStreamSynchronize(a.stream));
     if (ctx->stream_g) KB_CUDA(ctx, cudaStreamSynchronize(ctx->stream_g));
+    if (ctx->stream_h) KB_CUDA(ctx, cudaStreamSynchronize(ctx->stream_h));
     return KB_OK;
 }
 

@@ -232,7 +232,10 @@ __device__ __forceinline__ BlockTile make_block(uint32_t b, const DecGeom &g, co
 }
 
 template <int MAXW, int KK>
-__global__ void __launch_bounds__(MAXW * 32, 1)
+// Register budget: the decode CTA shares its SM with the fan-out context's persistent CTA (384 threads x 64) and with the
+// short kernels of other range batches in flight (256 threads x 32); at 96 registers x 12 warps they did not fit together
+// and waited for each other.  The long-key variant (K = 1) is the one that runs beside them.
+__global__ void __maxnreg__((KK == 1 || MAXW > 16) ? 80 : 128)
 k_decode_lcp(StoreDev st, const TileDev *__restrict__ tiles, DecGeom g, ScanMode mode, uint32_t *__restrict__ meta,
              unsigned int *__restrict__ work_ctr, unsigned int *__restrict__ err_flag)
 {

@@ -158,6 +158,31 @@ struct Watcher {
 
 struct WatchTablesDev;  // kb_watch.cu
 
+struct SearchPubBuf {  // mapped pinned: [flag u64 | pad to 64 bytes | results u32 x nb], written by k_search
+    uint8_t *host = nullptr;
+    size_t cap = 0;
+    uint64_t epoch = 0;
+};
+
+// The per-batch state of a range call.  kb_ctx holds the CURRENT lane's fields directly (every entry point works on
+// them); kb_range_submit leaves its batch in flight and exchanges them with a parked lane's, so that the next batch is laid out and
+// launched on another stream / scratch set while the earlier ones' kernels run (lane_swap rotates through `parked`).
+struct ScanLane {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_jobs = nullptr;
+    uint8_t *h_rout = nullptr;
+    size_t h_rout_cap = 0;
+    uint64_t rout_epoch = 0;
+    DBuf d_bounds, d_bres, d_reqs, d_tiles, d_meta, d_tgt, d_tcnt, d_tscan, d_reqout, d_sel, d_slot;
+    HBuf h_stage, h_stage2;
+    SearchPubBuf search_pub;
+    uint32_t ctr_base = 0;   // this lane's work counters inside d_ctrs
+    int id = 0;
+};
+constexpr int KB_MAX_LANES = 4;
+
+struct kb_pending;  // a submitted range batch (kb_scan.cu)
+
 struct kb_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -168,6 +193,14 @@ struct kb_ctx {
     cudaStream_t stream_g = nullptr;
     cudaEvent_t ev_jobs = nullptr, ev_gather[2] = {nullptr, nullptr};
     uint64_t batch_seq = 0;
+    ScanLane parked[KB_MAX_LANES - 1];            // the other lanes (kb_range_submit rotates through them)
+    int n_lanes = 2, park_next = 0;
+    int lane = 0;                                 // which lane the context's own fields are right now
+    uint32_t ctr_base = 0;                        // the current lane's work counters inside d_ctrs
+    kb_pending *lane_pending[KB_MAX_LANES] = {nullptr, nullptr, nullptr, nullptr};  // submitted, rows not yet read back, per lane
+    int prio_bulk = 0;                            // priority of the bulk kernels (decode, gather): the lowest
+    bool prio_split = false;                      // the lane streams run above prio_bulk
+    cudaStream_t stream_h = nullptr;              // device -> host copies of KB_OUT_HOST answers (behind the gather's event)
     // per-request results (ReqOut) published by the device into mapped pinned memory: [flag u64 | pad to 64 | rows]
     uint8_t *h_rout = nullptr;
     size_t   h_rout_cap = 0;
@@ -202,11 +235,7 @@ struct kb_ctx {
     HBuf h_stage, h_stage2;
 
     // kb_range_prefetch: bound searches started ahead of the kb_range_batch that will use them (two in flight at most)
-    struct SearchPubBuf {  // mapped pinned: [flag u64 | pad to 64 bytes | results u32 x nb], written by k_search
-        uint8_t *host = nullptr;
-        size_t cap = 0;
-        uint64_t epoch = 0;
-    };
+    typedef ::SearchPubBuf SearchPubBuf;
     SearchPubBuf search_pub;  // of the search a range call runs itself
     struct SearchSlot {
         HBuf stage;
@@ -302,8 +331,12 @@ int hbuf_ensure(kb_ctx *ctx, HBuf &b, size_t bytes);
 int pool_get_dev(kb_ctx *ctx, size_t bytes, DBuf *out);
 int pool_get_arena(kb_ctx *ctx, size_t bytes, DBuf *out);
 void pool_put_arena(kb_ctx *ctx, DBuf b);
-// wait for the gather stream: every entry point other than kb_range_batch starts with it
+// read back the rows of every submitted range batch, then wait for the gather stream: every entry point other than the
+// range calls starts with it
 int ctx_quiesce(kb_ctx *ctx);
+int kb_pending_harvest_all(kb_ctx *ctx);  // kb_scan.cu
+void kb_pending_drop_all(kb_ctx *ctx);
+void lane_swap(kb_ctx *ctx);
 int pool_get_host(kb_ctx *ctx, size_t bytes, HBuf *out);
 void pool_put_dev(kb_ctx *ctx, DBuf b);
 void pool_put_host(kb_ctx *ctx, HBuf b);

@@ -23,6 +23,7 @@
 //   k_gather / k_wire_copy [SG] bulk-TMA copy of the winners' key+value into the response arena (padded pairs, or
 //                 etcd protobuf elements); overlaps the next batch's k_decode_lcp .. k_place
 #include <algorithm>
+#include <memory>
 
 #include "kb_internal.cuh"
 #include "kb_decode.cuh"
@@ -286,7 +287,7 @@ __device__ __forceinline__ LM lookback_lm(TileState *ts, uint32_t t, uint32_t t0
 }
 
 template <bool COMPACT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 8)  // <= 32 registers: must fit beside the persistent CTAs of other batches
 k_emit(StoreDev st, const ReqDev *__restrict__ reqs, const TileDev *__restrict__ tiles, const uint32_t *__restrict__ meta,
        TileState *__restrict__ ts, unsigned int *__restrict__ ticket, uint32_t *__restrict__ tgt,
        uint32_t *__restrict__ tail_tgt, uint64_t *__restrict__ tcnt, int wire, unsigned int *__restrict__ decode_ctr)
@@ -479,7 +480,7 @@ struct __align__(16) ChunkState {
     uint32_t pad[3];
 };
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 8)  // <= 32 registers: must fit beside the persistent CTAs of other batches
 k_tile_scan(const uint64_t *__restrict__ tcnt, uint64_t *__restrict__ tscan, uint32_t ntiles, ChunkState *__restrict__ cs)
 {
     __shared__ uint64_t ws2[18];
@@ -563,7 +564,7 @@ k_req_totals(const ReqDev *__restrict__ reqs, uint32_t nreq, const uint64_t *__r
 // k_place: ordered selection (range) -- position = emissions before it in the request; the first `limit`
 // positions are kept (commonResultReceiver.needMore, receiver.go:82-87).
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 8)  // <= 32 registers: must fit beside the persistent CTAs of other batches
 k_place(StoreDev st, const ReqDev *__restrict__ reqs, const TileDev *__restrict__ tiles,
         const uint32_t *__restrict__ tgt, const uint32_t *__restrict__ tail_tgt,
         const uint64_t *__restrict__ tscan, uint32_t *__restrict__ sel, uint64_t *__restrict__ slot,
@@ -628,7 +629,7 @@ k_place(StoreDev st, const ReqDev *__restrict__ reqs, const TileDev *__restrict_
 }
 
 // ordered delete calls (compact): per record [superseded prev] [tombstone] [revision record] | [ttl]
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 8)  // <= 32 registers: must fit beside the persistent CTAs of other batches
 k_place_victims(const ReqDev *__restrict__ reqs, const TileDev *__restrict__ tiles,
                 const uint32_t *__restrict__ meta, const uint32_t *__restrict__ tgt,
                 const uint64_t *__restrict__ tscan, uint32_t *__restrict__ vidx, uint8_t *__restrict__ vcls)
@@ -768,7 +769,7 @@ __device__ __forceinline__ void mbar_wait_parity(uint64_t *bar, uint32_t parity,
 // [key][value] pair so that a typical kv is exactly one piece and two CTAs fit per SM.  Blocks of 32 jobs are handed
 // out through a global counter (zeroed by the kernel that builds the jobs), so a CTA that starts late -- the SM was
 // still busy with another stream's kernel -- simply takes fewer blocks.
-__global__ void __launch_bounds__(GATHER_WARPS * 32, 2)
+__global__ void __launch_bounds__(GATHER_WARPS * 32, 8)  // 32 registers: only lane 0 of a warp does more than fetch jobs
 k_gather(StoreDev st, const GatherJob *__restrict__ jobs, const uint64_t *__restrict__ n_kvs_dev,
          uint4 *__restrict__ arena, uint32_t piece, uint32_t stages, unsigned long long *__restrict__ work_ctr,
          unsigned int *__restrict__ err_flag)
@@ -1084,7 +1085,7 @@ __global__ void __launch_bounds__(256) k_publish_rout(const ReqOut *__restrict__
 
 // single CTA: per-request emitted count / response bytes (limit applied) and their exclusive prefixes over the
 // requests: job_first[q] = first kv of request q, arena_base[q] = first arena byte of request q; [nreq] = totals
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 8)  // <= 32 registers: must fit beside the persistent CTAs of other batches
 k_req_finalize(const ReqDev *__restrict__ reqs, uint32_t nreq, const ReqOut *__restrict__ rout,
                uint64_t *__restrict__ job_first, uint64_t *__restrict__ arena_base,
                unsigned long long *__restrict__ work_ctr, uint8_t *host_rout, uint64_t epoch,
@@ -1254,10 +1255,6 @@ int enqueue_search(kb_ctx *ctx, HBuf &stage, DBuf &d_bounds, DBuf &d_bres, uint6
         pb.cap = need * 2;
         pb.epoch = 0;
     }
-    if (!ctx->d_ctrs.p) {
-        KB_TRY(dbuf_ensure(ctx, ctx->d_ctrs, 256));
-        KB_CUDA(ctx, cudaMemsetAsync(ctx->d_ctrs.p, 0, 256, ss));
-    }
     KB_CUDA(ctx, cudaMemcpyAsync(d_bounds.p, hs, chunks * 16 + nb * 8, cudaMemcpyHostToDevice, ss));
     const uint32_t *d_boff = (const uint32_t *)((const uint8_t *)d_bounds.p + chunks * 16);
     const unsigned sgrid = (unsigned)((nb * 32 + 127) / 128);
@@ -1320,7 +1317,7 @@ int resolve_requests(kb_ctx *ctx, const kb_range_req *reqs, uint64_t nreq, bool 
         // batch's gather is still draining the host already learns the record intervals of this one.
         // (With every kernel bracketed by profiling events -- level 1 -- it stays on the main stream.)
         cudaStream_t ss = ctx->prof_on == 1 ? ctx->stream : ctx->stream2;
-        KB_TRY(enqueue_search(ctx, ctx->h_stage, ctx->d_bounds, ctx->d_bres, chunks, nb, ss, ctx->search_pub, 2));
+        KB_TRY(enqueue_search(ctx, ctx->h_stage, ctx->d_bounds, ctx->d_bres, chunks, nb, ss, ctx->search_pub, 2 + ctx->lane));
         if (tseg) kb_seg(ctx, "host:range_search_enqueue", *tseg);
         KB_TRY(search_wait(ctx, ctx->search_pub, ss));
         hres = (const uint32_t *)(ctx->search_pub.host + 64);
@@ -1390,9 +1387,24 @@ static int launch_decode_t(kb_ctx *ctx, const DecGeom &g, size_t smem, uint64_t 
         attr_smem = 227 * 1024 - 2048;
     }
     const uint32_t grid = std::min<uint32_t>((g.n_blocks + g.warps - 1) / g.warps, 148);
-    unsigned int *ctrs = (unsigned int *)ctx->d_ctrs.p;
+    unsigned int *ctrs = (unsigned int *)ctx->d_ctrs.p;  // work counter of this lane, error flag shared
+    // The decode CTA needs (nearly) all of an SM's shared memory, so its grid cannot be distributed while a gather of another
+    // batch is resident; at the stream's priority it would sit at the head of the block scheduler's queue and hold back
+    // every short kernel of the other lane behind it.  It is launched at the lowest priority instead (the lane streams
+    // run above it), so only the bulk kernels wait for each other.
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(g.warps * 32);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributePriority;
+    attr[0].val.priority = ctx->prio_bulk;
+    cfg.attrs = attr;
+    cfg.numAttrs = ctx->prio_split ? 1 : 0;
     KB_LAUNCH(ctx, "k_decode_lcp", alg_bytes,
-              (k_decode_lcp<MAXW, KK><<<grid, g.warps * 32, smem, ctx->stream>>>(ctx->st, d_tiles, g, mode, d_meta, ctrs, ctrs + 8)));
+              (cudaLaunchKernelEx(&cfg, k_decode_lcp<MAXW, KK>, ctx->st, d_tiles, g, mode, d_meta, ctrs + ctx->ctr_base, ctrs + 8)));
     return KB_OK;
 }
 
@@ -1429,8 +1441,9 @@ static int launch_gather(kb_ctx *ctx, cudaStream_t strm, const GatherJob *d_jobs
                                           (int)(GATHER_WARPS * GATHER_WARP_CHUNKS * 16)));
         ctx->gather_attr_set = true;
     }
+    static const unsigned per_sm = getenv("KB_GATHER_CTAS") ? (unsigned)std::max(1, atoi(getenv("KB_GATHER_CTAS"))) : 2;  // experiment knob
     const unsigned ggrid =
-        (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((n_jobs + GATHER_WARPS * 32 - 1) / (GATHER_WARPS * 32), 2 * 148));
+        (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((n_jobs + GATHER_WARPS * 32 - 1) / (GATHER_WARPS * 32), per_sm * 148));
     KB_LAUNCH_S(ctx, strm, "k_gather", alg_bytes,
                 (k_gather<<<ggrid, GATHER_WARPS * 32, gsmem, strm>>>(ctx->st, d_jobs, d_njobs, arena, piece, stages, d_ctr,
                                                                      (unsigned int *)ctx->d_ctrs.p + 8)));
@@ -1456,10 +1469,6 @@ static int launch_scan_core(kb_ctx *ctx, const Resolved &R, const ScanMode &mode
     uint64_t *d_tcnt = (uint64_t *)ctx->d_tcnt.p, *d_tscan = d_tcnt + (size_t)std::max<uint32_t>(nt, 1) * 2;
     ReqOut *d_rout = (ReqOut *)ctx->d_reqout.p;
     const uint64_t kbytes = scan_alg_bytes(ctx, R.n_records);
-    if (!ctx->d_ctrs.p) {  // work counters [0..7] + error flag [8]: zero once, every consumer leaves the counters at zero
-        KB_TRY(dbuf_ensure(ctx, ctx->d_ctrs, 256));
-        KB_CUDA(ctx, cudaMemsetAsync(ctx->d_ctrs.p, 0, 256, ctx->stream));
-    }
     if (nt) {
         // the ticket and the look-back states start empty
         KB_CUDA(ctx, cudaMemsetAsync(ctx->d_tscan.p, 0, 64 + (size_t)nchunks * sizeof(ChunkState) + (size_t)nt * sizeof(TileState),
@@ -1468,11 +1477,11 @@ static int launch_scan_core(kb_ctx *ctx, const Resolved &R, const ScanMode &mode
         if (mode.compact) {
             KB_LAUNCH(ctx, "k_emit_compact", R.n_records * 8,
                       (k_emit<true><<<nt, 256, 0, ctx->stream>>>(ctx->st, d_reqs, d_tiles, d_meta, d_ts, d_ticket, d_tgt, d_tail,
-                                                                d_tcnt, 0, (unsigned int *)ctx->d_ctrs.p)));
+                                                                d_tcnt, 0, (unsigned int *)ctx->d_ctrs.p + ctx->ctr_base)));
         } else {
             KB_LAUNCH(ctx, "k_emit", R.n_records * 8,
                       (k_emit<false><<<nt, 256, 0, ctx->stream>>>(ctx->st, d_reqs, d_tiles, d_meta, d_ts, d_ticket, d_tgt, d_tail,
-                                                                 d_tcnt, mode.wire, (unsigned int *)ctx->d_ctrs.p)));
+                                                                 d_tcnt, mode.wire, (unsigned int *)ctx->d_ctrs.p + ctx->ctr_base)));
         }
         KB_LAUNCH(ctx, "k_tile_scan", (uint64_t)nt * 32,
                   (k_tile_scan<<<nchunks, 256, 0, ctx->stream>>>(d_tcnt, d_tscan, nt, d_cs)));
@@ -1584,23 +1593,44 @@ static int rout_map_ensure(kb_ctx *ctx, uint64_t nreq)
 
 // wait until the device has published the rows of `epoch`; the stream is only consulted now and then, to notice a
 // failed launch or kernel instead of spinning forever
-static int rout_wait(kb_ctx *ctx, uint64_t epoch)
+static int rout_wait(kb_ctx *ctx, const uint8_t *h_rout, cudaStream_t strm, uint64_t epoch)
 {
-    volatile uint64_t *flag = (volatile uint64_t *)ctx->h_rout;
+    volatile const uint64_t *flag = (volatile const uint64_t *)h_rout;
     for (uint64_t spins = 1;; spins++) {
         if (*flag == epoch) return KB_OK;
         kb_cpu_relax();
         if ((spins & 0xFFFF) == 0) {
-            const cudaError_t q = cudaStreamQuery(ctx->stream);
+            const cudaError_t q = cudaStreamQuery(strm);
             if (q == cudaSuccess) return *flag == epoch ? KB_OK : kb_fail(ctx, KB_ECUDA, "range scan: results were not published");
             if (q != cudaErrorNotReady) return kb_cuda_fail(ctx, q, "range scan");
         }
     }
 }
 
-extern "C" int kb_range_batch(kb_ctx *ctx, const kb_range_req *reqs, uint64_t nreq, int out_mode, kb_result **out)
+// a range batch between its submission and the collection of its answer
+struct kb_pending {
+    int lane = 0;
+    Resolved R;
+    uint64_t nreq = 0;
+    int out_mode = 0, wire = 0;
+    bool want_kvs = false;
+    kb_result *res = nullptr;
+    DBuf d_om;
+    GatherOut go;
+    uint64_t *d_elem_off = nullptr;
+    uint64_t epoch = 0;
+    const uint8_t *h_rout = nullptr;  // the lane's mapped row buffer and stream at submission time
+    cudaStream_t stream = nullptr;
+    kb_tp t_submit;
+    std::vector<ReqOut> rout;         // rows, once read back
+    bool harvested = false;
+    int harvest_rc = KB_OK;
+};
+static int pending_harvest(kb_ctx *ctx, kb_pending *P);
+
+// first half of a range call: everything up to the launch of the last kernel; the batch is then in flight on the current lane
+static int range_submit_locked(kb_ctx *ctx, const kb_range_req *reqs, uint64_t nreq, int out_mode, kb_pending **out)
 {
-    if (!ctx || !out || (nreq && !reqs)) return KB_EINVAL;
     // wire modes: the arena holds etcd protobuf elements instead of padded [key][value] pairs (kb_wire.cuh)
     const int wire_flags = out_mode & (KB_WIRE_ETCD_KVS | KB_WIRE_ETCD_EVENTS);
     out_mode &= ~(KB_WIRE_ETCD_KVS | KB_WIRE_ETCD_EVENTS);
@@ -1608,9 +1638,10 @@ extern "C" int kb_range_batch(kb_ctx *ctx, const kb_range_req *reqs, uint64_t nr
     if (wire_flags == (KB_WIRE_ETCD_KVS | KB_WIRE_ETCD_EVENTS) || (wire_flags && out_mode == KB_OUT_COUNT)) return KB_EINVAL;
     const int wire = wire_flags == KB_WIRE_ETCD_KVS ? KB_WIRE_KVS_I : wire_flags == KB_WIRE_ETCD_EVENTS ? KB_WIRE_EVENTS_I : 0;
     *out = nullptr;
-    std::lock_guard<std::mutex> g(ctx->mu);
     if (!ctx->loaded) return kb_fail(ctx, KB_ESTATE, "no store loaded");
     cudaSetDevice(ctx->device);
+    // this lane's previous batch still owns the lane's host-visible buffers until its rows have been read back
+    if (ctx->lane_pending[ctx->lane]) KB_TRY(pending_harvest(ctx, ctx->lane_pending[ctx->lane]));
     for (uint64_t q = 0; q < nreq; q++) {
         // checkCompactRace (scanner.go:594-626)
         if (ctx->compact_present && ctx->compact_rev > reqs[q].read_rev)
@@ -1618,7 +1649,8 @@ extern "C" int kb_range_batch(kb_ctx *ctx, const kb_range_req *reqs, uint64_t nr
                            (unsigned long long)reqs[q].read_rev, (unsigned long long)ctx->compact_rev);
     }
     kb_tp tseg = kb_now();
-    Resolved R;
+    std::unique_ptr<kb_pending> P(new kb_pending());
+    Resolved &R = P->R;
     KB_TRY(resolve_requests(ctx, reqs, nreq, true, R, &tseg));
     kb_seg(ctx, "host:range_layout", tseg);
     bool probe_is_final = false;
@@ -1759,19 +1791,99 @@ extern "C" int kb_range_batch(kb_ctx *ctx, const kb_range_req *reqs, uint64_t nr
         }
         KB_CUDA(ctx, cudaEventRecord(res->done_ev, sg));
     }
-    std::vector<ReqOut> rout(std::max<uint64_t>(nreq, 1));
     if (!want_kvs && nreq) {  // count-only / empty answers: nothing ran k_req_finalize, publish the rows directly
         KB_LAUNCH(ctx, "k_publish_rout", nreq * 32,
                   (k_publish_rout<<<1, 256, 0, ctx->stream>>>(d_rout, (uint32_t)nreq, ctx->h_rout, epoch,
                                                               (const unsigned int *)ctx->d_ctrs.p + 8)));
     }
     kb_seg(ctx, "host:range_launch", tseg);
-    if (nreq) {
-        KB_TRY(rout_wait(ctx, epoch));
-        memcpy(rout.data(), ctx->h_rout + 64, nreq * sizeof(ReqOut));
-        if (*(volatile uint64_t *)(ctx->h_rout + 8) != 0)
-            return kb_fail(ctx, KB_ECUDA, "range scan: a bulk copy of the decode pass never completed");
+    guard.armed = false;
+    P->lane = ctx->lane;
+    P->nreq = nreq;
+    P->out_mode = out_mode;
+    P->wire = wire;
+    P->want_kvs = want_kvs;
+    P->res = res;
+    P->d_om = d_om;
+    P->go = go;
+    P->d_elem_off = d_elem_off;
+    P->epoch = epoch;
+    P->h_rout = ctx->h_rout;
+    P->stream = ctx->stream;
+    P->t_submit = tseg;
+    ctx->lane_pending[ctx->lane] = P.get();
+    *out = P.release();
+    return KB_OK;
+}
+
+// wait for the rows of a submitted batch and keep them with it: afterwards the lane's buffers are free again
+static int pending_harvest(kb_ctx *ctx, kb_pending *P)
+{
+    if (P->harvested) return P->harvest_rc;
+    P->harvested = true;
+    if (ctx->lane_pending[P->lane] == P) ctx->lane_pending[P->lane] = nullptr;
+    P->rout.resize(std::max<uint64_t>(P->nreq, 1));
+    if (P->nreq) {
+        P->harvest_rc = rout_wait(ctx, P->h_rout, P->stream, P->epoch);
+        if (P->harvest_rc != KB_OK) return P->harvest_rc;
+        memcpy(P->rout.data(), P->h_rout + 64, P->nreq * sizeof(ReqOut));
+        if (*(volatile uint64_t *)(P->h_rout + 8) != 0)
+            return P->harvest_rc = kb_fail(ctx, KB_ECUDA, "range scan: a bulk copy of the decode pass never completed");
     }
+    return KB_OK;
+}
+
+int kb_pending_harvest_all(kb_ctx *ctx)
+{
+    for (int l = 0; l < KB_MAX_LANES; l++)
+        if (ctx->lane_pending[l]) KB_TRY(pending_harvest(ctx, ctx->lane_pending[l]));
+    return KB_OK;
+}
+
+static void pending_drop(kb_ctx *ctx, kb_pending *P)
+{
+    if (ctx->lane_pending[P->lane] == P) ctx->lane_pending[P->lane] = nullptr;
+    pool_put_dev(ctx, P->d_om);
+    result_release_locked(ctx, P->res);
+    delete P;
+}
+
+void kb_pending_drop_all(kb_ctx *ctx)  // kb_close: batches nobody collected
+{
+    for (int l = 0; l < KB_MAX_LANES; l++)
+        if (kb_pending *P = ctx->lane_pending[l]) {
+            pending_harvest(ctx, P);
+            pending_drop(ctx, P);
+        }
+}
+
+// second half: rows -> the result's per-request arrays, host copies for KB_OUT_HOST
+static int range_collect_locked(kb_ctx *ctx, kb_pending *P, kb_result **out)
+{
+    *out = nullptr;
+    cudaSetDevice(ctx->device);
+    const uint64_t nreq = P->nreq;
+    const int out_mode = P->out_mode, wire = P->wire;
+    const bool want_kvs = P->want_kvs;
+    Resolved &R = P->R;
+    kb_result *res = P->res;
+    DBuf &d_om = P->d_om;
+    GatherOut &go = P->go;
+    uint64_t *d_elem_off = P->d_elem_off;
+    kb_tp tseg = kb_now();
+    struct Guard {  // every return below ends the batch: a failed one hands its buffers back
+        kb_ctx *ctx;
+        kb_pending *P;
+        bool armed = true;
+        ~Guard()
+        {
+            if (armed) pending_drop(ctx, P);
+        }
+    } guard{ctx, P};
+    int rc = pending_harvest(ctx, P);
+    if (rc != KB_OK) return rc;
+    std::vector<ReqOut> &rout = P->rout;
+    cudaStream_t sg = ctx->stream_g;
     kb_seg(ctx, "host:range_sync", tseg);
 
     res->req_first.resize(nreq + 1);
@@ -1813,13 +1925,17 @@ extern "C" int kb_range_batch(kb_ctx *ctx, const kb_range_req *reqs, uint64_t nr
                 const size_t cnt[7] = {nk, nk, nk, wire ? nk + 1 : 0, nk, nk, nk};
                 const size_t esz[7] = {8, 8, 8, 8, 4, 4, 4};
                 size_t off = 0;
+                // on the host-copy stream, behind this batch's gather: a later batch's gather (already queued on the copy
+                // stream when batches are submitted ahead) does not sit between the answer and the host
+                cudaStream_t sh = ctx->stream_h;
+                if (res->done_ev) cudaStreamWaitEvent(sh, res->done_ev, 0);
                 for (int i = 0; i < 7; i++) {
-                    if (cnt[i]) cudaMemcpyAsync(hm + off, srcs[i], cnt[i] * esz[i], cudaMemcpyDeviceToHost, sg);
+                    if (cnt[i]) cudaMemcpyAsync(hm + off, srcs[i], cnt[i] * esz[i], cudaMemcpyDeviceToHost, sh);
                     off += cnt[i] * esz[i];
                 }
-                cudaMemcpyAsync(res->h_bytes.p, res->d_bytes.p, nbytes, cudaMemcpyDeviceToHost, sg);
+                cudaMemcpyAsync(res->h_bytes.p, res->d_bytes.p, nbytes, cudaMemcpyDeviceToHost, sh);
             }
-            cudaError_t e = cudaStreamSynchronize(sg);  // behind the gather (which waited for the per-kv arrays)
+            cudaError_t e = cudaStreamSynchronize(ctx->stream_h);  // behind the gather (which waited for the per-kv arrays)
             kb_seg(ctx, "host:range_d2h", tseg);
             if (rc == KB_OK && e != cudaSuccess) rc = kb_cuda_fail(ctx, e, "range D2H");
             if (rc != KB_OK) return rc;
@@ -1856,8 +1972,50 @@ extern "C" int kb_range_batch(kb_ctx *ctx, const kb_range_req *reqs, uint64_t nr
     }
     guard.armed = false;
     *out = res;
+    delete P;
     kb_seg(ctx, "host:range_finish", tseg);
     return KB_OK;
+}
+
+extern "C" int kb_range_batch(kb_ctx *ctx, const kb_range_req *reqs, uint64_t nreq, int out_mode, kb_result **out)
+{
+    if (!ctx || !out || (nreq && !reqs)) return KB_EINVAL;
+    *out = nullptr;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    kb_pending *P = nullptr;
+    KB_TRY(range_submit_locked(ctx, reqs, nreq, out_mode, &P));
+    return range_collect_locked(ctx, P, out);
+}
+
+// The two halves on their own: a caller with a queue of batches submits batch n+1 before it collects batch n, so the
+// host's part of n+1 (bound search round trip, layout, launches) and its first kernels overlap the kernels of n.  Each
+// submission leaves its batch on the current lane and moves the context to the other one; two batches in flight at most
+// (a third submission first reads back the rows of the batch that last used its lane).
+extern "C" int kb_range_submit(kb_ctx *ctx, const kb_range_req *reqs, uint64_t nreq, int out_mode, kb_pending **out)
+{
+    if (!ctx || !out || (nreq && !reqs)) return KB_EINVAL;
+    *out = nullptr;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    KB_TRY(range_submit_locked(ctx, reqs, nreq, out_mode, out));
+    lane_swap(ctx);
+    return KB_OK;
+}
+
+extern "C" int kb_range_collect(kb_ctx *ctx, kb_pending *pending, kb_result **out)
+{
+    if (!ctx || !pending || !out) return KB_EINVAL;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    return range_collect_locked(ctx, pending, out);
+}
+
+// give up a submitted batch without reading its answer
+extern "C" void kb_pending_free(kb_ctx *ctx, kb_pending *pending)
+{
+    if (!ctx || !pending) return;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    cudaSetDevice(ctx->device);
+    pending_harvest(ctx, pending);  // its kernels must be done before its buffers go back to the pools
+    pending_drop(ctx, pending);
 }
 
 // Start the bound search of a batch that a later kb_range_batch will ask for (same bounds, same snapshot): a caller with a

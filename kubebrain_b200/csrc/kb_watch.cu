@@ -613,7 +613,7 @@ __device__ __forceinline__ uint64_t fan_now_ns()
     return t;
 }
 
-__global__ void __launch_bounds__(FAN_THREADS, 1)
+__global__ void __maxnreg__(64)  // 384 threads x 64 registers: leaves the scan context's decode CTA its 12 warps x 80 on the same SM
 k_fanout(EvDev ev, TabDev tb, FanScratch sc)
 {
     // phase timestamps of CTA 0 (profiling: kb_prof_read reports them as fan:P1 .. fan:finish when profiling is on)

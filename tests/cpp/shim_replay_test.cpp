@@ -142,19 +142,42 @@ struct Backend {  // just enough of pkg/backend/txn.go to produce the reference'
 };
 
 // ---- comparisons ---------------------------------------------------------------------------------------------------
-static void check_scan(const MiniEngine &e, const Bytes &prefix, uint64_t read_rev, int64_t limit)
+// b200Scanner.rangeOnce is two critical sections: kb_range_submit under the engine lock, then kb_range_collect under the
+// lock again -- another goroutine's submission may sit between them (two batches in flight on the device)
+struct ScanCall {
+    Bytes s, t;
+    uint64_t read_rev;
+    int64_t limit;
+    kb_pending *pend;
+};
+
+static ScanCall scan_submit(const Bytes &prefix, uint64_t read_rev, int64_t limit)
+{
+    ScanCall c;
+    Bytes end = prefix;
+    end.back()++;
+    c.s = ikey(prefix, 0);
+    c.t = ikey(end, 0);
+    c.read_rev = read_rev;
+    c.limit = limit;
+    c.pend = nullptr;
+    kb_range_req rq{(const uint8_t *)c.s.data(), c.s.size(), (const uint8_t *)c.t.data(), c.t.size(), read_rev, limit};
+    CHECK(kb_range_submit(ctx, &rq, 1, KB_OUT_HOST, &c.pend) == KB_OK);
+    CHECK(c.pend != nullptr);
+    return c;  // (the bound keys are only read during the submission: the Go slices are unpinned here)
+}
+
+static void scan_collect_check(const MiniEngine &e, ScanCall &c)
 {
     const Packed p = iterate(e);
     const ko_store st = p.view();
-    Bytes end = prefix;
-    end.back()++;
-    const Bytes s = ikey(prefix, 0), t = ikey(end, 0);
     ko_result exp;
     ko_result_init(&exp);
-    CHECK(ko_range(&st, (const uint8_t *)s.data(), s.size(), (const uint8_t *)t.data(), t.size(), read_rev, limit, 0, 0, &exp) == 0);
-    kb_range_req rq{(const uint8_t *)s.data(), s.size(), (const uint8_t *)t.data(), t.size(), read_rev, limit};
+    CHECK(ko_range(&st, (const uint8_t *)c.s.data(), c.s.size(), (const uint8_t *)c.t.data(), c.t.size(), c.read_rev, c.limit, 0, 0,
+                   &exp) == 0);
     kb_result *res = nullptr;
-    CHECK(kb_range_batch(ctx, &rq, 1, KB_OUT_HOST, &res) == KB_OK);
+    CHECK(kb_range_collect(ctx, c.pend, &res) == KB_OK);
+    c.pend = nullptr;
     kb_range_view v;
     CHECK(kb_range_view_get(res, &v) == KB_OK);
     CHECK(v.n_kvs == exp.n_emit);
@@ -173,6 +196,25 @@ static void check_scan(const MiniEngine &e, const Bytes &prefix, uint64_t read_r
     ko_result_free(&exp);
 }
 
+static void check_scan(const MiniEngine &e, const Bytes &prefix, uint64_t read_rev, int64_t limit)
+{
+    ScanCall c = scan_submit(prefix, read_rev, limit);
+    scan_collect_check(e, c);
+}
+
+// three goroutines in Range at once: submissions and collections interleave in lock-acquisition order
+static void check_concurrent_scans(const MiniEngine &e, uint64_t read_rev)
+{
+    ScanCall a = scan_submit("/registry/pods/", read_rev, 0);
+    ScanCall b = scan_submit("/registry/events/", read_rev, 3);
+    ScanCall c = scan_submit("/registry/", read_rev, 0);  // third submission: the first one's rows are read back first
+    scan_collect_check(e, b);
+    ScanCall d = scan_submit("/registry/pods/", read_rev, 2);
+    scan_collect_check(e, a);
+    scan_collect_check(e, d);
+    scan_collect_check(e, c);
+}
+
 static void check_store_equals(const MiniEngine &e)
 {
     uint64_t n = 0;
@@ -181,6 +223,7 @@ static void check_store_equals(const MiniEngine &e)
     check_scan(e, "/registry/", ~0ull >> 1, 0);
     check_scan(e, "/registry/", 1005, 0);
     check_scan(e, "/registry/pods/", ~0ull >> 1, 3);
+    check_concurrent_scans(e, ~0ull >> 1);
 }
 
 int main()

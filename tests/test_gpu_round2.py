@@ -15,7 +15,7 @@ import numpy as np
 import pytest
 
 from kubebrain_b200 import synth, wire
-from kubebrain_b200._lib import KB_OUT_COUNT, KB_OUT_HOST, Engine
+from kubebrain_b200._lib import KB_OUT_COUNT, KB_OUT_DEVICE, KB_OUT_HOST, Engine
 from kubebrain_b200.coder import NormalCoder, prefix_end
 from kubebrain_b200.packed import PackedStore
 from oracle import binding as ko
@@ -251,3 +251,76 @@ def test_decode_geometries(geom):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, env=env, cwd=root)
     assert out.returncode == 0 and "GEOM OK" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
+
+
+def _check_result(res, store, st, reqs):
+    for q, (s, e, rev, lim) in enumerate(reqs):
+        exp = ko.range_(st, s, e, rev, lim)
+        assert res.rec_indices(q).astype(np.uint64).tolist() == exp.emit.tolist(), (q, rev, lim)
+        assert int(res.req_count[q]) == exp.count and int(res.req_examined[q]) == exp.examined, q
+        assert res.kvs(q) == exp.kvs(store), (q, "kv bytes")
+
+
+def test_range_submit_collect(eng):
+    """kb_range_submit / kb_range_collect: batches in flight on the two lanes answer exactly like kb_range_batch, in any
+    collection order, with more submissions than lanes, with other entry points in between (a write sees the submitted
+    batches finish on the snapshot they were submitted on), and a pending that is given up frees its buffers"""
+    store, meta = synth.gen_store(6000, 4, 64, 90, 9, config_id=2, tomb_frac=0.1)
+    st = ko.OracleStore(store)
+    eng.load_sorted(store)
+    p = b"/registry/pods/ns-00002/"
+    a = [(LO, HI, meta.read_rev, 0), (CODER.encode_object_key(p, 0), CODER.encode_object_key(prefix_end(p), 0), meta.last_rev, 5)]
+    b = [(LO, HI, meta.last_rev, 7), (LO, HI, meta.first_rev, 0), (HI, HI, meta.last_rev, 0)]
+    c = [(LO, HI, meta.last_rev, 0)]
+    for mode in (KB_OUT_HOST, KB_OUT_DEVICE):
+        # in order, out of order, three submissions before the first collection
+        for order in ((0, 1, 2), (2, 0, 1), (1, 2, 0)):
+            batches = [a, b, c]
+            pend = [eng.range_submit(x, mode) for x in batches]
+            for i in order:
+                r = pend[i].collect()
+                if mode == KB_OUT_DEVICE:
+                    h = eng.range_batch(batches[i], KB_OUT_HOST)
+                    assert r.req_first.tolist() == h.req_first.tolist()
+                    assert r.req_count.tolist() == h.req_count.tolist() and r.req_examined.tolist() == h.req_examined.tolist()
+                    assert r.device_array("rec_idx", np.uint32).tolist() == h.rec_idx.tolist()
+                    assert r.device_array("rev", np.uint64).tolist() == h.rev.tolist()
+                    assert r.n_bytes == h.n_bytes
+                    assert eng.read_device(r.bytes_ptr, int(r.n_bytes), sync=False) == bytes(h.arena[: int(r.n_bytes)])
+                    h.close()
+                else:
+                    _check_result(r, store, st, batches[i])
+                r.close()
+    # the plain call between a submission and its collection
+    pa = eng.range_submit(a, KB_OUT_HOST)
+    check_ranges(eng, store, st, b)
+    pb = eng.range_submit(b, KB_OUT_HOST)
+    check_ranges(eng, store, st, c)
+    r = pb.collect(); _check_result(r, store, st, b); r.close()
+    r = pa.collect(); _check_result(r, store, st, a); r.close()
+    # a write between submission and collection: the submitted batches were answered on the old snapshot
+    pa = eng.range_submit(a, KB_OUT_HOST)
+    pc = eng.range_submit(c, KB_OUT_HOST)
+    k = store.keys[17]
+    eng.apply_batch([(k, None)])
+    r = pa.collect(); _check_result(r, store, st, a); r.close()
+    r = pc.collect(); _check_result(r, store, st, c); r.close()
+    items = dict(zip(store.keys.tolist(), store.vals.tolist()))
+    items.pop(k)
+    cur = PackedStore.from_items(list(items.items()))
+    cst = ko.OracleStore(cur)
+    pa = eng.range_submit(a, KB_OUT_HOST)
+    pgone = eng.range_submit(b, KB_OUT_DEVICE)
+    pgone.close()  # given up
+    with pytest.raises(Exception):
+        pgone.collect()
+    r = pa.collect(); _check_result(r, cur, cst, a); r.close()
+    # many rounds with two in flight
+    prev = eng.range_submit(a, KB_OUT_HOST)
+    for i in range(20):
+        nxt = eng.range_submit(a if i % 2 else c, KB_OUT_HOST)
+        r = prev.collect()
+        _check_result(r, cur, cst, c if i % 2 else a)
+        r.close()
+        prev = nxt
+    prev.collect().close()
