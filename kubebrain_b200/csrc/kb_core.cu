@@ -416,6 +416,7 @@ extern "C" int kb_sync(kb_ctx *ctx)
         if (a.stream) KB_CUDA(ctx, cudaStreamSynchronize(a.stream));
     if (ctx->stream_g) KB_CUDA(ctx, cudaStreamSynchronize(ctx->stream_g));
     if (ctx->stream_h) KB_CUDA(ctx, cudaStreamSynchronize(ctx->stream_h));
+    if (ctx->stream2) KB_CUDA(ctx, cudaStreamSynchronize(ctx->stream2));  // the delivery lists of the last watch match
     return KB_OK;
 }
 

@@ -55,6 +55,11 @@ struct WatchTablesDev {
     uint32_t fan_gen = 0;         // value of the grid-barrier generation word after the last launch
     uint32_t fan_set = 0;         // which of the two sets of group state the next k_fanout uses
     int fan_grid = 0;             // co-resident CTAs of k_fanout on this device (0: not queried yet)
+    // The delivery lists are written by k_expand_write on the context's second stream, so the write of burst n overlaps
+    // k_fanout of burst n+1: what the write reads (sorted segments, running max, per-watcher state, offsets, total) exists
+    // twice, `wr_set` alternates.  ev_fan: end of the last k_fanout; ev_write[s]: end of the last write that read set s.
+    uint32_t wr_set = 0;
+    cudaEvent_t ev_fan = nullptr, ev_write[2] = {nullptr, nullptr};
 };
 
 namespace {
@@ -936,6 +941,9 @@ void watch_tables_free(kb_ctx *ctx)
     if (!ctx->wt) return;
     WatchTablesDev &T = *ctx->wt;
     if (T.arena.p) cudaFree(T.arena.p);  // every other buffer is a view into it
+    if (T.ev_fan) cudaEventDestroy(T.ev_fan);
+    for (auto e : T.ev_write)
+        if (e) cudaEventDestroy(e);
     delete ctx->wt;
     ctx->wt = nullptr;
     if (ctx->ev_scratch) {
@@ -1045,7 +1053,10 @@ static int wpub_wait(kb_ctx *ctx, uint64_t epoch)
 static int match_locked(kb_ctx *ctx, const kb_events_dev *d, int out_mode, kb_result **out)
 {
     kb_tp tseg = kb_now();
-    if (ctx->watch_dirty || !ctx->wt) KB_TRY(rebuild_tables(ctx));
+    if (ctx->watch_dirty || !ctx->wt) {
+        KB_CUDA(ctx, cudaStreamSynchronize(ctx->stream2));  // the previous burst's write still reads the tables
+        KB_TRY(rebuild_tables(ctx));
+    }
     WatchTablesDev &T = *ctx->wt;
     if (d->stride < needed_stride(ctx))
         return kb_fail(ctx, KB_ESTATE, "event slab was uploaded for shorter watcher prefixes (stride %u < %u); upload again",
@@ -1062,15 +1073,18 @@ static int match_locked(kb_ctx *ctx, const kb_events_dev *d, int out_mode, kb_re
     const size_t bitmap_bytes = std::max<size_t>((size_t)max_large * bm_words * 4, 16);
     // per-call scratch behind the tables (one arena, see WatchTablesDev); a layout change voids the "clean" state
     // (group state -- gcnt | gfill, galloc, bitmaps -- twice: the sets alternate between calls)
+    // (the last five exist twice -- see wr_set; each copy starts on an arena boundary)
+    const size_t one[5] = {arena_align(seg_cap * 4), arena_align(std::max<size_t>((size_t)E * 8, 16)), arena_align((size_t)(W + 1) * 16),
+                           arena_align((size_t)(W + 2) * 8), arena_align(16)};
     const size_t sizes[11] = {gstate_words * 4, (size_t)2 * (G + 1) * 8, 2 * bitmap_bytes, (size_t)(G + max_large + 2) * 4, seg_cap * 4,
-                              seg_cap * 4, seg_cap * 4, std::max<size_t>((size_t)E * 8, 16), (size_t)(W + 1) * 16,
-                              (size_t)(W + 2) * 8, 16};
+                              seg_cap * 4, 2 * one[0], 2 * one[1], 2 * one[2], 2 * one[3], 2 * one[4]};
     size_t scr = 0, sig = 1469598103934665603ull;
     for (size_t x : sizes) {
         scr += arena_align(std::max<size_t>(x, 16));
         sig = (sig ^ x) * 1099511628211ull;
     }
     if (T.tab_end + scr > T.arena.cap) {
+        KB_CUDA(ctx, cudaStreamSynchronize(ctx->stream2));
         T.scr_bytes = scr;
         KB_TRY(arena_reserve(ctx, T, T.tab_end + scr + 4096));
         KB_TRY(rebuild_tables(ctx));  // the tables moved with the arena
@@ -1120,16 +1134,17 @@ static int match_locked(kb_ctx *ctx, const kb_events_dev *d, int out_mode, kb_re
     sc.large_list = sc.med_list + G + 1;
     sc.ematch = (uint32_t *)T.ematch.p;
     sc.seg = (uint32_t *)T.seg.p;
-    sc.sorted = (uint32_t *)T.seg_sorted.p;
+    const uint32_t ws = T.wr_set & 1;  // the set this burst's write reads
+    sc.sorted = (uint32_t *)((uint8_t *)T.seg_sorted.p + ws * one[0]);
     sc.bitmaps = (uint32_t *)T.bitmaps.p + (size_t)set * (bitmap_bytes / 4);
     sc.z_bitmaps = (uint32_t *)T.bitmaps.p + (size_t)(set ^ 1) * (bitmap_bytes / 4);
-    sc.pm = (uint64_t *)T.pm.p;
-    sc.wcnt = (uint32_t *)T.wstate.p;
+    sc.pm = (uint64_t *)((uint8_t *)T.pm.p + ws * one[1]);
+    sc.wcnt = (uint32_t *)((uint8_t *)T.wstate.p + ws * one[2]);
     sc.wsrc = sc.wcnt + (W + 1);
     sc.wn = sc.wsrc + (W + 1);
     sc.wlo = sc.wn + (W + 1);
-    sc.wstart = (uint64_t *)T.wstart.p;
-    sc.total = (uint64_t *)T.total.p;
+    sc.wstart = (uint64_t *)((uint8_t *)T.wstart.p + ws * one[3]);
+    sc.total = (uint64_t *)((uint8_t *)T.total.p + ws * one[4]);
     sc.big_t = big_t;
     sc.max_large = max_large;
     sc.bm_words = bm_words;
@@ -1168,6 +1183,14 @@ static int match_locked(kb_ctx *ctx, const kb_events_dev *d, int out_mode, kb_re
         pool_put_dev(ctx, d_out);
         return rc;
     }
+    if (!T.ev_fan) {
+        cudaEventCreateWithFlags(&T.ev_fan, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&T.ev_write[0], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&T.ev_write[1], cudaEventDisableTiming);
+    }
+    cudaStream_t sw = ctx->stream2;  // the write stream
+    // this burst overwrites the set the write two bursts ago read
+    KB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, T.ev_write[ws], 0));
     const uint64_t wepoch = ++ctx->wpub_epoch;
     sc.o_start = (uint64_t *)d_out.p;
     sc.h_start = (uint64_t *)h_out.p;
@@ -1193,8 +1216,8 @@ static int match_locked(kb_ctx *ctx, const kb_events_dev *d, int out_mode, kb_re
         T.fan_set ^= 1;  // the next call uses the other set of group state and clears this one
     } else {
         // no events or no watchers: every list is empty
-        cudaMemsetAsync(T.wstart.p, 0, (size_t)(W + 2) * 8, ctx->stream);
-        cudaMemsetAsync(T.total.p, 0, 16, ctx->stream);
+        cudaMemsetAsync(sc.wstart, 0, (size_t)(W + 2) * 8, ctx->stream);
+        cudaMemsetAsync(sc.total, 0, 16, ctx->stream);
         cudaMemsetAsync(d_out.p, 0, (size_t)(W + 1) * 8, ctx->stream);
         memset(h_out.p, 0, (size_t)(W + 1) * 8);
         k_publish_total<<<1, 32, 0, ctx->stream>>>(sc.total, ctx->h_wpub, wepoch);
@@ -1202,11 +1225,14 @@ static int match_locked(kb_ctx *ctx, const kb_events_dev *d, int out_mode, kb_re
     auto launch_write = [&](uint32_t *o_idx, uint64_t capacity) {
         const unsigned wgrid = (unsigned)std::max<uint64_t>(std::min<uint64_t>((capacity + 255) / 256, 148 * 16),
                                                             std::min<uint64_t>(((uint64_t)W * 32 + 255) / 256, 148 * 16));
-        KB_LAUNCH(ctx, "k_expand_write", capacity * 8,
-                  (k_expand_write<<<wgrid, 256, 0, ctx->stream>>>(W, tb.wminrev, sc.wsrc, sc.wn, sc.wlo, sc.sorted, sc.pm, sc.total,
-                                                                 sc.wstart, capacity, o_idx)));
+        KB_LAUNCH_S(ctx, sw, "k_expand_write", capacity * 8,
+                    (k_expand_write<<<wgrid, 256, 0, sw>>>(W, tb.wminrev, sc.wsrc, sc.wn, sc.wlo, sc.sorted, sc.pm, sc.total,
+                                                          sc.wstart, capacity, o_idx)));
     };
+    cudaEventRecord(T.ev_fan, ctx->stream);
+    cudaStreamWaitEvent(sw, T.ev_fan, 0);
     if (run) launch_write((uint32_t *)((uint64_t *)d_out.p + W + 1), cap);
+    T.wr_set ^= 1;
     // the total (and the offsets) are published in front of the write kernel: a device-resident answer returns on the flag
     // while the delivery lists are still being written (they are valid in stream order)
     kb_seg(ctx, "host:match_launch", tseg);
@@ -1238,17 +1264,18 @@ static int match_locked(kb_ctx *ctx, const kb_events_dev *d, int out_mode, kb_re
             pool_put_host(ctx, h_out);
             return rc;
         }
-        cudaMemcpyAsync(d_out.p, sc.wstart, (size_t)(W + 1) * 8, cudaMemcpyDeviceToDevice, ctx->stream);
+        cudaMemcpyAsync(d_out.p, sc.wstart, (size_t)(W + 1) * 8, cudaMemcpyDeviceToDevice, sw);
         launch_write((uint32_t *)((uint64_t *)d_out.p + W + 1), cap);
     }
+    cudaEventRecord(T.ev_write[ws], sw);  // the set may be overwritten (and the answer read) once this has fired
     T.scratch_clean = run;  // everything was enqueued: k_fanout restores the scratch before it ends
     if (out_mode == KB_OUT_HOST) {
         pool_put_host(ctx, h_out);
         h_out = HBuf();
         rc = pool_get_host(ctx, (size_t)(W + 1) * 8 + D * 4 + 16, &h_out);
         if (rc == KB_OK)
-            cudaMemcpyAsync(h_out.p, d_out.p, (size_t)(W + 1) * 8 + D * 4, cudaMemcpyDeviceToHost, ctx->stream);
-        cudaError_t e = cudaStreamSynchronize(ctx->stream);
+            cudaMemcpyAsync(h_out.p, d_out.p, (size_t)(W + 1) * 8 + D * 4, cudaMemcpyDeviceToHost, sw);
+        cudaError_t e = cudaStreamSynchronize(sw);
         kb_seg(ctx, "host:match_d2h", tseg);
         if (rc == KB_OK && e != cudaSuccess) rc = kb_cuda_fail(ctx, e, "watch match");
     }
@@ -1267,6 +1294,15 @@ static int match_locked(kb_ctx *ctx, const kb_events_dev *d, int out_mode, kb_re
     res->n_deliveries = D;
     res->h_match = h_out;
     res->d_match = d_out;
+    if (out_mode == KB_OUT_DEVICE) {  // the lists are complete when the write stream gets here (kb_result_wait, kb_sync)
+        if (!ctx->ev_pool.empty()) {
+            res->done_ev = ctx->ev_pool.back();
+            ctx->ev_pool.pop_back();
+        } else if (cudaEventCreate(&res->done_ev) != cudaSuccess) {
+            res->done_ev = nullptr;
+        }
+        if (res->done_ev) cudaEventRecord(res->done_ev, sw);
+    }
     *out = res;
     return KB_OK;
 }
