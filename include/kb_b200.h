@@ -56,7 +56,8 @@ int kb_abi_version(void);
 int kb_open(int device_ordinal, const kb_config *cfg, kb_ctx **out);
 void kb_close(kb_ctx *ctx);
 const char *kb_last_error(kb_ctx *ctx);
-/* the cudaStream_t every kernel of this ctx is launched on (so callers can record events on it) */
+/* the main cudaStream_t of this ctx (callers may record events on it).  Device-resident answers are completed on other
+ * streams of the context: order consumers with kb_result_wait, not with this stream. */
 void *kb_stream(kb_ctx *ctx);
 int kb_sync(kb_ctx *ctx);
 
@@ -168,7 +169,7 @@ int kb_range_submit(kb_ctx *ctx, const kb_range_req *reqs, uint64_t n_req, int o
 int kb_range_collect(kb_ctx *ctx, kb_pending *pending, kb_result **out);
 void kb_pending_free(kb_ctx *ctx, kb_pending *pending);
 int kb_range_view_get(const kb_result *res, kb_range_view *view);
-/* Completion of a KB_OUT_DEVICE range answer: cuda_stream (a cudaStream_t) is made to wait for it on the device;
+/* Completion of a KB_OUT_DEVICE answer (range arena and per-kv arrays; delivery lists of a watch match): cuda_stream (a cudaStream_t) is made to wait for it on the device;
  * with cuda_stream == NULL the calling host thread blocks until it is complete.  No-op for host-resident results. */
 int kb_result_wait(kb_ctx *ctx, const kb_result *res, void *cuda_stream);
 
@@ -250,7 +251,8 @@ typedef struct kb_match_view {
     const uint64_t *start;       /* n_watchers+1: deliveries of watcher id w = [start[w],start[w+1]) */
     const uint32_t *event_idx;   /* event indices, ascending per watcher (stream order)             */
     uint64_t n_deliveries;
-    int on_device;
+    int on_device;               /* 1: event_idx is a device pointer, complete after kb_result_wait / kb_sync (start[]
+                                    and n_deliveries are host values, final when the call returns)          */
 } kb_match_view;
 
 int kb_watch_match(kb_ctx *ctx, const kb_events *ev, int out_mode, kb_result **out);

@@ -427,12 +427,17 @@ class MatchResult:
         self.start = _np(v.start, self.n_watchers + 1, np.uint64).copy()
         self.event_idx = (_np(v.event_idx, self.n_deliveries, np.uint32).copy()
                           if not self.on_device else np.zeros(0, np.uint32))
-        # KB_OUT_DEVICE: the delivery lists stay in HBM and may still be being written when the call returns (they are
-        # valid in stream order on kb_stream(ctx); kb_sync before reading them from the host)
+        # KB_OUT_DEVICE: the delivery lists stay in HBM and may still be being written when the call returns (on the
+        # context's second stream): wait() / kb_sync before reading them
         self.event_idx_ptr = int(v.event_idx or 0) if self.on_device else 0
 
+    def wait(self, cuda_stream: int = 0):
+        """KB_OUT_DEVICE answers: order `cuda_stream` behind the delivery lists (0: block the host instead)"""
+        self._eng._check(lib().kb_result_wait(self._eng._ctx, self._h, C.c_void_p(cuda_stream or None)))
+
     def device_event_idx(self) -> np.ndarray:
-        raw = self._eng.read_device(self.event_idx_ptr, self.n_deliveries * 4)
+        self.wait()
+        raw = self._eng.read_device(self.event_idx_ptr, self.n_deliveries * 4, sync=False)
         return np.frombuffer(raw, dtype=np.uint32).copy()
 
     def deliveries(self, watcher_id: int) -> np.ndarray:
