@@ -601,6 +601,22 @@ def run_b200(args, rank: int, local_rank: int, world: int):
         cursor_us = {k: float(v) for k, v in zip(("p2p", "nccl"), t.tolist()) if v > 0}
     # parity of the very answers that were timed, on every rank (raises -> rc != 0)
     parity = None if args.no_parity else parity_check(eng, weng, wl, evh, reqs, rank, world, dist)
+    # the two bulk kernels with the GPU to themselves (untimed; CUDA events around each launch): inside the timed region their
+    # event brackets include the time they wait for SM residency behind the other lane's bulk kernel
+    alone = None
+    if rank == 0:
+        eng.sync()
+        weng.sync()
+        eng.prof_reset()
+        eng.prof_enable(2)
+        for _ in range(6):
+            r = eng.range_batch(reqs, KB_OUT_DEVICE)
+            r.wait()
+            r.close()
+            eng.sync()
+        eng.prof_enable(0)
+        alone = {p["name"]: p for p in eng.prof_read() if p["launches"]}
+        eng.prof_reset()
     if orig_affinity is not None:
         os.sched_setaffinity(0, orig_affinity)  # CPU legs below use every core the container has
 
@@ -646,6 +662,21 @@ def run_b200(args, rank: int, local_rank: int, world: int):
             # compares with a serialised ncu launch list is the one of the summed kernel time
             ksum = sum(k["avg_us"] * k["launches_per_step"] for k in kern)
             roof["share_of_kernel_time"] = dom["avg_us"] * dom["launches_per_step"] / ksum if ksum else None
+            # the same kernels with the GPU to themselves, and the step as a whole (all algorithmic bytes of a step over the
+            # step time): with batches in flight the event brackets of the bulk kernels overlap each other
+            roof["alone"] = {}
+            for name in ("k_gather", "k_decode_lcp"):
+                a = (alone or {}).get(name)
+                if a:
+                    us = 1e3 * a["total_ms"] / a["launches"]
+                    gbs = (a["alg_bytes"] / a["launches"] / 1e9) / (us / 1e6)
+                    roof["alone"][name] = {"avg_us": us, "achieved": gbs, "frac": gbs / peak}
+            step_bytes = sum(k["alg_bytes_per_launch"] * k["launches_per_step"] for k in kern)
+            roof["step"] = {"alg_bytes": step_bytes, "achieved": step_bytes / 1e9 / (ms_per_step / 1e3),
+                            "frac": step_bytes / 1e9 / (ms_per_step / 1e3) / peak}
+            roof["note"] = ("achieved / frac: CUDA events around the kernel inside the timed region (includes waiting for SM "
+                            "residency when another batch's bulk kernel holds the shared memory); alone: the same launch with the "
+                            "GPU to itself; step: all algorithmic bytes of a step over ms_per_step")
         line = {
             "metric": METRIC, "value": value, "unit": "events/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.mode,
