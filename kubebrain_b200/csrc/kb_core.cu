@@ -284,15 +284,11 @@ extern "C" int kb_open(int device_ordinal, const kb_config *cfg, kb_ctx **out)
     // the other lanes of range batches (kb_range_submit): KB_LANES batches in flight at most
     ctx->n_lanes = getenv("KB_LANES") ? std::min(std::max(atoi(getenv("KB_LANES")), 1), KB_MAX_LANES) : 3;
     ctx->ctr_base = 64;
-    for (int l = 1; l < ctx->n_lanes; l++) {
+    ctx->prio_lane = high ? prio_hi : prio_lane;
+    for (int l = 1; l < ctx->n_lanes; l++) {  // their streams are created when a submission first rotates onto them
         ScanLane &a = ctx->parked[l - 1];
         a.id = l;
         a.ctr_base = 64 + 16 * l;
-        if (cudaStreamCreateWithPriority(&a.stream, cudaStreamNonBlocking, high ? prio_hi : prio_lane) != cudaSuccess ||
-            cudaEventCreateWithFlags(&a.ev_jobs, cudaEventDisableTiming) != cudaSuccess) {
-            delete ctx;
-            return KB_ECUDA;
-        }
     }
     *out = ctx;
     return KB_OK;
@@ -303,6 +299,15 @@ void lane_swap(kb_ctx *ctx)
 {
     if (ctx->n_lanes < 2) return;
     ScanLane &a = ctx->parked[ctx->park_next];
+    if (!a.stream) {  // first use of this lane (a context that never submits ahead -- the watch context -- has one lane)
+        if (cudaStreamCreateWithPriority(&a.stream, cudaStreamNonBlocking, ctx->prio_lane) != cudaSuccess ||
+            cudaEventCreateWithFlags(&a.ev_jobs, cudaEventDisableTiming) != cudaSuccess) {
+            if (a.stream) cudaStreamDestroy(a.stream);
+            a.stream = nullptr;
+            cudaGetLastError();
+            return;  // stay on the current lane: the next submission first reads this lane's rows back
+        }
+    }
     ctx->park_next = (ctx->park_next + 1) % (ctx->n_lanes - 1);
     std::swap(ctx->stream, a.stream);
     std::swap(ctx->ev_jobs, a.ev_jobs);

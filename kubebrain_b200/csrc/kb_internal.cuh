@@ -198,6 +198,7 @@ struct kb_ctx {
     int lane = 0;                                 // which lane the context's own fields are right now
     uint32_t ctr_base = 0;                        // the current lane's work counters inside d_ctrs
     kb_pending *lane_pending[KB_MAX_LANES] = {nullptr, nullptr, nullptr, nullptr};  // submitted, rows not yet read back, per lane
+    int prio_lane = 0;                            // priority of the lane streams
     int prio_bulk = 0;                            // priority of the bulk kernels (decode, gather): the lowest
     bool prio_split = false;                      // the lane streams run above prio_bulk
     cudaStream_t stream_h = nullptr;              // device -> host copies of KB_OUT_HOST answers (behind the gather's event)
