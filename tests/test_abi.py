@@ -134,3 +134,19 @@ int main(void) {
                            "-L", libdir, "-lkbb200", "-Wl,-rpath," + libdir])
     out = subprocess.check_output([exe]).decode().strip()
     assert int(out) == _lib.lib().kb_abi_version()
+
+
+def test_entry_points_reject_null_arguments():
+    """argument checks come before any CUDA call: the range halves, the prefetch and the waits answer KB_EINVAL on NULL
+    handles (what the cgo shim's error path relies on); kb_pending_free / kb_result_free ignore NULL"""
+    L = _lib.lib()
+    h = ctypes.c_void_p()
+    req = (_lib.KbRangeReq * 1)()
+    assert L.kb_range_submit(None, req, 1, _lib.KB_OUT_HOST, ctypes.byref(h)) == _lib.KB_EINVAL
+    assert L.kb_range_collect(None, None, ctypes.byref(h)) == _lib.KB_EINVAL
+    assert L.kb_range_batch(None, req, 1, _lib.KB_OUT_HOST, ctypes.byref(h)) == _lib.KB_EINVAL
+    assert L.kb_range_prefetch(None, req, 1) == _lib.KB_EINVAL
+    assert L.kb_result_wait(None, None, None) == _lib.KB_EINVAL
+    L.kb_pending_free(None, None)
+    L.kb_result_free(None, None)
+    assert h.value is None
